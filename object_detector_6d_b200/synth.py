@@ -1,0 +1,374 @@
+"""Seeded synthetic inputs for the detection path: frames, encoder weights, Hough forests, option files.
+
+Nothing the reference needs at test time ships with it (no meshes, forest, weights or images -- SURVEY.md F4), so every
+benchmark/parity input is synthesised here, to the *contracts* the reference defines:
+
+* frames follow the PatchGen renderer's output contract (PatchGen/src/render_views_tesselated_sphere_mod.cpp:60-138):
+  8-bit colour on a white background, depth as uint16 millimetres with 0 = no surface, pinhole camera f = 575 px at
+  640x480, objects 0.6-1.2 m from the camera.  Procedural boxes / cylinders stand in for meshes/*.ply.
+* forests are written in the reference's on-disk format (HoughForest/src/HFBase.cpp:4-38, 110-145): forest.txt plus
+  pre-order treeN.dat files.  Split thresholds are drawn from a calibration batch of real encoder features, as the
+  trainer does (HoughForest/src/HFTrain.cpp:365-386), so descents are balanced.
+* encoder weights use the net's own fillers (generate_scripts.sh:448-456: gaussian std 1, sparse 40; zero bias).
+
+Pure numpy; no GPU, no oracle.
+"""
+from __future__ import annotations
+
+import os
+import struct
+from dataclasses import dataclass
+
+import numpy as np
+
+ENCODER_DIMS = (256, 1500, 1000, 800)  # generate_scripts.sh:424-524
+
+
+# --------------------------------------------------------------------------------------------------------- frames
+@dataclass
+class Camera:
+    W: int = 640
+    H: int = 480
+    fx: float = 575.0
+    fy: float = 575.0
+    cx: float = 319.5
+    cy: float = 239.5
+
+    @staticmethod
+    def scaled(s: int) -> "Camera":
+        """The 640x480 Xtion camera at s x resolution (s=2 is BASELINE config C4: 1280x960, f=1150)."""
+        return Camera(640 * s, 480 * s, 575.0 * s, 575.0 * s, 320.0 * s - 0.5, 240.0 * s - 0.5)
+
+
+def _rot_axis(axis, ang):
+    axis = np.asarray(axis, np.float64)
+    axis = axis / np.linalg.norm(axis)
+    K = np.array([[0, -axis[2], axis[1]], [axis[2], 0, -axis[0]], [-axis[1], axis[0], 0]])
+    return np.eye(3) + np.sin(ang) * K + (1 - np.cos(ang)) * (K @ K)
+
+
+def _texture(local, base, kind, freq):
+    """Procedural albedo from object-frame coordinates (metres)."""
+    if kind == 0:  # checker
+        s = np.floor(local[..., 0] * freq) + np.floor(local[..., 1] * freq) + np.floor(local[..., 2] * freq)
+        m = (np.mod(s, 2) * 0.55 + 0.45)[..., None]
+    elif kind == 1:  # stripes
+        m = (0.6 + 0.4 * np.sin(local[..., 1] * freq * 6.283))[..., None]
+    else:  # blobs
+        m = (0.65 + 0.35 * np.sin(local[..., 0] * freq * 5.1) * np.cos(local[..., 2] * freq * 4.3))[..., None]
+    return base[None, :] * m
+
+
+def render_frame(seed: int, cam: Camera = Camera(), n_objects: int = 6, table: bool = True):
+    """Ray-cast a cluttered table-top scene.  Returns (bgr uint8 [H,W,3], depth_mm uint16 [H,W])."""
+    rng = np.random.default_rng(seed)
+    H, W = cam.H, cam.W
+    v, u = np.mgrid[0:H, 0:W]
+    d = np.stack([(u - cam.cx) / cam.fx, (v - cam.cy) / cam.fy, np.ones((H, W))], -1).reshape(-1, 3)
+    N = d.shape[0]
+    tbest = np.full(N, np.inf)
+    color = np.full((N, 3), 255.0)  # white background (renderer .cpp:260)
+    light = np.array([0.3, -0.6, -0.74])
+    light /= np.linalg.norm(light)
+
+    # table plane: tilted away from the camera, ~0.7-1.2 m
+    n_pl = np.array([0.0, -0.6, -0.8])
+    n_pl /= np.linalg.norm(n_pl)
+    p0 = np.array([0.0, 0.1, 0.95])
+    if table:
+        denom = d @ n_pl
+        t = np.where(np.abs(denom) > 1e-9, (p0 @ n_pl) / denom, np.inf)
+        ok = (t > 0.3) & (t < 1.495)
+        hit = d * t[:, None]
+        tex = 120 + 60 * (np.mod(np.floor(hit[:, 0] * 12) + np.floor(hit[:, 2] * 12), 2))
+        tbest = np.where(ok, t, tbest)
+        color = np.where(ok[:, None], np.stack([tex * 0.8, tex * 0.9, tex], -1), color)
+
+    # plane frame for placing objects
+    ex = np.array([1.0, 0, 0])
+    ez = np.cross(ex, n_pl)
+    ez /= np.linalg.norm(ez)
+    for k in range(n_objects):
+        kind = int(rng.integers(0, 2))  # 0 box, 1 cylinder
+        size = rng.uniform(0.05, 0.2, 3)
+        if n_objects == 1:
+            centre = np.array([0.0, 0.0, 0.7])  # C1: one object, centred, 0.7 m
+            R = _rot_axis(rng.normal(size=3), rng.uniform(0, 6.283))
+        else:
+            a, b = rng.uniform(-0.33, 0.33), rng.uniform(-0.22, 0.22)
+            R = np.stack([ex, -n_pl, ez], 1) @ _rot_axis([0, 1, 0], rng.uniform(0, 6.283))
+            centre = p0 + a * ex + b * ez + n_pl * (size[1] * 0.5)
+        base = rng.uniform(40, 230, 3)
+        tkind, freq = int(rng.integers(0, 3)), rng.uniform(15, 60)
+        o = -(R.T @ centre)  # ray origin in object frame
+        dl = d @ R  # ray directions in object frame
+        if kind == 0:
+            hs = size * 0.5
+            with np.errstate(divide="ignore", invalid="ignore"):
+                t1 = (-hs - o) / dl
+                t2 = (hs - o) / dl
+            tn = np.minimum(t1, t2).max(1)
+            tf = np.maximum(t1, t2).min(1)
+            ok = (tn <= tf) & (tn > 0.05)
+            t = tn
+            pl = o + dl * t[:, None]
+            nl = np.zeros_like(pl)
+            ax = np.argmax(np.abs(pl) / hs, 1)
+            nl[np.arange(N), ax] = np.sign(pl[np.arange(N), ax])
+        else:
+            r, hh = size[0] * 0.5, size[1] * 0.5
+            A = dl[:, 0] ** 2 + dl[:, 2] ** 2
+            B = 2 * (o[0] * dl[:, 0] + o[2] * dl[:, 2])
+            C = o[0] ** 2 + o[2] ** 2 - r * r
+            disc = B * B - 4 * A * C
+            with np.errstate(divide="ignore", invalid="ignore"):
+                sq = np.sqrt(np.maximum(disc, 0))
+                ts = (-B - sq) / (2 * A)
+                ys = o[1] + dl[:, 1] * ts
+                side_ok = (disc > 0) & (np.abs(ys) <= hh) & (ts > 0.05)
+                tc = (-hh * np.sign(dl[:, 1]) - o[1]) / dl[:, 1]  # cap facing the ray
+                pc = o + dl * tc[:, None]
+                cap_ok = (pc[:, 0] ** 2 + pc[:, 2] ** 2 <= r * r) & (tc > 0.05)
+            t = np.where(side_ok, ts, np.inf)
+            t = np.where(cap_ok & (tc < t), tc, t)
+            ok = np.isfinite(t)
+            pl = o + dl * np.where(ok, t, 0)[:, None]
+            is_cap = cap_ok & (t == tc)
+            nl = np.stack([pl[:, 0], np.zeros(N), pl[:, 2]], 1) / r
+            nl[is_cap] = np.array([0, 1.0, 0]) * -np.sign(dl[is_cap, 1])[:, None]
+        ok &= t < tbest
+        nw = nl @ R.T
+        shade = np.clip(0.35 + 0.65 * np.maximum(nw @ (-light), 0), 0, 1)
+        col = np.clip(_texture(pl, base, tkind, freq) * shade[:, None], 0, 255)
+        tbest = np.where(ok, t, tbest)
+        color = np.where(ok[:, None], col, color)
+
+    depth = np.where(np.isfinite(tbest), np.rint(tbest * 1000.0), 0)  # z == t because d.z == 1
+    depth = np.clip(depth, 0, 65535).astype(np.uint16).reshape(H, W)
+    bgr = np.ascontiguousarray(np.clip(np.rint(color), 0, 255).astype(np.uint8).reshape(H, W, 3))
+    return bgr, depth
+
+
+# ------------------------------------------------------------------------------------------------ encoder weights
+def make_encoder_weights(seed: int, dims=ENCODER_DIMS):
+    """[(W [out,in] f32, b [out] f32)] x3 with the net's own fillers: gaussian std 1, `sparse: 40`, zero bias
+    (Caffe keeps a weight with probability sparse/num_output)."""
+    rng = np.random.default_rng(seed)
+    layers = []
+    for i in range(3):
+        n_in, n_out = dims[i], dims[i + 1]
+        Wm = rng.standard_normal((n_out, n_in)).astype(np.float32)
+        mask = rng.random((n_out, n_in)) < (40.0 / n_out)
+        Wm = np.where(mask, Wm, np.float32(0)).astype(np.float32)
+        layers.append((np.ascontiguousarray(Wm), np.zeros(n_out, np.float32)))
+    return layers
+
+
+def write_weights_raw(path: str, layers) -> None:
+    """Raw container: 'HF6DW001', int32 n_layers, then per layer int32 out, int32 in, W[out][in] f32, b[out] f32."""
+    with open(path, "wb") as f:
+        f.write(b"HF6DW001")
+        f.write(struct.pack("<i", len(layers)))
+        for Wm, b in layers:
+            f.write(struct.pack("<ii", Wm.shape[0], Wm.shape[1]))
+            f.write(np.ascontiguousarray(Wm, np.float32).tobytes())
+            f.write(np.ascontiguousarray(b, np.float32).tobytes())
+
+
+def _pb_varint(v: int) -> bytes:
+    out = bytearray()
+    while True:
+        b = v & 0x7F
+        v >>= 7
+        if v:
+            out.append(b | 0x80)
+        else:
+            out.append(b)
+            return bytes(out)
+
+
+def _pb_field(num: int, wt: int, payload: bytes) -> bytes:
+    if wt == 2:
+        return _pb_varint((num << 3) | 2) + _pb_varint(len(payload)) + payload
+    return _pb_varint((num << 3) | wt) + payload
+
+
+def write_caffemodel_v1(path: str, layers, names=("encode1", "encode2", "encode3")) -> None:
+    """Minimal V1 .caffemodel: NetParameter{name=1, layers=2{name=4, type=5(INNER_PRODUCT=14), blobs=6{num=1,
+    channels=2,height=3,width=4,data=5 packed}}} -- the subset the detector reads."""
+
+    def blob(arr, shape4):
+        p = b"".join(_pb_field(i + 1, 0, _pb_varint(s)) for i, s in enumerate(shape4))
+        p += _pb_field(5, 2, np.ascontiguousarray(arr, "<f4").tobytes())
+        return p
+
+    net = _pb_field(1, 2, b"PATCHAutoencoder")
+    for (Wm, b), nm in zip(layers, names):
+        lay = _pb_field(2, 2, b"data") + _pb_field(3, 2, nm.encode()) + _pb_field(4, 2, nm.encode())
+        lay += _pb_field(5, 0, _pb_varint(14))
+        lay += _pb_field(6, 2, blob(Wm, (1, 1, Wm.shape[0], Wm.shape[1])))
+        lay += _pb_field(6, 2, blob(b, (1, 1, 1, b.shape[0])))
+        net += _pb_field(2, 2, lay)
+    with open(path, "wb") as f:
+        f.write(net)
+
+
+# ----------------------------------------------------------------------------------------------------- forests
+def _build_tree(rng, feats, max_depth, min_samples, K, votes_per_leaf):
+    """Level-wise random tree over a calibration batch.  Returns dict of node arrays (index 0 = root)."""
+    N, F = feats.shape
+    is_leaf, mode, f1, f2, thr, left, right, depth_of = [], [], [], [], [], [], [], []
+
+    def new_nodes(n, d):
+        base = len(is_leaf)
+        is_leaf.extend([True] * n)
+        mode.extend([0] * n)
+        f1.extend([0] * n)
+        f2.extend([0] * n)
+        thr.extend([0.0] * n)
+        left.extend([-1] * n)
+        right.extend([-1] * n)
+        depth_of.extend([d] * n)
+        return base
+
+    new_nodes(1, 0)
+    node_of = np.zeros(N, np.int64)
+    active = np.array([0])
+    for d in range(max_depth):
+        if active.size == 0:
+            break
+        # samples per active node
+        order = np.argsort(node_of, kind="stable")
+        sorted_nodes = node_of[order]
+        starts = np.searchsorted(sorted_nodes, active, "left")
+        ends = np.searchsorted(sorted_nodes, active, "right")
+        counts = ends - starts
+        split = counts >= min_samples
+        nodes = active[split]
+        if nodes.size == 0:
+            break
+        s_, c_ = starts[split], counts[split]
+        m = rng.integers(0, 2, nodes.size)
+        a = rng.integers(0, F, nodes.size)
+        b = rng.integers(0, F, nodes.size)
+        pick = order[s_ + (rng.random(nodes.size) * c_).astype(np.int64)]
+        va = feats[pick, a]
+        vb = feats[pick, b]
+        th = np.where(m == 0, va - vb, va).astype(np.float32)
+        # nudge so the picked sample goes right and a non-trivial share goes left
+        base = new_nodes(2 * nodes.size, d + 1)
+        lch = base + 2 * np.arange(nodes.size)
+        for i, n in enumerate(nodes):
+            is_leaf[n] = False
+            mode[n], f1[n], f2[n], thr[n] = int(m[i]), int(a[i]), int(b[i]), float(th[i])
+            left[n], right[n] = int(lch[i]), int(lch[i] + 1)
+        # route samples
+        lut = np.full(len(is_leaf), -1, np.int64)
+        lut[nodes] = np.arange(nodes.size)
+        idx = lut[node_of]
+        sel = idx >= 0
+        ii = idx[sel]
+        smp = np.nonzero(sel)[0]
+        val = np.where(m[ii] == 0, feats[smp, a[ii]] - feats[smp, b[ii]], feats[smp, a[ii]]).astype(np.float32)
+        go_left = val < th[ii]
+        node_of[smp] = np.where(go_left, lch[ii], lch[ii] + 1)
+        active = np.concatenate([lch, lch + 1])
+    n_nodes = len(is_leaf)
+    is_leaf = np.array(is_leaf)
+    # leaf payloads
+    leaf_idx = np.nonzero(is_leaf)[0]
+    nl = leaf_idx.size
+    dom = rng.integers(0, K, nl)
+    p_dom = rng.uniform(0.5, 1.0, nl).astype(np.float32)
+    probs = np.zeros((nl, K), np.float32)
+    if K > 1:
+        rest = rng.random((nl, K)).astype(np.float32)
+        rest[np.arange(nl), dom] = 0
+        rest = rest / np.maximum(rest.sum(1, keepdims=True), 1e-9) * (1 - p_dom)[:, None]
+        probs = rest
+    probs[np.arange(nl), dom] = p_dom if K > 1 else 1.0
+    return dict(is_leaf=is_leaf, mode=np.array(mode, np.int32), f1=np.array(f1, np.int32), f2=np.array(f2, np.int32),
+                thr=np.array(thr, np.float32), left=np.array(left, np.int64), right=np.array(right, np.int64),
+                leaf_idx=leaf_idx, dom=dom, probs=probs, n_nodes=n_nodes, votes_per_leaf=votes_per_leaf)
+
+
+def _random_votes(rng, n):
+    v = np.empty((n, 6), np.float32)
+    v[:, 0] = rng.uniform(-np.pi, np.pi, n)  # yaw
+    v[:, 1] = rng.uniform(-np.pi / 2, np.pi / 2, n)  # pitch
+    v[:, 2] = rng.uniform(-np.pi, np.pi, n)  # roll
+    v[:, 3:] = rng.uniform(-0.1, 0.1, (n, 3))  # object-frame offset of the patch [m]
+    return v
+
+
+def _serialise_tree(rng, tree, K) -> bytes:
+    """Pre-order, left first (HFBase.cpp:4-38).  leaf_id values are a random permutation: the trainer numbers leaves
+    in hash-map order (HFTrain.cpp:167), not file order."""
+    out = bytearray()
+    leaf_pos = {int(n): i for i, n in enumerate(tree["leaf_idx"])}
+    ids = rng.permutation(len(leaf_pos)).astype(np.int32)
+    V = tree["votes_per_leaf"]
+    stack = [0]
+    is_leaf, mode, f1, f2, thr = tree["is_leaf"], tree["mode"], tree["f1"], tree["f2"], tree["thr"]
+    left, right = tree["left"], tree["right"]
+    file_order = 0
+    while stack:
+        n = stack.pop()
+        if is_leaf[n]:
+            li = leaf_pos[n]
+            out += struct.pack("<Bi", 1, int(ids[file_order]))
+            file_order += 1
+            out += tree["probs"][li].tobytes()
+            for c in range(K):
+                if c == tree["dom"][li]:
+                    nv = V
+                else:  # a few gated-out votes for minority classes, as a trained leaf has
+                    nv = int(rng.integers(0, 3)) if tree["probs"][li, c] > 0.1 else 0
+                out += struct.pack("<i", nv)
+                if nv:
+                    out += _random_votes(rng, nv).tobytes()
+        else:
+            out += struct.pack("<Biiif", 0, int(mode[n]), int(f1[n]), int(f2[n]), float(thr[n]))
+            stack.append(int(right[n]))
+            stack.append(int(left[n]))
+    return bytes(out)
+
+
+def write_forest(folder: str, calib_features: np.ndarray, T: int = 4, K: int = 6, max_depth: int = 20,
+                 votes_per_leaf: int = 16, seed: int = 7, min_samples: int = 2, patch_vox: int = 8,
+                 voxel_m: float = 0.005) -> dict:
+    """Write forest.txt + tree<t>.dat.  Returns summary statistics."""
+    os.makedirs(folder, exist_ok=True)
+    feats = np.ascontiguousarray(calib_features, np.float32)
+    F = feats.shape[1]
+    rng = np.random.default_rng(seed)
+    stats = dict(T=T, K=K, F=F, leaves=[], nodes=[])
+    for t in range(T):
+        tree = _build_tree(rng, feats, max_depth, min_samples, K, votes_per_leaf)
+        with open(os.path.join(folder, f"tree{t}.dat"), "wb") as f:
+            f.write(_serialise_tree(rng, tree, K))
+        stats["leaves"].append(int(tree["leaf_idx"].size))
+        stats["nodes"].append(int(tree["n_nodes"]))
+    with open(os.path.join(folder, "forest.txt"), "w") as f:
+        f.write(f"{T} {K} {F} {patch_vox} {voxel_m:g}\n")  # HFTrain.cpp:1225-1231
+    return stats
+
+
+# ------------------------------------------------------------------------------------------------ options file
+def write_options(path: str, forest_folder: str, weights_path: str, K: int, cam: Camera = Camera(), stride: int = 2,
+                  segmented: bool = True, definition: str = "patch_autoencoder_half.prototxt", extra: str = "") -> None:
+    """Text-format DetectorOptions.Options as generate_scripts.sh:541-572 emits it."""
+    lines = []
+    for k in range(K):
+        lines.append(f'object_options {{\n  name: "obj{k}"\n  mesh_file: "meshes/obj{k}.ply"\n  instances: 1\n'
+                     f"  nn_search_radius: 0.01\n  icp_iterations: 60\n  max_location_hypotheses: 12\n"
+                     f"  should_detect: true\n}}")
+    lines += [f'caffe_definition: "{definition}"', f'caffe_weights: "{weights_path}"',
+              f'forest_folder: "{forest_folder}"', "num_threads: 8", f"stride: {stride}",
+              "max_depth_range_in_patch_in_m: 0.25", "gpu: 0", "batch_size: 100", f"fx: {cam.fx:g}", f"fy: {cam.fy:g}",
+              f"cx: {cam.cx:g}", f"cy: {cam.cy:g}", "distance_threshold: 1.5",
+              f"are_objects_segmented: {'true' if segmented else 'false'}"]
+    if extra:
+        lines.append(extra)
+    with open(path, "w") as f:
+        f.write("\n".join(lines) + "\n")

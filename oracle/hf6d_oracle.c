@@ -315,6 +315,10 @@ void hf6d_ref_gather(const uint8_t* bgr, const uint16_t* depth, const hf6d_ref_p
 }
 
 /* ------------------------------------------------------------------------------------------------ A3 */
+static inline int32_t d2i_x86(double y) { /* C11 */
+    if (!(y == y) || y >= 2147483648.0 || y < -2147483648.0) return INT_MIN;
+    return (int32_t)y;
+}
 static inline int32_t f2i_x86(float y) { /* C11 */
     if (!(y == y) || y >= 2147483648.0f || y < -2147483648.0f) return INT_MIN;
     return (int32_t)y;
@@ -619,7 +623,7 @@ static void pose_from_tuple(const hf6d_ref_params* p, int cx, int cy, float z, i
 
 typedef struct { int32_t Y, Pp; const ref_node* leaf; } roll_entry;
 
-static int hypotheses_for_centre(const hf6d_ref_forest* f, const hf6d_ref_params* p, int c, const uint16_t* depth,
+static int hypotheses_for_centre(const hf6d_ref_params* p, int c, const uint16_t* depth,
                                  const entry_list* entries, int ctr_x, int ctr_y, float loc_score,
                                  hf6d_ref_hypothesis* out, int cap) {
     const int W = p->W, H = p->H;
@@ -649,15 +653,9 @@ static int hypotheses_for_centre(const hf6d_ref_forest* f, const hf6d_ref_params
                 int zb = f2i_x86(c3[2] / z_bin_size);
                 if (zb < zbins && zb >= 0) zacc[zb] += w;
             }
-            int yaw = f2i_x86((float)((double)vote[0] / M_PI * (double)180.0f));   /* :779 int = double expr */
-            int pitch = f2i_x86((float)0), dummy = 0;
-            (void)dummy;
-            {
-                double yd = (double)vote[0] / M_PI * 180.0;
-                double pd = (double)vote[1] / M_PI * 180.0;
-                yaw = (yd != yd || yd >= 2147483648.0 || yd < -2147483648.0) ? INT_MIN : (int)yd;
-                pitch = (pd != pd || pd >= 2147483648.0 || pd < -2147483648.0) ? INT_MIN : (int)pd;
-            }
+            /* HFTest.cpp:779-780: int = float / M_PI(double) * 180.0f -> double expression, truncated */
+            const int yaw = d2i_x86((double)vote[0] / M_PI * 180.0);
+            const int pitch = d2i_x86((double)vote[1] / M_PI * 180.0);
             for (int k1 = 0; k1 < 2; ++k1)
                 for (int k2 = 0; k2 < 2; ++k2) {
                     int sy = yaw < 0 ? -1 : 1, sp = pitch < 0 ? -1 : 1; /* copysign(1,(float)int): sign(0)=+1 */
@@ -711,8 +709,8 @@ static int hypotheses_for_centre(const hf6d_ref_forest* f, const hf6d_ref_params
             const ref_node* leaf = rl[e].leaf;
             const uint32_t w = qweight(leaf->class_prob[c]);
             for (int v = 0; v < leaf->nvotes[c]; ++v) {
-                double rd = (double)leaf->votes[c][6 * v + 2] * (double)180.0f / M_PI; /* :863 */
-                int r = (rd != rd || rd >= 2147483648.0 || rd < -2147483648.0) ? INT_MIN : (int)rd;
+                /* :863  float * 180.0f (float) / M_PI (double) */
+                const int r = d2i_x86((double)(leaf->votes[c][6 * v + 2] * 180.0f) / M_PI);
                 int b0 = r + 360, b1 = r < 0 ? r + 720 : r;
                 if (b0 >= 0 && b0 < NB) racc[b0] += w;
                 if (b1 >= 0 && b1 < NB) racc[b1] += w;
@@ -731,8 +729,9 @@ static int hypotheses_for_centre(const hf6d_ref_forest* f, const hf6d_ref_params
         for (int i = 0; i < nr && h_roll < p->max_roll_hypotheses; ++i) {
             const float roll_score = rh[i].score / rh[0].score;
             const int ry = rh[i].y;
-            double dot = cos(prev / 180.0f * M_PI) * cos(ry / 180.0f * M_PI) +
-                         sin(prev / 180.0f * M_PI) * sin(ry / 180.0f * M_PI); /* HFTest.cpp:918-921 */
+            /* HFTest.cpp:918-921: double expression narrowed to a float `dot`, acos() of that float */
+            float dot = (float)(cos(prev / 180.0f * M_PI) * cos(ry / 180.0f * M_PI) +
+                                sin(prev / 180.0f * M_PI) * sin(ry / 180.0f * M_PI));
             if (h_roll == 0 || acos(dot) / M_PI * 180.0f > 7) {
                 if (produced < cap) {
                     hf6d_ref_hypothesis* o = &out[produced];
@@ -779,7 +778,7 @@ int32_t hf6d_ref_hypotheses(const hf6d_ref_forest* f, const int32_t* leaf_ord, c
 #pragma omp parallel for schedule(dynamic)
         for (int k = 0; k < max_loc; ++k) {
             if (ch[k].score / ch[0].score < p->min_location_score_ratio) continue; /* HFTest.cpp:726 */
-            counts[k] = hypotheses_for_centre(f, p, c, depth, &entries[c], ch[k].x, ch[k].y, ch[k].score,
+            counts[k] = hypotheses_for_centre(p, c, depth, &entries[c], ch[k].x, ch[k].y, ch[k].score,
                                               tmp + (size_t)k * 32, 32);
             if (counts[k] > 32) counts[k] = 32;
         }
