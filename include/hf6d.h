@@ -1,0 +1,190 @@
+/* libhf6d.so -- C ABI of the B200-native Hough-forest detection path.
+ *
+ * Drop-in boundary for the per-frame hot path of the reference's `HoughForest --test`:
+ *
+ *   reference interface                                          replaced by
+ *   ------------------------------------------------------------ --------------------------------------------------
+ *   HFTest::DetectObjects()        HoughForest/src/HFTest.cpp:1152  hf6d_create_from_options + hf6d_detect loop
+ *   HFTest::setInputForest()       HoughForest/include/HFTest.h:131 hf6d_create (forest_dir)
+ *   HFTest::setCaffeModel()        HoughForest/include/HFTest.h:122 hf6d_create (weights_path)
+ *   HFTest::test_image()           HoughForest/include/HFTest.h:114 hf6d_detect / hf6d_submit + hf6d_wait
+ *   patch_extractor_gpu::extract_patches_rgbd()
+ *                                  PatchGen/include/cuda/patch_extractor.h:29
+ *                                                                   stages HF6D_STAGE_SCAN + HF6D_STAGE_GATHER
+ *   caffe::Net::ForwardPrefilled() HoughForest/src/HFTest.cpp:593   stage HF6D_STAGE_ENCODE
+ *   HFTest::detect()/get_leaf()    HoughForest/src/HFTest.cpp:144-217 stages HF6D_STAGE_TRAVERSE + HF6D_STAGE_VOTE
+ *   cv::blur + non_max_suppression HoughForest/src/HFTest.cpp:702-707 stage HF6D_STAGE_CENTRES
+ *   z / yaw-pitch / roll seeking   HoughForest/src/HFTest.cpp:742-925 stage HF6D_STAGE_POSE
+ *   MeshUtils::icp() pre-ICP pose  HoughForest/src/MeshUtils.cpp:423-440 hf6d_hypothesis.pose
+ *
+ * Everything is plain C: opaque handle, pointers and sizes.  Every entry point returns 0 on success or a negative
+ * HF6D_E* code; hf6d_last_error() gives the message.  Nothing here aborts, prints, or reads stdin (the reference's
+ * CUDA_SAFE_CALL blocks on getchar(), PatchGen/include/cuda/cuda_utils.h:18-72).
+ *
+ * There is no CPU fallback: every entry point that computes fails with HF6D_ECUDA when no sm_100 device is usable.
+ */
+#ifndef HF6D_H_
+#define HF6D_H_
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HF6D_OK 0
+#define HF6D_EINVAL (-1)  /* bad argument */
+#define HF6D_EIO (-2)     /* file missing / malformed (forest, weights, options) */
+#define HF6D_ECUDA (-3)   /* CUDA runtime error or no usable device */
+#define HF6D_ENOMEM (-4)
+#define HF6D_ESTATE (-5)  /* call order (e.g. wait on an unknown ticket) */
+
+#define HF6D_WEIGHT_SHIFT 16 /* vote weights are Q16 fixed point: w = (uint32)(class_prob * 65536 + 0.5) */
+#define HF6D_Z_BINS 300      /* HFTest.cpp:743-745: 3 m / 1 cm */
+#define HF6D_POSE_BINS 720   /* HFTest.cpp:756: degrees in [-360, 359] */
+#define HF6D_MAX_CLASSES 32
+#define HF6D_MAX_CENTRES 16  /* max_location_hypotheses upper bound per object */
+#define HF6D_MAX_HYPOTHESES_PER_CENTRE 32
+
+typedef struct hf6d_ctx hf6d_ctx;
+
+/* Frame geometry + the reference's options (detector_options.proto:18-70) + hard-coded constants (HFTest.h:175-194).
+ * Layout is shared with the oracle's parameter block so that parity tests pass one struct to both. */
+typedef struct {
+    int32_t W, H;
+    int32_t stride;                /* Options.stride */
+    float fx, fy, cx, cy;          /* Options.fx .. cy */
+    int32_t patch_vox;             /* forest.txt: patch_size_in_voxels (overwritten from the forest at create) */
+    float voxel_m;                 /* forest.txt: voxel_size_in_m      (overwritten from the forest at create) */
+    float max_depth_range_m;       /* Options.max_depth_range_in_patch_in_m */
+    float distance_threshold_m;    /* Options.distance_threshold */
+    int32_t fill_random;           /* = !Options.are_objects_segmented */
+    uint64_t fill_seed;            /* counter-based RNG key for the border fill (reference: clock64()) */
+    int32_t batch_size;            /* Options.batch_size: P' = floor(P / batch_size) * batch_size patches are processed */
+    int32_t max_yaw_pitch_hypotheses, max_roll_hypotheses;
+    float min_location_score_ratio, min_yaw_pitch_drop_ratio;
+    int32_t centers_blur_size, centers_nms_wsize, pose_blur_size, pose_nms_wsize;
+} hf6d_params;
+
+typedef struct {
+    int32_t cls, cx, cy;                  /* class, centre pixel (column, row) */
+    float z;                              /* mode_z [m] */
+    int32_t yaw_deg, pitch_deg, roll_deg; /* quantised pose mode */
+    float loc_score, yawpitch_score, roll_score;
+    float pose[16];                       /* pre-ICP 4x4, row-major, camera (xtion) frame */
+} hf6d_hypothesis;
+
+/* Per-object switches (detector_options.proto:3-16). */
+typedef struct {
+    char name[64];
+    int32_t should_detect;
+    int32_t max_location_hypotheses;
+    int32_t instances;
+} hf6d_object;
+
+typedef enum {
+    HF6D_STAGE_SCAN = 0,     /* valid patch centres, row-major order             patch_extractor.cu:372-391 */
+    HF6D_STAGE_GATHER = 1,   /* bilinear RGB-D gather + local normalise + quantise  patch_extractor.cu:230-309, HFTest.cpp:500-570 */
+    HF6D_STAGE_ENCODE = 2,   /* 256-1500-1000-800 sigmoid encoder (tcgen05)      HFTest.cpp:585-596 */
+    HF6D_STAGE_TRAVERSE = 3, /* every patch through every (owned) tree            HFTest.cpp:144-163 */
+    HF6D_STAGE_VOTE = 4,     /* centre votes into per-class accumulators         HFTest.cpp:166-217 */
+    HF6D_STAGE_CENTRES = 5,  /* box blur + sliding-window NMS -> centre list     HFTest.cpp:702-707 */
+    HF6D_STAGE_POSE = 6,     /* z / yaw-pitch / roll mode seeking -> hypotheses  HFTest.cpp:742-925 */
+    HF6D_STAGE_COUNT = 7
+} hf6d_stage;
+
+typedef enum {
+    HF6D_BUF_COUNTS = 0,   /* int32[2]  = P (valid centres), P' (processed) */
+    HF6D_BUF_LOCS = 1,     /* int32[P][2] = (x, y) */
+    HF6D_BUF_PATCH_U8 = 2, /* uint8[P'][4*ps*ps] quantised CHW patches (only when debug capture is on) */
+    HF6D_BUF_FEATURES = 3, /* float[P'][F] */
+    HF6D_BUF_LEAF_ORD = 4, /* int32[P'][T]: file-order ordinal of the leaf inside its tree; -1 for trees not owned */
+    HF6D_BUF_MAPS = 5,     /* uint64[K][H][W] Q16 vote sums */
+    HF6D_BUF_BLURRED = 6,  /* float[K][H][W] */
+    HF6D_BUF_CENTRES = 7,  /* per class: int32 n, then HF6D_MAX_CENTRES x {float score, int32 x, int32 y} (see hf6d_centre) */
+    HF6D_BUF_FRAME_BGR = 8,
+    HF6D_BUF_FRAME_DEPTH = 9,
+    HF6D_BUF_COUNT = 10
+} hf6d_buffer;
+
+typedef struct {
+    float score;
+    int32_t x, y;
+} hf6d_centre;
+
+typedef struct {
+    int32_t n;
+    hf6d_centre c[HF6D_MAX_CENTRES];
+} hf6d_centre_list;
+
+typedef struct {
+    int32_t T, K, F, patch_vox;
+    float voxel_m;
+    int64_t n_leaves, n_internal, n_votes; /* n_votes: votes of (leaf, class) groups that pass the 0.5 gate */
+    int32_t max_depth;
+    int32_t dims[4]; /* encoder 256, 1500, 1000, 800 */
+} hf6d_model_info;
+
+/* ---------------------------------------------------------------------------------------------- lifecycle */
+void hf6d_default_params(hf6d_params* p);
+
+/* forest_dir: forest.txt + tree<N>.dat (HFBase.cpp:110-145).  weights_path: a V1 .caffemodel with layers encode1..3
+ * (generate_scripts.sh:424-524) or the raw "HF6DW001" container.  n_slots frames may be in flight (>=1). */
+int hf6d_create(const hf6d_params* p, const char* forest_dir, const char* weights_path, int device, int n_slots,
+                hf6d_ctx** out);
+/* Text-format DetectorOptions.Options file, as HoughForest --test --detector_options_file takes (HFTest.cpp:1155-1235).
+ * W, H: frame size the context is sized for. */
+int hf6d_create_from_options(const char* options_path, int W, int H, int device, int n_slots, hf6d_ctx** out);
+void hf6d_destroy(hf6d_ctx* c);
+const char* hf6d_last_error(const hf6d_ctx* c); /* c may be NULL: error of the last failed create on this thread */
+
+int hf6d_get_params(const hf6d_ctx* c, hf6d_params* out);
+int hf6d_model(const hf6d_ctx* c, hf6d_model_info* out);
+int hf6d_set_objects(hf6d_ctx* c, const hf6d_object* objs, int n);   /* n must equal K */
+int hf6d_get_objects(const hf6d_ctx* c, hf6d_object* objs, int cap); /* returns K */
+int hf6d_set_fill_seed(hf6d_ctx* c, uint64_t seed);
+/* Tree sharding (one process per GPU): this context traverses and votes only trees t with t % world == rank.
+ * The caller sums HF6D_BUF_MAPS across ranks (NCCL all-reduce, uint64 sum) and max-reduces HF6D_BUF_LEAF_ORD between
+ * hf6d_run(.., VOTE) and hf6d_run(CENTRES, ..). */
+int hf6d_set_tree_shard(hf6d_ctx* c, int rank, int world);
+/* Encoder arithmetic: 0 = bf16 operands (default), 1 = split-bf16 (hi+lo operands, 3 MMAs per product, ~fp32). */
+int hf6d_set_encoder_mode(hf6d_ctx* c, int mode);
+int hf6d_set_debug_capture(hf6d_ctx* c, int on); /* keep HF6D_BUF_PATCH_U8 */
+
+/* ---------------------------------------------------------------------------------------------- whole frame */
+/* Host buffers: bgr uint8[H][W][3] (OpenCV imread order), depth_mm uint16[H][W].  Synchronous. */
+int hf6d_detect(hf6d_ctx* c, const uint8_t* bgr, const uint16_t* depth_mm, hf6d_hypothesis* out, int cap, int* n_out);
+/* Pipelined form: up to n_slots frames in flight; H2D copy, kernels and D2H of frame i overlap those of frame i+1.
+ * Host buffers must stay valid until the matching hf6d_wait; pinned memory (hf6d_host_alloc) makes the copy async. */
+int hf6d_submit(hf6d_ctx* c, const uint8_t* bgr, const uint16_t* depth_mm, int* ticket);
+int hf6d_wait(hf6d_ctx* c, int ticket, hf6d_hypothesis* out, int cap, int* n_out);
+void* hf6d_host_alloc(size_t bytes); /* pinned */
+void hf6d_host_free(void* p);
+
+/* ---------------------------------------------------------------------------------------------- stage level */
+/* Used by the parity tests, the bench (device-resident timing) and the multi-GPU driver. slot in [0, n_slots). */
+int hf6d_upload(hf6d_ctx* c, int slot, const uint8_t* bgr, const uint16_t* depth_mm); /* async H2D on the slot stream */
+int hf6d_run(hf6d_ctx* c, int slot, int first_stage, int last_stage);                 /* async, inclusive range */
+int hf6d_sync(hf6d_ctx* c, int slot);
+int hf6d_collect(hf6d_ctx* c, int slot, hf6d_hypothesis* out, int cap, int* n_out);   /* D2H + host pose finalise; syncs */
+/* Copy a device buffer to the host (syncs the slot).  Returns bytes written, or <0. */
+int64_t hf6d_fetch(hf6d_ctx* c, int slot, int what, void* dst, size_t cap_bytes);
+/* Overwrite a device buffer from the host: FEATURES (rows = P'), LEAF_ORD, MAPS, COUNTS/LOCS (stage-isolated parity). */
+int hf6d_inject(hf6d_ctx* c, int slot, int what, const void* src, size_t bytes);
+/* Raw device pointer of a buffer (for NCCL collectives issued by the caller). */
+int hf6d_device_ptr(hf6d_ctx* c, int slot, int what, void** ptr, size_t* bytes);
+/* Run the slot on a caller-owned CUDA stream (cudaStream_t as void*), e.g. torch's current stream; NULL restores. */
+int hf6d_set_stream(hf6d_ctx* c, int slot, void* cuda_stream);
+/* Milliseconds per stage of the last hf6d_run on this slot (CUDA events on the slot stream); ms[HF6D_STAGE_COUNT]. */
+int hf6d_stage_ms(hf6d_ctx* c, int slot, float* ms);
+/* Number of kernels the last hf6d_run on this slot launched. */
+int hf6d_launch_count(const hf6d_ctx* c, int slot);
+
+/* Pre-ICP pose of a hypothesis tuple (HFTest.cpp:922-924 + MeshUtils.cpp:423-440); host arithmetic. */
+void hf6d_pose_from_tuple(const hf6d_params* p, int cx, int cy, float z, int yaw_deg, int pitch_deg, int roll_deg,
+                          float pose[16]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,325 @@
+"""ctypes binding of libhf6d.so (include/hf6d.h) -- the host-side mirror of the reference's HFTest interface.
+
+The reference is compiled C++ (HoughForest/include/HFTest.h); its host side here is C++ too (csrc/hough_forest_main.cpp
+is the `HoughForest --test` drop-in).  This module exists for the parity tests, the bench and the multi-GPU driver: it
+loads the C ABI and nothing else -- no numpy implementation of any stage lives here, and importing it never touches the
+oracle.  If the shared library is missing it is built in-tree with nvcc; if that fails the import raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+STAGE_SCAN, STAGE_GATHER, STAGE_ENCODE, STAGE_TRAVERSE, STAGE_VOTE, STAGE_CENTRES, STAGE_POSE = range(7)
+STAGE_COUNT = 7
+STAGE_NAMES = ("scan", "gather", "encode", "traverse", "vote", "centres", "pose")
+(BUF_COUNTS, BUF_LOCS, BUF_PATCH_U8, BUF_FEATURES, BUF_LEAF_ORD, BUF_MAPS, BUF_BLURRED, BUF_CENTRES, BUF_FRAME_BGR,
+ BUF_FRAME_DEPTH) = range(10)
+MAX_CENTRES = 16
+
+EXPORTS = (
+    "hf6d_default_params", "hf6d_create", "hf6d_create_from_options", "hf6d_destroy", "hf6d_last_error",
+    "hf6d_get_params", "hf6d_model", "hf6d_set_objects", "hf6d_get_objects", "hf6d_set_fill_seed",
+    "hf6d_set_tree_shard", "hf6d_set_encoder_mode", "hf6d_set_debug_capture", "hf6d_detect", "hf6d_submit",
+    "hf6d_wait", "hf6d_host_alloc", "hf6d_host_free", "hf6d_upload", "hf6d_run", "hf6d_sync", "hf6d_collect",
+    "hf6d_fetch", "hf6d_inject", "hf6d_device_ptr", "hf6d_set_stream", "hf6d_stage_ms", "hf6d_launch_count",
+    "hf6d_pose_from_tuple",
+)
+
+
+class Params(C.Structure):
+    _fields_ = [("W", C.c_int32), ("H", C.c_int32), ("stride", C.c_int32), ("fx", C.c_float), ("fy", C.c_float),
+                ("cx", C.c_float), ("cy", C.c_float), ("patch_vox", C.c_int32), ("voxel_m", C.c_float),
+                ("max_depth_range_m", C.c_float), ("distance_threshold_m", C.c_float), ("fill_random", C.c_int32),
+                ("fill_seed", C.c_uint64), ("batch_size", C.c_int32), ("max_yaw_pitch_hypotheses", C.c_int32),
+                ("max_roll_hypotheses", C.c_int32), ("min_location_score_ratio", C.c_float),
+                ("min_yaw_pitch_drop_ratio", C.c_float), ("centers_blur_size", C.c_int32),
+                ("centers_nms_wsize", C.c_int32), ("pose_blur_size", C.c_int32), ("pose_nms_wsize", C.c_int32)]
+
+
+class ObjectOptions(C.Structure):
+    _fields_ = [("name", C.c_char * 64), ("should_detect", C.c_int32), ("max_location_hypotheses", C.c_int32),
+                ("instances", C.c_int32)]
+
+
+class ModelInfo(C.Structure):
+    _fields_ = [("T", C.c_int32), ("K", C.c_int32), ("F", C.c_int32), ("patch_vox", C.c_int32),
+                ("voxel_m", C.c_float), ("n_leaves", C.c_int64), ("n_internal", C.c_int64), ("n_votes", C.c_int64),
+                ("max_depth", C.c_int32), ("dims", C.c_int32 * 4)]
+
+
+HYP_DTYPE = np.dtype([("cls", "<i4"), ("cx", "<i4"), ("cy", "<i4"), ("z", "<f4"), ("yaw_deg", "<i4"),
+                      ("pitch_deg", "<i4"), ("roll_deg", "<i4"), ("loc_score", "<f4"), ("yawpitch_score", "<f4"),
+                      ("roll_score", "<f4"), ("pose", "<f4", (16,))])
+CENTRE_DTYPE = np.dtype([("score", "<f4"), ("x", "<i4"), ("y", "<i4")])
+CENTRE_LIST_DTYPE = np.dtype([("n", "<i4"), ("c", CENTRE_DTYPE, (MAX_CENTRES,))])
+
+_lib = None
+
+
+class Hf6dError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"hf6d error {code}: {msg}")
+        self.code = code
+
+
+def lib_path() -> str:
+    return _build.LIB
+
+
+def load():
+    """Load (building if necessary) libhf6d.so.  Raises if the CUDA extension cannot be built or loaded."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.build_lib()
+    L = C.CDLL(path)
+    vp, i32, i64 = C.c_void_p, C.c_int, C.c_int64
+    L.hf6d_default_params.argtypes = [C.POINTER(Params)]
+    L.hf6d_default_params.restype = None
+    L.hf6d_create.argtypes = [C.POINTER(Params), C.c_char_p, C.c_char_p, i32, i32, C.POINTER(vp)]
+    L.hf6d_create_from_options.argtypes = [C.c_char_p, i32, i32, i32, i32, C.POINTER(vp)]
+    L.hf6d_destroy.argtypes = [vp]
+    L.hf6d_destroy.restype = None
+    L.hf6d_last_error.argtypes = [vp]
+    L.hf6d_last_error.restype = C.c_char_p
+    L.hf6d_get_params.argtypes = [vp, C.POINTER(Params)]
+    L.hf6d_model.argtypes = [vp, C.POINTER(ModelInfo)]
+    L.hf6d_set_objects.argtypes = [vp, C.POINTER(ObjectOptions), i32]
+    L.hf6d_get_objects.argtypes = [vp, C.POINTER(ObjectOptions), i32]
+    L.hf6d_set_fill_seed.argtypes = [vp, C.c_uint64]
+    L.hf6d_set_tree_shard.argtypes = [vp, i32, i32]
+    L.hf6d_set_encoder_mode.argtypes = [vp, i32]
+    L.hf6d_set_debug_capture.argtypes = [vp, i32]
+    L.hf6d_detect.argtypes = [vp, vp, vp, vp, i32, C.POINTER(i32)]
+    L.hf6d_submit.argtypes = [vp, vp, vp, C.POINTER(i32)]
+    L.hf6d_wait.argtypes = [vp, i32, vp, i32, C.POINTER(i32)]
+    L.hf6d_host_alloc.argtypes = [C.c_size_t]
+    L.hf6d_host_alloc.restype = vp
+    L.hf6d_host_free.argtypes = [vp]
+    L.hf6d_host_free.restype = None
+    L.hf6d_upload.argtypes = [vp, i32, vp, vp]
+    L.hf6d_run.argtypes = [vp, i32, i32, i32]
+    L.hf6d_sync.argtypes = [vp, i32]
+    L.hf6d_collect.argtypes = [vp, i32, vp, i32, C.POINTER(i32)]
+    L.hf6d_fetch.argtypes = [vp, i32, i32, vp, C.c_size_t]
+    L.hf6d_fetch.restype = i64
+    L.hf6d_inject.argtypes = [vp, i32, i32, vp, C.c_size_t]
+    L.hf6d_device_ptr.argtypes = [vp, i32, i32, C.POINTER(vp), C.POINTER(C.c_size_t)]
+    L.hf6d_set_stream.argtypes = [vp, i32, vp]
+    L.hf6d_stage_ms.argtypes = [vp, i32, C.POINTER(C.c_float)]
+    L.hf6d_launch_count.argtypes = [vp, i32]
+    L.hf6d_pose_from_tuple.argtypes = [C.POINTER(Params), i32, i32, C.c_float, i32, i32, i32, C.POINTER(C.c_float)]
+    L.hf6d_pose_from_tuple.restype = None
+    _lib = L
+    return L
+
+
+def default_params(**kw) -> Params:
+    p = Params()
+    load().hf6d_default_params(C.byref(p))
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+class PinnedArray:
+    """numpy view over pinned host memory from hf6d_host_alloc."""
+
+    def __init__(self, shape, dtype):
+        self.nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        self.ptr = load().hf6d_host_alloc(self.nbytes)
+        if not self.ptr:
+            raise MemoryError("hf6d_host_alloc failed")
+        buf = (C.c_uint8 * self.nbytes).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            load().hf6d_host_free(self.ptr)
+            self.ptr = None
+
+
+class _CudaArray:
+    """Minimal __cuda_array_interface__ holder so torch.as_tensor can wrap a libhf6d device buffer (for NCCL)."""
+
+    def __init__(self, ptr, shape, typestr, owner):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+        self._owner = owner
+
+
+class Detector:
+    """One libhf6d context = the model on one GPU plus `n_slots` frame workspaces.
+
+    Mirrors what HFTest holds between frames (HoughForest/include/HFTest.h:25-50): forest, encoder, options.
+    """
+
+    def __init__(self, forest_dir=None, weights_path=None, params: Params | None = None, device: int = 0,
+                 n_slots: int = 1, options_path: str | None = None, frame_size=None):
+        self._L = load()
+        self._h = C.c_void_p()
+        if options_path is not None:
+            W, H = frame_size or (640, 480)
+            rc = self._L.hf6d_create_from_options(options_path.encode(), W, H, device, n_slots, C.byref(self._h))
+        else:
+            p = params if params is not None else default_params()
+            rc = self._L.hf6d_create(C.byref(p), forest_dir.encode(), weights_path.encode(), device, n_slots,
+                                     C.byref(self._h))
+        if rc:
+            raise Hf6dError(rc, (self._L.hf6d_last_error(None) or b"").decode())
+        self.params = Params()
+        self._L.hf6d_get_params(self._h, C.byref(self.params))
+        self.model = ModelInfo()
+        self._L.hf6d_model(self._h, C.byref(self.model))
+        self.n_slots = n_slots
+        self.T, self.K, self.F = self.model.T, self.model.K, self.model.F
+        self.W, self.H = self.params.W, self.params.H
+
+    # ------------------------------------------------------------------ plumbing
+    def _ck(self, rc):
+        if rc < 0:
+            raise Hf6dError(rc, (self._L.hf6d_last_error(self._h) or b"").decode())
+        return rc
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.hf6d_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @staticmethod
+    def _ptr(a):
+        return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+    def _check_frame(self, bgr, depth):
+        if bgr.dtype != np.uint8 or bgr.shape != (self.H, self.W, 3) or not bgr.flags.c_contiguous:
+            raise ValueError(f"bgr must be contiguous uint8 [{self.H},{self.W},3]")
+        if depth.dtype != np.uint16 or depth.shape != (self.H, self.W) or not depth.flags.c_contiguous:
+            raise ValueError(f"depth must be contiguous uint16 [{self.H},{self.W}]")
+
+    # ------------------------------------------------------------------ configuration
+    def set_objects(self, should_detect=None, max_loc=None, names=None, instances=None):
+        objs = (ObjectOptions * self.K)()
+        for k in range(self.K):
+            objs[k].name = (names[k] if names else f"object{k}").encode()
+            objs[k].should_detect = int(should_detect[k]) if should_detect is not None else 1
+            objs[k].max_location_hypotheses = int(max_loc[k]) if max_loc is not None else 12
+            objs[k].instances = int(instances[k]) if instances is not None else 1
+        self._ck(self._L.hf6d_set_objects(self._h, objs, self.K))
+
+    def objects(self):
+        objs = (ObjectOptions * self.K)()
+        self._ck(self._L.hf6d_get_objects(self._h, objs, self.K))
+        return [dict(name=o.name.decode(), should_detect=bool(o.should_detect),
+                     max_location_hypotheses=o.max_location_hypotheses, instances=o.instances) for o in objs]
+
+    def set_fill_seed(self, seed: int):
+        self._ck(self._L.hf6d_set_fill_seed(self._h, seed))
+
+    def set_tree_shard(self, rank: int, world: int):
+        self._ck(self._L.hf6d_set_tree_shard(self._h, rank, world))
+
+    def set_debug_capture(self, on: bool):
+        self._ck(self._L.hf6d_set_debug_capture(self._h, int(on)))
+
+    def set_stream(self, slot: int, cuda_stream: int | None):
+        self._ck(self._L.hf6d_set_stream(self._h, slot, C.c_void_p(cuda_stream) if cuda_stream else None))
+
+    # ------------------------------------------------------------------ whole frame (the call a user makes)
+    def detect(self, bgr, depth, cap: int = 4096):
+        self._check_frame(bgr, depth)
+        out = np.zeros(cap, HYP_DTYPE)
+        n = C.c_int(0)
+        self._ck(self._L.hf6d_detect(self._h, self._ptr(bgr), self._ptr(depth), self._ptr(out), cap, C.byref(n)))
+        return out[:min(n.value, cap)].copy()
+
+    def submit(self, bgr, depth) -> int:
+        t = C.c_int(0)
+        self._ck(self._L.hf6d_submit(self._h, self._ptr(bgr), self._ptr(depth), C.byref(t)))
+        return t.value
+
+    def wait(self, ticket: int, cap: int = 4096):
+        out = np.zeros(cap, HYP_DTYPE)
+        n = C.c_int(0)
+        self._ck(self._L.hf6d_wait(self._h, ticket, self._ptr(out), cap, C.byref(n)))
+        return out[:min(n.value, cap)].copy()
+
+    # ------------------------------------------------------------------ stage level
+    def upload(self, slot, bgr, depth):
+        self._check_frame(bgr, depth)
+        self._ck(self._L.hf6d_upload(self._h, slot, self._ptr(bgr), self._ptr(depth)))
+
+    def run(self, slot=0, first=STAGE_SCAN, last=STAGE_POSE):
+        self._ck(self._L.hf6d_run(self._h, slot, first, last))
+
+    def sync(self, slot=0):
+        self._ck(self._L.hf6d_sync(self._h, slot))
+
+    def collect(self, slot=0, cap: int = 4096):
+        out = np.zeros(cap, HYP_DTYPE)
+        n = C.c_int(0)
+        self._ck(self._L.hf6d_collect(self._h, slot, self._ptr(out), cap, C.byref(n)))
+        return out[:min(n.value, cap)].copy()
+
+    def stage_ms(self, slot=0):
+        ms = (C.c_float * STAGE_COUNT)()
+        self._ck(self._L.hf6d_stage_ms(self._h, slot, ms))
+        return np.array(list(ms), np.float64)
+
+    def launch_count(self, slot=0) -> int:
+        return self._ck(self._L.hf6d_launch_count(self._h, slot))
+
+    def counts(self, slot=0):
+        a = np.zeros(2, np.int32)
+        self._ck(self._L.hf6d_fetch(self._h, slot, BUF_COUNTS, self._ptr(a), a.nbytes))
+        return int(a[0]), int(a[1])
+
+    def fetch(self, what, slot=0):
+        P, Pp = self.counts(slot)
+        K, T, F, H, W = self.K, self.T, self.F, self.H, self.W
+        shapes = {
+            BUF_COUNTS: ((2,), np.int32), BUF_LOCS: ((P, 2), np.int32), BUF_PATCH_U8: ((Pp, 256), np.uint8),
+            BUF_FEATURES: ((Pp, F), np.float32), BUF_LEAF_ORD: ((Pp, T), np.int32), BUF_MAPS: ((K, H, W), np.uint64),
+            BUF_BLURRED: ((K, H, W), np.float32), BUF_CENTRES: ((K,), CENTRE_LIST_DTYPE),
+            BUF_FRAME_BGR: ((H, W, 3), np.uint8), BUF_FRAME_DEPTH: ((H, W), np.uint16),
+        }
+        shape, dt = shapes[what]
+        a = np.zeros(shape, dt)
+        n = self._ck(self._L.hf6d_fetch(self._h, slot, what, self._ptr(a), a.nbytes))
+        assert n == a.nbytes, (n, a.nbytes)
+        return a
+
+    def inject(self, what, array, slot=0):
+        a = np.ascontiguousarray(array)
+        self._ck(self._L.hf6d_inject(self._h, slot, what, self._ptr(a), a.nbytes))
+
+    def device_ptr(self, what, slot=0):
+        p = C.c_void_p()
+        n = C.c_size_t()
+        self._ck(self._L.hf6d_device_ptr(self._h, slot, what, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def device_array(self, what, slot=0):
+        """A __cuda_array_interface__ view of MAPS (int64 [K,H,W]) or LEAF_ORD (int32 [cap,T]) for torch.as_tensor."""
+        ptr, nbytes = self.device_ptr(what, slot)
+        if what == BUF_MAPS:
+            return _CudaArray(ptr, (self.K, self.H, self.W), "<i8", self)
+        if what == BUF_LEAF_ORD:
+            return _CudaArray(ptr, (nbytes // (4 * self.T), self.T), "<i4", self)
+        raise ValueError("device_array supports BUF_MAPS and BUF_LEAF_ORD")
+
+    def pose_from_tuple(self, cx, cy, z, yaw_deg, pitch_deg, roll_deg):
+        out = (C.c_float * 16)()
+        self._L.hf6d_pose_from_tuple(C.byref(self.params), cx, cy, C.c_float(z), yaw_deg, pitch_deg, roll_deg, out)
+        return np.array(list(out), np.float32).reshape(4, 4)

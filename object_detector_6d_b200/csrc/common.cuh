@@ -1,0 +1,54 @@
+// Shared device/host definitions for libhf6d kernels.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+
+#include "../../include/hf6d.h"
+#include "model.hpp"
+
+namespace hf6d {
+
+// Per-frame constants every kernel needs (passed by value).
+struct FrameGeom {
+    int W, H, stride;
+    int gw, gh;          // stride-grid size: ceil(W/stride), ceil(H/stride)
+    float fx, fy, cx, cy;
+    int ps;              // patch_size_in_voxels (8)
+    float vox, range, dist_thr;
+    int fill_random;
+    unsigned long long fill_seed;
+    int batch;
+    int cap;             // patch capacity of the per-slot buffers (multiple of 128)
+};
+
+// Device view of the flattened forest (model.hpp::HostForest).
+struct DevForest {
+    int T, K, F;
+    const PackedNode* nodes;
+    const int32_t* root;       // [T]
+    const int32_t* leaf_base;  // [T+1]
+    const int32_t* group_off;  // [L+1]
+    const VoteGroup* groups;
+    const float *ox, *oy, *oz;
+    const int16_t *yaw, *pitch, *roll;
+};
+
+// x86 cvttss2si semantics: NaN / out of range -> INT_MIN (CUDA's cast saturates and maps NaN to 0).
+__device__ __forceinline__ int f2i_x86(float y) {
+    if (!(y == y) || y >= 2147483648.0f || y < -2147483648.0f) return INT_MIN;
+    return (int)y;
+}
+
+__device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+
+// patch_extractor.cu:257 / :378 -- ((ps*vox)/d)*f in fp32, truncated
+__device__ __forceinline__ int adaptive_size(const FrameGeom& g, float depth_m) {
+    return (int)__fmul_rn(__fdiv_rn(__fmul_rn((float)g.ps, g.vox), depth_m), g.fx);
+}
+
+}  // namespace hf6d

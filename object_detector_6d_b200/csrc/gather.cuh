@@ -1,0 +1,264 @@
+// Stage SCAN + GATHER: valid patch centres (ordered compaction) and the fused
+// bilinear RGB-D gather + local normalisation + uint8 quantisation.
+//
+// Replaces  patch_extractor_gpu::extract_patches_rgbd  (PatchGen/src/cuda/patch_extractor.cu:230-309, 318-433: host
+// loop over the stride grid, 3-D texture upload, one 64-thread block per patch, 71 MB D2H of fp32 patches) and the
+// single-threaded normalise/quantise loop of HFTest::test_image (HoughForest/src/HFTest.cpp:500-570).
+//
+// B200 design: the frame stays in its 5 B/pixel form (uint8 BGR + uint16 depth, 1.5 MB: L2 resident), the
+// stride-grid scan is an ordered two-kernel compaction (so patch indices equal the reference's row-major push order),
+// and one kernel produces the encoder's A operand directly: bf16 [P'][256] holding the quantised value q as an exact
+// integer (1/255 is folded into the first layer's weights).  The fp32 patches never exist in memory.
+//
+// Arithmetic is the oracle's, operation for operation (IEEE _rn intrinsics, no FMA contraction), including the strictly
+// sequential mean / variance accumulation order c -> row -> col of the reference, so the uint8 patches are bit-exact.
+#pragma once
+#include "common.cuh"
+
+namespace hf6d {
+
+__device__ __forceinline__ bool centre_valid(const uint16_t* __restrict__ depth, const FrameGeom& g, int w, int h) {
+    const float d = (float)depth[(size_t)h * g.W + w];
+    if (d == 0.0f) return false;
+    const float dm = __fdiv_rn(d, 1000.0f);
+    if (!(dm < g.dist_thr)) return false;
+    const int a = adaptive_size(g, dm);
+    const int x0 = w - a / 2, x1 = x0 + a - 1;
+    const int y0 = h - a / 2, y1 = y0 + a - 1;
+    return x0 >= 0 && y0 >= 0 && x1 < g.W && y1 < g.H;
+}
+
+// One warp per stride-grid row: number of valid centres in the row.
+__global__ void scan_count_kernel(const uint16_t* __restrict__ depth, FrameGeom g, int* __restrict__ row_count) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= g.gh) return;
+    const int h = row * g.stride;
+    int n = 0;
+    for (int c0 = 0; c0 < g.gw; c0 += 32) {
+        const int c = c0 + lane;
+        const bool ok = c < g.gw && centre_valid(depth, g, c * g.stride, h);
+        n += __popc(__ballot_sync(0xffffffffu, ok));
+    }
+    if (lane == 0) row_count[row] = n;
+}
+
+// One warp per stride-grid row: exclusive offset = sum of the counts of earlier rows, then ballot compaction.
+// counts[0] = P, counts[1] = P' = floor(P / batch) * batch (the reference drops the partial batch, HFTest.cpp:433).
+__global__ void scan_compact_kernel(const uint16_t* __restrict__ depth, FrameGeom g, const int* __restrict__ row_count,
+                                    int* __restrict__ locs, int* __restrict__ counts) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= g.gh) return;
+    int before = 0, total = 0;
+    for (int r = lane; r < g.gh; r += 32) {
+        const int n = row_count[r];
+        total += n;
+        if (r < row) before += n;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        before += __shfl_xor_sync(0xffffffffu, before, o);
+        total += __shfl_xor_sync(0xffffffffu, total, o);
+    }
+    if (row == 0 && lane == 0) {
+        counts[0] = total;
+        counts[1] = (total / g.batch) * g.batch;
+    }
+    const int h = row * g.stride;
+    int pos = before;
+    for (int c0 = 0; c0 < g.gw; c0 += 32) {
+        const int c = c0 + lane;
+        const bool ok = c < g.gw && centre_valid(depth, g, c * g.stride, h);
+        const unsigned m = __ballot_sync(0xffffffffu, ok);
+        if (ok) {
+            const int i = pos + __popc(m & ((1u << lane) - 1u));
+            if (i < g.cap) {
+                locs[2 * i] = c * g.stride;
+                locs[2 * i + 1] = h;
+            }
+        }
+        pos += __popc(m);
+    }
+}
+
+// Software restatement of the texture fetch the reference uses (3-D float texture, unnormalised coordinates,
+// linear filter, border address mode): fraction rounded to 8 bits, out-of-range texel = 0,
+// S = ((w00*T00 + w10*T10) + w01*T01) + w11*T11 in fp32.
+struct Bilerp {
+    int i, j;
+    float w00, w10, w01, w11;
+};
+__device__ __forceinline__ float frac8(float a) { return floorf(__fadd_rn(__fmul_rn(a, 256.0f), 0.5f)) * (1.0f / 256.0f); }
+__device__ __forceinline__ Bilerp make_bilerp(float u, float v) {
+    Bilerp b;
+    const float fu = floorf(u), fv = floorf(v);
+    b.i = (int)fu;
+    b.j = (int)fv;
+    const float a = frac8(__fsub_rn(u, fu)), c = frac8(__fsub_rn(v, fv));
+    const float na = __fsub_rn(1.0f, a), nc = __fsub_rn(1.0f, c);
+    b.w00 = __fmul_rn(na, nc);
+    b.w10 = __fmul_rn(a, nc);
+    b.w01 = __fmul_rn(na, c);
+    b.w11 = __fmul_rn(a, c);
+    return b;
+}
+__device__ __forceinline__ float blend(const Bilerp& b, float t00, float t10, float t01, float t11) {
+    float s = __fmul_rn(b.w00, t00);
+    s = __fadd_rn(s, __fmul_rn(b.w10, t10));
+    s = __fadd_rn(s, __fmul_rn(b.w01, t01));
+    s = __fadd_rn(s, __fmul_rn(b.w11, t11));
+    return s;
+}
+
+constexpr int GATHER_PATCHES_PER_CTA = 16;
+constexpr int GATHER_THREADS = GATHER_PATCHES_PER_CTA * 8;
+
+// 8 threads per patch (one per patch row), 16 patches per CTA.  ps == 8 only (the 256-input encoder).
+// a_out : bf16 [cap][256], CHW order, value = q (exact integer 0..255)
+// q_out : optional uint8 [cap][256] (debug capture / parity)
+__global__ void __launch_bounds__(GATHER_THREADS)
+gather_normalise_kernel(const uint8_t* __restrict__ bgr, const uint16_t* __restrict__ depth, FrameGeom g,
+                        const int* __restrict__ locs, const int* __restrict__ counts,
+                        __nv_bfloat16* __restrict__ a_out, uint8_t* __restrict__ q_out) {
+    __shared__ float s_term[GATHER_PATCHES_PER_CTA][257];  // +1: the per-patch chains of one warp hit distinct banks
+    __shared__ float s_stat[GATHER_PATCHES_PER_CTA][4];  // mean_rgb, mean_d, var_rgb, var_d
+
+    const int Pp = counts[1];
+    const int pl = threadIdx.x >> 3;
+    const int ty = threadIdx.x & 7;
+    const int p = blockIdx.x * GATHER_PATCHES_PER_CTA + pl;
+    if (blockIdx.x * GATHER_PATCHES_PER_CTA >= Pp) return;  // whole CTA out of range
+    const bool live = p < Pp;
+
+    float val[4][8];
+    if (live) {
+        const int cx = locs[2 * p], cy = locs[2 * p + 1];
+        const float dc = __fdiv_rn((float)depth[(size_t)cy * g.W + cx], 1000.0f);  // exact texel fetch, :253
+        const int a = adaptive_size(g, dc);
+        const int x0 = cx - a / 2, y0 = cy - a / 2;
+        const float step = __fdiv_rn((float)a, (float)g.ps);
+        float fill[4] = {0.f, 0.f, 0.f, 0.f};
+        if (g.fill_random) {
+            // counter-based stand-in for the clock64()-seeded cuRAND draw of patch_extractor.cu:236-244
+            const unsigned long long z = mix64(g.fill_seed + 0x9E3779B97F4A7C15ULL * (unsigned long long)(p + 1));
+            const float r = __fdiv_rn((float)((z & 0xFFFF) % 255), 255.0f);
+            const float gg = __fdiv_rn((float)(((z >> 16) & 0xFFFF) % 255), 255.0f);
+            const float b = __fdiv_rn((float)(((z >> 32) & 0xFFFF) % 255), 255.0f);
+            const float d = __fdiv_rn((float)(((z >> 48) & 0xFFFF) % 255), 255.0f);
+            fill[0] = b; fill[1] = gg; fill[2] = r; fill[3] = d;
+        }
+        const float v = __fadd_rn((float)y0, __fmul_rn((float)ty, step));
+#pragma unroll
+        for (int tx = 0; tx < 8; ++tx) {
+            const float u = __fadd_rn((float)x0, __fmul_rn((float)tx, step));
+            const Bilerp b = make_bilerp(u, v);
+            const bool in_x0 = b.i >= 0 && b.i < g.W, in_x1 = b.i + 1 >= 0 && b.i + 1 < g.W;
+            const bool in_y0 = b.j >= 0 && b.j < g.H, in_y1 = b.j + 1 >= 0 && b.j + 1 < g.H;
+            const size_t o00 = (size_t)b.j * g.W + b.i;
+            const bool k00 = in_x0 && in_y0, k10 = in_x1 && in_y0, k01 = in_x0 && in_y1, k11 = in_x1 && in_y1;
+            const float d00 = k00 ? (float)__ldg(depth + o00) : 0.f;
+            const float d10 = k10 ? (float)__ldg(depth + o00 + 1) : 0.f;
+            const float d01 = k01 ? (float)__ldg(depth + o00 + g.W) : 0.f;
+            const float d11 = k11 ? (float)__ldg(depth + o00 + g.W + 1) : 0.f;
+            const float d = __fdiv_rn(blend(b, d00, d10, d01, d11), 1000.0f);
+            if (d > 0.f) {
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) {
+                    const float t00 = k00 ? __fdiv_rn((float)__ldg(bgr + o00 * 3 + ch), 255.0f) : 0.f;
+                    const float t10 = k10 ? __fdiv_rn((float)__ldg(bgr + (o00 + 1) * 3 + ch), 255.0f) : 0.f;
+                    const float t01 = k01 ? __fdiv_rn((float)__ldg(bgr + (o00 + g.W) * 3 + ch), 255.0f) : 0.f;
+                    const float t11 = k11 ? __fdiv_rn((float)__ldg(bgr + (o00 + g.W + 1) * 3 + ch), 255.0f) : 0.f;
+                    val[ch][tx] = blend(b, t00, t10, t01, t11);
+                }
+                float td = __fadd_rn(__fdiv_rn(__fsub_rn(d, dc), g.range), 0.5f);
+                if (td > 1.0f) td = 1.0f;
+                if (td < 0.0f) td = 0.0f;
+                val[3][tx] = td;
+            } else {
+#pragma unroll
+                for (int ch = 0; ch < 4; ++ch) val[ch][tx] = fill[ch];
+            }
+        }
+    } else {
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch)
+#pragma unroll
+            for (int tx = 0; tx < 8; ++tx) val[ch][tx] = 0.f;
+    }
+
+    // ---- means: terms x/N in parallel, then the reference's sequential accumulation (HFTest.cpp:508-524)
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch)
+#pragma unroll
+        for (int tx = 0; tx < 8; ++tx)
+            s_term[pl][ch * 64 + ty * 8 + tx] = __fdiv_rn(val[ch][tx], ch < 3 ? 192.0f : 64.0f);
+    __syncthreads();
+    if (ty == 0) {
+        float m = 0.f;
+#pragma unroll 16
+        for (int j = 0; j < 192; ++j) m = __fadd_rn(m, s_term[pl][j]);
+        s_stat[pl][0] = m;
+    } else if (ty == 1) {
+        float m = 0.f;
+#pragma unroll 16
+        for (int j = 192; j < 256; ++j) m = __fadd_rn(m, s_term[pl][j]);
+        s_stat[pl][1] = m;
+    }
+    __syncthreads();
+    const float mean_rgb = s_stat[pl][0], mean_d = s_stat[pl][1];
+    // ---- "std" (variance, never sqrt'ed; float d*d) (HFTest.cpp:527-534)
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch)
+#pragma unroll
+        for (int tx = 0; tx < 8; ++tx) {
+            const float d = __fsub_rn(val[ch][tx], ch < 3 ? mean_rgb : mean_d);
+            s_term[pl][ch * 64 + ty * 8 + tx] = __fdiv_rn(__fmul_rn(d, d), ch < 3 ? 192.0f : 64.0f);
+        }
+    __syncthreads();
+    if (ty == 0) {
+        float m = 0.f;
+#pragma unroll 16
+        for (int j = 0; j < 192; ++j) m = __fadd_rn(m, s_term[pl][j]);
+        s_stat[pl][2] = m;
+    } else if (ty == 1) {
+        float m = 0.f;
+#pragma unroll 16
+        for (int j = 192; j < 256; ++j) m = __fadd_rn(m, s_term[pl][j]);
+        s_stat[pl][3] = m;
+    }
+    __syncthreads();
+    if (!live) return;
+    const float lim_rgb = __fmul_rn(3.0f, s_stat[pl][2]), lim_d = __fmul_rn(3.0f, s_stat[pl][3]);
+    // ---- clip to +-3 "std", scale to [0.1, 0.9], quantise (HFTest.cpp:538-565); NaN (lim == 0) -> 0
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) {
+        const float m = ch < 3 ? mean_rgb : mean_d;
+        const float lim = ch < 3 ? lim_rgb : lim_d;
+        uint32_t qb[8];
+#pragma unroll
+        for (int tx = 0; tx < 8; ++tx) {
+            float x = __fsub_rn(val[ch][tx], m);
+            if (x > lim) x = lim;
+            if (x < -lim) x = -lim;
+            x = __fdiv_rn(x, lim);
+            x = __fadd_rn(__fmul_rn(__fadd_rn(x, 1.0f), 0.4f), 0.1f);
+            qb[tx] = (uint32_t)(f2i_x86(__fmul_rn(x, 255.0f)) & 0xFF);
+        }
+        const size_t o = (size_t)p * 256 + ch * 64 + ty * 8;
+        uint32_t pk[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            __nv_bfloat162 h2 = __floats2bfloat162_rn((float)qb[2 * k], (float)qb[2 * k + 1]);
+            pk[k] = *reinterpret_cast<uint32_t*>(&h2);
+        }
+        *reinterpret_cast<uint4*>(a_out + o) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        if (q_out) {
+            const uint32_t lo = qb[0] | (qb[1] << 8) | (qb[2] << 16) | (qb[3] << 24);
+            const uint32_t hi = qb[4] | (qb[5] << 8) | (qb[6] << 16) | (qb[7] << 24);
+            *reinterpret_cast<uint2*>(q_out + o) = make_uint2(lo, hi);
+        }
+    }
+}
+
+}  // namespace hf6d

@@ -1,0 +1,946 @@
+// libhf6d.so: the C ABI of include/hf6d.h.  Owns the model on the device, the per-slot frame workspaces and streams,
+// and launches the stage kernels (gather.cuh, encoder.cuh, forest.cuh, vote.cuh, modes.cuh).
+// There is deliberately no CPU path in this file: without a usable sm_100 device every compute entry point fails.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/hf6d.h"
+#include "common.cuh"
+#include "encoder.cuh"
+#include "forest.cuh"
+#include "gather.cuh"
+#include "model.hpp"
+#include "modes.cuh"
+#include "vote.cuh"
+
+using namespace hf6d;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+constexpr int MAX_YP = 16;    // upper bound for max_yaw_pitch_hypotheses
+constexpr int MAX_ROLL = 8;   // upper bound for max_roll_hypotheses
+
+struct DeviceModel {
+    DevForest f{};
+    // owned allocations
+    std::vector<void*> allocs;
+    // encoder
+    __nv_bfloat16* W[3] = {nullptr, nullptr, nullptr};
+    float* b[3] = {nullptr, nullptr, nullptr};
+    int n_in[3], n_out[3], k_pad[3], n_pad[3], block_n[3];
+    uint8_t* sep_ok = nullptr;
+};
+
+struct Slot {
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaEvent_t ev[HF6D_STAGE_COUNT + 1];
+    bool ev_valid[HF6D_STAGE_COUNT + 1];
+    int launches = 0;
+    // frame
+    uint8_t* bgr = nullptr;
+    uint16_t* depth = nullptr;
+    int* row_count = nullptr;
+    int* counts = nullptr;  // [2] inside the result block
+    int* locs = nullptr;
+    __nv_bfloat16 *A0 = nullptr, *H1 = nullptr, *H2 = nullptr;
+    uint8_t* q_u8 = nullptr;
+    float* feat = nullptr;
+    int* leaf_ord = nullptr;
+    unsigned long long *maps = nullptr, *map_tmp = nullptr;
+    float* blurred = nullptr;
+    unsigned long long* list = nullptr;
+    int* list_n = nullptr;
+    unsigned long long *zacc = nullptr, *ypacc = nullptr, *yptmp = nullptr, *racc = nullptr;
+    float* ypblur = nullptr;
+    // result block (one D2H)
+    uint8_t* res_dev = nullptr;
+    uint8_t* res_host = nullptr;  // pinned
+    EncoderLayerLaunch enc[3];
+    bool busy = false;  // submit/wait bookkeeping
+    int ticket = -1;
+    std::vector<void*> allocs;
+};
+
+struct ResultLayout {
+    size_t counts, centres, active, mode_z, n_peaks, peak_yx, peak_score, records, total;
+};
+
+}  // namespace
+
+struct hf6d_ctx {
+    hf6d_params p{};
+    int device = 0, n_slots = 1, sms = 148;
+    HostForest hf;
+    std::vector<HostLayer> layers;
+    std::vector<hf6d_object> objects;
+    DeviceModel dm;
+    std::vector<Slot> slots;
+    FrameGeom g{};
+    int S = 0;  // accumulator slots = K * HF6D_MAX_CENTRES
+    PoseRegion reg{};
+    ResultLayout rl{};
+    int shard_rank = 0, shard_world = 1;
+    int encoder_mode = 0;
+    int debug_capture = 0;
+    int next_ticket = 0;
+    std::string err;
+    std::mutex mu;
+};
+
+namespace {
+
+int fail(hf6d_ctx* c, int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CU_TRY(c, expr)                                                                              \
+    do {                                                                                             \
+        cudaError_t e_ = (expr);                                                                     \
+        if (e_ != cudaSuccess) return fail(c, HF6D_ECUDA, "%s: %s", #expr, cudaGetErrorString(e_)); \
+    } while (0)
+
+template <class T>
+int dev_alloc(hf6d_ctx* c, std::vector<void*>& owner, T** out, size_t count) {
+    void* p = nullptr;
+    const size_t bytes = std::max<size_t>(count * sizeof(T), 16);
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) return fail(c, HF6D_ENOMEM, "cudaMalloc(%zu bytes): %s", bytes, cudaGetErrorString(e));
+    owner.push_back(p);
+    *out = reinterpret_cast<T*>(p);
+    return HF6D_OK;
+}
+
+template <class T>
+int dev_upload(hf6d_ctx* c, std::vector<void*>& owner, const T** out, const std::vector<T>& v) {
+    T* p = nullptr;
+    int r = dev_alloc(c, owner, &p, v.size());
+    if (r) return r;
+    if (!v.empty()) CU_TRY(c, cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *out = p;
+    return HF6D_OK;
+}
+
+int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+// The reference's roll-separation test (HFTest.cpp:918-921), tabulated with libm for every pair of kept roll bins.
+void build_sep_table(std::vector<uint8_t>& t) {
+    t.assign(361 * 361, 0);
+    for (int a = 0; a <= 360; ++a)
+        for (int b = 0; b <= 360; ++b) {
+            const float prev = (float)(a + 180);
+            const int ry = b + 180;
+            const float dot = (float)(cos(prev / 180.0f * M_PI) * cos(ry / 180.0f * M_PI) +
+                                      sin(prev / 180.0f * M_PI) * sin(ry / 180.0f * M_PI));
+            t[a * 361 + b] = acos(dot) / M_PI * 180.0f > 7 ? 1 : 0;
+        }
+}
+
+int upload_model(hf6d_ctx* c) {
+    DeviceModel& dm = c->dm;
+    const HostForest& hf = c->hf;
+    dm.f.T = hf.T; dm.f.K = hf.K; dm.f.F = hf.F;
+    int r;
+    if ((r = dev_upload(c, dm.allocs, &dm.f.nodes, hf.nodes))) return r;
+    if ((r = dev_upload(c, dm.allocs, &dm.f.root, hf.root))) return r;
+    if ((r = dev_upload(c, dm.allocs, &dm.f.leaf_base, hf.leaf_base))) return r;
+    if ((r = dev_upload(c, dm.allocs, &dm.f.group_off, hf.group_off))) return r;
+    if ((r = dev_upload(c, dm.allocs, &dm.f.groups, hf.groups))) return r;
+    if ((r = dev_upload(c, dm.allocs, &dm.f.ox, hf.ox))) return r;
+    if ((r = dev_upload(c, dm.allocs, &dm.f.oy, hf.oy))) return r;
+    if ((r = dev_upload(c, dm.allocs, &dm.f.oz, hf.oz))) return r;
+    if ((r = dev_upload(c, dm.allocs, &dm.f.yaw, hf.yaw))) return r;
+    if ((r = dev_upload(c, dm.allocs, &dm.f.pitch, hf.pitch))) return r;
+    if ((r = dev_upload(c, dm.allocs, &dm.f.roll, hf.roll))) return r;
+    std::vector<uint8_t> sep;
+    build_sep_table(sep);
+    const uint8_t* sp = nullptr;
+    if ((r = dev_upload(c, dm.allocs, &sp, sep))) return r;
+    dm.sep_ok = const_cast<uint8_t*>(sp);
+
+    // encoder: bf16 weights [n_pad][k_pad], zero padded; 1/255 folded into layer 1 (the A operand holds q itself)
+    for (int l = 0; l < 3; ++l) {
+        const HostLayer& L = c->layers[l];
+        dm.n_in[l] = L.in;
+        dm.n_out[l] = L.out;
+        dm.k_pad[l] = l == 0 ? L.in : dm.n_pad[l - 1];
+        const bool last = l == 2;
+        if (last) {
+            dm.block_n[l] = (L.out % 160 == 0) ? 160 : 256;
+            dm.n_pad[l] = round_up(L.out, dm.block_n[l]);
+        } else {
+            dm.block_n[l] = 256;
+            dm.n_pad[l] = round_up(L.out, 256);
+        }
+        if (dm.k_pad[l] % ENC_BLOCK_K) return fail(c, HF6D_EINVAL, "encoder layer %d: K=%d is not a multiple of 64", l, dm.k_pad[l]);
+        if (dm.n_pad[l] > ENC_MAX_N) return fail(c, HF6D_EINVAL, "encoder layer %d wider than %d", l, ENC_MAX_N);
+        std::vector<__nv_bfloat16> w((size_t)dm.n_pad[l] * dm.k_pad[l], __float2bfloat16(0.f));
+        for (int n = 0; n < L.out; ++n)
+            for (int k = 0; k < L.in; ++k) {
+                float v = L.W[(size_t)n * L.in + k];
+                if (l == 0) v = v / 255.0f;
+                w[(size_t)n * dm.k_pad[l] + k] = __float2bfloat16(v);
+            }
+        std::vector<float> b(dm.n_pad[l], 0.f);
+        for (int n = 0; n < L.out; ++n) b[n] = L.b[n];
+        const __nv_bfloat16* wp = nullptr;
+        const float* bp = nullptr;
+        if ((r = dev_upload(c, dm.allocs, &wp, w))) return r;
+        if ((r = dev_upload(c, dm.allocs, &bp, b))) return r;
+        dm.W[l] = const_cast<__nv_bfloat16*>(wp);
+        dm.b[l] = const_cast<float*>(bp);
+    }
+    return HF6D_OK;
+}
+
+int alloc_slot(hf6d_ctx* c, Slot& s) {
+    const FrameGeom& g = c->g;
+    const int K = c->hf.K, T = c->hf.T, F = c->hf.F, S = c->S;
+    const size_t HW = (size_t)g.W * g.H;
+    int r;
+    CU_TRY(c, cudaStreamCreateWithFlags(&s.own_stream, cudaStreamNonBlocking));
+    s.stream = s.own_stream;
+    for (int i = 0; i <= HF6D_STAGE_COUNT; ++i) {
+        CU_TRY(c, cudaEventCreate(&s.ev[i]));
+        s.ev_valid[i] = false;
+    }
+    if ((r = dev_alloc(c, s.allocs, &s.bgr, HW * 3))) return r;
+    if ((r = dev_alloc(c, s.allocs, &s.depth, HW))) return r;
+    if ((r = dev_alloc(c, s.allocs, &s.row_count, (size_t)g.gh))) return r;
+    if ((r = dev_alloc(c, s.allocs, &s.locs, (size_t)g.cap * 2))) return r;
+    if ((r = dev_alloc(c, s.allocs, &s.A0, (size_t)g.cap * c->dm.k_pad[0]))) return r;
+    if ((r = dev_alloc(c, s.allocs, &s.q_u8, (size_t)g.cap * 256))) return r;
+    if ((r = dev_alloc(c, s.allocs, &s.H1, (size_t)g.cap * c->dm.n_pad[0]))) return r;
+    if ((r = dev_alloc(c, s.allocs, &s.H2, (size_t)g.cap * c->dm.n_pad[1]))) return r;
+    if ((r = dev_alloc(c, s.allocs, &s.feat, (size_t)g.cap * F))) return r;
+    if ((r = dev_alloc(c, s.allocs, &s.leaf_ord, (size_t)g.cap * T))) return r;
+    if ((r = dev_alloc(c, s.allocs, &s.maps, HW * K))) return r;
+    if ((r = dev_alloc(c, s.allocs, &s.map_tmp, HW * K))) return r;
+    if ((r = dev_alloc(c, s.allocs, &s.blurred, HW * K))) return r;
+    const int n_lists = std::max(K, S);
+    if ((r = dev_alloc(c, s.allocs, &s.list, (size_t)n_lists * NMS_LIST_CAP))) return r;
+    if ((r = dev_alloc(c, s.allocs, &s.list_n, (size_t)n_lists))) return r;
+    const size_t yp = (size_t)c->reg.size * c->reg.size;
+    if ((r = dev_alloc(c, s.allocs, &s.zacc, (size_t)S * HF6D_Z_BINS))) return r;
+    if ((r = dev_alloc(c, s.allocs, &s.ypacc, (size_t)S * yp))) return r;
+    if ((r = dev_alloc(c, s.allocs, &s.yptmp, (size_t)S * yp))) return r;
+    if ((r = dev_alloc(c, s.allocs, &s.ypblur, (size_t)S * yp))) return r;
+    if ((r = dev_alloc(c, s.allocs, &s.racc, (size_t)S * MAX_YP * HF6D_POSE_BINS))) return r;
+    if ((r = dev_alloc(c, s.allocs, &s.res_dev, c->rl.total))) return r;
+    CU_TRY(c, cudaMemset(s.res_dev, 0, c->rl.total));
+    CU_TRY(c, cudaMemset(s.leaf_ord, 0xFF, (size_t)g.cap * T * 4));
+    CU_TRY(c, cudaMemset(s.A0, 0, (size_t)g.cap * c->dm.k_pad[0] * 2));
+    CU_TRY(c, cudaMallocHost(reinterpret_cast<void**>(&s.res_host), c->rl.total));
+    memset(s.res_host, 0, c->rl.total);
+    s.counts = reinterpret_cast<int*>(s.res_dev + c->rl.counts);
+
+    // encoder launches: tensor maps over this slot's activation buffers
+    const DeviceModel& dm = c->dm;
+    const void* a_in[3] = {s.A0, s.H1, s.H2};
+    void* outs[3] = {s.H1, s.H2, s.feat};
+    for (int l = 0; l < 3; ++l) {
+        EncoderLayerLaunch& L = s.enc[l];
+        if (!make_bf16_kmajor_map(&L.tmA, a_in[l], (uint64_t)g.cap, (uint64_t)dm.k_pad[l], ENC_BLOCK_M) ||
+            !make_bf16_kmajor_map(&L.tmB, dm.W[l], (uint64_t)dm.n_pad[l], (uint64_t)dm.k_pad[l], (uint32_t)dm.block_n[l]))
+            return fail(c, HF6D_ECUDA, "cuTensorMapEncodeTiled failed for encoder layer %d", l);
+        L.bias = dm.b[l];
+        L.out = outs[l];
+        L.last = l == 2;
+        L.out_ld = L.last ? F : dm.n_pad[l];
+        L.n_valid = L.last ? dm.n_out[l] : dm.n_pad[l];
+        L.K = dm.k_pad[l];
+        L.n_pad = dm.n_pad[l];
+        L.block_n = dm.block_n[l];
+    }
+    return HF6D_OK;
+}
+
+void free_all(hf6d_ctx* c) {
+    for (Slot& s : c->slots) {
+        for (void* p : s.allocs) cudaFree(p);
+        if (s.res_host) cudaFreeHost(s.res_host);
+        for (int i = 0; i <= HF6D_STAGE_COUNT; ++i) if (s.ev[i]) cudaEventDestroy(s.ev[i]);
+        if (s.own_stream) cudaStreamDestroy(s.own_stream);
+    }
+    for (void* p : c->dm.allocs) cudaFree(p);
+}
+
+ObjectSwitches switches_of(const hf6d_ctx* c) {
+    ObjectSwitches sw;
+    memset(&sw, 0, sizeof sw);
+    for (size_t i = 0; i < c->objects.size(); ++i) sw.should_detect[i] = c->objects[i].should_detect ? 1 : 0;
+    return sw;
+}
+
+struct ResView {
+    int* counts;
+    hf6d_centre_list* centres;
+    uint8_t* active;
+    float* mode_z;
+    int* n_peaks;
+    int* peak_yx;
+    float* peak_score;
+    HypRecord* records;
+};
+ResView view_of(const hf6d_ctx* c, uint8_t* base) {
+    ResView v;
+    v.counts = reinterpret_cast<int*>(base + c->rl.counts);
+    v.centres = reinterpret_cast<hf6d_centre_list*>(base + c->rl.centres);
+    v.active = base + c->rl.active;
+    v.mode_z = reinterpret_cast<float*>(base + c->rl.mode_z);
+    v.n_peaks = reinterpret_cast<int*>(base + c->rl.n_peaks);
+    v.peak_yx = reinterpret_cast<int*>(base + c->rl.peak_yx);
+    v.peak_score = reinterpret_cast<float*>(base + c->rl.peak_score);
+    v.records = reinterpret_cast<HypRecord*>(base + c->rl.records);
+    return v;
+}
+
+#define LAUNCH_CHECK(c, s)                                                                                  \
+    do {                                                                                                    \
+        cudaError_t e_ = cudaGetLastError();                                                                \
+        if (e_ != cudaSuccess) return fail(c, HF6D_ECUDA, "kernel launch (%s:%d): %s", __FILE__, __LINE__,  \
+                                           cudaGetErrorString(e_));                                         \
+        ++(s).launches;                                                                                     \
+    } while (0)
+
+int run_stage(hf6d_ctx* c, Slot& s, int stage) {
+    const FrameGeom& g = c->g;
+    const DevForest& f = c->dm.f;
+    const int K = f.K, S = c->S;
+    cudaStream_t st = s.stream;
+    const hf6d_params& p = c->p;
+    ResView rv = view_of(c, s.res_dev);
+    switch (stage) {
+        case HF6D_STAGE_SCAN: {
+            const int blocks = (g.gh + 7) / 8;
+            scan_count_kernel<<<blocks, 256, 0, st>>>(s.depth, g, s.row_count);
+            LAUNCH_CHECK(c, s);
+            scan_compact_kernel<<<blocks, 256, 0, st>>>(s.depth, g, s.row_count, s.locs, s.counts);
+            LAUNCH_CHECK(c, s);
+            break;
+        }
+        case HF6D_STAGE_GATHER: {
+            gather_normalise_kernel<<<g.cap / GATHER_PATCHES_PER_CTA, GATHER_THREADS, 0, st>>>(
+                s.bgr, s.depth, g, s.locs, s.counts, s.A0, c->debug_capture ? s.q_u8 : nullptr);
+            LAUNCH_CHECK(c, s);
+            break;
+        }
+        case HF6D_STAGE_ENCODE: {
+            for (int l = 0; l < 3; ++l) {
+                cudaError_t e = launch_encoder_layer(s.enc[l], s.counts + 1, c->sms, st);
+                if (e != cudaSuccess) return fail(c, HF6D_ECUDA, "encoder layer %d launch: %s", l, cudaGetErrorString(e));
+                ++s.launches;
+            }
+            break;
+        }
+        case HF6D_STAGE_TRAVERSE: {
+            const size_t smem = traverse_smem_bytes(f.F);
+            const int n_owned = (f.T - c->shard_rank + c->shard_world - 1) / c->shard_world;
+            const int per_warp = (n_owned + TRV_WARPS - 1) / TRV_WARPS;
+            const int grid = c->sms * 2;
+            if (per_warp <= 1)
+                traverse_kernel<1><<<grid, TRV_THREADS, smem, st>>>(s.feat, f, s.counts, s.leaf_ord, c->shard_rank, c->shard_world);
+            else if (per_warp <= 2)
+                traverse_kernel<2><<<grid, TRV_THREADS, smem, st>>>(s.feat, f, s.counts, s.leaf_ord, c->shard_rank, c->shard_world);
+            else
+                traverse_kernel<4><<<grid, TRV_THREADS, smem, st>>>(s.feat, f, s.counts, s.leaf_ord, c->shard_rank, c->shard_world);
+            LAUNCH_CHECK(c, s);
+            break;
+        }
+        case HF6D_STAGE_VOTE: {
+            CU_TRY(c, cudaMemsetAsync(s.maps, 0, (size_t)K * g.W * g.H * 8, st));
+            const long long items = (long long)g.cap * f.T;
+            const int blocks = (int)std::min<long long>((items + VOTE_THREADS - 1) / VOTE_THREADS, (long long)c->sms * 8);
+            vote_kernel<<<blocks, VOTE_THREADS, 0, st>>>(f, g, switches_of(c), s.locs, s.depth, s.leaf_ord, s.counts, s.maps);
+            LAUNCH_CHECK(c, s);
+            break;
+        }
+        case HF6D_STAGE_CENTRES: {
+            MapRegion mr{g.H, g.W, 0, 0, g.H, g.W};
+            const int kb = p.centers_blur_size, w = p.centers_nms_wsize;
+            box_rows_kernel<<<dim3((g.H + BLUR_WARPS - 1) / BLUR_WARPS, K), BLUR_WARPS * 32,
+                              (size_t)BLUR_WARPS * (g.W + 1) * 8, st>>>(s.maps, s.map_tmp, mr, kb, nullptr);
+            LAUNCH_CHECK(c, s);
+            box_cols_kernel<<<dim3((g.W + 127) / 128, (g.H + BLUR_COL_CHUNK - 1) / BLUR_COL_CHUNK, K), 128, 0, st>>>(
+                s.map_tmp, s.blurred, mr, kb, 1.0 / ((double)kb * kb), nullptr);
+            LAUNCH_CHECK(c, s);
+            CU_TRY(c, cudaMemsetAsync(s.list_n, 0, (size_t)std::max(K, S) * 4, st));
+            const int n_left = g.W - w + 1, n_top = g.H - 2 * w + 2;
+            if (n_left > 0 && n_top > 0) {
+                nms_tile_kernel<<<dim3((n_left + NMS_TILE - 1) / NMS_TILE, (n_top + NMS_TILE - 1) / NMS_TILE, K),
+                                  NMS_THREADS, nms_smem_bytes(w, w), st>>>(s.blurred, mr, w, w, -1, 0, 0, 0, n_left,
+                                                                           n_top, s.list, s.list_n, nullptr);
+                LAUNCH_CHECK(c, s);
+            }
+            ObjectLimits lim;
+            memset(&lim, 0, sizeof lim);
+            for (int k = 0; k < K; ++k) {
+                lim.max_loc[k] = c->objects[k].max_location_hypotheses;
+                lim.should_detect[k] = c->objects[k].should_detect ? 1 : 0;
+            }
+            select_centres_kernel<<<K, 256, 0, st>>>(s.list, s.list_n, lim, p.min_location_score_ratio, rv.centres, rv.active);
+            LAUNCH_CHECK(c, s);
+            break;
+        }
+        case HF6D_STAGE_POSE: {
+            const size_t yp = (size_t)c->reg.size * c->reg.size;
+            const int max_yp = p.max_yaw_pitch_hypotheses, max_roll = p.max_roll_hypotheses;
+            CU_TRY(c, cudaMemsetAsync(s.zacc, 0, (size_t)S * HF6D_Z_BINS * 8, st));
+            CU_TRY(c, cudaMemsetAsync(s.ypacc, 0, (size_t)S * yp * 8, st));
+            CU_TRY(c, cudaMemsetAsync(s.racc, 0, (size_t)S * MAX_YP * HF6D_POSE_BINS * 8, st));
+            CU_TRY(c, cudaMemsetAsync(s.list_n, 0, (size_t)std::max(K, S) * 4, st));
+            const long long items = (long long)g.cap * f.T;
+            const int blocks = (int)std::min<long long>((items + VOTE_THREADS - 1) / VOTE_THREADS, (long long)c->sms * 8);
+            CentreTable ct{rv.centres, rv.active};
+            const int half_win = p.centers_nms_wsize / 2;
+            pose_accum_kernel<<<blocks, VOTE_THREADS, 0, st>>>(f, g, switches_of(c), s.locs, s.depth, s.leaf_ord, s.counts,
+                                                               ct, half_win, c->reg, s.zacc, s.ypacc);
+            LAUNCH_CHECK(c, s);
+            z_mode_kernel<<<S, 128, 0, st>>>(s.zacc, 20 /* HFTest.cpp:745 */, rv.active, rv.mode_z);
+            LAUNCH_CHECK(c, s);
+            MapRegion mr{HF6D_POSE_BINS, HF6D_POSE_BINS, c->reg.lo, c->reg.lo, c->reg.size, c->reg.size};
+            const int kb = p.pose_blur_size, w = p.pose_nms_wsize;
+            box_rows_kernel<<<dim3((mr.nr + BLUR_WARPS - 1) / BLUR_WARPS, S), BLUR_WARPS * 32,
+                              (size_t)BLUR_WARPS * (mr.nc + 1) * 8, st>>>(s.ypacc, s.yptmp, mr, kb, rv.active);
+            LAUNCH_CHECK(c, s);
+            box_cols_kernel<<<dim3((mr.nc + 127) / 128, (mr.nr + BLUR_COL_CHUNK - 1) / BLUR_COL_CHUNK, S), 128, 0, st>>>(
+                s.yptmp, s.ypblur, mr, kb, 1.0 / ((double)kb * kb), rv.active);
+            LAUNCH_CHECK(c, s);
+            // window origins whose centre lies in [180, 540], intersected with the reference's loop bounds
+            int left0 = std::max(180 - w / 2, 0), left1 = std::min(540 - w / 2, HF6D_POSE_BINS - w);
+            int top0 = left0, top1 = std::min(540 - w / 2, HF6D_POSE_BINS - 2 * w + 1);
+            if (left1 >= left0 && top1 >= top0) {
+                const int n_left = left1 - left0 + 1, n_top = top1 - top0 + 1;
+                nms_tile_kernel<<<dim3((n_left + NMS_TILE - 1) / NMS_TILE, (n_top + NMS_TILE - 1) / NMS_TILE, S),
+                                  NMS_THREADS, nms_smem_bytes(w, w), st>>>(s.ypblur, mr, w, w, 180, 540, left0, top0,
+                                                                           n_left, n_top, s.list, s.list_n, rv.active);
+                LAUNCH_CHECK(c, s);
+            }
+            select_peaks_kernel<<<S, 256, 0, st>>>(s.list, s.list_n, rv.active, max_yp, p.min_yaw_pitch_drop_ratio,
+                                                   rv.n_peaks, rv.peak_yx, rv.peak_score);
+            LAUNCH_CHECK(c, s);
+            PeakTable pk{rv.n_peaks, rv.peak_yx, max_yp};
+            roll_accum_kernel<<<blocks, VOTE_THREADS, 0, st>>>(f, g, switches_of(c), s.locs, s.depth, s.leaf_ord, s.counts,
+                                                               ct, half_win, pk, p.pose_blur_size / 2, s.racc);
+            LAUNCH_CHECK(c, s);
+            roll_modes_kernel<<<dim3(S, max_yp), 128, 0, st>>>(s.racc, rv.n_peaks, max_yp, p.pose_blur_size,
+                                                               p.pose_nms_wsize, max_roll, c->dm.sep_ok, rv.records);
+            LAUNCH_CHECK(c, s);
+            break;
+        }
+        default:
+            return fail(c, HF6D_EINVAL, "unknown stage %d", stage);
+    }
+    return HF6D_OK;
+}
+
+int run_range(hf6d_ctx* c, Slot& s, int first, int last) {
+    if (first < 0 || last >= HF6D_STAGE_COUNT || first > last) return fail(c, HF6D_EINVAL, "bad stage range %d..%d", first, last);
+    s.launches = 0;
+    for (int i = 0; i <= HF6D_STAGE_COUNT; ++i) s.ev_valid[i] = false;
+    CU_TRY(c, cudaEventRecord(s.ev[first], s.stream));
+    s.ev_valid[first] = true;
+    for (int st = first; st <= last; ++st) {
+        int r = run_stage(c, s, st);
+        if (r) return r;
+        CU_TRY(c, cudaEventRecord(s.ev[st + 1], s.stream));
+        s.ev_valid[st + 1] = true;
+    }
+    return HF6D_OK;
+}
+
+int collect_host(hf6d_ctx* c, Slot& s, hf6d_hypothesis* out, int cap, int* n_out) {
+    CU_TRY(c, cudaMemcpyAsync(s.res_host, s.res_dev, c->rl.total, cudaMemcpyDeviceToHost, s.stream));
+    CU_TRY(c, cudaStreamSynchronize(s.stream));
+    ResView rv = view_of(c, s.res_host);
+    const int K = c->hf.K, max_yp = c->p.max_yaw_pitch_hypotheses, max_roll = c->p.max_roll_hypotheses;
+    int n = 0;
+    for (int cls = 0; cls < K; ++cls) {
+        const hf6d_centre_list& cl = rv.centres[cls];
+        for (int k = 0; k < cl.n; ++k) {
+            const int s_ = cls * HF6D_MAX_CENTRES + k;
+            if (!rv.active[s_]) continue;
+            int per_centre = 0;
+            for (int h = 0; h < rv.n_peaks[s_]; ++h)
+                for (int r = 0; r < max_roll; ++r) {
+                    const HypRecord& rec = rv.records[((size_t)s_ * max_yp + h) * max_roll + r];
+                    if (!rec.valid) continue;
+                    if (per_centre >= HF6D_MAX_HYPOTHESES_PER_CENTRE) continue;
+                    ++per_centre;
+                    if (n < cap && out) {
+                        hf6d_hypothesis& o = out[n];
+                        o.cls = cls;
+                        o.cx = cl.c[k].x;
+                        o.cy = cl.c[k].y;
+                        o.z = rv.mode_z[s_];
+                        o.yaw_deg = rv.peak_yx[(s_ * max_yp + h) * 2] - 360;
+                        o.pitch_deg = rv.peak_yx[(s_ * max_yp + h) * 2 + 1] - 360;
+                        o.roll_deg = rec.roll_bin - 360;
+                        o.loc_score = cl.c[k].score;
+                        o.yawpitch_score = rv.peak_score[s_ * max_yp + h];
+                        o.roll_score = rec.roll_score;
+                        hf6d_pose_from_tuple(&c->p, o.cx, o.cy, o.z, o.yaw_deg, o.pitch_deg, o.roll_deg, o.pose);
+                    }
+                    ++n;
+                }
+        }
+    }
+    if (n_out) *n_out = n;
+    return HF6D_OK;
+}
+
+int check_slot(hf6d_ctx* c, int slot) {
+    if (!c) return HF6D_EINVAL;
+    if (slot < 0 || slot >= c->n_slots) return fail(c, HF6D_EINVAL, "slot %d out of range [0,%d)", slot, c->n_slots);
+    return HF6D_OK;
+}
+
+struct BufInfo {
+    void* ptr;
+    size_t bytes;  // capacity
+};
+int buffer_of(hf6d_ctx* c, Slot& s, int what, BufInfo& b) {
+    const FrameGeom& g = c->g;
+    const size_t HW = (size_t)g.W * g.H;
+    switch (what) {
+        case HF6D_BUF_COUNTS: b = {s.counts, 8}; break;
+        case HF6D_BUF_LOCS: b = {s.locs, (size_t)g.cap * 8}; break;
+        case HF6D_BUF_PATCH_U8: b = {s.q_u8, (size_t)g.cap * 256}; break;
+        case HF6D_BUF_FEATURES: b = {s.feat, (size_t)g.cap * c->hf.F * 4}; break;
+        case HF6D_BUF_LEAF_ORD: b = {s.leaf_ord, (size_t)g.cap * c->hf.T * 4}; break;
+        case HF6D_BUF_MAPS: b = {s.maps, HW * c->hf.K * 8}; break;
+        case HF6D_BUF_BLURRED: b = {s.blurred, HW * c->hf.K * 4}; break;
+        case HF6D_BUF_CENTRES: b = {s.res_dev + c->rl.centres, (size_t)c->hf.K * sizeof(hf6d_centre_list)}; break;
+        case HF6D_BUF_FRAME_BGR: b = {s.bgr, HW * 3}; break;
+        case HF6D_BUF_FRAME_DEPTH: b = {s.depth, HW * 2}; break;
+        default: return fail(c, HF6D_EINVAL, "unknown buffer %d", what);
+    }
+    return HF6D_OK;
+}
+
+int finish_create(hf6d_ctx* c, int device, int n_slots) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+        return fail(c, HF6D_ECUDA, "no CUDA device available (libhf6d has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(c, HF6D_EINVAL, "device %d out of range (%d devices)", device, ndev);
+    cudaDeviceProp prop;
+    CU_TRY(c, cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(c, HF6D_ECUDA, "device %d is sm_%d%d; libhf6d is built for sm_100a only", device, prop.major, prop.minor);
+    CU_TRY(c, cudaSetDevice(device));
+    c->device = device;
+    c->sms = prop.multiProcessorCount;
+    c->n_slots = std::max(1, n_slots);
+
+    hf6d_params& p = c->p;
+    p.patch_vox = c->hf.ps;  // forest.txt wins (HFBase.cpp:118-119)
+    p.voxel_m = c->hf.vox;
+    if (p.W <= 0 || p.H <= 0 || p.W > 65535 || p.H > 65535) return fail(c, HF6D_EINVAL, "bad frame size %dx%d", p.W, p.H);
+    if (p.stride <= 0) return fail(c, HF6D_EINVAL, "Stride should be more than 0");
+    if (p.batch_size <= 0) return fail(c, HF6D_EINVAL, "batch_size must be positive");
+    if (p.patch_vox != 8) return fail(c, HF6D_EINVAL, "patch_size_in_voxels = %d: only 8 (the 256-input encoder) is supported", p.patch_vox);
+    if (c->layers.size() != 3) return fail(c, HF6D_EINVAL, "encoder must have 3 layers");
+    if (c->layers[0].in != 4 * p.patch_vox * p.patch_vox)
+        return fail(c, HF6D_EINVAL, "encoder input %d != 4*patch^2 = %d", c->layers[0].in, 4 * p.patch_vox * p.patch_vox);
+    if (c->layers[1].in != c->layers[0].out || c->layers[2].in != c->layers[1].out)
+        return fail(c, HF6D_EINVAL, "encoder layer shapes do not chain");
+    if (c->layers[2].out != c->hf.F)  // HFTest.cpp:595-596
+        return fail(c, HF6D_EINVAL, "Output vector size of caffe net (%d) and Input vector size of forest (%d) do not match", c->layers[2].out, c->hf.F);
+    if (c->hf.F % 4) return fail(c, HF6D_EINVAL, "feature length must be a multiple of 4");
+    if (p.max_yaw_pitch_hypotheses < 0 || p.max_yaw_pitch_hypotheses > MAX_YP || p.max_roll_hypotheses < 0 || p.max_roll_hypotheses > MAX_ROLL)
+        return fail(c, HF6D_EINVAL, "max_yaw_pitch_hypotheses / max_roll_hypotheses out of range");
+    if (p.centers_blur_size < 1 || p.pose_blur_size < 1 || p.centers_nms_wsize < 1 || p.pose_nms_wsize < 1 ||
+        p.centers_nms_wsize > 128 || p.pose_nms_wsize > 128)
+        return fail(c, HF6D_EINVAL, "blur / NMS window sizes out of range");
+
+    FrameGeom& g = c->g;
+    g.W = p.W; g.H = p.H; g.stride = p.stride;
+    g.gw = (p.W + p.stride - 1) / p.stride;
+    g.gh = (p.H + p.stride - 1) / p.stride;
+    g.fx = p.fx; g.fy = p.fy; g.cx = p.cx; g.cy = p.cy;
+    g.ps = p.patch_vox; g.vox = p.voxel_m; g.range = p.max_depth_range_m; g.dist_thr = p.distance_threshold_m;
+    g.fill_random = p.fill_random; g.fill_seed = p.fill_seed; g.batch = p.batch_size;
+    g.cap = round_up(g.gw * g.gh, 128);
+
+    const int K = c->hf.K;
+    c->S = K * HF6D_MAX_CENTRES;
+    // yaw/pitch accumulators: only bins that can influence a kept peak ([180,540] +- nms/2 +- blur/2)
+    const int margin = p.pose_nms_wsize / 2 + p.pose_blur_size / 2 + 1;
+    c->reg.lo = std::max(0, 180 - margin);
+    c->reg.size = std::min(HF6D_POSE_BINS - 1, 540 + margin) - c->reg.lo + 1;
+
+    if ((int)c->objects.size() != K) {
+        c->objects.assign(K, hf6d_object{});
+        for (int k = 0; k < K; ++k) {
+            snprintf(c->objects[k].name, sizeof c->objects[k].name, "object%d", k);
+            c->objects[k].should_detect = 1;
+            c->objects[k].max_location_hypotheses = 12;
+            c->objects[k].instances = 1;
+        }
+    }
+    for (int k = 0; k < K; ++k)
+        if (c->objects[k].max_location_hypotheses < 0 || c->objects[k].max_location_hypotheses > HF6D_MAX_CENTRES)
+            return fail(c, HF6D_EINVAL, "max_location_hypotheses of object %d must be in [0, %d]", k, HF6D_MAX_CENTRES);
+
+    // result block layout
+    ResultLayout& rl = c->rl;
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t at = o; o += (bytes + 15) / 16 * 16; return at; };
+    rl.counts = take(16);
+    rl.centres = take((size_t)K * sizeof(hf6d_centre_list));
+    rl.active = take((size_t)c->S);
+    rl.mode_z = take((size_t)c->S * 4);
+    rl.n_peaks = take((size_t)c->S * 4);
+    rl.peak_yx = take((size_t)c->S * MAX_YP * 2 * 4);
+    rl.peak_score = take((size_t)c->S * MAX_YP * 4);
+    rl.records = take((size_t)c->S * MAX_YP * MAX_ROLL * sizeof(HypRecord));
+    rl.total = o;
+
+    int r = upload_model(c);
+    if (r) return r;
+
+    // opt in to large dynamic shared memory once
+    CU_TRY(c, cudaFuncSetAttribute(traverse_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)traverse_smem_bytes(c->hf.F)));
+    CU_TRY(c, cudaFuncSetAttribute(traverse_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)traverse_smem_bytes(c->hf.F)));
+    CU_TRY(c, cudaFuncSetAttribute(traverse_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)traverse_smem_bytes(c->hf.F)));
+    const size_t nms_smem = std::max(nms_smem_bytes(p.centers_nms_wsize, p.centers_nms_wsize), nms_smem_bytes(p.pose_nms_wsize, p.pose_nms_wsize));
+    CU_TRY(c, cudaFuncSetAttribute(nms_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nms_smem));
+    CU_TRY(c, cudaFuncSetAttribute(box_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)((size_t)BLUR_WARPS * (std::max(p.W, HF6D_POSE_BINS) + 1) * 8)));
+
+    c->slots.resize(c->n_slots);
+    for (Slot& s : c->slots) {
+        memset(s.ev, 0, sizeof s.ev);
+        if ((r = alloc_slot(c, s))) return r;
+    }
+    CU_TRY(c, cudaDeviceSynchronize());
+    return HF6D_OK;
+}
+
+}  // namespace
+
+// ==================================================================================================== C ABI
+extern "C" {
+
+void hf6d_default_params(hf6d_params* p) {
+    memset(p, 0, sizeof *p);
+    p->W = 640; p->H = 480;
+    p->stride = 2;  // generate_scripts.sh:53; HFTest.h:98
+    p->fx = 575.f; p->fy = 575.f; p->cx = 319.5f; p->cy = 239.5f;
+    p->patch_vox = 8; p->voxel_m = 0.005f;
+    p->max_depth_range_m = 0.25f;
+    p->distance_threshold_m = 1.5f;
+    p->fill_random = 1; p->fill_seed = 0;
+    p->batch_size = 100;
+    p->max_yaw_pitch_hypotheses = 7;  // HFTest.h:175-183
+    p->max_roll_hypotheses = 3;
+    p->min_location_score_ratio = 1.0f / 1000.0f;
+    p->min_yaw_pitch_drop_ratio = 1.0f / 1000.0f;
+    p->centers_blur_size = 13; p->centers_nms_wsize = 40;
+    p->pose_blur_size = 35; p->pose_nms_wsize = 35;
+}
+
+const char* hf6d_last_error(const hf6d_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+int hf6d_create(const hf6d_params* p, const char* forest_dir, const char* weights_path, int device, int n_slots,
+                hf6d_ctx** out) {
+    if (!p || !forest_dir || !weights_path || !out) return fail(nullptr, HF6D_EINVAL, "null argument");
+    *out = nullptr;
+    hf6d_ctx* c = new hf6d_ctx();
+    c->p = *p;
+    std::string err;
+    int r = HF6D_OK;
+    if (!load_forest(forest_dir, c->hf, err)) r = fail(nullptr, HF6D_EIO, "%s", err.c_str());
+    else if (!load_weights(weights_path, c->layers, err)) r = fail(nullptr, HF6D_EIO, "%s", err.c_str());
+    else {
+        r = finish_create(c, device, n_slots);
+        if (r) g_create_error = c->err;
+    }
+    if (r) { free_all(c); delete c; return r; }
+    *out = c;
+    return HF6D_OK;
+}
+
+int hf6d_create_from_options(const char* options_path, int W, int H, int device, int n_slots, hf6d_ctx** out) {
+    if (!options_path || !out) return fail(nullptr, HF6D_EINVAL, "null argument");
+    *out = nullptr;
+    HostOptions o;
+    std::string err;
+    if (!load_options(options_path, o, err)) return fail(nullptr, HF6D_EIO, "%s", err.c_str());
+    hf6d_params p;
+    hf6d_default_params(&p);
+    p.W = W; p.H = H;
+    p.stride = o.stride;
+    p.fx = o.fx; p.fy = o.fy; p.cx = o.cx; p.cy = o.cy;
+    p.max_depth_range_m = o.max_depth_range;
+    p.distance_threshold_m = o.distance_threshold;
+    p.fill_random = o.are_objects_segmented ? 0 : 1;  // HFTest.cpp:1235
+    p.batch_size = o.batch_size;
+    hf6d_ctx* c = new hf6d_ctx();
+    c->p = p;
+    c->objects = o.objects;
+    int r = HF6D_OK;
+    if (!load_forest(o.forest_folder, c->hf, err)) r = fail(nullptr, HF6D_EIO, "%s", err.c_str());
+    else if (!load_weights(o.caffe_weights, c->layers, err)) r = fail(nullptr, HF6D_EIO, "%s", err.c_str());
+    else if ((int)o.objects.size() != c->hf.K)  // HFTest.cpp:1186
+        r = fail(nullptr, HF6D_EINVAL, "Number of objects provided in the options file (%zu) does not match the number of classes in the forest (%d)", o.objects.size(), c->hf.K);
+    else {
+        r = finish_create(c, device >= 0 ? device : std::max(o.gpu, 0), n_slots);
+        if (r) g_create_error = c->err;
+    }
+    if (r) { free_all(c); delete c; return r; }
+    *out = c;
+    return HF6D_OK;
+}
+
+void hf6d_destroy(hf6d_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    free_all(c);
+    delete c;
+}
+
+int hf6d_get_params(const hf6d_ctx* c, hf6d_params* out) {
+    if (!c || !out) return HF6D_EINVAL;
+    *out = c->p;
+    return HF6D_OK;
+}
+
+int hf6d_model(const hf6d_ctx* c, hf6d_model_info* out) {
+    if (!c || !out) return HF6D_EINVAL;
+    out->T = c->hf.T; out->K = c->hf.K; out->F = c->hf.F; out->patch_vox = c->hf.ps;
+    out->voxel_m = c->hf.vox;
+    out->n_leaves = (int64_t)c->hf.leaf_id.size();
+    out->n_internal = c->hf.n_internal;
+    out->n_votes = (int64_t)c->hf.ox.size();
+    out->max_depth = c->hf.max_depth;
+    out->dims[0] = c->layers[0].in;
+    for (int l = 0; l < 3; ++l) out->dims[l + 1] = c->layers[l].out;
+    return HF6D_OK;
+}
+
+int hf6d_set_objects(hf6d_ctx* c, const hf6d_object* objs, int n) {
+    if (!c || !objs) return HF6D_EINVAL;
+    if (n != c->hf.K) return fail(c, HF6D_EINVAL, "Number of objects (%d) does not match the number of classes in the forest (%d)", n, c->hf.K);
+    for (int k = 0; k < n; ++k)
+        if (objs[k].max_location_hypotheses < 0 || objs[k].max_location_hypotheses > HF6D_MAX_CENTRES)
+            return fail(c, HF6D_EINVAL, "max_location_hypotheses of object %d must be in [0, %d]", k, HF6D_MAX_CENTRES);
+    c->objects.assign(objs, objs + n);
+    return HF6D_OK;
+}
+
+int hf6d_get_objects(const hf6d_ctx* c, hf6d_object* objs, int cap) {
+    if (!c) return HF6D_EINVAL;
+    for (int k = 0; k < (int)c->objects.size() && k < cap && objs; ++k) objs[k] = c->objects[k];
+    return (int)c->objects.size();
+}
+
+int hf6d_set_fill_seed(hf6d_ctx* c, uint64_t seed) {
+    if (!c) return HF6D_EINVAL;
+    c->p.fill_seed = seed;
+    c->g.fill_seed = seed;
+    return HF6D_OK;
+}
+
+int hf6d_set_tree_shard(hf6d_ctx* c, int rank, int world) {
+    if (!c) return HF6D_EINVAL;
+    if (world < 1 || rank < 0 || rank >= world) return fail(c, HF6D_EINVAL, "bad tree shard %d/%d", rank, world);
+    c->shard_rank = rank;
+    c->shard_world = world;
+    return HF6D_OK;
+}
+
+int hf6d_set_encoder_mode(hf6d_ctx* c, int mode) {
+    if (!c) return HF6D_EINVAL;
+    if (mode != 0) return fail(c, HF6D_EINVAL, "encoder mode %d not available", mode);
+    c->encoder_mode = mode;
+    return HF6D_OK;
+}
+
+int hf6d_set_debug_capture(hf6d_ctx* c, int on) {
+    if (!c) return HF6D_EINVAL;
+    c->debug_capture = on ? 1 : 0;
+    return HF6D_OK;
+}
+
+void* hf6d_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) return nullptr;
+    return p;
+}
+void hf6d_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+int hf6d_upload(hf6d_ctx* c, int slot, const uint8_t* bgr, const uint16_t* depth_mm) {
+    int r = check_slot(c, slot);
+    if (r) return r;
+    if (!bgr || !depth_mm) return fail(c, HF6D_EINVAL, "null frame");
+    Slot& s = c->slots[slot];
+    const size_t HW = (size_t)c->g.W * c->g.H;
+    CU_TRY(c, cudaSetDevice(c->device));
+    CU_TRY(c, cudaMemcpyAsync(s.bgr, bgr, HW * 3, cudaMemcpyHostToDevice, s.stream));
+    CU_TRY(c, cudaMemcpyAsync(s.depth, depth_mm, HW * 2, cudaMemcpyHostToDevice, s.stream));
+    return HF6D_OK;
+}
+
+int hf6d_run(hf6d_ctx* c, int slot, int first_stage, int last_stage) {
+    int r = check_slot(c, slot);
+    if (r) return r;
+    CU_TRY(c, cudaSetDevice(c->device));
+    return run_range(c, c->slots[slot], first_stage, last_stage);
+}
+
+int hf6d_sync(hf6d_ctx* c, int slot) {
+    int r = check_slot(c, slot);
+    if (r) return r;
+    CU_TRY(c, cudaStreamSynchronize(c->slots[slot].stream));
+    return HF6D_OK;
+}
+
+int hf6d_collect(hf6d_ctx* c, int slot, hf6d_hypothesis* out, int cap, int* n_out) {
+    int r = check_slot(c, slot);
+    if (r) return r;
+    CU_TRY(c, cudaSetDevice(c->device));
+    return collect_host(c, c->slots[slot], out, cap, n_out);
+}
+
+int hf6d_detect(hf6d_ctx* c, const uint8_t* bgr, const uint16_t* depth_mm, hf6d_hypothesis* out, int cap, int* n_out) {
+    int r = hf6d_upload(c, 0, bgr, depth_mm);
+    if (r) return r;
+    if ((r = hf6d_run(c, 0, 0, HF6D_STAGE_COUNT - 1))) return r;
+    return hf6d_collect(c, 0, out, cap, n_out);
+}
+
+int hf6d_submit(hf6d_ctx* c, const uint8_t* bgr, const uint16_t* depth_mm, int* ticket) {
+    if (!c || !ticket) return HF6D_EINVAL;
+    const int t = c->next_ticket;
+    const int slot = t % c->n_slots;
+    Slot& s = c->slots[slot];
+    if (s.busy) return fail(c, HF6D_ESTATE, "all %d slots are in flight: hf6d_wait ticket %d first", c->n_slots, s.ticket);
+    int r = hf6d_upload(c, slot, bgr, depth_mm);
+    if (r) return r;
+    if ((r = hf6d_run(c, slot, 0, HF6D_STAGE_COUNT - 1))) return r;
+    CU_TRY(c, cudaMemcpyAsync(s.res_host, s.res_dev, c->rl.total, cudaMemcpyDeviceToHost, s.stream));
+    s.busy = true;
+    s.ticket = t;
+    ++c->next_ticket;
+    *ticket = t;
+    return HF6D_OK;
+}
+
+int hf6d_wait(hf6d_ctx* c, int ticket, hf6d_hypothesis* out, int cap, int* n_out) {
+    if (!c) return HF6D_EINVAL;
+    if (ticket < 0) return fail(c, HF6D_ESTATE, "unknown ticket %d", ticket);
+    Slot& s = c->slots[ticket % c->n_slots];
+    if (!s.busy || s.ticket != ticket) return fail(c, HF6D_ESTATE, "unknown ticket %d", ticket);
+    int r = collect_host(c, s, out, cap, n_out);
+    s.busy = false;
+    return r;
+}
+
+int64_t hf6d_fetch(hf6d_ctx* c, int slot, int what, void* dst, size_t cap_bytes) {
+    int r = check_slot(c, slot);
+    if (r) return r;
+    Slot& s = c->slots[slot];
+    CU_TRY(c, cudaSetDevice(c->device));
+    CU_TRY(c, cudaStreamSynchronize(s.stream));
+    BufInfo b;
+    if ((r = buffer_of(c, s, what, b))) return r;
+    size_t bytes = b.bytes;
+    if (what == HF6D_BUF_LOCS || what == HF6D_BUF_PATCH_U8 || what == HF6D_BUF_FEATURES || what == HF6D_BUF_LEAF_ORD) {
+        int counts[2];
+        CU_TRY(c, cudaMemcpy(counts, s.counts, 8, cudaMemcpyDeviceToHost));
+        const size_t P = (size_t)std::min(counts[0], c->g.cap), Pp = (size_t)std::min(counts[1], c->g.cap);
+        if (what == HF6D_BUF_LOCS) bytes = P * 8;
+        else if (what == HF6D_BUF_PATCH_U8) {
+            if (!c->debug_capture) return fail(c, HF6D_ESTATE, "HF6D_BUF_PATCH_U8 needs hf6d_set_debug_capture(1) before the run");
+            bytes = Pp * 256;
+        } else if (what == HF6D_BUF_FEATURES) bytes = Pp * c->hf.F * 4;
+        else bytes = Pp * c->hf.T * 4;
+    }
+    if (bytes > cap_bytes) return fail(c, HF6D_EINVAL, "destination too small: need %zu bytes, have %zu", bytes, cap_bytes);
+    if (bytes) CU_TRY(c, cudaMemcpy(dst, b.ptr, bytes, cudaMemcpyDeviceToHost));
+    return (int64_t)bytes;
+}
+
+int hf6d_inject(hf6d_ctx* c, int slot, int what, const void* src, size_t bytes) {
+    int r = check_slot(c, slot);
+    if (r) return r;
+    Slot& s = c->slots[slot];
+    CU_TRY(c, cudaSetDevice(c->device));
+    BufInfo b;
+    if ((r = buffer_of(c, s, what, b))) return r;
+    if (bytes > b.bytes) return fail(c, HF6D_EINVAL, "buffer %d holds %zu bytes, got %zu", what, b.bytes, bytes);
+    CU_TRY(c, cudaStreamSynchronize(s.stream));
+    CU_TRY(c, cudaMemcpy(b.ptr, src, bytes, cudaMemcpyHostToDevice));
+    return HF6D_OK;
+}
+
+int hf6d_device_ptr(hf6d_ctx* c, int slot, int what, void** ptr, size_t* bytes) {
+    int r = check_slot(c, slot);
+    if (r) return r;
+    BufInfo b;
+    if ((r = buffer_of(c, c->slots[slot], what, b))) return r;
+    if (ptr) *ptr = b.ptr;
+    if (bytes) *bytes = b.bytes;
+    return HF6D_OK;
+}
+
+int hf6d_set_stream(hf6d_ctx* c, int slot, void* cuda_stream) {
+    int r = check_slot(c, slot);
+    if (r) return r;
+    Slot& s = c->slots[slot];
+    cudaStreamSynchronize(s.stream);
+    s.stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : s.own_stream;
+    return HF6D_OK;
+}
+
+int hf6d_stage_ms(hf6d_ctx* c, int slot, float* ms) {
+    int r = check_slot(c, slot);
+    if (r) return r;
+    Slot& s = c->slots[slot];
+    CU_TRY(c, cudaStreamSynchronize(s.stream));
+    for (int st = 0; st < HF6D_STAGE_COUNT; ++st) {
+        ms[st] = 0.f;
+        if (s.ev_valid[st] && s.ev_valid[st + 1]) cudaEventElapsedTime(&ms[st], s.ev[st], s.ev[st + 1]);
+    }
+    return HF6D_OK;
+}
+
+int hf6d_launch_count(const hf6d_ctx* c, int slot) {
+    if (!c || slot < 0 || slot >= c->n_slots) return HF6D_EINVAL;
+    return c->slots[slot].launches;
+}
+
+void hf6d_pose_from_tuple(const hf6d_params* p, int cx, int cy, float z, int yaw_deg, int pitch_deg, int roll_deg,
+                          float pose[16]) {
+    const float yaw = (float)((float)yaw_deg / 180.0f * M_PI);
+    const float pitch = (float)((float)pitch_deg / 180.0f * M_PI);
+    const float roll = (float)((float)roll_deg / 180.0f * M_PI);
+    float R[9];
+    rot_from_ypr(yaw, pitch, roll, R);
+    const float x = ((float)cx - p->cx) * z / p->fx;
+    const float y = ((float)cy - p->cy) * z / p->fy;
+    pose[0] = R[0]; pose[1] = R[1]; pose[2] = R[2]; pose[3] = x;
+    pose[4] = R[3]; pose[5] = R[4]; pose[6] = R[5]; pose[7] = y;
+    pose[8] = R[6]; pose[9] = R[7]; pose[10] = R[8]; pose[11] = z;
+    pose[12] = 0; pose[13] = 0; pose[14] = 0; pose[15] = 1;
+}
+
+}  // extern "C"

@@ -251,11 +251,16 @@ def _build_tree(rng, feats, max_depth, min_samples, K, votes_per_leaf):
         m = rng.integers(0, 2, nodes.size)
         a = rng.integers(0, F, nodes.size)
         b = rng.integers(0, F, nodes.size)
-        pick = order[s_ + (rng.random(nodes.size) * c_).astype(np.int64)]
-        va = feats[pick, a]
-        vb = feats[pick, b]
-        th = np.where(m == 0, va - vb, va).astype(np.float32)
-        # nudge so the picked sample goes right and a non-trivial share goes left
+        # threshold ~ U(min, max) of the test's values over the node's samples, as the trainer draws it
+        # (HoughForest/src/HFTrain.cpp:365-386: rand()/RAND_MAX * range + min)
+        seg_id = np.repeat(np.arange(nodes.size), c_)
+        seg_smp = order[np.concatenate([np.arange(s, s + c) for s, c in zip(s_, c_)])]
+        seg_val = np.where(m[seg_id] == 0, feats[seg_smp, a[seg_id]] - feats[seg_smp, b[seg_id]],
+                           feats[seg_smp, a[seg_id]]).astype(np.float32)
+        starts_rel = np.concatenate([[0], np.cumsum(c_)[:-1]])
+        vmin = np.minimum.reduceat(seg_val, starts_rel)
+        vmax = np.maximum.reduceat(seg_val, starts_rel)
+        th = (rng.random(nodes.size).astype(np.float32) * (vmax - vmin) + vmin).astype(np.float32)
         base = new_nodes(2 * nodes.size, d + 1)
         lch = base + 2 * np.arange(nodes.size)
         for i, n in enumerate(nodes):
