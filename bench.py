@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""bench.py -- HoughForest test-time detection path on B200 (BASELINE.json metric: frames/s and patch-tree
+traversals/s per 640x480 RGB-D frame).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (libhf6d.so through its C ABI)
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's algorithm on the host cores (CPU oracle)
+
+A "step" is one pass of the hot path (scan -> gather -> encode -> traverse -> vote -> centres -> pose) over one batch
+of BATCH synthetic frames (BASELINE.json configs[1]: 6-object forest, T=4, depth ~20, 16 votes per leaf, 64 cluttered
+640x480 frames).  One JSON line on stdout (rank 0).
+
+Multi-GPU (torchrun, one rank per GPU): frames are independent (the reference's frame loop carries no state,
+HFTest.cpp:1238), so ranks take their own batch -- weak scaling, no data-path collective -- and additionally the
+tree-sharded mode the north star names (trees t % N == rank, vote maps summed with NCCL before mode seeking) is run and
+reported under "tree_sharded".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from object_detector_6d_b200 import synth  # noqa: E402
+
+BATCH = 64            # frames per step (configs[1])
+DISTINCT_FRAMES = 8   # rendered once (the numpy ray-caster takes ~2 s per frame); the batch cycles through them
+K_CLASSES, T_TREES, MAX_DEPTH, VOTES = 6, 4, 20, 16
+ENC_FLOP_PER_PATCH = 2 * (256 * 1500 + 1500 * 1000 + 1000 * 800)
+METRIC = "frames/s (640x480 RGB-D, HoughForest --test hot path)"
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            pk = json.load(f)
+        return dict(hbm=float(pk["hbm_gbs"]), tf_burst=float(pk["bf16_tflops"]),
+                    tf_sustained=float(pk.get("bf16_tflops_sustained", pk["bf16_tflops"])), source="measured")
+    except Exception:
+        return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback")
+
+
+def make_workload(tmpdir: str, n_frames: int, seed0: int = 1, T: int = T_TREES):
+    frames = [synth.render_frame(seed0 + i) for i in range(n_frames)]
+    layers = synth.make_encoder_weights(3)
+    calib = synth.calibration_features(frames[0][0], frames[0][1], layers, n=30000)
+    forest_dir = os.path.join(tmpdir, f"forest_T{T}")
+    stats = synth.write_forest(forest_dir, calib, T=T, K=K_CLASSES, max_depth=MAX_DEPTH, votes_per_leaf=VOTES, seed=7)
+    wpath = os.path.join(tmpdir, "weights.bin")
+    synth.write_weights_raw(wpath, layers)
+    return frames, layers, forest_dir, wpath, stats
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.path = tempfile.mktemp(suffix=".csv")
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[])
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 7:
+                    continue
+                try:
+                    sm.append(float(f[0]))
+                    mx.append(float(f[1]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out = dict(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons),
+                       samples=len(sm))
+        return out
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def run_reference(args, rank, world):
+    """The reference's CPU algorithm for the path (its own binary cannot be built here: SURVEY.md F5), i.e. the oracle
+    port, OpenMP over all host cores.  One step = one frame of the batch (bounded sample)."""
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    cores = os.cpu_count() or 1
+    with tempfile.TemporaryDirectory() as d:
+        frames, layers, forest_dir, _, stats = make_workload(d, min(2, DISTINCT_FRAMES))
+        forest = O.Forest(forest_dir)
+        p = O.default_params(fill_random=1, fill_seed=1)
+        n_trav = 0
+        for i in range(args.warmup):
+            O.detect(forest, frames[i % len(frames)][0], frames[i % len(frames)][1], p, layers)
+        t0 = time.perf_counter()
+        stage = np.zeros(6)
+        for i in range(args.steps):
+            _, (P, Pp), st = O.detect(forest, frames[i % len(frames)][0], frames[i % len(frames)][1], p, layers)
+            n_trav += Pp * forest.T
+            stage += st
+        dt = time.perf_counter() - t0
+    fps = args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(stats, sample="1 frame per step"),
+        "traversals_per_s": n_trav / dt,
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} frames of the batch, one per step, all stages, OpenMP on {cores} threads",
+                         "stage_s_per_frame": {k: float(v / args.steps) for k, v in
+                                               zip(("gather", "normalise", "encode", "traverse", "vote+modes", "total"), stage)}},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(stats, **extra):
+    cfg = {"workload": "configs[1]: 6-object forest, batch of 64 synthetic cluttered 640x480 RGB-D frames",
+           "frame": "640x480", "stride": 2, "classes": K_CLASSES, "trees": T_TREES, "mean_leaf_depth":
+           float(np.mean(stats["mean_depth"])), "votes_per_leaf": VOTES, "leaves": int(sum(stats["leaves"])),
+           "batch_frames": BATCH, "distinct_frames": DISTINCT_FRAMES, "fill": "random (are_objects_segmented: false)",
+           "l2": "per-frame intermediates (0.9 GB) exceed the 126 MB L2; frames cycle through 8 distinct inputs"}
+    cfg.update(extra)
+    return cfg
+
+
+# ------------------------------------------------------------------------------------------------ CUDA arm
+def run_cuda(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from object_detector_6d_b200 import api
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the libhf6d path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    peaks = load_peaks()
+
+    with tempfile.TemporaryDirectory() as d:
+        frames, layers, forest_dir, wpath, stats = make_workload(d, DISTINCT_FRAMES)
+        p = api.default_params(fill_random=1, fill_seed=1)
+        n_slots = 3
+        det = api.Detector(forest_dir, wpath, p, device=local_rank, n_slots=n_slots)
+
+        # ---- device-resident inputs
+        bgr_all = torch.from_numpy(np.stack([f[0] for f in frames])).cuda()
+        dep_all = torch.from_numpy(np.stack([f[1] for f in frames]).view(np.int16)).cuda()
+        stream = torch.cuda.Stream()
+        for s in range(n_slots):
+            det.set_stream(s, stream.cuda_stream)
+
+        def step_resident():
+            launches = 0
+            for i in range(BATCH):
+                s = i % n_slots
+                j = i % DISTINCT_FRAMES
+                det.bind_frame(s, bgr_all[j].data_ptr(), dep_all[j].data_ptr())
+                det.run(s)
+                launches += det.launch_count(s)
+            return launches
+
+        with torch.cuda.stream(stream):
+            for _ in range(args.warmup):
+                step_resident()
+            stream.synchronize()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            sampler = ClockSampler(local_rank) if rank == 0 else None
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            launches = 0
+            for _ in range(args.steps):
+                launches += step_resident()
+            e1.record(stream)
+            stream.synchronize()
+            torch.cuda.synchronize()
+            ms_total = e0.elapsed_time(e1)
+        # per-stage times of the last frames (events recorded inside the timed region, one set per slot)
+        stage_ms = np.mean([det.stage_ms(s) for s in range(n_slots)], axis=0)
+        enc_ms = np.mean([det.encoder_layer_ms(s) for s in range(n_slots)], axis=0)
+        counts = [det.counts(s) for s in range(n_slots)]
+        # patches per frame: exact, from the scan of every distinct frame
+        Pp_frames = []
+        for j in range(DISTINCT_FRAMES):
+            det.bind_frame(0, bgr_all[j].data_ptr(), dep_all[j].data_ptr())
+            det.run(0, api.STAGE_SCAN, api.STAGE_SCAN)
+            Pp_frames.append(det.counts(0)[1])
+        Pp_mean = float(np.mean([Pp_frames[i % DISTINCT_FRAMES] for i in range(BATCH)]))
+        for s in range(n_slots):
+            det.bind_frame(s, None, None)
+            det.set_stream(s, None)
+        if world > 1:
+            t = torch.tensor([ms_total], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_total = float(t.item())
+
+        # ---- end to end through the public API: pinned host frames -> hf6d_submit / hf6d_wait -> host hypotheses
+        pin_b = [api.PinnedArray((480, 640, 3), np.uint8) for _ in range(DISTINCT_FRAMES)]
+        pin_d = [api.PinnedArray((480, 640), np.uint16) for _ in range(DISTINCT_FRAMES)]
+        for j in range(DISTINCT_FRAMES):
+            pin_b[j].array[...] = frames[j][0]
+            pin_d[j].array[...] = frames[j][1]
+
+        def step_e2e():
+            tickets, nh = [], 0
+            for i in range(BATCH):
+                j = i % DISTINCT_FRAMES
+                if len(tickets) == n_slots:
+                    nh += len(det.wait(tickets.pop(0)))
+                tickets.append(det.submit(pin_b[j].array, pin_d[j].array))
+            while tickets:
+                nh += len(det.wait(tickets.pop(0)))
+            return nh
+
+        for _ in range(max(1, args.warmup // 2)):
+            step_e2e()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        n_hyp = 0
+        for _ in range(args.steps):
+            n_hyp += step_e2e()
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([e2e_s], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_s = float(t.item())
+        clocks = sampler.stop() if sampler else None
+        for a in pin_b + pin_d:
+            a.free()
+        d2h = BATCH * det.result_bytes()
+        h2d = BATCH * (640 * 480 * 5)
+
+        # ---- CPU baseline (rank 0, N == 1 only): the oracle port on a bounded sample, all host cores
+        cpu = None
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            from oracle import oracle as O
+            forest = O.Forest(forest_dir)
+            po = O.default_params(fill_random=1, fill_seed=1)
+            O.detect(forest, frames[0][0], frames[0][1], po, layers)  # warm
+            n_s = 2
+            t0 = time.perf_counter()
+            for i in range(n_s):
+                O.detect(forest, frames[i][0], frames[i][1], po, layers)
+            dt = time.perf_counter() - t0
+            cpu = {"value": n_s / dt, "unit": "frames/s", "cores": os.cpu_count() or 1, "kind": "port",
+                   "sample": f"{n_s} frames of the batch, all stages, OpenMP on all host cores"}
+        det.close()
+
+    frames_total = BATCH * args.steps * world
+    sec = ms_total * 1e-3
+    fps = frames_total / sec
+    ms_frame = ms_total / (BATCH * args.steps)
+    # stage rooflines from SURVEY.md §8(d)'s algorithmic work per frame
+    Pp = Pp_mean
+    votes_cast = Pp * T_TREES * VOTES
+    alg = {
+        "scan": (640 * 480 * 2 + Pp * 8, "hbm"),
+        "gather": (640 * 480 * 5 + Pp * 512, "hbm"),                 # frame once + bf16 A operand [P'][256]
+        "encode": (Pp * ENC_FLOP_PER_PATCH, "tensor"),
+        "traverse": (Pp * 800 * 4 + Pp * T_TREES * 4, "hbm"),
+        "vote": (Pp * T_TREES * 4 + votes_cast * 12 + K_CLASSES * 640 * 480 * 8, "hbm"),
+        "centres": (K_CLASSES * 640 * 480 * (8 + 4), "hbm"),
+        "pose": (2 * (Pp * T_TREES * 4 + votes_cast * 12), "hbm"),
+    }
+    stages = {}
+    for name, ms in zip(api.STAGE_NAMES, stage_ms):
+        work, bound = alg[name]
+        if ms <= 0:
+            continue
+        if bound == "tensor":
+            ach = work / (ms * 1e-3) / 1e12
+            stages[name] = {"ms": float(ms), "bound": bound, "achieved": ach, "unit": "TFLOP/s", "frac": ach / peaks["tf_sustained"]}
+        else:
+            ach = work / (ms * 1e-3) / 1e9
+            stages[name] = {"ms": float(ms), "bound": bound, "achieved": ach, "unit": "GB/s", "frac": ach / peaks["hbm"]}
+    # dominant kernel: encoder layer 2 (K=1536 -> N=1024 padded; algorithmic 1500 x 1000)
+    l2_flop = 2.0 * Pp * 1500 * 1000
+    l2_ach = l2_flop / (enc_ms[1] * 1e-3) / 1e12 if enc_ms[1] > 0 else 0.0
+    roofline = {"kernel": "encoder_layer_kernel<256,false> (layer 2: 1500->1000)", "bound": "tensor", "achieved": l2_ach,
+                "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": l2_ach / peaks["tf_sustained"],
+                "traffic": None, "peak_source": peaks["source"] + " (sustained bf16)",
+                "encoder_layer_ms": [float(x) for x in enc_ms],
+                "encoder_stage_tflops": float(Pp * ENC_FLOP_PER_PATCH / (sum(enc_ms) * 1e-3) / 1e12) if sum(enc_ms) > 0 else 0.0}
+    e2e_fps = frames_total / e2e_s
+    line = {
+        "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": workload_config(stats, patches_per_frame=Pp, parallelism=f"frames x{world}" if world > 1 else "1 GPU"),
+        "ms_per_frame": ms_frame, "traversals_per_s": fps * Pp * T_TREES,
+        "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "timing": "wall clock around hf6d_submit/hf6d_wait with pinned host frames, device sync both sides",
+                "hypotheses_per_frame": n_hyp / (BATCH * args.steps)},
+        "gpu_launches": launches,
+        "roofline": roofline, "stages": stages, "cpu_baseline": cpu, "clocks": clocks,
+    }
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        args.warmup = max(args.warmup, 3)
+        run_cuda(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -164,6 +164,9 @@ void hf6d_host_free(void* p);
 /* ---------------------------------------------------------------------------------------------- stage level */
 /* Used by the parity tests, the bench (device-resident timing) and the multi-GPU driver. slot in [0, n_slots). */
 int hf6d_upload(hf6d_ctx* c, int slot, const uint8_t* bgr, const uint16_t* depth_mm); /* async H2D on the slot stream */
+/* Make the slot read a frame that already lives in device memory (caller-owned, same layouts); NULL, NULL restores
+ * the slot's own frame buffer.  hf6d_upload also restores it. */
+int hf6d_bind_frame(hf6d_ctx* c, int slot, const void* d_bgr, const void* d_depth_mm);
 int hf6d_run(hf6d_ctx* c, int slot, int first_stage, int last_stage);                 /* async, inclusive range */
 int hf6d_sync(hf6d_ctx* c, int slot);
 int hf6d_collect(hf6d_ctx* c, int slot, hf6d_hypothesis* out, int cap, int* n_out);   /* D2H + host pose finalise; syncs */
@@ -177,6 +180,10 @@ int hf6d_device_ptr(hf6d_ctx* c, int slot, int what, void** ptr, size_t* bytes);
 int hf6d_set_stream(hf6d_ctx* c, int slot, void* cuda_stream);
 /* Milliseconds per stage of the last hf6d_run on this slot (CUDA events on the slot stream); ms[HF6D_STAGE_COUNT]. */
 int hf6d_stage_ms(hf6d_ctx* c, int slot, float* ms);
+/* Milliseconds of the three encoder layer launches of the last run that included HF6D_STAGE_ENCODE; ms[3]. */
+int hf6d_encoder_layer_ms(hf6d_ctx* c, int slot, float* ms);
+/* Bytes of the per-frame result block that hf6d_collect / hf6d_wait copy device -> host. */
+int64_t hf6d_result_bytes(const hf6d_ctx* c);
 /* Number of kernels the last hf6d_run on this slot launched. */
 int hf6d_launch_count(const hf6d_ctx* c, int slot);
 

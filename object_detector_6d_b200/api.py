@@ -27,7 +27,7 @@ EXPORTS = (
     "hf6d_set_tree_shard", "hf6d_set_encoder_mode", "hf6d_set_debug_capture", "hf6d_detect", "hf6d_submit",
     "hf6d_wait", "hf6d_host_alloc", "hf6d_host_free", "hf6d_upload", "hf6d_run", "hf6d_sync", "hf6d_collect",
     "hf6d_fetch", "hf6d_inject", "hf6d_device_ptr", "hf6d_set_stream", "hf6d_stage_ms", "hf6d_launch_count",
-    "hf6d_pose_from_tuple",
+    "hf6d_pose_from_tuple", "hf6d_bind_frame", "hf6d_encoder_layer_ms", "hf6d_result_bytes",
 )
 
 
@@ -113,6 +113,10 @@ def load():
     L.hf6d_set_stream.argtypes = [vp, i32, vp]
     L.hf6d_stage_ms.argtypes = [vp, i32, C.POINTER(C.c_float)]
     L.hf6d_launch_count.argtypes = [vp, i32]
+    L.hf6d_bind_frame.argtypes = [vp, i32, vp, vp]
+    L.hf6d_result_bytes.argtypes = [vp]
+    L.hf6d_result_bytes.restype = i64
+    L.hf6d_encoder_layer_ms.argtypes = [vp, i32, C.POINTER(C.c_float)]
     L.hf6d_pose_from_tuple.argtypes = [C.POINTER(Params), i32, i32, C.c_float, i32, i32, i32, C.POINTER(C.c_float)]
     L.hf6d_pose_from_tuple.restype = None
     _lib = L
@@ -260,6 +264,16 @@ class Detector:
         self._check_frame(bgr, depth)
         self._ck(self._L.hf6d_upload(self._h, slot, self._ptr(bgr), self._ptr(depth)))
 
+    def bind_frame(self, slot, d_bgr_ptr, d_depth_ptr):
+        """Device-resident frame (raw device pointers, e.g. torch tensor .data_ptr()); (None, None) unbinds."""
+        self._ck(self._L.hf6d_bind_frame(self._h, slot, C.c_void_p(d_bgr_ptr) if d_bgr_ptr else None,
+                                         C.c_void_p(d_depth_ptr) if d_depth_ptr else None))
+
+    def encoder_layer_ms(self, slot=0):
+        ms = (C.c_float * 3)()
+        self._ck(self._L.hf6d_encoder_layer_ms(self._h, slot, ms))
+        return np.array(list(ms), np.float64)
+
     def run(self, slot=0, first=STAGE_SCAN, last=STAGE_POSE):
         self._ck(self._L.hf6d_run(self._h, slot, first, last))
 
@@ -276,6 +290,9 @@ class Detector:
         ms = (C.c_float * STAGE_COUNT)()
         self._ck(self._L.hf6d_stage_ms(self._h, slot, ms))
         return np.array(list(ms), np.float64)
+
+    def result_bytes(self) -> int:
+        return int(self._L.hf6d_result_bytes(self._h))
 
     def launch_count(self, slot=0) -> int:
         return self._ck(self._L.hf6d_launch_count(self._h, slot))

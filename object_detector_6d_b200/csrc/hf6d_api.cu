@@ -49,8 +49,12 @@ struct Slot {
     bool ev_valid[HF6D_STAGE_COUNT + 1];
     int launches = 0;
     // frame
-    uint8_t* bgr = nullptr;
+    uint8_t* bgr = nullptr;       // frame the kernels read: own_bgr or a caller-owned device frame (hf6d_bind_frame)
     uint16_t* depth = nullptr;
+    uint8_t* own_bgr = nullptr;
+    uint16_t* own_depth = nullptr;
+    cudaEvent_t ev_enc[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool ev_enc_valid = false;
     int* row_count = nullptr;
     int* counts = nullptr;  // [2] inside the result block
     int* locs = nullptr;
@@ -221,8 +225,11 @@ int alloc_slot(hf6d_ctx* c, Slot& s) {
         CU_TRY(c, cudaEventCreate(&s.ev[i]));
         s.ev_valid[i] = false;
     }
-    if ((r = dev_alloc(c, s.allocs, &s.bgr, HW * 3))) return r;
-    if ((r = dev_alloc(c, s.allocs, &s.depth, HW))) return r;
+    for (int i = 0; i < 4; ++i) CU_TRY(c, cudaEventCreate(&s.ev_enc[i]));
+    if ((r = dev_alloc(c, s.allocs, &s.own_bgr, HW * 3))) return r;
+    if ((r = dev_alloc(c, s.allocs, &s.own_depth, HW))) return r;
+    s.bgr = s.own_bgr;
+    s.depth = s.own_depth;
     if ((r = dev_alloc(c, s.allocs, &s.row_count, (size_t)g.gh))) return r;
     if ((r = dev_alloc(c, s.allocs, &s.locs, (size_t)g.cap * 2))) return r;
     if ((r = dev_alloc(c, s.allocs, &s.A0, (size_t)g.cap * c->dm.k_pad[0]))) return r;
@@ -277,6 +284,7 @@ void free_all(hf6d_ctx* c) {
         for (void* p : s.allocs) cudaFree(p);
         if (s.res_host) cudaFreeHost(s.res_host);
         for (int i = 0; i <= HF6D_STAGE_COUNT; ++i) if (s.ev[i]) cudaEventDestroy(s.ev[i]);
+        for (int i = 0; i < 4; ++i) if (s.ev_enc[i]) cudaEventDestroy(s.ev_enc[i]);
         if (s.own_stream) cudaStreamDestroy(s.own_stream);
     }
     for (void* p : c->dm.allocs) cudaFree(p);
@@ -343,11 +351,14 @@ int run_stage(hf6d_ctx* c, Slot& s, int stage) {
             break;
         }
         case HF6D_STAGE_ENCODE: {
+            CU_TRY(c, cudaEventRecord(s.ev_enc[0], st));
             for (int l = 0; l < 3; ++l) {
                 cudaError_t e = launch_encoder_layer(s.enc[l], s.counts + 1, c->sms, st);
                 if (e != cudaSuccess) return fail(c, HF6D_ECUDA, "encoder layer %d launch: %s", l, cudaGetErrorString(e));
                 ++s.launches;
+                CU_TRY(c, cudaEventRecord(s.ev_enc[l + 1], st));
             }
+            s.ev_enc_valid = true;
             break;
         }
         case HF6D_STAGE_TRAVERSE: {
@@ -607,9 +618,10 @@ int finish_create(hf6d_ctx* c, int device, int n_slots) {
     rl.active = take((size_t)c->S);
     rl.mode_z = take((size_t)c->S * 4);
     rl.n_peaks = take((size_t)c->S * 4);
-    rl.peak_yx = take((size_t)c->S * MAX_YP * 2 * 4);
-    rl.peak_score = take((size_t)c->S * MAX_YP * 4);
-    rl.records = take((size_t)c->S * MAX_YP * MAX_ROLL * sizeof(HypRecord));
+    const size_t n_yp = (size_t)std::max(1, p.max_yaw_pitch_hypotheses), n_roll = (size_t)std::max(1, p.max_roll_hypotheses);
+    rl.peak_yx = take((size_t)c->S * n_yp * 2 * 4);
+    rl.peak_score = take((size_t)c->S * n_yp * 4);
+    rl.records = take((size_t)c->S * n_yp * n_roll * sizeof(HypRecord));
     rl.total = o;
 
     int r = upload_model(c);
@@ -794,8 +806,32 @@ int hf6d_upload(hf6d_ctx* c, int slot, const uint8_t* bgr, const uint16_t* depth
     Slot& s = c->slots[slot];
     const size_t HW = (size_t)c->g.W * c->g.H;
     CU_TRY(c, cudaSetDevice(c->device));
+    s.bgr = s.own_bgr;
+    s.depth = s.own_depth;
     CU_TRY(c, cudaMemcpyAsync(s.bgr, bgr, HW * 3, cudaMemcpyHostToDevice, s.stream));
     CU_TRY(c, cudaMemcpyAsync(s.depth, depth_mm, HW * 2, cudaMemcpyHostToDevice, s.stream));
+    return HF6D_OK;
+}
+
+int hf6d_bind_frame(hf6d_ctx* c, int slot, const void* d_bgr, const void* d_depth_mm) {
+    int r = check_slot(c, slot);
+    if (r) return r;
+    Slot& s = c->slots[slot];
+    if ((d_bgr == nullptr) != (d_depth_mm == nullptr)) return fail(c, HF6D_EINVAL, "bind both planes or neither");
+    s.bgr = d_bgr ? const_cast<uint8_t*>(static_cast<const uint8_t*>(d_bgr)) : s.own_bgr;
+    s.depth = d_depth_mm ? const_cast<uint16_t*>(static_cast<const uint16_t*>(d_depth_mm)) : s.own_depth;
+    return HF6D_OK;
+}
+
+int hf6d_encoder_layer_ms(hf6d_ctx* c, int slot, float* ms) {
+    int r = check_slot(c, slot);
+    if (r) return r;
+    Slot& s = c->slots[slot];
+    CU_TRY(c, cudaStreamSynchronize(s.stream));
+    for (int l = 0; l < 3; ++l) {
+        ms[l] = 0.f;
+        if (s.ev_enc_valid) cudaEventElapsedTime(&ms[l], s.ev_enc[l], s.ev_enc[l + 1]);
+    }
     return HF6D_OK;
 }
 
@@ -922,6 +958,8 @@ int hf6d_stage_ms(hf6d_ctx* c, int slot, float* ms) {
     }
     return HF6D_OK;
 }
+
+int64_t hf6d_result_bytes(const hf6d_ctx* c) { return c ? (int64_t)c->rl.total : HF6D_EINVAL; }
 
 int hf6d_launch_count(const hf6d_ctx* c, int slot) {
     if (!c || slot < 0 || slot >= c->n_slots) return HF6D_EINVAL;

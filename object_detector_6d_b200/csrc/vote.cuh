@@ -71,7 +71,7 @@ __device__ __forceinline__ void project(const FrameGeom& g, float x, float y, fl
 constexpr int VOTE_THREADS = 256;
 
 __global__ void __launch_bounds__(VOTE_THREADS)
-vote_kernel(DevForest f, FrameGeom g, ObjectSwitches sw, const int* __restrict__ locs,
+vote_kernel(DevForest f, FrameGeom g, const __grid_constant__ ObjectSwitches sw, const int* __restrict__ locs,
             const uint16_t* __restrict__ depth, const int* __restrict__ leaf_ord, const int* __restrict__ counts,
             unsigned long long* __restrict__ maps) {
     const int lane = threadIdx.x & 31;
@@ -114,7 +114,7 @@ struct CentreTable {  // device copy of the per-class centre lists
 };
 
 __global__ void __launch_bounds__(VOTE_THREADS)
-pose_accum_kernel(DevForest f, FrameGeom g, ObjectSwitches sw, const int* __restrict__ locs,
+pose_accum_kernel(DevForest f, FrameGeom g, const __grid_constant__ ObjectSwitches sw, const int* __restrict__ locs,
                   const uint16_t* __restrict__ depth, const int* __restrict__ leaf_ord,
                   const int* __restrict__ counts, CentreTable ct, int half_win, PoseRegion reg,
                   unsigned long long* __restrict__ zacc /*[S][Z_BINS]*/,
@@ -222,7 +222,7 @@ struct PeakTable {
 };
 
 __global__ void __launch_bounds__(VOTE_THREADS)
-roll_accum_kernel(DevForest f, FrameGeom g, ObjectSwitches sw, const int* __restrict__ locs,
+roll_accum_kernel(DevForest f, FrameGeom g, const __grid_constant__ ObjectSwitches sw, const int* __restrict__ locs,
                   const uint16_t* __restrict__ depth, const int* __restrict__ leaf_ord,
                   const int* __restrict__ counts, CentreTable ct, int half_win, PeakTable pk, int half_box,
                   unsigned long long* __restrict__ racc /*[S][max_peaks][POSE_BINS]*/) {

@@ -213,6 +213,50 @@ def write_caffemodel_v1(path: str, layers, names=("encode1", "encode2", "encode3
         f.write(net)
 
 
+
+# ------------------------------------------------------------------------------------------ calibration features
+def calibration_features(bgr, depth, layers, n=8000, cam: Camera = Camera(), seed=0, patch_vox=8, voxel_m=0.005,
+                         max_range=0.25, dist_thr=1.5):
+    """Plausible encoder features for `n` patches of a frame, in plain numpy (nearest-neighbour sampling, fp32 matmul).
+
+    Only used to draw split thresholds for synthetic forests from a realistic feature distribution; it is NOT a
+    restatement of the product path (no bilinear filter, no sequential sums) and nothing checks against it."""
+    rng = np.random.default_rng(seed)
+    H, W = depth.shape
+    ys, xs = np.nonzero((depth > 0) & (depth < dist_thr * 1000))
+    if ys.size == 0:
+        return np.zeros((0, layers[-1][0].shape[0]), np.float32)
+    sel = rng.choice(ys.size, size=min(n, ys.size), replace=False)
+    ys, xs = ys[sel], xs[sel]
+    dc = depth[ys, xs].astype(np.float32) / 1000.0
+    a = (patch_vox * voxel_m / dc * cam.fx).astype(np.int64)
+    ok = (xs - a // 2 >= 0) & (ys - a // 2 >= 0) & (xs - a // 2 + a - 1 < W) & (ys - a // 2 + a - 1 < H) & (a > 0)
+    ys, xs, dc, a = ys[ok], xs[ok], dc[ok], a[ok]
+    t = np.arange(patch_vox, dtype=np.float32)
+    u = (xs - a // 2)[:, None] + (t[None, :] * (a[:, None] / patch_vox)).astype(np.int64)
+    v = (ys - a // 2)[:, None] + (t[None, :] * (a[:, None] / patch_vox)).astype(np.int64)
+    vv, uu = v[:, :, None], u[:, None, :]
+    col = bgr[vv, uu].astype(np.float32) / 255.0  # [n,8,8,3]
+    dd = depth[vv, uu].astype(np.float32) / 1000.0
+    td = np.clip((dd - dc[:, None, None]) / max_range + 0.5, 0, 1)
+    hole = dd <= 0
+    col[hole] = 0
+    td[hole] = 0
+    x = np.concatenate([col.transpose(0, 3, 1, 2).reshape(len(a), -1), td.reshape(len(a), -1)], 1)  # CHW
+    rgb, dch = x[:, :192], x[:, 192:]
+    out = np.empty_like(x)
+    for part, sl in ((rgb, slice(0, 192)), (dch, slice(192, 256))):
+        m = part.mean(1, keepdims=True)
+        var = ((part - m) ** 2).mean(1, keepdims=True)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            z = np.clip(part - m, -3 * var, 3 * var) / (3 * var)
+        z = np.nan_to_num((z + 1) * 0.4 + 0.1, nan=0.0)
+        out[:, sl] = np.floor(z * 255.0) / 255.0
+    h = out.astype(np.float32)
+    for Wm, b in layers:
+        h = 1.0 / (1.0 + np.exp(-(h @ Wm.T + b)))
+    return np.ascontiguousarray(h, np.float32)
+
 # ----------------------------------------------------------------------------------------------------- forests
 def _build_tree(rng, feats, max_depth, min_samples, K, votes_per_leaf):
     """Level-wise random tree over a calibration batch.  Returns dict of node arrays (index 0 = root)."""
@@ -292,7 +336,8 @@ def _build_tree(rng, feats, max_depth, min_samples, K, votes_per_leaf):
         rest = rest / np.maximum(rest.sum(1, keepdims=True), 1e-9) * (1 - p_dom)[:, None]
         probs = rest
     probs[np.arange(nl), dom] = p_dom if K > 1 else 1.0
-    return dict(is_leaf=is_leaf, mode=np.array(mode, np.int32), f1=np.array(f1, np.int32), f2=np.array(f2, np.int32),
+    sample_depth = float(np.mean(np.array(depth_of)[node_of])) if N else 0.0
+    return dict(sample_depth=sample_depth, is_leaf=is_leaf, mode=np.array(mode, np.int32), f1=np.array(f1, np.int32), f2=np.array(f2, np.int32),
                 thr=np.array(thr, np.float32), left=np.array(left, np.int64), right=np.array(right, np.int64),
                 leaf_idx=leaf_idx, dom=dom, probs=probs, n_nodes=n_nodes, votes_per_leaf=votes_per_leaf)
 
@@ -347,13 +392,14 @@ def write_forest(folder: str, calib_features: np.ndarray, T: int = 4, K: int = 6
     feats = np.ascontiguousarray(calib_features, np.float32)
     F = feats.shape[1]
     rng = np.random.default_rng(seed)
-    stats = dict(T=T, K=K, F=F, leaves=[], nodes=[])
+    stats = dict(T=T, K=K, F=F, leaves=[], nodes=[], mean_depth=[])
     for t in range(T):
         tree = _build_tree(rng, feats, max_depth, min_samples, K, votes_per_leaf)
         with open(os.path.join(folder, f"tree{t}.dat"), "wb") as f:
             f.write(_serialise_tree(rng, tree, K))
         stats["leaves"].append(int(tree["leaf_idx"].size))
         stats["nodes"].append(int(tree["n_nodes"]))
+        stats["mean_depth"].append(round(tree["sample_depth"], 2))
     with open(os.path.join(folder, "forest.txt"), "w") as f:
         f.write(f"{T} {K} {F} {patch_vox} {voxel_m:g}\n")  # HFTrain.cpp:1225-1231
     return stats
