@@ -31,7 +31,7 @@ struct DevForest {
     const int32_t* group_off;  // [L+1]
     const VoteGroup* groups;
     const float *ox, *oy, *oz;
-    const int16_t *yaw, *pitch, *roll;
+    const short4* bins;        // per vote: integer-degree yaw, pitch, roll bins (HFTest.cpp:779-780, :863)
 };
 
 // x86 cvttss2si semantics: NaN / out of range -> INT_MIN (CUDA's cast saturates and maps NaN to 0).

@@ -68,6 +68,8 @@ struct Slot {
     int* list_n = nullptr;
     unsigned long long *zacc = nullptr, *ypacc = nullptr, *yptmp = nullptr, *racc = nullptr;
     float* ypblur = nullptr;
+    unsigned long long* rowkey = nullptr;
+    unsigned* win_cnt = nullptr;  // [S][n_groups] window entries per (slot, vote group)
     // result block (one D2H)
     uint8_t* res_dev = nullptr;
     uint8_t* res_host = nullptr;  // pinned
@@ -93,8 +95,11 @@ struct hf6d_ctx {
     std::vector<Slot> slots;
     FrameGeom g{};
     int S = 0;  // accumulator slots = K * HF6D_MAX_CENTRES
-    PoseRegion reg{};
+    PoseRegion reg{};       // yaw/pitch accumulator rectangle
+    MapRect yp_blur{};      // rectangle of the blurred yaw/pitch map that is computed
+    int yp_left0 = 0, yp_nleft = 0, yp_top0 = 0, yp_ntop = 0;  // NMS window origins on the yaw/pitch map
     ResultLayout rl{};
+    int lanes_per_hit = 32;      // lanes that share one (slot, group) pair: 16 when no vote group holds more than 16 votes
     int shard_rank = 0, shard_world = 1;
     int encoder_mode = 0;
     int debug_capture = 0;
@@ -170,9 +175,11 @@ int upload_model(hf6d_ctx* c) {
     if ((r = dev_upload(c, dm.allocs, &dm.f.ox, hf.ox))) return r;
     if ((r = dev_upload(c, dm.allocs, &dm.f.oy, hf.oy))) return r;
     if ((r = dev_upload(c, dm.allocs, &dm.f.oz, hf.oz))) return r;
-    if ((r = dev_upload(c, dm.allocs, &dm.f.yaw, hf.yaw))) return r;
-    if ((r = dev_upload(c, dm.allocs, &dm.f.pitch, hf.pitch))) return r;
-    if ((r = dev_upload(c, dm.allocs, &dm.f.roll, hf.roll))) return r;
+    {
+        std::vector<short4> bins(hf.yaw.size());
+        for (size_t i = 0; i < bins.size(); ++i) bins[i] = make_short4(hf.yaw[i], hf.pitch[i], hf.roll[i], 0);
+        if ((r = dev_upload(c, dm.allocs, &dm.f.bins, bins))) return r;
+    }
     std::vector<uint8_t> sep;
     build_sep_table(sep);
     const uint8_t* sp = nullptr;
@@ -244,11 +251,18 @@ int alloc_slot(hf6d_ctx* c, Slot& s) {
     const int n_lists = std::max(K, S);
     if ((r = dev_alloc(c, s.allocs, &s.list, (size_t)n_lists * NMS_LIST_CAP))) return r;
     if ((r = dev_alloc(c, s.allocs, &s.list_n, (size_t)n_lists))) return r;
-    const size_t yp = (size_t)c->reg.size * c->reg.size;
+    const size_t yp = (size_t)c->reg.ny * c->reg.np;
+    const size_t yp_tmp = (size_t)c->reg.ny * c->yp_blur.nc, yp_out = (size_t)c->yp_blur.nr * c->yp_blur.nc;
     if ((r = dev_alloc(c, s.allocs, &s.zacc, (size_t)S * HF6D_Z_BINS))) return r;
     if ((r = dev_alloc(c, s.allocs, &s.ypacc, (size_t)S * yp))) return r;
-    if ((r = dev_alloc(c, s.allocs, &s.yptmp, (size_t)S * yp))) return r;
-    if ((r = dev_alloc(c, s.allocs, &s.ypblur, (size_t)S * yp))) return r;
+    if ((r = dev_alloc(c, s.allocs, &s.yptmp, (size_t)S * yp_tmp))) return r;
+    if ((r = dev_alloc(c, s.allocs, &s.ypblur, (size_t)S * yp_out))) return r;
+    {
+        const size_t rm_centres = HW * K;  // rowmax scratch: centre maps, or the yaw/pitch maps
+        const size_t rm_pose = (size_t)S * c->yp_blur.nr * std::max(c->yp_nleft, 1);
+        if ((r = dev_alloc(c, s.allocs, &s.rowkey, std::max(rm_centres, rm_pose)))) return r;
+    }
+    if ((r = dev_alloc(c, s.allocs, &s.win_cnt, (size_t)S * c->hf.groups.size()))) return r;
     if ((r = dev_alloc(c, s.allocs, &s.racc, (size_t)S * MAX_YP * HF6D_POSE_BINS))) return r;
     if ((r = dev_alloc(c, s.allocs, &s.res_dev, c->rl.total))) return r;
     CU_TRY(c, cudaMemset(s.res_dev, 0, c->rl.total));
@@ -384,20 +398,26 @@ int run_stage(hf6d_ctx* c, Slot& s, int stage) {
             break;
         }
         case HF6D_STAGE_CENTRES: {
-            MapRegion mr{g.H, g.W, 0, 0, g.H, g.W};
+            const MapDims md{g.H, g.W};
+            const MapRect full{0, 0, g.H, g.W};
             const int kb = p.centers_blur_size, w = p.centers_nms_wsize;
             box_rows_kernel<<<dim3((g.H + BLUR_WARPS - 1) / BLUR_WARPS, K), BLUR_WARPS * 32,
-                              (size_t)BLUR_WARPS * (g.W + 1) * 8, st>>>(s.maps, s.map_tmp, mr, kb, nullptr);
+                              (size_t)BLUR_WARPS * (g.W + 1) * 8, st>>>(s.maps, s.map_tmp, md, full, full, kb, nullptr);
             LAUNCH_CHECK(c, s);
             box_cols_kernel<<<dim3((g.W + 127) / 128, (g.H + BLUR_COL_CHUNK - 1) / BLUR_COL_CHUNK, K), 128, 0, st>>>(
-                s.map_tmp, s.blurred, mr, kb, 1.0 / ((double)kb * kb), nullptr);
+                s.map_tmp, s.blurred, md, full, full, kb, 1.0 / ((double)kb * kb), nullptr);
             LAUNCH_CHECK(c, s);
             CU_TRY(c, cudaMemsetAsync(s.list_n, 0, (size_t)std::max(K, S) * 4, st));
+            // reference loop bounds: lefts 0..cols-wx, tops 0..rows-2*wy+1 (HFTest.cpp:246-249)
             const int n_left = g.W - w + 1, n_top = g.H - 2 * w + 2;
             if (n_left > 0 && n_top > 0) {
-                nms_tile_kernel<<<dim3((n_left + NMS_TILE - 1) / NMS_TILE, (n_top + NMS_TILE - 1) / NMS_TILE, K),
-                                  NMS_THREADS, nms_smem_bytes(w, w), st>>>(s.blurred, mr, w, w, -1, 0, 0, 0, n_left,
-                                                                           n_top, s.list, s.list_n, nullptr);
+                nms_rowmax_kernel<<<dim3((g.H + NMS_ROW_WARPS - 1) / NMS_ROW_WARPS, K), NMS_ROW_WARPS * 32,
+                                    (size_t)NMS_ROW_WARPS * 2 * (n_left + w - 1) * 8, st>>>(s.blurred, s.rowkey, full, w, 0,
+                                                                                             n_left, nullptr);
+                LAUNCH_CHECK(c, s);
+                nms_emit_kernel<<<dim3((n_left + NMS_COL_TW - 1) / NMS_COL_TW, (n_top + NMS_COL_TH - 1) / NMS_COL_TH, K),
+                                  NMS_COL_THREADS, nms_col_smem_bytes(w), st>>>(s.rowkey, full, w, w, 0, n_left, 0, n_top,
+                                                                                s.list, s.list_n, nullptr);
                 LAUNCH_CHECK(c, s);
             }
             ObjectLimits lim;
@@ -411,45 +431,65 @@ int run_stage(hf6d_ctx* c, Slot& s, int stage) {
             break;
         }
         case HF6D_STAGE_POSE: {
-            const size_t yp = (size_t)c->reg.size * c->reg.size;
+            const size_t yp = (size_t)c->reg.ny * c->reg.np;
             const int max_yp = p.max_yaw_pitch_hypotheses, max_roll = p.max_roll_hypotheses;
-            CU_TRY(c, cudaMemsetAsync(s.zacc, 0, (size_t)S * HF6D_Z_BINS * 8, st));
-            CU_TRY(c, cudaMemsetAsync(s.ypacc, 0, (size_t)S * yp * 8, st));
-            CU_TRY(c, cudaMemsetAsync(s.racc, 0, (size_t)S * MAX_YP * HF6D_POSE_BINS * 8, st));
+            // clear only the accumulator slots a class can use (slot = class * HF6D_MAX_CENTRES + centre rank)
+            for (int k = 0; k < K; ++k) {
+                const int n = c->objects[k].should_detect ? c->objects[k].max_location_hypotheses : 0;
+                if (n <= 0) continue;
+                const size_t s0 = (size_t)k * HF6D_MAX_CENTRES;
+                CU_TRY(c, cudaMemsetAsync(s.zacc + s0 * HF6D_Z_BINS, 0, (size_t)n * HF6D_Z_BINS * 8, st));
+                CU_TRY(c, cudaMemsetAsync(s.ypacc + s0 * yp, 0, (size_t)n * yp * 8, st));
+                CU_TRY(c, cudaMemsetAsync(s.racc + s0 * max_yp * HF6D_POSE_BINS, 0, (size_t)n * max_yp * HF6D_POSE_BINS * 8, st));
+                CU_TRY(c, cudaMemsetAsync(s.win_cnt + s0 * c->hf.groups.size(), 0, (size_t)n * c->hf.groups.size() * 4, st));
+            }
             CU_TRY(c, cudaMemsetAsync(s.list_n, 0, (size_t)std::max(K, S) * 4, st));
             const long long items = (long long)g.cap * f.T;
             const int blocks = (int)std::min<long long>((items + VOTE_THREADS - 1) / VOTE_THREADS, (long long)c->sms * 8);
             CentreTable ct{rv.centres, rv.active};
             const int half_win = p.centers_nms_wsize / 2;
-            pose_accum_kernel<<<blocks, VOTE_THREADS, 0, st>>>(f, g, switches_of(c), s.locs, s.depth, s.leaf_ord, s.counts,
-                                                               ct, half_win, c->reg, s.zacc, s.ypacc);
+            const int n_groups = (int)c->hf.groups.size();
+            const size_t cell_bytes = cell_grid_bytes(g.W, g.H, half_win, K);
+            const int table_blocks = c->sms * 8;
+            window_count_kernel<<<blocks, VOTE_THREADS, cell_bytes, st>>>(f, g, switches_of(c), s.locs, s.depth, s.leaf_ord,
+                                                                          s.counts, ct, half_win, n_groups, s.win_cnt, s.zacc);
+            LAUNCH_CHECK(c, s);
+            if (c->lanes_per_hit == 16)
+                yawpitch_from_counts_kernel<16><<<table_blocks, TABLE_THREADS, 0, st>>>(f, s.win_cnt, n_groups, rv.active, S, c->reg, s.ypacc);
+            else
+                yawpitch_from_counts_kernel<32><<<table_blocks, TABLE_THREADS, 0, st>>>(f, s.win_cnt, n_groups, rv.active, S, c->reg, s.ypacc);
             LAUNCH_CHECK(c, s);
             z_mode_kernel<<<S, 128, 0, st>>>(s.zacc, 20 /* HFTest.cpp:745 */, rv.active, rv.mode_z);
             LAUNCH_CHECK(c, s);
-            MapRegion mr{HF6D_POSE_BINS, HF6D_POSE_BINS, c->reg.lo, c->reg.lo, c->reg.size, c->reg.size};
+            const MapDims md{HF6D_POSE_BINS, HF6D_POSE_BINS};
+            const MapRect rin{c->reg.y0, c->reg.p0, c->reg.ny, c->reg.np};
+            const MapRect rout = c->yp_blur;
             const int kb = p.pose_blur_size, w = p.pose_nms_wsize;
-            box_rows_kernel<<<dim3((mr.nr + BLUR_WARPS - 1) / BLUR_WARPS, S), BLUR_WARPS * 32,
-                              (size_t)BLUR_WARPS * (mr.nc + 1) * 8, st>>>(s.ypacc, s.yptmp, mr, kb, rv.active);
+            box_rows_kernel<<<dim3((rin.nr + BLUR_WARPS - 1) / BLUR_WARPS, S), BLUR_WARPS * 32,
+                              (size_t)BLUR_WARPS * (rin.nc + 1) * 8, st>>>(s.ypacc, s.yptmp, md, rin, rout, kb, rv.active);
             LAUNCH_CHECK(c, s);
-            box_cols_kernel<<<dim3((mr.nc + 127) / 128, (mr.nr + BLUR_COL_CHUNK - 1) / BLUR_COL_CHUNK, S), 128, 0, st>>>(
-                s.yptmp, s.ypblur, mr, kb, 1.0 / ((double)kb * kb), rv.active);
+            box_cols_kernel<<<dim3((rout.nc + 127) / 128, (rout.nr + BLUR_COL_CHUNK - 1) / BLUR_COL_CHUNK, S), 128, 0, st>>>(
+                s.yptmp, s.ypblur, md, rin, rout, kb, 1.0 / ((double)kb * kb), rv.active);
             LAUNCH_CHECK(c, s);
-            // window origins whose centre lies in [180, 540], intersected with the reference's loop bounds
-            int left0 = std::max(180 - w / 2, 0), left1 = std::min(540 - w / 2, HF6D_POSE_BINS - w);
-            int top0 = left0, top1 = std::min(540 - w / 2, HF6D_POSE_BINS - 2 * w + 1);
-            if (left1 >= left0 && top1 >= top0) {
-                const int n_left = left1 - left0 + 1, n_top = top1 - top0 + 1;
-                nms_tile_kernel<<<dim3((n_left + NMS_TILE - 1) / NMS_TILE, (n_top + NMS_TILE - 1) / NMS_TILE, S),
-                                  NMS_THREADS, nms_smem_bytes(w, w), st>>>(s.ypblur, mr, w, w, 180, 540, left0, top0,
-                                                                           n_left, n_top, s.list, s.list_n, rv.active);
+            if (c->yp_nleft > 0 && c->yp_ntop > 0) {
+                nms_rowmax_kernel<<<dim3((rout.nr + NMS_ROW_WARPS - 1) / NMS_ROW_WARPS, S), NMS_ROW_WARPS * 32,
+                                    (size_t)NMS_ROW_WARPS * 2 * (c->yp_nleft + w - 1) * 8, st>>>(
+                    s.ypblur, s.rowkey, rout, w, c->yp_left0, c->yp_nleft, rv.active);
+                LAUNCH_CHECK(c, s);
+                nms_emit_kernel<<<dim3((c->yp_nleft + NMS_COL_TW - 1) / NMS_COL_TW, (c->yp_ntop + NMS_COL_TH - 1) / NMS_COL_TH, S),
+                                  NMS_COL_THREADS, nms_col_smem_bytes(w), st>>>(s.rowkey, rout, w, w, c->yp_left0, c->yp_nleft,
+                                                                                c->yp_top0, c->yp_ntop, s.list, s.list_n,
+                                                                                rv.active);
                 LAUNCH_CHECK(c, s);
             }
             select_peaks_kernel<<<S, 256, 0, st>>>(s.list, s.list_n, rv.active, max_yp, p.min_yaw_pitch_drop_ratio,
                                                    rv.n_peaks, rv.peak_yx, rv.peak_score);
             LAUNCH_CHECK(c, s);
             PeakTable pk{rv.n_peaks, rv.peak_yx, max_yp};
-            roll_accum_kernel<<<blocks, VOTE_THREADS, 0, st>>>(f, g, switches_of(c), s.locs, s.depth, s.leaf_ord, s.counts,
-                                                               ct, half_win, pk, p.pose_blur_size / 2, s.racc);
+            if (c->lanes_per_hit == 16)
+                roll_from_counts_kernel<16><<<table_blocks, TABLE_THREADS, 0, st>>>(f, s.win_cnt, n_groups, S, pk, p.pose_blur_size / 2, s.racc);
+            else
+                roll_from_counts_kernel<32><<<table_blocks, TABLE_THREADS, 0, st>>>(f, s.win_cnt, n_groups, S, pk, p.pose_blur_size / 2, s.racc);
             LAUNCH_CHECK(c, s);
             roll_modes_kernel<<<dim3(S, max_yp), 128, 0, st>>>(s.racc, rv.n_peaks, max_yp, p.pose_blur_size,
                                                                p.pose_nms_wsize, max_roll, c->dm.sep_ok, rv.records);
@@ -591,10 +631,51 @@ int finish_create(hf6d_ctx* c, int device, int n_slots) {
 
     const int K = c->hf.K;
     c->S = K * HF6D_MAX_CENTRES;
-    // yaw/pitch accumulators: only bins that can influence a kept peak ([180,540] +- nms/2 +- blur/2)
-    const int margin = p.pose_nms_wsize / 2 + p.pose_blur_size / 2 + 1;
-    c->reg.lo = std::max(0, 180 - margin);
-    c->reg.size = std::min(HF6D_POSE_BINS - 1, 540 + margin) - c->reg.lo + 1;
+    // Yaw/pitch accumulator rectangle: bins that (a) can influence a kept peak -- [180,540] +- nms/2 +- blur/2 -- and
+    // (b) can receive a vote at all: the bounding box of every vote copy of the loaded forest (HFTest.cpp:778-791).
+    {
+        const int bh = p.pose_blur_size / 2 + 1, nh = p.pose_nms_wsize / 2 + 1;
+        const int need_lo = std::max(0, 180 - nh - bh), need_hi = std::min(HF6D_POSE_BINS - 1, 540 + nh + bh);
+        int ylo = INT_MAX, yhi = INT_MIN, plo = INT_MAX, phi = INT_MIN;
+        const HostForest& hf = c->hf;
+        for (size_t i = 0; i < hf.yaw.size(); ++i) {
+            const int yaw = hf.yaw[i], pit = hf.pitch[i];
+            const int sy = yaw < 0 ? -1 : 1, sp = pit < 0 ? -1 : 1;
+            for (int k1 = 0; k1 < 2; ++k1) {
+                const int Y = yaw - sy * k1 * 360 + 360;
+                if (Y >= need_lo && Y <= need_hi) { ylo = std::min(ylo, Y); yhi = std::max(yhi, Y); }
+                const int P = pit - sp * k1 * 360 + 360;
+                if (P >= need_lo && P <= need_hi) { plo = std::min(plo, P); phi = std::max(phi, P); }
+            }
+        }
+        if (ylo > yhi) { ylo = yhi = need_lo; }
+        if (plo > phi) { plo = phi = need_lo; }
+        c->reg = PoseRegion{ylo, yhi - ylo + 1, plo, phi - plo + 1};
+        // blurred values can be non-zero up to blur/2 away from the data; peaks are kept only in [180,540] and the
+        // NMS window reads nms/2 further
+        const int b_lo = std::max(0, 180 - nh), b_hi = std::min(HF6D_POSE_BINS - 1, 540 + nh);
+        const int by0 = std::max(b_lo, ylo - bh), by1 = std::min(b_hi, yhi + bh);
+        const int bp0 = std::max(b_lo, plo - bh), bp1 = std::min(b_hi, phi + bh);
+        c->yp_blur = MapRect{by0, bp0, std::max(1, by1 - by0 + 1), std::max(1, bp1 - bp0 + 1)};
+        // window origins: centres in [180,540] (HFTest.cpp:825-834) that can be non-zero, within the reference's loop
+        // bounds lefts 0..720-w, tops 0..720-2w+1
+        const int w = p.pose_nms_wsize;
+        const int cx0 = std::max(180, bp0), cx1 = std::min(540, bp1), cy0 = std::max(180, by0), cy1 = std::min(540, by1);
+        const int l0 = std::max(cx0 - w / 2, 0), l1 = std::min(cx1 - w / 2, HF6D_POSE_BINS - w);
+        const int t0 = std::max(cy0 - w / 2, 0), t1 = std::min(cy1 - w / 2, HF6D_POSE_BINS - 2 * w + 1);
+        c->yp_left0 = l0; c->yp_nleft = std::max(0, l1 - l0 + 1);
+        c->yp_top0 = t0; c->yp_ntop = std::max(0, t1 - t0 + 1);
+    }
+
+    // (slot, vote group) entry counters of the pose stage
+    {
+        int max_group_votes = 1;
+        for (const VoteGroup& vg : c->hf.groups) max_group_votes = std::max(max_group_votes, vg.vcnt);
+        c->lanes_per_hit = max_group_votes <= 16 ? 16 : 32;
+        if ((long long)c->S * (long long)c->hf.groups.size() > (1LL << 30))
+            return fail(c, HF6D_ENOMEM, "forest too large: %zu vote groups x %d centre slots exceeds the counter table budget",
+                        c->hf.groups.size(), c->S);
+    }
 
     if ((int)c->objects.size() != K) {
         c->objects.assign(K, hf6d_object{});
@@ -631,8 +712,14 @@ int finish_create(hf6d_ctx* c, int device, int n_slots) {
     CU_TRY(c, cudaFuncSetAttribute(traverse_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)traverse_smem_bytes(c->hf.F)));
     CU_TRY(c, cudaFuncSetAttribute(traverse_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)traverse_smem_bytes(c->hf.F)));
     CU_TRY(c, cudaFuncSetAttribute(traverse_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)traverse_smem_bytes(c->hf.F)));
-    const size_t nms_smem = std::max(nms_smem_bytes(p.centers_nms_wsize, p.centers_nms_wsize), nms_smem_bytes(p.pose_nms_wsize, p.pose_nms_wsize));
-    CU_TRY(c, cudaFuncSetAttribute(nms_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nms_smem));
+    CU_TRY(c, cudaFuncSetAttribute(nms_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)std::max(nms_col_smem_bytes(p.centers_nms_wsize), nms_col_smem_bytes(p.pose_nms_wsize))));
+    CU_TRY(c, cudaFuncSetAttribute(nms_rowmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)((size_t)NMS_ROW_WARPS * 2 * (std::max(p.W, HF6D_POSE_BINS) + 128) * 8)));
+    if (cell_grid_bytes(p.W, p.H, p.centers_nms_wsize / 2, K) > 160 * 1024)
+        return fail(c, HF6D_EINVAL, "frame too large for the centre-window lookup grid");
+    CU_TRY(c, cudaFuncSetAttribute(window_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)cell_grid_bytes(p.W, p.H, p.centers_nms_wsize / 2, K)));
     CU_TRY(c, cudaFuncSetAttribute(box_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)((size_t)BLUR_WARPS * (std::max(p.W, HF6D_POSE_BINS) + 1) * 8)));
 

@@ -8,8 +8,8 @@
 //                 running sum), scaled once in double:  (float)((double)S / 65536 * 1/(kx*ky))  -- what cv::blur does
 //                 on CV_32F (double accumulation, single scale) without its summation-order dependence.
 //  * NMS        = separable sliding-window maximum over 64-bit keys  (value bits | ~row | ~col)  computed by window
-//                 doubling in shared memory; the key order reproduces the reference's monotonic-deque tie-breaking
-//                 (leftmost in a row, then topmost), and a window emits only if its maximum sits at the window centre.
+//                 doubling in shared memory (row pass, then column pass); the key order reproduces the reference's
+//                 monotonic-deque tie-breaking, and a window emits only if its maximum sits at the window centre.
 //                 The reference's loop-bound quirk (the vertical pass stops at rows-wy, so the bottom wy-1 window rows
 //                 are never produced) is kept.
 //  * top-N      = block-wide selection on a sort key (score desc, then emission order x-major).
@@ -24,50 +24,53 @@ __host__ __device__ __forceinline__ int reflect101(int i, int n) {  // cv::BORDE
     return i;
 }
 
-// A rectangular region [r0, r0+nr) x [c0, c0+nc) of a (rows x cols) map, stored densely (nr x nc) per map.
-struct MapRegion {
-    int rows, cols;  // full (virtual) map
+// A rectangle [r0, r0+nr) x [c0, c0+nc) of a virtual (rows x cols) map, stored densely (nr x nc) per map.  Cells of the
+// virtual map outside the rectangle are exactly zero (no vote can land there), so reads outside return 0.
+struct MapRect {
     int r0, c0, nr, nc;
+};
+struct MapDims {
+    int rows, cols;
 };
 
 // ------------------------------------------------------------------------------------------------ box blur
 constexpr int BLUR_WARPS = 4;
 
-// tmp[m][r][c] = sum_k acc[m][r][reflect(c - kx/2 + k)]   (region coordinates; out-of-region terms count as 0)
+// tmp[m][r][c] = sum_k acc[m][r][reflect(c - kx/2 + k)]   for r in in.rows, c in out.cols  (tmp is in.nr x out.nc)
 __global__ void __launch_bounds__(BLUR_WARPS * 32)
-box_rows_kernel(const unsigned long long* __restrict__ acc, unsigned long long* __restrict__ tmp, MapRegion mr, int kx,
-                const uint8_t* __restrict__ map_active) {
-    extern __shared__ unsigned long long s_pre[];  // [BLUR_WARPS][nc + 1]
+box_rows_kernel(const unsigned long long* __restrict__ acc, unsigned long long* __restrict__ tmp, MapDims md, MapRect in,
+                MapRect out, int kx, const uint8_t* __restrict__ map_active) {
+    extern __shared__ unsigned long long s_pre[];  // [BLUR_WARPS][in.nc + 1]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m = blockIdx.y;
     if (map_active && !map_active[m]) return;
     const int r = blockIdx.x * BLUR_WARPS + warp;
-    if (r >= mr.nr) return;
-    unsigned long long* pre = s_pre + (size_t)warp * (mr.nc + 1);
-    const unsigned long long* src = acc + ((size_t)m * mr.nr + r) * mr.nc;
+    if (r >= in.nr) return;
+    unsigned long long* pre = s_pre + (size_t)warp * (in.nc + 1);
+    const unsigned long long* src = acc + ((size_t)m * in.nr + r) * in.nc;
     unsigned long long carry = 0;
     if (lane == 0) pre[0] = 0;
-    for (int c0 = 0; c0 < mr.nc; c0 += 32) {
+    for (int c0 = 0; c0 < in.nc; c0 += 32) {
         const int c = c0 + lane;
-        unsigned long long v = c < mr.nc ? src[c] : 0ull;
+        unsigned long long v = c < in.nc ? src[c] : 0ull;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const unsigned long long n = __shfl_up_sync(0xffffffffu, v, o);
             if (lane >= o) v += n;
         }
-        if (c < mr.nc) pre[c + 1] = carry + v;
+        if (c < in.nc) pre[c + 1] = carry + v;
         carry += __shfl_sync(0xffffffffu, v, 31);
     }
     __syncwarp();
-    auto seg = [&](int a, int b) -> unsigned long long {  // sum over global columns [a, b], clipped to the region
-        a = max(a, mr.c0);
-        b = min(b, mr.c0 + mr.nc - 1);
-        return b >= a ? pre[b - mr.c0 + 1] - pre[a - mr.c0] : 0ull;
+    auto seg = [&](int a, int b) -> unsigned long long {  // sum over global columns [a, b], clipped to the input rectangle
+        a = max(a, in.c0);
+        b = min(b, in.c0 + in.nc - 1);
+        return b >= a ? pre[b - in.c0 + 1] - pre[a - in.c0] : 0ull;
     };
-    unsigned long long* dst = tmp + ((size_t)m * mr.nr + r) * mr.nc;
-    const int n = mr.cols;
-    for (int c = lane; c < mr.nc; c += 32) {
-        const int a = mr.c0 + c - kx / 2, b = a + kx - 1;
+    unsigned long long* dst = tmp + ((size_t)m * in.nr + r) * out.nc;
+    const int n = md.cols;
+    for (int c = lane; c < out.nc; c += 32) {
+        const int a = out.c0 + c - kx / 2, b = a + kx - 1;
         unsigned long long s;
         if (n > 1 && a > -n && b < 2 * n - 1) {
             s = seg(max(a, 0), min(b, n - 1));
@@ -81,125 +84,132 @@ box_rows_kernel(const unsigned long long* __restrict__ acc, unsigned long long* 
     }
 }
 
-// out[m][r][c] = (float)( (double)(sum_k tmp[m][reflect(r - ky/2 + k)][c]) / 65536 * scale )
-constexpr int BLUR_COL_CHUNK = 16;
+// out[m][r][c] = (float)( (double)(sum_k tmp[m][reflect(r - ky/2 + k)][c]) / 65536 * scale )  for (r, c) in out
+constexpr int BLUR_COL_CHUNK = 32;
 __global__ void __launch_bounds__(128)
-box_cols_kernel(const unsigned long long* __restrict__ tmp, float* __restrict__ out, MapRegion mr, int ky, double scale,
-                const uint8_t* __restrict__ map_active) {
+box_cols_kernel(const unsigned long long* __restrict__ tmp, float* __restrict__ dst_all, MapDims md, MapRect in,
+                MapRect out, int ky, double scale, const uint8_t* __restrict__ map_active) {
     const int m = blockIdx.z;
     if (map_active && !map_active[m]) return;
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     const int rbeg = blockIdx.y * BLUR_COL_CHUNK;
-    if (c >= mr.nc || rbeg >= mr.nr) return;
-    const unsigned long long* src = tmp + (size_t)m * mr.nr * mr.nc + c;
-    float* dst = out + (size_t)m * mr.nr * mr.nc + c;
-    const int n = mr.rows;
-    auto at = [&](int gr) -> unsigned long long {  // global row, reflected; out-of-region rows count as 0
-        const int rr = reflect101(gr, n) - mr.r0;
-        return (rr >= 0 && rr < mr.nr) ? src[(size_t)rr * mr.nc] : 0ull;
+    if (c >= out.nc || rbeg >= out.nr) return;
+    const unsigned long long* src = tmp + (size_t)m * in.nr * out.nc + c;
+    float* dst = dst_all + (size_t)m * out.nr * out.nc + c;
+    const int n = md.rows;
+    auto at = [&](int gr) -> unsigned long long {  // global row, reflected; rows outside the input rectangle are zero
+        const int rr = reflect101(gr, n) - in.r0;
+        return (rr >= 0 && rr < in.nr) ? src[(size_t)rr * out.nc] : 0ull;
     };
-    const int rend = min(rbeg + BLUR_COL_CHUNK, mr.nr);
+    const int rend = min(rbeg + BLUR_COL_CHUNK, out.nr);
     unsigned long long s = 0;
     {
-        const int a = mr.r0 + rbeg - ky / 2;
+        const int a = out.r0 + rbeg - ky / 2;
         for (int k = 0; k < ky; ++k) s += at(a + k);
     }
     for (int r = rbeg; r < rend; ++r) {
-        dst[(size_t)r * mr.nc] = (float)(((double)s / 65536.0) * scale);
-        const int a = mr.r0 + r - ky / 2;
+        dst[(size_t)r * out.nc] = (float)(((double)s / 65536.0) * scale);
+        const int a = out.r0 + r - ky / 2;
         s += at(a + ky);
         s -= at(a);
     }
 }
 
 // ------------------------------------------------------------------------------------------------ NMS
-constexpr int NMS_TILE = 32;
-constexpr int NMS_THREADS = 256;
+// Separable sliding-window maximum over 64-bit keys  (value bits | ~row | ~col).  Values are >= 0, so float bits order
+// like unsigned integers; ~row / ~col make the maximum pick the topmost row, then the leftmost column among equal
+// values -- the element the reference's two monotonic deques keep at their front (HFTest.cpp:232-262).
+//   1. rowkey[r][left] = max key of in[r][left .. left+wx-1]         one warp per row, window doubling in shared memory
+//   2. key(left, top)  = max of rowkey[top .. top+wy-1][left]        32 x 64 origins per CTA, doubling along y;
+//      the window emits iff its value != 0 and the winning element is the window centre.
 constexpr int NMS_LIST_CAP = 4096;
+constexpr int NMS_ROW_WARPS = 4;
 
 __device__ __forceinline__ unsigned long long nms_key(float v, int gy, int gx) {
     return ((unsigned long long)__float_as_uint(v) << 32) | ((unsigned long long)(0xFFFFu - (unsigned)gy) << 16) |
            (unsigned long long)(0xFFFFu - (unsigned)gx);
 }
 
-inline size_t nms_smem_bytes(int wx, int wy) { return (size_t)(NMS_TILE + wx - 1) * (NMS_TILE + wy - 1) * 8 * 2; }
-
-// in: float [M][nr][nc] (region of a rows x cols map).  Window origins (left, top) in global coordinates:
-//   left in [0, cols-wx], top in [0, rows-2*wy+1]  (reference loop bounds), further clipped to centres inside
-//   [keep_lo, keep_hi]^2 when keep_lo >= 0.  Emits sort keys (score | ~x | ~y) into list[m].
-__global__ void __launch_bounds__(NMS_THREADS)
-nms_tile_kernel(const float* __restrict__ in, MapRegion mr, int wx, int wy, int keep_lo, int keep_hi, int left0,
-                int top0, int n_left, int n_top, unsigned long long* __restrict__ list, int* __restrict__ list_n,
-                const uint8_t* __restrict__ map_active) {
-    extern __shared__ unsigned long long s_keys[];
-    const int m = blockIdx.z;
+// in: float [M][R.nr][R.nc]; rowkey: u64 [M][R.nr][n_left] for window lefts left0 .. left0+n_left-1 (global coords)
+__global__ void __launch_bounds__(NMS_ROW_WARPS * 32)
+nms_rowmax_kernel(const float* __restrict__ in, unsigned long long* __restrict__ rowkey, MapRect R, int wx, int left0,
+                  int n_left, const uint8_t* __restrict__ map_active) {
+    extern __shared__ unsigned long long s_row[];  // [NMS_ROW_WARPS][2][span], span = n_left + wx - 1
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m = blockIdx.y;
     if (map_active && !map_active[m]) return;
-    const int tw = NMS_TILE + wx - 1, th = NMS_TILE + wy - 1;
-    unsigned long long* A = s_keys;
-    unsigned long long* B = s_keys + (size_t)tw * th;
-    const int left_base = left0 + blockIdx.x * NMS_TILE, top_base = top0 + blockIdx.y * NMS_TILE;
-    const float* src = in + (size_t)m * mr.nr * mr.nc;
-    for (int i = threadIdx.x; i < tw * th; i += NMS_THREADS) {
-        const int y = i / tw, x = i % tw;
-        const int gy = top_base + y, gx = left_base + x;
-        const int ry = gy - mr.r0, rx = gx - mr.c0;
-        unsigned long long k = 0;
-        if (gy < mr.rows && gx < mr.cols && ry >= 0 && ry < mr.nr && rx >= 0 && rx < mr.nc)
-            k = nms_key(src[(size_t)ry * mr.nc + rx], gy, gx);
-        A[i] = k;
+    const int r = blockIdx.x * NMS_ROW_WARPS + warp;
+    if (r >= R.nr) return;
+    const int span = n_left + wx - 1;
+    unsigned long long* A = s_row + (size_t)warp * 2 * span;
+    unsigned long long* B = A + span;
+    const float* src = in + ((size_t)m * R.nr + r) * R.nc;
+    const int gy = R.r0 + r;
+    for (int x = lane; x < span; x += 32) {
+        const int gx = left0 + x, rc = gx - R.c0;
+        A[x] = nms_key((rc >= 0 && rc < R.nc) ? src[rc] : 0.f, gy, gx);
     }
-    __syncthreads();
-    // horizontal windows of wx by doubling: after the loop A[y][x] = max over [x, x+p)
+    __syncwarp();
     int p = 1;
     while (p * 2 <= wx) {
-        for (int i = threadIdx.x; i < tw * th; i += NMS_THREADS) {
-            const int x = i % tw;
-            unsigned long long k = A[i];
-            if (x + p < tw) k = max(k, A[i + p]);
-            B[i] = k;
-        }
-        __syncthreads();
+        for (int x = lane; x < span; x += 32) B[x] = x + p < span ? max(A[x], A[x + p]) : A[x];
+        __syncwarp();
         unsigned long long* t = A; A = B; B = t;
         p *= 2;
     }
-    for (int i = threadIdx.x; i < tw * th; i += NMS_THREADS) {
-        const int x = i % tw;
-        unsigned long long k = A[i];
-        if (x + (wx - p) < tw) k = max(k, A[i + (wx - p)]);
-        B[i] = k;  // valid for x < NMS_TILE
+    unsigned long long* dst = rowkey + ((size_t)m * R.nr + r) * n_left;
+    for (int x = lane; x < n_left; x += 32) dst[x] = max(A[x], A[x + (wx - p)]);
+}
+
+constexpr int NMS_COL_TW = 32;   // window origins per CTA in x
+constexpr int NMS_COL_TH = 64;   // and in y
+constexpr int NMS_COL_THREADS = 256;
+inline size_t nms_col_smem_bytes(int wy) { return (size_t)(NMS_COL_TH + wy - 1) * NMS_COL_TW * 8 * 2; }
+
+// Window origins (left, top) in global coordinates: left in [left0, left0+n_left), top in [top0, top0+n_top).
+// Rows outside the rectangle R are zero.  Emits sort keys (score | ~x | ~y) into list[m].
+__global__ void __launch_bounds__(NMS_COL_THREADS)
+nms_emit_kernel(const unsigned long long* __restrict__ rowkey, MapRect R, int wx, int wy, int left0, int n_left,
+                int top0, int n_top, unsigned long long* __restrict__ list, int* __restrict__ list_n,
+                const uint8_t* __restrict__ map_active) {
+    extern __shared__ unsigned long long s_col[];
+    const int m = blockIdx.z;
+    if (map_active && !map_active[m]) return;
+    const int th = NMS_COL_TH + wy - 1;
+    unsigned long long* A = s_col;
+    unsigned long long* B = s_col + (size_t)th * NMS_COL_TW;
+    const int lx0 = blockIdx.x * NMS_COL_TW, ty0 = blockIdx.y * NMS_COL_TH;
+    const unsigned long long* rk = rowkey + (size_t)m * R.nr * n_left;
+    for (int i = threadIdx.x; i < th * NMS_COL_TW; i += NMS_COL_THREADS) {
+        const int y = i / NMS_COL_TW, x = i % NMS_COL_TW;
+        const int rr = top0 + ty0 + y - R.r0, lx = lx0 + x;
+        A[i] = (rr >= 0 && rr < R.nr && lx < n_left) ? rk[(size_t)rr * n_left + lx] : 0ull;
     }
     __syncthreads();
-    { unsigned long long* t = A; A = B; B = t; }
-    // vertical windows of wy
-    p = 1;
+    int p = 1;
     while (p * 2 <= wy) {
-        for (int i = threadIdx.x; i < tw * th; i += NMS_THREADS) {
-            const int y = i / tw;
-            unsigned long long k = A[i];
-            if (y + p < th) k = max(k, A[i + p * tw]);
-            B[i] = k;
+        for (int i = threadIdx.x; i < th * NMS_COL_TW; i += NMS_COL_THREADS) {
+            const int y = i / NMS_COL_TW;
+            B[i] = y + p < th ? max(A[i], A[i + p * NMS_COL_TW]) : A[i];
         }
         __syncthreads();
         unsigned long long* t = A; A = B; B = t;
         p *= 2;
     }
-    for (int i = threadIdx.x; i < NMS_TILE * NMS_TILE; i += NMS_THREADS) {
-        const int y = i / NMS_TILE, x = i % NMS_TILE;
-        const int left = left_base + x, top = top_base + y;
-        if (left >= left0 + n_left || top >= top0 + n_top) continue;
-        unsigned long long k = A[y * tw + x];
-        if (y + (wy - p) < th) k = max(k, A[(y + (wy - p)) * tw + x]);
+    for (int i = threadIdx.x; i < NMS_COL_TH * NMS_COL_TW; i += NMS_COL_THREADS) {
+        const int y = i / NMS_COL_TW, x = i % NMS_COL_TW;
+        if (lx0 + x >= n_left || ty0 + y >= n_top) continue;
+        const unsigned long long k = max(A[y * NMS_COL_TW + x], A[(y + (wy - p)) * NMS_COL_TW + x]);
         const unsigned vb = (unsigned)(k >> 32);
+        if (vb == 0u) continue;
         const int gy = 0xFFFF - (int)((k >> 16) & 0xFFFFu), gx = 0xFFFF - (int)(k & 0xFFFFu);
-        const int ccx = left + wx / 2, ccy = top + wy / 2;
-        if (vb != 0u && gx == ccx && gy == ccy) {
-            if (keep_lo >= 0 && (ccx < keep_lo || ccx > keep_hi || ccy < keep_lo || ccy > keep_hi)) continue;
-            const int idx = atomicAdd(list_n + m, 1);
-            if (idx < NMS_LIST_CAP)
-                list[(size_t)m * NMS_LIST_CAP + idx] = ((unsigned long long)vb << 32) |
-                                                       ((unsigned long long)(0xFFFFu - (unsigned)ccx) << 16) |
-                                                       (unsigned long long)(0xFFFFu - (unsigned)ccy);
-        }
+        const int ccx = left0 + lx0 + x + wx / 2, ccy = top0 + ty0 + y + wy / 2;
+        if (gx != ccx || gy != ccy) continue;
+        const int idx = atomicAdd(list_n + m, 1);
+        if (idx < NMS_LIST_CAP)
+            list[(size_t)m * NMS_LIST_CAP + idx] = ((unsigned long long)vb << 32) |
+                                                   ((unsigned long long)(0xFFFFu - (unsigned)ccx) << 16) |
+                                                   (unsigned long long)(0xFFFFu - (unsigned)ccy);
     }
 }
 
