@@ -151,6 +151,22 @@ int hf6d_set_tree_shard(hf6d_ctx* c, int rank, int world);
 int hf6d_set_encoder_mode(hf6d_ctx* c, int mode);
 int hf6d_set_debug_capture(hf6d_ctx* c, int on); /* keep HF6D_BUF_PATCH_U8 */
 
+/* ---------------------------------------------------------------------------------------------- host-only helpers */
+/* These three touch no GPU: they parse and validate the model artefacts exactly as hf6d_create* does (same loaders), so
+ * the CLI can report a bad options file / forest / weights file before it selects a device, and the CPU test-suite can
+ * cover the format readers.  On failure the message is available from hf6d_last_error(NULL). */
+typedef struct {
+    hf6d_params params;         /* Options fields mapped onto hf6d_params (W, H left at the defaults 640 x 480) */
+    int32_t gpu;                /* Options.gpu (-1 = unset) */
+    int32_t n_objects;          /* number of object_options blocks */
+    char forest_folder[1024];   /* Options.forest_folder */
+    char caffe_weights[1024];   /* Options.caffe_weights */
+    char caffe_definition[1024];
+} hf6d_options;
+int hf6d_parse_options(const char* options_path, hf6d_options* out, hf6d_object* objs, int cap);
+int hf6d_inspect_forest(const char* forest_dir, hf6d_model_info* out); /* dims[] left zero */
+int hf6d_inspect_weights(const char* weights_path, int32_t dims[4]);
+
 /* ---------------------------------------------------------------------------------------------- whole frame */
 /* Host buffers: bgr uint8[H][W][3] (OpenCV imread order), depth_mm uint16[H][W].  Synchronous. */
 int hf6d_detect(hf6d_ctx* c, const uint8_t* bgr, const uint16_t* depth_mm, hf6d_hypothesis* out, int cap, int* n_out);

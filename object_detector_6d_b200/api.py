@@ -28,6 +28,7 @@ EXPORTS = (
     "hf6d_wait", "hf6d_host_alloc", "hf6d_host_free", "hf6d_upload", "hf6d_run", "hf6d_sync", "hf6d_collect",
     "hf6d_fetch", "hf6d_inject", "hf6d_device_ptr", "hf6d_set_stream", "hf6d_stage_ms", "hf6d_launch_count",
     "hf6d_pose_from_tuple", "hf6d_bind_frame", "hf6d_encoder_layer_ms", "hf6d_result_bytes",
+    "hf6d_parse_options", "hf6d_inspect_forest", "hf6d_inspect_weights",
 )
 
 
@@ -50,6 +51,11 @@ class ModelInfo(C.Structure):
     _fields_ = [("T", C.c_int32), ("K", C.c_int32), ("F", C.c_int32), ("patch_vox", C.c_int32),
                 ("voxel_m", C.c_float), ("n_leaves", C.c_int64), ("n_internal", C.c_int64), ("n_votes", C.c_int64),
                 ("max_depth", C.c_int32), ("dims", C.c_int32 * 4)]
+
+
+class Options(C.Structure):
+    _fields_ = [("params", Params), ("gpu", C.c_int32), ("n_objects", C.c_int32), ("forest_folder", C.c_char * 1024),
+                ("caffe_weights", C.c_char * 1024), ("caffe_definition", C.c_char * 1024)]
 
 
 HYP_DTYPE = np.dtype([("cls", "<i4"), ("cx", "<i4"), ("cy", "<i4"), ("z", "<f4"), ("yaw_deg", "<i4"),
@@ -119,6 +125,9 @@ def load():
     L.hf6d_encoder_layer_ms.argtypes = [vp, i32, C.POINTER(C.c_float)]
     L.hf6d_pose_from_tuple.argtypes = [C.POINTER(Params), i32, i32, C.c_float, i32, i32, i32, C.POINTER(C.c_float)]
     L.hf6d_pose_from_tuple.restype = None
+    L.hf6d_parse_options.argtypes = [C.c_char_p, C.POINTER(Options), C.POINTER(ObjectOptions), i32]
+    L.hf6d_inspect_forest.argtypes = [C.c_char_p, C.POINTER(ModelInfo)]
+    L.hf6d_inspect_weights.argtypes = [C.c_char_p, C.POINTER(C.c_int32)]
     _lib = L
     return L
 
@@ -129,6 +138,34 @@ def default_params(**kw) -> Params:
     for k, v in kw.items():
         setattr(p, k, v)
     return p
+
+
+def _ck_host(rc):
+    if rc < 0:
+        raise Hf6dError(rc, (load().hf6d_last_error(None) or b"").decode())
+
+
+def parse_options(path: str):
+    """Host-only: a DetectorOptions text file -> (Options, [object dicts]).  Raises Hf6dError on a malformed file."""
+    o = Options()
+    objs = (ObjectOptions * 32)()
+    _ck_host(load().hf6d_parse_options(path.encode(), C.byref(o), objs, 32))
+    return o, [dict(name=objs[k].name.decode(), should_detect=bool(objs[k].should_detect),
+                    max_location_hypotheses=objs[k].max_location_hypotheses, instances=objs[k].instances)
+               for k in range(min(o.n_objects, 32))]
+
+
+def inspect_forest(forest_dir: str) -> ModelInfo:
+    """Host-only: load + flatten forest.txt / treeN.dat with the product's own reader; counts only."""
+    mi = ModelInfo()
+    _ck_host(load().hf6d_inspect_forest(forest_dir.encode(), C.byref(mi)))
+    return mi
+
+
+def inspect_weights(path: str):
+    dims = (C.c_int32 * 4)()
+    _ck_host(load().hf6d_inspect_weights(path.encode(), dims))
+    return tuple(dims)
 
 
 class PinnedArray:

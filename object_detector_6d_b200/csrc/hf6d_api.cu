@@ -732,6 +732,15 @@ int finish_create(hf6d_ctx* c, int device, int n_slots) {
     return HF6D_OK;
 }
 
+void params_from_options(const HostOptions& o, hf6d_params& p) {
+    p.stride = o.stride;
+    p.fx = o.fx; p.fy = o.fy; p.cx = o.cx; p.cy = o.cy;
+    p.max_depth_range_m = o.max_depth_range;
+    p.distance_threshold_m = o.distance_threshold;
+    p.fill_random = o.are_objects_segmented ? 0 : 1;  // HFTest.cpp:1235
+    p.batch_size = o.batch_size;
+}
+
 }  // namespace
 
 // ==================================================================================================== C ABI
@@ -785,12 +794,7 @@ int hf6d_create_from_options(const char* options_path, int W, int H, int device,
     hf6d_params p;
     hf6d_default_params(&p);
     p.W = W; p.H = H;
-    p.stride = o.stride;
-    p.fx = o.fx; p.fy = o.fy; p.cx = o.cx; p.cy = o.cy;
-    p.max_depth_range_m = o.max_depth_range;
-    p.distance_threshold_m = o.distance_threshold;
-    p.fill_random = o.are_objects_segmented ? 0 : 1;  // HFTest.cpp:1235
-    p.batch_size = o.batch_size;
+    params_from_options(o, p);
     hf6d_ctx* c = new hf6d_ctx();
     c->p = p;
     c->objects = o.objects;
@@ -805,6 +809,49 @@ int hf6d_create_from_options(const char* options_path, int W, int H, int device,
     }
     if (r) { free_all(c); delete c; return r; }
     *out = c;
+    return HF6D_OK;
+}
+
+int hf6d_parse_options(const char* options_path, hf6d_options* out, hf6d_object* objs, int cap) {
+    if (!options_path || !out) return fail(nullptr, HF6D_EINVAL, "null argument");
+    HostOptions o;
+    std::string err;
+    if (!load_options(options_path, o, err)) return fail(nullptr, HF6D_EIO, "%s", err.c_str());
+    memset(out, 0, sizeof *out);
+    hf6d_default_params(&out->params);
+    params_from_options(o, out->params);
+    out->gpu = o.gpu;
+    out->n_objects = (int32_t)o.objects.size();
+    snprintf(out->forest_folder, sizeof out->forest_folder, "%s", o.forest_folder.c_str());
+    snprintf(out->caffe_weights, sizeof out->caffe_weights, "%s", o.caffe_weights.c_str());
+    snprintf(out->caffe_definition, sizeof out->caffe_definition, "%s", o.caffe_definition.c_str());
+    for (int k = 0; k < (int)o.objects.size() && k < cap && objs; ++k) objs[k] = o.objects[k];
+    return HF6D_OK;
+}
+
+int hf6d_inspect_forest(const char* forest_dir, hf6d_model_info* out) {
+    if (!forest_dir || !out) return fail(nullptr, HF6D_EINVAL, "null argument");
+    HostForest hf;
+    std::string err;
+    if (!load_forest(forest_dir, hf, err)) return fail(nullptr, HF6D_EIO, "%s", err.c_str());
+    memset(out, 0, sizeof *out);
+    out->T = hf.T; out->K = hf.K; out->F = hf.F; out->patch_vox = hf.ps;
+    out->voxel_m = hf.vox;
+    out->n_leaves = (int64_t)hf.leaf_id.size();
+    out->n_internal = hf.n_internal;
+    out->n_votes = (int64_t)hf.ox.size();
+    out->max_depth = hf.max_depth;
+    return HF6D_OK;
+}
+
+int hf6d_inspect_weights(const char* weights_path, int32_t dims[4]) {
+    if (!weights_path || !dims) return fail(nullptr, HF6D_EINVAL, "null argument");
+    std::vector<HostLayer> layers;
+    std::string err;
+    if (!load_weights(weights_path, layers, err)) return fail(nullptr, HF6D_EIO, "%s", err.c_str());
+    if (layers.size() != 3) return fail(nullptr, HF6D_EINVAL, "encoder must have 3 layers, file has %zu", layers.size());
+    dims[0] = layers[0].in;
+    for (int l = 0; l < 3; ++l) dims[l + 1] = layers[l].out;
     return HF6D_OK;
 }
 

@@ -1,0 +1,103 @@
+"""Tree-sharded detection across the GPUs of one box: one process per GPU, torch.distributed for the plumbing.
+
+The reference's voting loop runs trees outermost (HoughForest/src/HFTest.cpp:177) and trees interact only through the
+per-class vote maps and the centre->leaf back-map, so rank r of N owns trees {t : t % N == r}:
+
+  every rank      : scan -> gather -> encode the frame (replicated: no traffic, and all ranks need all P' x F features)
+  rank r          : traverse + vote its own trees into its own Q16 maps          hf6d_run(SCAN .. VOTE)
+  ONE exchange    : all-reduce(SUM) of the maps   [K][H][W] uint64 (as int64)    14.7 MB at 6 x 480 x 640
+                    all-reduce(MAX) of the leaf table [cap][T] int32             (entries of foreign trees are -1)
+  every rank      : centres + pose mode seeking on the summed maps / merged table hf6d_run(CENTRES .. POSE)
+
+Vote weights are Q16 integers, so the summed maps -- and everything downstream -- are bit-identical to the single-GPU
+result whatever N is (the reference's float maps depend on the OpenMP schedule, HFTest.cpp:645-654).
+
+The exchange runs on the slot's CUDA stream (NCCL is stream-ordered after the vote kernel; no host sync in between).
+`exchange()` itself is backend-agnostic: the CPU test-suite drives it with gloo at world_size 2.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import api
+
+
+def owned_trees(rank: int, world: int, T: int):
+    """Trees of rank `rank` (the rule hf6d_set_tree_shard implements on the device side)."""
+    return [t for t in range(T) if t % world == rank]
+
+
+def exchange(maps, leaf_table, group=None):
+    """The path's one exchange step: in-place SUM of the vote maps and MAX of the leaf table across the group.
+
+    maps: int64 tensor (Q16 sums; uint64 bit pattern, sums stay far below 2^63), leaf_table: int32 tensor with -1 for
+    trees a rank does not own.  Works on CUDA tensors (nccl) and CPU tensors (gloo)."""
+    import torch.distributed as dist
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    h1 = dist.all_reduce(maps, op=dist.ReduceOp.SUM, group=group, async_op=True)
+    h2 = dist.all_reduce(leaf_table, op=dist.ReduceOp.MAX, group=group, async_op=True)
+    h1.wait()
+    h2.wait()
+
+
+class TreeShardedDetector:
+    """This rank's libhf6d context plus the exchange.  Construct it on every rank after init_process_group."""
+
+    def __init__(self, forest_dir, weights_path, params=None, device=0, n_slots=2, group=None):
+        import torch
+        import torch.distributed as dist
+        self.torch = torch
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.det = api.Detector(forest_dir, weights_path, params, device=device, n_slots=n_slots)
+        self.det.set_tree_shard(self.rank, self.world)
+        self.device = device
+        self.stream = torch.cuda.Stream(device=device)
+        self._views = []
+        for s in range(n_slots):
+            self.det.set_stream(s, self.stream.cuda_stream)
+            maps = torch.as_tensor(self.det.device_array(api.BUF_MAPS, s), device=f"cuda:{device}")
+            leaf = torch.as_tensor(self.det.device_array(api.BUF_LEAF_ORD, s), device=f"cuda:{device}")
+            self._views.append((maps, leaf))
+
+    @property
+    def trees(self):
+        return owned_trees(self.rank, self.world, self.det.T)
+
+    def run(self, slot=0):
+        """Launch one frame (already uploaded / bound on `slot`) asynchronously on the shard stream."""
+        torch = self.torch
+        with torch.cuda.stream(self.stream):
+            self.det.run(slot, api.STAGE_SCAN, api.STAGE_VOTE)
+            n = self.det.launch_count(slot)
+            maps, leaf = self._views[slot]
+            exchange(maps, leaf, self.group)
+            self.det.run(slot, api.STAGE_CENTRES, api.STAGE_POSE)
+            self._launches = n + self.det.launch_count(slot)
+
+    def detect(self, bgr, depth, slot=0):
+        self.det.upload(slot, bgr, depth)
+        self.run(slot)
+        return self.det.collect(slot)
+
+    def launches_per_frame(self) -> int:
+        """Kernels of this repo launched by the last run() (the two NCCL all-reduces are not counted)."""
+        return getattr(self, "_launches", 0)
+
+    def close(self):
+        for s in range(self.det.n_slots):
+            self.det.set_stream(s, None)
+        self._views = []
+        self.det.close()
+
+
+def merge_numpy(parts_maps, parts_leaf):
+    """Host-side statement of the exchange (used by tests): sum of maps, max of leaf tables."""
+    maps = np.zeros_like(parts_maps[0])
+    leaf = np.full_like(parts_leaf[0], -1)
+    for m, lf in zip(parts_maps, parts_leaf):
+        maps += m
+        leaf = np.maximum(leaf, lf)
+    return maps, leaf

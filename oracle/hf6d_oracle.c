@@ -481,7 +481,9 @@ static int64_t cast_votes(const hf6d_ref_forest* f, const int32_t* leaf_ord, con
         const int px = locs[2 * i], py = locs[2 * i + 1];
         const uint16_t d = depth[(size_t)py * W + px]; /* HFTest.cpp:628 */
         for (int t = 0; t < T; ++t) {
-            const ref_node* leaf = f->leaves[t][leaf_ord[(size_t)i * T + t]];
+            const int32_t ord = leaf_ord[(size_t)i * T + t];
+            if (ord < 0) continue; /* tree not owned by this shard (multi-GPU tests); never in the reference */
+            const ref_node* leaf = f->leaves[t][ord];
             for (int c = 0; c < K; ++c) {
                 if (should_detect && !should_detect[c]) continue;
                 if (!(leaf->class_prob[c] >= 0.5f)) continue; /* HFTest.cpp:191 */
