@@ -203,6 +203,11 @@ int64_t hf6d_result_bytes(const hf6d_ctx* c);
 /* Number of kernels the last hf6d_run on this slot launched. */
 int hf6d_launch_count(const hf6d_ctx* c, int slot);
 
+/* Diagnostic (not on the hot path): gathers the slot's P' patches through a real CUDA texture object built exactly as
+ * the reference builds its texture (patch_extractor.cu:339-343, fill = 0) and copies them to the host as
+ * float[P'][ps][ps][4] (HWC).  Needs a prior hf6d_run(.., SCAN, ..) on the slot.  Returns bytes written, or <0. */
+int64_t hf6d_debug_texture_gather(hf6d_ctx* c, int slot, float* dst, size_t cap_bytes);
+
 /* Pre-ICP pose of a hypothesis tuple (HFTest.cpp:922-924 + MeshUtils.cpp:423-440); host arithmetic. */
 void hf6d_pose_from_tuple(const hf6d_params* p, int cx, int cy, float z, int yaw_deg, int pitch_deg, int roll_deg,
                           float pose[16]);

@@ -28,7 +28,7 @@ EXPORTS = (
     "hf6d_wait", "hf6d_host_alloc", "hf6d_host_free", "hf6d_upload", "hf6d_run", "hf6d_sync", "hf6d_collect",
     "hf6d_fetch", "hf6d_inject", "hf6d_device_ptr", "hf6d_set_stream", "hf6d_stage_ms", "hf6d_launch_count",
     "hf6d_pose_from_tuple", "hf6d_bind_frame", "hf6d_encoder_layer_ms", "hf6d_result_bytes",
-    "hf6d_parse_options", "hf6d_inspect_forest", "hf6d_inspect_weights",
+    "hf6d_parse_options", "hf6d_inspect_forest", "hf6d_inspect_weights", "hf6d_debug_texture_gather",
 )
 
 
@@ -125,6 +125,8 @@ def load():
     L.hf6d_encoder_layer_ms.argtypes = [vp, i32, C.POINTER(C.c_float)]
     L.hf6d_pose_from_tuple.argtypes = [C.POINTER(Params), i32, i32, C.c_float, i32, i32, i32, C.POINTER(C.c_float)]
     L.hf6d_pose_from_tuple.restype = None
+    L.hf6d_debug_texture_gather.argtypes = [vp, i32, vp, C.c_size_t]
+    L.hf6d_debug_texture_gather.restype = i64
     L.hf6d_parse_options.argtypes = [C.c_char_p, C.POINTER(Options), C.POINTER(ObjectOptions), i32]
     L.hf6d_inspect_forest.argtypes = [C.c_char_p, C.POINTER(ModelInfo)]
     L.hf6d_inspect_weights.argtypes = [C.c_char_p, C.POINTER(C.c_int32)]
@@ -352,6 +354,15 @@ class Detector:
         a = np.zeros(shape, dt)
         n = self._ck(self._L.hf6d_fetch(self._h, slot, what, self._ptr(a), a.nbytes))
         assert n == a.nbytes, (n, a.nbytes)
+        return a
+
+    def texture_gather(self, slot=0):
+        """Diagnostic: the slot's patches through a real CUDA texture object (the reference's own fetch), fp32 HWC."""
+        _, Pp = self.counts(slot)
+        ps = self.params.patch_vox
+        a = np.zeros((Pp, ps, ps, 4), np.float32)
+        n = self._ck(self._L.hf6d_debug_texture_gather(self._h, slot, self._ptr(a), a.nbytes))
+        assert n == a.nbytes
         return a
 
     def inject(self, what, array, slot=0):

@@ -21,6 +21,7 @@
 #include "gather.cuh"
 #include "model.hpp"
 #include "modes.cuh"
+#include "texture_check.cuh"
 #include "vote.cuh"
 
 using namespace hf6d;
@@ -1091,6 +1092,72 @@ int hf6d_stage_ms(hf6d_ctx* c, int slot, float* ms) {
         if (s.ev_valid[st] && s.ev_valid[st + 1]) cudaEventElapsedTime(&ms[st], s.ev[st], s.ev[st + 1]);
     }
     return HF6D_OK;
+}
+
+int64_t hf6d_debug_texture_gather(hf6d_ctx* c, int slot, float* dst, size_t cap_bytes) {
+    int r = check_slot(c, slot);
+    if (r) return r;
+    Slot& s = c->slots[slot];
+    const FrameGeom& g = c->g;
+    CU_TRY(c, cudaSetDevice(c->device));
+    CU_TRY(c, cudaStreamSynchronize(s.stream));
+    int counts[2];
+    CU_TRY(c, cudaMemcpy(counts, s.counts, 8, cudaMemcpyDeviceToHost));
+    const size_t Pp = (size_t)std::min(counts[1], g.cap);
+    const size_t bytes = Pp * g.ps * g.ps * 4 * sizeof(float);
+    if (bytes > cap_bytes) return fail(c, HF6D_EINVAL, "destination too small: need %zu bytes, have %zu", bytes, cap_bytes);
+    if (!Pp) return 0;
+    float* vol = nullptr;
+    float* out = nullptr;
+    cudaArray_t arr = nullptr;
+    cudaTextureObject_t tex = 0;
+    int rc = HF6D_OK;
+    auto cleanup = [&]() {
+        if (tex) cudaDestroyTextureObject(tex);
+        if (arr) cudaFreeArray(arr);
+        if (vol) cudaFree(vol);
+        if (out) cudaFree(out);
+    };
+#define TX_TRY(expr)                                                                                   \
+    do {                                                                                               \
+        cudaError_t e_ = (expr);                                                                       \
+        if (e_ != cudaSuccess) { rc = fail(c, HF6D_ECUDA, "%s: %s", #expr, cudaGetErrorString(e_)); cleanup(); return rc; } \
+    } while (0)
+    const size_t HW = (size_t)g.W * g.H;
+    TX_TRY(cudaMalloc(&vol, HW * 4 * sizeof(float)));
+    TX_TRY(cudaMalloc(&out, bytes));
+    texture_build_kernel<<<(unsigned)((HW + 255) / 256), 256, 0, s.stream>>>(s.bgr, s.depth, g.W, g.H, vol);
+    TX_TRY(cudaGetLastError());
+    // extent (width = 4 channels, height = W, depth = H): patch_extractor.cu:322-337
+    cudaChannelFormatDesc fd = cudaCreateChannelDesc<float>();
+    const cudaExtent ext = make_cudaExtent(4, g.W, g.H);
+    TX_TRY(cudaMalloc3DArray(&arr, &fd, ext));
+    cudaMemcpy3DParms cp;
+    memset(&cp, 0, sizeof cp);
+    cp.srcPtr = make_cudaPitchedPtr(vol, 4 * sizeof(float), 4, g.W);
+    cp.dstArray = arr;
+    cp.extent = ext;
+    cp.kind = cudaMemcpyDeviceToDevice;
+    TX_TRY(cudaStreamSynchronize(s.stream));
+    TX_TRY(cudaMemcpy3D(&cp));
+    cudaResourceDesc rd;
+    memset(&rd, 0, sizeof rd);
+    rd.resType = cudaResourceTypeArray;
+    rd.res.array.array = arr;
+    cudaTextureDesc td;
+    memset(&td, 0, sizeof td);
+    td.normalizedCoords = 0;
+    td.filterMode = cudaFilterModeLinear;
+    td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeBorder;
+    td.readMode = cudaReadModeElementType;
+    TX_TRY(cudaCreateTextureObject(&tex, &rd, &td, nullptr));
+    texture_gather_kernel<<<(unsigned)Pp, 64, 0, s.stream>>>(tex, g, s.locs, s.counts, out);
+    TX_TRY(cudaGetLastError());
+    TX_TRY(cudaStreamSynchronize(s.stream));
+    TX_TRY(cudaMemcpy(dst, out, bytes, cudaMemcpyDeviceToHost));
+#undef TX_TRY
+    cleanup();
+    return (int64_t)bytes;
 }
 
 int64_t hf6d_result_bytes(const hf6d_ctx* c) { return c ? (int64_t)c->rl.total : HF6D_EINVAL; }

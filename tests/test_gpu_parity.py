@@ -245,3 +245,33 @@ def test_empty_frame(case):
     hyp = det.detect(case["bgr"], np.zeros_like(case["depth"]))
     assert len(hyp) == 0
     assert det.counts(0) == (0, 0)
+
+
+def test_software_filter_equals_the_texture_unit(case):
+    """the reference's gather is the hardware texture filter (patch_extractor.cu:339-343).  Rebuild that
+    exact fetch with a cudaTextureObject_t on this GPU and compare it with the oracle's software filter (choice C1:
+    fraction in 1.8 fixed point, border 0, (w00*T00 + w10*T10) + w01*T01 + w11*T11 in fp32)."""
+    import ctypes as C
+    from object_detector_6d_b200 import api
+    from oracle import oracle as O
+    p = O.Params()
+    C.memmove(C.byref(p), C.byref(case["params"]), C.sizeof(p))
+    p.fill_random = 0
+    det = case["det"]
+    det.upload(1, case["bgr"], case["depth"])
+    det.run(1, api.STAGE_SCAN, api.STAGE_SCAN)
+    hw = det.texture_gather(slot=1)
+    locs = O.scan_centres(case["depth"], p)
+    Pp = (len(locs) // 100) * 100
+    sw = O.gather(case["bgr"], case["depth"], p, locs[:Pp])
+    assert hw.shape == sw.shape
+    diff = np.abs(hw - sw)
+    n_bad = int((hw != sw).sum())
+    print(f"texture unit vs software filter: {n_bad} of {hw.size} values differ, max abs diff {diff.max():.3e}")
+    # ps = 8: every sample fraction is a multiple of 1/8, exactly representable in the unit's 8 fractional bits, so
+    # the only freedom left is the order of the fp32 blend; the quantised patches downstream must not move
+    assert diff.max() <= 2e-6
+    q_hw, q_sw = O.normalise(hw), O.normalise(sw)
+    frac = float((q_hw != q_sw).mean())
+    print(f"quantised uint8 values that differ between hardware and software filter: {frac * 100:.4f}%")
+    assert frac < 1e-3
