@@ -162,6 +162,8 @@ typedef struct {
     char forest_folder[1024];   /* Options.forest_folder */
     char caffe_weights[1024];   /* Options.caffe_weights */
     char caffe_definition[1024];
+    float location_score_coeff; /* Options.location_score_coeff / pose_score_coeff: the Hough terms of the reference's */
+    float pose_score_coeff;     /* final score (MeshUtils.cpp:780-784); the CLI ranks pre-ICP hypotheses with them    */
 } hf6d_options;
 int hf6d_parse_options(const char* options_path, hf6d_options* out, hf6d_object* objs, int cap);
 int hf6d_inspect_forest(const char* forest_dir, hf6d_model_info* out); /* dims[] left zero */

@@ -55,7 +55,8 @@ class ModelInfo(C.Structure):
 
 class Options(C.Structure):
     _fields_ = [("params", Params), ("gpu", C.c_int32), ("n_objects", C.c_int32), ("forest_folder", C.c_char * 1024),
-                ("caffe_weights", C.c_char * 1024), ("caffe_definition", C.c_char * 1024)]
+                ("caffe_weights", C.c_char * 1024), ("caffe_definition", C.c_char * 1024),
+                ("location_score_coeff", C.c_float), ("pose_score_coeff", C.c_float)]
 
 
 HYP_DTYPE = np.dtype([("cls", "<i4"), ("cx", "<i4"), ("cy", "<i4"), ("z", "<f4"), ("yaw_deg", "<i4"),

@@ -823,6 +823,8 @@ int hf6d_parse_options(const char* options_path, hf6d_options* out, hf6d_object*
     params_from_options(o, out->params);
     out->gpu = o.gpu;
     out->n_objects = (int32_t)o.objects.size();
+    out->location_score_coeff = o.location_score_coeff;
+    out->pose_score_coeff = o.pose_score_coeff;
     snprintf(out->forest_folder, sizeof out->forest_folder, "%s", o.forest_folder.c_str());
     snprintf(out->caffe_weights, sizeof out->caffe_weights, "%s", o.caffe_weights.c_str());
     snprintf(out->caffe_definition, sizeof out->caffe_definition, "%s", o.caffe_definition.c_str());

@@ -339,6 +339,7 @@ struct HostOptions {
     int stride = 4, gpu = -1, num_threads = 4, batch_size = 100;  // proto defaults (detector_options.proto:23-27)
     float max_depth_range = 0.25f, fx = 575.f, fy = 575.f, cx = 319.5f, cy = 239.5f, distance_threshold = 1.5f;
     bool are_objects_segmented = false;
+    float location_score_coeff = 1.0f, pose_score_coeff = 0.7f;  // detector_options.proto:46-47 (used by the CLI's ranking)
 };
 
 // Minimal protobuf text-format reader for DetectorOptions.Options: `key: value`, `key { ... }`, `key: { ... }`,
@@ -407,6 +408,8 @@ class OptionsParser {
                 else if (key == "cy") o.cy = strtof(v.c_str(), nullptr);
                 else if (key == "distance_threshold") o.distance_threshold = strtof(v.c_str(), nullptr);
                 else if (key == "are_objects_segmented") { if (!boolean(v, b)) return fail(err, "bad bool for " + key); o.are_objects_segmented = b != 0; }
+                else if (key == "location_score_coeff") o.location_score_coeff = strtof(v.c_str(), nullptr);
+                else if (key == "pose_score_coeff") o.pose_score_coeff = strtof(v.c_str(), nullptr);
                 else if (is_downstream_key(key)) {}  // ICP / scoring / clustering options: parsed, not used by this path
                 else return fail(err, "unknown field " + key);
             }
