@@ -59,8 +59,8 @@ def build_cli(force: bool = False) -> str:
         return ""
     if force or _newer(CLI, [src, LIB]):
         build_lib()
-        cmd = [_host_cxx(), "-O2", "-std=c++17", "-I", os.path.join(HERE, "..", "include"), "-o", CLI, src,
-               "-L", HERE, "-lhf6d", "-Wl,-rpath,$ORIGIN"]
+        cmd = [_host_cxx(), "-O2", "-std=c++17", "-ffp-contract=off", "-I", os.path.join(HERE, "..", "include"), "-o", CLI, src,
+               "-L", HERE, "-lhf6d", "-lz", "-Wl,-rpath,$ORIGIN"]
         subprocess.check_call(cmd)
     return CLI
 

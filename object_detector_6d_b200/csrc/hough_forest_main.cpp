@@ -1,0 +1,512 @@
+// HoughForest -- command-line drop-in for the reference's `HoughForest --test` (HoughForest/src/main.cpp:33-78 and
+// HFTest::DetectObjects, HoughForest/src/HFTest.cpp:1152-1311), on top of the C ABI in include/hf6d.h.
+//
+//   HoughForest --test --detector_options_file=<options.txt> [--output_folder=<dir>]  < pairs.txt
+//
+// stdin carries whitespace-separated `rgb_path depth_path` pairs until EOF (HFTest.cpp:1238).  For every pair the
+// program writes `<output_folder><stem>_res.txt` (object name, instance counter, 4x4 pose in Eigen's default stream
+// format, blank line -- HFTest.cpp:1264-1290) and `<output_folder><stem>_res.png`, and prints the reference's progress
+// lines to stdout.  Unreadable images are reported and skipped (HFTest.cpp:1242-1251).
+//
+// Scope: ICP, hypothesis verification and the joint optimisation are not part of this path, so the
+// poses written are the *pre-ICP* poses (HFTest.cpp:922-924 + MeshUtils.cpp:423-440) and hypotheses are ranked by the
+// Hough terms of the reference's final score, pose_score * pose_score_coeff + location_score * location_score_coeff
+// (MeshUtils.cpp:780-784) with pose_score = (yaw-pitch score + roll score) / 2 (HFTest.cpp:934).  The result image is
+// the input colour image (the mesh overlay needs the renderer).
+//
+// Host code only: every frame goes through hf6d_submit / hf6d_wait; there is no CPU detection path in this file.
+#include <zlib.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "../../include/hf6d.h"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------ image files
+struct Image {
+    int w = 0, h = 0, channels = 0, bits = 0;  // bits per sample: 8 or 16
+    std::vector<uint16_t> px;                  // samples widened to 16 bits, interleaved
+};
+
+bool read_file(const std::string& path, std::vector<uint8_t>& out) {
+    std::ifstream f(path.c_str(), std::ios::binary);
+    if (!f) return false;
+    f.seekg(0, std::ios::end);
+    const std::streamoff n = f.tellg();
+    if (n < 0) return false;
+    f.seekg(0);
+    out.resize((size_t)n);
+    if (n) f.read(reinterpret_cast<char*>(out.data()), n);
+    return (bool)f;
+}
+
+uint32_t be32(const uint8_t* p) { return (uint32_t)p[0] << 24 | (uint32_t)p[1] << 16 | (uint32_t)p[2] << 8 | p[3]; }
+
+int paeth(int a, int b, int c) {
+    const int p = a + b - c, pa = std::abs(p - a), pb = std::abs(p - b), pc = std::abs(p - c);
+    return (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c);
+}
+
+// Non-interlaced PNG, colour types 0/2/3/4/6, bit depths 1..16 (what cv::imread accepts for these inputs).
+bool decode_png(const std::vector<uint8_t>& file, Image& img, std::string& err) {
+    static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
+    if (file.size() < 8 || memcmp(file.data(), sig, 8)) { err = "not a PNG file"; return false; }
+    size_t at = 8;
+    int w = 0, h = 0, depth = 0, ctype = -1, interlace = 0;
+    std::vector<uint8_t> idat, palette;
+    bool end = false;
+    while (!end && at + 12 <= file.size()) {
+        const uint32_t len = be32(&file[at]);
+        const char* type = reinterpret_cast<const char*>(&file[at + 4]);
+        if (at + 12 + (size_t)len > file.size()) { err = "truncated PNG chunk"; return false; }
+        const uint8_t* body = &file[at + 8];
+        if (!memcmp(type, "IHDR", 4)) {
+            if (len < 13) { err = "bad IHDR"; return false; }
+            w = (int)be32(body); h = (int)be32(body + 4); depth = body[8]; ctype = body[9]; interlace = body[12];
+        } else if (!memcmp(type, "PLTE", 4)) palette.assign(body, body + len);
+        else if (!memcmp(type, "IDAT", 4)) idat.insert(idat.end(), body, body + len);
+        else if (!memcmp(type, "IEND", 4)) end = true;
+        at += 12 + (size_t)len;
+    }
+    if (w <= 0 || h <= 0 || w > 65535 || h > 65535) { err = "bad PNG dimensions"; return false; }
+    if (interlace) { err = "interlaced PNG is not supported"; return false; }
+    int nch;
+    switch (ctype) {
+        case 0: nch = 1; break;
+        case 2: nch = 3; break;
+        case 3: nch = 1; break;
+        case 4: nch = 2; break;
+        case 6: nch = 4; break;
+        default: err = "bad PNG colour type"; return false;
+    }
+    if (!(depth == 1 || depth == 2 || depth == 4 || depth == 8 || depth == 16)) { err = "bad PNG bit depth"; return false; }
+    const size_t bpp_bits = (size_t)nch * depth, stride = ((size_t)w * bpp_bits + 7) / 8, bpp = std::max<size_t>(1, bpp_bits / 8);
+    std::vector<uint8_t> raw((stride + 1) * (size_t)h);
+    uLongf raw_len = (uLongf)raw.size();
+    if (idat.empty() || uncompress(raw.data(), &raw_len, idat.data(), (uLong)idat.size()) != Z_OK || raw_len != raw.size()) {
+        err = "PNG data does not inflate to the image size";
+        return false;
+    }
+    std::vector<uint8_t> prev(stride, 0), cur(stride);
+    const bool pal = ctype == 3;
+    const int out_ch = pal ? 3 : nch;
+    img.w = w; img.h = h; img.channels = out_ch; img.bits = (depth == 16) ? 16 : 8;
+    img.px.assign((size_t)w * h * out_ch, 0);
+    for (int y = 0; y < h; ++y) {
+        const uint8_t* line = &raw[(stride + 1) * (size_t)y];
+        const int filter = line[0];
+        for (size_t i = 0; i < stride; ++i) {
+            const int a = i >= bpp ? cur[i - bpp] : 0, b = prev[i], c = i >= bpp ? prev[i - bpp] : 0;
+            int v = line[1 + i];
+            switch (filter) {
+                case 0: break;
+                case 1: v += a; break;
+                case 2: v += b; break;
+                case 3: v += (a + b) / 2; break;
+                case 4: v += paeth(a, b, c); break;
+                default: err = "bad PNG filter"; return false;
+            }
+            cur[i] = (uint8_t)v;
+        }
+        uint16_t* dst = &img.px[(size_t)y * w * out_ch];
+        for (int x = 0; x < w; ++x)
+            for (int ch = 0; ch < nch; ++ch) {
+                const size_t s = (size_t)x * nch + ch;
+                unsigned v;
+                if (depth == 16) v = (unsigned)cur[2 * s] << 8 | cur[2 * s + 1];
+                else if (depth == 8) v = cur[s];
+                else {
+                    const size_t bit = s * depth;
+                    v = (cur[bit / 8] >> (8 - depth - (bit % 8))) & ((1u << depth) - 1);
+                    if (!pal) v = v * 255u / ((1u << depth) - 1);  // grey samples scale to 8 bits
+                }
+                if (pal) {
+                    if ((size_t)v * 3 + 2 >= palette.size()) { err = "PNG palette index out of range"; return false; }
+                    dst[x * 3 + 0] = palette[v * 3]; dst[x * 3 + 1] = palette[v * 3 + 1]; dst[x * 3 + 2] = palette[v * 3 + 2];
+                } else dst[(size_t)x * nch + ch] = (uint16_t)v;
+            }
+        prev.swap(cur);
+    }
+    return true;
+}
+
+// Binary PGM / PPM (P5 / P6), 8 or 16 bit big-endian samples.
+bool decode_pnm(const std::vector<uint8_t>& file, Image& img, std::string& err) {
+    if (file.size() < 3 || file[0] != 'P' || (file[1] != '5' && file[1] != '6')) { err = "not a binary PGM/PPM file"; return false; }
+    size_t at = 2;
+    auto next_int = [&](long& v) {
+        for (;;) {
+            while (at < file.size() && isspace(file[at])) ++at;
+            if (at < file.size() && file[at] == '#') { while (at < file.size() && file[at] != '\n') ++at; continue; }
+            break;
+        }
+        if (at >= file.size() || !isdigit(file[at])) return false;
+        v = 0;
+        while (at < file.size() && isdigit(file[at])) v = v * 10 + (file[at++] - '0');
+        return true;
+    };
+    long w, h, maxv;
+    if (!next_int(w) || !next_int(h) || !next_int(maxv) || w <= 0 || h <= 0 || w > 65535 || h > 65535 || maxv <= 0 || maxv > 65535) {
+        err = "bad PNM header";
+        return false;
+    }
+    ++at;  // single whitespace after maxval
+    const int nch = file[1] == '6' ? 3 : 1, bytes = maxv > 255 ? 2 : 1;
+    const size_t need = (size_t)w * h * nch * bytes;
+    if (at + need > file.size()) { err = "truncated PNM data"; return false; }
+    img.w = (int)w; img.h = (int)h; img.channels = nch; img.bits = bytes * 8;
+    img.px.resize((size_t)w * h * nch);
+    const uint8_t* p = &file[at];
+    for (size_t i = 0; i < img.px.size(); ++i) img.px[i] = bytes == 2 ? (uint16_t)(p[2 * i] << 8 | p[2 * i + 1]) : p[i];
+    return true;
+}
+
+bool load_image(const std::string& path, Image& img, std::string& err) {
+    std::vector<uint8_t> file;
+    if (!read_file(path, file)) { err = "cannot open"; return false; }
+    if (file.size() >= 2 && file[0] == 'P') return decode_pnm(file, img, err);
+    return decode_png(file, img, err);
+}
+
+// cv::imread(path) default flag: 3-channel 8-bit BGR whatever the file holds (HFTest.cpp:1241).
+void to_bgr8(const Image& img, uint8_t* bgr) {
+    const size_t n = (size_t)img.w * img.h;
+    const int sh = img.bits == 16 ? 8 : 0;
+    for (size_t i = 0; i < n; ++i) {
+        const uint16_t* s = &img.px[i * img.channels];
+        uint8_t r, g, b;
+        if (img.channels >= 3) { r = (uint8_t)(s[0] >> sh); g = (uint8_t)(s[1] >> sh); b = (uint8_t)(s[2] >> sh); }
+        else r = g = b = (uint8_t)(s[0] >> sh);
+        bgr[i * 3 + 0] = b; bgr[i * 3 + 1] = g; bgr[i * 3 + 2] = r;
+    }
+}
+
+// cv::imread(path, ANYDEPTH | ANYCOLOR) of a single-channel 16-bit depth image, read as ushort millimetres
+// (HFTest.cpp:1247, :376).  Colour depth files have no defined meaning in the reference (it reads at<ushort>).
+bool to_depth16(const Image& img, uint16_t* depth, std::string& err) {
+    if (img.channels != 1) { err = "depth image must have one channel"; return false; }
+    memcpy(depth, img.px.data(), (size_t)img.w * img.h * 2);
+    return true;
+}
+
+bool write_png_rgb(const std::string& path, const uint8_t* bgr, int w, int h) {
+    std::vector<uint8_t> raw(((size_t)w * 3 + 1) * h);
+    for (int y = 0; y < h; ++y) {
+        uint8_t* line = &raw[((size_t)w * 3 + 1) * y];
+        line[0] = 0;
+        for (int x = 0; x < w; ++x) {
+            const uint8_t* s = &bgr[((size_t)y * w + x) * 3];
+            line[1 + x * 3] = s[2]; line[2 + x * 3] = s[1]; line[3 + x * 3] = s[0];
+        }
+    }
+    uLongf zlen = compressBound((uLong)raw.size());
+    std::vector<uint8_t> z(zlen);
+    if (compress2(z.data(), &zlen, raw.data(), (uLong)raw.size(), 1) != Z_OK) return false;
+    std::ofstream f(path.c_str(), std::ios::binary);
+    if (!f) return false;
+    auto chunk = [&](const char* type, const uint8_t* body, uint32_t len) {
+        uint8_t hdr[8] = {(uint8_t)(len >> 24), (uint8_t)(len >> 16), (uint8_t)(len >> 8), (uint8_t)len,
+                          (uint8_t)type[0], (uint8_t)type[1], (uint8_t)type[2], (uint8_t)type[3]};
+        uLong crc = crc32(0L, hdr + 4, 4);
+        if (len) crc = crc32(crc, body, len);
+        const uint8_t tail[4] = {(uint8_t)(crc >> 24), (uint8_t)(crc >> 16), (uint8_t)(crc >> 8), (uint8_t)crc};
+        f.write(reinterpret_cast<const char*>(hdr), 8);
+        if (len) f.write(reinterpret_cast<const char*>(body), len);
+        f.write(reinterpret_cast<const char*>(tail), 4);
+    };
+    static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
+    f.write(reinterpret_cast<const char*>(sig), 8);
+    const uint8_t ihdr[13] = {(uint8_t)(w >> 24), (uint8_t)(w >> 16), (uint8_t)(w >> 8), (uint8_t)w,
+                              (uint8_t)(h >> 24), (uint8_t)(h >> 16), (uint8_t)(h >> 8), (uint8_t)h, 8, 2, 0, 0, 0};
+    chunk("IHDR", ihdr, 13);
+    chunk("IDAT", z.data(), (uint32_t)zlen);
+    chunk("IEND", nullptr, 0);
+    return (bool)f;
+}
+
+// ------------------------------------------------------------------------------------------------ text output
+// Eigen's `operator<<` for a Matrix4f with the default IOFormat: stream precision (6 significant digits), every
+// coefficient right-aligned to the widest one, one space between columns, '\n' between rows (HFTest.cpp:1286).
+std::string eigen_format(const float m[16]) {
+    std::string cell[16];
+    size_t width = 0;
+    for (int i = 0; i < 16; ++i) {
+        std::ostringstream s;
+        s << m[i];
+        cell[i] = s.str();
+        width = std::max(width, cell[i].size());
+    }
+    std::string out;
+    for (int r = 0; r < 4; ++r) {
+        if (r) out += '\n';
+        for (int c = 0; c < 4; ++c) {
+            if (c) out += ' ';
+            out.append(width - cell[r * 4 + c].size(), ' ');
+            out += cell[r * 4 + c];
+        }
+    }
+    return out;
+}
+
+// GetOutName, HFTest.cpp:1135-1143
+std::string out_stem(const std::string& filename) {
+    std::string res = filename;
+    size_t p = filename.find_last_of('/');
+    if (p != std::string::npos) res = filename.substr(p + 1);
+    p = res.find_last_of('.');
+    if (p != std::string::npos) res = res.substr(0, p);
+    return res;
+}
+
+// ------------------------------------------------------------------------------------------------ flags
+struct Flags {
+    bool test = false, train = false, other_mode = false, help = false, stage_times = false, check_inputs = false;
+    std::string options_file, output_folder;
+    int device = -1;
+};
+
+bool parse_bool(const std::string& v) { return !(v == "false" || v == "0" || v == "no" || v == "f" || v == "n"); }
+
+// gflags syntax: -flag / --flag, --flag=value or --flag value, --noflag for booleans.
+bool parse_flags(int argc, char** argv, Flags& fl, std::string& err) {
+    for (int i = 1; i < argc; ++i) {
+        std::string a = argv[i];
+        if (a.size() < 2 || a[0] != '-') { err = "unexpected argument: " + a; return false; }
+        a = a.substr(a[1] == '-' ? 2 : 1);
+        std::string val;
+        bool has_val = false;
+        const size_t eq = a.find('=');
+        if (eq != std::string::npos) { val = a.substr(eq + 1); a = a.substr(0, eq); has_val = true; }
+        auto need = [&](std::string& dst) {
+            if (!has_val) {
+                if (i + 1 >= argc) { err = "flag --" + a + " needs a value"; return false; }
+                val = argv[++i];
+            }
+            dst = val;
+            return true;
+        };
+        std::string tmp;
+        if (a == "test") fl.test = has_val ? parse_bool(val) : true;
+        else if (a == "notest") fl.test = false;
+        else if (a == "train") fl.train = has_val ? parse_bool(val) : true;
+        else if (a == "learn_transitions" || a == "save_forest_map") fl.other_mode = true;
+        else if (a == "detector_options_file" || a == "object_options_file") { if (!need(fl.options_file)) return false; }
+        else if (a == "output_folder" || a == "output_dir") { if (!need(fl.output_folder)) return false; }  // README spelling
+        else if (a == "device") { if (!need(tmp)) return false; fl.device = atoi(tmp.c_str()); }
+        else if (a == "stage_times") fl.stage_times = has_val ? parse_bool(val) : true;
+        else if (a == "check_inputs") fl.check_inputs = has_val ? parse_bool(val) : true;
+        else if (a == "show_scene" || a == "visualize_hypotheses" || a == "noshow_scene" || a == "novisualize_hypotheses") {}
+        else if (a == "help" || a == "h") fl.help = true;
+        else if (a == "input" || a == "output" || a == "trees" || a == "min_samples" || a == "tests_per_node" ||
+                 a == "thresholds_per_test" || a == "threads_per_tree" || a == "threads_for_parallel_trees" ||
+                 a == "start_tree_no" || a == "patch_size_in_voxels" || a == "voxel_size_in_m" || a == "logtostderr" ||
+                 a == "v" || a == "minloglevel") { if (!need(tmp)) return false; }  // training / glog flags: accepted, unused
+        else { err = "unknown command line flag '" + a + "'"; return false; }
+    }
+    return true;
+}
+
+const char* kUsage =
+    "usage: HoughForest --test --detector_options_file=<options.txt> [--output_folder=<dir>] [--device=<n>] [--stage_times]\n"
+    "       `rgb_path depth_path` pairs are read from stdin until EOF; results go to <dir><stem>_res.txt / _res.png\n"
+    "       HoughForest --check_inputs   decode the stdin pairs only and print size + FNV-1a checksum of each frame\n";
+
+uint64_t fnv1a(const void* data, size_t n) {
+    const uint8_t* p = static_cast<const uint8_t*>(data);
+    uint64_t h = 1469598103934665603ull;
+    for (size_t i = 0; i < n; ++i) { h ^= p[i]; h *= 1099511628211ull; }
+    return h;
+}
+
+// Host-only: decode every stdin pair exactly as --test would hand it to hf6d_submit and report what was read.
+int check_inputs() {
+    std::string rgb_fname, depth_fname, err;
+    int bad = 0;
+    while (std::cin >> rgb_fname >> depth_fname) {
+        Image rgb_img, depth_img;
+        if (!load_image(rgb_fname, rgb_img, err)) { std::cout << "Cannot read file: " << rgb_fname << " (" << err << ")" << std::endl; ++bad; continue; }
+        if (!load_image(depth_fname, depth_img, err)) { std::cout << "Cannot read file: " << depth_fname << " (" << err << ")" << std::endl; ++bad; continue; }
+        std::vector<uint8_t> bgr((size_t)rgb_img.w * rgb_img.h * 3);
+        std::vector<uint16_t> depth((size_t)depth_img.w * depth_img.h);
+        to_bgr8(rgb_img, bgr.data());
+        if (!to_depth16(depth_img, depth.data(), err)) { std::cout << "Cannot read file: " << depth_fname << " (" << err << ")" << std::endl; ++bad; continue; }
+        char line[256];
+        snprintf(line, sizeof line, "bgr %dx%d %016llx depth %dx%d %016llx", rgb_img.w, rgb_img.h,
+                 (unsigned long long)fnv1a(bgr.data(), bgr.size()), depth_img.w, depth_img.h,
+                 (unsigned long long)fnv1a(depth.data(), depth.size() * 2));
+        std::cout << line << std::endl;
+    }
+    return bad ? 4 : 0;
+}
+
+struct Ranked {
+    float final_score;
+    int index;
+};
+
+}  // namespace
+
+int main(int argc, char** argv) {
+    Flags fl;
+    std::string err;
+    if (!parse_flags(argc, argv, fl, err)) {
+        std::cerr << "ERROR: " << err << "\n" << kUsage;
+        return 1;
+    }
+    if (fl.help) { std::cout << kUsage; return 0; }
+    if (fl.train || fl.other_mode) {
+        std::cerr << "HoughForest: only --test is built here (forest training is out of scope, DESIGN.md section 6)\n";
+        return 2;
+    }
+    if (fl.check_inputs) return check_inputs();
+    if (!fl.test) return 0;  // main.cpp:70-76: nothing to do without a mode flag
+    if (fl.options_file.empty()) {
+        std::cerr << "Check failed: No detector options file specified (--detector_options_file)\n";
+        return 1;
+    }
+    // HFTest.cpp:1190-1192: a '/' is appended to a non-empty output folder
+    if (!fl.output_folder.empty() && fl.output_folder[fl.output_folder.size() - 1] != '/') fl.output_folder += '/';
+
+    // model artefacts are validated on the host before a device is touched
+    hf6d_options opt;
+    std::vector<hf6d_object> objects(HF6D_MAX_CLASSES);
+    if (hf6d_parse_options(fl.options_file.c_str(), &opt, objects.data(), (int)objects.size())) {
+        std::cerr << "Cannot use options file " << fl.options_file << ": " << hf6d_last_error(nullptr) << std::endl;
+        return 1;
+    }
+    objects.resize((size_t)std::min<int>(opt.n_objects, HF6D_MAX_CLASSES));
+    hf6d_model_info forest;
+    if (hf6d_inspect_forest(opt.forest_folder, &forest)) {
+        std::cerr << "Cannot load forest: " << hf6d_last_error(nullptr) << std::endl;
+        return 1;
+    }
+    int32_t dims[4];
+    if (hf6d_inspect_weights(opt.caffe_weights, dims)) {
+        std::cerr << "Cannot load encoder weights: " << hf6d_last_error(nullptr) << std::endl;
+        return 1;
+    }
+    if (opt.n_objects != forest.K) {  // HFTest.cpp:1186
+        std::cerr << "Check failed: Number of objects provided in the options file (" << opt.n_objects
+                  << ") does not match the number of classes in the forest (" << forest.K << ")" << std::endl;
+        return 1;
+    }
+
+    hf6d_ctx* ctx = nullptr;
+    int ctx_w = 0, ctx_h = 0;
+    uint8_t* bgr = nullptr;
+    uint16_t* depth = nullptr;
+    std::vector<hf6d_hypothesis> hyp(HF6D_MAX_CLASSES * HF6D_MAX_CENTRES * HF6D_MAX_HYPOTHESES_PER_CENTRE);
+    int rc = 0;
+
+    std::string rgb_fname, depth_fname;
+    while (std::cin >> rgb_fname >> depth_fname) {
+        Image rgb_img, depth_img;
+        if (!load_image(rgb_fname, rgb_img, err)) {
+            std::cout << "Cannot read file: " << rgb_fname << std::endl;
+            continue;
+        }
+        if (!load_image(depth_fname, depth_img, err)) {
+            std::cout << "Cannot read file: " << depth_fname << std::endl;
+            continue;
+        }
+        if (depth_img.w != rgb_img.w || depth_img.h != rgb_img.h) {
+            std::cout << "Cannot read file: " << depth_fname << " (size differs from " << rgb_fname << ")" << std::endl;
+            continue;
+        }
+        if (!ctx || rgb_img.w != ctx_w || rgb_img.h != ctx_h) {
+            if (ctx) { hf6d_destroy(ctx); ctx = nullptr; }
+            if (bgr) hf6d_host_free(bgr);
+            if (depth) hf6d_host_free(depth);
+            ctx_w = rgb_img.w; ctx_h = rgb_img.h;
+            bgr = static_cast<uint8_t*>(hf6d_host_alloc((size_t)ctx_w * ctx_h * 3));
+            depth = static_cast<uint16_t*>(hf6d_host_alloc((size_t)ctx_w * ctx_h * 2));
+            if (hf6d_create_from_options(fl.options_file.c_str(), ctx_w, ctx_h, fl.device, 1, &ctx) || !bgr || !depth) {
+                std::cerr << "HoughForest: cannot create the detector: " << hf6d_last_error(nullptr) << std::endl;
+                return 3;
+            }
+        }
+        to_bgr8(rgb_img, bgr);
+        if (!to_depth16(depth_img, depth, err)) {
+            std::cout << "Cannot read file: " << depth_fname << " (" << err << ")" << std::endl;
+            continue;
+        }
+
+        const auto t0 = std::chrono::steady_clock::now();
+        int n = 0, ticket = -1;
+        if (hf6d_submit(ctx, bgr, depth, &ticket) || hf6d_wait(ctx, ticket, hyp.data(), (int)hyp.size(), &n)) {
+            std::cerr << "HoughForest: detection failed on " << rgb_fname << ": " << hf6d_last_error(ctx) << std::endl;
+            rc = 3;
+            break;
+        }
+        n = std::min<int>(n, (int)hyp.size());
+        const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        int32_t counts[2] = {0, 0};
+        hf6d_fetch(ctx, 0, HF6D_BUF_COUNTS, counts, sizeof counts);
+        std::cout << "Number of patches: " << counts[0] << std::endl;  // HFTest.cpp:427
+        for (int k = 0; k < forest.K; ++k) {
+            if (!objects[k].should_detect) continue;
+            int centres = 0, last_cx = -1, last_cy = -1;
+            for (int i = 0; i < n; ++i)
+                if (hyp[i].cls == k && (hyp[i].cx != last_cx || hyp[i].cy != last_cy)) { ++centres; last_cx = hyp[i].cx; last_cy = hyp[i].cy; }
+            std::cout << "Generating Hypotheses for class: " << objects[k].name << std::endl;  // HFTest.cpp:697
+            std::cout << "max locations: " << centres << std::endl;                             // HFTest.cpp:712
+        }
+        std::cout << "Total execution time: " << secs << "sec" << std::endl;  // HFTest.cpp:986
+        if (fl.stage_times) {
+            float ms[HF6D_STAGE_COUNT];
+            static const char* names[HF6D_STAGE_COUNT] = {"scan", "gather", "encode", "traverse", "vote", "centres", "pose"};
+            if (!hf6d_stage_ms(ctx, 0, ms))
+                for (int s = 0; s < HF6D_STAGE_COUNT; ++s) std::cout << "  stage " << names[s] << ": " << ms[s] << " ms" << std::endl;
+        }
+
+        // HFTest.cpp:1261: sort by final score, descending (stable here, so equal scores keep emission order)
+        std::vector<Ranked> order((size_t)n);
+        for (int i = 0; i < n; ++i) {
+            const float pose_score = (hyp[i].yawpitch_score + hyp[i].roll_score) / 2.0f;
+            order[i] = Ranked{pose_score * opt.pose_score_coeff + hyp[i].loc_score * opt.location_score_coeff, i};
+        }
+        std::stable_sort(order.begin(), order.end(), [](const Ranked& a, const Ranked& b) { return a.final_score > b.final_score; });
+
+        const std::string stem = out_stem(rgb_fname);
+        const std::string out_fname = fl.output_folder + stem + "_res.txt";
+        std::ofstream fout(out_fname.c_str());
+        if (!fout) {
+            std::cerr << "Check failed: Cannot write to output file " << out_fname << std::endl;
+            rc = 1;
+            break;
+        }
+        std::cout << "Writing info to: " << out_fname << std::endl;
+        std::vector<int> hcounter((size_t)forest.K, 0);
+        int total_found = 0;
+        for (const Ranked& r : order) {
+            const hf6d_hypothesis& h = hyp[r.index];
+            if (hcounter[h.cls] < objects[h.cls].instances) {
+                ++hcounter[h.cls];
+                ++total_found;
+                fout << objects[h.cls].name << "(" << hcounter[h.cls] << ")" << ": " << std::endl;
+                fout << eigen_format(h.pose) << std::endl;
+                fout << std::endl;
+            }
+        }
+        fout.close();
+        const std::string rgb_out_fname = fl.output_folder + stem + "_res.png";
+        std::cout << "Writing result image to: " << rgb_out_fname << std::endl;
+        if (!write_png_rgb(rgb_out_fname, bgr, ctx_w, ctx_h)) std::cerr << "cannot write " << rgb_out_fname << std::endl;
+        std::cout << "Detection finished. Total objects found: " << total_found << std::endl;
+    }
+    if (ctx) hf6d_destroy(ctx);
+    if (bgr) hf6d_host_free(bgr);
+    if (depth) hf6d_host_free(depth);
+    return rc;
+}

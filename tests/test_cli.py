@@ -1,0 +1,163 @@
+"""`HoughForest --test` command-line drop-in (csrc/hough_forest_main.cpp) against the reference's process interface:
+flags (main.cpp:9-31), stdin pairs (HFTest.cpp:1238), `_res.txt` / `_res.png` (HFTest.cpp:1261-1311).
+
+CPU part: flag handling, artefact validation before any device is touched, image decoding (vs cv2), no-GPU failure.
+GPU part: an end-to-end run whose `_res.txt` must equal what the C ABI returns for the same frames, formatted the way
+Eigen's operator<< prints a Matrix4f.
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from object_detector_6d_b200 import api, build, synth
+
+cv2 = pytest.importorskip("cv2")
+
+
+@pytest.fixture(scope="module")
+def cli():
+    path = build.build_cli()
+    assert path and os.path.exists(path)
+    return path
+
+
+def run(cli, args, stdin=""):
+    return subprocess.run([cli] + args, input=stdin, capture_output=True, text=True, timeout=300)
+
+
+def fnv1a(b: bytes) -> int:
+    h = 1469598103934665603
+    for x in b:
+        h = ((h ^ x) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+    return h
+
+
+def eigen_format(m):
+    """Eigen default IOFormat: 6 significant digits, cells right-aligned to the widest, single-space separated."""
+    cells = [[f"{float(v):g}" for v in row] for row in np.asarray(m, np.float32).reshape(4, 4)]
+    w = max(len(c) for r in cells for c in r)
+    return "\n".join(" ".join(c.rjust(w) for c in r) for r in cells)
+
+
+def test_flags_and_modes(cli):
+    assert run(cli, []).returncode == 0                       # no mode flag: nothing to do (main.cpp:70-76)
+    r = run(cli, ["--test"])
+    assert r.returncode == 1 and "detector_options_file" in r.stderr
+    r = run(cli, ["--train", "--input", "x", "--output=y", "--trees", "4"])
+    assert r.returncode == 2 and "only --test" in r.stderr
+    r = run(cli, ["--bogus_flag"])
+    assert r.returncode == 1 and "unknown command line flag" in r.stderr
+    assert "usage" in run(cli, ["-help"]).stdout
+
+
+def test_artefacts_are_validated_before_a_device_is_selected(cli, tmp_path):
+    r = run(cli, ["--test", "--detector_options_file", str(tmp_path / "missing.txt")])
+    assert r.returncode == 1 and "Cannot use options file" in r.stderr
+    opt = tmp_path / "opt.txt"
+    synth.write_options(str(opt), str(tmp_path / "no_forest"), str(tmp_path / "w.bin"), K=2)
+    r = run(cli, ["--test", f"--detector_options_file={opt}"])
+    assert r.returncode == 1 and "Cannot load forest" in r.stderr
+    opt.write_text(opt.read_text() + "no_such_field: 3\n")
+    r = run(cli, ["--test", f"--detector_options_file={opt}"])
+    assert r.returncode == 1 and "no_such_field" in r.stderr
+
+
+def test_image_decoding_matches_cv2(cli, tmp_path):
+    rng = np.random.default_rng(5)
+    h, w = 37, 53
+    bgr = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    depth = rng.integers(0, 65536, (h, w), dtype=np.uint16)
+    grey = rng.integers(0, 256, (h, w), dtype=np.uint8)
+    files = {}
+    cv2.imwrite(str(tmp_path / "c.png"), bgr)                                          # RGB8, adaptive filters
+    cv2.imwrite(str(tmp_path / "c9.png"), bgr, [cv2.IMWRITE_PNG_COMPRESSION, 9])
+    cv2.imwrite(str(tmp_path / "a.png"), np.dstack([bgr, grey]))                       # RGBA8
+    cv2.imwrite(str(tmp_path / "g.png"), grey)                                         # grey 8 as a colour image
+    cv2.imwrite(str(tmp_path / "d.png"), depth)                                        # grey 16
+    cv2.imwrite(str(tmp_path / "c.ppm"), bgr)
+    cv2.imwrite(str(tmp_path / "d.pgm"), depth)
+    pairs = [("c.png", "d.png", bgr), ("c9.png", "d.pgm", bgr), ("a.png", "d.png", bgr), ("c.ppm", "d.png", bgr),
+             ("g.png", "d.png", np.dstack([grey] * 3))]
+    stdin = "".join(f"{tmp_path / a} {tmp_path / b}\n" for a, b, _ in pairs)
+    r = run(cli, ["--check_inputs"], stdin)
+    assert r.returncode == 0, r.stdout + r.stderr
+    lines = r.stdout.strip().splitlines()
+    assert len(lines) == len(pairs)
+    for line, (a, b, want) in zip(lines, pairs):
+        # what cv::imread(rgb) / cv::imread(depth, ANYDEPTH|ANYCOLOR) give the reference (HFTest.cpp:1241-1247)
+        ref_bgr = cv2.imread(str(tmp_path / a))
+        ref_d = cv2.imread(str(tmp_path / b), cv2.IMREAD_ANYDEPTH | cv2.IMREAD_ANYCOLOR)
+        assert np.array_equal(ref_bgr, want) and np.array_equal(ref_d, depth)
+        assert line == (f"bgr {w}x{h} {fnv1a(ref_bgr.tobytes()):016x} depth {w}x{h} {fnv1a(ref_d.tobytes()):016x}"), (a, b)
+    # unreadable / wrong files are reported and skipped, as the reference does
+    (tmp_path / "junk.png").write_bytes(b"not a png")
+    r = run(cli, ["--check_inputs"], f"{tmp_path / 'junk.png'} {tmp_path / 'd.png'}\n{tmp_path / 'c.png'} {tmp_path / 'c.png'}\n")
+    assert r.returncode == 4 and r.stdout.count("Cannot read file") == 2
+
+
+def _write_case(tmp_path, n_frames=2):
+    from tests.helpers import make_case
+    cam = synth.Camera(320, 240, 287.5, 287.5, 159.5, 119.5)
+    cs = make_case(str(tmp_path), K=2, T=2, seed=5, max_depth=10, votes_per_leaf=4, cam=cam, calib_patches=3000)
+    opt = tmp_path / "detector_options.proto"
+    synth.write_options(str(opt), cs["forest_dir"], cs["weights"], K=2, cam=cam, segmented=True)
+    frames = []
+    for i in range(n_frames):
+        bgr, depth = (cs["bgr"], cs["depth"]) if i == 0 else synth.render_frame(40 + i, cam, n_objects=3)
+        cv2.imwrite(str(tmp_path / f"frame{i}.png"), bgr)
+        cv2.imwrite(str(tmp_path / f"frame{i}_depth.png"), depth)
+        frames.append((bgr, depth))
+    return cs, opt, frames
+
+
+def test_no_gpu_means_no_detection(cli, tmp_path):
+    """The product path fails loudly without a device (exit 3, message from the C ABI); it never falls back."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("box has a GPU")
+    cs, opt, frames = _write_case(tmp_path, 1)
+    out = tmp_path / "out"
+    out.mkdir()
+    r = run(cli, ["--test", f"--detector_options_file={opt}", f"--output_folder={out}"],
+            f"{tmp_path / 'frame0.png'} {tmp_path / 'frame0_depth.png'}\n")
+    assert r.returncode == 3 and "no CUDA device" in r.stderr
+    assert not list(out.iterdir())
+
+
+@pytest.mark.gpu
+def test_cli_end_to_end_matches_the_c_abi(cli, tmp_path):
+    cs, opt, frames = _write_case(tmp_path, 2)
+    out = tmp_path / "out"
+    out.mkdir()
+    stdin = "".join(f"{tmp_path / f'frame{i}.png'} {tmp_path / f'frame{i}_depth.png'}\n" for i in range(len(frames)))
+    stdin += f"{tmp_path / 'absent.png'} {tmp_path / 'frame0_depth.png'}\n"
+    r = run(cli, ["--test", f"--detector_options_file={opt}", f"--output_dir={out}", "--stage_times"], stdin)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count("Detection finished. Total objects found:") == len(frames)
+    assert f"Cannot read file: {tmp_path / 'absent.png'}" in r.stdout
+    assert "Number of patches:" in r.stdout and "Generating Hypotheses for class: obj0" in r.stdout
+
+    o, objs = api.parse_options(str(opt))
+    det = api.Detector(options_path=str(opt), frame_size=(320, 240), device=0)
+    for i, (bgr, depth) in enumerate(frames):
+        hyp = det.detect(bgr, depth)
+        final = ((hyp["yawpitch_score"] + hyp["roll_score"]) / np.float32(2.0)) * np.float32(o.pose_score_coeff) + \
+            hyp["loc_score"] * np.float32(o.location_score_coeff)
+        order = np.argsort(-final, kind="stable")
+        want, seen = [], {}
+        for j in order:
+            c = int(hyp["cls"][j])
+            if seen.get(c, 0) < objs[c]["instances"]:
+                seen[c] = seen.get(c, 0) + 1
+                want.append(f"{objs[c]['name']}({seen[c]}): \n{eigen_format(hyp['pose'][j])}\n\n")
+        got = (out / f"frame{i}_res.txt").read_text()
+        assert got == "".join(want)
+        if i == 0:
+            assert len(want) > 0
+        img = cv2.imread(str(out / f"frame{i}_res.png"))
+        assert np.array_equal(img, bgr)
+    det.close()
