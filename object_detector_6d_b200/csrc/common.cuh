@@ -30,14 +30,16 @@ struct DevForest {
     const int32_t* leaf_base;  // [T+1]
     const int32_t* group_off;  // [L+1]
     const VoteGroup* groups;
-    const float *ox, *oy, *oz;
+    const float* oz;           // per vote: z of R(yaw,pitch,roll)*(-x,-y,-z) (the z-histogram re-walk reads only this)
+    const float4* vote4;       // per vote: (ox, oy, oz, bits: cls | w << 5) -- one 16-byte load casts a vote
+    const int32_t* vgroup;     // per vote: its group (read only for votes that land in a centre window)
+    const int2* leaf_votes;    // per leaf: (first vote, number of gated votes) over all its groups (contiguous)
     const short4* bins;        // per vote: integer-degree yaw, pitch, roll bins (HFTest.cpp:779-780, :863)
 };
 
 // x86 cvttss2si semantics: NaN / out of range -> INT_MIN (CUDA's cast saturates and maps NaN to 0).
 __device__ __forceinline__ int f2i_x86(float y) {
-    if (!(y == y) || y >= 2147483648.0f || y < -2147483648.0f) return INT_MIN;
-    return (int)y;
+    return fabsf(y) < 2147483648.0f ? (int)y : INT_MIN;  // the comparison is false for NaN; -2^31 itself maps to INT_MIN either way
 }
 
 __device__ __forceinline__ unsigned long long mix64(unsigned long long z) {

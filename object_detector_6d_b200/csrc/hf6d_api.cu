@@ -69,7 +69,7 @@ struct Slot {
     int* list_n = nullptr;
     unsigned long long *zacc = nullptr, *ypacc = nullptr, *yptmp = nullptr, *racc = nullptr;
     float* ypblur = nullptr;
-    unsigned long long* rowkey = nullptr;
+    unsigned long long* bmax = nullptr;  // [maps][block rows][block cols] key-maxima of 8x8 blocks (NMS)
     unsigned* win_cnt = nullptr;  // [S][n_groups] window entries per (slot, vote group)
     // result block (one D2H)
     uint8_t* res_dev = nullptr;
@@ -101,6 +101,7 @@ struct hf6d_ctx {
     int yp_left0 = 0, yp_nleft = 0, yp_top0 = 0, yp_ntop = 0;  // NMS window origins on the yaw/pitch map
     ResultLayout rl{};
     int lanes_per_hit = 32;      // lanes that share one (slot, group) pair: 16 when no vote group holds more than 16 votes
+    int wc_ctas_per_sm = 1;      // resident CTAs of window_count_kernel per SM
     int shard_rank = 0, shard_world = 1;
     int encoder_mode = 0;
     int debug_capture = 0;
@@ -173,9 +174,22 @@ int upload_model(hf6d_ctx* c) {
     if ((r = dev_upload(c, dm.allocs, &dm.f.leaf_base, hf.leaf_base))) return r;
     if ((r = dev_upload(c, dm.allocs, &dm.f.group_off, hf.group_off))) return r;
     if ((r = dev_upload(c, dm.allocs, &dm.f.groups, hf.groups))) return r;
-    if ((r = dev_upload(c, dm.allocs, &dm.f.ox, hf.ox))) return r;
-    if ((r = dev_upload(c, dm.allocs, &dm.f.oy, hf.oy))) return r;
     if ((r = dev_upload(c, dm.allocs, &dm.f.oz, hf.oz))) return r;
+    if ((r = dev_upload(c, dm.allocs, &dm.f.vgroup, hf.vgroup))) return r;
+    {
+        std::vector<float4> v4(hf.ox.size());
+        for (size_t i = 0; i < v4.size(); ++i) {
+            const VoteGroup& vg = hf.groups[hf.vgroup[i]];
+            const uint32_t meta = (uint32_t)vg.cls | (vg.w << 5);  // cls < 32, w <= 65536
+            float mf;
+            memcpy(&mf, &meta, 4);
+            v4[i] = make_float4(hf.ox[i], hf.oy[i], hf.oz[i], mf);
+        }
+        if ((r = dev_upload(c, dm.allocs, &dm.f.vote4, v4))) return r;
+        std::vector<int2> lv(hf.leaf_vbeg.size());
+        for (size_t i = 0; i < lv.size(); ++i) lv[i] = make_int2(hf.leaf_vbeg[i], hf.leaf_vcnt[i]);
+        if ((r = dev_upload(c, dm.allocs, &dm.f.leaf_votes, lv))) return r;
+    }
     {
         std::vector<short4> bins(hf.yaw.size());
         for (size_t i = 0; i < bins.size(); ++i) bins[i] = make_short4(hf.yaw[i], hf.pitch[i], hf.roll[i], 0);
@@ -251,7 +265,7 @@ int alloc_slot(hf6d_ctx* c, Slot& s) {
     if ((r = dev_alloc(c, s.allocs, &s.blurred, HW * K))) return r;
     const int n_lists = std::max(K, S);
     if ((r = dev_alloc(c, s.allocs, &s.list, (size_t)n_lists * NMS_LIST_CAP))) return r;
-    if ((r = dev_alloc(c, s.allocs, &s.list_n, (size_t)n_lists))) return r;
+    if ((r = dev_alloc(c, s.allocs, &s.list_n, (size_t)n_lists + 1))) return r;  // +1: batch counter of the pose pass
     const size_t yp = (size_t)c->reg.ny * c->reg.np;
     const size_t yp_tmp = (size_t)c->reg.ny * c->yp_blur.nc, yp_out = (size_t)c->yp_blur.nr * c->yp_blur.nc;
     if ((r = dev_alloc(c, s.allocs, &s.zacc, (size_t)S * HF6D_Z_BINS))) return r;
@@ -259,9 +273,8 @@ int alloc_slot(hf6d_ctx* c, Slot& s) {
     if ((r = dev_alloc(c, s.allocs, &s.yptmp, (size_t)S * yp_tmp))) return r;
     if ((r = dev_alloc(c, s.allocs, &s.ypblur, (size_t)S * yp_out))) return r;
     {
-        const size_t rm_centres = HW * K;  // rowmax scratch: centre maps, or the yaw/pitch maps
-        const size_t rm_pose = (size_t)S * c->yp_blur.nr * std::max(c->yp_nleft, 1);
-        if ((r = dev_alloc(c, s.allocs, &s.rowkey, std::max(rm_centres, rm_pose)))) return r;
+        const BlockGrid b1 = make_block_grid(MapRect{0, 0, g.H, g.W}), b2 = make_block_grid(c->yp_blur);
+        if ((r = dev_alloc(c, s.allocs, &s.bmax, std::max((size_t)K * b1.by * b1.bx, (size_t)S * b2.by * b2.bx)))) return r;
     }
     if ((r = dev_alloc(c, s.allocs, &s.win_cnt, (size_t)S * c->hf.groups.size()))) return r;
     if ((r = dev_alloc(c, s.allocs, &s.racc, (size_t)S * MAX_YP * HF6D_POSE_BINS))) return r;
@@ -412,13 +425,11 @@ int run_stage(hf6d_ctx* c, Slot& s, int stage) {
             // reference loop bounds: lefts 0..cols-wx, tops 0..rows-2*wy+1 (HFTest.cpp:246-249)
             const int n_left = g.W - w + 1, n_top = g.H - 2 * w + 2;
             if (n_left > 0 && n_top > 0) {
-                nms_rowmax_kernel<<<dim3((g.H + NMS_ROW_WARPS - 1) / NMS_ROW_WARPS, K), NMS_ROW_WARPS * 32,
-                                    (size_t)NMS_ROW_WARPS * 2 * (n_left + w - 1) * 8, st>>>(s.blurred, s.rowkey, full, w, 0,
-                                                                                             n_left, nullptr);
+                const BlockGrid bg = make_block_grid(full);
+                nms_blockmax_kernel<<<dim3((g.W + 31) / 32, (bg.by + 7) / 8, K), 256, 0, st>>>(s.blurred, s.bmax, full, nullptr);
                 LAUNCH_CHECK(c, s);
-                nms_emit_kernel<<<dim3((n_left + NMS_COL_TW - 1) / NMS_COL_TW, (n_top + NMS_COL_TH - 1) / NMS_COL_TH, K),
-                                  NMS_COL_THREADS, nms_col_smem_bytes(w), st>>>(s.rowkey, full, w, w, 0, n_left, 0, n_top,
-                                                                                s.list, s.list_n, nullptr);
+                nms_select_kernel<<<dim3((bg.by * bg.bx + NMS_SELECT_THREADS - 1) / NMS_SELECT_THREADS, 1, K), NMS_SELECT_THREADS, 0, st>>>(s.blurred, s.bmax, full, w, w, 0, n_left, 0,
+                                                                                         n_top, s.list, s.list_n, nullptr);
                 LAUNCH_CHECK(c, s);
             }
             ObjectLimits lim;
@@ -444,16 +455,20 @@ int run_stage(hf6d_ctx* c, Slot& s, int stage) {
                 CU_TRY(c, cudaMemsetAsync(s.racc + s0 * max_yp * HF6D_POSE_BINS, 0, (size_t)n * max_yp * HF6D_POSE_BINS * 8, st));
                 CU_TRY(c, cudaMemsetAsync(s.win_cnt + s0 * c->hf.groups.size(), 0, (size_t)n * c->hf.groups.size() * 4, st));
             }
-            CU_TRY(c, cudaMemsetAsync(s.list_n, 0, (size_t)std::max(K, S) * 4, st));
+            CU_TRY(c, cudaMemsetAsync(s.list_n, 0, ((size_t)std::max(K, S) + 1) * 4, st));
             const long long items = (long long)g.cap * f.T;
-            const int blocks = (int)std::min<long long>((items + VOTE_THREADS - 1) / VOTE_THREADS, (long long)c->sms * 8);
             CentreTable ct{rv.centres, rv.active};
             const int half_win = p.centers_nms_wsize / 2;
             const int n_groups = (int)c->hf.groups.size();
             const size_t cell_bytes = cell_grid_bytes(g.W, g.H, half_win, K);
             const int table_blocks = c->sms * 8;
-            window_count_kernel<<<blocks, VOTE_THREADS, cell_bytes, st>>>(f, g, switches_of(c), s.locs, s.depth, s.leaf_ord,
-                                                                          s.counts, ct, half_win, n_groups, s.win_cnt, s.zacc);
+            {
+                // one resident wave; batches of 32 items are handed out through list_n[n_lists] (zeroed above)
+                const int wc_blocks = (int)std::min<long long>((items + VOTE_THREADS - 1) / VOTE_THREADS, (long long)c->sms * c->wc_ctas_per_sm);
+                window_count_kernel<<<wc_blocks, VOTE_THREADS, cell_bytes, st>>>(f, g, switches_of(c), s.locs, s.depth, s.leaf_ord,
+                                                                               s.counts, ct, half_win, n_groups,
+                                                                               s.list_n + std::max(K, S), s.win_cnt, s.zacc);
+            }
             LAUNCH_CHECK(c, s);
             if (c->lanes_per_hit == 16)
                 yawpitch_from_counts_kernel<16><<<table_blocks, TABLE_THREADS, 0, st>>>(f, s.win_cnt, n_groups, rv.active, S, c->reg, s.ypacc);
@@ -473,14 +488,11 @@ int run_stage(hf6d_ctx* c, Slot& s, int stage) {
                 s.yptmp, s.ypblur, md, rin, rout, kb, 1.0 / ((double)kb * kb), rv.active);
             LAUNCH_CHECK(c, s);
             if (c->yp_nleft > 0 && c->yp_ntop > 0) {
-                nms_rowmax_kernel<<<dim3((rout.nr + NMS_ROW_WARPS - 1) / NMS_ROW_WARPS, S), NMS_ROW_WARPS * 32,
-                                    (size_t)NMS_ROW_WARPS * 2 * (c->yp_nleft + w - 1) * 8, st>>>(
-                    s.ypblur, s.rowkey, rout, w, c->yp_left0, c->yp_nleft, rv.active);
+                const BlockGrid bg = make_block_grid(rout);
+                nms_blockmax_kernel<<<dim3((rout.nc + 31) / 32, (bg.by + 7) / 8, S), 256, 0, st>>>(s.ypblur, s.bmax, rout, rv.active);
                 LAUNCH_CHECK(c, s);
-                nms_emit_kernel<<<dim3((c->yp_nleft + NMS_COL_TW - 1) / NMS_COL_TW, (c->yp_ntop + NMS_COL_TH - 1) / NMS_COL_TH, S),
-                                  NMS_COL_THREADS, nms_col_smem_bytes(w), st>>>(s.rowkey, rout, w, w, c->yp_left0, c->yp_nleft,
-                                                                                c->yp_top0, c->yp_ntop, s.list, s.list_n,
-                                                                                rv.active);
+                nms_select_kernel<<<dim3((bg.by * bg.bx + NMS_SELECT_THREADS - 1) / NMS_SELECT_THREADS, 1, S), NMS_SELECT_THREADS, 0, st>>>(
+                    s.ypblur, s.bmax, rout, w, w, c->yp_left0, c->yp_nleft, c->yp_top0, c->yp_ntop, s.list, s.list_n, rv.active);
                 LAUNCH_CHECK(c, s);
             }
             select_peaks_kernel<<<S, 256, 0, st>>>(s.list, s.list_n, rv.active, max_yp, p.min_yaw_pitch_drop_ratio,
@@ -713,14 +725,14 @@ int finish_create(hf6d_ctx* c, int device, int n_slots) {
     CU_TRY(c, cudaFuncSetAttribute(traverse_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)traverse_smem_bytes(c->hf.F)));
     CU_TRY(c, cudaFuncSetAttribute(traverse_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)traverse_smem_bytes(c->hf.F)));
     CU_TRY(c, cudaFuncSetAttribute(traverse_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)traverse_smem_bytes(c->hf.F)));
-    CU_TRY(c, cudaFuncSetAttribute(nms_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)std::max(nms_col_smem_bytes(p.centers_nms_wsize), nms_col_smem_bytes(p.pose_nms_wsize))));
-    CU_TRY(c, cudaFuncSetAttribute(nms_rowmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)((size_t)NMS_ROW_WARPS * 2 * (std::max(p.W, HF6D_POSE_BINS) + 128) * 8)));
-    if (cell_grid_bytes(p.W, p.H, p.centers_nms_wsize / 2, K) > 160 * 1024)
+    if (cell_grid_bytes(p.W, p.H, p.centers_nms_wsize / 2, K) > 96 * 1024)
         return fail(c, HF6D_EINVAL, "frame too large for the centre-window lookup grid");
+    if ((long long)g.cap * c->hf.T >= (1LL << 31)) return fail(c, HF6D_EINVAL, "patches x trees exceeds 2^31");
     CU_TRY(c, cudaFuncSetAttribute(window_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)cell_grid_bytes(p.W, p.H, p.centers_nms_wsize / 2, K)));
+    CU_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->wc_ctas_per_sm, window_count_kernel, VOTE_THREADS,
+                                                             cell_grid_bytes(p.W, p.H, p.centers_nms_wsize / 2, K)));
+    c->wc_ctas_per_sm = std::max(1, c->wc_ctas_per_sm);
     CU_TRY(c, cudaFuncSetAttribute(box_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)((size_t)BLUR_WARPS * (std::max(p.W, HF6D_POSE_BINS) + 1) * 8)));
 

@@ -47,6 +47,8 @@ struct HostForest {
     // per gated vote, SoA
     std::vector<float> ox, oy, oz;          // R(yaw,pitch,roll) * (-x,-y,-z): the patch-independent part of HFTest.cpp:41-102
     std::vector<int16_t> yaw, pitch, roll;  // integer-degree bins (HFTest.cpp:779-780, :863), saturated to +-30000
+    std::vector<int32_t> vgroup;            // [votes] vote -> its group
+    std::vector<int32_t> leaf_vbeg, leaf_vcnt;  // [L] all gated votes of a leaf are contiguous: first vote, count
     int64_t n_internal = 0;
 };
 
@@ -161,6 +163,7 @@ inline bool load_forest(const std::string& dir, HostForest& hf, std::string& err
                         float R[9];
                         rot_from_ypr(v[0], v[1], v[2], R);
                         const float vx = -v[3], vy = -v[4], vz = -v[5];
+                        hf.vgroup.push_back((int32_t)hf.groups.size() - 1);
                         hf.ox.push_back((R[0] * vx + R[1] * vy) + R[2] * vz);
                         hf.oy.push_back((R[3] * vx + R[4] * vy) + R[5] * vz);
                         hf.oz.push_back((R[6] * vx + R[7] * vy) + R[8] * vz);
@@ -170,6 +173,12 @@ inline bool load_forest(const std::string& dir, HostForest& hf, std::string& err
                     }
                 }
                 hf.group_off.push_back((int32_t)hf.groups.size());
+                {
+                    const int32_t g0 = hf.group_off[hf.group_off.size() - 2], g1 = hf.group_off.back();
+                    const int32_t vb = g1 > g0 ? hf.groups[g0].vbeg : (int32_t)hf.ox.size();
+                    hf.leaf_vbeg.push_back(vb);
+                    hf.leaf_vcnt.push_back((int32_t)hf.ox.size() - vb);
+                }
             } else {
                 int32_t hdr[3];
                 if (!fb.get(hdr, 12) || !fb.get(&n.thr, 4)) { err = "truncated " + path; return false; }

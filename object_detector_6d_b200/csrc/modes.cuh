@@ -7,11 +7,11 @@
 //  * box blur   = exact 64-bit integer window sums (row pass on a per-row prefix sum in shared memory, column pass as a
 //                 running sum), scaled once in double:  (float)((double)S / 65536 * 1/(kx*ky))  -- what cv::blur does
 //                 on CV_32F (double accumulation, single scale) without its summation-order dependence.
-//  * NMS        = separable sliding-window maximum over 64-bit keys  (value bits | ~row | ~col)  computed by window
-//                 doubling in shared memory (row pass, then column pass); the key order reproduces the reference's
-//                 monotonic-deque tie-breaking, and a window emits only if its maximum sits at the window centre.
-//                 The reference's loop-bound quirk (the vertical pass stops at rows-wy, so the bottom wy-1 window rows
-//                 are never produced) is kept.
+//  * NMS        = tiled neighbour reduction: key-maxima of 8x8 blocks, candidates pruned against the blocks inside their
+//                 window, exact warp-cooperative verification of the survivors.  A window emits only if no element
+//                 beats its centre under the order (value desc, row asc, col asc), which is the reference's
+//                 monotonic-deque tie-breaking.  The reference's loop-bound quirk (the vertical pass stops at rows-wy,
+//                 so the bottom wy-1 window rows are never produced) is kept.
 //  * top-N      = block-wide selection on a sort key (score desc, then emission order x-major).
 #pragma once
 #include "common.cuh"
@@ -116,100 +116,151 @@ box_cols_kernel(const unsigned long long* __restrict__ tmp, float* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------------ NMS
-// Separable sliding-window maximum over 64-bit keys  (value bits | ~row | ~col).  Values are >= 0, so float bits order
-// like unsigned integers; ~row / ~col make the maximum pick the topmost row, then the leftmost column among equal
-// values -- the element the reference's two monotonic deques keep at their front (HFTest.cpp:232-262).
-//   1. rowkey[r][left] = max key of in[r][left .. left+wx-1]         one warp per row, window doubling in shared memory
-//   2. key(left, top)  = max of rowkey[top .. top+wy-1][left]        32 x 64 origins per CTA, doubling along y;
-//      the window emits iff its value != 0 and the winning element is the window centre.
+// The reference's sliding-window NMS (HFTest.cpp:219-268) emits a window iff the window maximum is non-zero and sits
+// at the window centre, where its two monotonic deques resolve ties to the topmost row, then the leftmost column.
+// Equivalently: candidate (ccx, ccy) = (left + wx/2, top + wy/2) is emitted iff its value v != 0 and NO element of the
+// window  [left, left+wx) x [top, top+wy)  "beats" it under the total order  key = (value, ~row, ~col).
+// Tiled neighbour reduction in two kernels:
+//   1. nms_blockmax_kernel: the key-maximum of every aligned 8x8 block of the map (one coalesced pass over the data);
+//   2. nms_select_kernel  : one lane per block.  A window wider than 15 contains its centre's own block, so only the
+//      block maximum can be a window maximum (1 candidate in 64 survives); it is then compared with the maxima of the
+//      blocks that overlap its window (a larger maximum that itself lies in the window beats it); the few survivors
+//      are verified exactly, the warp scanning the whole window 512 elements at a time with early exit.
+// The pruning steps only ever reject a candidate because a concrete window element beats it, so the result is exactly
+// the reference's.  Windows narrower than 16 skip the pruning (every element of the block is verified directly).
+// The reference's loop bounds (lefts 0..cols-wx, tops 0..rows-2*wy+1; the bottom wy-1 window rows are never produced)
+// are applied by the caller through the origin ranges.
 constexpr int NMS_LIST_CAP = 4096;
-constexpr int NMS_ROW_WARPS = 4;
+constexpr int NMS_BLOCK = 8;
 
 __device__ __forceinline__ unsigned long long nms_key(float v, int gy, int gx) {
     return ((unsigned long long)__float_as_uint(v) << 32) | ((unsigned long long)(0xFFFFu - (unsigned)gy) << 16) |
            (unsigned long long)(0xFFFFu - (unsigned)gx);
 }
 
-// in: float [M][R.nr][R.nc]; rowkey: u64 [M][R.nr][n_left] for window lefts left0 .. left0+n_left-1 (global coords)
-__global__ void __launch_bounds__(NMS_ROW_WARPS * 32)
-nms_rowmax_kernel(const float* __restrict__ in, unsigned long long* __restrict__ rowkey, MapRect R, int wx, int left0,
-                  int n_left, const uint8_t* __restrict__ map_active) {
-    extern __shared__ unsigned long long s_row[];  // [NMS_ROW_WARPS][2][span], span = n_left + wx - 1
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m = blockIdx.y;
-    if (map_active && !map_active[m]) return;
-    const int r = blockIdx.x * NMS_ROW_WARPS + warp;
-    if (r >= R.nr) return;
-    const int span = n_left + wx - 1;
-    unsigned long long* A = s_row + (size_t)warp * 2 * span;
-    unsigned long long* B = A + span;
-    const float* src = in + ((size_t)m * R.nr + r) * R.nc;
-    const int gy = R.r0 + r;
-    for (int x = lane; x < span; x += 32) {
-        const int gx = left0 + x, rc = gx - R.c0;
-        A[x] = nms_key((rc >= 0 && rc < R.nc) ? src[rc] : 0.f, gy, gx);
-    }
-    __syncwarp();
-    int p = 1;
-    while (p * 2 <= wx) {
-        for (int x = lane; x < span; x += 32) B[x] = x + p < span ? max(A[x], A[x + p]) : A[x];
-        __syncwarp();
-        unsigned long long* t = A; A = B; B = t;
-        p *= 2;
-    }
-    unsigned long long* dst = rowkey + ((size_t)m * R.nr + r) * n_left;
-    for (int x = lane; x < n_left; x += 32) dst[x] = max(A[x], A[x + (wx - p)]);
+struct BlockGrid {
+    int by, bx;  // blocks per map: ceil(nr / 8), ceil(nc / 8); block (i, j) covers rectangle rows [8i, 8i+8), cols [8j, 8j+8)
+};
+__host__ __device__ __forceinline__ BlockGrid make_block_grid(MapRect R) {
+    return BlockGrid{(R.nr + NMS_BLOCK - 1) / NMS_BLOCK, (R.nc + NMS_BLOCK - 1) / NMS_BLOCK};
 }
 
-constexpr int NMS_COL_TW = 32;   // window origins per CTA in x
-constexpr int NMS_COL_TH = 64;   // and in y
-constexpr int NMS_COL_THREADS = 256;
-inline size_t nms_col_smem_bytes(int wy) { return (size_t)(NMS_COL_TH + wy - 1) * NMS_COL_TW * 8 * 2; }
-
-// Window origins (left, top) in global coordinates: left in [left0, left0+n_left), top in [top0, top0+n_top).
-// Rows outside the rectangle R are zero.  Emits sort keys (score | ~x | ~y) into list[m].
-__global__ void __launch_bounds__(NMS_COL_THREADS)
-nms_emit_kernel(const unsigned long long* __restrict__ rowkey, MapRect R, int wx, int wy, int left0, int n_left,
-                int top0, int n_top, unsigned long long* __restrict__ list, int* __restrict__ list_n,
-                const uint8_t* __restrict__ map_active) {
-    extern __shared__ unsigned long long s_col[];
+// in: float [M][R.nr][R.nc]; bmax: u64 [M][by][bx] key-maximum of each block (values >= 0, so float bits order like
+// unsigned integers).  One warp covers 8 rows x 32 columns = 4 blocks.
+__global__ void __launch_bounds__(256)
+nms_blockmax_kernel(const float* __restrict__ in, unsigned long long* __restrict__ bmax, MapRect R,
+                    const uint8_t* __restrict__ map_active) {
     const int m = blockIdx.z;
     if (map_active && !map_active[m]) return;
-    const int th = NMS_COL_TH + wy - 1;
-    unsigned long long* A = s_col;
-    unsigned long long* B = s_col + (size_t)th * NMS_COL_TW;
-    const int lx0 = blockIdx.x * NMS_COL_TW, ty0 = blockIdx.y * NMS_COL_TH;
-    const unsigned long long* rk = rowkey + (size_t)m * R.nr * n_left;
-    for (int i = threadIdx.x; i < th * NMS_COL_TW; i += NMS_COL_THREADS) {
-        const int y = i / NMS_COL_TW, x = i % NMS_COL_TW;
-        const int rr = top0 + ty0 + y - R.r0, lx = lx0 + x;
-        A[i] = (rr >= 0 && rr < R.nr && lx < n_left) ? rk[(size_t)rr * n_left + lx] : 0ull;
-    }
-    __syncthreads();
-    int p = 1;
-    while (p * 2 <= wy) {
-        for (int i = threadIdx.x; i < th * NMS_COL_TW; i += NMS_COL_THREADS) {
-            const int y = i / NMS_COL_TW;
-            B[i] = y + p < th ? max(A[i], A[i + p * NMS_COL_TW]) : A[i];
+    const BlockGrid bg = make_block_grid(R);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int bi = blockIdx.y * 8 + warp;            // block row
+    if (bi >= bg.by) return;
+    const int col = blockIdx.x * 32 + lane;          // rectangle-local column
+    const float* src = in + (size_t)m * R.nr * R.nc;
+    unsigned long long best = 0;
+    if (col < R.nc) {
+#pragma unroll
+        for (int r = 0; r < NMS_BLOCK; ++r) {
+            const int row = bi * NMS_BLOCK + r;
+            if (row < R.nr) best = max(best, nms_key(__ldg(src + (size_t)row * R.nc + col), R.r0 + row, R.c0 + col));
         }
-        __syncthreads();
-        unsigned long long* t = A; A = B; B = t;
-        p *= 2;
     }
-    for (int i = threadIdx.x; i < NMS_COL_TH * NMS_COL_TW; i += NMS_COL_THREADS) {
-        const int y = i / NMS_COL_TW, x = i % NMS_COL_TW;
-        if (lx0 + x >= n_left || ty0 + y >= n_top) continue;
-        const unsigned long long k = max(A[y * NMS_COL_TW + x], A[(y + (wy - p)) * NMS_COL_TW + x]);
-        const unsigned vb = (unsigned)(k >> 32);
-        if (vb == 0u) continue;
-        const int gy = 0xFFFF - (int)((k >> 16) & 0xFFFFu), gx = 0xFFFF - (int)(k & 0xFFFFu);
-        const int ccx = left0 + lx0 + x + wx / 2, ccy = top0 + ty0 + y + wy / 2;
-        if (gx != ccx || gy != ccy) continue;
-        const int idx = atomicAdd(list_n + m, 1);
-        if (idx < NMS_LIST_CAP)
-            list[(size_t)m * NMS_LIST_CAP + idx] = ((unsigned long long)vb << 32) |
-                                                   ((unsigned long long)(0xFFFFu - (unsigned)ccx) << 16) |
-                                                   (unsigned long long)(0xFFFFu - (unsigned)ccy);
+#pragma unroll
+    for (int o = 1; o < NMS_BLOCK; o <<= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
+    const int bj = col / NMS_BLOCK;
+    if ((lane & (NMS_BLOCK - 1)) == 0 && bj < bg.bx) bmax[((size_t)m * bg.by + bi) * bg.bx + bj] = best;
+}
+
+// Window origins (left, top) in global coordinates: left in [left0, left0+n_left), top in [top0, top0+n_top).
+// Emits sort keys (score | ~x | ~y) into list[m].
+constexpr int NMS_SELECT_THREADS = 64;
+constexpr int NMS_VERIFY_LOADS = 16;  // window elements per lane in flight during the exact verification
+__global__ void __launch_bounds__(NMS_SELECT_THREADS)
+nms_select_kernel(const float* __restrict__ in, const unsigned long long* __restrict__ bmax, MapRect R, int wx, int wy,
+                  int left0, int n_left, int top0, int n_top, unsigned long long* __restrict__ list,
+                  int* __restrict__ list_n, const uint8_t* __restrict__ map_active) {
+    const int m = blockIdx.z;
+    if (map_active && !map_active[m]) return;
+    const BlockGrid bg = make_block_grid(R);
+    const int lane = threadIdx.x & 31;
+    const float* src = in + (size_t)m * R.nr * R.nc;
+    const unsigned long long* bm = bmax + (size_t)m * bg.by * bg.bx;
+    const int lo_x = -(wx / 2), hi_x = wx - 1 - wx / 2, lo_y = -(wy / 2), hi_y = wy - 1 - wy / 2;
+    const bool prune = wx >= 2 * NMS_BLOCK && wy >= 2 * NMS_BLOCK;  // the window then contains the centre's own block
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;           // block id within the map (warp-uniform bound below)
+    const int nb = bg.by * bg.bx;
+    const int bi = b / bg.bx, bj = b % bg.bx;
+    // candidates of this lane: the block maximum (pruned mode) or every element of the block
+    for (int e = 0; e < (prune ? 1 : NMS_BLOCK * NMS_BLOCK); ++e) {
+        int cx = 0, cy = 0;
+        float v = 0.f;
+        bool alive = false;
+        if (b < nb) {
+            if (prune) {
+                const unsigned long long k = bm[b];
+                v = __uint_as_float((unsigned)(k >> 32));
+                cy = 0xFFFF - (int)((k >> 16) & 0xFFFFu);
+                cx = 0xFFFF - (int)(k & 0xFFFFu);
+            } else {
+                const int row = bi * NMS_BLOCK + e / NMS_BLOCK, col = bj * NMS_BLOCK + e % NMS_BLOCK;
+                if (row < R.nr && col < R.nc) {
+                    v = __ldg(src + (size_t)row * R.nc + col);
+                    cy = R.r0 + row;
+                    cx = R.c0 + col;
+                }
+            }
+            const int left = cx + lo_x, top = cy + lo_y;
+            alive = v != 0.f && left >= left0 && left < left0 + n_left && top >= top0 && top < top0 + n_top;
+            if (alive && prune) {
+                // Every block that overlaps the window [cx+lo_x, cx+hi_x] x [cy+lo_y, cy+hi_y] (rectangle-local block
+                // coordinates): a larger block maximum beats the candidate if the block lies completely inside the
+                // window or if the maximum itself does.
+                const unsigned long long mine = nms_key(v, cy, cx);
+                const int wx_lo = cx + lo_x, wx_hi = cx + hi_x, wy_lo = cy + lo_y, wy_hi = cy + hi_y;  // global
+                const int j0 = max(0, (wx_lo - R.c0) >> 3), j1 = min(bg.bx - 1, (wx_hi - R.c0) >> 3);
+                const int i0 = max(0, (wy_lo - R.r0) >> 3), i1 = min(bg.by - 1, (wy_hi - R.r0) >> 3);
+                for (int i = i0; i <= i1 && alive; ++i)
+                    for (int j = j0; j <= j1; ++j) {
+                        const unsigned long long k = bm[(size_t)i * bg.bx + j];
+                        if (k <= mine) continue;
+                        const int ky = 0xFFFF - (int)((k >> 16) & 0xFFFFu), kx = 0xFFFF - (int)(k & 0xFFFFu);
+                        if (ky >= wy_lo && ky <= wy_hi && kx >= wx_lo && kx <= wx_hi) { alive = false; break; }
+                    }
+            }
+        }
+        unsigned todo = __ballot_sync(0xffffffffu, alive);
+        while (todo) {  // exact verification, warp-cooperative: 8 window rows (up to 8 loads per lane in flight) per step
+            const int src_lane = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int ccx = __shfl_sync(0xffffffffu, cx, src_lane), ccy = __shfl_sync(0xffffffffu, cy, src_lane);
+            const float cv = __shfl_sync(0xffffffffu, v, src_lane);
+            bool beaten = false;
+            const int n_el = wx * wy;
+            for (int i0 = 0; i0 < n_el && !beaten; i0 += 32 * NMS_VERIFY_LOADS) {
+                float el[NMS_VERIFY_LOADS];
+                int dxy[NMS_VERIFY_LOADS];
+#pragma unroll
+                for (int r = 0; r < NMS_VERIFY_LOADS; ++r) {
+                    const int i = i0 + r * 32 + lane;
+                    const int wy_i = i / wx, dx = lo_x + (i - wy_i * wx), dy = lo_y + wy_i;
+                    const int rr = ccy + dy - R.r0, rc = ccx + dx - R.c0;
+                    dxy[r] = (dy < 0 || (dy == 0 && dx < 0)) ? 1 : 0;
+                    el[r] = (i < n_el && rr >= 0 && rr < R.nr && rc >= 0 && rc < R.nc) ? __ldg(src + (size_t)rr * R.nc + rc) : 0.f;
+                }
+                bool bt = false;
+#pragma unroll
+                for (int r = 0; r < NMS_VERIFY_LOADS; ++r) bt |= el[r] > cv || (el[r] == cv && dxy[r]);
+                beaten = __any_sync(0xffffffffu, bt);
+            }
+            if (!beaten && lane == 0) {
+                const int idx = atomicAdd(list_n + m, 1);
+                if (idx < NMS_LIST_CAP)
+                    list[(size_t)m * NMS_LIST_CAP + idx] = ((unsigned long long)__float_as_uint(cv) << 32) |
+                                                           ((unsigned long long)(0xFFFFu - (unsigned)ccx) << 16) |
+                                                           (unsigned long long)(0xFFFFu - (unsigned)ccy);
+            }
+        }
     }
 }
 

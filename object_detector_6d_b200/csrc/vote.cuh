@@ -33,36 +33,6 @@ struct PoseRegion {
     int y0, ny, p0, np;
 };
 
-struct ItemCtx {
-    int gb, ge;       // vote-group range of the item's leaf
-    float tx, ty, tz; // back-projected patch centre (HFTest.cpp:83-88)
-};
-
-__device__ __forceinline__ ItemCtx load_item(const DevForest& f, const FrameGeom& g, const int* __restrict__ locs,
-                                             const uint16_t* __restrict__ depth, const int* __restrict__ leaf_ord,
-                                             long long item, long long n_items) {
-    ItemCtx it;
-    it.gb = it.ge = 0;
-    it.tx = it.ty = it.tz = 0.f;
-    if (item < n_items) {
-        const int p = (int)(item / f.T), t = (int)(item % f.T);
-        const int ord = leaf_ord[item];
-        if (ord >= 0) {
-            const int gl = __ldg(f.leaf_base + t) + ord;
-            it.gb = __ldg(f.group_off + gl);
-            it.ge = __ldg(f.group_off + gl + 1);
-            if (it.ge > it.gb) {
-                const int px = locs[2 * p], py = locs[2 * p + 1];
-                const float z = __fdiv_rn((float)depth[(size_t)py * g.W + px], 1000.0f);  // HFTest.cpp:628
-                it.tz = z;
-                it.tx = __fdiv_rn(__fmul_rn(__fsub_rn((float)px, g.cx), z), g.fx);
-                it.ty = __fdiv_rn(__fmul_rn(__fsub_rn((float)py, g.cy), z), g.fy);
-            }
-        }
-    }
-    return it;
-}
-
 // Point3DToImage, HFTest.cpp:21-37
 __device__ __forceinline__ void project(const FrameGeom& g, float x, float y, float z, int& u, int& v) {
     if (z == 0.f) { u = 0; v = 0; return; }
@@ -71,39 +41,103 @@ __device__ __forceinline__ void project(const FrameGeom& g, float x, float y, fl
 }
 
 constexpr int VOTE_THREADS = 256;
+constexpr int VOTE_WARPS = VOTE_THREADS / 32;
+
+// Per-warp staging of one batch of 32 (patch, tree) items: inclusive prefix of their vote counts and what a vote needs
+// from its item -- the back-projected patch centre (HFTest.cpp:83-88) and the offset that turns a position in the
+// batch's flattened vote list into a vote index.
+struct WarpItems {
+    int incl[32];
+    float4 geo[32];  // tx, ty, tz, bits: vbeg - exclusive prefix
+};
+
+// Vote-parallel enumeration of every vote the reference casts (HFTest.cpp:177-214): a warp takes 32 (patch, tree) items,
+// prefix-sums their leaves' vote counts, and then walks the flattened vote list 32 votes at a time -- one vote per lane
+// whatever the votes-per-leaf distribution is; a lane finds its item by a 5-step binary search in shared memory.
+// body(valid, vote index, tx, ty, tz) is called by all 32 lanes (converged), so it may use warp collectives.
+// Batches are handed out dynamically through a global counter (zeroed before the launch) when `next_batch` is given:
+// the work per batch varies a lot in the pose pass (votes cluster where the objects are), and a static stride leaves
+// most warps idle behind the few that own the busy batches.
+template <class Body>
+__device__ __forceinline__ void for_each_cast_vote(const DevForest& f, const FrameGeom& g, const int* __restrict__ locs,
+                                                   const uint16_t* __restrict__ depth, const int* __restrict__ leaf_ord,
+                                                   int n_items, WarpItems& wi, int* next_batch, Body&& body) {
+    const int lane = threadIdx.x & 31;
+    const int warp0 = (blockIdx.x * VOTE_WARPS + (threadIdx.x >> 5)) * 32;
+    const int stride = gridDim.x * VOTE_THREADS;
+    for (int base = warp0;; base += stride) {
+        if (next_batch) {
+            int b = 0;
+            if (lane == 0) b = atomicAdd(next_batch, 1);
+            base = __shfl_sync(0xffffffffu, b, 0) * 32;
+        }
+        if (base >= n_items) break;
+        int vbeg = 0, vcnt = 0;
+        float tx = 0.f, ty = 0.f, tz = 0.f;
+        const int item = base + lane;
+        if (item < n_items) {
+            const int ord = leaf_ord[item];
+            if (ord >= 0) {  // -1: tree owned by another rank
+                const int p = item / f.T, t = item - p * f.T;
+                const int2 lv = __ldg(f.leaf_votes + __ldg(f.leaf_base + t) + ord);
+                vbeg = lv.x;
+                vcnt = lv.y;
+                if (vcnt > 0) {
+                    const int2 pc = *reinterpret_cast<const int2*>(locs + 2 * p);
+                    const float z = __fdiv_rn((float)depth[(size_t)pc.y * g.W + pc.x], 1000.0f);  // HFTest.cpp:628
+                    tz = z;
+                    tx = __fdiv_rn(__fmul_rn(__fsub_rn((float)pc.x, g.cx), z), g.fx);
+                    ty = __fdiv_rn(__fmul_rn(__fsub_rn((float)pc.y, g.cy), z), g.fy);
+                }
+            }
+        }
+        int incl = vcnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int n = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += n;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        __syncwarp();  // the previous batch's readers are done
+        wi.incl[lane] = incl;
+        wi.geo[lane] = make_float4(tx, ty, tz, __int_as_float(vbeg - (incl - vcnt)));
+        __syncwarp();
+        for (int j0 = 0; j0 < total; j0 += 32) {
+            const int j = j0 + lane;
+            const bool valid = j < total;
+            int lo = 0;  // smallest i with incl[i] > j
+            if (valid) {
+#pragma unroll
+                for (int s = 16; s; s >>= 1)
+                    if (wi.incl[lo + s - 1] <= j) lo += s;
+            }
+            const float4 ge = wi.geo[lo];
+            body(valid, __float_as_int(ge.w) + j, ge.x, ge.y, ge.z);
+        }
+    }
+}
 
 __global__ void __launch_bounds__(VOTE_THREADS)
 vote_kernel(DevForest f, FrameGeom g, const __grid_constant__ ObjectSwitches sw, const int* __restrict__ locs,
             const uint16_t* __restrict__ depth, const int* __restrict__ leaf_ord, const int* __restrict__ counts,
             unsigned long long* __restrict__ maps) {
-    const int lane = threadIdx.x & 31;
-    const long long n_items = (long long)counts[1] * f.T;
-    const long long warp0 = ((long long)blockIdx.x * (VOTE_THREADS >> 5) + (threadIdx.x >> 5)) * 32;
-    const long long stride = (long long)gridDim.x * VOTE_THREADS;
-    for (long long base = warp0; base < n_items; base += stride) {
-        const ItemCtx it = load_item(f, g, locs, depth, leaf_ord, base + lane, n_items);
-        unsigned todo = __ballot_sync(0xffffffffu, it.ge > it.gb);
-        while (todo) {
-            const int src = __ffs(todo) - 1;
-            todo &= todo - 1;
-            const int gb = __shfl_sync(0xffffffffu, it.gb, src), ge = __shfl_sync(0xffffffffu, it.ge, src);
-            const float tx = __shfl_sync(0xffffffffu, it.tx, src), ty = __shfl_sync(0xffffffffu, it.ty, src);
-            const float tz = __shfl_sync(0xffffffffu, it.tz, src);
-            for (int gi = gb; gi < ge; ++gi) {
-                const int4 grp = __ldg(reinterpret_cast<const int4*>(f.groups) + gi);  // cls, w, vbeg, vcnt
-                if (!sw.should_detect[grp.x]) continue;
-                unsigned long long* map = maps + (size_t)grp.x * g.H * g.W;
-                for (int v = lane; v < grp.w; v += 32) {
-                    const int vi = grp.z + v;
-                    int uu, vv;
-                    project(g, __fadd_rn(__ldg(f.ox + vi), tx), __fadd_rn(__ldg(f.oy + vi), ty),
-                            __fadd_rn(__ldg(f.oz + vi), tz), uu, vv);
-                    if (uu >= 0 && uu < g.W && vv >= 0 && vv < g.H)
-                        atomicAdd(map + (size_t)vv * g.W + uu, (unsigned long long)(unsigned)grp.y);
-                }
-            }
-        }
-    }
+    __shared__ WarpItems s_items[VOTE_WARPS];
+    __shared__ uint8_t s_detect[HF6D_MAX_CLASSES];
+    if (threadIdx.x < HF6D_MAX_CLASSES) s_detect[threadIdx.x] = sw.should_detect[threadIdx.x];
+    __syncthreads();
+    const size_t HW = (size_t)g.H * g.W;
+    for_each_cast_vote(f, g, locs, depth, leaf_ord, counts[1] * f.T, s_items[threadIdx.x >> 5], nullptr,
+                       [&](bool valid, int vi, float tx, float ty, float tz) {
+                           if (!valid) return;
+                           const float4 v = __ldg(f.vote4 + vi);
+                           const unsigned meta = __float_as_uint(v.w);
+                           const int cls = (int)(meta & 31u);
+                           if (!s_detect[cls]) return;
+                           int uu, vv;
+                           project(g, __fadd_rn(v.x, tx), __fadd_rn(v.y, ty), __fadd_rn(v.z, tz), uu, vv);
+                           if (uu >= 0 && uu < g.W && vv >= 0 && vv < g.H)
+                               atomicAdd(maps + (size_t)cls * HW + (size_t)vv * g.W + uu, (unsigned long long)(meta >> 5));
+                       });
 }
 
 // ------------------------------------------------------------------------------------------------ pose pass A
@@ -127,137 +161,153 @@ __device__ __forceinline__ void load_centres(SharedCentres& sc, const CentreTabl
     __syncthreads();
 }
 
-// bit k set <=> (u, v) lies in the window of active centre k of class c
-__device__ __forceinline__ unsigned window_mask(const SharedCentres& sc, int c, int nctr, int half_win, int uu, int vv) {
-    unsigned m = 0;
-    for (int k = 0; k < nctr; ++k) {
-        const int ccx = sc.ctr[c].c[k].x, ccy = sc.ctr[c].c[k].y;
-        const bool hit = sc.act[c][k] && vv >= ccy - half_win && vv < ccy + half_win && uu >= ccx - half_win &&
-                         uu < ccx + half_win;
-        m |= (unsigned)hit << k;
-    }
-    return m;
-}
-
-// Coarse lookup in shared memory: the image (plus a margin of one window) is cut into cells of half_win pixels; a cell
-// holds the OR of the centres whose window touches it.  Most votes hit an empty cell and skip the exact window tests.
+// Coarse lookup in shared memory: the image (plus a margin of two cells) is cut into square cells whose side is the
+// smallest power of two >= half_win; a cell holds the OR of the centres whose window touches it.  Most votes hit an
+// empty cell and skip the exact window tests.
 struct CellGrid {
-    int cell, gx, gy, x0, y0;  // cell size, grid size, pixel of cell (0,0)
+    int shift, gx, gy, x0, y0;  // log2(cell side), grid size, pixel of cell (0,0)
 };
 __host__ __device__ __forceinline__ CellGrid make_cell_grid(int W, int H, int half_win) {
     CellGrid cg;
-    cg.cell = half_win > 0 ? half_win : 1;
-    cg.x0 = -2 * cg.cell;
-    cg.y0 = -2 * cg.cell;
-    cg.gx = (W + 4 * cg.cell + cg.cell - 1) / cg.cell;
-    cg.gy = (H + 4 * cg.cell + cg.cell - 1) / cg.cell;
+    cg.shift = 0;
+    while ((1 << cg.shift) < half_win) ++cg.shift;
+    const int cell = 1 << cg.shift;
+    cg.x0 = -2 * cell;
+    cg.y0 = -2 * cell;
+    cg.gx = (W + 4 * cell + cell - 1) >> cg.shift;
+    cg.gy = (H + 4 * cell + cell - 1) >> cg.shift;
     return cg;
 }
 inline size_t cell_grid_bytes(int W, int H, int half_win, int K) {
     const CellGrid cg = make_cell_grid(W, H, half_win);
-    return ((size_t)cg.gx * cg.gy * K * sizeof(uint16_t) + 7) / 8 * 8;
+    return ((size_t)cg.gx * cg.gy * K * sizeof(uint16_t) + 15) / 16 * 16;
 }
+
+// Per-warp staging of the window entries found in one chunk of 32 votes (see window_count_kernel).
+struct WarpHits {
+    int incl[32];        // inclusive prefix of the entries' leaf-vote counts (INT_MAX beyond the last entry)
+    float zz[32];        // depth of the window pixel [m]
+    int vb[32];          // first vote of the entry's group minus the exclusive prefix
+    unsigned w[32];      // Q16 weight
+    unsigned cm[32];     // class << 16 | mask of the centres whose window holds the entry
+};
 
 // Pass A.1: enumerate the cast votes again (same arithmetic as vote_kernel, so the same pixels).  For every vote that
 // falls in the window of an active centre ("entry" of the reference's center_leaf_map):
 //   * cnt[slot][group] += 1                  -- everything the entry contributes to the yaw/pitch and roll maps depends
 //                                               only on its leaf, so those maps are built later from these counts;
 //   * z histogram of the slot: the WINDOW pixel's depth stands in for the patch centre and every vote of the leaf is
-//     re-projected (HFTest.cpp:766-775), so this part is per entry.
+//     re-projected (HFTest.cpp:766-775), so this part is per entry: the (entry, leaf vote) pairs of a chunk are
+//     flattened over the 32 lanes again (prefix sum + search in shared memory), one 64-bit atomic per pair and slot.
 __global__ void __launch_bounds__(VOTE_THREADS)
 window_count_kernel(DevForest f, FrameGeom g, const __grid_constant__ ObjectSwitches sw, const int* __restrict__ locs,
                     const uint16_t* __restrict__ depth, const int* __restrict__ leaf_ord,
-                    const int* __restrict__ counts, CentreTable ct, int half_win, int n_groups,
+                    const int* __restrict__ counts, CentreTable ct, int half_win, int n_groups, int* next_batch,
                     unsigned* __restrict__ cnt /*[S][n_groups]*/, unsigned long long* __restrict__ zacc /*[S][Z_BINS]*/) {
     __shared__ SharedCentres sc;
-    extern __shared__ uint16_t s_cells[];  // [K][gy][gx]
+    __shared__ WarpItems s_items[VOTE_WARPS];
+    __shared__ WarpHits s_hits[VOTE_WARPS];
+    __shared__ unsigned s_classes;  // classes that are detected and have at least one active centre
+    extern __shared__ __align__(16) uint8_t wc_smem[];
+    uint16_t* s_cells = reinterpret_cast<uint16_t*>(wc_smem);  // [K][gy][gx]
     load_centres(sc, ct, f.K);
     const CellGrid cg = make_cell_grid(g.W, g.H, half_win);
     const int cells_per_class = cg.gx * cg.gy;
+    const int S = f.K * HF6D_MAX_CENTRES;
     for (int i = threadIdx.x; i < f.K * cells_per_class; i += blockDim.x) s_cells[i] = 0;
+    if (threadIdx.x == 0) s_classes = 0;
     __syncthreads();
-    for (int i = threadIdx.x; i < f.K * HF6D_MAX_CENTRES; i += blockDim.x) {
+    for (int i = threadIdx.x; i < S; i += blockDim.x) {
         const int c = i / HF6D_MAX_CENTRES, k = i % HF6D_MAX_CENTRES;
-        if (k >= sc.ctr[c].n || !sc.act[c][k]) continue;
+        if (k >= sc.ctr[c].n || !sc.act[c][k] || !sw.should_detect[c]) continue;
+        atomicOr(&s_classes, 1u << c);
         const int x_lo = sc.ctr[c].c[k].x - half_win, y_lo = sc.ctr[c].c[k].y - half_win;
-        for (int y = y_lo; y < y_lo + 2 * half_win + cg.cell; y += cg.cell)
-            for (int x = x_lo; x < x_lo + 2 * half_win + cg.cell; x += cg.cell) {
-                const int yy = min(y, y_lo + 2 * half_win - 1), xx = min(x, x_lo + 2 * half_win - 1);
-                const int cyi = (yy - cg.y0) / cg.cell, cxi = (xx - cg.x0) / cg.cell;
-                if (cxi < 0 || cxi >= cg.gx || cyi < 0 || cyi >= cg.gy) continue;
-                // 16-bit atomicOr through the containing 32-bit word
-                const int idx = c * cells_per_class + cyi * cg.gx + cxi;
+        const int cx0 = max(0, (x_lo - cg.x0) >> cg.shift), cx1 = min(cg.gx - 1, (x_lo + 2 * half_win - 1 - cg.x0) >> cg.shift);
+        const int cy0 = max(0, (y_lo - cg.y0) >> cg.shift), cy1 = min(cg.gy - 1, (y_lo + 2 * half_win - 1 - cg.y0) >> cg.shift);
+        for (int cyi = cy0; cyi <= cy1; ++cyi)
+            for (int cxi = cx0; cxi <= cx1; ++cxi) {
+                const int idx = c * cells_per_class + cyi * cg.gx + cxi;  // 16-bit atomicOr through the containing word
                 atomicOr(reinterpret_cast<unsigned*>(s_cells) + (idx >> 1), (1u << k) << ((idx & 1) * 16));
             }
     }
     __syncthreads();
-
+    const unsigned classes = s_classes;
     const int lane = threadIdx.x & 31;
-    const long long n_items = (long long)counts[1] * f.T;
-    const long long warp0 = ((long long)blockIdx.x * (VOTE_THREADS >> 5) + (threadIdx.x >> 5)) * 32;
-    const long long stride = (long long)gridDim.x * VOTE_THREADS;
-    for (long long base = warp0; base < n_items; base += stride) {
-        const ItemCtx it = load_item(f, g, locs, depth, leaf_ord, base + lane, n_items);
-        unsigned todo = __ballot_sync(0xffffffffu, it.ge > it.gb);
-        while (todo) {
-            const int src = __ffs(todo) - 1;
-            todo &= todo - 1;
-            const int gb = __shfl_sync(0xffffffffu, it.gb, src), ge = __shfl_sync(0xffffffffu, it.ge, src);
-            const float tx = __shfl_sync(0xffffffffu, it.tx, src), ty = __shfl_sync(0xffffffffu, it.ty, src);
-            const float tz = __shfl_sync(0xffffffffu, it.tz, src);
-            for (int gi = gb; gi < ge; ++gi) {
-                const int4 grp = __ldg(reinterpret_cast<const int4*>(f.groups) + gi);
-                const int c = grp.x;
-                if (!sw.should_detect[c]) continue;
-                const int nctr = sc.ctr[c].n;
-                if (nctr == 0) continue;
-                const unsigned long long w = (unsigned)grp.y;
-                for (int v0 = 0; v0 < grp.w; v0 += 32) {
-                    const int v = v0 + lane;
-                    int uu = INT_MIN, vv = INT_MIN;
-                    unsigned mask = 0;
-                    if (v < grp.w) {
-                        const int vi = grp.z + v;
-                        project(g, __fadd_rn(__ldg(f.ox + vi), tx), __fadd_rn(__ldg(f.oy + vi), ty),
-                                __fadd_rn(__ldg(f.oz + vi), tz), uu, vv);
-                        const int cxi = uu >= cg.x0 ? (uu - cg.x0) / cg.cell : -1, cyi = vv >= cg.y0 ? (vv - cg.y0) / cg.cell : -1;
-                        unsigned cand = 0;
-                        if (cxi >= 0 && cxi < cg.gx && cyi >= 0 && cyi < cg.gy)
-                            cand = s_cells[c * cells_per_class + cyi * cg.gx + cxi];
-                        while (cand) {  // exact test for the few centres whose window touches the cell
-                            const int k = __ffs(cand) - 1;
-                            cand &= cand - 1;
-                            const int ccx = sc.ctr[c].c[k].x, ccy = sc.ctr[c].c[k].y;
-                            const bool hit = vv >= ccy - half_win && vv < ccy + half_win && uu >= ccx - half_win && uu < ccx + half_win;
-                            mask |= (unsigned)hit << k;
-                        }
-                    }
-                    unsigned slots = __reduce_or_sync(0xffffffffu, mask);
-                    while (slots) {  // warp-uniform: every centre window that received an entry from this chunk
-                        const int k = __ffs(slots) - 1;
-                        slots &= slots - 1;
-                        unsigned hm = __ballot_sync(0xffffffffu, (mask >> k) & 1u);
-                        const size_t s = (size_t)c * HF6D_MAX_CENTRES + k;
-                        if (lane == 0) atomicAdd(cnt + s * n_groups + gi, (unsigned)__popc(hm));
-                        unsigned long long* zs = zacc + s * HF6D_Z_BINS;
-                        while (hm) {
-                            const int j = __ffs(hm) - 1;
-                            hm &= hm - 1;
-                            const int col = __shfl_sync(0xffffffffu, uu, j), row = __shfl_sync(0xffffffffu, vv, j);
-                            if (row < 0 || row >= g.H || col < 0 || col >= g.W) continue;  // reference reads out of bounds
-                            const unsigned d = depth[(size_t)row * g.W + col];
-                            if (d == 0) continue;
-                            const float zz = __fdiv_rn((float)d, 1000.0f);
-                            for (int q = lane; q < grp.w; q += 32) {
-                                const int zb = f2i_x86(__fdiv_rn(__fadd_rn(__ldg(f.oz + grp.z + q), zz), 0.01f));
-                                if (zb >= 0 && zb < HF6D_Z_BINS) atomicAdd(zs + zb, w);
-                            }
-                        }
-                    }
+    WarpHits& wh = s_hits[threadIdx.x >> 5];
+    for_each_cast_vote(f, g, locs, depth, leaf_ord, counts[1] * f.T, s_items[threadIdx.x >> 5], next_batch,
+                       [&](bool valid, int vi, float tx, float ty, float tz) {
+        unsigned mask = 0;
+        int c = 0, uu = 0, vv = 0;
+        if (valid) {
+            const float4 v = __ldg(f.vote4 + vi);
+            c = (int)(__float_as_uint(v.w) & 31u);
+            if ((classes >> c) & 1u) {
+                project(g, __fadd_rn(v.x, tx), __fadd_rn(v.y, ty), __fadd_rn(v.z, tz), uu, vv);
+                const int cxi = (uu - cg.x0) >> cg.shift, cyi = (vv - cg.y0) >> cg.shift;  // negative stays negative
+                unsigned cand = 0;
+                if (cxi >= 0 && cxi < cg.gx && cyi >= 0 && cyi < cg.gy) cand = s_cells[c * cells_per_class + cyi * cg.gx + cxi];
+                while (cand) {  // exact test for the few centres whose window touches the cell
+                    const int k = __ffs(cand) - 1;
+                    cand &= cand - 1;
+                    const int ccx = sc.ctr[c].c[k].x, ccy = sc.ctr[c].c[k].y;
+                    const bool hit = vv >= ccy - half_win && vv < ccy + half_win && uu >= ccx - half_win && uu < ccx + half_win;
+                    mask |= (unsigned)hit << k;
                 }
             }
         }
-    }
+        if (!__ballot_sync(0xffffffffu, mask != 0)) return;  // the common case: no lane of this chunk hit a window
+        int4 grp = make_int4(0, 0, 0, 0);
+        float zz = 0.f;
+        bool zok = false;
+        if (mask) {
+            const int gi = __ldg(f.vgroup + vi);
+            grp = __ldg(reinterpret_cast<const int4*>(f.groups) + gi);  // cls, w, vbeg, vcnt
+            if (vv >= 0 && vv < g.H && uu >= 0 && uu < g.W) {  // the reference reads out of bounds here
+                const unsigned d = depth[(size_t)vv * g.W + uu];
+                if (d != 0) { zz = __fdiv_rn((float)d, 1000.0f); zok = true; }
+            }
+            for (unsigned m = mask; m; m &= m - 1)
+                atomicAdd(cnt + (size_t)(c * HF6D_MAX_CENTRES + __ffs(m) - 1) * n_groups + gi, 1u);
+        }
+        const unsigned zl = __ballot_sync(0xffffffffu, zok);
+        if (!zl) return;
+        // flatten the (entry, leaf vote) pairs of this chunk over the lanes
+        int incl = zok ? grp.w : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int n = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += n;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        wh.incl[lane] = INT_MAX;
+        __syncwarp();
+        if (zok) {
+            const int r = __popc(zl & ((1u << lane) - 1u));
+            wh.incl[r] = incl;
+            wh.zz[r] = zz;
+            wh.vb[r] = grp.z - (incl - grp.w);
+            wh.w[r] = (unsigned)grp.y;
+            wh.cm[r] = ((unsigned)c << 16) | mask;
+        }
+        __syncwarp();
+        for (int p0 = 0; p0 < total; p0 += 32) {
+            const int pidx = p0 + lane;
+            if (pidx < total) {
+                int h = 0;  // smallest h with incl[h] > pidx
+#pragma unroll
+                for (int s = 16; s; s >>= 1)
+                    if (wh.incl[h + s - 1] <= pidx) h += s;
+                const int zb = f2i_x86(__fdiv_rn(__fadd_rn(__ldg(f.oz + wh.vb[h] + pidx), wh.zz[h]), 0.01f));
+                if (zb >= 0 && zb < HF6D_Z_BINS) {
+                    const unsigned cm = wh.cm[h];
+                    const unsigned long long w = wh.w[h];
+                    unsigned long long* zs = zacc + (size_t)(cm >> 16) * HF6D_MAX_CENTRES * HF6D_Z_BINS + zb;
+                    for (unsigned m = cm & 0xFFFFu; m; m &= m - 1) atomicAdd(zs + (size_t)(__ffs(m) - 1) * HF6D_Z_BINS, w);
+                }
+            }
+        }
+        __syncwarp();
+    });
 }
 
 // Pass A.2: yaw/pitch maps from the (slot, group) entry counts: every entry re-walks all votes of its leaf
