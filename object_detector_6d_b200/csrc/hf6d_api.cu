@@ -225,7 +225,7 @@ int upload_model(hf6d_ctx* c) {
                 w[(size_t)n * dm.k_pad[l] + k] = __float2bfloat16(v);
             }
         std::vector<float> b(dm.n_pad[l], 0.f);
-        for (int n = 0; n < L.out; ++n) b[n] = L.b[n];
+        for (int n = 0; n < L.out; ++n) b[n] = last ? L.b[n] : 0.5f * L.b[n];  // hidden layers evaluate tanh(x/2)
         const __nv_bfloat16* wp = nullptr;
         const float* bp = nullptr;
         if ((r = dev_upload(c, dm.allocs, &wp, w))) return r;
@@ -295,14 +295,14 @@ int alloc_slot(hf6d_ctx* c, Slot& s) {
         if (!make_bf16_kmajor_map(&L.tmA, a_in[l], (uint64_t)g.cap, (uint64_t)dm.k_pad[l], ENC_BLOCK_M) ||
             !make_bf16_kmajor_map(&L.tmB, dm.W[l], (uint64_t)dm.n_pad[l], (uint64_t)dm.k_pad[l], (uint32_t)dm.block_n[l]))
             return fail(c, HF6D_ECUDA, "cuTensorMapEncodeTiled failed for encoder layer %d", l);
-        L.bias = dm.b[l];
-        L.out = outs[l];
         L.last = l == 2;
-        L.out_ld = L.last ? F : dm.n_pad[l];
-        L.n_valid = L.last ? dm.n_out[l] : dm.n_pad[l];
+        if (!make_out_map(&L.tmC, outs[l], (uint64_t)g.cap, (uint64_t)(L.last ? F : dm.n_pad[l]), L.last ? 4 : 2))
+            return fail(c, HF6D_ECUDA, "cuTensorMapEncodeTiled failed for the output of encoder layer %d", l);
+        L.bias = dm.b[l];
         L.K = dm.k_pad[l];
         L.n_pad = dm.n_pad[l];
         L.block_n = dm.block_n[l];
+        L.short_k = dm.k_pad[l] / ENC_BLOCK_K <= 6;
     }
     return HF6D_OK;
 }
