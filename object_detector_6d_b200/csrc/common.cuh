@@ -42,6 +42,18 @@ __device__ __forceinline__ int f2i_x86(float y) {
     return fabsf(y) < 2147483648.0f ? (int)y : INT_MIN;  // the comparison is false for NaN; -2^31 itself maps to INT_MIN either way
 }
 
+// x / Y for a compile-time constant Y without the IEEE division sequence: q = x * RN(1/Y), one FMA for the exact
+// remainder, one FMA to correct.  Bit-identical to x / Y for every x with |x| in [1e-30, 1e30) and for x = +0 (checked
+// exhaustively over all 2^32 floats for Y = 3, 64, 192, 255, 1000, 0.01 by tools/check_const_division.c); callers
+// guarantee the range, or only use the truncated integer part (tiny / huge / infinite x then give the same integer).
+template <int NUM, int DEN>
+__device__ __forceinline__ float div_const(float x) {
+    constexpr float Y = (float)NUM / (float)DEN;
+    constexpr float R = 1.0f / Y;
+    const float q = __fmul_rn(x, R);
+    return __fmaf_rn(__fmaf_rn(-Y, q, x), R, q);
+}
+
 __device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
     z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
     z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;

@@ -111,17 +111,48 @@ __device__ __forceinline__ float blend(const Bilerp& b, float t00, float t10, fl
     return s;
 }
 
+// The reference's texture holds (B/255, G/255, R/255, depth mm) per texel (HFTest.cpp:370-379).  Here a texel is 8 bytes,
+// {B | G<<8 | R<<16, depth}: one 8-byte load instead of three byte loads and a 16-bit load (the gather is bound by load
+// instructions, not by bytes), converted to the reference's float values in registers.  2.4 MB at 640x480: L2 resident.
+__global__ void pack_frame_kernel(const uint8_t* __restrict__ bgr, const uint16_t* __restrict__ depth, int n_px,
+                                  uint2* __restrict__ tex) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_px) return;
+    const uint8_t* p = bgr + (size_t)i * 3;
+    tex[i] = make_uint2((unsigned)p[0] | ((unsigned)p[1] << 8) | ((unsigned)p[2] << 16), (unsigned)depth[i]);
+}
+
 constexpr int GATHER_PATCHES_PER_CTA = 16;
 constexpr int GATHER_THREADS = GATHER_PATCHES_PER_CTA * 8;
+constexpr int GATHER_ROW = 258;    // floats per patch row of the term buffer: 2 (mod 32), so the 32 chains below hit 32 banks
+constexpr int GATHER_D_OFF = 193;  // depth terms start here: 1 (mod 32)
+
+// The reference's strictly sequential float accumulation (HFTest.cpp:508-534: `mean += x / N` element by element, c ->
+// row -> col) for all 16 patches of the CTA at once: lane 2p walks the 192 colour terms of patch p, lane 2p+1 its 64
+// depth terms -- 32 independent chains, one warp, conflict-free shared-memory reads.
+__device__ __forceinline__ void sequential_sums(const float (*term)[GATHER_ROW], float (*stat)[4], int first_stat) {
+    if (threadIdx.x < 32) {
+        const int pl = threadIdx.x >> 1, which = threadIdx.x & 1;
+        const float* src = term[pl] + (which ? GATHER_D_OFF : 0);
+        float m = 0.f;
+#pragma unroll 16
+        for (int j = 0; j < 64; ++j) m = __fadd_rn(m, src[j]);
+        if (!which) {
+#pragma unroll 16
+            for (int j = 64; j < 192; ++j) m = __fadd_rn(m, src[j]);
+        }
+        stat[pl][first_stat + which] = m;
+    }
+}
 
 // 8 threads per patch (one per patch row), 16 patches per CTA.  ps == 8 only (the 256-input encoder).
 // a_out : bf16 [cap][256], CHW order, value = q (exact integer 0..255)
 // q_out : optional uint8 [cap][256] (debug capture / parity)
 __global__ void __launch_bounds__(GATHER_THREADS)
-gather_normalise_kernel(const uint8_t* __restrict__ bgr, const uint16_t* __restrict__ depth, FrameGeom g,
-                        const int* __restrict__ locs, const int* __restrict__ counts,
+gather_normalise_kernel(const uint2* __restrict__ tex, FrameGeom g, const int* __restrict__ locs,
+                        const int* __restrict__ counts,
                         __nv_bfloat16* __restrict__ a_out, uint8_t* __restrict__ q_out) {
-    __shared__ float s_term[GATHER_PATCHES_PER_CTA][257];  // +1: the per-patch chains of one warp hit distinct banks
+    __shared__ float s_term[GATHER_PATCHES_PER_CTA][GATHER_ROW];
     __shared__ float s_stat[GATHER_PATCHES_PER_CTA][4];  // mean_rgb, mean_d, var_rgb, var_d
 
     const int Pp = counts[1];
@@ -133,8 +164,9 @@ gather_normalise_kernel(const uint8_t* __restrict__ bgr, const uint16_t* __restr
 
     float val[4][8];
     if (live) {
-        const int cx = locs[2 * p], cy = locs[2 * p + 1];
-        const float dc = __fdiv_rn((float)depth[(size_t)cy * g.W + cx], 1000.0f);  // exact texel fetch, :253
+        const int2 ctr = *reinterpret_cast<const int2*>(locs + 2 * p);
+        const int cx = ctr.x, cy = ctr.y;
+        const float dc = div_const<1000, 1>((float)tex[(size_t)cy * g.W + cx].y);  // exact texel fetch, :253
         const int a = adaptive_size(g, dc);
         const int x0 = cx - a / 2, y0 = cy - a / 2;
         const float step = __fdiv_rn((float)a, (float)g.ps);
@@ -142,35 +174,42 @@ gather_normalise_kernel(const uint8_t* __restrict__ bgr, const uint16_t* __restr
         if (g.fill_random) {
             // counter-based stand-in for the clock64()-seeded cuRAND draw of patch_extractor.cu:236-244
             const unsigned long long z = mix64(g.fill_seed + 0x9E3779B97F4A7C15ULL * (unsigned long long)(p + 1));
-            const float r = __fdiv_rn((float)((z & 0xFFFF) % 255), 255.0f);
-            const float gg = __fdiv_rn((float)(((z >> 16) & 0xFFFF) % 255), 255.0f);
-            const float b = __fdiv_rn((float)(((z >> 32) & 0xFFFF) % 255), 255.0f);
-            const float d = __fdiv_rn((float)(((z >> 48) & 0xFFFF) % 255), 255.0f);
-            fill[0] = b; fill[1] = gg; fill[2] = r; fill[3] = d;
+            fill[2] = div_const<255, 1>((float)((z & 0xFFFF) % 255));
+            fill[1] = div_const<255, 1>((float)(((z >> 16) & 0xFFFF) % 255));
+            fill[0] = div_const<255, 1>((float)(((z >> 32) & 0xFFFF) % 255));
+            fill[3] = div_const<255, 1>((float)(((z >> 48) & 0xFFFF) % 255));
         }
         const float v = __fadd_rn((float)y0, __fmul_rn((float)ty, step));
+        // the row pair (j, j+1) and the vertical weights are shared by the 8 samples of this thread
+        const float fv = floorf(v);
+        const int j = (int)fv;
+        const float c = frac8(__fsub_rn(v, fv)), nc = __fsub_rn(1.0f, c);
+        const bool in_y0 = j >= 0 && j < g.H, in_y1 = j + 1 >= 0 && j + 1 < g.H;
 #pragma unroll
         for (int tx = 0; tx < 8; ++tx) {
             const float u = __fadd_rn((float)x0, __fmul_rn((float)tx, step));
-            const Bilerp b = make_bilerp(u, v);
-            const bool in_x0 = b.i >= 0 && b.i < g.W, in_x1 = b.i + 1 >= 0 && b.i + 1 < g.W;
-            const bool in_y0 = b.j >= 0 && b.j < g.H, in_y1 = b.j + 1 >= 0 && b.j + 1 < g.H;
-            const size_t o00 = (size_t)b.j * g.W + b.i;
+            const float fu = floorf(u);
+            const int i = (int)fu;
+            const float al = frac8(__fsub_rn(u, fu)), na = __fsub_rn(1.0f, al);
+            Bilerp b;
+            b.w00 = __fmul_rn(na, nc);
+            b.w10 = __fmul_rn(al, nc);
+            b.w01 = __fmul_rn(na, c);
+            b.w11 = __fmul_rn(al, c);
+            const bool in_x0 = i >= 0 && i < g.W, in_x1 = i + 1 >= 0 && i + 1 < g.W;
+            const uint2* t0 = tex + ((size_t)j * g.W + i);
             const bool k00 = in_x0 && in_y0, k10 = in_x1 && in_y0, k01 = in_x0 && in_y1, k11 = in_x1 && in_y1;
-            const float d00 = k00 ? (float)__ldg(depth + o00) : 0.f;
-            const float d10 = k10 ? (float)__ldg(depth + o00 + 1) : 0.f;
-            const float d01 = k01 ? (float)__ldg(depth + o00 + g.W) : 0.f;
-            const float d11 = k11 ? (float)__ldg(depth + o00 + g.W + 1) : 0.f;
-            const float d = __fdiv_rn(blend(b, d00, d10, d01, d11), 1000.0f);
+            const uint2 zero = make_uint2(0u, 0u);  // border texel
+            const uint2 q00 = k00 ? __ldg(t0) : zero, q10 = k10 ? __ldg(t0 + 1) : zero;
+            const uint2 q01 = k01 ? __ldg(t0 + g.W) : zero, q11 = k11 ? __ldg(t0 + g.W + 1) : zero;
+            const float d = div_const<1000, 1>(blend(b, (float)q00.y, (float)q10.y, (float)q01.y, (float)q11.y));
             if (d > 0.f) {
 #pragma unroll
-                for (int ch = 0; ch < 3; ++ch) {
-                    const float t00 = k00 ? __fdiv_rn((float)__ldg(bgr + o00 * 3 + ch), 255.0f) : 0.f;
-                    const float t10 = k10 ? __fdiv_rn((float)__ldg(bgr + (o00 + 1) * 3 + ch), 255.0f) : 0.f;
-                    const float t01 = k01 ? __fdiv_rn((float)__ldg(bgr + (o00 + g.W) * 3 + ch), 255.0f) : 0.f;
-                    const float t11 = k11 ? __fdiv_rn((float)__ldg(bgr + (o00 + g.W + 1) * 3 + ch), 255.0f) : 0.f;
-                    val[ch][tx] = blend(b, t00, t10, t01, t11);
-                }
+                for (int ch = 0; ch < 3; ++ch)
+                    val[ch][tx] = blend(b, div_const<255, 1>((float)((q00.x >> (8 * ch)) & 0xFFu)),
+                                        div_const<255, 1>((float)((q10.x >> (8 * ch)) & 0xFFu)),
+                                        div_const<255, 1>((float)((q01.x >> (8 * ch)) & 0xFFu)),
+                                        div_const<255, 1>((float)((q11.x >> (8 * ch)) & 0xFFu)));
                 float td = __fadd_rn(__fdiv_rn(__fsub_rn(d, dc), g.range), 0.5f);
                 if (td > 1.0f) td = 1.0f;
                 if (td < 0.0f) td = 0.0f;
@@ -192,19 +231,10 @@ gather_normalise_kernel(const uint8_t* __restrict__ bgr, const uint16_t* __restr
     for (int ch = 0; ch < 4; ++ch)
 #pragma unroll
         for (int tx = 0; tx < 8; ++tx)
-            s_term[pl][ch * 64 + ty * 8 + tx] = __fdiv_rn(val[ch][tx], ch < 3 ? 192.0f : 64.0f);
+            s_term[pl][(ch < 3 ? ch * 64 : GATHER_D_OFF) + ty * 8 + tx] =
+                ch < 3 ? div_const<192, 1>(val[ch][tx]) : __fmul_rn(val[ch][tx], 1.0f / 64.0f);
     __syncthreads();
-    if (ty == 0) {
-        float m = 0.f;
-#pragma unroll 16
-        for (int j = 0; j < 192; ++j) m = __fadd_rn(m, s_term[pl][j]);
-        s_stat[pl][0] = m;
-    } else if (ty == 1) {
-        float m = 0.f;
-#pragma unroll 16
-        for (int j = 192; j < 256; ++j) m = __fadd_rn(m, s_term[pl][j]);
-        s_stat[pl][1] = m;
-    }
+    sequential_sums(s_term, s_stat, 0);
     __syncthreads();
     const float mean_rgb = s_stat[pl][0], mean_d = s_stat[pl][1];
     // ---- "std" (variance, never sqrt'ed; float d*d) (HFTest.cpp:527-534)
@@ -213,20 +243,11 @@ gather_normalise_kernel(const uint8_t* __restrict__ bgr, const uint16_t* __restr
 #pragma unroll
         for (int tx = 0; tx < 8; ++tx) {
             const float d = __fsub_rn(val[ch][tx], ch < 3 ? mean_rgb : mean_d);
-            s_term[pl][ch * 64 + ty * 8 + tx] = __fdiv_rn(__fmul_rn(d, d), ch < 3 ? 192.0f : 64.0f);
+            const float dd = __fmul_rn(d, d);
+            s_term[pl][(ch < 3 ? ch * 64 : GATHER_D_OFF) + ty * 8 + tx] = ch < 3 ? div_const<192, 1>(dd) : __fmul_rn(dd, 1.0f / 64.0f);
         }
     __syncthreads();
-    if (ty == 0) {
-        float m = 0.f;
-#pragma unroll 16
-        for (int j = 0; j < 192; ++j) m = __fadd_rn(m, s_term[pl][j]);
-        s_stat[pl][2] = m;
-    } else if (ty == 1) {
-        float m = 0.f;
-#pragma unroll 16
-        for (int j = 192; j < 256; ++j) m = __fadd_rn(m, s_term[pl][j]);
-        s_stat[pl][3] = m;
-    }
+    sequential_sums(s_term, s_stat, 2);
     __syncthreads();
     if (!live) return;
     const float lim_rgb = __fmul_rn(3.0f, s_stat[pl][2]), lim_d = __fmul_rn(3.0f, s_stat[pl][3]);

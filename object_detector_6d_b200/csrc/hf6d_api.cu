@@ -52,6 +52,7 @@ struct Slot {
     // frame
     uint8_t* bgr = nullptr;       // frame the kernels read: own_bgr or a caller-owned device frame (hf6d_bind_frame)
     uint16_t* depth = nullptr;
+    uint2* tex = nullptr;         // packed texels {B | G<<8 | R<<16, depth mm} built from bgr + depth by the gather stage
     uint8_t* own_bgr = nullptr;
     uint16_t* own_depth = nullptr;
     cudaEvent_t ev_enc[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -252,6 +253,7 @@ int alloc_slot(hf6d_ctx* c, Slot& s) {
     if ((r = dev_alloc(c, s.allocs, &s.own_depth, HW))) return r;
     s.bgr = s.own_bgr;
     s.depth = s.own_depth;
+    if ((r = dev_alloc(c, s.allocs, &s.tex, HW))) return r;
     if ((r = dev_alloc(c, s.allocs, &s.row_count, (size_t)g.gh))) return r;
     if ((r = dev_alloc(c, s.allocs, &s.locs, (size_t)g.cap * 2))) return r;
     if ((r = dev_alloc(c, s.allocs, &s.A0, (size_t)g.cap * c->dm.k_pad[0]))) return r;
@@ -373,8 +375,10 @@ int run_stage(hf6d_ctx* c, Slot& s, int stage) {
             break;
         }
         case HF6D_STAGE_GATHER: {
+            pack_frame_kernel<<<(g.W * g.H + 255) / 256, 256, 0, st>>>(s.bgr, s.depth, g.W * g.H, s.tex);
+            LAUNCH_CHECK(c, s);
             gather_normalise_kernel<<<g.cap / GATHER_PATCHES_PER_CTA, GATHER_THREADS, 0, st>>>(
-                s.bgr, s.depth, g, s.locs, s.counts, s.A0, c->debug_capture ? s.q_u8 : nullptr);
+                s.tex, g, s.locs, s.counts, s.A0, c->debug_capture ? s.q_u8 : nullptr);
             LAUNCH_CHECK(c, s);
             break;
         }

@@ -84,7 +84,7 @@ __device__ __forceinline__ void for_each_cast_vote(const DevForest& f, const Fra
                 vcnt = lv.y;
                 if (vcnt > 0) {
                     const int2 pc = *reinterpret_cast<const int2*>(locs + 2 * p);
-                    const float z = __fdiv_rn((float)depth[(size_t)pc.y * g.W + pc.x], 1000.0f);  // HFTest.cpp:628
+                    const float z = div_const<1000, 1>((float)depth[(size_t)pc.y * g.W + pc.x]);  // HFTest.cpp:628
                     tz = z;
                     tx = __fdiv_rn(__fmul_rn(__fsub_rn((float)pc.x, g.cx), z), g.fx);
                     ty = __fdiv_rn(__fmul_rn(__fsub_rn((float)pc.y, g.cy), z), g.fy);
@@ -264,7 +264,7 @@ window_count_kernel(DevForest f, FrameGeom g, const __grid_constant__ ObjectSwit
             grp = __ldg(reinterpret_cast<const int4*>(f.groups) + gi);  // cls, w, vbeg, vcnt
             if (vv >= 0 && vv < g.H && uu >= 0 && uu < g.W) {  // the reference reads out of bounds here
                 const unsigned d = depth[(size_t)vv * g.W + uu];
-                if (d != 0) { zz = __fdiv_rn((float)d, 1000.0f); zok = true; }
+                if (d != 0) { zz = div_const<1000, 1>((float)d); zok = true; }
             }
             for (unsigned m = mask; m; m &= m - 1)
                 atomicAdd(cnt + (size_t)(c * HF6D_MAX_CENTRES + __ffs(m) - 1) * n_groups + gi, 1u);
@@ -297,7 +297,7 @@ window_count_kernel(DevForest f, FrameGeom g, const __grid_constant__ ObjectSwit
 #pragma unroll
                 for (int s = 16; s; s >>= 1)
                     if (wh.incl[h + s - 1] <= pidx) h += s;
-                const int zb = f2i_x86(__fdiv_rn(__fadd_rn(__ldg(f.oz + wh.vb[h] + pidx), wh.zz[h]), 0.01f));
+                const int zb = f2i_x86(div_const<1, 100>(__fadd_rn(__ldg(f.oz + wh.vb[h] + pidx), wh.zz[h])));  // only the integer part is used
                 if (zb >= 0 && zb < HF6D_Z_BINS) {
                     const unsigned cm = wh.cm[h];
                     const unsigned long long w = wh.w[h];
