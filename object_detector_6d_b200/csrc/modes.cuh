@@ -124,8 +124,9 @@ box_cols_kernel(const unsigned long long* __restrict__ tmp, float* __restrict__ 
 //   1. nms_blockmax_kernel: the key-maximum of every aligned 8x8 block of the map (one coalesced pass over the data);
 //   2. nms_select_kernel  : one lane per block.  A window wider than 15 contains its centre's own block, so only the
 //      block maximum can be a window maximum (1 candidate in 64 survives); it is then compared with the maxima of the
-//      blocks that overlap its window (a larger maximum that itself lies in the window beats it); the few survivors
-//      are verified exactly, the warp scanning the whole window 512 elements at a time with early exit.
+//      blocks that overlap its window: a larger maximum that itself lies in the window beats it, a block whose
+//      maximum is not larger cannot hold a beating element, and the (rare) remaining "suspect" blocks -- larger
+//      maximum outside the window -- have their in-window elements checked by the warp, 64 elements at a time.
 // The pruning steps only ever reject a candidate because a concrete window element beats it, so the result is exactly
 // the reference's.  Windows narrower than 16 skip the pruning (every element of the block is verified directly).
 // The reference's loop bounds (lefts 0..cols-wx, tops 0..rows-2*wy+1; the bottom wy-1 window rows are never produced)
@@ -188,14 +189,22 @@ nms_select_kernel(const float* __restrict__ in, const unsigned long long* __rest
     const unsigned long long* bm = bmax + (size_t)m * bg.by * bg.bx;
     const int lo_x = -(wx / 2), hi_x = wx - 1 - wx / 2, lo_y = -(wy / 2), hi_y = wy - 1 - wy / 2;
     const bool prune = wx >= 2 * NMS_BLOCK && wy >= 2 * NMS_BLOCK;  // the window then contains the centre's own block
+    auto emit = [&](int ex, int ey, float ev) {
+        const int idx = atomicAdd(list_n + m, 1);
+        if (idx < NMS_LIST_CAP)
+            list[(size_t)m * NMS_LIST_CAP + idx] = ((unsigned long long)__float_as_uint(ev) << 32) |
+                                                   ((unsigned long long)(0xFFFFu - (unsigned)ex) << 16) |
+                                                   (unsigned long long)(0xFFFFu - (unsigned)ey);
+    };
     const int b = blockIdx.x * blockDim.x + threadIdx.x;           // block id within the map (warp-uniform bound below)
     const int nb = bg.by * bg.bx;
     const int bi = b / bg.bx, bj = b % bg.bx;
     // candidates of this lane: the block maximum (pruned mode) or every element of the block
     for (int e = 0; e < (prune ? 1 : NMS_BLOCK * NMS_BLOCK); ++e) {
-        int cx = 0, cy = 0;
+        int cx = 0, cy = 0, i0 = 0, j0 = 0, nj = 1;
         float v = 0.f;
-        bool alive = false;
+        bool alive = false, scan_all = false;
+        unsigned long long suspects = 0ull;
         if (b < nb) {
             if (prune) {
                 const unsigned long long k = bm[b];
@@ -214,52 +223,82 @@ nms_select_kernel(const float* __restrict__ in, const unsigned long long* __rest
             alive = v != 0.f && left >= left0 && left < left0 + n_left && top >= top0 && top < top0 + n_top;
             if (alive && prune) {
                 // Every block that overlaps the window [cx+lo_x, cx+hi_x] x [cy+lo_y, cy+hi_y] (rectangle-local block
-                // coordinates): a larger block maximum beats the candidate if the block lies completely inside the
-                // window or if the maximum itself does.
+                // coordinates).  A block whose maximum does not beat the candidate holds no element that does.  A block
+                // with a larger maximum beats the candidate at once if that maximum lies in the window; otherwise it
+                // is a "suspect": only its in-window elements still have to be looked at.
                 const unsigned long long mine = nms_key(v, cy, cx);
                 const int wx_lo = cx + lo_x, wx_hi = cx + hi_x, wy_lo = cy + lo_y, wy_hi = cy + hi_y;  // global
-                const int j0 = max(0, (wx_lo - R.c0) >> 3), j1 = min(bg.bx - 1, (wx_hi - R.c0) >> 3);
-                const int i0 = max(0, (wy_lo - R.r0) >> 3), i1 = min(bg.by - 1, (wy_hi - R.r0) >> 3);
+                j0 = max(0, (wx_lo - R.c0) >> 3);
+                i0 = max(0, (wy_lo - R.r0) >> 3);
+                const int j1 = min(bg.bx - 1, (wx_hi - R.c0) >> 3), i1 = min(bg.by - 1, (wy_hi - R.r0) >> 3);
+                nj = j1 - j0 + 1;
+                const bool fits = nj * (i1 - i0 + 1) <= 64;
                 for (int i = i0; i <= i1 && alive; ++i)
                     for (int j = j0; j <= j1; ++j) {
                         const unsigned long long k = bm[(size_t)i * bg.bx + j];
                         if (k <= mine) continue;
                         const int ky = 0xFFFF - (int)((k >> 16) & 0xFFFFu), kx = 0xFFFF - (int)(k & 0xFFFFu);
                         if (ky >= wy_lo && ky <= wy_hi && kx >= wx_lo && kx <= wx_hi) { alive = false; break; }
+                        if (fits) suspects |= 1ull << ((i - i0) * nj + (j - j0));
+                        else scan_all = true;
                     }
+            } else if (alive) {
+                scan_all = true;
             }
         }
+        const float cv = v;
+        if (alive && !scan_all && suspects == 0ull) {  // nothing left that could beat it
+            emit(cx, cy, cv);
+            alive = false;
+        }
         unsigned todo = __ballot_sync(0xffffffffu, alive);
-        while (todo) {  // exact verification, warp-cooperative: 8 window rows (up to 8 loads per lane in flight) per step
+        while (todo) {  // exact verification of what is left, warp-cooperative
             const int src_lane = __ffs(todo) - 1;
             todo &= todo - 1;
             const int ccx = __shfl_sync(0xffffffffu, cx, src_lane), ccy = __shfl_sync(0xffffffffu, cy, src_lane);
-            const float cv = __shfl_sync(0xffffffffu, v, src_lane);
+            const float ccv = __shfl_sync(0xffffffffu, cv, src_lane);
+            const bool all = __shfl_sync(0xffffffffu, (int)scan_all, src_lane) != 0;
             bool beaten = false;
-            const int n_el = wx * wy;
-            for (int i0 = 0; i0 < n_el && !beaten; i0 += 32 * NMS_VERIFY_LOADS) {
-                float el[NMS_VERIFY_LOADS];
-                int dxy[NMS_VERIFY_LOADS];
+            if (!all) {
+                unsigned long long sus = __shfl_sync(0xffffffffu, suspects, src_lane);
+                const int bi0 = __shfl_sync(0xffffffffu, i0, src_lane), bj0 = __shfl_sync(0xffffffffu, j0, src_lane);
+                const int bnj = __shfl_sync(0xffffffffu, nj, src_lane);
+                while (sus && !beaten) {  // the 64 elements of one suspect block, two per lane
+                    const int bit = __ffsll((long long)sus) - 1;
+                    sus &= sus - 1;
+                    const int bi = bi0 + bit / bnj, bj = bj0 + bit % bnj;
+                    bool bt = false;
 #pragma unroll
-                for (int r = 0; r < NMS_VERIFY_LOADS; ++r) {
-                    const int i = i0 + r * 32 + lane;
-                    const int wy_i = i / wx, dx = lo_x + (i - wy_i * wx), dy = lo_y + wy_i;
-                    const int rr = ccy + dy - R.r0, rc = ccx + dx - R.c0;
-                    dxy[r] = (dy < 0 || (dy == 0 && dx < 0)) ? 1 : 0;
-                    el[r] = (i < n_el && rr >= 0 && rr < R.nr && rc >= 0 && rc < R.nc) ? __ldg(src + (size_t)rr * R.nc + rc) : 0.f;
+                    for (int h = 0; h < 2; ++h) {
+                        const int rr = bi * NMS_BLOCK + h * 4 + (lane >> 3), rc = bj * NMS_BLOCK + (lane & 7);
+                        const int dy = R.r0 + rr - ccy, dx = R.c0 + rc - ccx;
+                        if (rr < R.nr && rc < R.nc && dy >= lo_y && dy <= hi_y && dx >= lo_x && dx <= hi_x) {
+                            const float el = __ldg(src + (size_t)rr * R.nc + rc);
+                            bt |= el > ccv || (el == ccv && (dy < 0 || (dy == 0 && dx < 0)));
+                        }
+                    }
+                    beaten = __any_sync(0xffffffffu, bt);
                 }
-                bool bt = false;
+            } else {
+                const int n_el = wx * wy;
+                for (int e0 = 0; e0 < n_el && !beaten; e0 += 32 * NMS_VERIFY_LOADS) {
+                    float el[NMS_VERIFY_LOADS];
+                    int early[NMS_VERIFY_LOADS];
 #pragma unroll
-                for (int r = 0; r < NMS_VERIFY_LOADS; ++r) bt |= el[r] > cv || (el[r] == cv && dxy[r]);
-                beaten = __any_sync(0xffffffffu, bt);
+                    for (int r = 0; r < NMS_VERIFY_LOADS; ++r) {
+                        const int i = e0 + r * 32 + lane;
+                        const int wy_i = i / wx, dx = lo_x + (i - wy_i * wx), dy = lo_y + wy_i;
+                        const int rr = ccy + dy - R.r0, rc = ccx + dx - R.c0;
+                        early[r] = (dy < 0 || (dy == 0 && dx < 0)) ? 1 : 0;
+                        el[r] = (i < n_el && rr >= 0 && rr < R.nr && rc >= 0 && rc < R.nc) ? __ldg(src + (size_t)rr * R.nc + rc) : 0.f;
+                    }
+                    bool bt = false;
+#pragma unroll
+                    for (int r = 0; r < NMS_VERIFY_LOADS; ++r) bt |= el[r] > ccv || (el[r] == ccv && early[r]);
+                    beaten = __any_sync(0xffffffffu, bt);
+                }
             }
-            if (!beaten && lane == 0) {
-                const int idx = atomicAdd(list_n + m, 1);
-                if (idx < NMS_LIST_CAP)
-                    list[(size_t)m * NMS_LIST_CAP + idx] = ((unsigned long long)__float_as_uint(cv) << 32) |
-                                                           ((unsigned long long)(0xFFFFu - (unsigned)ccx) << 16) |
-                                                           (unsigned long long)(0xFFFFu - (unsigned)ccy);
-            }
+            if (!beaten && lane == 0) emit(ccx, ccy, ccv);
         }
     }
 }
