@@ -30,6 +30,7 @@ namespace {
 
 thread_local std::string g_create_error;
 
+constexpr int WA_MAX_DYN_SMEM = 200 * 1024;  // shared-memory z histograms of window_accumulate_kernel
 constexpr int MAX_YP = 16;    // upper bound for max_yaw_pitch_hypotheses
 constexpr int MAX_ROLL = 8;   // upper bound for max_roll_hypotheses
 
@@ -71,6 +72,7 @@ struct Slot {
     unsigned long long *zacc = nullptr, *ypacc = nullptr, *yptmp = nullptr, *racc = nullptr;
     float* ypblur = nullptr;
     unsigned long long* bmax = nullptr;  // [maps][block rows][block cols] key-maxima of 8x8 blocks (NMS)
+    uint4* entries = nullptr;     // window entries of the pose stage: {vote, class << 16 | window mask, pixel depth, -}
     unsigned* win_cnt = nullptr;  // [S][n_groups] window entries per (slot, vote group)
     // result block (one D2H)
     uint8_t* res_dev = nullptr;
@@ -102,7 +104,8 @@ struct hf6d_ctx {
     int yp_left0 = 0, yp_nleft = 0, yp_top0 = 0, yp_ntop = 0;  // NMS window origins on the yaw/pitch map
     ResultLayout rl{};
     int lanes_per_hit = 32;      // lanes that share one (slot, group) pair: 16 when no vote group holds more than 16 votes
-    int wc_ctas_per_sm = 1;      // resident CTAs of window_count_kernel per SM
+    int wc_ctas_per_sm = 1;      // resident CTAs of window_entries_kernel per SM
+    int entry_cap = 0;           // capacity of a frame slot's window-entry list (entries beyond it are accumulated in place)
     int shard_rank = 0, shard_world = 1;
     int encoder_mode = 0;
     int debug_capture = 0;
@@ -267,7 +270,8 @@ int alloc_slot(hf6d_ctx* c, Slot& s) {
     if ((r = dev_alloc(c, s.allocs, &s.blurred, HW * K))) return r;
     const int n_lists = std::max(K, S);
     if ((r = dev_alloc(c, s.allocs, &s.list, (size_t)n_lists * NMS_LIST_CAP))) return r;
-    if ((r = dev_alloc(c, s.allocs, &s.list_n, (size_t)n_lists + 1))) return r;  // +1: batch counter of the pose pass
+    if ((r = dev_alloc(c, s.allocs, &s.list_n, (size_t)n_lists + 2))) return r;  // +2: batch counter, reserved entries (pose pass)
+    if ((r = dev_alloc(c, s.allocs, &s.entries, (size_t)c->entry_cap))) return r;
     const size_t yp = (size_t)c->reg.ny * c->reg.np;
     const size_t yp_tmp = (size_t)c->reg.ny * c->yp_blur.nc, yp_out = (size_t)c->yp_blur.nr * c->yp_blur.nc;
     if ((r = dev_alloc(c, s.allocs, &s.zacc, (size_t)S * HF6D_Z_BINS))) return r;
@@ -459,7 +463,7 @@ int run_stage(hf6d_ctx* c, Slot& s, int stage) {
                 CU_TRY(c, cudaMemsetAsync(s.racc + s0 * max_yp * HF6D_POSE_BINS, 0, (size_t)n * max_yp * HF6D_POSE_BINS * 8, st));
                 CU_TRY(c, cudaMemsetAsync(s.win_cnt + s0 * c->hf.groups.size(), 0, (size_t)n * c->hf.groups.size() * 4, st));
             }
-            CU_TRY(c, cudaMemsetAsync(s.list_n, 0, ((size_t)std::max(K, S) + 1) * 4, st));
+            CU_TRY(c, cudaMemsetAsync(s.list_n, 0, ((size_t)std::max(K, S) + 2) * 4, st));
             const long long items = (long long)g.cap * f.T;
             CentreTable ct{rv.centres, rv.active};
             const int half_win = p.centers_nms_wsize / 2;
@@ -467,11 +471,29 @@ int run_stage(hf6d_ctx* c, Slot& s, int stage) {
             const size_t cell_bytes = cell_grid_bytes(g.W, g.H, half_win, K);
             const int table_blocks = c->sms * 8;
             {
-                // one resident wave; batches of 32 items are handed out through list_n[n_lists] (zeroed above)
+                // one resident wave; batches of 32 items are handed out through list_n[n_lists], list space is reserved
+                // through list_n[n_lists + 1] (both zeroed above)
+                int* ctr = s.list_n + std::max(K, S);
                 const int wc_blocks = (int)std::min<long long>((items + VOTE_THREADS - 1) / VOTE_THREADS, (long long)c->sms * c->wc_ctas_per_sm);
-                window_count_kernel<<<wc_blocks, VOTE_THREADS, cell_bytes, st>>>(f, g, switches_of(c), s.locs, s.depth, s.leaf_ord,
-                                                                               s.counts, ct, half_win, n_groups,
-                                                                               s.list_n + std::max(K, S), s.win_cnt, s.zacc);
+                window_entries_kernel<<<wc_blocks, VOTE_THREADS, cell_bytes, st>>>(f, g, switches_of(c), s.locs, s.depth, s.leaf_ord,
+                                                                                 s.counts, ct, half_win, n_groups, ctr, s.entries,
+                                                                                 c->entry_cap, ctr + 1, s.win_cnt, s.zacc);
+                LAUNCH_CHECK(c, s);
+                if (c->entry_cap >= ENTRY_BLOCK) {
+                    ZSlotTable zt;
+                    memset(&zt, 0, sizeof zt);
+                    for (int k = 0; k < K; ++k)
+                        zt.zoff[k + 1] = (int16_t)(zt.zoff[k] + (c->objects[k].should_detect ? c->objects[k].max_location_hypotheses : 0));
+                    const size_t zbytes = (size_t)zt.zoff[K] * HF6D_Z_BINS * 4;
+                    static const bool smem_z_ok = !(getenv("HF6D_WA_SMEM_Z") && atoi(getenv("HF6D_WA_SMEM_Z")) == 0);  // tuning override
+                    if (smem_z_ok && zbytes <= (size_t)WA_MAX_DYN_SMEM)
+                        window_accumulate_kernel<true><<<c->sms * std::max<size_t>(1, std::min<size_t>(2, (200 * 1024) / (zbytes + 24 * 1024))),
+                                                         WA_THREADS, zbytes, st>>>(f, s.entries, c->entry_cap, ctr + 1, n_groups, zt,
+                                                                                    s.win_cnt, s.zacc);
+                    else
+                        window_accumulate_kernel<false><<<c->sms * 2, WA_THREADS, 0, st>>>(f, s.entries, c->entry_cap, ctr + 1, n_groups,
+                                                                                          zt, s.win_cnt, s.zacc);
+                }
             }
             LAUNCH_CHECK(c, s);
             if (c->lanes_per_hit == 16)
@@ -732,14 +754,25 @@ int finish_create(hf6d_ctx* c, int device, int n_slots) {
     if (cell_grid_bytes(p.W, p.H, p.centers_nms_wsize / 2, K) > 96 * 1024)
         return fail(c, HF6D_EINVAL, "frame too large for the centre-window lookup grid");
     if ((long long)g.cap * c->hf.T >= (1LL << 31)) return fail(c, HF6D_EINVAL, "patches x trees exceeds 2^31");
-    CU_TRY(c, cudaFuncSetAttribute(window_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CU_TRY(c, cudaFuncSetAttribute(window_entries_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)cell_grid_bytes(p.W, p.H, p.centers_nms_wsize / 2, K)));
-    CU_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->wc_ctas_per_sm, window_count_kernel, VOTE_THREADS,
+    CU_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->wc_ctas_per_sm, window_entries_kernel, VOTE_THREADS,
                                                              cell_grid_bytes(p.W, p.H, p.centers_nms_wsize / 2, K)));
     c->wc_ctas_per_sm = std::max(1, c->wc_ctas_per_sm);
     CU_TRY(c, cudaFuncSetAttribute(box_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)((size_t)BLUR_WARPS * (std::max(p.W, HF6D_POSE_BINS) + 1) * 8)));
 
+    {
+        // worst case: every cast vote is an entry; budget 64 MB per frame slot (4 M entries), the overflow path stays exact
+        long long max_leaf_votes = 1;
+        for (size_t i = 0; i < c->hf.leaf_vcnt.size(); ++i) max_leaf_votes = std::max<long long>(max_leaf_votes, c->hf.leaf_vcnt[i]);
+        const long long worst = ((long long)g.cap * c->hf.T * max_leaf_votes + ENTRY_BLOCK - 1) / ENTRY_BLOCK * ENTRY_BLOCK +
+                                (long long)c->sms * 64 * ENTRY_BLOCK;  // + one partly filled block per resident warp
+        long long cap_entries = std::min<long long>(worst, 4LL << 20);
+        if (const char* e = getenv("HF6D_ENTRY_CAP")) cap_entries = std::max(0LL, atoll(e));  // tests force the overflow path
+        c->entry_cap = (int)cap_entries;
+    }
+    CU_TRY(c, cudaFuncSetAttribute(window_accumulate_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WA_MAX_DYN_SMEM));
     c->slots.resize(c->n_slots);
     for (Slot& s : c->slots) {
         memset(s.ev, 0, sizeof s.ev);

@@ -183,30 +183,46 @@ inline size_t cell_grid_bytes(int W, int H, int half_win, int K) {
     return ((size_t)cg.gx * cg.gy * K * sizeof(uint16_t) + 15) / 16 * 16;
 }
 
-// Per-warp staging of the window entries found in one chunk of 32 votes (see window_count_kernel).
-struct WarpHits {
-    int incl[32];        // inclusive prefix of the entries' leaf-vote counts (INT_MAX beyond the last entry)
-    float zz[32];        // depth of the window pixel [m]
-    int vb[32];          // first vote of the entry's group minus the exclusive prefix
-    unsigned w[32];      // Q16 weight
-    unsigned cm[32];     // class << 16 | mask of the centres whose window holds the entry
-};
-
-// Pass A.1: enumerate the cast votes again (same arithmetic as vote_kernel, so the same pixels).  For every vote that
-// falls in the window of an active centre ("entry" of the reference's center_leaf_map):
-//   * cnt[slot][group] += 1                  -- everything the entry contributes to the yaw/pitch and roll maps depends
-//                                               only on its leaf, so those maps are built later from these counts;
+// One window entry of the reference's center_leaf_map: cast vote `vi` landed on a pixel that lies in the windows `mask`
+// of class `c`; zz = depth of that pixel in metres, < 0 when the pixel is outside the image or has no depth.
+//   * cnt[slot][group] += 1   -- everything the entry contributes to the yaw/pitch and roll maps depends only on its
+//                                leaf, so those maps are built later from these counts;
 //   * z histogram of the slot: the WINDOW pixel's depth stands in for the patch centre and every vote of the leaf is
-//     re-projected (HFTest.cpp:766-775), so this part is per entry: the (entry, leaf vote) pairs of a chunk are
-//     flattened over the 32 lanes again (prefix sum + search in shared memory), one 64-bit atomic per pair and slot.
+//     re-projected (HFTest.cpp:766-775).  `add_z(centre rank, bin, weight)` receives the increments.
+template <class AddZ>
+__device__ __forceinline__ void accumulate_entry(const DevForest& f, int vi, int c, unsigned mask, float zz, int n_groups,
+                                                 unsigned* __restrict__ cnt, AddZ&& add_z) {
+    const int gi = __ldg(f.vgroup + vi);
+    for (unsigned m = mask; m; m &= m - 1)
+        atomicAdd(cnt + (size_t)(c * HF6D_MAX_CENTRES + __ffs(m) - 1) * n_groups + gi, 1u);
+    if (zz < 0.f) return;
+    const int4 grp = __ldg(reinterpret_cast<const int4*>(f.groups) + gi);  // cls, w, vbeg, vcnt
+#pragma unroll 4
+    for (int q = 0; q < grp.w; ++q) {
+        const int zb = f2i_x86(div_const<1, 100>(__fadd_rn(__ldg(f.oz + grp.z + q), zz)));  // only the integer part is used
+        if (zb < 0 || zb >= HF6D_Z_BINS) continue;
+        for (unsigned m = mask; m; m &= m - 1) add_z(__ffs(m) - 1, zb, (unsigned)grp.y);
+    }
+}
+
+constexpr int ENTRY_BLOCK = 64;               // entries a warp reserves at a time (one global atomic per block)
+constexpr unsigned ENTRY_INVALID = 0xFFFFFFFFu;
+
+// Pass A.1a: enumerate the cast votes again (same arithmetic as vote_kernel, so the same pixels) and append every vote
+// that falls in the window of an active centre to the entry list (16 bytes: vote, class | window mask, pixel depth).
+// Only ~10 % of the votes are entries, and what an entry costs (a walk over its leaf's votes with histogram updates that
+// all land on a handful of hot bins) needs privatised histograms, so it is split off into its own fully parallel pass.
+// A warp reserves list space ENTRY_BLOCK entries at a time and pads what it leaves unused with ENTRY_INVALID.  Entries
+// that do not fit the list (capacity is a fixed budget, the worst case is every cast vote) are accumulated in place with
+// global atomics, so the result never depends on the capacity.
 __global__ void __launch_bounds__(VOTE_THREADS)
-window_count_kernel(DevForest f, FrameGeom g, const __grid_constant__ ObjectSwitches sw, const int* __restrict__ locs,
-                    const uint16_t* __restrict__ depth, const int* __restrict__ leaf_ord,
-                    const int* __restrict__ counts, CentreTable ct, int half_win, int n_groups, int* next_batch,
-                    unsigned* __restrict__ cnt /*[S][n_groups]*/, unsigned long long* __restrict__ zacc /*[S][Z_BINS]*/) {
+window_entries_kernel(DevForest f, FrameGeom g, const __grid_constant__ ObjectSwitches sw, const int* __restrict__ locs,
+                      const uint16_t* __restrict__ depth, const int* __restrict__ leaf_ord,
+                      const int* __restrict__ counts, CentreTable ct, int half_win, int n_groups, int* next_batch,
+                      uint4* __restrict__ entries, int entry_cap, int* __restrict__ n_reserved,
+                      unsigned* __restrict__ cnt /*[S][n_groups]*/, unsigned long long* __restrict__ zacc /*[S][Z_BINS]*/) {
     __shared__ SharedCentres sc;
     __shared__ WarpItems s_items[VOTE_WARPS];
-    __shared__ WarpHits s_hits[VOTE_WARPS];
     __shared__ unsigned s_classes;  // classes that are detected and have at least one active centre
     extern __shared__ __align__(16) uint8_t wc_smem[];
     uint16_t* s_cells = reinterpret_cast<uint16_t*>(wc_smem);  // [K][gy][gx]
@@ -233,7 +249,8 @@ window_count_kernel(DevForest f, FrameGeom g, const __grid_constant__ ObjectSwit
     __syncthreads();
     const unsigned classes = s_classes;
     const int lane = threadIdx.x & 31;
-    WarpHits& wh = s_hits[threadIdx.x >> 5];
+    int blk_base = 0, blk_used = ENTRY_BLOCK;  // warp-uniform: the block this warp is filling (none yet)
+    bool overflow = false;                     // the list is full: accumulate in place from now on
     for_each_cast_vote(f, g, locs, depth, leaf_ord, counts[1] * f.T, s_items[threadIdx.x >> 5], next_batch,
                        [&](bool valid, int vi, float tx, float ty, float tz) {
         unsigned mask = 0;
@@ -255,59 +272,134 @@ window_count_kernel(DevForest f, FrameGeom g, const __grid_constant__ ObjectSwit
                 }
             }
         }
-        if (!__ballot_sync(0xffffffffu, mask != 0)) return;  // the common case: no lane of this chunk hit a window
-        int4 grp = make_int4(0, 0, 0, 0);
-        float zz = 0.f;
-        bool zok = false;
-        if (mask) {
-            const int gi = __ldg(f.vgroup + vi);
-            grp = __ldg(reinterpret_cast<const int4*>(f.groups) + gi);  // cls, w, vbeg, vcnt
-            if (vv >= 0 && vv < g.H && uu >= 0 && uu < g.W) {  // the reference reads out of bounds here
-                const unsigned d = depth[(size_t)vv * g.W + uu];
-                if (d != 0) { zz = div_const<1000, 1>((float)d); zok = true; }
-            }
-            for (unsigned m = mask; m; m &= m - 1)
-                atomicAdd(cnt + (size_t)(c * HF6D_MAX_CENTRES + __ffs(m) - 1) * n_groups + gi, 1u);
+        const unsigned hl = __ballot_sync(0xffffffffu, mask != 0);
+        if (!hl) return;  // the common case: no lane of this chunk hit a window
+        float zz = -1.f;
+        if (mask && vv >= 0 && vv < g.H && uu >= 0 && uu < g.W) {  // the reference reads out of bounds here
+            const unsigned d = depth[(size_t)vv * g.W + uu];
+            if (d != 0) zz = div_const<1000, 1>((float)d);
         }
-        const unsigned zl = __ballot_sync(0xffffffffu, zok);
-        if (!zl) return;
-        // flatten the (entry, leaf vote) pairs of this chunk over the lanes
-        int incl = zok ? grp.w : 0;
+        const int n = __popc(hl);
+        if (!overflow && blk_used + n > ENTRY_BLOCK) {  // pad the rest of the current block, reserve the next
+            for (int i = blk_used + lane; i < ENTRY_BLOCK; i += 32) entries[blk_base + i] = make_uint4(ENTRY_INVALID, 0u, 0u, 0u);
+            int b = 0;
+            if (lane == 0) b = atomicAdd(n_reserved, ENTRY_BLOCK);
+            blk_base = __shfl_sync(0xffffffffu, b, 0);
+            blk_used = 0;
+            if (blk_base + ENTRY_BLOCK > entry_cap) { overflow = true; blk_used = ENTRY_BLOCK; }
+        }
+        if (mask) {
+            if (!overflow)
+                entries[blk_base + blk_used + __popc(hl & ((1u << lane) - 1u))] =
+                    make_uint4((unsigned)vi, ((unsigned)c << 16) | mask, __float_as_uint(zz), 0u);
+            else
+                accumulate_entry(f, vi, c, mask, zz, n_groups, cnt, [&](int k, int zb, unsigned w) {
+                    atomicAdd(zacc + (size_t)(c * HF6D_MAX_CENTRES + k) * HF6D_Z_BINS + zb, (unsigned long long)w);
+                });
+        }
+        if (!overflow) blk_used += n;
+    });
+    if (!overflow)
+        for (int i = blk_used + lane; i < ENTRY_BLOCK; i += 32) entries[blk_base + i] = make_uint4(ENTRY_INVALID, 0u, 0u, 0u);
+}
+
+// Per-warp staging of 32 listed entries (see window_accumulate_kernel).
+struct WarpEntries {
+    int incl[32];        // inclusive prefix of the entries' leaf-vote counts
+    float zz[32];        // depth of the window pixel [m]
+    int vb[32];          // first vote of the entry's group minus the exclusive prefix
+    unsigned w[32];      // Q16 weight
+    unsigned cm[32];     // class << 16 | mask of the centres whose window holds the entry
+};
+
+// Pass A.1b: a warp takes 32 listed entries at a time (one per lane: group lookup and the cnt increments), then walks
+// the flattened (entry, leaf vote) pairs 32 per step -- coalesced, independent oz loads instead of one dependent load
+// chain per entry.  SMEM_Z: every CTA keeps the z histograms of all centres that can be active in shared memory
+// (uint32; a wrap of the 32-bit counter carries 2^32 into the global 64-bit accumulator, so the sums stay exact) and
+// flushes them once.  zoff[c] = first shared histogram of class c (centre rank k uses zoff[c] + k).
+struct ZSlotTable {
+    int16_t zoff[HF6D_MAX_CLASSES + 1];
+};
+constexpr int WA_THREADS = 1024;  // one CTA per SM when the histograms live in shared memory: 32 warps share them
+template <bool SMEM_Z>
+__global__ void __launch_bounds__(WA_THREADS)
+window_accumulate_kernel(DevForest f, const uint4* __restrict__ entries, int entry_cap, const int* __restrict__ n_reserved,
+                         int n_groups, const __grid_constant__ ZSlotTable zt, unsigned* __restrict__ cnt,
+                         unsigned long long* __restrict__ zacc) {
+    __shared__ WarpEntries s_we[WA_THREADS / 32];
+    extern __shared__ unsigned s_z[];  // [zt.zoff[K]][Z_BINS]
+    const int nz = zt.zoff[f.K];
+    if (SMEM_Z) {
+        for (int i = threadIdx.x; i < nz * HF6D_Z_BINS; i += WA_THREADS) s_z[i] = 0u;
+        __syncthreads();
+    }
+    const int n = min(*n_reserved, entry_cap / ENTRY_BLOCK * ENTRY_BLOCK);
+    const int lane = threadIdx.x & 31;
+    WarpEntries& we = s_we[threadIdx.x >> 5];
+    const int warp_id = (blockIdx.x * WA_THREADS + threadIdx.x) >> 5, n_warps = (gridDim.x * WA_THREADS) >> 5;
+    for (int base = warp_id * 32; base < n; base += n_warps * 32) {
+        const uint4 e = entries[base + lane];  // n is a multiple of ENTRY_BLOCK, so base + lane < n
+        int vcnt = 0;
+        if (e.x != ENTRY_INVALID) {
+            const int c = (int)(e.y >> 16);
+            const int gi = __ldg(f.vgroup + (int)e.x);
+            const int4 grp = __ldg(reinterpret_cast<const int4*>(f.groups) + gi);  // cls, w, vbeg, vcnt
+            for (unsigned m = e.y & 0xFFFFu; m; m &= m - 1)
+                atomicAdd(cnt + (size_t)(c * HF6D_MAX_CENTRES + __ffs(m) - 1) * n_groups + gi, 1u);
+            const float zz = __uint_as_float(e.z);
+            if (zz >= 0.f) {
+                vcnt = grp.w;
+                we.zz[lane] = zz;
+                we.w[lane] = (unsigned)grp.y;
+                we.cm[lane] = e.y;
+                we.vb[lane] = grp.z;  // corrected below once the prefix is known
+            }
+        }
+        int incl = vcnt;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const int n = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += n;
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
         }
         const int total = __shfl_sync(0xffffffffu, incl, 31);
-        wh.incl[lane] = INT_MAX;
-        __syncwarp();
-        if (zok) {
-            const int r = __popc(zl & ((1u << lane) - 1u));
-            wh.incl[r] = incl;
-            wh.zz[r] = zz;
-            wh.vb[r] = grp.z - (incl - grp.w);
-            wh.w[r] = (unsigned)grp.y;
-            wh.cm[r] = ((unsigned)c << 16) | mask;
-        }
+        we.incl[lane] = incl;
+        if (vcnt) we.vb[lane] -= incl - vcnt;
         __syncwarp();
         for (int p0 = 0; p0 < total; p0 += 32) {
             const int pidx = p0 + lane;
             if (pidx < total) {
                 int h = 0;  // smallest h with incl[h] > pidx
 #pragma unroll
-                for (int s = 16; s; s >>= 1)
-                    if (wh.incl[h + s - 1] <= pidx) h += s;
-                const int zb = f2i_x86(div_const<1, 100>(__fadd_rn(__ldg(f.oz + wh.vb[h] + pidx), wh.zz[h])));  // only the integer part is used
+                for (int st = 16; st; st >>= 1)
+                    if (we.incl[h + st - 1] <= pidx) h += st;
+                const int zb = f2i_x86(div_const<1, 100>(__fadd_rn(__ldg(f.oz + we.vb[h] + pidx), we.zz[h])));  // integer part only
                 if (zb >= 0 && zb < HF6D_Z_BINS) {
-                    const unsigned cm = wh.cm[h];
-                    const unsigned long long w = wh.w[h];
-                    unsigned long long* zs = zacc + (size_t)(cm >> 16) * HF6D_MAX_CENTRES * HF6D_Z_BINS + zb;
-                    for (unsigned m = cm & 0xFFFFu; m; m &= m - 1) atomicAdd(zs + (size_t)(__ffs(m) - 1) * HF6D_Z_BINS, w);
+                    const unsigned cm = we.cm[h], w = we.w[h];
+                    const int c = (int)(cm >> 16);
+                    for (unsigned m = cm & 0xFFFFu; m; m &= m - 1) {
+                        const int k = __ffs(m) - 1;
+                        if (SMEM_Z) {
+                            const unsigned old = atomicAdd(s_z + (zt.zoff[c] + k) * HF6D_Z_BINS + zb, w);
+                            if (old + w < old) atomicAdd(zacc + (size_t)(c * HF6D_MAX_CENTRES + k) * HF6D_Z_BINS + zb, 1ull << 32);
+                        } else {
+                            atomicAdd(zacc + (size_t)(c * HF6D_MAX_CENTRES + k) * HF6D_Z_BINS + zb, (unsigned long long)w);
+                        }
+                    }
                 }
             }
         }
         __syncwarp();
-    });
+    }
+    if (SMEM_Z) {
+        __syncthreads();
+        for (int c = 0; c < f.K; ++c) {
+            const int n_k = zt.zoff[c + 1] - zt.zoff[c];
+            for (int i = threadIdx.x; i < n_k * HF6D_Z_BINS; i += WA_THREADS) {
+                const unsigned v = s_z[zt.zoff[c] * HF6D_Z_BINS + i];
+                if (v) atomicAdd(zacc + (size_t)c * HF6D_MAX_CENTRES * HF6D_Z_BINS + i, (unsigned long long)v);
+            }
+        }
+    }
 }
 
 // Pass A.2: yaw/pitch maps from the (slot, group) entry counts: every entry re-walks all votes of its leaf

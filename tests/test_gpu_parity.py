@@ -275,3 +275,17 @@ def test_software_filter_equals_the_texture_unit(case):
     frac = float((q_hw != q_sw).mean())
     print(f"quantised uint8 values that differ between hardware and software filter: {frac * 100:.4f}%")
     assert frac < 1e-3
+
+
+@pytest.mark.parametrize("cap", [0, 777])
+def test_window_entry_list_overflow_is_exact(case, full_run, cap, monkeypatch):
+    """The pose stage lists window entries in a fixed-capacity buffer; entries that do not fit are accumulated in place.
+    Forcing a tiny capacity must not change a single bit of the result."""
+    from object_detector_6d_b200 import api
+    monkeypatch.setenv("HF6D_ENTRY_CAP", str(cap))
+    det = api.Detector(case["forest_dir"], case["weights"], to_api_params(case["params"]), device=0, n_slots=1)
+    try:
+        hyp = det.detect(case["bgr"], case["depth"])
+    finally:
+        det.close()
+    _same_hyps(hyp, full_run["hyp"])
