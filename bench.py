@@ -172,17 +172,20 @@ def run_cuda(args, rank, world, local_rank):
     with tempfile.TemporaryDirectory() as d:
         frames, layers, forest_dir, wpath, stats = make_workload(d, DISTINCT_FRAMES)
         p = api.default_params(fill_random=1, fill_seed=1)
-        n_slots = 3
+        n_slots = 4
         det = api.Detector(forest_dir, wpath, p, device=local_rank, n_slots=n_slots)
 
         # ---- device-resident inputs
         bgr_all = torch.from_numpy(np.stack([f[0] for f in frames])).cuda()
         dep_all = torch.from_numpy(np.stack([f[1] for f in frames]).view(np.int16)).cuda()
-        stream = torch.cuda.Stream()
+        main = torch.cuda.Stream()
+        streams = [torch.cuda.Stream() for _ in range(n_slots)]
         for s in range(n_slots):
-            det.set_stream(s, stream.cuda_stream)
+            det.set_stream(s, streams[s].cuda_stream)
 
         def step_resident():
+            # frames are independent: slot s (its own stream and workspace) takes frames s, s + n_slots, ...; the small
+            # kernels of one frame overlap the encoder of another
             launches = 0
             for i in range(BATCH):
                 s = i % n_slots
@@ -192,27 +195,49 @@ def run_cuda(args, rank, world, local_rank):
                 launches += det.launch_count(s)
             return launches
 
-        with torch.cuda.stream(stream):
-            for _ in range(args.warmup):
-                step_resident()
-            stream.synchronize()
-            if world > 1:
-                dist.barrier()
-            torch.cuda.synchronize()
-            sampler = ClockSampler(local_rank) if rank == 0 else None
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
-            launches = 0
-            for _ in range(args.steps):
-                launches += step_resident()
-            e1.record(stream)
-            stream.synchronize()
-            torch.cuda.synchronize()
-            ms_total = e0.elapsed_time(e1)
-        # per-stage times of the last frames (events recorded inside the timed region, one set per slot)
-        stage_ms = np.mean([det.stage_ms(s) for s in range(n_slots)], axis=0)
-        enc_ms = np.mean([det.encoder_layer_ms(s) for s in range(n_slots)], axis=0)
+        def fork():
+            ev = torch.cuda.Event()
+            ev.record(main)
+            for st in streams:
+                st.wait_event(ev)
+
+        def join():
+            for st in streams:
+                ev = torch.cuda.Event()
+                ev.record(st)
+                main.wait_event(ev)
+
+        for _ in range(args.warmup):
+            step_resident()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        sampler = ClockSampler(local_rank) if rank == 0 else None
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(main)
+        fork()
+        launches = 0
+        for _ in range(args.steps):
+            launches += step_resident()
+        join()
+        e1.record(main)
+        main.synchronize()
+        torch.cuda.synchronize()
+        ms_total = e0.elapsed_time(e1)
         counts = [det.counts(s) for s in range(n_slots)]
+        # per-stage times: a serial pass (one slot, nothing else on the GPU) so a stage's events bracket only its kernels
+        st_acc, enc_acc, n_ser = np.zeros(api.STAGE_COUNT), np.zeros(3), 0
+        for rep in range(2):
+            for j in range(DISTINCT_FRAMES):
+                det.bind_frame(0, bgr_all[j].data_ptr(), dep_all[j].data_ptr())
+                det.run(0)
+                det.sync(0)
+                if rep:
+                    st_acc += det.stage_ms(0)
+                    enc_acc += det.encoder_layer_ms(0)
+                    n_ser += 1
+        stage_ms, enc_ms = st_acc / n_ser, enc_acc / n_ser
         # patches per frame: exact, from the scan of every distinct frame
         Pp_frames = []
         for j in range(DISTINCT_FRAMES):
@@ -283,6 +308,44 @@ def run_cuda(args, rank, world, local_rank):
                    "sample": f"{n_s} frames of the batch, all stages, OpenMP on all host cores"}
         det.close()
 
+        # ---- the north star's multi-GPU mode: trees sharded over the ranks, ONE exchange step per frame (NCCL
+        # all-reduce SUM of the Q16 vote maps + MAX of the leaf table), every rank works on the same frames
+        tree = None
+        if world > 1:
+            from object_detector_6d_b200 import sharded
+            sd = sharded.TreeShardedDetector(forest_dir, wpath, p, device=local_rank, n_slots=2)
+            for s in range(2):
+                sd.det.bind_frame(s, bgr_all[0].data_ptr(), dep_all[0].data_ptr())
+
+            def step_tree():
+                for i in range(BATCH):
+                    s = i % 2
+                    j = i % DISTINCT_FRAMES
+                    sd.det.bind_frame(s, bgr_all[j].data_ptr(), dep_all[j].data_ptr())
+                    sd.run(s)
+
+            for _ in range(args.warmup):
+                step_tree()
+            sd.stream.synchronize()
+            dist.barrier()
+            torch.cuda.synchronize()
+            t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0e.record(sd.stream)
+            for _ in range(args.steps):
+                step_tree()
+            t1e.record(sd.stream)
+            sd.stream.synchronize()
+            t = torch.tensor([t0e.elapsed_time(t1e)], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_tree = float(t.item())
+            tree = {"frames_per_s": BATCH * args.steps / (ms_tree * 1e-3), "ms_per_frame": ms_tree / (BATCH * args.steps),
+                    "trees_per_rank": len(sd.trees), "exchange_bytes_per_frame": int(K_CLASSES * 640 * 480 * 8 + counts[0][1] * T_TREES * 4),
+                    "scaling": "strong (same frames on every rank, trees t % N == rank)",
+                    "note": "scan/gather/encode are replicated (every rank needs all features), traverse+vote are sharded"}
+            for s in range(2):
+                sd.det.bind_frame(s, None, None)
+            sd.close()
+
     frames_total = BATCH * args.steps * world
     sec = ms_total * 1e-3
     fps = frames_total / sec
@@ -310,12 +373,21 @@ def run_cuda(args, rank, world, local_rank):
         else:
             ach = work / (ms * 1e-3) / 1e9
             stages[name] = {"ms": float(ms), "bound": bound, "achieved": ach, "unit": "GB/s", "frac": ach / peaks["hbm"]}
-    # dominant kernel: encoder layer 2 (K=1536 -> N=1024 padded; algorithmic 1500 x 1000)
+    # dominant kernel: encoder layer 2 (K=1536 -> N=1024 padded; algorithmic 1500 x 1000), timed alone in the serial
+    # pass with the SM clock at its maximum -> the burst bf16 peak is the denominator (the sustained figure is for a
+    # kernel inside a long power-limited tensor step; this path spends ~1/3 of a frame on the tensor pipe)
     l2_flop = 2.0 * Pp * 1500 * 1000
     l2_ach = l2_flop / (enc_ms[1] * 1e-3) / 1e12 if enc_ms[1] > 0 else 0.0
-    roofline = {"kernel": "encoder_layer_kernel<256,false> (layer 2: 1500->1000)", "bound": "tensor", "achieved": l2_ach,
-                "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": l2_ach / peaks["tf_sustained"],
-                "traffic": None, "peak_source": peaks["source"] + " (sustained bf16)",
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get("encoder_layer_2", {}).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    roofline = {"kernel": "encoder_layer_kernel<256,false,4,1> (layer 2: 1500->1000)", "bound": "tensor", "achieved": l2_ach,
+                "peak": peaks["tf_burst"], "unit": "TFLOP/s", "frac": l2_ach / peaks["tf_burst"],
+                "traffic": traffic, "peak_source": peaks["source"] + " (burst bf16: kernel timed alone, SM clock at max)",
+                "frac_of_sustained_peak": l2_ach / peaks["tf_sustained"],
                 "encoder_layer_ms": [float(x) for x in enc_ms],
                 "encoder_stage_tflops": float(Pp * ENC_FLOP_PER_PATCH / (sum(enc_ms) * 1e-3) / 1e12) if sum(enc_ms) > 0 else 0.0}
     e2e_fps = frames_total / e2e_s
@@ -329,8 +401,12 @@ def run_cuda(args, rank, world, local_rank):
                 "timing": "wall clock around hf6d_submit/hf6d_wait with pinned host frames, device sync both sides",
                 "hypotheses_per_frame": n_hyp / (BATCH * args.steps)},
         "gpu_launches": launches,
-        "roofline": roofline, "stages": stages, "cpu_baseline": cpu, "clocks": clocks,
+        "roofline": roofline, "stages": stages, "stages_note": "serial pass: one frame at a time, sum = %.3f ms/frame; "
+        "`value` runs %d frames in flight on separate streams" % (float(np.sum(stage_ms)), n_slots),
+        "cpu_baseline": cpu, "clocks": clocks,
     }
+    if tree is not None:
+        line["tree_sharded"] = tree
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
