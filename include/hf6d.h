@@ -64,6 +64,12 @@ typedef struct {
     int32_t max_yaw_pitch_hypotheses, max_roll_hypotheses;
     float min_location_score_ratio, min_yaw_pitch_drop_ratio;
     int32_t centers_blur_size, centers_nms_wsize, pose_blur_size, pose_nms_wsize;
+    /* Patch channels: 0 = B,G,R,D with local normalisation (the reference's live path, patch_extractor.cu:230-309 +
+     * HFTest.cpp:500-570; encoder input 4*ps*ps); 1 = B,G,R + interpolated surface normals with plain quantisation (the
+     * variant the reference keeps next to it: surface_normals.cu:11-73, patch_extractor.cu:12-111, HFTest.cpp:322-363 and
+     * :443-470; encoder input 6*ps*ps).  normals_focal is that variant's hard-wired focal length (575.0f). */
+    int32_t patch_mode;
+    float normals_focal;
 } hf6d_params;
 
 typedef struct {
@@ -96,7 +102,7 @@ typedef enum {
 typedef enum {
     HF6D_BUF_COUNTS = 0,   /* int32[2]  = P (valid centres), P' (processed) */
     HF6D_BUF_LOCS = 1,     /* int32[P][2] = (x, y) */
-    HF6D_BUF_PATCH_U8 = 2, /* uint8[P'][4*ps*ps] quantised CHW patches (only when debug capture is on) */
+    HF6D_BUF_PATCH_U8 = 2, /* uint8[P'][C*ps*ps] quantised CHW patches, C = 4 or 6 (only when debug capture is on) */
     HF6D_BUF_FEATURES = 3, /* float[P'][F] */
     HF6D_BUF_LEAF_ORD = 4, /* int32[P'][T]: file-order ordinal of the leaf inside its tree; -1 for trees not owned */
     HF6D_BUF_MAPS = 5,     /* uint64[K][H][W] Q16 vote sums */
@@ -104,7 +110,8 @@ typedef enum {
     HF6D_BUF_CENTRES = 7,  /* per class: int32 n, then HF6D_MAX_CENTRES x {float score, int32 x, int32 y} (see hf6d_centre) */
     HF6D_BUF_FRAME_BGR = 8,
     HF6D_BUF_FRAME_DEPTH = 9,
-    HF6D_BUF_COUNT = 10
+    HF6D_BUF_NORMALS = 10, /* float[H][W][4] = (nx, ny, nz, 0): surface normals (patch_mode 1 only) */
+    HF6D_BUF_COUNT = 11
 } hf6d_buffer;
 
 typedef struct {

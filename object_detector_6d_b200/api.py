@@ -18,7 +18,7 @@ STAGE_SCAN, STAGE_GATHER, STAGE_ENCODE, STAGE_TRAVERSE, STAGE_VOTE, STAGE_CENTRE
 STAGE_COUNT = 7
 STAGE_NAMES = ("scan", "gather", "encode", "traverse", "vote", "centres", "pose")
 (BUF_COUNTS, BUF_LOCS, BUF_PATCH_U8, BUF_FEATURES, BUF_LEAF_ORD, BUF_MAPS, BUF_BLURRED, BUF_CENTRES, BUF_FRAME_BGR,
- BUF_FRAME_DEPTH) = range(10)
+ BUF_FRAME_DEPTH, BUF_NORMALS) = range(11)
 MAX_CENTRES = 16
 
 EXPORTS = (
@@ -39,7 +39,8 @@ class Params(C.Structure):
                 ("fill_seed", C.c_uint64), ("batch_size", C.c_int32), ("max_yaw_pitch_hypotheses", C.c_int32),
                 ("max_roll_hypotheses", C.c_int32), ("min_location_score_ratio", C.c_float),
                 ("min_yaw_pitch_drop_ratio", C.c_float), ("centers_blur_size", C.c_int32),
-                ("centers_nms_wsize", C.c_int32), ("pose_blur_size", C.c_int32), ("pose_nms_wsize", C.c_int32)]
+                ("centers_nms_wsize", C.c_int32), ("pose_blur_size", C.c_int32), ("pose_nms_wsize", C.c_int32),
+                ("patch_mode", C.c_int32), ("normals_focal", C.c_float)]
 
 
 class ObjectOptions(C.Structure):
@@ -346,10 +347,11 @@ class Detector:
         P, Pp = self.counts(slot)
         K, T, F, H, W = self.K, self.T, self.F, self.H, self.W
         shapes = {
-            BUF_COUNTS: ((2,), np.int32), BUF_LOCS: ((P, 2), np.int32), BUF_PATCH_U8: ((Pp, 256), np.uint8),
+            BUF_COUNTS: ((2,), np.int32), BUF_LOCS: ((P, 2), np.int32), BUF_PATCH_U8: ((Pp, self.model.dims[0]), np.uint8),
             BUF_FEATURES: ((Pp, F), np.float32), BUF_LEAF_ORD: ((Pp, T), np.int32), BUF_MAPS: ((K, H, W), np.uint64),
             BUF_BLURRED: ((K, H, W), np.float32), BUF_CENTRES: ((K,), CENTRE_LIST_DTYPE),
             BUF_FRAME_BGR: ((H, W, 3), np.uint8), BUF_FRAME_DEPTH: ((H, W), np.uint16),
+            BUF_NORMALS: ((H, W, 4), np.float32),
         }
         shape, dt = shapes[what]
         a = np.zeros(shape, dt)

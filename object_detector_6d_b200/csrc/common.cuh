@@ -20,6 +20,7 @@ struct FrameGeom {
     unsigned long long fill_seed;
     int batch;
     int cap;             // patch capacity of the per-slot buffers (multiple of 128)
+    float focal;         // focal length of the adaptive patch size: fx (RGB-D patches) or normals_focal (normals variant)
 };
 
 // Device view of the flattened forest (model.hpp::HostForest).
@@ -62,7 +63,7 @@ __device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
 
 // patch_extractor.cu:257 / :378 -- ((ps*vox)/d)*f in fp32, truncated
 __device__ __forceinline__ int adaptive_size(const FrameGeom& g, float depth_m) {
-    return (int)__fmul_rn(__fdiv_rn(__fmul_rn((float)g.ps, g.vox), depth_m), g.fx);
+    return (int)__fmul_rn(__fdiv_rn(__fmul_rn((float)g.ps, g.vox), depth_m), g.focal);
 }
 
 }  // namespace hf6d

@@ -282,4 +282,154 @@ gather_normalise_kernel(const uint2* __restrict__ tex, FrameGeom g, const int* _
     }
 }
 
+// ================================================================================================ A2c: normals variant
+// The patch mode the reference keeps next to the RGB-D one (HFTest.cpp:322-363 and :443-470, commented out there):
+// surface normals from depth by central differences (surface_normals.cu:11-73), a 7-channel texture B,G,R,D,nx,ny,nz
+// (patch_extractor.cu:12-111), 6-channel patches B,G,R + re-normalised interpolated normal, and plain uint8
+// quantisation (no local normalisation) into a 384-input encoder.
+//
+// normals: float4 [H][W] = (nx, ny, nz, 0), one 16-byte texel.  Products and sums without FMA contraction (oracle C12).
+__global__ void normals_kernel(const uint16_t* __restrict__ depth, int W, int H, float focal, float4* __restrict__ normals) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= W * H) return;
+    const int x = i % W, y = i / W;
+    float4 n = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (x > 0 && x < W - 1 && y > 0 && y < H - 1) {
+        const float z = __fdiv_rn((float)depth[i], 1000.0f);
+        const float z_left = __fdiv_rn((float)depth[i - 1], 1000.0f), z_right = __fdiv_rn((float)depth[i + 1], 1000.0f);
+        const float z_up = __fdiv_rn((float)depth[i - W], 1000.0f), z_down = __fdiv_rn((float)depth[i + W], 1000.0f);
+        if (z != 0.f && z_left != 0.f && z_right != 0.f && z_up != 0.f && z_down != 0.f) {
+            const float hw = __fdiv_rn((float)W, 2.0f), hh = __fdiv_rn((float)H, 2.0f);
+            const float xm = __fsub_rn(__fsub_rn((float)x, 1.0f), hw), xp = __fsub_rn(__fadd_rn((float)x, 1.0f), hw);
+            const float x0 = __fsub_rn((float)x, hw);
+            const float ym = __fsub_rn(__fsub_rn((float)y, 1.0f), hh), yp = __fsub_rn(__fadd_rn((float)y, 1.0f), hh);
+            const float y0 = __fsub_rn((float)y, hh);
+            const float x_left = __fdiv_rn(__fmul_rn(xm, z_left), focal), x_right = __fdiv_rn(__fmul_rn(xp, z_right), focal);
+            const float x_up = __fdiv_rn(__fmul_rn(x0, z_up), focal), x_down = __fdiv_rn(__fmul_rn(x0, z_down), focal);
+            const float y_left = __fdiv_rn(__fmul_rn(y0, z_left), focal), y_right = __fdiv_rn(__fmul_rn(y0, z_right), focal);
+            const float y_up = __fdiv_rn(__fmul_rn(ym, z_up), focal), y_down = __fdiv_rn(__fmul_rn(yp, z_down), focal);
+            const float ax = __fmul_rn(__fsub_rn(x_left, x_right), 0.5f), ay = __fmul_rn(__fsub_rn(y_left, y_right), 0.5f);
+            const float az = __fmul_rn(__fsub_rn(z_left, z_right), 0.5f);
+            const float bx = __fmul_rn(__fsub_rn(x_down, x_up), 0.5f), by = __fmul_rn(__fsub_rn(y_down, y_up), 0.5f);
+            const float bz = __fmul_rn(__fsub_rn(z_down, z_up), 0.5f);
+            const float nx = -__fsub_rn(__fmul_rn(ay, bz), __fmul_rn(az, by));
+            const float ny = -__fsub_rn(__fmul_rn(az, bx), __fmul_rn(ax, bz));
+            const float nz = -__fsub_rn(__fmul_rn(ax, by), __fmul_rn(ay, bx));
+            const float mag = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(nx, nx), __fmul_rn(ny, ny)), __fmul_rn(nz, nz)));
+            n = make_float4(__fdiv_rn(nx, mag), __fdiv_rn(ny, mag), __fdiv_rn(nz, mag), 0.f);
+        }
+    }
+    normals[i] = n;
+}
+
+// x86 cvttsd2si semantics for the double expression of HFTest.cpp:466
+__device__ __forceinline__ int d2i_x86_dev(double y) { return fabs(y) < 2147483648.0 ? (int)y : INT_MIN; }
+
+// 8 threads per patch (one per patch row), 16 patches per CTA, like gather_normalise_kernel; no statistics pass.
+// a_out : bf16 [cap][384], CHW order (B,G,R,nx,ny,nz planes), value = q (exact integer 0..255)
+__global__ void __launch_bounds__(GATHER_THREADS)
+gather_normals_kernel(const uint2* __restrict__ tex, const float4* __restrict__ normals, FrameGeom g,
+                      const int* __restrict__ locs, const int* __restrict__ counts, __nv_bfloat16* __restrict__ a_out,
+                      uint8_t* __restrict__ q_out) {
+    const int Pp = counts[1];
+    const int ty = threadIdx.x & 7;
+    const int p = blockIdx.x * GATHER_PATCHES_PER_CTA + (threadIdx.x >> 3);
+    if (p >= Pp) return;
+    const int2 ctr = *reinterpret_cast<const int2*>(locs + 2 * p);
+    const float dc = div_const<1000, 1>((float)tex[(size_t)ctr.y * g.W + ctr.x].y);
+    const int a = adaptive_size(g, dc);
+    const int x0 = ctr.x - a / 2, y0 = ctr.y - a / 2;
+    const float step = __fdiv_rn((float)a, (float)g.ps);
+    float fill[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (g.fill_random) {
+        unsigned long long z = mix64(g.fill_seed + 0x9E3779B97F4A7C15ULL * (unsigned long long)(p + 1));
+        fill[2] = div_const<255, 1>((float)((z & 0xFFFF) % 255));
+        fill[1] = div_const<255, 1>((float)(((z >> 16) & 0xFFFF) % 255));
+        fill[0] = div_const<255, 1>((float)(((z >> 32) & 0xFFFF) % 255));
+        fill[5] = 1.0f;
+        for (int attempt = 0; attempt < 4; ++attempt) {
+            const unsigned long long z2 = mix64(z + 0x9E3779B97F4A7C15ULL), z3 = mix64(z2 + 0x9E3779B97F4A7C15ULL);
+            z = z3;
+            const float xr = __fsub_rn((float)((unsigned)z2 % 100000u), 50000.0f);
+            const float yr = __fsub_rn((float)((unsigned)(z2 >> 32) % 100000u), 50000.0f);
+            const float zr = (float)((unsigned)z3 % 50000u);
+            const float norm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(xr, xr), __fmul_rn(yr, yr)), __fmul_rn(zr, zr)));
+            if (norm != 0.f) { fill[3] = __fdiv_rn(xr, norm); fill[4] = __fdiv_rn(yr, norm); fill[5] = __fdiv_rn(zr, norm); break; }
+        }
+    }
+    const float v = __fadd_rn((float)y0, __fmul_rn((float)ty, step));
+    const float fv = floorf(v);
+    const int j = (int)fv;
+    const float c = frac8(__fsub_rn(v, fv)), nc = __fsub_rn(1.0f, c);
+    const bool in_y0 = j >= 0 && j < g.H, in_y1 = j + 1 >= 0 && j + 1 < g.H;
+    uint32_t qb[6][8];
+#pragma unroll
+    for (int tx = 0; tx < 8; ++tx) {
+        const float u = __fadd_rn((float)x0, __fmul_rn((float)tx, step));
+        const float fu = floorf(u);
+        const int i = (int)fu;
+        const float al = frac8(__fsub_rn(u, fu)), na = __fsub_rn(1.0f, al);
+        Bilerp b;
+        b.w00 = __fmul_rn(na, nc);
+        b.w10 = __fmul_rn(al, nc);
+        b.w01 = __fmul_rn(na, c);
+        b.w11 = __fmul_rn(al, c);
+        const bool in_x0 = i >= 0 && i < g.W, in_x1 = i + 1 >= 0 && i + 1 < g.W;
+        const size_t o00 = (size_t)j * g.W + i;
+        const bool k00 = in_x0 && in_y0, k10 = in_x1 && in_y0, k01 = in_x0 && in_y1, k11 = in_x1 && in_y1;
+        const uint2 zero = make_uint2(0u, 0u);
+        const uint2 q00 = k00 ? __ldg(tex + o00) : zero, q10 = k10 ? __ldg(tex + o00 + 1) : zero;
+        const uint2 q01 = k01 ? __ldg(tex + o00 + g.W) : zero, q11 = k11 ? __ldg(tex + o00 + g.W + 1) : zero;
+        float val[6];
+        bool in_object = false;
+        const float d = div_const<1000, 1>(blend(b, (float)q00.y, (float)q10.y, (float)q01.y, (float)q11.y));
+        if (d > 0.f) {
+            const float4 zf = make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 n00 = k00 ? __ldg(normals + o00) : zf, n10 = k10 ? __ldg(normals + o00 + 1) : zf;
+            const float4 n01 = k01 ? __ldg(normals + o00 + g.W) : zf, n11 = k11 ? __ldg(normals + o00 + g.W + 1) : zf;
+            const float x = blend(b, n00.x, n10.x, n01.x, n11.x), y = blend(b, n00.y, n10.y, n01.y, n11.y);
+            const float z = blend(b, n00.z, n10.z, n01.z, n11.z);
+            const float norm = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z)));
+            if (norm > 0.f) {
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch)
+                    val[ch] = blend(b, div_const<255, 1>((float)((q00.x >> (8 * ch)) & 0xFFu)),
+                                    div_const<255, 1>((float)((q10.x >> (8 * ch)) & 0xFFu)),
+                                    div_const<255, 1>((float)((q01.x >> (8 * ch)) & 0xFFu)),
+                                    div_const<255, 1>((float)((q11.x >> (8 * ch)) & 0xFFu)));
+                val[3] = __fdiv_rn(x, norm);
+                val[4] = __fdiv_rn(y, norm);
+                val[5] = __fdiv_rn(z, norm);
+                in_object = true;
+            }
+        }
+        if (!in_object) {
+#pragma unroll
+            for (int ch = 0; ch < 6; ++ch) val[ch] = fill[ch];
+        }
+        // HFTest.cpp:463-466: colour (uchar)(v * 255.0f); normals (uchar)((v / 2.0 + 0.5f) * 255.0f), a double expression
+#pragma unroll
+        for (int ch = 0; ch < 3; ++ch) qb[ch][tx] = (uint32_t)(f2i_x86(__fmul_rn(val[ch], 255.0f)) & 0xFF);
+#pragma unroll
+        for (int ch = 3; ch < 6; ++ch)
+            qb[ch][tx] = (uint32_t)(d2i_x86_dev(__dmul_rn(__dadd_rn(__dmul_rn((double)val[ch], 0.5), 0.5), 255.0)) & 0xFF);
+    }
+#pragma unroll
+    for (int ch = 0; ch < 6; ++ch) {
+        const size_t o = (size_t)p * 384 + ch * 64 + ty * 8;
+        uint32_t pk[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            __nv_bfloat162 h2 = __floats2bfloat162_rn((float)qb[ch][2 * k], (float)qb[ch][2 * k + 1]);
+            pk[k] = *reinterpret_cast<uint32_t*>(&h2);
+        }
+        *reinterpret_cast<uint4*>(a_out + o) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        if (q_out) {
+            const uint32_t lo = qb[ch][0] | (qb[ch][1] << 8) | (qb[ch][2] << 16) | (qb[ch][3] << 24);
+            const uint32_t hi = qb[ch][4] | (qb[ch][5] << 8) | (qb[ch][6] << 16) | (qb[ch][7] << 24);
+            *reinterpret_cast<uint2*>(q_out + o) = make_uint2(lo, hi);
+        }
+    }
+}
+
 }  // namespace hf6d

@@ -54,6 +54,7 @@ struct Slot {
     uint8_t* bgr = nullptr;       // frame the kernels read: own_bgr or a caller-owned device frame (hf6d_bind_frame)
     uint16_t* depth = nullptr;
     uint2* tex = nullptr;         // packed texels {B | G<<8 | R<<16, depth mm} built from bgr + depth by the gather stage
+    float4* normals = nullptr;    // (nx, ny, nz, 0) per pixel, patch_mode 1 only
     uint8_t* own_bgr = nullptr;
     uint16_t* own_depth = nullptr;
     cudaEvent_t ev_enc[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -257,10 +258,11 @@ int alloc_slot(hf6d_ctx* c, Slot& s) {
     s.bgr = s.own_bgr;
     s.depth = s.own_depth;
     if ((r = dev_alloc(c, s.allocs, &s.tex, HW))) return r;
+    if (c->p.patch_mode == 1 && (r = dev_alloc(c, s.allocs, &s.normals, HW))) return r;
     if ((r = dev_alloc(c, s.allocs, &s.row_count, (size_t)g.gh))) return r;
     if ((r = dev_alloc(c, s.allocs, &s.locs, (size_t)g.cap * 2))) return r;
     if ((r = dev_alloc(c, s.allocs, &s.A0, (size_t)g.cap * c->dm.k_pad[0]))) return r;
-    if ((r = dev_alloc(c, s.allocs, &s.q_u8, (size_t)g.cap * 256))) return r;
+    if ((r = dev_alloc(c, s.allocs, &s.q_u8, (size_t)g.cap * c->dm.n_in[0]))) return r;
     if ((r = dev_alloc(c, s.allocs, &s.H1, (size_t)g.cap * c->dm.n_pad[0]))) return r;
     if ((r = dev_alloc(c, s.allocs, &s.H2, (size_t)g.cap * c->dm.n_pad[1]))) return r;
     if ((r = dev_alloc(c, s.allocs, &s.feat, (size_t)g.cap * F))) return r;
@@ -381,8 +383,14 @@ int run_stage(hf6d_ctx* c, Slot& s, int stage) {
         case HF6D_STAGE_GATHER: {
             pack_frame_kernel<<<(g.W * g.H + 255) / 256, 256, 0, st>>>(s.bgr, s.depth, g.W * g.H, s.tex);
             LAUNCH_CHECK(c, s);
-            gather_normalise_kernel<<<g.cap / GATHER_PATCHES_PER_CTA, GATHER_THREADS, 0, st>>>(
-                s.tex, g, s.locs, s.counts, s.A0, c->debug_capture ? s.q_u8 : nullptr);
+            if (c->p.patch_mode == 1) {
+                normals_kernel<<<(g.W * g.H + 255) / 256, 256, 0, st>>>(s.depth, g.W, g.H, c->p.normals_focal, s.normals);
+                LAUNCH_CHECK(c, s);
+                gather_normals_kernel<<<g.cap / GATHER_PATCHES_PER_CTA, GATHER_THREADS, 0, st>>>(
+                    s.tex, s.normals, g, s.locs, s.counts, s.A0, c->debug_capture ? s.q_u8 : nullptr);
+            } else
+                gather_normalise_kernel<<<g.cap / GATHER_PATCHES_PER_CTA, GATHER_THREADS, 0, st>>>(
+                    s.tex, g, s.locs, s.counts, s.A0, c->debug_capture ? s.q_u8 : nullptr);
             LAUNCH_CHECK(c, s);
             break;
         }
@@ -612,7 +620,11 @@ int buffer_of(hf6d_ctx* c, Slot& s, int what, BufInfo& b) {
     switch (what) {
         case HF6D_BUF_COUNTS: b = {s.counts, 8}; break;
         case HF6D_BUF_LOCS: b = {s.locs, (size_t)g.cap * 8}; break;
-        case HF6D_BUF_PATCH_U8: b = {s.q_u8, (size_t)g.cap * 256}; break;
+        case HF6D_BUF_PATCH_U8: b = {s.q_u8, (size_t)g.cap * c->dm.n_in[0]}; break;
+        case HF6D_BUF_NORMALS:
+            if (!s.normals) return fail(c, HF6D_ESTATE, "surface normals exist only in patch_mode 1");
+            b = {s.normals, HW * 16};
+            break;
         case HF6D_BUF_FEATURES: b = {s.feat, (size_t)g.cap * c->hf.F * 4}; break;
         case HF6D_BUF_LEAF_ORD: b = {s.leaf_ord, (size_t)g.cap * c->hf.T * 4}; break;
         case HF6D_BUF_MAPS: b = {s.maps, HW * c->hf.K * 8}; break;
@@ -646,8 +658,13 @@ int finish_create(hf6d_ctx* c, int device, int n_slots) {
     if (p.batch_size <= 0) return fail(c, HF6D_EINVAL, "batch_size must be positive");
     if (p.patch_vox != 8) return fail(c, HF6D_EINVAL, "patch_size_in_voxels = %d: only 8 (the 256-input encoder) is supported", p.patch_vox);
     if (c->layers.size() != 3) return fail(c, HF6D_EINVAL, "encoder must have 3 layers");
-    if (c->layers[0].in != 4 * p.patch_vox * p.patch_vox)
-        return fail(c, HF6D_EINVAL, "encoder input %d != 4*patch^2 = %d", c->layers[0].in, 4 * p.patch_vox * p.patch_vox);
+    if (p.patch_mode != 0 && p.patch_mode != 1) return fail(c, HF6D_EINVAL, "patch_mode must be 0 (RGB-D) or 1 (RGB + normals)");
+    if (p.patch_mode == 1 && !(p.normals_focal > 0.f)) return fail(c, HF6D_EINVAL, "normals_focal must be positive");
+    {
+        const int nch = p.patch_mode == 1 ? 6 : 4;
+        if (c->layers[0].in != nch * p.patch_vox * p.patch_vox)
+            return fail(c, HF6D_EINVAL, "encoder input %d != %d*patch^2 = %d", c->layers[0].in, nch, nch * p.patch_vox * p.patch_vox);
+    }
     if (c->layers[1].in != c->layers[0].out || c->layers[2].in != c->layers[1].out)
         return fail(c, HF6D_EINVAL, "encoder layer shapes do not chain");
     if (c->layers[2].out != c->hf.F)  // HFTest.cpp:595-596
@@ -664,6 +681,7 @@ int finish_create(hf6d_ctx* c, int device, int n_slots) {
     g.gw = (p.W + p.stride - 1) / p.stride;
     g.gh = (p.H + p.stride - 1) / p.stride;
     g.fx = p.fx; g.fy = p.fy; g.cx = p.cx; g.cy = p.cy;
+    g.focal = p.patch_mode == 1 ? p.normals_focal : p.fx;  // HFTest.cpp:394 vs :356
     g.ps = p.patch_vox; g.vox = p.voxel_m; g.range = p.max_depth_range_m; g.dist_thr = p.distance_threshold_m;
     g.fill_random = p.fill_random; g.fill_seed = p.fill_seed; g.batch = p.batch_size;
     g.cap = round_up(g.gw * g.gh, 128);
@@ -812,6 +830,8 @@ void hf6d_default_params(hf6d_params* p) {
     p->min_yaw_pitch_drop_ratio = 1.0f / 1000.0f;
     p->centers_blur_size = 13; p->centers_nms_wsize = 40;
     p->pose_blur_size = 35; p->pose_nms_wsize = 35;
+    p->patch_mode = 0;
+    p->normals_focal = 575.0f;  // HFTest.cpp:329, :356
 }
 
 const char* hf6d_last_error(const hf6d_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
@@ -1092,7 +1112,7 @@ int64_t hf6d_fetch(hf6d_ctx* c, int slot, int what, void* dst, size_t cap_bytes)
         if (what == HF6D_BUF_LOCS) bytes = P * 8;
         else if (what == HF6D_BUF_PATCH_U8) {
             if (!c->debug_capture) return fail(c, HF6D_ESTATE, "HF6D_BUF_PATCH_U8 needs hf6d_set_debug_capture(1) before the run");
-            bytes = Pp * 256;
+            bytes = Pp * (size_t)c->dm.n_in[0];
         } else if (what == HF6D_BUF_FEATURES) bytes = Pp * c->hf.F * 4;
         else bytes = Pp * c->hf.T * 4;
     }

@@ -33,6 +33,9 @@
  *     in double and scales once).
  *  C10 NMS result order for equal scores: emission order (std::sort is unstable in the reference).
  *  C11 float->int conversions that overflow or are NaN give INT_MIN (x86).
+ *  C12 (A2c, the RGB + surface-normals patch mode) the normal computation of surface_normals.cu and the length
+ *     normalisations of patch_extractor.cu:70-84 are evaluated in fp32 without FMA contraction; pixels the reference's
+ *     launch leaves unwritten are zero; the random normal used as fill comes from the counter-based generator of C2.
  */
 #include "hf6d_oracle.h"
 
@@ -212,12 +215,24 @@ void hf6d_ref_default_params(hf6d_ref_params* p) {
     p->centers_nms_wsize = 40;
     p->pose_blur_size = 35;
     p->pose_nms_wsize = 35;
+    p->patch_mode = 0;
+    p->normals_focal = 575.0f; /* HFTest.cpp:329, :356 */
+}
+
+static inline int32_t d2i_x86(double y) { /* C11 */
+    if (!(y == y) || y >= 2147483648.0 || y < -2147483648.0) return INT_MIN;
+    return (int32_t)y;
+}
+static inline int32_t f2i_x86(float y) { /* C11 */
+    if (!(y == y) || y >= 2147483648.0f || y < -2147483648.0f) return INT_MIN;
+    return (int32_t)y;
 }
 
 /* ------------------------------------------------------------------------------------------------ A2a */
 static int adaptive_size(const hf6d_ref_params* p, float depth_m) {
     /* patch_extractor.cu:257 / :378 -- ((ps*vox)/d)*f, float, truncated */
-    float v = (float)p->patch_vox * p->voxel_m / depth_m * p->fx;
+    /* the RGB-D extractor is handed fx (HFTest.cpp:394), the normals variant the literal 575.0f (HFTest.cpp:356) */
+    float v = (float)p->patch_vox * p->voxel_m / depth_m * (p->patch_mode ? p->normals_focal : p->fx);
     return (int)v;
 }
 
@@ -314,15 +329,142 @@ void hf6d_ref_gather(const uint8_t* bgr, const uint16_t* depth, const hf6d_ref_p
     }
 }
 
+/* ------------------------------------------------------------------------------------------------ A2c */
+/* surface_normals.cu:11-73.  The texture fetches sit on texel centres, so they return the texel itself.
+ * CHOICE (C12): products and sums are evaluated without FMA contraction, like everything else here (the reference's
+ * kernel is compiled by nvcc, whose contraction choices are not recoverable); pixels the reference's launch
+ * configuration leaves unwritten when W*H is not a multiple of 64 (:99-100) are zero. */
+void hf6d_ref_normals(const uint16_t* depth, int32_t W, int32_t H, float focal, float* normals) {
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < H; ++y)
+        for (int x = 0; x < W; ++x) {
+            float* o = normals + ((size_t)y * W + x) * 3;
+            o[0] = o[1] = o[2] = 0.0f;
+            if (!(x > 0 && x < W - 1 && y > 0 && y < H - 1)) continue;
+            const float z = (float)depth[(size_t)y * W + x] / 1000.0f;
+            const float z_left = (float)depth[(size_t)y * W + x - 1] / 1000.0f;
+            const float z_right = (float)depth[(size_t)y * W + x + 1] / 1000.0f;
+            const float z_up = (float)depth[(size_t)(y - 1) * W + x] / 1000.0f;
+            const float z_down = (float)depth[(size_t)(y + 1) * W + x] / 1000.0f;
+            if (!(z != 0 && z_left != 0 && z_right != 0 && z_up != 0 && z_down != 0)) continue;
+            const float hw = (float)W / 2.0f, hh = (float)H / 2.0f;
+            const float x_left = ((float)x - 1 - hw) * z_left / focal;
+            const float x_right = ((float)x + 1 - hw) * z_right / focal;
+            const float x_up = ((float)x - hw) * z_up / focal;
+            const float x_down = ((float)x - hw) * z_down / focal;
+            const float y_left = ((float)y - hh) * z_left / focal;
+            const float y_right = ((float)y - hh) * z_right / focal;
+            const float y_up = ((float)y - 1 - hh) * z_up / focal;
+            const float y_down = ((float)y + 1 - hh) * z_down / focal;
+            const float ax = (x_left - x_right) / 2.0f, ay = (y_left - y_right) / 2.0f, az = (z_left - z_right) / 2.0f;
+            const float bx = (x_down - x_up) / 2.0f, by = (y_down - y_up) / 2.0f, bz = (z_down - z_up) / 2.0f;
+            float nx = -(ay * bz - az * by);
+            float ny = -(az * bx - ax * bz);
+            float nz = -(ax * by - ay * bx);
+            const float mag = sqrtf(nx * nx + ny * ny + nz * nz);
+            o[0] = nx / mag; /* mag == 0 gives NaN, as in the reference */
+            o[1] = ny / mag;
+            o[2] = nz / mag;
+        }
+}
+
+static inline float texel7(const uint8_t* bgr, const uint16_t* depth, const float* normals, int W, int H, int x, int y,
+                           int ch) {
+    if (x < 0 || y < 0 || x >= W || y >= H) return 0.0f; /* cudaAddressModeBorder */
+    if (ch < 3) return (float)bgr[((size_t)y * W + x) * 3 + ch] / 255.0f;
+    if (ch == 3) return (float)depth[(size_t)y * W + x];
+    return normals[((size_t)y * W + x) * 3 + (ch - 4)];
+}
+
+static inline float bilinear7(const uint8_t* bgr, const uint16_t* depth, const float* normals, int W, int H, float u,
+                              float v, int ch) {
+    float fu = floorf(u), fv = floorf(v);
+    int i = (int)fu, j = (int)fv;
+    float a = frac8(u - fu), b = frac8(v - fv);
+    float w00 = (1.0f - a) * (1.0f - b), w10 = a * (1.0f - b), w01 = (1.0f - a) * b, w11 = a * b;
+    float s = w00 * texel7(bgr, depth, normals, W, H, i, j, ch);
+    s = s + w10 * texel7(bgr, depth, normals, W, H, i + 1, j, ch);
+    s = s + w01 * texel7(bgr, depth, normals, W, H, i, j + 1, ch);
+    s = s + w11 * texel7(bgr, depth, normals, W, H, i + 1, j + 1, ch);
+    return s;
+}
+
+/* patch_extractor.cu:12-111.  CHOICE (C2 again): the per-patch fill values come from a counter-based generator keyed
+ * on (fill_seed, patch index) instead of clock64()-seeded cuRAND; a zero-length draw is retried (:21-40). */
+void hf6d_ref_gather_normals(const uint8_t* bgr, const uint16_t* depth, const float* normals, const hf6d_ref_params* p,
+                             const int32_t* locs, int32_t P, float* patches) {
+    const int ps = p->patch_vox, W = p->W, H = p->H;
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < P; ++i) {
+        const int cx = locs[2 * i], cy = locs[2 * i + 1];
+        const float dc = (float)depth[(size_t)cy * W + cx] / 1000.0f;
+        const int a = adaptive_size(p, dc);
+        const int x0 = cx - a / 2, y0 = cy - a / 2;
+        const float step = (float)a / (float)ps;
+        float fill[6] = {0, 0, 0, 0, 0, 0};
+        if (p->fill_random) {
+            uint64_t z = mix64(p->fill_seed + 0x9E3779B97F4A7C15ULL * (uint64_t)(i + 1));
+            fill[2] = (float)((z & 0xFFFF) % 255) / 255.0f;         /* r */
+            fill[1] = (float)(((z >> 16) & 0xFFFF) % 255) / 255.0f; /* g */
+            fill[0] = (float)(((z >> 32) & 0xFFFF) % 255) / 255.0f; /* b */
+            fill[3] = 0.0f; fill[4] = 0.0f; fill[5] = 1.0f;
+            for (int attempt = 0; attempt < 4; ++attempt) {
+                const uint64_t z2 = mix64(z + 0x9E3779B97F4A7C15ULL), z3 = mix64(z2 + 0x9E3779B97F4A7C15ULL);
+                z = z3;
+                const float xr = (float)((uint32_t)z2 % 100000u) - 50000.0f;
+                const float yr = (float)((uint32_t)(z2 >> 32) % 100000u) - 50000.0f;
+                const float zr = (float)((uint32_t)z3 % 50000u); /* z >= 0: the normal faces the camera */
+                const float norm = sqrtf(xr * xr + yr * yr + zr * zr);
+                if (norm != 0) { fill[3] = xr / norm; fill[4] = yr / norm; fill[5] = zr / norm; break; }
+            }
+        }
+        float* out = patches + (size_t)i * ps * ps * 6;
+        for (int ty = 0; ty < ps; ++ty)
+            for (int tx = 0; tx < ps; ++tx) {
+                const float u = (float)x0 + (float)tx * step, v = (float)y0 + (float)ty * step;
+                float* o = out + (ty * ps + tx) * 6;
+                int in_object = 0;
+                const float d = bilinear7(bgr, depth, normals, W, H, u, v, 3) / 1000.0f;
+                if (d > 0) {
+                    const float x = bilinear7(bgr, depth, normals, W, H, u, v, 4);
+                    const float y = bilinear7(bgr, depth, normals, W, H, u, v, 5);
+                    const float z = bilinear7(bgr, depth, normals, W, H, u, v, 6);
+                    const float norm = sqrtf(x * x + y * y + z * z);
+                    if (norm > 0) {
+                        o[0] = bilinear7(bgr, depth, normals, W, H, u, v, 0);
+                        o[1] = bilinear7(bgr, depth, normals, W, H, u, v, 1);
+                        o[2] = bilinear7(bgr, depth, normals, W, H, u, v, 2);
+                        o[3] = x / norm; o[4] = y / norm; o[5] = z / norm;
+                        in_object = 1;
+                    }
+                }
+                if (!in_object)
+                    for (int c = 0; c < 6; ++c) o[c] = fill[c];
+            }
+    }
+}
+
+/* HFTest.cpp:443-470: colour channels (uchar)(v*255.0f); normals (uchar)((v/2.0 + 0.5f)*255.0f) -- the literal 2.0
+ * makes that expression double.  HWC -> CHW. */
+void hf6d_ref_quantise_normals(const float* patches, int32_t P, int32_t ps, uint8_t* q) {
+    const int n6 = ps * ps * 6;
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < P; ++i) {
+        const float* src = patches + (size_t)i * n6;
+        int pos = 0;
+        for (int c = 0; c < 6; ++c)
+            for (int row = 0; row < ps; ++row)
+                for (int col = 0; col < ps; ++col) {
+                    const float v = src[row * ps * 6 + col * 6 + c];
+                    int32_t k;
+                    if (c < 3) k = f2i_x86(v * 255.0f);
+                    else k = d2i_x86(((double)v / 2.0 + (double)0.5f) * (double)255.0f);
+                    q[(size_t)i * n6 + pos++] = (uint8_t)(k & 0xFF); /* C4 */
+                }
+    }
+}
+
 /* ------------------------------------------------------------------------------------------------ A3 */
-static inline int32_t d2i_x86(double y) { /* C11 */
-    if (!(y == y) || y >= 2147483648.0 || y < -2147483648.0) return INT_MIN;
-    return (int32_t)y;
-}
-static inline int32_t f2i_x86(float y) { /* C11 */
-    if (!(y == y) || y >= 2147483648.0f || y < -2147483648.0f) return INT_MIN;
-    return (int32_t)y;
-}
 
 void hf6d_ref_normalise(const float* patches, int32_t P, int32_t ps, uint8_t* q) {
     const int n1 = ps * ps, n3 = ps * ps * 3, n4 = ps * ps * 4;
@@ -823,11 +965,21 @@ int32_t hf6d_ref_detect(const hf6d_ref_forest* f, const uint8_t* bgr, const uint
     float* feat = NULL;
     double t1 = t0, t2 = t0, t3 = t0;
     if (!features_override) {
-        float* patches = (float*)malloc(sizeof(float) * (size_t)(Pp > 0 ? Pp : 1) * ps * ps * 4);
-        uint8_t* q = (uint8_t*)malloc((size_t)(Pp > 0 ? Pp : 1) * ps * ps * 4);
-        hf6d_ref_gather(bgr, depth, p, locs, Pp, patches);
-        t1 = now_s();
-        hf6d_ref_normalise(patches, Pp, ps, q);
+        const int nch = p->patch_mode ? 6 : 4;
+        float* patches = (float*)malloc(sizeof(float) * (size_t)(Pp > 0 ? Pp : 1) * ps * ps * nch);
+        uint8_t* q = (uint8_t*)malloc((size_t)(Pp > 0 ? Pp : 1) * ps * ps * nch);
+        if (p->patch_mode) {
+            float* normals = (float*)malloc(sizeof(float) * (size_t)p->W * p->H * 3);
+            hf6d_ref_normals(depth, p->W, p->H, p->normals_focal, normals);
+            hf6d_ref_gather_normals(bgr, depth, normals, p, locs, Pp, patches);
+            t1 = now_s();
+            hf6d_ref_quantise_normals(patches, Pp, ps, q);
+            free(normals);
+        } else {
+            hf6d_ref_gather(bgr, depth, p, locs, Pp, patches);
+            t1 = now_s();
+            hf6d_ref_normalise(patches, Pp, ps, q);
+        }
         t2 = now_s();
         feat = (float*)malloc(sizeof(float) * (size_t)(Pp > 0 ? Pp : 1) * dims[3]);
         hf6d_ref_encode(q, Pp, dims[0], weights[0], weights[1], dims[1], weights[2], weights[3], dims[2], weights[4],

@@ -38,6 +38,10 @@ typedef struct {
     int32_t max_yaw_pitch_hypotheses, max_roll_hypotheses;
     float min_location_score_ratio, min_yaw_pitch_drop_ratio;
     int32_t centers_blur_size, centers_nms_wsize, pose_blur_size, pose_nms_wsize;
+    /* A2c: 0 = RGB-D patches (4 channels, the live path), 1 = RGB + surface normals (6 channels, the variant the
+     * reference keeps commented out at HFTest.cpp:322-363 / :443-470); normals_focal is its hard-wired 575.0f */
+    int32_t patch_mode;
+    float normals_focal;
 } hf6d_ref_params;
 
 typedef struct {
@@ -62,6 +66,13 @@ int32_t hf6d_ref_scan_centres(const uint16_t* depth_mm, const hf6d_ref_params* p
 /* A1+A2b: patches [P][ps][ps][4] f32 HWC */
 void hf6d_ref_gather(const uint8_t* bgr, const uint16_t* depth_mm, const hf6d_ref_params* p, const int32_t* locs,
                      int32_t P, float* patches);
+/* A2c: surface normals [H][W][3] from the depth map (surface_normals.cu:11-73) */
+void hf6d_ref_normals(const uint16_t* depth_mm, int32_t W, int32_t H, float focal, float* normals);
+/* A2c: patches [P][ps][ps][6] f32 HWC = (B, G, R, nx, ny, nz)  (patch_extractor.cu:12-111) */
+void hf6d_ref_gather_normals(const uint8_t* bgr, const uint16_t* depth_mm, const float* normals, const hf6d_ref_params* p,
+                             const int32_t* locs, int32_t P, float* patches);
+/* A2c: q [P][6*ps*ps] u8, CHW -- plain quantisation, no local normalisation (HFTest.cpp:443-470) */
+void hf6d_ref_quantise_normals(const float* patches, int32_t P, int32_t ps, uint8_t* q);
 /* A3: q [P][4*ps*ps] u8, CHW */
 void hf6d_ref_normalise(const float* patches, int32_t P, int32_t ps, uint8_t* q);
 /* A4: features [P][n3].  W* are [out][in] row-major fp32 */

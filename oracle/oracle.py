@@ -31,7 +31,8 @@ class Params(C.Structure):
                 ("fill_seed", C.c_uint64), ("batch_size", C.c_int32), ("max_yaw_pitch_hypotheses", C.c_int32),
                 ("max_roll_hypotheses", C.c_int32), ("min_location_score_ratio", C.c_float),
                 ("min_yaw_pitch_drop_ratio", C.c_float), ("centers_blur_size", C.c_int32),
-                ("centers_nms_wsize", C.c_int32), ("pose_blur_size", C.c_int32), ("pose_nms_wsize", C.c_int32)]
+                ("centers_nms_wsize", C.c_int32), ("pose_blur_size", C.c_int32), ("pose_nms_wsize", C.c_int32),
+                ("patch_mode", C.c_int32), ("normals_focal", C.c_float)]
 
 
 class Hypothesis(C.Structure):
@@ -63,6 +64,10 @@ def lib():
         L.hf6d_ref_scan_centres.argtypes = [C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_int32]
         L.hf6d_ref_gather.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_int32, C.c_void_p]
         L.hf6d_ref_normalise.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
+        L.hf6d_ref_normals.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_void_p]
+        L.hf6d_ref_gather_normals.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_int32,
+                                              C.c_void_p]
+        L.hf6d_ref_quantise_normals.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
         L.hf6d_ref_encode.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
                                       C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
         L.hf6d_ref_traverse.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
@@ -129,6 +134,30 @@ def gather(bgr, depth, p: Params, locs):
     out = np.zeros((P, p.patch_vox, p.patch_vox, 4), np.float32)
     lib().hf6d_ref_gather(_p(bgr), _p(depth), C.byref(p), _p(np.ascontiguousarray(locs)), P, _p(out))
     return out
+
+
+def normals(depth, focal=575.0):
+    """A2c: surface normals [H][W][3] (surface_normals.cu:11-73)."""
+    H, W = depth.shape
+    out = np.zeros((H, W, 3), np.float32)
+    lib().hf6d_ref_normals(_p(depth), W, H, C.c_float(focal), _p(out))
+    return out
+
+
+def gather_normals(bgr, depth, nrm, p: Params, locs):
+    """A2c: patches [P][ps][ps][6] = (B, G, R, nx, ny, nz)."""
+    P = locs.shape[0]
+    out = np.zeros((P, p.patch_vox, p.patch_vox, 6), np.float32)
+    lib().hf6d_ref_gather_normals(_p(bgr), _p(depth), _p(np.ascontiguousarray(nrm)), C.byref(p),
+                                  _p(np.ascontiguousarray(locs)), P, _p(out))
+    return out
+
+
+def quantise_normals(patches):
+    P, ps = patches.shape[0], patches.shape[1]
+    q = np.zeros((P, 6 * ps * ps), np.uint8)
+    lib().hf6d_ref_quantise_normals(_p(np.ascontiguousarray(patches)), P, ps, _p(q))
+    return q
 
 
 def normalise(patches):

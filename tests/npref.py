@@ -105,6 +105,121 @@ def gather(bgr, depth, locs, W, H, ps, vox, fx, rng_m, fill_random=0, fill_seed=
     return out
 
 
+# ------------------------------------------------------------------------------------------------ A2c normals variant
+def surface_normals(depth, focal=575.0):
+    """PatchGen/src/cuda/surface_normals.cu:11-73: central differences of the back-projected neighbours, principal
+    point (W/2, H/2); zero where the pixel or one of its 4 neighbours has no depth, and on the image border."""
+    H, W = depth.shape
+    z = depth.astype(f32) / f32(1000.0)
+    out = np.zeros((H, W, 3), f32)
+    xs = np.arange(W, dtype=f32)[None, :].repeat(H, 0)
+    ys = np.arange(H, dtype=f32)[:, None].repeat(W, 1)
+    hw, hh, f = f32(W) / f32(2.0), f32(H) / f32(2.0), f32(focal)
+    c = (slice(1, H - 1), slice(1, W - 1))
+    zl, zr, zu, zd = z[1:-1, :-2], z[1:-1, 2:], z[:-2, 1:-1], z[2:, 1:-1]
+    X, Y = xs[c], ys[c]
+    x_left = (X - f32(1) - hw) * zl / f
+    x_right = (X + f32(1) - hw) * zr / f
+    x_up = (X - hw) * zu / f
+    x_down = (X - hw) * zd / f
+    y_left = (Y - hh) * zl / f
+    y_right = (Y - hh) * zr / f
+    y_up = (Y - f32(1) - hh) * zu / f
+    y_down = (Y + f32(1) - hh) * zd / f
+    ax, ay, az = (x_left - x_right) / f32(2), (y_left - y_right) / f32(2), (zl - zr) / f32(2)
+    bx, by, bz = (x_down - x_up) / f32(2), (y_down - y_up) / f32(2), (zd - zu) / f32(2)
+    nx = -(ay * bz - az * by)
+    ny = -(az * bx - ax * bz)
+    nz = -(ax * by - ay * bx)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        mag = np.sqrt(nx * nx + ny * ny + nz * nz)
+        n = np.stack([nx / mag, ny / mag, nz / mag], -1)
+    ok = (z[c] != 0) & (zl != 0) & (zr != 0) & (zu != 0) & (zd != 0)
+    out[c] = np.where(ok[..., None], n, f32(0))
+    return out
+
+
+def fill_values_normals(seed: int, p: int):
+    """Counter-based stand-in for patch_extractor.cu:21-40: colour k/255 and a random unit normal with z >= 0."""
+    golden = 0x9E3779B97F4A7C15
+    z = _mix64(seed + golden * (p + 1))
+    r = f32(float((z & 0xFFFF) % 255)) / f32(255.0)
+    g = f32(float(((z >> 16) & 0xFFFF) % 255)) / f32(255.0)
+    b = f32(float(((z >> 32) & 0xFFFF) % 255)) / f32(255.0)
+    n = (f32(0), f32(0), f32(1))
+    for _ in range(4):
+        z2 = _mix64(z + golden)
+        z3 = _mix64(z2 + golden)
+        z = z3
+        xr = f32(float((z2 & 0xFFFFFFFF) % 100000)) - f32(50000.0)
+        yr = f32(float((z2 >> 32) % 100000)) - f32(50000.0)
+        zr = f32(float((z3 & 0xFFFFFFFF) % 50000))
+        norm = np.sqrt(f32(f32(xr * xr + yr * yr) + zr * zr))
+        if norm != 0:
+            n = (xr / norm, yr / norm, zr / norm)
+            break
+    return (b, g, r) + n
+
+
+def gather_normals(bgr, depth, nrm, locs, W, H, ps, vox, focal, fill_random=0, fill_seed=0):
+    """patch_extractor.cu:12-111 on the 7-channel texture of HFTest.cpp:333-346.  Returns [P][ps][ps][6] f32, HWC."""
+    tex = np.zeros((H + 2, W + 2, 7), f32)
+    tex[1:-1, 1:-1, :3] = bgr.astype(f32) / f32(255.0)
+    tex[1:-1, 1:-1, 3] = depth.astype(f32)
+    tex[1:-1, 1:-1, 4:] = nrm
+    P = locs.shape[0]
+    cx, cy = locs[:, 0].astype(np.int64), locs[:, 1].astype(np.int64)
+    dc = tex[cy + 1, cx + 1, 3] / f32(1000.0)
+    a = (f32(ps) * f32(vox) / dc * f32(focal)).astype(np.int64)
+    x0, y0 = cx - a // 2, cy - a // 2
+    step = a.astype(f32) / f32(ps)
+    out = np.zeros((P, ps, ps, 6), f32)
+    fills = np.zeros((P, 6), f32)
+    if fill_random:
+        for p in range(P):
+            fills[p] = fill_values_normals(fill_seed, p)
+
+    def frac8(x):
+        return np.floor(x * f32(256.0) + f32(0.5)) * f32(1.0 / 256.0)
+
+    for ty in range(ps):
+        v = y0.astype(f32) + f32(ty) * step
+        j = np.floor(v)
+        beta = frac8(v - j)
+        j = j.astype(np.int64)
+        for tx in range(ps):
+            u = x0.astype(f32) + f32(tx) * step
+            i = np.floor(u)
+            alpha = frac8(u - i)
+            i = i.astype(np.int64)
+            ii, ii1 = np.clip(i + 1, 0, W + 1), np.clip(i + 2, 0, W + 1)
+            jj, jj1 = np.clip(j + 1, 0, H + 1), np.clip(j + 2, 0, H + 1)
+            w00, w10 = (f32(1) - alpha) * (f32(1) - beta), alpha * (f32(1) - beta)
+            w01, w11 = (f32(1) - alpha) * beta, alpha * beta
+            S = ((w00[:, None] * tex[jj, ii] + w10[:, None] * tex[jj, ii1]) + w01[:, None] * tex[jj1, ii]) + \
+                w11[:, None] * tex[jj1, ii1]
+            d = S[:, 3] / f32(1000.0)
+            x, y, z = S[:, 4], S[:, 5], S[:, 6]
+            norm = np.sqrt((x * x + y * y) + z * z)
+            with np.errstate(divide="ignore", invalid="ignore"):
+                val = np.stack([S[:, 0], S[:, 1], S[:, 2], x / norm, y / norm, z / norm], 1)
+            inside = (d > 0) & (norm > 0)
+            out[:, ty, tx, :] = np.where(inside[:, None], val, fills)
+    return out
+
+
+def quantise_normals(patches):
+    """HFTest.cpp:443-470: HWC -> CHW; colour (uchar)(v*255.0f); normals (uchar)((v/2.0 + 0.5f)*255.0f) in double."""
+    P, ps = patches.shape[0], patches.shape[1]
+    buf = np.ascontiguousarray(patches.transpose(0, 3, 1, 2)).reshape(P, 6, ps * ps)
+    q = np.zeros((P, 6, ps * ps), np.uint8)
+    col = buf[:, :3] * f32(255.0)
+    q[:, :3] = (np.where(np.isnan(col), f32(0), col).astype(np.int64) & 0xFF).astype(np.uint8)
+    nr = (buf[:, 3:].astype(np.float64) / 2.0 + 0.5) * 255.0
+    q[:, 3:] = (np.where(np.isnan(nr), 0.0, nr).astype(np.int64) & 0xFF).astype(np.uint8)
+    return q.reshape(P, 6 * ps * ps)
+
+
 # ------------------------------------------------------------------------------------------------ A3 normalise
 def normalise(patches):
     """HFTest.cpp:500-570: HWC -> CHW, sequential float sums, variance (never sqrt'ed), clip, scale, truncate.

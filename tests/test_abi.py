@@ -48,8 +48,10 @@ def test_library_is_built_for_sm_100a_and_never_links_the_oracle():
 
 
 def test_struct_layouts_match_the_header():
-    # hf6d_params: 22 fields, one 8-byte member after 12 4-byte members -> 96 bytes with natural alignment
-    assert C.sizeof(api.Params) == 96
+    # hf6d_params: 24 fields, one 8-byte member after 12 4-byte members -> 104 bytes with natural alignment
+    assert C.sizeof(api.Params) == 104
+    from oracle import oracle as O
+    assert C.sizeof(O.Params) == C.sizeof(api.Params)  # parity tests hand one block to both sides
     assert api.HYP_DTYPE.itemsize == 4 * 10 + 64
     assert C.sizeof(api.ObjectOptions) == 64 + 12
     assert api.CENTRE_LIST_DTYPE.itemsize == 4 + 16 * 12
@@ -57,6 +59,7 @@ def test_struct_layouts_match_the_header():
     assert (p.W, p.H, p.stride, p.batch_size) == (640, 480, 2, 100)
     assert (p.centers_blur_size, p.centers_nms_wsize, p.pose_blur_size, p.pose_nms_wsize) == (13, 40, 35, 35)
     assert (p.max_yaw_pitch_hypotheses, p.max_roll_hypotheses) == (7, 3)  # HFTest.h:175-183
+    assert p.patch_mode == 0 and p.normals_focal == 575.0                 # HFTest.cpp:329, :356
 
 
 @pytest.fixture(scope="module")
