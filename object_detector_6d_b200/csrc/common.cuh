@@ -26,8 +26,8 @@ struct FrameGeom {
 // Device view of the flattened forest (model.hpp::HostForest).
 struct DevForest {
     int T, K, F;
-    const PackedNode* nodes;
-    const int32_t* root;       // [T]
+    const PackedRecord* recs;  // two tree levels per 48-byte record
+    const int32_t* root;       // [T] record-numbered root entries
     const int32_t* leaf_base;  // [T+1]
     const int32_t* group_off;  // [L+1]
     const VoteGroup* groups;

@@ -174,8 +174,8 @@ int upload_model(hf6d_ctx* c) {
     const HostForest& hf = c->hf;
     dm.f.T = hf.T; dm.f.K = hf.K; dm.f.F = hf.F;
     int r;
-    if ((r = dev_upload(c, dm.allocs, &dm.f.nodes, hf.nodes))) return r;
-    if ((r = dev_upload(c, dm.allocs, &dm.f.root, hf.root))) return r;
+    if ((r = dev_upload(c, dm.allocs, &dm.f.recs, hf.recs))) return r;
+    if ((r = dev_upload(c, dm.allocs, &dm.f.root, hf.rec_root))) return r;
     if ((r = dev_upload(c, dm.allocs, &dm.f.leaf_base, hf.leaf_base))) return r;
     if ((r = dev_upload(c, dm.allocs, &dm.f.group_off, hf.group_off))) return r;
     if ((r = dev_upload(c, dm.allocs, &dm.f.groups, hf.groups))) return r;
@@ -406,16 +406,19 @@ int run_stage(hf6d_ctx* c, Slot& s, int stage) {
             break;
         }
         case HF6D_STAGE_TRAVERSE: {
-            const size_t smem = traverse_smem_bytes(f.F);
+            const TraversePlan tp = traverse_plan(f.F, f.T);
             const int n_owned = (f.T - c->shard_rank + c->shard_world - 1) / c->shard_world;
-            const int per_warp = (n_owned + TRV_WARPS - 1) / TRV_WARPS;
-            const int grid = c->sms * 2;
-            if (per_warp <= 1)
-                traverse_kernel<1><<<grid, TRV_THREADS, smem, st>>>(s.feat, f, s.counts, s.leaf_ord, c->shard_rank, c->shard_world);
-            else if (per_warp <= 2)
-                traverse_kernel<2><<<grid, TRV_THREADS, smem, st>>>(s.feat, f, s.counts, s.leaf_ord, c->shard_rank, c->shard_world);
+            const int per_slot = (n_owned + TRV_SLOTS - 1) / TRV_SLOTS;
+            const int threads = (tp.n_bufs + 1) * 32, n_recs = (int)c->hf.recs.size();
+            if (per_slot <= 1)
+                traverse_kernel<1><<<c->sms, threads, tp.smem, st>>>(s.feat, f, s.counts, s.leaf_ord, c->shard_rank, c->shard_world,
+                                                                   tp.n_bufs, tp.n_cache, n_recs);
+            else if (per_slot <= 2)
+                traverse_kernel<2><<<c->sms, threads, tp.smem, st>>>(s.feat, f, s.counts, s.leaf_ord, c->shard_rank, c->shard_world,
+                                                                   tp.n_bufs, tp.n_cache, n_recs);
             else
-                traverse_kernel<4><<<grid, TRV_THREADS, smem, st>>>(s.feat, f, s.counts, s.leaf_ord, c->shard_rank, c->shard_world);
+                traverse_kernel<4><<<c->sms, threads, tp.smem, st>>>(s.feat, f, s.counts, s.leaf_ord, c->shard_rank, c->shard_world,
+                                                                   tp.n_bufs, tp.n_cache, n_recs);
             LAUNCH_CHECK(c, s);
             break;
         }
@@ -766,9 +769,9 @@ int finish_create(hf6d_ctx* c, int device, int n_slots) {
     if (r) return r;
 
     // opt in to large dynamic shared memory once
-    CU_TRY(c, cudaFuncSetAttribute(traverse_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)traverse_smem_bytes(c->hf.F)));
-    CU_TRY(c, cudaFuncSetAttribute(traverse_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)traverse_smem_bytes(c->hf.F)));
-    CU_TRY(c, cudaFuncSetAttribute(traverse_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)traverse_smem_bytes(c->hf.F)));
+    CU_TRY(c, cudaFuncSetAttribute(traverse_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)traverse_plan(c->hf.F, c->hf.T).smem));
+    CU_TRY(c, cudaFuncSetAttribute(traverse_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)traverse_plan(c->hf.F, c->hf.T).smem));
+    CU_TRY(c, cudaFuncSetAttribute(traverse_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)traverse_plan(c->hf.F, c->hf.T).smem));
     if (cell_grid_bytes(p.W, p.H, p.centers_nms_wsize / 2, K) > 96 * 1024)
         return fail(c, HF6D_EINVAL, "frame too large for the centre-window lookup grid");
     if ((long long)g.cap * c->hf.T >= (1LL << 31)) return fail(c, HF6D_EINVAL, "patches x trees exceeds 2^31");

@@ -27,6 +27,17 @@ struct PackedNode {
 };
 static_assert(sizeof(PackedNode) == 16, "one node = one 16-byte load");
 
+// Two tree levels per load: a record holds the test of an internal node at even depth and the tests of its two
+// children, plus the four grandchild entries.  A missing child test (the child is a leaf) is "0 < +inf" -> left, with
+// both entries of that side pointing at the leaf.  An entry is a record index (>= 0) or ~global_leaf (< 0).
+struct PackedRecord {
+    uint32_t f1f2[3];  // node, left child, right child
+    float thr[3];
+    int32_t next[4];   // [2 * (went right at the node) + (went right at the child)]
+    uint32_t pad[2];
+};
+static_assert(sizeof(PackedRecord) == 48, "one record = three 16-byte loads");
+
 struct VoteGroup {   // votes of one (leaf, class) pair that passes the class_prob >= 0.5 gate (HFTest.cpp:191)
     int32_t cls;
     uint32_t w;      // Q16 weight
@@ -38,7 +49,9 @@ struct HostForest {
     float vox = 0;
     int max_depth = 0;
     std::vector<PackedNode> nodes;
-    std::vector<int32_t> root;       // [T] entry of each tree's root
+    std::vector<PackedRecord> recs;  // the same trees, two levels per record (what the traversal kernel walks)
+    std::vector<int32_t> root;       // [T] entry of each tree's root (node numbering)
+    std::vector<int32_t> rec_root;   // [T] entry of each tree's root (record numbering)
     std::vector<int32_t> leaf_base;  // [T+1] first global leaf of tree t (leaves in file order)
     std::vector<int32_t> leaf_id;    // [L] leaf_id field of the file
     std::vector<float> class_prob;   // [L][K]
@@ -219,8 +232,55 @@ inline bool load_forest(const std::string& dir, HostForest& hf, std::string& err
             hf.nodes.push_back(pn);
         }
         hf.n_internal += (int64_t)order.size();
+        // two-level records: breadth-first over the internal nodes at even depth
+        {
+            const int32_t rbase = (int32_t)hf.recs.size();
+            std::vector<int32_t> rorder, ridx(tn.size(), -1);
+            if (tn[root_idx].leaf < 0) { rorder.push_back(root_idx); ridx[root_idx] = rbase; }
+            for (size_t h = 0; h < rorder.size(); ++h) {
+                const TmpNode& n = tn[rorder[h]];
+                for (int s = 0; s < 2; ++s) {
+                    const TmpNode& ch = tn[n.child[s]];
+                    if (ch.leaf >= 0) continue;
+                    for (int b = 0; b < 2; ++b) {
+                        const int32_t gc = ch.child[b];
+                        if (tn[gc].leaf < 0) { ridx[gc] = rbase + (int32_t)rorder.size(); rorder.push_back(gc); }
+                    }
+                }
+            }
+            auto test_of = [&](const TmpNode& n, uint32_t& f1f2, float& thr) {
+                uint32_t f1 = (uint32_t)hf.F, f2 = (uint32_t)hf.F;
+                if (n.mode == 0) { f1 = (uint32_t)n.f1; f2 = (uint32_t)n.f2; }
+                else if (n.mode == 1) { f1 = (uint32_t)n.f1; }
+                f1f2 = f1 | (f2 << 16);
+                thr = n.thr;
+            };
+            hf.rec_root.push_back(tn[root_idx].leaf >= 0 ? ~tn[root_idx].leaf : ridx[root_idx]);
+            for (size_t h = 0; h < rorder.size(); ++h) {
+                const TmpNode& n = tn[rorder[h]];
+                PackedRecord r;
+                memset(&r, 0, sizeof r);
+                test_of(n, r.f1f2[0], r.thr[0]);
+                for (int s = 0; s < 2; ++s) {
+                    const TmpNode& ch = tn[n.child[s]];
+                    if (ch.leaf >= 0) {
+                        r.f1f2[1 + s] = (uint32_t)hf.F | ((uint32_t)hf.F << 16);  // 0 - 0 < +inf: always "left"
+                        r.thr[1 + s] = INFINITY;
+                        r.next[2 * s] = r.next[2 * s + 1] = ~ch.leaf;
+                    } else {
+                        test_of(ch, r.f1f2[1 + s], r.thr[1 + s]);
+                        for (int b = 0; b < 2; ++b) {
+                            const int32_t gc = ch.child[b];
+                            r.next[2 * s + b] = tn[gc].leaf >= 0 ? ~tn[gc].leaf : ridx[gc];
+                        }
+                    }
+                }
+                hf.recs.push_back(r);
+            }
+        }
     }
     if (hf.nodes.empty()) hf.nodes.push_back(PackedNode{0, 0.f, -1, -1});  // keep device arrays non-empty
+    if (hf.recs.empty()) { PackedRecord r; memset(&r, 0, sizeof r); hf.recs.push_back(r); }
     return true;
 }
 
