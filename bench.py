@@ -313,36 +313,44 @@ def run_cuda(args, rank, world, local_rank):
         tree = None
         if world > 1:
             from object_detector_6d_b200 import sharded
-            sd = sharded.TreeShardedDetector(forest_dir, wpath, p, device=local_rank, n_slots=2)
-            for s in range(2):
+            sd = sharded.TreeShardedDetector(forest_dir, wpath, p, device=local_rank, n_slots=n_slots)
+            for s in range(n_slots):
                 sd.det.bind_frame(s, bgr_all[0].data_ptr(), dep_all[0].data_ptr())
 
             def step_tree():
                 for i in range(BATCH):
-                    s = i % 2
+                    s = i % n_slots
                     j = i % DISTINCT_FRAMES
                     sd.det.bind_frame(s, bgr_all[j].data_ptr(), dep_all[j].data_ptr())
                     sd.run(s)
 
+            main_t = torch.cuda.Stream()
             for _ in range(args.warmup):
                 step_tree()
-            sd.stream.synchronize()
+            torch.cuda.synchronize()
             dist.barrier()
             torch.cuda.synchronize()
             t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            t0e.record(sd.stream)
+            t0e.record(main_t)
+            for st_ in sd.streams:
+                st_.wait_event(t0e)
             for _ in range(args.steps):
                 step_tree()
-            t1e.record(sd.stream)
-            sd.stream.synchronize()
+            for st_ in sd.streams:
+                ev = torch.cuda.Event()
+                ev.record(st_)
+                main_t.wait_event(ev)
+            t1e.record(main_t)
+            main_t.synchronize()
             t = torch.tensor([t0e.elapsed_time(t1e)], device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms_tree = float(t.item())
             tree = {"frames_per_s": BATCH * args.steps / (ms_tree * 1e-3), "ms_per_frame": ms_tree / (BATCH * args.steps),
-                    "trees_per_rank": len(sd.trees), "exchange_bytes_per_frame": int(K_CLASSES * 640 * 480 * 8 + counts[0][1] * T_TREES * 4),
+                    "trees_per_rank": len(sd.trees), "classes_per_rank": len(sd.classes), "exchange_bytes_per_frame": int(K_CLASSES * 640 * 480 * 8 + counts[0][1] * T_TREES * 4),
                     "scaling": "strong (same frames on every rank, trees t % N == rank)",
-                    "note": "scan/gather/encode are replicated (every rank needs all features), traverse+vote are sharded"}
-            for s in range(2):
+                    "note": "scan/gather/encode are replicated (every rank needs all features); traverse+vote are sharded by tree, "
+                            "centres+pose by class after the exchange; %d frames in flight (the exchange overlaps other frames' kernels)" % n_slots + ""}
+            for s in range(n_slots):
                 sd.det.bind_frame(s, None, None)
             sd.close()
 

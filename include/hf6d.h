@@ -154,6 +154,10 @@ int hf6d_set_fill_seed(hf6d_ctx* c, uint64_t seed);
  * The caller sums HF6D_BUF_MAPS across ranks (NCCL all-reduce, uint64 sum) and max-reduces HF6D_BUF_LEAF_ORD between
  * hf6d_run(.., VOTE) and hf6d_run(CENTRES, ..). */
 int hf6d_set_tree_shard(hf6d_ctx* c, int rank, int world);
+/* Class sharding of the stages after the exchange: this context seeks centres and poses (HF6D_STAGE_CENTRES, _POSE)
+ * only for classes k with k % world == rank; votes are still cast for every detected class.  The hypothesis lists of
+ * the ranks, concatenated in class order, equal the unsharded list. */
+int hf6d_set_class_shard(hf6d_ctx* c, int rank, int world);
 /* Encoder arithmetic: 0 = bf16 operands (default), 1 = split-bf16 (hi+lo operands, 3 MMAs per product, ~fp32). */
 int hf6d_set_encoder_mode(hf6d_ctx* c, int mode);
 int hf6d_set_debug_capture(hf6d_ctx* c, int on); /* keep HF6D_BUF_PATCH_U8 */

@@ -24,7 +24,7 @@ MAX_CENTRES = 16
 EXPORTS = (
     "hf6d_default_params", "hf6d_create", "hf6d_create_from_options", "hf6d_destroy", "hf6d_last_error",
     "hf6d_get_params", "hf6d_model", "hf6d_set_objects", "hf6d_get_objects", "hf6d_set_fill_seed",
-    "hf6d_set_tree_shard", "hf6d_set_encoder_mode", "hf6d_set_debug_capture", "hf6d_detect", "hf6d_submit",
+    "hf6d_set_tree_shard", "hf6d_set_class_shard", "hf6d_set_encoder_mode", "hf6d_set_debug_capture", "hf6d_detect", "hf6d_submit",
     "hf6d_wait", "hf6d_host_alloc", "hf6d_host_free", "hf6d_upload", "hf6d_run", "hf6d_sync", "hf6d_collect",
     "hf6d_fetch", "hf6d_inject", "hf6d_device_ptr", "hf6d_set_stream", "hf6d_stage_ms", "hf6d_launch_count",
     "hf6d_pose_from_tuple", "hf6d_bind_frame", "hf6d_encoder_layer_ms", "hf6d_result_bytes",
@@ -101,6 +101,7 @@ def load():
     L.hf6d_get_objects.argtypes = [vp, C.POINTER(ObjectOptions), i32]
     L.hf6d_set_fill_seed.argtypes = [vp, C.c_uint64]
     L.hf6d_set_tree_shard.argtypes = [vp, i32, i32]
+    L.hf6d_set_class_shard.argtypes = [vp, i32, i32]
     L.hf6d_set_encoder_mode.argtypes = [vp, i32]
     L.hf6d_set_debug_capture.argtypes = [vp, i32]
     L.hf6d_detect.argtypes = [vp, vp, vp, vp, i32, C.POINTER(i32)]
@@ -274,6 +275,9 @@ class Detector:
 
     def set_tree_shard(self, rank: int, world: int):
         self._ck(self._L.hf6d_set_tree_shard(self._h, rank, world))
+
+    def set_class_shard(self, rank: int, world: int):
+        self._ck(self._L.hf6d_set_class_shard(self._h, rank, world))
 
     def set_debug_capture(self, on: bool):
         self._ck(self._L.hf6d_set_debug_capture(self._h, int(on)))

@@ -43,6 +43,7 @@ struct DeviceModel {
     float* b[3] = {nullptr, nullptr, nullptr};
     int n_in[3], n_out[3], k_pad[3], n_pad[3], block_n[3];
     uint8_t* sep_ok = nullptr;
+    uint8_t* class_mask = nullptr;  // [HF6D_MAX_CLASSES] classes whose centres / poses this context seeks
 };
 
 struct Slot {
@@ -108,6 +109,7 @@ struct hf6d_ctx {
     int wc_ctas_per_sm = 1;      // resident CTAs of window_entries_kernel per SM
     int entry_cap = 0;           // capacity of a frame slot's window-entry list (entries beyond it are accumulated in place)
     int shard_rank = 0, shard_world = 1;
+    int class_rank = 0, class_world = 1;  // centres + pose only for classes k % class_world == class_rank
     int encoder_mode = 0;
     int debug_capture = 0;
     int next_ticket = 0;
@@ -169,6 +171,8 @@ void build_sep_table(std::vector<uint8_t>& t) {
         }
 }
 
+int upload_class_mask(hf6d_ctx* c);
+
 int upload_model(hf6d_ctx* c) {
     DeviceModel& dm = c->dm;
     const HostForest& hf = c->hf;
@@ -205,6 +209,8 @@ int upload_model(hf6d_ctx* c) {
     const uint8_t* sp = nullptr;
     if ((r = dev_upload(c, dm.allocs, &sp, sep))) return r;
     dm.sep_ok = const_cast<uint8_t*>(sp);
+    if ((r = dev_alloc(c, dm.allocs, &dm.class_mask, (size_t)HF6D_MAX_CLASSES))) return r;
+    if ((r = upload_class_mask(c))) return r;
 
     // encoder: bf16 weights [n_pad][k_pad], zero padded; 1/255 folded into layer 1 (the A operand holds q itself)
     for (int l = 0; l < 3; ++l) {
@@ -326,11 +332,29 @@ void free_all(hf6d_ctx* c) {
     for (void* p : c->dm.allocs) cudaFree(p);
 }
 
-ObjectSwitches switches_of(const hf6d_ctx* c) {
+// Classes whose centres and poses this context seeks: detected AND owned under the class shard (votes are cast for every
+// detected class regardless, because the summed maps of a class need the votes of all ranks' trees).
+bool seeks_class(const hf6d_ctx* c, int k) {
+    return c->objects[k].should_detect && (k % c->class_world) == c->class_rank;
+}
+
+ObjectSwitches switches_of(const hf6d_ctx* c, bool pose_stage = false) {
     ObjectSwitches sw;
     memset(&sw, 0, sizeof sw);
-    for (size_t i = 0; i < c->objects.size(); ++i) sw.should_detect[i] = c->objects[i].should_detect ? 1 : 0;
+    for (size_t i = 0; i < c->objects.size(); ++i)
+        sw.should_detect[i] = (pose_stage ? seeks_class(c, (int)i) : (bool)c->objects[i].should_detect) ? 1 : 0;
     return sw;
+}
+
+int upload_class_mask(hf6d_ctx* c) {
+    uint8_t m[HF6D_MAX_CLASSES];
+    memset(m, 0, sizeof m);
+    for (int k = 0; k < c->hf.K && k < (int)c->objects.size(); ++k) m[k] = seeks_class(c, k) ? 1 : 0;
+    if (c->dm.class_mask) {
+        cudaError_t e = cudaMemcpy(c->dm.class_mask, m, sizeof m, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { c->err = std::string("cudaMemcpy(class mask): ") + cudaGetErrorString(e); return HF6D_ECUDA; }
+    }
+    return HF6D_OK;
 }
 
 struct ResView {
@@ -435,27 +459,27 @@ int run_stage(hf6d_ctx* c, Slot& s, int stage) {
             const MapRect full{0, 0, g.H, g.W};
             const int kb = p.centers_blur_size, w = p.centers_nms_wsize;
             box_rows_kernel<<<dim3((g.H + BLUR_WARPS - 1) / BLUR_WARPS, K), BLUR_WARPS * 32,
-                              (size_t)BLUR_WARPS * (g.W + 1) * 8, st>>>(s.maps, s.map_tmp, md, full, full, kb, nullptr);
+                              (size_t)BLUR_WARPS * (g.W + 1) * 8, st>>>(s.maps, s.map_tmp, md, full, full, kb, c->dm.class_mask);
             LAUNCH_CHECK(c, s);
             box_cols_kernel<<<dim3((g.W + 127) / 128, (g.H + BLUR_COL_CHUNK - 1) / BLUR_COL_CHUNK, K), 128, 0, st>>>(
-                s.map_tmp, s.blurred, md, full, full, kb, 1.0 / ((double)kb * kb), nullptr);
+                s.map_tmp, s.blurred, md, full, full, kb, 1.0 / ((double)kb * kb), c->dm.class_mask);
             LAUNCH_CHECK(c, s);
             CU_TRY(c, cudaMemsetAsync(s.list_n, 0, (size_t)std::max(K, S) * 4, st));
             // reference loop bounds: lefts 0..cols-wx, tops 0..rows-2*wy+1 (HFTest.cpp:246-249)
             const int n_left = g.W - w + 1, n_top = g.H - 2 * w + 2;
             if (n_left > 0 && n_top > 0) {
                 const BlockGrid bg = make_block_grid(full);
-                nms_blockmax_kernel<<<dim3((g.W + 31) / 32, (bg.by + 7) / 8, K), 256, 0, st>>>(s.blurred, s.bmax, full, nullptr);
+                nms_blockmax_kernel<<<dim3((g.W + 31) / 32, (bg.by + 7) / 8, K), 256, 0, st>>>(s.blurred, s.bmax, full, c->dm.class_mask);
                 LAUNCH_CHECK(c, s);
                 nms_select_kernel<<<dim3((bg.by * bg.bx + NMS_SELECT_THREADS - 1) / NMS_SELECT_THREADS, 1, K), NMS_SELECT_THREADS, 0, st>>>(s.blurred, s.bmax, full, w, w, 0, n_left, 0,
-                                                                                         n_top, s.list, s.list_n, nullptr);
+                                                                                         n_top, s.list, s.list_n, c->dm.class_mask);
                 LAUNCH_CHECK(c, s);
             }
             ObjectLimits lim;
             memset(&lim, 0, sizeof lim);
             for (int k = 0; k < K; ++k) {
                 lim.max_loc[k] = c->objects[k].max_location_hypotheses;
-                lim.should_detect[k] = c->objects[k].should_detect ? 1 : 0;
+                lim.should_detect[k] = seeks_class(c, k) ? 1 : 0;
             }
             select_centres_kernel<<<K, 256, 0, st>>>(s.list, s.list_n, lim, p.min_location_score_ratio, rv.centres, rv.active);
             LAUNCH_CHECK(c, s);
@@ -466,7 +490,7 @@ int run_stage(hf6d_ctx* c, Slot& s, int stage) {
             const int max_yp = p.max_yaw_pitch_hypotheses, max_roll = p.max_roll_hypotheses;
             // clear only the accumulator slots a class can use (slot = class * HF6D_MAX_CENTRES + centre rank)
             for (int k = 0; k < K; ++k) {
-                const int n = c->objects[k].should_detect ? c->objects[k].max_location_hypotheses : 0;
+                const int n = seeks_class(c, k) ? c->objects[k].max_location_hypotheses : 0;
                 if (n <= 0) continue;
                 const size_t s0 = (size_t)k * HF6D_MAX_CENTRES;
                 CU_TRY(c, cudaMemsetAsync(s.zacc + s0 * HF6D_Z_BINS, 0, (size_t)n * HF6D_Z_BINS * 8, st));
@@ -486,7 +510,7 @@ int run_stage(hf6d_ctx* c, Slot& s, int stage) {
                 // through list_n[n_lists + 1] (both zeroed above)
                 int* ctr = s.list_n + std::max(K, S);
                 const int wc_blocks = (int)std::min<long long>((items + VOTE_THREADS - 1) / VOTE_THREADS, (long long)c->sms * c->wc_ctas_per_sm);
-                window_entries_kernel<<<wc_blocks, VOTE_THREADS, cell_bytes, st>>>(f, g, switches_of(c), s.locs, s.depth, s.leaf_ord,
+                window_entries_kernel<<<wc_blocks, VOTE_THREADS, cell_bytes, st>>>(f, g, switches_of(c, true), s.locs, s.depth, s.leaf_ord,
                                                                                  s.counts, ct, half_win, n_groups, ctr, s.entries,
                                                                                  c->entry_cap, ctr + 1, s.win_cnt, s.zacc);
                 LAUNCH_CHECK(c, s);
@@ -494,7 +518,7 @@ int run_stage(hf6d_ctx* c, Slot& s, int stage) {
                     ZSlotTable zt;
                     memset(&zt, 0, sizeof zt);
                     for (int k = 0; k < K; ++k)
-                        zt.zoff[k + 1] = (int16_t)(zt.zoff[k] + (c->objects[k].should_detect ? c->objects[k].max_location_hypotheses : 0));
+                        zt.zoff[k + 1] = (int16_t)(zt.zoff[k] + (seeks_class(c, k) ? c->objects[k].max_location_hypotheses : 0));
                     const size_t zbytes = (size_t)zt.zoff[K] * HF6D_Z_BINS * 4;
                     static const bool smem_z_ok = !(getenv("HF6D_WA_SMEM_Z") && atoi(getenv("HF6D_WA_SMEM_Z")) == 0);  // tuning override
                     if (smem_z_ok && zbytes <= (size_t)WA_MAX_DYN_SMEM)
@@ -964,7 +988,7 @@ int hf6d_set_objects(hf6d_ctx* c, const hf6d_object* objs, int n) {
         if (objs[k].max_location_hypotheses < 0 || objs[k].max_location_hypotheses > HF6D_MAX_CENTRES)
             return fail(c, HF6D_EINVAL, "max_location_hypotheses of object %d must be in [0, %d]", k, HF6D_MAX_CENTRES);
     c->objects.assign(objs, objs + n);
-    return HF6D_OK;
+    return upload_class_mask(c);
 }
 
 int hf6d_get_objects(const hf6d_ctx* c, hf6d_object* objs, int cap) {
@@ -986,6 +1010,14 @@ int hf6d_set_tree_shard(hf6d_ctx* c, int rank, int world) {
     c->shard_rank = rank;
     c->shard_world = world;
     return HF6D_OK;
+}
+
+int hf6d_set_class_shard(hf6d_ctx* c, int rank, int world) {
+    if (!c) return HF6D_EINVAL;
+    if (world < 1 || rank < 0 || rank >= world) return fail(c, HF6D_EINVAL, "bad class shard %d/%d", rank, world);
+    c->class_rank = rank;
+    c->class_world = world;
+    return upload_class_mask(c);
 }
 
 int hf6d_set_encoder_mode(hf6d_ctx* c, int mode) {

@@ -7,12 +7,16 @@ per-class vote maps and the centre->leaf back-map, so rank r of N owns trees {t 
   rank r          : traverse + vote its own trees into its own Q16 maps          hf6d_run(SCAN .. VOTE)
   ONE exchange    : all-reduce(SUM) of the maps   [K][H][W] uint64 (as int64)    14.7 MB at 6 x 480 x 640
                     all-reduce(MAX) of the leaf table [cap][T] int32             (entries of foreign trees are -1)
-  every rank      : centres + pose mode seeking on the summed maps / merged table hf6d_run(CENTRES .. POSE)
+  rank r          : centres + pose mode seeking on the summed maps / merged table hf6d_run(CENTRES .. POSE)
+                    for ITS classes (k % N == r, hf6d_set_class_shard): the centres of different classes are
+                    independent units of work, so the stage that follows the exchange shards too
+  (optional)      : the ranks' hypothesis lists, concatenated in class order, are the unsharded list (gather())
 
 Vote weights are Q16 integers, so the summed maps -- and everything downstream -- are bit-identical to the single-GPU
 result whatever N is (the reference's float maps depend on the OpenMP schedule, HFTest.cpp:645-654).
 
-The exchange runs on the slot's CUDA stream (NCCL is stream-ordered after the vote kernel; no host sync in between).
+The exchange runs on the slot's own CUDA stream (NCCL is stream-ordered after the vote kernel; no host sync in between),
+and every frame slot has its own stream, so the exchange of frame i overlaps the encoder of frame i+1.
 `exchange()` itself is backend-agnostic: the CPU test-suite drives it with gloo at world_size 2.
 """
 from __future__ import annotations
@@ -44,7 +48,7 @@ def exchange(maps, leaf_table, group=None):
 class TreeShardedDetector:
     """This rank's libhf6d context plus the exchange.  Construct it on every rank after init_process_group."""
 
-    def __init__(self, forest_dir, weights_path, params=None, device=0, n_slots=2, group=None):
+    def __init__(self, forest_dir, weights_path, params=None, device=0, n_slots=2, group=None, shard_classes=True):
         import torch
         import torch.distributed as dist
         self.torch = torch
@@ -53,11 +57,15 @@ class TreeShardedDetector:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.det = api.Detector(forest_dir, weights_path, params, device=device, n_slots=n_slots)
         self.det.set_tree_shard(self.rank, self.world)
+        self.shard_classes = bool(shard_classes) and self.world > 1
+        if self.shard_classes:
+            self.det.set_class_shard(self.rank, self.world)
         self.device = device
-        self.stream = torch.cuda.Stream(device=device)
+        self.streams = [torch.cuda.Stream(device=device) for _ in range(n_slots)]
+        self.stream = self.streams[0]
         self._views = []
         for s in range(n_slots):
-            self.det.set_stream(s, self.stream.cuda_stream)
+            self.det.set_stream(s, self.streams[s].cuda_stream)
             maps = torch.as_tensor(self.det.device_array(api.BUF_MAPS, s), device=f"cuda:{device}")
             leaf = torch.as_tensor(self.det.device_array(api.BUF_LEAF_ORD, s), device=f"cuda:{device}")
             self._views.append((maps, leaf))
@@ -66,10 +74,16 @@ class TreeShardedDetector:
     def trees(self):
         return owned_trees(self.rank, self.world, self.det.T)
 
+    @property
+    def classes(self):
+        """Classes whose centres / poses this rank seeks."""
+        K = self.det.K
+        return [k for k in range(K) if not self.shard_classes or k % self.world == self.rank]
+
     def run(self, slot=0):
-        """Launch one frame (already uploaded / bound on `slot`) asynchronously on the shard stream."""
+        """Launch one frame (already uploaded / bound on `slot`) asynchronously on the slot's stream."""
         torch = self.torch
-        with torch.cuda.stream(self.stream):
+        with torch.cuda.stream(self.streams[slot]):
             self.det.run(slot, api.STAGE_SCAN, api.STAGE_VOTE)
             n = self.det.launch_count(slot)
             maps, leaf = self._views[slot]
@@ -77,10 +91,20 @@ class TreeShardedDetector:
             self.det.run(slot, api.STAGE_CENTRES, api.STAGE_POSE)
             self._launches = n + self.det.launch_count(slot)
 
-    def detect(self, bgr, depth, slot=0):
+    def detect(self, bgr, depth, slot=0, gather=True):
+        """One frame.  With gather (default) every rank returns the complete hypothesis list."""
         self.det.upload(slot, bgr, depth)
         self.run(slot)
-        return self.det.collect(slot)
+        mine = self.det.collect(slot)
+        return self.gather(mine) if gather and self.shard_classes else mine
+
+    def gather(self, mine):
+        """All ranks' hypothesis arrays, merged in class order (= the order of the unsharded list)."""
+        import torch.distributed as dist
+        parts = [None] * self.world
+        dist.all_gather_object(parts, mine, group=self.group)
+        allh = np.concatenate(parts) if parts else mine
+        return allh[np.argsort(allh["cls"], kind="stable")]
 
     def launches_per_frame(self) -> int:
         """Kernels of this repo launched by the last run() (the two NCCL all-reduces are not counted)."""

@@ -289,3 +289,22 @@ def test_window_entry_list_overflow_is_exact(case, full_run, cap, monkeypatch):
     finally:
         det.close()
     _same_hyps(hyp, full_run["hyp"])
+
+
+def test_class_shards_concatenate_to_the_full_list(case, full_run):
+    """hf6d_set_class_shard: centres + pose for classes k % N == r only; the shards' lists merge to the unsharded one."""
+    from object_detector_6d_b200 import api
+    det = case["det"]
+    try:
+        for world in (2, 3):
+            parts = []
+            for rank in range(world):
+                det.set_class_shard(rank, world)
+                h = det.detect(case["bgr"], case["depth"])
+                assert set(np.unique(h["cls"])) <= {k for k in range(det.K) if k % world == rank}
+                parts.append(h)
+            allh = np.concatenate(parts)
+            allh = allh[np.argsort(allh["cls"], kind="stable")]
+            _same_hyps(allh, full_run["hyp"])
+    finally:
+        det.set_class_shard(0, 1)
