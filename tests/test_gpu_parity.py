@@ -308,3 +308,34 @@ def test_class_shards_concatenate_to_the_full_list(case, full_run):
             _same_hyps(allh, full_run["hyp"])
     finally:
         det.set_class_shard(0, 1)
+
+
+@pytest.mark.parametrize("seed,T,depth", [(1, 1, 0), (2, 3, 1), (3, 5, 7), (4, 9, 12)])
+def test_traverse_random_forests_with_nans(case, seed, T, depth, tmp_path):
+    """Stage-isolated traversal on random forest files (a root that is a leaf, odd depths, single-level trees -- the
+    two-levels-per-record layout has to pad those) and features that contain NaNs (NaN compares false -> right)."""
+    from object_detector_6d_b200 import api
+    from oracle import oracle as O
+    from tests.test_properties import _write_random_tree
+    rng = np.random.default_rng(seed)
+    d = str(tmp_path)
+    K, F = 2, 800
+    for t in range(T):
+        _write_random_tree(rng, f"{d}/tree{t}.dat", K, F, depth)
+    with open(f"{d}/forest.txt", "w") as f:
+        f.write(f"{T} {K} {F} 8 0.005\n")
+    det = api.Detector(d, case["weights"], to_api_params(case["params"]), device=0, n_slots=1)
+    try:
+        det.upload(0, case["bgr"], case["depth"])
+        det.run(0, api.STAGE_SCAN, api.STAGE_SCAN)
+        det.sync(0)
+        P, Pp = det.counts(0)
+        feats = rng.normal(0, 0.4, (Pp, F)).astype(np.float32)
+        feats[rng.random(feats.shape) < 0.02] = np.nan
+        det.inject(api.BUF_FEATURES, feats)
+        det.run(0, api.STAGE_TRAVERSE, api.STAGE_TRAVERSE)
+        det.sync(0)
+        _, ords = O.traverse(O.Forest(d), feats)
+        assert np.array_equal(det.fetch(api.BUF_LEAF_ORD), ords)
+    finally:
+        det.close()
