@@ -462,15 +462,13 @@ int run_stage(hf6d_ctx* c, Slot& s, int stage) {
                               (size_t)BLUR_WARPS * (g.W + 1) * 8, st>>>(s.maps, s.map_tmp, md, full, full, kb, c->dm.class_mask);
             LAUNCH_CHECK(c, s);
             box_cols_kernel<<<dim3((g.W + 127) / 128, (g.H + BLUR_COL_CHUNK - 1) / BLUR_COL_CHUNK, K), 128, 0, st>>>(
-                s.map_tmp, s.blurred, md, full, full, kb, 1.0 / ((double)kb * kb), c->dm.class_mask);
+                s.map_tmp, s.blurred, md, full, full, kb, 1.0 / ((double)kb * kb), c->dm.class_mask, s.bmax);
             LAUNCH_CHECK(c, s);
             CU_TRY(c, cudaMemsetAsync(s.list_n, 0, (size_t)std::max(K, S) * 4, st));
             // reference loop bounds: lefts 0..cols-wx, tops 0..rows-2*wy+1 (HFTest.cpp:246-249)
             const int n_left = g.W - w + 1, n_top = g.H - 2 * w + 2;
             if (n_left > 0 && n_top > 0) {
                 const BlockGrid bg = make_block_grid(full);
-                nms_blockmax_kernel<<<dim3((g.W + 31) / 32, (bg.by + 7) / 8, K), 256, 0, st>>>(s.blurred, s.bmax, full, c->dm.class_mask);
-                LAUNCH_CHECK(c, s);
                 nms_select_kernel<<<dim3((bg.by * bg.bx + NMS_SELECT_THREADS - 1) / NMS_SELECT_THREADS, 1, K), NMS_SELECT_THREADS, 0, st>>>(s.blurred, s.bmax, full, w, w, 0, n_left, 0,
                                                                                          n_top, s.list, s.list_n, c->dm.class_mask);
                 LAUNCH_CHECK(c, s);
@@ -488,15 +486,23 @@ int run_stage(hf6d_ctx* c, Slot& s, int stage) {
         case HF6D_STAGE_POSE: {
             const size_t yp = (size_t)c->reg.ny * c->reg.np;
             const int max_yp = p.max_yaw_pitch_hypotheses, max_roll = p.max_roll_hypotheses;
-            // clear only the accumulator slots a class can use (slot = class * HF6D_MAX_CENTRES + centre rank)
-            for (int k = 0; k < K; ++k) {
-                const int n = seeks_class(c, k) ? c->objects[k].max_location_hypotheses : 0;
-                if (n <= 0) continue;
-                const size_t s0 = (size_t)k * HF6D_MAX_CENTRES;
-                CU_TRY(c, cudaMemsetAsync(s.zacc + s0 * HF6D_Z_BINS, 0, (size_t)n * HF6D_Z_BINS * 8, st));
-                CU_TRY(c, cudaMemsetAsync(s.ypacc + s0 * yp, 0, (size_t)n * yp * 8, st));
-                CU_TRY(c, cudaMemsetAsync(s.racc + s0 * max_yp * HF6D_POSE_BINS, 0, (size_t)n * max_yp * HF6D_POSE_BINS * 8, st));
-                CU_TRY(c, cudaMemsetAsync(s.win_cnt + s0 * c->hf.groups.size(), 0, (size_t)n * c->hf.groups.size() * 4, st));
+            // clear only the accumulator slots a class can use (slot = class * HF6D_MAX_CENTRES + centre rank): one launch
+            {
+                ClearPlan cp;
+                memset(&cp, 0, sizeof cp);
+                cp.base[0] = s.zacc;    cp.slot_bytes[0] = (unsigned long long)HF6D_Z_BINS * 8;
+                cp.base[1] = s.ypacc;   cp.slot_bytes[1] = (unsigned long long)yp * 8;
+                cp.base[2] = s.racc;    cp.slot_bytes[2] = (unsigned long long)max_yp * HF6D_POSE_BINS * 8;
+                cp.base[3] = s.win_cnt; cp.slot_bytes[3] = (unsigned long long)c->hf.groups.size() * 4;
+                bool any = false;
+                for (int k = 0; k < K; ++k) {
+                    cp.n_slots[k] = seeks_class(c, k) ? c->objects[k].max_location_hypotheses : 0;
+                    any |= cp.n_slots[k] > 0;
+                }
+                if (any) {
+                    clear_accumulators_kernel<<<dim3(c->sms, K, 4), 256, 0, st>>>(cp);
+                    LAUNCH_CHECK(c, s);
+                }
             }
             CU_TRY(c, cudaMemsetAsync(s.list_n, 0, ((size_t)std::max(K, S) + 2) * 4, st));
             const long long items = (long long)g.cap * f.T;
@@ -521,13 +527,14 @@ int run_stage(hf6d_ctx* c, Slot& s, int stage) {
                         zt.zoff[k + 1] = (int16_t)(zt.zoff[k] + (seeks_class(c, k) ? c->objects[k].max_location_hypotheses : 0));
                     const size_t zbytes = (size_t)zt.zoff[K] * HF6D_Z_BINS * 4;
                     static const bool smem_z_ok = !(getenv("HF6D_WA_SMEM_Z") && atoi(getenv("HF6D_WA_SMEM_Z")) == 0);  // tuning override
-                    if (smem_z_ok && zbytes <= (size_t)WA_MAX_DYN_SMEM)
-                        window_accumulate_kernel<true><<<c->sms * std::max<size_t>(1, std::min<size_t>(2, (200 * 1024) / (zbytes + 24 * 1024))),
-                                                         WA_THREADS, zbytes, st>>>(f, s.entries, c->entry_cap, ctr + 1, n_groups, zt,
-                                                                                    s.win_cnt, s.zacc);
-                    else
-                        window_accumulate_kernel<false><<<c->sms * 2, WA_THREADS, 0, st>>>(f, s.entries, c->entry_cap, ctr + 1, n_groups,
-                                                                                          zt, s.win_cnt, s.zacc);
+                    const bool zs = smem_z_ok && zbytes <= (size_t)WA_MAX_DYN_SMEM;
+                    const int wa_grid = c->sms * (zs ? (int)std::max<size_t>(1, std::min<size_t>(2, (200 * 1024) / (zbytes + 24 * 1024))) : 2);
+#define HF6D_WA(SZ, GG)                                                                                                     \
+    window_accumulate_kernel<SZ, GG><<<wa_grid, WA_THREADS, (SZ) ? zbytes : 0, st>>>(f, s.entries, c->entry_cap, ctr + 1, n_groups, \
+                                                                                   zt, s.win_cnt, s.zacc)
+                    if (zs) { if (c->lanes_per_hit == 16) HF6D_WA(true, 16); else HF6D_WA(true, 32); }
+                    else { if (c->lanes_per_hit == 16) HF6D_WA(false, 16); else HF6D_WA(false, 32); }
+#undef HF6D_WA
                 }
             }
             LAUNCH_CHECK(c, s);
@@ -546,12 +553,10 @@ int run_stage(hf6d_ctx* c, Slot& s, int stage) {
                               (size_t)BLUR_WARPS * (rin.nc + 1) * 8, st>>>(s.ypacc, s.yptmp, md, rin, rout, kb, rv.active);
             LAUNCH_CHECK(c, s);
             box_cols_kernel<<<dim3((rout.nc + 127) / 128, (rout.nr + BLUR_COL_CHUNK - 1) / BLUR_COL_CHUNK, S), 128, 0, st>>>(
-                s.yptmp, s.ypblur, md, rin, rout, kb, 1.0 / ((double)kb * kb), rv.active);
+                s.yptmp, s.ypblur, md, rin, rout, kb, 1.0 / ((double)kb * kb), rv.active, s.bmax);
             LAUNCH_CHECK(c, s);
             if (c->yp_nleft > 0 && c->yp_ntop > 0) {
                 const BlockGrid bg = make_block_grid(rout);
-                nms_blockmax_kernel<<<dim3((rout.nc + 31) / 32, (bg.by + 7) / 8, S), 256, 0, st>>>(s.ypblur, s.bmax, rout, rv.active);
-                LAUNCH_CHECK(c, s);
                 nms_select_kernel<<<dim3((bg.by * bg.bx + NMS_SELECT_THREADS - 1) / NMS_SELECT_THREADS, 1, S), NMS_SELECT_THREADS, 0, st>>>(
                     s.ypblur, s.bmax, rout, w, w, c->yp_left0, c->yp_nleft, c->yp_top0, c->yp_ntop, s.list, s.list_n, rv.active);
                 LAUNCH_CHECK(c, s);
@@ -817,7 +822,8 @@ int finish_create(hf6d_ctx* c, int device, int n_slots) {
         if (const char* e = getenv("HF6D_ENTRY_CAP")) cap_entries = std::max(0LL, atoll(e));  // tests force the overflow path
         c->entry_cap = (int)cap_entries;
     }
-    CU_TRY(c, cudaFuncSetAttribute(window_accumulate_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WA_MAX_DYN_SMEM));
+    CU_TRY(c, cudaFuncSetAttribute(window_accumulate_kernel<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, WA_MAX_DYN_SMEM));
+    CU_TRY(c, cudaFuncSetAttribute(window_accumulate_kernel<true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, WA_MAX_DYN_SMEM));
     c->slots.resize(c->n_slots);
     for (Slot& s : c->slots) {
         memset(s.ev, 0, sizeof s.ev);

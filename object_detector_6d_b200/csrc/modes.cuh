@@ -33,6 +33,32 @@ struct MapDims {
     int rows, cols;
 };
 
+// ------------------------------------------------------------------------------------------------ accumulator reset
+// One launch clears the pose accumulators of every class that is sought: segment g of class k starts at
+// base[g] + k * HF6D_MAX_CENTRES * slot_bytes[g] and spans n_slots[k] * slot_bytes[g] bytes (slot_bytes multiples of 4,
+// bases 256-byte aligned, so class starts are 16-byte aligned).  grid = (x, K, segments).
+struct ClearPlan {
+    void* base[4];
+    unsigned long long slot_bytes[4];
+    int n_slots[HF6D_MAX_CLASSES];
+};
+__global__ void __launch_bounds__(256)
+clear_accumulators_kernel(const __grid_constant__ ClearPlan plan) {
+    const int k = blockIdx.y, gseg = blockIdx.z;
+    const unsigned long long bytes = (unsigned long long)plan.n_slots[k] * plan.slot_bytes[gseg];
+    if (bytes == 0 || plan.base[gseg] == nullptr) return;
+    uint8_t* p = static_cast<uint8_t*>(plan.base[gseg]) + (unsigned long long)k * HF6D_MAX_CENTRES * plan.slot_bytes[gseg];
+    const unsigned long long n16 = bytes / 16;
+    uint4* p16 = reinterpret_cast<uint4*>(p);
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16;
+         i += (unsigned long long)gridDim.x * blockDim.x)
+        p16[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (blockIdx.x == 0) {
+        unsigned* tail = reinterpret_cast<unsigned*>(p + n16 * 16);
+        if (threadIdx.x < (bytes - n16 * 16) / 4) tail[threadIdx.x] = 0u;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ box blur
 constexpr int BLUR_WARPS = 4;
 
@@ -85,33 +111,67 @@ box_rows_kernel(const unsigned long long* __restrict__ acc, unsigned long long* 
 }
 
 // out[m][r][c] = (float)( (double)(sum_k tmp[m][reflect(r - ky/2 + k)][c]) / 65536 * scale )  for (r, c) in out
+// Also emits bmax[m][r/8][c/8], the key-maximum (value, ~row, ~col) of every aligned 8x8 block of the output -- the
+// first step of the NMS below -- while the values are still in registers.
 constexpr int BLUR_COL_CHUNK = 32;
+constexpr int NMS_BLOCK = 8;
+static_assert(BLUR_COL_CHUNK % NMS_BLOCK == 0, "a column chunk must hold whole NMS blocks");
+
+__device__ __forceinline__ unsigned long long nms_key(float v, int gy, int gx) {
+    return ((unsigned long long)__float_as_uint(v) << 32) | ((unsigned long long)(0xFFFFu - (unsigned)gy) << 16) |
+           (unsigned long long)(0xFFFFu - (unsigned)gx);
+}
+
 __global__ void __launch_bounds__(128)
 box_cols_kernel(const unsigned long long* __restrict__ tmp, float* __restrict__ dst_all, MapDims md, MapRect in,
-                MapRect out, int ky, double scale, const uint8_t* __restrict__ map_active) {
+                MapRect out, int ky, double scale, const uint8_t* __restrict__ map_active,
+                unsigned long long* __restrict__ bmax) {
     const int m = blockIdx.z;
     if (map_active && !map_active[m]) return;
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     const int rbeg = blockIdx.y * BLUR_COL_CHUNK;
-    if (c >= out.nc || rbeg >= out.nr) return;
-    const unsigned long long* src = tmp + (size_t)m * in.nr * out.nc + c;
-    float* dst = dst_all + (size_t)m * out.nr * out.nc + c;
+    if (rbeg >= out.nr) return;
+    const bool live = c < out.nc;
+    const int cc = live ? c : 0;
+    const unsigned long long* src = tmp + (size_t)m * in.nr * out.nc + cc;
+    float* dst = dst_all + (size_t)m * out.nr * out.nc + cc;
     const int n = md.rows;
     auto at = [&](int gr) -> unsigned long long {  // global row, reflected; rows outside the input rectangle are zero
         const int rr = reflect101(gr, n) - in.r0;
         return (rr >= 0 && rr < in.nr) ? src[(size_t)rr * out.nc] : 0ull;
     };
     const int rend = min(rbeg + BLUR_COL_CHUNK, out.nr);
+    const int bx = (out.nc + NMS_BLOCK - 1) / NMS_BLOCK, by = (out.nr + NMS_BLOCK - 1) / NMS_BLOCK;
     unsigned long long s = 0;
     {
         const int a = out.r0 + rbeg - ky / 2;
         for (int k = 0; k < ky; ++k) s += at(a + k);
     }
-    for (int r = rbeg; r < rend; ++r) {
-        dst[(size_t)r * out.nc] = (float)(((double)s / 65536.0) * scale);
-        const int a = out.r0 + r - ky / 2;
-        s += at(a + ky);
-        s -= at(a);
+    for (int r0 = rbeg; r0 < rend; r0 += NMS_BLOCK) {  // one block row at a time: its 16 loads are issued together
+        unsigned long long add[NMS_BLOCK], sub[NMS_BLOCK];
+#pragma unroll
+        for (int i = 0; i < NMS_BLOCK; ++i) {
+            const int a = out.r0 + r0 + i - ky / 2;
+            add[i] = at(a + ky);
+            sub[i] = at(a);
+        }
+        float best_v = 0.f;  // maximum of this column inside the block row (values are >= 0), topmost on ties
+        int best_r = r0;
+#pragma unroll
+        for (int i = 0; i < NMS_BLOCK; ++i) {
+            const int r = r0 + i;
+            if (r < rend) {
+                const float v = (float)(((double)s / 65536.0) * scale);
+                if (live) dst[(size_t)r * out.nc] = v;
+                if (v > best_v) { best_v = v; best_r = r; }
+                s += add[i];
+                s -= sub[i];
+            }
+        }
+        unsigned long long b = live ? nms_key(best_v, out.r0 + best_r, out.c0 + c) : 0ull;
+#pragma unroll
+        for (int o = 1; o < NMS_BLOCK; o <<= 1) b = max(b, __shfl_xor_sync(0xffffffffu, b, o));
+        if (bmax && live && (threadIdx.x & (NMS_BLOCK - 1)) == 0) bmax[((size_t)m * by + r0 / NMS_BLOCK) * bx + c / NMS_BLOCK] = b;
     }
 }
 
@@ -121,7 +181,7 @@ box_cols_kernel(const unsigned long long* __restrict__ tmp, float* __restrict__ 
 // Equivalently: candidate (ccx, ccy) = (left + wx/2, top + wy/2) is emitted iff its value v != 0 and NO element of the
 // window  [left, left+wx) x [top, top+wy)  "beats" it under the total order  key = (value, ~row, ~col).
 // Tiled neighbour reduction in two kernels:
-//   1. nms_blockmax_kernel: the key-maximum of every aligned 8x8 block of the map (one coalesced pass over the data);
+//   1. the key-maximum of every aligned 8x8 block of the map (written by box_cols_kernel as it produces the map);
 //   2. nms_select_kernel  : one lane per block.  A window wider than 15 contains its centre's own block, so only the
 //      block maximum can be a window maximum (1 candidate in 64 survives); it is then compared with the maxima of the
 //      blocks that overlap its window: a larger maximum that itself lies in the window beats it, a block whose
@@ -132,45 +192,12 @@ box_cols_kernel(const unsigned long long* __restrict__ tmp, float* __restrict__ 
 // The reference's loop bounds (lefts 0..cols-wx, tops 0..rows-2*wy+1; the bottom wy-1 window rows are never produced)
 // are applied by the caller through the origin ranges.
 constexpr int NMS_LIST_CAP = 4096;
-constexpr int NMS_BLOCK = 8;
-
-__device__ __forceinline__ unsigned long long nms_key(float v, int gy, int gx) {
-    return ((unsigned long long)__float_as_uint(v) << 32) | ((unsigned long long)(0xFFFFu - (unsigned)gy) << 16) |
-           (unsigned long long)(0xFFFFu - (unsigned)gx);
-}
 
 struct BlockGrid {
     int by, bx;  // blocks per map: ceil(nr / 8), ceil(nc / 8); block (i, j) covers rectangle rows [8i, 8i+8), cols [8j, 8j+8)
 };
 __host__ __device__ __forceinline__ BlockGrid make_block_grid(MapRect R) {
     return BlockGrid{(R.nr + NMS_BLOCK - 1) / NMS_BLOCK, (R.nc + NMS_BLOCK - 1) / NMS_BLOCK};
-}
-
-// in: float [M][R.nr][R.nc]; bmax: u64 [M][by][bx] key-maximum of each block (values >= 0, so float bits order like
-// unsigned integers).  One warp covers 8 rows x 32 columns = 4 blocks.
-__global__ void __launch_bounds__(256)
-nms_blockmax_kernel(const float* __restrict__ in, unsigned long long* __restrict__ bmax, MapRect R,
-                    const uint8_t* __restrict__ map_active) {
-    const int m = blockIdx.z;
-    if (map_active && !map_active[m]) return;
-    const BlockGrid bg = make_block_grid(R);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int bi = blockIdx.y * 8 + warp;            // block row
-    if (bi >= bg.by) return;
-    const int col = blockIdx.x * 32 + lane;          // rectangle-local column
-    const float* src = in + (size_t)m * R.nr * R.nc;
-    unsigned long long best = 0;
-    if (col < R.nc) {
-#pragma unroll
-        for (int r = 0; r < NMS_BLOCK; ++r) {
-            const int row = bi * NMS_BLOCK + r;
-            if (row < R.nr) best = max(best, nms_key(__ldg(src + (size_t)row * R.nc + col), R.r0 + row, R.c0 + col));
-        }
-    }
-#pragma unroll
-    for (int o = 1; o < NMS_BLOCK; o <<= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
-    const int bj = col / NMS_BLOCK;
-    if ((lane & (NMS_BLOCK - 1)) == 0 && bj < bg.bx) bmax[((size_t)m * bg.by + bi) * bg.bx + bj] = best;
 }
 
 // Window origins (left, top) in global coordinates: left in [left0, left0+n_left), top in [top0, top0+n_top).
@@ -481,14 +508,25 @@ roll_modes_kernel(const unsigned long long* __restrict__ racc, const int* __rest
         }
     }
     __syncthreads();
+    // sort by key, descending: keys are distinct (they carry the bin), so a key's rank is the number of larger keys
+    {
+        const int n = s_n;
+        unsigned long long mine[(HF6D_POSE_BINS + 127) / 128];
+        int rank[(HF6D_POSE_BINS + 127) / 128];
+        int cnt = 0;
+        for (int i = threadIdx.x; i < n; i += blockDim.x, ++cnt) {
+            const unsigned long long k = s_keys[i];
+            int r = 0;
+            for (int j = 0; j < n; ++j) r += s_keys[j] > k;
+            mine[cnt] = k;
+            rank[cnt] = r;
+        }
+        __syncthreads();
+        for (int q = 0; q < cnt; ++q) s_keys[rank[q]] = mine[q];
+    }
+    __syncthreads();
     if (threadIdx.x == 0) {
         const int n = s_n;
-        // selection sort by key desc (n <= ~40)
-        for (int a = 0; a < n; ++a) {
-            int b = a;
-            for (int i = a + 1; i < n; ++i) if (s_keys[i] > s_keys[b]) b = i;
-            const unsigned long long t = s_keys[a]; s_keys[a] = s_keys[b]; s_keys[b] = t;
-        }
         int got = 0, prev = -1;
         const float top = n ? __uint_as_float((unsigned)(s_keys[0] >> 32)) : 0.f;
         for (int i = 0; i < n && got < max_roll; ++i) {

@@ -305,23 +305,24 @@ window_entries_kernel(DevForest f, FrameGeom g, const __grid_constant__ ObjectSw
 
 // Per-warp staging of 32 listed entries (see window_accumulate_kernel).
 struct WarpEntries {
-    int incl[32];        // inclusive prefix of the entries' leaf-vote counts
-    float zz[32];        // depth of the window pixel [m]
-    int vb[32];          // first vote of the entry's group minus the exclusive prefix
+    float zz[32];        // depth of the window pixel [m]; < 0: no z contribution
+    int vb[32];          // first vote of the entry's group
+    int vn[32];          // votes of the group
     unsigned w[32];      // Q16 weight
     unsigned cm[32];     // class << 16 | mask of the centres whose window holds the entry
 };
 
-// Pass A.1b: a warp takes 32 listed entries at a time (one per lane: group lookup and the cnt increments), then walks
-// the flattened (entry, leaf vote) pairs 32 per step -- coalesced, independent oz loads instead of one dependent load
-// chain per entry.  SMEM_Z: every CTA keeps the z histograms of all centres that can be active in shared memory
-// (uint32; a wrap of the 32-bit counter carries 2^32 into the global 64-bit accumulator, so the sums stay exact) and
-// flushes them once.  zoff[c] = first shared histogram of class c (centre rank k uses zoff[c] + k).
+// Pass A.1b: a warp takes 32 listed entries at a time (one per lane: group lookup and the cnt increments), then G
+// lanes walk one entry's leaf votes together (G = 16 when no vote group holds more than 16 votes: two entries per
+// step, coalesced independent oz loads instead of one dependent load chain per entry).  SMEM_Z: every CTA keeps the z
+// histograms of all centres that can be active in shared memory (uint32; a wrap of the 32-bit counter carries 2^32
+// into the global 64-bit accumulator, so the sums stay exact) and flushes them once.  zoff[c] = first shared histogram
+// of class c (centre rank k uses zoff[c] + k).
 struct ZSlotTable {
     int16_t zoff[HF6D_MAX_CLASSES + 1];
 };
 constexpr int WA_THREADS = 1024;  // one CTA per SM when the histograms live in shared memory: 32 warps share them
-template <bool SMEM_Z>
+template <bool SMEM_Z, int G>
 __global__ void __launch_bounds__(WA_THREADS)
 window_accumulate_kernel(DevForest f, const uint4* __restrict__ entries, int entry_cap, const int* __restrict__ n_reserved,
                          int n_groups, const __grid_constant__ ZSlotTable zt, unsigned* __restrict__ cnt,
@@ -334,56 +335,45 @@ window_accumulate_kernel(DevForest f, const uint4* __restrict__ entries, int ent
         __syncthreads();
     }
     const int n = min(*n_reserved, entry_cap / ENTRY_BLOCK * ENTRY_BLOCK);
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, sub = lane % G, part = lane / G;
+    constexpr int PARTS = 32 / G;
     WarpEntries& we = s_we[threadIdx.x >> 5];
     const int warp_id = (blockIdx.x * WA_THREADS + threadIdx.x) >> 5, n_warps = (gridDim.x * WA_THREADS) >> 5;
     for (int base = warp_id * 32; base < n; base += n_warps * 32) {
         const uint4 e = entries[base + lane];  // n is a multiple of ENTRY_BLOCK, so base + lane < n
-        int vcnt = 0;
+        float zz = -1.f;
+        int4 grp = make_int4(0, 0, 0, 0);
         if (e.x != ENTRY_INVALID) {
             const int c = (int)(e.y >> 16);
             const int gi = __ldg(f.vgroup + (int)e.x);
-            const int4 grp = __ldg(reinterpret_cast<const int4*>(f.groups) + gi);  // cls, w, vbeg, vcnt
+            grp = __ldg(reinterpret_cast<const int4*>(f.groups) + gi);  // cls, w, vbeg, vcnt
             for (unsigned m = e.y & 0xFFFFu; m; m &= m - 1)
                 atomicAdd(cnt + (size_t)(c * HF6D_MAX_CENTRES + __ffs(m) - 1) * n_groups + gi, 1u);
-            const float zz = __uint_as_float(e.z);
-            if (zz >= 0.f) {
-                vcnt = grp.w;
-                we.zz[lane] = zz;
-                we.w[lane] = (unsigned)grp.y;
-                we.cm[lane] = e.y;
-                we.vb[lane] = grp.z;  // corrected below once the prefix is known
-            }
+            zz = __uint_as_float(e.z);
         }
-        int incl = vcnt;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
-        }
-        const int total = __shfl_sync(0xffffffffu, incl, 31);
-        we.incl[lane] = incl;
-        if (vcnt) we.vb[lane] -= incl - vcnt;
+        we.zz[lane] = zz;
+        we.vb[lane] = grp.z;
+        we.vn[lane] = grp.w;
+        we.w[lane] = (unsigned)grp.y;
+        we.cm[lane] = e.y;
         __syncwarp();
-        for (int p0 = 0; p0 < total; p0 += 32) {
-            const int pidx = p0 + lane;
-            if (pidx < total) {
-                int h = 0;  // smallest h with incl[h] > pidx
-#pragma unroll
-                for (int st = 16; st; st >>= 1)
-                    if (we.incl[h + st - 1] <= pidx) h += st;
-                const int zb = f2i_x86(div_const<1, 100>(__fadd_rn(__ldg(f.oz + we.vb[h] + pidx), we.zz[h])));  // integer part only
-                if (zb >= 0 && zb < HF6D_Z_BINS) {
-                    const unsigned cm = we.cm[h], w = we.w[h];
-                    const int c = (int)(cm >> 16);
-                    for (unsigned m = cm & 0xFFFFu; m; m &= m - 1) {
-                        const int k = __ffs(m) - 1;
-                        if (SMEM_Z) {
-                            const unsigned old = atomicAdd(s_z + (zt.zoff[c] + k) * HF6D_Z_BINS + zb, w);
-                            if (old + w < old) atomicAdd(zacc + (size_t)(c * HF6D_MAX_CENTRES + k) * HF6D_Z_BINS + zb, 1ull << 32);
-                        } else {
-                            atomicAdd(zacc + (size_t)(c * HF6D_MAX_CENTRES + k) * HF6D_Z_BINS + zb, (unsigned long long)w);
-                        }
+#pragma unroll 2
+        for (int j = part; j < 32; j += PARTS) {
+            const float zj = we.zz[j];
+            if (zj < 0.f) continue;  // uniform within the G lanes of this entry
+            const int vb = we.vb[j], vn = we.vn[j];
+            const unsigned cm = we.cm[j], w = we.w[j];
+            const int c = (int)(cm >> 16);
+            for (int q = sub; q < vn; q += G) {
+                const int zb = f2i_x86(div_const<1, 100>(__fadd_rn(__ldg(f.oz + vb + q), zj)));  // integer part only
+                if (zb < 0 || zb >= HF6D_Z_BINS) continue;
+                for (unsigned m = cm & 0xFFFFu; m; m &= m - 1) {
+                    const int k = __ffs(m) - 1;
+                    if (SMEM_Z) {
+                        const unsigned old = atomicAdd(s_z + (zt.zoff[c] + k) * HF6D_Z_BINS + zb, w);
+                        if (old + w < old) atomicAdd(zacc + (size_t)(c * HF6D_MAX_CENTRES + k) * HF6D_Z_BINS + zb, 1ull << 32);
+                    } else {
+                        atomicAdd(zacc + (size_t)(c * HF6D_MAX_CENTRES + k) * HF6D_Z_BINS + zb, (unsigned long long)w);
                     }
                 }
             }
