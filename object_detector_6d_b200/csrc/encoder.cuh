@@ -15,6 +15,7 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
+#include <algorithm>
 #include <cstdint>
 
 #include "ptx_sm100.cuh"
@@ -27,16 +28,16 @@ constexpr int ENC_THREADS = 384;
 constexpr int ENC_EPI_WARPS = 8;
 constexpr int ENC_TMEM_COLS = 512;
 constexpr int ENC_MAX_N = 1536;
-constexpr int ENC_EPI_BUF_BYTES = 32 * 64;  // one staged output chunk of a warp: 32 rows x 64 bytes
-
-// STAGES: depth of the TMA->MMA operand ring.  EPI_BUFS: staged output chunks per epilogue warp (ring).
-template <int BLOCK_N, int STAGES, int EPI_BUFS>
+// STAGES: depth of the TMA->MMA operand ring.  EPI_BUFS: staged output chunks per epilogue warp (ring), each 32 rows x
+// CHUNK_BYTES (64 or 128: the inner extent of the TMA store box; 128-byte rows halve the number of stores).
+template <int BLOCK_N, int STAGES, int EPI_BUFS, int CHUNK_BYTES>
 struct EncSmem {
+    static constexpr int EPI_BUF_BYTES = 32 * CHUNK_BYTES;
     static constexpr int A_BYTES = ENC_BLOCK_M * ENC_BLOCK_K * 2;
     static constexpr int B_BYTES = BLOCK_N * ENC_BLOCK_K * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int EPI_OFF = STAGES * STAGE_BYTES;
-    static constexpr int BIAS_OFF = EPI_OFF + ENC_EPI_WARPS * EPI_BUFS * ENC_EPI_BUF_BYTES;
+    static constexpr int BIAS_OFF = EPI_OFF + ENC_EPI_WARPS * EPI_BUFS * EPI_BUF_BYTES;
     static constexpr int BAR_OFF = BIAS_OFF + ENC_MAX_N * 4;
     static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 4) * 8 + 16;
     static constexpr int DYN_BYTES = TOTAL + 1024;  // slack for manual 1024-B alignment
@@ -65,12 +66,17 @@ __device__ __forceinline__ float sigmoid_accurate(float x) {
 //              zero weight columns in the next layer); `bias` holds 0.5*b (the tanh form wants x/2)
 // LAST=true  : out is fp32 [m_cap][n_valid]; columns >= n_valid are clipped by the TMA store
 // tmC is the output tensor map: boxes of 32 rows x 64 bytes, 64-byte swizzle.
-template <int BLOCK_N, bool LAST, int STAGES, int EPI_BUFS>
+// CLUSTER = 2: CTA pairs (thread-block cluster of 2) work on two m-blocks of the SAME n-block; each CTA loads its own A
+//              tile and HALF of the weight tile, multicast into both CTAs' shared memory, so a CTA pulls A + B/2 per
+//              k-block from L2 instead of A + B (layers 1 and 3 are bound by exactly that traffic).  A stage may be
+//              refilled only when BOTH CTAs' MMAs have read it: the MMA commit arrives on the `empty` barrier of both
+//              CTAs (count 2).  tmB then has a box of BLOCK_N/2 rows.
+template <int BLOCK_N, bool LAST, int STAGES, int EPI_BUFS, int CLUSTER, int CHUNK_BYTES>
 __global__ void __launch_bounds__(ENC_THREADS, 1)
 encoder_layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmC, const float* __restrict__ bias,
                      const int* __restrict__ m_ptr, int K, int n_pad) {
-    using S = EncSmem<BLOCK_N, STAGES, EPI_BUFS>;
+    using S = EncSmem<BLOCK_N, STAGES, EPI_BUFS, CHUNK_BYTES>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
@@ -89,7 +95,12 @@ encoder_layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     const int m_blocks = (M + ENC_BLOCK_M - 1) / ENC_BLOCK_M;
     const int n_blocks = n_pad / BLOCK_N;
     const int k_blocks = K / ENC_BLOCK_K;
-    const int tiles = m_blocks * n_blocks;
+    // tile schedule: work item w -> (m-block pair or m-block, n-block); in cluster mode both CTAs of a pair walk the same
+    // items and take the m-blocks 2*mp and 2*mp + 1 (a missing last m-block is computed on zeros and clipped by TMA)
+    const int cta_rank = CLUSTER > 1 ? (int)ptx::cluster_ctarank() : 0;
+    const int m_groups = (m_blocks + CLUSTER - 1) / CLUSTER;
+    const int tiles = m_groups * n_blocks;
+    const int first = blockIdx.x / CLUSTER, step = gridDim.x / CLUSTER;
 
     for (int i = threadIdx.x; i < n_pad; i += ENC_THREADS) s_bias[i] = bias[i];
 
@@ -101,7 +112,7 @@ encoder_layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
             ptx::mbar_init(&full[s], 1);
-            ptx::mbar_init(&empty[s], 1);
+            ptx::mbar_init(&empty[s], CLUSTER);
         }
         for (int a = 0; a < 2; ++a) {
             ptx::mbar_init(&tfull[a], 1);
@@ -115,6 +126,7 @@ encoder_layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     }
     ptx::tc_fence_before();
     __syncthreads();
+    if (CLUSTER > 1) ptx::cluster_sync();  // the peer's barriers are initialised before anything is multicast to them
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -123,15 +135,19 @@ encoder_layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
-                const int mb = t / n_blocks, nb = t % n_blocks;
+            for (int t = first; t < tiles; t += step) {
+                const int mb = (t / n_blocks) * CLUSTER + cta_rank, nb = t % n_blocks;
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     ptx::mbar_wait(&empty[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * S::STAGE_BYTES;
                     uint8_t* sb = sa + S::A_BYTES;
                     ptx::mbar_arrive_expect_tx(&full[stage], S::STAGE_BYTES);
                     ptx::tma_load_2d(sa, &tmA, &full[stage], kb * ENC_BLOCK_K, mb * ENC_BLOCK_M);
-                    ptx::tma_load_2d(sb, &tmB, &full[stage], kb * ENC_BLOCK_K, nb * BLOCK_N);
+                    if constexpr (CLUSTER > 1)
+                        ptx::tma_load_2d_multicast(sb + cta_rank * (S::B_BYTES / 2), &tmB, &full[stage], kb * ENC_BLOCK_K,
+                                                   nb * BLOCK_N + cta_rank * (BLOCK_N / 2), (uint16_t)0x3);
+                    else
+                        ptx::tma_load_2d(sb, &tmB, &full[stage], kb * ENC_BLOCK_K, nb * BLOCK_N);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -145,7 +161,7 @@ encoder_layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+            for (int t = first; t < tiles; t += step) {
                 ptx::mbar_wait(&tempty[acc], acc_phase ^ 1);
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * 256;
@@ -160,7 +176,8 @@ encoder_layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                         // +32 B per K=16 step inside the 128-B swizzle row: +2 in the (addr>>4) field
                         ptx::umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
                     }
-                    ptx::umma_commit(&empty[stage]);
+                    if constexpr (CLUSTER > 1) ptx::umma_commit_multicast(&empty[stage], (uint16_t)0x3);
+                    else ptx::umma_commit(&empty[stage]);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
                 ptx::umma_commit(&tfull[acc]);
@@ -174,54 +191,65 @@ encoder_layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         // 16-byte vector stores of a warp spread over all banks) -> TMA store: full-sector, fully coalesced writes
         // issued by the copy engine, off the LSU.
         const int q = warp & 3;               // TMEM lane quadrant this warp may touch
-        const int half = (warp - 4) >> 2;     // which half of the tile's columns
-        constexpr int HALF_N = BLOCK_N / 2;
-        constexpr int CHUNK_COLS = LAST ? 16 : 32;  // 64 bytes of output per row
-        constexpr int CHUNKS = HALF_N / CHUNK_COLS;
-        static_assert(HALF_N % CHUNK_COLS == 0, "column half must be a whole number of 64-byte chunks");
-        const uint32_t stage_base = ptx::smem_u32(smem + S::EPI_OFF + (warp - 4) * EPI_BUFS * ENC_EPI_BUF_BYTES);
-        const uint32_t row_off = (uint32_t)lane * 64u;
-        const uint32_t sw = ((uint32_t)lane >> 1) & 3u;  // 64-byte swizzle: 16-byte unit index ^= bits [7,9) of the address
+        const int half = (warp - 4) >> 2;     // the two warps of a quadrant take alternate column chunks
+        constexpr int CHUNK_COLS = CHUNK_BYTES / (LAST ? 4 : 2);  // output columns per staged chunk
+        constexpr int TILE_CHUNKS = BLOCK_N / CHUNK_COLS;
+        constexpr int UNITS = CHUNK_BYTES / 16;                   // 16-byte units per staged row
+        static_assert(BLOCK_N % CHUNK_COLS == 0, "the tile must be a whole number of chunks");
+        static_assert(CHUNK_COLS == 16 || CHUNK_COLS == 32 || CHUNK_COLS == 64, "TMEM loads come in x16 / x32");
+        const uint32_t stage_base = ptx::smem_u32(smem + S::EPI_OFF + (warp - 4) * EPI_BUFS * S::EPI_BUF_BYTES);
+        const uint32_t row_off = (uint32_t)lane * CHUNK_BYTES;
+        // TMA swizzle: the 16-byte unit index is XORed with address bits [7, 7 + log2(UNITS))
+        const uint32_t sw = UNITS == 8 ? ((uint32_t)lane & 7u) : (((uint32_t)lane >> 1) & 3u);
         int it = 0;                                      // chunks staged by this warp so far
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
-            const int mb = t / n_blocks, nb = t % n_blocks;
+        for (int t = first; t < tiles; t += step) {
+            const int mb = (t / n_blocks) * CLUSTER + cta_rank, nb = t % n_blocks;
             const int row0 = mb * ENC_BLOCK_M + q * 32;
             ptx::mbar_wait(&tfull[acc], acc_phase);
             ptx::tc_fence_after();
-            const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256 + half * HALF_N;
+            const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256;
 #pragma unroll 1
-            for (int c = 0; c < CHUNKS; ++c, ++it) {
-                const int col = nb * BLOCK_N + half * HALF_N + c * CHUNK_COLS;
-                uint32_t o[16];
+            for (int c = half; c < TILE_CHUNKS; c += 2, ++it) {
+                const int tcol = c * CHUNK_COLS;             // column inside the tile
+                const int col = nb * BLOCK_N + tcol;
+                uint32_t o[UNITS * 4];
                 if constexpr (!LAST) {
-                    uint32_t v[32];
-                    ptx::tmem_ld_32x32b_x32(taddr0 + c * CHUNK_COLS, v);
-                    ptx::tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        o[j] = sigmoid_pair_bf16(fmaf(__uint_as_float(v[2 * j]), 0.5f, s_bias[col + 2 * j]),
-                                                 fmaf(__uint_as_float(v[2 * j + 1]), 0.5f, s_bias[col + 2 * j + 1]));
+                    for (int h = 0; h < CHUNK_COLS / 32; ++h) {
+                        uint32_t v[32];
+                        ptx::tmem_ld_32x32b_x32(taddr0 + tcol + h * 32, v);
+                        ptx::tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            o[h * 16 + j] = sigmoid_pair_bf16(fmaf(__uint_as_float(v[2 * j]), 0.5f, s_bias[col + h * 32 + 2 * j]),
+                                                              fmaf(__uint_as_float(v[2 * j + 1]), 0.5f, s_bias[col + h * 32 + 2 * j + 1]));
+                    }
                 } else {
-                    uint32_t v[16];
-                    ptx::tmem_ld_32x32b_x16(taddr0 + c * CHUNK_COLS, v);
-                    ptx::tmem_ld_wait();
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) o[j] = __float_as_uint(sigmoid_accurate(__uint_as_float(v[j]) + s_bias[col + j]));
+                    for (int h = 0; h < CHUNK_COLS / 16; ++h) {
+                        uint32_t v[16];
+                        ptx::tmem_ld_32x32b_x16(taddr0 + tcol + h * 16, v);
+                        ptx::tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            o[h * 16 + j] = __float_as_uint(sigmoid_accurate(__uint_as_float(v[j]) + s_bias[col + h * 16 + j]));
+                    }
                 }
-                if (c == CHUNKS - 1) {  // the accumulator is drained: hand it back before the stores
+                const bool last_chunk = c + 2 >= TILE_CHUNKS;
+                if (last_chunk) {  // this warp has drained its part of the accumulator: hand it back before the stores
                     ptx::tc_fence_before();
                     __syncwarp();
                     if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
                 }
-                const uint32_t buf = stage_base + (uint32_t)(it % EPI_BUFS) * ENC_EPI_BUF_BYTES;
+                const uint32_t buf = stage_base + (uint32_t)(it % EPI_BUFS) * S::EPI_BUF_BYTES;
                 if (it >= EPI_BUFS) {  // the TMA store that last used this buffer must have read it
                     if (lane == 0) ptx::tma_store_wait_read<EPI_BUFS - 1>();
                     __syncwarp();
                 }
 #pragma unroll
-                for (int u = 0; u < 4; ++u)
+                for (int u = 0; u < UNITS; ++u)
                     ptx::st_shared_v4(buf + row_off + (((uint32_t)u ^ sw) << 4), o[4 * u], o[4 * u + 1], o[4 * u + 2], o[4 * u + 3]);
                 ptx::fence_proxy_async();
                 __syncwarp();
@@ -229,6 +257,11 @@ encoder_layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                     ptx::tma_store_2d(&tmC, reinterpret_cast<const void*>(smem + (buf - ptx::smem_u32(smem))), col, row0);
                     ptx::tma_store_commit();
                 }
+            }
+            if (half >= TILE_CHUNKS) {  // a half without any chunk still has to release the accumulator
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
@@ -238,6 +271,7 @@ encoder_layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 
     ptx::tc_fence_before();
     __syncthreads();
+    if (CLUSTER > 1) ptx::cluster_sync();  // no CTA leaves while its peer may still multicast into it or arrive on its barriers
     if (warp == 2) {
         ptx::tc_fence_after();
         ptx::tmem_dealloc(tmem_base, ENC_TMEM_COLS);
@@ -277,46 +311,86 @@ inline bool make_bf16_kmajor_map(CUtensorMap* map, const void* base, uint64_t ro
     return r == CUDA_SUCCESS;
 }
 
-// Output map: row-major [rows][cols] of elem_bytes-wide elements, boxes of 32 rows x 64 bytes, 64-byte swizzle.
-inline bool make_out_map(CUtensorMap* map, void* base, uint64_t rows, uint64_t cols, int elem_bytes) {
+// Output map: row-major [rows][cols] of elem_bytes-wide elements, boxes of 32 rows x chunk_bytes (64 or 128), swizzle =
+// chunk_bytes.
+inline bool make_out_map(CUtensorMap* map, void* base, uint64_t rows, uint64_t cols, int elem_bytes, int chunk_bytes) {
     PFN_tensorMapEncodeTiled enc = get_tensor_map_encoder();
     if (!enc) return false;
     cuuint64_t gdim[2] = {cols, rows};
     cuuint64_t gstride[1] = {cols * (uint64_t)elem_bytes};
-    cuuint32_t box[2] = {(cuuint32_t)(64 / elem_bytes), 32};
+    cuuint32_t box[2] = {(cuuint32_t)(chunk_bytes / elem_bytes), 32};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(map, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, gdim,
-                     gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                     gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, chunk_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                      CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
 }
 
 struct EncoderLayerLaunch {
-    CUtensorMap tmA, tmB, tmC;
+    CUtensorMap tmA, tmB, tmB_half, tmC;  // tmB_half: box of block_n / 2 rows (cluster mode)
     const float* bias;  // hidden layers: 0.5 * b
     int K, n_pad, block_n;
     bool last, short_k;  // short_k: few K blocks per tile -> 3 operand stages, deeper output staging
+    int cluster;         // 1, or 2 = CTA pairs with the weight tile multicast
 };
 
-template <int BLOCK_N, bool LAST, int STAGES, int EPI_BUFS>
-inline cudaError_t launch_encoder_layer_t(const EncoderLayerLaunch& L, const int* m_ptr, int grid, cudaStream_t st) {
-    auto kern = encoder_layer_kernel<BLOCK_N, LAST, STAGES, EPI_BUFS>;
-    using S = EncSmem<BLOCK_N, STAGES, EPI_BUFS>;
-    static bool attr_set = false;
-    if (!attr_set) {
+template <int BLOCK_N, bool LAST, int STAGES, int EPI_BUFS, int CLUSTER, int CHUNK_BYTES>
+inline cudaError_t launch_encoder_layer_t(const EncoderLayerLaunch& L, const int* m_ptr, int sms, cudaStream_t st) {
+    auto kern = encoder_layer_kernel<BLOCK_N, LAST, STAGES, EPI_BUFS, CLUSTER, CHUNK_BYTES>;
+    using S = EncSmem<BLOCK_N, STAGES, EPI_BUFS, CHUNK_BYTES>;
+    static int grid = 0;
+    if (!grid) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::DYN_BYTES);
         if (e != cudaSuccess) return e;
-        attr_set = true;
+        grid = sms;
+        if (CLUSTER > 1) {  // as many co-resident pairs as the GPCs can hold
+            cudaLaunchConfig_t q{};
+            q.gridDim = dim3(sms / CLUSTER * CLUSTER);
+            q.blockDim = dim3(ENC_THREADS);
+            q.dynamicSmemBytes = S::DYN_BYTES;
+            cudaLaunchAttribute a[1];
+            a[0].id = cudaLaunchAttributeClusterDimension;
+            a[0].val.clusterDim.x = CLUSTER; a[0].val.clusterDim.y = 1; a[0].val.clusterDim.z = 1;
+            q.attrs = a; q.numAttrs = 1;
+            int n_clusters = 0;
+            e = cudaOccupancyMaxActiveClusters(&n_clusters, kern, &q);
+            if (e != cudaSuccess) return e;
+            if (n_clusters < 1) return cudaErrorInvalidConfiguration;
+            grid = std::min(n_clusters, sms / CLUSTER) * CLUSTER;
+        }
     }
-    kern<<<grid, ENC_THREADS, S::DYN_BYTES, st>>>(L.tmA, L.tmB, L.tmC, L.bias, m_ptr, L.K, L.n_pad);
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(ENC_THREADS);
+    cfg.dynamicSmemBytes = S::DYN_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attrs[1];
+    attrs[0].id = cudaLaunchAttributeClusterDimension;
+    attrs[0].val.clusterDim.x = CLUSTER; attrs[0].val.clusterDim.y = 1; attrs[0].val.clusterDim.z = 1;
+    cfg.attrs = attrs;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, L.tmA, CLUSTER > 1 ? L.tmB_half : L.tmB, L.tmC, L.bias, m_ptr, L.K, L.n_pad);
 }
 
-inline cudaError_t launch_encoder_layer(const EncoderLayerLaunch& L, const int* m_ptr, int grid, cudaStream_t st) {
-    if (L.block_n == 256 && !L.last && L.short_k) return launch_encoder_layer_t<256, false, 3, 4>(L, m_ptr, grid, st);
-    if (L.block_n == 256 && !L.last) return launch_encoder_layer_t<256, false, 4, 1>(L, m_ptr, grid, st);
-    if (L.block_n == 160 && L.last) return launch_encoder_layer_t<160, true, 4, 4>(L, m_ptr, grid, st);
-    if (L.block_n == 256 && L.last) return launch_encoder_layer_t<256, true, 4, 1>(L, m_ptr, grid, st);
+// Output chunk width per configuration (the slot's tensor maps are built with the same rule).
+inline int encoder_chunk_bytes(int block_n, bool last, bool short_k) {
+    if (block_n == 256 && !last && !short_k) return 64;  // 4 operand stages leave 16 KB for staging: 64-byte chunks
+    if (block_n == 256 && last) return 64;
+    return 128;
+}
+
+inline cudaError_t launch_encoder_layer(const EncoderLayerLaunch& L, const int* m_ptr, int sms, cudaStream_t st) {
+    if (L.cluster == 2) {
+        if (L.block_n == 256 && !L.last && L.short_k) return launch_encoder_layer_t<256, false, 3, 2, 2, 128>(L, m_ptr, sms, st);
+        if (L.block_n == 256 && !L.last) return launch_encoder_layer_t<256, false, 4, 1, 2, 64>(L, m_ptr, sms, st);
+        if (L.block_n == 160 && L.last) return launch_encoder_layer_t<160, true, 4, 2, 2, 128>(L, m_ptr, sms, st);
+        if (L.block_n == 256 && L.last) return launch_encoder_layer_t<256, true, 4, 1, 2, 64>(L, m_ptr, sms, st);
+        return cudaErrorInvalidValue;
+    }
+    if (L.block_n == 256 && !L.last && L.short_k) return launch_encoder_layer_t<256, false, 3, 2, 1, 128>(L, m_ptr, sms, st);
+    if (L.block_n == 256 && !L.last) return launch_encoder_layer_t<256, false, 4, 1, 1, 64>(L, m_ptr, sms, st);
+    if (L.block_n == 160 && L.last) return launch_encoder_layer_t<160, true, 4, 2, 1, 128>(L, m_ptr, sms, st);
+    if (L.block_n == 256 && L.last) return launch_encoder_layer_t<256, true, 4, 1, 1, 64>(L, m_ptr, sms, st);
     return cudaErrorInvalidValue;
 }
 

@@ -33,7 +33,7 @@ def main():
     ts = sum(x[1] for x in lines) or 1
     print(f"# {rep}: {ti} warp instructions, {ts} stall samples")
     print("# by instructions executed")
-    for n, s, f, ln, src, st in sorted(lines, reverse=True)[:top]:
+    for n, s, f, ln, src, st in sorted(lines, key=lambda x: -x[0])[:top]:
         print(f"{100 * n / ti:5.1f}% inst {100 * s / ts:5.1f}% smpl  {f}:{ln:<4d} {src[:110]}")
     print("# by stall samples")
     for n, s, f, ln, src, st in sorted(lines, key=lambda x: -x[1])[:top]:

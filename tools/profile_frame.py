@@ -28,6 +28,7 @@ def main():
             det.run(0)
             det.sync(0)
         print("stage ms", dict(zip(api.STAGE_NAMES, np.round(det.stage_ms(0), 4))), "launches", det.launch_count(0))
+        print("encoder layer ms", np.round(det.encoder_layer_ms(0), 4))
         print("hyps", len(det.collect(0)), "counts", det.counts(0))
         det.close()
 
