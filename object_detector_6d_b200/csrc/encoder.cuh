@@ -3,11 +3,15 @@
 // Replaces the Caffe InnerProduct+Sigmoid triple the reference runs per batch of 100 patches
 // (reference: HoughForest/src/HFTest.cpp:585-596, net definition generate_scripts.sh:424-524).
 //
-// B200 design: persistent, warp-specialised tcgen05 kernel.
-//   warp 0      : TMA producer  (A tile 128x64 bf16, W tile BLOCK_Nx64 bf16, 128-byte swizzle, 4-stage ring)
-//   warp 1      : MMA issuer    (tcgen05.mma cta_group::1 kind::f16, M=128, N=BLOCK_N, K=16; fp32 accum in TMEM)
-//   warp 2      : TMEM allocator (512 columns = two accumulator buffers, so epilogue(i) overlaps mma(i+1))
-//   warps 4..11 : epilogue      (tcgen05.ld -> +bias -> sigmoid -> swizzled shared-memory staging -> TMA store)
+// B200 design: persistent, warp-specialised tcgen05 kernel, launched as CTA pairs (thread-block clusters of 2 = one TPC).
+//   warp 0       : TMA producer  (A tile 128x64 bf16 + this CTA's HALF of the W tile, 128-byte swizzle, mbarrier ring)
+//   warp 1       : MMA issuer    (even CTA only: tcgen05.mma cta_group::2 kind::f16, M=256 over the pair, N=BLOCK_N, K=16;
+//                                 each CTA's 128 rows accumulate in fp32 in its own TMEM)
+//   warp 2       : TMEM allocator (512 columns = two accumulator buffers, so epilogue(i) overlaps mma(i+1))
+//   warps 4..    : epilogue      (tcgen05.ld -> +bias -> sigmoid -> swizzled shared-memory staging -> TMA store)
+// Why pairs: with cta_group::1 every MMA streams A (4 KB) + the whole W slice (N x 32 B) out of shared memory while TMA
+// writes A + W into it; at N = 160 that is more than the shared-memory pipe delivers (tensor pipe 47 % busy).  In a pair
+// each CTA holds and reads only half of W, and pulls A + W/2 per k-block from L2.
 // M (= number of processed patches P') is read from device memory so the launch is graph-capturable and needs no
 // host round trip after the centre scan.
 #pragma once
@@ -24,23 +28,24 @@ namespace hf6d {
 
 constexpr int ENC_BLOCK_M = 128;
 constexpr int ENC_BLOCK_K = 64;  // 64 bf16 = 128 B = one swizzle row
-constexpr int ENC_THREADS = 384;
-constexpr int ENC_EPI_WARPS = 8;
 constexpr int ENC_TMEM_COLS = 512;
 constexpr int ENC_MAX_N = 1536;
 // STAGES: depth of the TMA->MMA operand ring.  EPI_BUFS: staged output chunks per epilogue warp (ring), each 32 rows x
 // CHUNK_BYTES (64 or 128: the inner extent of the TMA store box; 128-byte rows halve the number of stores).
-template <int BLOCK_N, int STAGES, int EPI_BUFS, int CHUNK_BYTES>
+// PAIR: 1 = stand-alone CTAs (cta_group::1), 2 = CTA pairs (cta_group::2).  EPI_WARPS: 8 or 16 epilogue warps.
+template <int BLOCK_N, int STAGES, int EPI_BUFS, int PAIR, int CHUNK_BYTES, int EPI_WARPS>
 struct EncSmem {
+    static constexpr int THREADS = (4 + EPI_WARPS) * 32;
     static constexpr int EPI_BUF_BYTES = 32 * CHUNK_BYTES;
     static constexpr int A_BYTES = ENC_BLOCK_M * ENC_BLOCK_K * 2;
-    static constexpr int B_BYTES = BLOCK_N * ENC_BLOCK_K * 2;
+    static constexpr int B_BYTES = (BLOCK_N / PAIR) * ENC_BLOCK_K * 2;  // this CTA's share of the weight tile
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int EPI_OFF = STAGES * STAGE_BYTES;
-    static constexpr int BIAS_OFF = EPI_OFF + ENC_EPI_WARPS * EPI_BUFS * EPI_BUF_BYTES;
+    static constexpr int BIAS_OFF = EPI_OFF + EPI_WARPS * EPI_BUFS * EPI_BUF_BYTES;
     static constexpr int BAR_OFF = BIAS_OFF + ENC_MAX_N * 4;
     static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 4) * 8 + 16;
     static constexpr int DYN_BYTES = TOTAL + 1024;  // slack for manual 1024-B alignment
+    static_assert(STAGE_BYTES % 1024 == 0, "operand tiles must stay 1024-byte aligned (128-byte swizzle atoms)");
     static_assert(DYN_BYTES <= 232448, "shared memory budget of one SM exceeded");
 };
 
@@ -65,18 +70,22 @@ __device__ __forceinline__ float sigmoid_accurate(float x) {
 // LAST=false : out is bf16 [m_cap][n_pad], all BLOCK_N columns stored (padded columns hold sigma(0)=0.5 and meet
 //              zero weight columns in the next layer); `bias` holds 0.5*b (the tanh form wants x/2)
 // LAST=true  : out is fp32 [m_cap][n_valid]; columns >= n_valid are clipped by the TMA store
-// tmC is the output tensor map: boxes of 32 rows x 64 bytes, 64-byte swizzle.
-// CLUSTER = 2: CTA pairs (thread-block cluster of 2) work on two m-blocks of the SAME n-block; each CTA loads its own A
-//              tile and HALF of the weight tile, multicast into both CTAs' shared memory, so a CTA pulls A + B/2 per
-//              k-block from L2 instead of A + B (layers 1 and 3 are bound by exactly that traffic).  A stage may be
-//              refilled only when BOTH CTAs' MMAs have read it: the MMA commit arrives on the `empty` barrier of both
-//              CTAs (count 2).  tmB then has a box of BLOCK_N/2 rows.
-template <int BLOCK_N, bool LAST, int STAGES, int EPI_BUFS, int CLUSTER, int CHUNK_BYTES>
-__global__ void __launch_bounds__(ENC_THREADS, 1)
+// tmC is the output tensor map: boxes of 32 rows x CHUNK_BYTES, swizzle = CHUNK_BYTES.
+// PAIR = 2   : the two CTAs of a cluster take the m-blocks 2*g and 2*g + 1 of the SAME n-block (a missing last m-block is
+//              computed on whatever the padded rows hold and clipped by the TMA store).  tmB has a box of BLOCK_N / 2 rows:
+//              CTA r loads weight rows [r * BLOCK_N / 2, (r + 1) * BLOCK_N / 2) of the tile.  Barrier protocol:
+//                full[s]   lives in the even CTA: one arrive.expect_tx by its producer for the bytes of BOTH CTAs; both
+//                          producers' TMA loads complete on it (cp.async.bulk.tensor.cta_group::2)
+//                empty[s]  one per CTA: tcgen05.commit.cta_group::2 multicast frees the stage in both
+//                tfull[a]  one per CTA, same multicast commit; tempty[a] in the even CTA counts the epilogue warps of both
+template <int BLOCK_N, bool LAST, int STAGES, int EPI_BUFS, int PAIR, int CHUNK_BYTES, int EPI_WARPS>
+__global__ void __launch_bounds__((4 + EPI_WARPS) * 32, 1)
 encoder_layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmC, const float* __restrict__ bias,
                      const int* __restrict__ m_ptr, int K, int n_pad) {
-    using S = EncSmem<BLOCK_N, STAGES, EPI_BUFS, CHUNK_BYTES>;
+    using S = EncSmem<BLOCK_N, STAGES, EPI_BUFS, PAIR, CHUNK_BYTES, EPI_WARPS>;
+    static_assert(PAIR == 1 || PAIR == 2, "stand-alone CTAs or CTA pairs");
+    static_assert(EPI_WARPS % 4 == 0, "every TMEM lane quadrant needs the same number of epilogue warps");
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
@@ -88,21 +97,21 @@ encoder_layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     uint64_t* tempty = tfull + 2;          // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
-    const int warp = threadIdx.x >> 5;
+    // warp-uniform by construction, and known to be so by the compiler (see ptx::elect_one)
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
 
-    const int M = *m_ptr;
+    const int M = __shfl_sync(0xffffffffu, *m_ptr, 0);
     const int m_blocks = (M + ENC_BLOCK_M - 1) / ENC_BLOCK_M;
     const int n_blocks = n_pad / BLOCK_N;
     const int k_blocks = K / ENC_BLOCK_K;
-    // tile schedule: work item w -> (m-block pair or m-block, n-block); in cluster mode both CTAs of a pair walk the same
-    // items and take the m-blocks 2*mp and 2*mp + 1 (a missing last m-block is computed on zeros and clipped by TMA)
-    const int cta_rank = CLUSTER > 1 ? (int)ptx::cluster_ctarank() : 0;
-    const int m_groups = (m_blocks + CLUSTER - 1) / CLUSTER;
+    // tile schedule: work item -> (m-block group, n-block); both CTAs of a pair walk the same items
+    const int cta_rank = PAIR > 1 ? (int)ptx::cluster_ctarank() : 0;
+    const int m_groups = (m_blocks + PAIR - 1) / PAIR;
     const int tiles = m_groups * n_blocks;
-    const int first = blockIdx.x / CLUSTER, step = gridDim.x / CLUSTER;
+    const int first = blockIdx.x / PAIR, step = gridDim.x / PAIR;
 
-    for (int i = threadIdx.x; i < n_pad; i += ENC_THREADS) s_bias[i] = bias[i];
+    for (int i = threadIdx.x; i < n_pad; i += S::THREADS) s_bias[i] = bias[i];
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&tmA);
@@ -112,57 +121,66 @@ encoder_layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
             ptx::mbar_init(&full[s], 1);
-            ptx::mbar_init(&empty[s], CLUSTER);
+            ptx::mbar_init(&empty[s], 1);
         }
         for (int a = 0; a < 2; ++a) {
             ptx::mbar_init(&tfull[a], 1);
-            ptx::mbar_init(&tempty[a], ENC_EPI_WARPS);
+            ptx::mbar_init(&tempty[a], PAIR * EPI_WARPS);
         }
         ptx::fence_barrier_init();
     }
     if (warp == 2) {
-        ptx::tmem_alloc(tmem_slot, ENC_TMEM_COLS);
-        ptx::tmem_relinquish();
+        if constexpr (PAIR > 1) {
+            ptx::tmem_alloc_pair(tmem_slot, ENC_TMEM_COLS);
+            ptx::tmem_relinquish_pair();
+        } else {
+            ptx::tmem_alloc(tmem_slot, ENC_TMEM_COLS);
+            ptx::tmem_relinquish();
+        }
     }
     ptx::tc_fence_before();
     __syncthreads();
-    if (CLUSTER > 1) ptx::cluster_sync();  // the peer's barriers are initialised before anything is multicast to them
+    if (PAIR > 1) ptx::cluster_sync();  // the peer's barriers are initialised before anything signals them
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ------------------------------------------------------------ TMA producer
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int t = first; t < tiles; t += step) {
-                const int mb = (t / n_blocks) * CLUSTER + cta_rank, nb = t % n_blocks;
-                for (int kb = 0; kb < k_blocks; ++kb) {
-                    ptx::mbar_wait(&empty[stage], phase ^ 1);
-                    uint8_t* sa = smem + stage * S::STAGE_BYTES;
-                    uint8_t* sb = sa + S::A_BYTES;
-                    ptx::mbar_arrive_expect_tx(&full[stage], S::STAGE_BYTES);
-                    ptx::tma_load_2d(sa, &tmA, &full[stage], kb * ENC_BLOCK_K, mb * ENC_BLOCK_M);
-                    if constexpr (CLUSTER > 1)
-                        ptx::tma_load_2d_multicast(sb + cta_rank * (S::B_BYTES / 2), &tmB, &full[stage], kb * ENC_BLOCK_K,
-                                                   nb * BLOCK_N + cta_rank * (BLOCK_N / 2), (uint16_t)0x3);
-                    else
+        // ------------------------------------------------------------ TMA producer (whole warp walks, one lane issues)
+        int stage = 0;
+        uint32_t phase = 0;
+        const uint32_t full0 = PAIR > 1 ? ptx::mapa_shared(ptx::smem_u32(&full[0]), 0) : 0;  // the even CTA's barriers
+        for (int t = first; t < tiles; t += step) {
+            const int mb = (t / n_blocks) * PAIR + cta_rank, nb = t % n_blocks;
+            for (int kb = 0; kb < k_blocks; ++kb) {
+                ptx::mbar_wait(&empty[stage], phase ^ 1);
+                uint8_t* sa = smem + stage * S::STAGE_BYTES;
+                uint8_t* sb = sa + S::A_BYTES;
+                if (ptx::elect_one()) {
+                    if constexpr (PAIR > 1) {
+                        if (cta_rank == 0) ptx::mbar_arrive_expect_tx(&full[stage], PAIR * S::STAGE_BYTES);
+                        ptx::tma_load_2d_pair(sa, &tmA, full0 + stage * 8, kb * ENC_BLOCK_K, mb * ENC_BLOCK_M);
+                        ptx::tma_load_2d_pair(sb, &tmB, full0 + stage * 8, kb * ENC_BLOCK_K,
+                                              nb * BLOCK_N + cta_rank * (BLOCK_N / 2));
+                    } else {
+                        ptx::mbar_arrive_expect_tx(&full[stage], S::STAGE_BYTES);
+                        ptx::tma_load_2d(sa, &tmA, &full[stage], kb * ENC_BLOCK_K, mb * ENC_BLOCK_M);
                         ptx::tma_load_2d(sb, &tmB, &full[stage], kb * ENC_BLOCK_K, nb * BLOCK_N);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
                 }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
-        __syncwarp();
     } else if (warp == 1) {
-        // ------------------------------------------------------------ MMA issuer (single thread)
-        if (lane == 0) {
-            constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(ENC_BLOCK_M, BLOCK_N);
+        // ------------------------------------------------------------ MMA issuer (the even CTA of a pair; one lane issues)
+        if (cta_rank == 0) {
+            constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(ENC_BLOCK_M * PAIR, BLOCK_N);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
             for (int t = first; t < tiles; t += step) {
-                ptx::mbar_wait(&tempty[acc], acc_phase ^ 1);
+                ptx::mbar_wait<(PAIR > 1)>(&tempty[acc], acc_phase ^ 1);
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * 256;
                 for (int kb = 0; kb < k_blocks; ++kb) {
@@ -171,27 +189,35 @@ encoder_layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                     const uint32_t sa = ptx::smem_u32(smem + stage * S::STAGE_BYTES);
                     const uint64_t adesc = ptx::make_kmajor_sw128_desc(sa);
                     const uint64_t bdesc = ptx::make_kmajor_sw128_desc(sa + S::A_BYTES);
+                    if (ptx::elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < ENC_BLOCK_K / 16; ++k) {
-                        // +32 B per K=16 step inside the 128-B swizzle row: +2 in the (addr>>4) field
-                        ptx::umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                        for (int k = 0; k < ENC_BLOCK_K / 16; ++k) {
+                            // +32 B per K=16 step inside the 128-B swizzle row: +2 in the (addr>>4) field
+                            if constexpr (PAIR > 1) ptx::umma_bf16_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                            else ptx::umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                        }
+                        if constexpr (PAIR > 1) ptx::umma_commit_pair(&empty[stage], (uint16_t)0x3);
+                        else ptx::umma_commit(&empty[stage]);
                     }
-                    if constexpr (CLUSTER > 1) ptx::umma_commit_multicast(&empty[stage], (uint16_t)0x3);
-                    else ptx::umma_commit(&empty[stage]);
+                    __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                ptx::umma_commit(&tfull[acc]);
+                if (ptx::elect_one()) {
+                    if constexpr (PAIR > 1) ptx::umma_commit_pair(&tfull[acc], (uint16_t)0x3);
+                    else ptx::umma_commit(&tfull[acc]);
+                }
+                __syncwarp();
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
-        __syncwarp();
     } else if (warp >= 4) {
         // ------------------------------------------------------------ epilogue
-        // TMEM -> registers -> bias + sigmoid -> 64-byte row chunks staged in shared memory (64-byte swizzle, so the
-        // 16-byte vector stores of a warp spread over all banks) -> TMA store: full-sector, fully coalesced writes
-        // issued by the copy engine, off the LSU.
+        // TMEM -> registers -> bias + sigmoid -> row chunks staged in shared memory (swizzled, so the 16-byte vector
+        // stores of a warp spread over all banks) -> TMA store: full-sector, fully coalesced writes issued by the copy
+        // engine, off the LSU.
         const int q = warp & 3;               // TMEM lane quadrant this warp may touch
-        const int half = (warp - 4) >> 2;     // the two warps of a quadrant take alternate column chunks
+        const int sub = (warp - 4) >> 2;      // the warps of a quadrant take the column chunks round-robin
+        constexpr int SUBS = EPI_WARPS / 4;
         constexpr int CHUNK_COLS = CHUNK_BYTES / (LAST ? 4 : 2);  // output columns per staged chunk
         constexpr int TILE_CHUNKS = BLOCK_N / CHUNK_COLS;
         constexpr int UNITS = CHUNK_BYTES / 16;                   // 16-byte units per staged row
@@ -201,51 +227,61 @@ encoder_layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const uint32_t row_off = (uint32_t)lane * CHUNK_BYTES;
         // TMA swizzle: the 16-byte unit index is XORed with address bits [7, 7 + log2(UNITS))
         const uint32_t sw = UNITS == 8 ? ((uint32_t)lane & 7u) : (((uint32_t)lane >> 1) & 3u);
+        const uint32_t tempty0 = PAIR > 1 ? ptx::mapa_shared(ptx::smem_u32(&tempty[0]), 0) : 0;  // the even CTA's barriers
         int it = 0;                                      // chunks staged by this warp so far
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int t = first; t < tiles; t += step) {
-            const int mb = (t / n_blocks) * CLUSTER + cta_rank, nb = t % n_blocks;
+            const int mb = (t / n_blocks) * PAIR + cta_rank, nb = t % n_blocks;
             const int row0 = mb * ENC_BLOCK_M + q * 32;
             ptx::mbar_wait(&tfull[acc], acc_phase);
             ptx::tc_fence_after();
             const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256;
 #pragma unroll 1
-            for (int c = half; c < TILE_CHUNKS; c += 2, ++it) {
+            for (int c = sub; c < TILE_CHUNKS; c += SUBS, ++it) {
                 const int tcol = c * CHUNK_COLS;             // column inside the tile
                 const int col = nb * BLOCK_N + tcol;
+                uint32_t v[CHUNK_COLS];
+                if constexpr (CHUNK_COLS == 16) {
+                    ptx::tmem_ld_32x32b_x16(taddr0 + tcol, v);
+                } else {
+#pragma unroll
+                    for (int h = 0; h < CHUNK_COLS / 32; ++h)
+                        ptx::tmem_ld_32x32b_x32(taddr0 + tcol + h * 32, *reinterpret_cast<uint32_t(*)[32]>(&v[h * 32]));
+                }
+                ptx::tmem_ld_wait();
+                if (c + SUBS >= TILE_CHUNKS) {  // this warp has drained its part of the accumulator: hand it back now
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if constexpr (PAIR > 1) ptx::mbar_arrive_cluster(tempty0 + acc * 8);
+                        else ptx::mbar_arrive(&tempty[acc]);
+                    }
+                }
                 uint32_t o[UNITS * 4];
+                const uint32_t bias_addr = ptx::smem_u32(s_bias + col);  // broadcast reads, 16 bytes each
                 if constexpr (!LAST) {
 #pragma unroll
-                    for (int h = 0; h < CHUNK_COLS / 32; ++h) {
-                        uint32_t v[32];
-                        ptx::tmem_ld_32x32b_x32(taddr0 + tcol + h * 32, v);
-                        ptx::tmem_ld_wait();
-#pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            o[h * 16 + j] = sigmoid_pair_bf16(fmaf(__uint_as_float(v[2 * j]), 0.5f, s_bias[col + h * 32 + 2 * j]),
-                                                              fmaf(__uint_as_float(v[2 * j + 1]), 0.5f, s_bias[col + h * 32 + 2 * j + 1]));
+                    for (int j = 0; j < CHUNK_COLS / 4; ++j) {
+                        const float4 b = ptx::ld_shared_f4(bias_addr + 16 * j);
+                        o[2 * j] = sigmoid_pair_bf16(fmaf(__uint_as_float(v[4 * j]), 0.5f, b.x),
+                                                     fmaf(__uint_as_float(v[4 * j + 1]), 0.5f, b.y));
+                        o[2 * j + 1] = sigmoid_pair_bf16(fmaf(__uint_as_float(v[4 * j + 2]), 0.5f, b.z),
+                                                         fmaf(__uint_as_float(v[4 * j + 3]), 0.5f, b.w));
                     }
                 } else {
 #pragma unroll
-                    for (int h = 0; h < CHUNK_COLS / 16; ++h) {
-                        uint32_t v[16];
-                        ptx::tmem_ld_32x32b_x16(taddr0 + tcol + h * 16, v);
-                        ptx::tmem_ld_wait();
-#pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            o[h * 16 + j] = __float_as_uint(sigmoid_accurate(__uint_as_float(v[j]) + s_bias[col + h * 16 + j]));
+                    for (int j = 0; j < CHUNK_COLS / 4; ++j) {
+                        const float4 b = ptx::ld_shared_f4(bias_addr + 16 * j);
+                        o[4 * j] = __float_as_uint(sigmoid_accurate(__uint_as_float(v[4 * j]) + b.x));
+                        o[4 * j + 1] = __float_as_uint(sigmoid_accurate(__uint_as_float(v[4 * j + 1]) + b.y));
+                        o[4 * j + 2] = __float_as_uint(sigmoid_accurate(__uint_as_float(v[4 * j + 2]) + b.z));
+                        o[4 * j + 3] = __float_as_uint(sigmoid_accurate(__uint_as_float(v[4 * j + 3]) + b.w));
                     }
-                }
-                const bool last_chunk = c + 2 >= TILE_CHUNKS;
-                if (last_chunk) {  // this warp has drained its part of the accumulator: hand it back before the stores
-                    ptx::tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
                 }
                 const uint32_t buf = stage_base + (uint32_t)(it % EPI_BUFS) * S::EPI_BUF_BYTES;
                 if (it >= EPI_BUFS) {  // the TMA store that last used this buffer must have read it
-                    if (lane == 0) ptx::tma_store_wait_read<EPI_BUFS - 1>();
+                    if (ptx::elect_one()) ptx::tma_store_wait_read<EPI_BUFS - 1>();  // always the same lane: bulk groups are per thread
                     __syncwarp();
                 }
 #pragma unroll
@@ -253,28 +289,32 @@ encoder_layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                     ptx::st_shared_v4(buf + row_off + (((uint32_t)u ^ sw) << 4), o[4 * u], o[4 * u + 1], o[4 * u + 2], o[4 * u + 3]);
                 ptx::fence_proxy_async();
                 __syncwarp();
-                if (lane == 0) {
+                if (ptx::elect_one()) {
                     ptx::tma_store_2d(&tmC, reinterpret_cast<const void*>(smem + (buf - ptx::smem_u32(smem))), col, row0);
                     ptx::tma_store_commit();
                 }
             }
-            if (half >= TILE_CHUNKS) {  // a half without any chunk still has to release the accumulator
+            if (sub >= TILE_CHUNKS) {  // a warp without any chunk still has to release the accumulator
                 ptx::tc_fence_before();
                 __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
+                if (lane == 0) {
+                    if constexpr (PAIR > 1) ptx::mbar_arrive_cluster(tempty0 + acc * 8);
+                    else ptx::mbar_arrive(&tempty[acc]);
+                }
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
-        if (lane == 0) ptx::tma_store_wait_all<0>();  // shared memory must outlive the copies; writes complete before exit
+        if (ptx::elect_one()) ptx::tma_store_wait_all<0>();  // shared memory must outlive the copies; writes complete before exit
         __syncwarp();
     }
 
     ptx::tc_fence_before();
     __syncthreads();
-    if (CLUSTER > 1) ptx::cluster_sync();  // no CTA leaves while its peer may still multicast into it or arrive on its barriers
+    if (PAIR > 1) ptx::cluster_sync();  // no CTA leaves while its peer's MMAs read its operands or signal its barriers
     if (warp == 2) {
         ptx::tc_fence_after();
-        ptx::tmem_dealloc(tmem_base, ENC_TMEM_COLS);
+        if constexpr (PAIR > 1) ptx::tmem_dealloc_pair(tmem_base, ENC_TMEM_COLS);
+        else ptx::tmem_dealloc(tmem_base, ENC_TMEM_COLS);
     }
 }
 
@@ -327,70 +367,95 @@ inline bool make_out_map(CUtensorMap* map, void* base, uint64_t rows, uint64_t c
 }
 
 struct EncoderLayerLaunch {
-    CUtensorMap tmA, tmB, tmB_half, tmC;  // tmB_half: box of block_n / 2 rows (cluster mode)
-    const float* bias;  // hidden layers: 0.5 * b
+    CUtensorMap tmA, tmB, tmC;  // tmB: box of block_n / pair rows
+    const float* bias;          // hidden layers: 0.5 * b
     int K, n_pad, block_n;
-    bool last, short_k;  // short_k: few K blocks per tile -> 3 operand stages, deeper output staging
-    int cluster;         // 1, or 2 = CTA pairs with the weight tile multicast
+    bool last, short_k;  // short_k: few K blocks per tile
+    int pair;            // 1 = stand-alone CTAs, 2 = CTA pairs (cta_group::2)
+    int epi_warps;       // 8 or 16
 };
 
-template <int BLOCK_N, bool LAST, int STAGES, int EPI_BUFS, int CLUSTER, int CHUNK_BYTES>
+template <int BLOCK_N, bool LAST, int STAGES, int EPI_BUFS, int PAIR, int CHUNK_BYTES, int EPI_WARPS>
 inline cudaError_t launch_encoder_layer_t(const EncoderLayerLaunch& L, const int* m_ptr, int sms, cudaStream_t st) {
-    auto kern = encoder_layer_kernel<BLOCK_N, LAST, STAGES, EPI_BUFS, CLUSTER, CHUNK_BYTES>;
-    using S = EncSmem<BLOCK_N, STAGES, EPI_BUFS, CHUNK_BYTES>;
+    auto kern = encoder_layer_kernel<BLOCK_N, LAST, STAGES, EPI_BUFS, PAIR, CHUNK_BYTES, EPI_WARPS>;
+    using S = EncSmem<BLOCK_N, STAGES, EPI_BUFS, PAIR, CHUNK_BYTES, EPI_WARPS>;
     static int grid = 0;
     if (!grid) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::DYN_BYTES);
         if (e != cudaSuccess) return e;
         grid = sms;
-        if (CLUSTER > 1) {  // as many co-resident pairs as the GPCs can hold
+        if (PAIR > 1) {  // as many co-resident pairs as the GPCs can hold
             cudaLaunchConfig_t q{};
-            q.gridDim = dim3(sms / CLUSTER * CLUSTER);
-            q.blockDim = dim3(ENC_THREADS);
+            q.gridDim = dim3(sms / PAIR * PAIR);
+            q.blockDim = dim3(S::THREADS);
             q.dynamicSmemBytes = S::DYN_BYTES;
             cudaLaunchAttribute a[1];
             a[0].id = cudaLaunchAttributeClusterDimension;
-            a[0].val.clusterDim.x = CLUSTER; a[0].val.clusterDim.y = 1; a[0].val.clusterDim.z = 1;
+            a[0].val.clusterDim.x = PAIR; a[0].val.clusterDim.y = 1; a[0].val.clusterDim.z = 1;
             q.attrs = a; q.numAttrs = 1;
             int n_clusters = 0;
             e = cudaOccupancyMaxActiveClusters(&n_clusters, kern, &q);
             if (e != cudaSuccess) return e;
             if (n_clusters < 1) return cudaErrorInvalidConfiguration;
-            grid = std::min(n_clusters, sms / CLUSTER) * CLUSTER;
+            grid = std::min(n_clusters, sms / PAIR) * PAIR;
         }
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(ENC_THREADS);
+    cfg.blockDim = dim3(S::THREADS);
     cfg.dynamicSmemBytes = S::DYN_BYTES;
     cfg.stream = st;
     cudaLaunchAttribute attrs[1];
     attrs[0].id = cudaLaunchAttributeClusterDimension;
-    attrs[0].val.clusterDim.x = CLUSTER; attrs[0].val.clusterDim.y = 1; attrs[0].val.clusterDim.z = 1;
+    attrs[0].val.clusterDim.x = PAIR; attrs[0].val.clusterDim.y = 1; attrs[0].val.clusterDim.z = 1;
     cfg.attrs = attrs;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kern, L.tmA, CLUSTER > 1 ? L.tmB_half : L.tmB, L.tmC, L.bias, m_ptr, L.K, L.n_pad);
+    return cudaLaunchKernelEx(&cfg, kern, L.tmA, L.tmB, L.tmC, L.bias, m_ptr, L.K, L.n_pad);
 }
 
-// Output chunk width per configuration (the slot's tensor maps are built with the same rule).
-inline int encoder_chunk_bytes(int block_n, bool last, bool short_k) {
-    if (block_n == 256 && !last && !short_k) return 64;  // 4 operand stages leave 16 KB for staging: 64-byte chunks
-    if (block_n == 256 && last) return 64;
-    return 128;
+// The kernel configurations, one table for the launcher and for the slot's tensor maps (output chunk width).
+//   shape class: 0 = hidden layer, short K (<= 6 k-blocks);  1 = hidden layer;  2 = feature layer N % 160 == 0;
+//                3 = feature layer, 256-wide tiles
+#define HF6D_ENC_CONFIGS(X)                                   \
+    /*  cls  N   LAST  ST EB PAIR CHUNK EPI */                \
+    X(0, 256, false, 3, 2, 1, 128, 8)                         \
+    X(1, 256, false, 4, 1, 1, 64, 8)                          \
+    X(2, 160, true, 4, 2, 1, 128, 8)                          \
+    X(3, 256, true, 4, 1, 1, 64, 8)                           \
+    X(0, 256, false, 3, 1, 1, 128, 16)                        \
+    X(1, 256, false, 3, 1, 1, 128, 16)                        \
+    X(2, 160, true, 4, 2, 1, 64, 16)                          \
+    X(3, 256, true, 3, 1, 1, 128, 16)                         \
+    X(0, 256, false, 4, 2, 2, 128, 8)                         \
+    X(1, 256, false, 5, 2, 2, 64, 8)                          \
+    X(2, 160, true, 5, 2, 2, 128, 8)                          \
+    X(3, 256, true, 4, 2, 2, 64, 8)                           \
+    X(0, 256, false, 4, 1, 2, 128, 16)                        \
+    X(1, 256, false, 5, 1, 2, 64, 16)                         \
+    X(2, 160, true, 5, 2, 2, 64, 16)                          \
+    X(3, 256, true, 4, 1, 2, 64, 16)
+
+inline int encoder_shape_class(int block_n, bool last, bool short_k) {
+    if (!last) return short_k ? 0 : 1;
+    return block_n == 160 ? 2 : 3;
+}
+
+inline int encoder_chunk_bytes(int block_n, bool last, bool short_k, int pair, int epi_warps) {
+    const int cls = encoder_shape_class(block_n, last, short_k);
+#define X(CLS, N, LAST, ST, EB, PAIR, CHUNK, EPI) \
+    if (cls == CLS && block_n == N && pair == PAIR && epi_warps == EPI) return CHUNK;
+    HF6D_ENC_CONFIGS(X)
+#undef X
+    return 0;
 }
 
 inline cudaError_t launch_encoder_layer(const EncoderLayerLaunch& L, const int* m_ptr, int sms, cudaStream_t st) {
-    if (L.cluster == 2) {
-        if (L.block_n == 256 && !L.last && L.short_k) return launch_encoder_layer_t<256, false, 3, 2, 2, 128>(L, m_ptr, sms, st);
-        if (L.block_n == 256 && !L.last) return launch_encoder_layer_t<256, false, 4, 1, 2, 64>(L, m_ptr, sms, st);
-        if (L.block_n == 160 && L.last) return launch_encoder_layer_t<160, true, 4, 2, 2, 128>(L, m_ptr, sms, st);
-        if (L.block_n == 256 && L.last) return launch_encoder_layer_t<256, true, 4, 1, 2, 64>(L, m_ptr, sms, st);
-        return cudaErrorInvalidValue;
-    }
-    if (L.block_n == 256 && !L.last && L.short_k) return launch_encoder_layer_t<256, false, 3, 2, 1, 128>(L, m_ptr, sms, st);
-    if (L.block_n == 256 && !L.last) return launch_encoder_layer_t<256, false, 4, 1, 1, 64>(L, m_ptr, sms, st);
-    if (L.block_n == 160 && L.last) return launch_encoder_layer_t<160, true, 4, 2, 1, 128>(L, m_ptr, sms, st);
-    if (L.block_n == 256 && L.last) return launch_encoder_layer_t<256, true, 4, 1, 1, 64>(L, m_ptr, sms, st);
+    const int cls = encoder_shape_class(L.block_n, L.last, L.short_k);
+#define X(CLS, N, LAST, ST, EB, PAIR, CHUNK, EPI)                                \
+    if (cls == CLS && L.block_n == N && L.pair == PAIR && L.epi_warps == EPI)    \
+        return launch_encoder_layer_t<N, LAST, ST, EB, PAIR, CHUNK, EPI>(L, m_ptr, sms, st);
+    HF6D_ENC_CONFIGS(X)
+#undef X
     return cudaErrorInvalidValue;
 }
 

@@ -111,7 +111,10 @@ struct hf6d_ctx {
     int shard_rank = 0, shard_world = 1;
     int class_rank = 0, class_world = 1;  // centres + pose only for classes k % class_world == class_rank
     int encoder_mode = 0;
-    int enc_cluster = 2;  // encoder CTA pairs with multicast weight tiles (HF6D_ENC_CLUSTER=1 turns it off)
+    // per encoder layer: CTA pairs (tcgen05 cta_group::2) or stand-alone CTAs, and the number of epilogue warps.
+    // Tuning switches: HF6D_ENC_PAIR="1,2,2", HF6D_ENC_EPI="16,8,8".
+    int enc_pair[3] = {1, 2, 2};
+    int enc_epi_warps[3] = {8, 8, 8};
     int debug_capture = 0;
     int next_ticket = 0;
     std::string err;
@@ -308,19 +311,21 @@ int alloc_slot(hf6d_ctx* c, Slot& s) {
     for (int l = 0; l < 3; ++l) {
         EncoderLayerLaunch& L = s.enc[l];
         if (!make_bf16_kmajor_map(&L.tmA, a_in[l], (uint64_t)g.cap, (uint64_t)dm.k_pad[l], ENC_BLOCK_M) ||
-            !make_bf16_kmajor_map(&L.tmB, dm.W[l], (uint64_t)dm.n_pad[l], (uint64_t)dm.k_pad[l], (uint32_t)dm.block_n[l]) ||
-            !make_bf16_kmajor_map(&L.tmB_half, dm.W[l], (uint64_t)dm.n_pad[l], (uint64_t)dm.k_pad[l], (uint32_t)dm.block_n[l] / 2))
+            !make_bf16_kmajor_map(&L.tmB, dm.W[l], (uint64_t)dm.n_pad[l], (uint64_t)dm.k_pad[l],
+                                  (uint32_t)(dm.block_n[l] / c->enc_pair[l])))
             return fail(c, HF6D_ECUDA, "cuTensorMapEncodeTiled failed for encoder layer %d", l);
         L.last = l == 2;
         if (!make_out_map(&L.tmC, outs[l], (uint64_t)g.cap, (uint64_t)(L.last ? F : dm.n_pad[l]), L.last ? 4 : 2,
-                          encoder_chunk_bytes(dm.block_n[l], L.last, dm.k_pad[l] / ENC_BLOCK_K <= 6)))
+                          encoder_chunk_bytes(dm.block_n[l], L.last, dm.k_pad[l] / ENC_BLOCK_K <= 6, c->enc_pair[l],
+                                              c->enc_epi_warps[l])))
             return fail(c, HF6D_ECUDA, "cuTensorMapEncodeTiled failed for the output of encoder layer %d", l);
         L.bias = dm.b[l];
         L.K = dm.k_pad[l];
         L.n_pad = dm.n_pad[l];
         L.block_n = dm.block_n[l];
         L.short_k = dm.k_pad[l] / ENC_BLOCK_K <= 6;
-        L.cluster = c->enc_cluster;
+        L.pair = c->enc_pair[l];
+        L.epi_warps = c->enc_epi_warps[l];
     }
     return HF6D_OK;
 }
@@ -828,7 +833,16 @@ int finish_create(hf6d_ctx* c, int device, int n_slots) {
     }
     CU_TRY(c, cudaFuncSetAttribute(window_accumulate_kernel<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, WA_MAX_DYN_SMEM));
     CU_TRY(c, cudaFuncSetAttribute(window_accumulate_kernel<true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, WA_MAX_DYN_SMEM));
-    if (const char* e = getenv("HF6D_ENC_CLUSTER")) c->enc_cluster = atoi(e) == 1 ? 1 : 2;
+    if (const char* e = getenv("HF6D_ENC_PAIR")) {
+        int v[3];
+        if (sscanf(e, "%d,%d,%d", &v[0], &v[1], &v[2]) == 3)
+            for (int l = 0; l < 3; ++l) c->enc_pair[l] = v[l] == 1 ? 1 : 2;
+    }
+    if (const char* e = getenv("HF6D_ENC_EPI")) {
+        int v[3];
+        if (sscanf(e, "%d,%d,%d", &v[0], &v[1], &v[2]) == 3)
+            for (int l = 0; l < 3; ++l) c->enc_epi_warps[l] = v[l] == 16 ? 16 : 8;
+    }
     c->slots.resize(c->n_slots);
     for (Slot& s : c->slots) {
         memset(s.ev, 0, sizeof s.ev);
