@@ -367,12 +367,11 @@ inline bool make_out_map(CUtensorMap* map, void* base, uint64_t rows, uint64_t c
 }
 
 struct EncoderLayerLaunch {
-    CUtensorMap tmA, tmB, tmC;  // tmB: box of block_n / pair rows
+    CUtensorMap tmA, tmB, tmC;  // tmB: box of block_n / pair rows; tmC: boxes of 32 rows x chunk bytes
     const float* bias;          // hidden layers: 0.5 * b
     int K, n_pad, block_n;
     bool last, short_k;  // short_k: few K blocks per tile
-    int pair;            // 1 = stand-alone CTAs, 2 = CTA pairs (cta_group::2)
-    int epi_warps;       // 8 or 16
+    int variant;         // row of HF6D_ENC_CONFIGS for this layer's shape class
 };
 
 template <int BLOCK_N, bool LAST, int STAGES, int EPI_BUFS, int PAIR, int CHUNK_BYTES, int EPI_WARPS>
@@ -413,46 +412,52 @@ inline cudaError_t launch_encoder_layer_t(const EncoderLayerLaunch& L, const int
     return cudaLaunchKernelEx(&cfg, kern, L.tmA, L.tmB, L.tmC, L.bias, m_ptr, L.K, L.n_pad);
 }
 
-// The kernel configurations, one table for the launcher and for the slot's tensor maps (output chunk width).
+// The kernel configurations, one table for the launcher and for the slot's tensor maps (W box rows, output chunk width).
 //   shape class: 0 = hidden layer, short K (<= 6 k-blocks);  1 = hidden layer;  2 = feature layer N % 160 == 0;
 //                3 = feature layer, 256-wide tiles
-#define HF6D_ENC_CONFIGS(X)                                   \
-    /*  cls  N   LAST  ST EB PAIR CHUNK EPI */                \
-    X(0, 256, false, 3, 2, 1, 128, 8)                         \
-    X(1, 256, false, 4, 1, 1, 64, 8)                          \
-    X(2, 160, true, 4, 2, 1, 128, 8)                          \
-    X(3, 256, true, 4, 1, 1, 64, 8)                           \
-    X(0, 256, false, 3, 1, 1, 128, 16)                        \
-    X(1, 256, false, 3, 1, 1, 128, 16)                        \
-    X(2, 160, true, 4, 2, 1, 64, 16)                          \
-    X(3, 256, true, 3, 1, 1, 128, 16)                         \
-    X(0, 256, false, 4, 2, 2, 128, 8)                         \
-    X(1, 256, false, 5, 2, 2, 64, 8)                          \
-    X(2, 160, true, 5, 2, 2, 128, 8)                          \
-    X(3, 256, true, 4, 2, 2, 64, 8)                           \
-    X(0, 256, false, 4, 1, 2, 128, 16)                        \
-    X(1, 256, false, 5, 1, 2, 64, 16)                         \
-    X(2, 160, true, 5, 2, 2, 64, 16)                          \
-    X(3, 256, true, 4, 1, 2, 64, 16)
+//   variant 0 is the default of its class; the others are kept for HF6D_ENC_VARIANT="a,b,c" (per layer) experiments and
+//   as the fallback when CTA pairs cannot be scheduled (variant 1: stand-alone CTAs, cta_group::1).
+#define HF6D_ENC_CONFIGS(X)                                        \
+    /*  cls var  N   LAST  ST EB PAIR CHUNK EPI      B200, 70.9 k patches: us per layer */ \
+    X(0, 0, 256, false, 5, 1, 2, 128, 8)  /* 57.7 */               \
+    X(0, 1, 256, false, 3, 2, 1, 128, 8)  /* 65.5 */               \
+    X(0, 2, 256, false, 4, 2, 2, 128, 8)  /* 60.1 */               \
+    X(0, 3, 256, false, 4, 2, 2, 64, 16)  /* 59.6 */               \
+    X(0, 4, 256, false, 6, 1, 2, 64, 8)   /* 63.7 */               \
+    X(1, 0, 256, false, 6, 1, 2, 64, 8)   /* 129.0 */              \
+    X(1, 1, 256, false, 4, 1, 1, 64, 8)   /* 151.6 */              \
+    X(1, 2, 256, false, 5, 2, 2, 64, 8)   /* 135.1 */              \
+    X(1, 3, 256, false, 4, 2, 2, 128, 8)  /* 146.2 */              \
+    X(2, 0, 160, true, 7, 1, 2, 128, 8)   /* 98.3 */               \
+    X(2, 1, 160, true, 4, 2, 1, 128, 8)   /* 118.8 */              \
+    X(2, 2, 160, true, 5, 2, 2, 128, 8)   /* 104.5 */              \
+    X(2, 3, 160, true, 7, 2, 2, 64, 8)    /* 98.5 */               \
+    X(2, 4, 160, true, 4, 2, 2, 128, 12)  /* 122.9 */              \
+    X(3, 0, 256, true, 4, 2, 2, 64, 8)                             \
+    X(3, 1, 256, true, 4, 1, 1, 64, 8)
 
 inline int encoder_shape_class(int block_n, bool last, bool short_k) {
     if (!last) return short_k ? 0 : 1;
     return block_n == 160 ? 2 : 3;
 }
 
-inline int encoder_chunk_bytes(int block_n, bool last, bool short_k, int pair, int epi_warps) {
+struct EncoderConfig {
+    int pair, chunk_bytes;
+};
+// pair == 0: no such variant
+inline EncoderConfig encoder_config(int block_n, bool last, bool short_k, int variant) {
     const int cls = encoder_shape_class(block_n, last, short_k);
-#define X(CLS, N, LAST, ST, EB, PAIR, CHUNK, EPI) \
-    if (cls == CLS && block_n == N && pair == PAIR && epi_warps == EPI) return CHUNK;
+#define X(CLS, VAR, N, LAST, ST, EB, PAIR, CHUNK, EPI) \
+    if (cls == CLS && variant == VAR && block_n == N) return EncoderConfig{PAIR, CHUNK};
     HF6D_ENC_CONFIGS(X)
 #undef X
-    return 0;
+    return EncoderConfig{0, 0};
 }
 
 inline cudaError_t launch_encoder_layer(const EncoderLayerLaunch& L, const int* m_ptr, int sms, cudaStream_t st) {
     const int cls = encoder_shape_class(L.block_n, L.last, L.short_k);
-#define X(CLS, N, LAST, ST, EB, PAIR, CHUNK, EPI)                                \
-    if (cls == CLS && L.block_n == N && L.pair == PAIR && L.epi_warps == EPI)    \
+#define X(CLS, VAR, N, LAST, ST, EB, PAIR, CHUNK, EPI)                 \
+    if (cls == CLS && L.variant == VAR && L.block_n == N)              \
         return launch_encoder_layer_t<N, LAST, ST, EB, PAIR, CHUNK, EPI>(L, m_ptr, sms, st);
     HF6D_ENC_CONFIGS(X)
 #undef X

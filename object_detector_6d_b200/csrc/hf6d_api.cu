@@ -111,10 +111,9 @@ struct hf6d_ctx {
     int shard_rank = 0, shard_world = 1;
     int class_rank = 0, class_world = 1;  // centres + pose only for classes k % class_world == class_rank
     int encoder_mode = 0;
-    // per encoder layer: CTA pairs (tcgen05 cta_group::2) or stand-alone CTAs, and the number of epilogue warps.
-    // Tuning switches: HF6D_ENC_PAIR="1,2,2", HF6D_ENC_EPI="16,8,8".
-    int enc_pair[3] = {1, 2, 2};
-    int enc_epi_warps[3] = {8, 8, 8};
+    // per encoder layer: row of HF6D_ENC_CONFIGS within the layer's shape class (0 = default: CTA pairs, cta_group::2;
+    // 1 = stand-alone CTAs).  Tuning switch: HF6D_ENC_VARIANT="a,b,c".
+    int enc_variant[3] = {0, 0, 0};
     int debug_capture = 0;
     int next_ticket = 0;
     std::string err;
@@ -310,22 +309,23 @@ int alloc_slot(hf6d_ctx* c, Slot& s) {
     void* outs[3] = {s.H1, s.H2, s.feat};
     for (int l = 0; l < 3; ++l) {
         EncoderLayerLaunch& L = s.enc[l];
+        const bool short_k = dm.k_pad[l] / ENC_BLOCK_K <= 6;
+        const EncoderConfig cfg = encoder_config(dm.block_n[l], l == 2, short_k, c->enc_variant[l]);
+        if (!cfg.pair) return fail(c, HF6D_EINVAL, "encoder layer %d has no kernel variant %d", l, c->enc_variant[l]);
         if (!make_bf16_kmajor_map(&L.tmA, a_in[l], (uint64_t)g.cap, (uint64_t)dm.k_pad[l], ENC_BLOCK_M) ||
             !make_bf16_kmajor_map(&L.tmB, dm.W[l], (uint64_t)dm.n_pad[l], (uint64_t)dm.k_pad[l],
-                                  (uint32_t)(dm.block_n[l] / c->enc_pair[l])))
+                                  (uint32_t)(dm.block_n[l] / cfg.pair)))
             return fail(c, HF6D_ECUDA, "cuTensorMapEncodeTiled failed for encoder layer %d", l);
         L.last = l == 2;
         if (!make_out_map(&L.tmC, outs[l], (uint64_t)g.cap, (uint64_t)(L.last ? F : dm.n_pad[l]), L.last ? 4 : 2,
-                          encoder_chunk_bytes(dm.block_n[l], L.last, dm.k_pad[l] / ENC_BLOCK_K <= 6, c->enc_pair[l],
-                                              c->enc_epi_warps[l])))
+                          cfg.chunk_bytes))
             return fail(c, HF6D_ECUDA, "cuTensorMapEncodeTiled failed for the output of encoder layer %d", l);
         L.bias = dm.b[l];
         L.K = dm.k_pad[l];
         L.n_pad = dm.n_pad[l];
         L.block_n = dm.block_n[l];
-        L.short_k = dm.k_pad[l] / ENC_BLOCK_K <= 6;
-        L.pair = c->enc_pair[l];
-        L.epi_warps = c->enc_epi_warps[l];
+        L.short_k = short_k;
+        L.variant = c->enc_variant[l];
     }
     return HF6D_OK;
 }
@@ -833,15 +833,10 @@ int finish_create(hf6d_ctx* c, int device, int n_slots) {
     }
     CU_TRY(c, cudaFuncSetAttribute(window_accumulate_kernel<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, WA_MAX_DYN_SMEM));
     CU_TRY(c, cudaFuncSetAttribute(window_accumulate_kernel<true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, WA_MAX_DYN_SMEM));
-    if (const char* e = getenv("HF6D_ENC_PAIR")) {
+    if (const char* e = getenv("HF6D_ENC_VARIANT")) {
         int v[3];
         if (sscanf(e, "%d,%d,%d", &v[0], &v[1], &v[2]) == 3)
-            for (int l = 0; l < 3; ++l) c->enc_pair[l] = v[l] == 1 ? 1 : 2;
-    }
-    if (const char* e = getenv("HF6D_ENC_EPI")) {
-        int v[3];
-        if (sscanf(e, "%d,%d,%d", &v[0], &v[1], &v[2]) == 3)
-            for (int l = 0; l < 3; ++l) c->enc_epi_warps[l] = v[l] == 16 ? 16 : 8;
+            for (int l = 0; l < 3; ++l) c->enc_variant[l] = v[l];
     }
     c->slots.resize(c->n_slots);
     for (Slot& s : c->slots) {

@@ -19,7 +19,11 @@ def main():
     ap.add_argument("--frames", type=int, default=3)
     ap.add_argument("--distinct", type=int, default=2)
     ap.add_argument("--trees", type=int, default=bench.T_TREES)
+    ap.add_argument("--lib", default=None, help="load this build of libhf6d.so instead (timing experiments)")
     a = ap.parse_args()
+    if a.lib:
+        from object_detector_6d_b200 import build as _b
+        _b.build_lib = lambda *x, **k: os.path.abspath(a.lib)
     with tempfile.TemporaryDirectory() as d:
         frames, layers, forest_dir, wpath, stats = bench.make_workload(d, a.distinct, T=a.trees)
         det = api.Detector(forest_dir, wpath, api.default_params(fill_random=1, fill_seed=1), device=0, n_slots=1)
