@@ -172,7 +172,7 @@ def run_cuda(args, rank, world, local_rank):
     with tempfile.TemporaryDirectory() as d:
         frames, layers, forest_dir, wpath, stats = make_workload(d, DISTINCT_FRAMES)
         p = api.default_params(fill_random=1, fill_seed=1)
-        n_slots = 4
+        n_slots = args.slots
         det = api.Detector(forest_dir, wpath, p, device=local_rank, n_slots=n_slots)
 
         # ---- device-resident inputs
@@ -434,6 +434,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--slots", type=int, default=4, help="frames in flight (one stream + workspace each)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -424,15 +424,19 @@ inline cudaError_t launch_encoder_layer_t(const EncoderLayerLaunch& L, const int
     X(0, 2, 256, false, 4, 2, 2, 128, 8)  /* 60.1 */               \
     X(0, 3, 256, false, 4, 2, 2, 64, 16)  /* 59.6 */               \
     X(0, 4, 256, false, 6, 1, 2, 64, 8)   /* 63.7 */               \
+    X(0, 5, 256, false, 4, 1, 2, 128, 8)                           \
     X(1, 0, 256, false, 6, 1, 2, 64, 8)   /* 129.0 */              \
     X(1, 1, 256, false, 4, 1, 1, 64, 8)   /* 151.6 */              \
     X(1, 2, 256, false, 5, 2, 2, 64, 8)   /* 135.1 */              \
     X(1, 3, 256, false, 4, 2, 2, 128, 8)  /* 146.2 */              \
+    X(1, 4, 256, false, 5, 1, 2, 64, 8)                            \
     X(2, 0, 160, true, 7, 1, 2, 128, 8)   /* 98.3 */               \
     X(2, 1, 160, true, 4, 2, 1, 128, 8)   /* 118.8 */              \
     X(2, 2, 160, true, 5, 2, 2, 128, 8)   /* 104.5 */              \
     X(2, 3, 160, true, 7, 2, 2, 64, 8)    /* 98.5 */               \
     X(2, 4, 160, true, 4, 2, 2, 128, 12)  /* 122.9 */              \
+    X(2, 5, 160, true, 6, 1, 2, 128, 8)                            \
+    X(2, 6, 160, true, 5, 1, 2, 128, 8)                            \
     X(3, 0, 256, true, 4, 2, 2, 64, 8)                             \
     X(3, 1, 256, true, 4, 1, 1, 64, 8)
 

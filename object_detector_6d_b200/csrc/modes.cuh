@@ -61,6 +61,8 @@ clear_accumulators_kernel(const __grid_constant__ ClearPlan plan) {
 
 // ------------------------------------------------------------------------------------------------ box blur
 constexpr int BLUR_WARPS = 4;
+constexpr int ROW_BATCH = 4;   // 32-column groups loaded together by the row pass
+constexpr int COL_BATCH = 8;   // rows loaded together while the column pass builds its first window sum
 
 // tmp[m][r][c] = sum_k acc[m][r][reflect(c - kx/2 + k)]   for r in in.rows, c in out.cols  (tmp is in.nr x out.nc)
 __global__ void __launch_bounds__(BLUR_WARPS * 32)
@@ -76,16 +78,25 @@ box_rows_kernel(const unsigned long long* __restrict__ acc, unsigned long long* 
     const unsigned long long* src = acc + ((size_t)m * in.nr + r) * in.nc;
     unsigned long long carry = 0;
     if (lane == 0) pre[0] = 0;
-    for (int c0 = 0; c0 < in.nc; c0 += 32) {
-        const int c = c0 + lane;
-        unsigned long long v = c < in.nc ? src[c] : 0ull;
+    for (int c0 = 0; c0 < in.nc; c0 += 32 * ROW_BATCH) {  // ROW_BATCH independent loads in flight per lane, then the scans
+        unsigned long long vv[ROW_BATCH];
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned long long n = __shfl_up_sync(0xffffffffu, v, o);
-            if (lane >= o) v += n;
+        for (int j = 0; j < ROW_BATCH; ++j) {
+            const int c = c0 + j * 32 + lane;
+            vv[j] = c < in.nc ? src[c] : 0ull;
         }
-        if (c < in.nc) pre[c + 1] = carry + v;
-        carry += __shfl_sync(0xffffffffu, v, 31);
+#pragma unroll
+        for (int j = 0; j < ROW_BATCH; ++j) {
+            const int c = c0 + j * 32 + lane;
+            unsigned long long v = vv[j];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned long long n = __shfl_up_sync(0xffffffffu, v, o);
+                if (lane >= o) v += n;
+            }
+            if (c < in.nc) pre[c + 1] = carry + v;
+            carry += __shfl_sync(0xffffffffu, v, 31);
+        }
     }
     __syncwarp();
     auto seg = [&](int a, int b) -> unsigned long long {  // sum over global columns [a, b], clipped to the input rectangle
@@ -145,7 +156,13 @@ box_cols_kernel(const unsigned long long* __restrict__ tmp, float* __restrict__ 
     unsigned long long s = 0;
     {
         const int a = out.r0 + rbeg - ky / 2;
-        for (int k = 0; k < ky; ++k) s += at(a + k);
+        for (int k0 = 0; k0 < ky; k0 += COL_BATCH) {  // batches of independent loads (a plain loop waits for every one)
+            unsigned long long v[COL_BATCH];
+#pragma unroll
+            for (int i = 0; i < COL_BATCH; ++i) v[i] = k0 + i < ky ? at(a + k0 + i) : 0ull;
+#pragma unroll
+            for (int i = 0; i < COL_BATCH; ++i) s += v[i];
+        }
     }
     for (int r0 = rbeg; r0 < rend; r0 += NMS_BLOCK) {  // one block row at a time: its 16 loads are issued together
         unsigned long long add[NMS_BLOCK], sub[NMS_BLOCK];
@@ -203,6 +220,7 @@ __host__ __device__ __forceinline__ BlockGrid make_block_grid(MapRect R) {
 // Window origins (left, top) in global coordinates: left in [left0, left0+n_left), top in [top0, top0+n_top).
 // Emits sort keys (score | ~x | ~y) into list[m].
 constexpr int NMS_SELECT_THREADS = 64;
+constexpr int NMS_ROW_BATCH = 6;      // block maxima of one block row fetched together (a 40-wide window spans <= 6 blocks)
 constexpr int NMS_VERIFY_LOADS = 16;  // window elements per lane in flight during the exact verification
 __global__ void __launch_bounds__(NMS_SELECT_THREADS)
 nms_select_kernel(const float* __restrict__ in, const unsigned long long* __restrict__ bmax, MapRect R, int wx, int wy,
@@ -261,13 +279,20 @@ nms_select_kernel(const float* __restrict__ in, const unsigned long long* __rest
                 nj = j1 - j0 + 1;
                 const bool fits = nj * (i1 - i0 + 1) <= 64;
                 for (int i = i0; i <= i1 && alive; ++i)
-                    for (int j = j0; j <= j1; ++j) {
-                        const unsigned long long k = bm[(size_t)i * bg.bx + j];
-                        if (k <= mine) continue;
-                        const int ky = 0xFFFF - (int)((k >> 16) & 0xFFFFu), kx = 0xFFFF - (int)(k & 0xFFFFu);
-                        if (ky >= wy_lo && ky <= wy_hi && kx >= wx_lo && kx <= wx_hi) { alive = false; break; }
-                        if (fits) suspects |= 1ull << ((i - i0) * nj + (j - j0));
-                        else scan_all = true;
+                    for (int jb = j0; jb <= j1 && alive; jb += NMS_ROW_BATCH) {  // a batch of independent loads per step
+                        unsigned long long kk[NMS_ROW_BATCH];
+#pragma unroll
+                        for (int u = 0; u < NMS_ROW_BATCH; ++u) kk[u] = jb + u <= j1 ? bm[(size_t)i * bg.bx + jb + u] : 0ull;
+#pragma unroll
+                        for (int u = 0; u < NMS_ROW_BATCH; ++u) {
+                            const unsigned long long k = kk[u];
+                            const int j = jb + u;
+                            if (!alive || j > j1 || k <= mine) continue;
+                            const int ky = 0xFFFF - (int)((k >> 16) & 0xFFFFu), kx = 0xFFFF - (int)(k & 0xFFFFu);
+                            if (ky >= wy_lo && ky <= wy_hi && kx >= wx_lo && kx <= wx_hi) { alive = false; continue; }
+                            if (fits) suspects |= 1ull << ((i - i0) * nj + (j - j0));
+                            else scan_all = true;
+                        }
                     }
             } else if (alive) {
                 scan_all = true;
@@ -491,7 +516,13 @@ roll_modes_kernel(const unsigned long long* __restrict__ racc, const int* __rest
     const double scale = 1.0 / (double)blur;
     for (int i = threadIdx.x; i < NB; i += blockDim.x) {
         unsigned long long sum = 0;
-        for (int k = 0; k < blur; ++k) sum += s_acc[reflect101(i - blur / 2 + k, NB)];
+        const int a = i - blur / 2;
+        if (a >= 0 && a + blur <= NB) {  // interior bins: no border reflection
+#pragma unroll 5
+            for (int k = 0; k < blur; ++k) sum += s_acc[a + k];
+        } else {
+            for (int k = 0; k < blur; ++k) sum += s_acc[reflect101(a + k, NB)];
+        }
         s_blur[i] = (float)(((double)sum / 65536.0) * scale);
     }
     __syncthreads();
