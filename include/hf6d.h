@@ -158,6 +158,20 @@ int hf6d_set_tree_shard(hf6d_ctx* c, int rank, int world);
  * only for classes k with k % world == rank; votes are still cast for every detected class.  The hypothesis lists of
  * the ranks, concatenated in class order, equal the unsharded list. */
 int hf6d_set_class_shard(hf6d_ctx* c, int rank, int world);
+/* Peer exchange: the tree-sharded mode without a collective library, for the GPUs of one NVLink / NVSwitch box (one
+ * process per GPU).  Every rank publishes a small blob (CUDA IPC handles of its vote maps, leaf tables and flag block),
+ * the caller hands every rank all blobs (any transport: torch.distributed all_gather, MPI, a file), and from then on
+ * hf6d_run exchanges nothing through the host: the kernels after the exchange point read the peers' maps and leaf tables
+ * in place over NVLink, and the ranks synchronise through flags in each other's memory (see "peer exchange" in
+ * csrc/hf6d_api.cu).  hf6d_peer_attach also sets the tree shard and the class shard to rank/world.  Every rank must then
+ * run the same frames on the same slots (whole frames, or SCAN..VOTE followed by CENTRES..POSE).  Replaces the
+ * reference's merge of per-thread vote maps and leaf lists, HoughForest/src/HFTest.cpp:645-654, across GPUs. */
+#define HF6D_MAX_SLOTS 16
+size_t hf6d_peer_blob_bytes(void);
+int hf6d_peer_export(hf6d_ctx* c, void* blob, size_t cap_bytes);
+int hf6d_peer_attach(hf6d_ctx* c, int rank, int world, const void* blobs /* world blobs, rank order */, size_t bytes_each);
+int hf6d_peer_detach(hf6d_ctx* c);
+int hf6d_peer_timed_out(hf6d_ctx* c); /* 1 if a flag wait gave up (fallback wait kernel only); results are then invalid */
 /* Encoder arithmetic: 0 = bf16 operands (default), 1 = split-bf16 (hi+lo operands, 3 MMAs per product, ~fp32). */
 int hf6d_set_encoder_mode(hf6d_ctx* c, int mode);
 int hf6d_set_debug_capture(hf6d_ctx* c, int on); /* keep HF6D_BUF_PATCH_U8 */

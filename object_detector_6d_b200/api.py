@@ -24,7 +24,8 @@ MAX_CENTRES = 16
 EXPORTS = (
     "hf6d_default_params", "hf6d_create", "hf6d_create_from_options", "hf6d_destroy", "hf6d_last_error",
     "hf6d_get_params", "hf6d_model", "hf6d_set_objects", "hf6d_get_objects", "hf6d_set_fill_seed",
-    "hf6d_set_tree_shard", "hf6d_set_class_shard", "hf6d_set_encoder_mode", "hf6d_set_debug_capture", "hf6d_detect", "hf6d_submit",
+    "hf6d_set_tree_shard", "hf6d_set_class_shard", "hf6d_peer_blob_bytes", "hf6d_peer_export", "hf6d_peer_attach",
+    "hf6d_peer_detach", "hf6d_peer_timed_out", "hf6d_set_encoder_mode", "hf6d_set_debug_capture", "hf6d_detect", "hf6d_submit",
     "hf6d_wait", "hf6d_host_alloc", "hf6d_host_free", "hf6d_upload", "hf6d_run", "hf6d_sync", "hf6d_collect",
     "hf6d_fetch", "hf6d_inject", "hf6d_device_ptr", "hf6d_set_stream", "hf6d_stage_ms", "hf6d_launch_count",
     "hf6d_pose_from_tuple", "hf6d_bind_frame", "hf6d_encoder_layer_ms", "hf6d_result_bytes",
@@ -102,6 +103,12 @@ def load():
     L.hf6d_set_fill_seed.argtypes = [vp, C.c_uint64]
     L.hf6d_set_tree_shard.argtypes = [vp, i32, i32]
     L.hf6d_set_class_shard.argtypes = [vp, i32, i32]
+    L.hf6d_peer_blob_bytes.argtypes = []
+    L.hf6d_peer_blob_bytes.restype = C.c_size_t
+    L.hf6d_peer_export.argtypes = [vp, vp, C.c_size_t]
+    L.hf6d_peer_attach.argtypes = [vp, i32, i32, vp, C.c_size_t]
+    L.hf6d_peer_detach.argtypes = [vp]
+    L.hf6d_peer_timed_out.argtypes = [vp]
     L.hf6d_set_encoder_mode.argtypes = [vp, i32]
     L.hf6d_set_debug_capture.argtypes = [vp, i32]
     L.hf6d_detect.argtypes = [vp, vp, vp, vp, i32, C.POINTER(i32)]
@@ -278,6 +285,28 @@ class Detector:
 
     def set_class_shard(self, rank: int, world: int):
         self._ck(self._L.hf6d_set_class_shard(self._h, rank, world))
+
+    # ------------------------------------------------------------------ peer exchange (tree-sharded mode over NVLink)
+    def peer_export(self) -> bytes:
+        """This rank's blob (CUDA IPC handles of its vote maps, leaf tables and flag block)."""
+        n = int(self._L.hf6d_peer_blob_bytes())
+        buf = C.create_string_buffer(n)
+        self._ck(self._L.hf6d_peer_export(self._h, buf, n))
+        return buf.raw
+
+    def peer_attach(self, rank: int, world: int, blobs):
+        """Map the peers' buffers; `blobs` = every rank's peer_export(), in rank order."""
+        blobs = [bytes(b) for b in blobs]
+        if len(blobs) != world or len({len(b) for b in blobs}) != 1:
+            raise ValueError("need one blob of equal size per rank")
+        joined = C.create_string_buffer(b"".join(blobs), len(blobs[0]) * world)
+        self._ck(self._L.hf6d_peer_attach(self._h, rank, world, joined, len(blobs[0])))
+
+    def peer_detach(self):
+        self._ck(self._L.hf6d_peer_detach(self._h))
+
+    def peer_timed_out(self) -> bool:
+        return bool(self._L.hf6d_peer_timed_out(self._h))
 
     def set_debug_capture(self, on: bool):
         self._ck(self._L.hf6d_set_debug_capture(self._h, int(on)))

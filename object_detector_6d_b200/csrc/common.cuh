@@ -47,6 +47,8 @@ __device__ __forceinline__ int f2i_x86(float y) {
 // remainder, one FMA to correct.  Bit-identical to x / Y for every x with |x| in [1e-30, 1e30) and for x = +0 (checked
 // exhaustively over all 2^32 floats for Y = 3, 64, 192, 255, 1000, 0.01 by tools/check_const_division.c); callers
 // guarantee the range, or only use the truncated integer part (tiny / huge / infinite x then give the same integer).
+constexpr int HF6D_MAX_PEERS = 8;  // ranks of a tree-sharded group on one NVLink / NVSwitch box
+
 template <int NUM, int DEN>
 __device__ __forceinline__ float div_const(float x) {
     constexpr float Y = (float)NUM / (float)DEN;

@@ -80,6 +80,7 @@ struct Slot {
     uint8_t* res_dev = nullptr;
     uint8_t* res_host = nullptr;  // pinned
     EncoderLayerLaunch enc[3];
+    uint32_t peer_seq = 0;  // frames this slot has pushed through the peer exchange (both flags carry it)
     bool busy = false;  // submit/wait bookkeeping
     int ticket = -1;
     std::vector<void*> allocs;
@@ -110,6 +111,15 @@ struct hf6d_ctx {
     int entry_cap = 0;           // capacity of a frame slot's window-entry list (entries beyond it are accumulated in place)
     int shard_rank = 0, shard_world = 1;
     int class_rank = 0, class_world = 1;  // centres + pose only for classes k % class_world == class_rank
+    // peer exchange (tree-sharded mode over NVLink peer memory, hf6d_peer_attach)
+    bool peer_on = false;
+    int peer_rank = 0, peer_world = 1;
+    uint32_t* peer_flags = nullptr;                                   // own flag block [n_slots][2][HF6D_MAX_PEERS]
+    uint32_t* peer_flags_of[HF6D_MAX_PEERS] = {};                     // every rank's flag block (own entry = own block)
+    std::vector<const unsigned long long*> peer_maps[HF6D_MAX_PEERS]; // [rank][slot]
+    std::vector<const int*> peer_leaf[HF6D_MAX_PEERS];                // [rank][slot]
+    std::vector<void*> peer_opened;                                   // cudaIpcOpenMemHandle results
+    int* peer_timeout = nullptr;                                      // set by the fallback wait kernel when it gives up
     int encoder_mode = 0;
     // per encoder layer: row of HF6D_ENC_CONFIGS within the layer's shape class (0 = default: CTA pairs, cta_group::2;
     // 1 = stand-alone CTAs).  Tuning switch: HF6D_ENC_VARIANT="a,b,c".
@@ -397,6 +407,110 @@ ResView view_of(const hf6d_ctx* c, uint8_t* base) {
         ++(s).launches;                                                                                     \
     } while (0)
 
+// ------------------------------------------------------------------------------------------------ peer exchange
+// Tree-sharded mode without a collective library.  Every rank maps its peers' vote maps, leaf tables and a small flag
+// block (CUDA IPC); the first kernels after the exchange point read the peers' buffers in place over NVLink
+// (box_rows_kernel sums the ranks' maps of this rank's classes as it loads them, window_entries_kernel reads a tree's leaf
+// ordinals from the rank that traversed it).  What is left of the "collective" is its synchronisation, two flags per
+// (slot, rank), each written REMOTELY by a one-warp kernel and waited for LOCALLY by a stream memory operation
+// (cuStreamWaitValue32: no SM, no spinning kernel):
+//   ready[slot][r]    = n : rank r has finished traverse + vote of its n-th frame on this slot      (r -> everyone)
+//   consumed[slot][r] = n : rank r has finished every kernel that reads its peers' n-th frame       (r -> everyone)
+// Order on a slot's stream:  wait consumed >= n-1 | traverse, vote | write ready = n | wait ready >= n | centres, pose |
+// write consumed = n.  Every wait depends only on work the peer enqueued BEFORE its own next wait, so the ranks cannot
+// wait for each other in a cycle as long as every rank runs the same frames on the same slots.
+constexpr int PEER_FLAG_READY = 0, PEER_FLAG_CONSUMED = 1;
+inline size_t peer_flag_index(int slot, int kind, int rank) { return ((size_t)slot * 2 + kind) * HF6D_MAX_PEERS + rank; }
+
+struct PeerTargets {
+    uint32_t* p[HF6D_MAX_PEERS];
+    int n;
+};
+__global__ void peer_signal_kernel(const __grid_constant__ PeerTargets t, uint32_t value) {
+    if ((int)threadIdx.x < t.n) {
+        __threadfence_system();  // everything this stream wrote before is visible to whoever sees the flag
+        *reinterpret_cast<volatile uint32_t*>(t.p[threadIdx.x]) = value;
+    }
+}
+// Fallback when the driver offers no stream memory operations: a one-warp spinning kernel with a bounded wait.
+__global__ void peer_wait_kernel(const uint32_t* flags, int n, uint32_t value, int* timed_out) {
+    if ((int)threadIdx.x >= n) return;
+    const volatile uint32_t* f = flags + threadIdx.x;
+    for (long long spin = 0; spin < (1ll << 24); ++spin) {
+        if ((int32_t)(*f - value) >= 0) { __threadfence_system(); return; }
+        __nanosleep(200);
+    }
+    *timed_out = 1;
+}
+
+typedef CUresult (*PFN_streamWaitValue32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+inline PFN_streamWaitValue32 get_stream_wait_value() {
+    static PFN_streamWaitValue32 fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        const char* mode = getenv("HF6D_PEER_WAIT");
+        if (mode && !strcmp(mode, "kernel")) return nullptr;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_streamWaitValue32>(p);
+    }
+    return fn;
+}
+
+int peer_signal(hf6d_ctx* c, Slot& s, int slot, int kind, uint32_t value) {
+    PeerTargets t;
+    memset(&t, 0, sizeof t);
+    for (int r = 0; r < c->peer_world; ++r)
+        if (r != c->peer_rank) t.p[t.n++] = c->peer_flags_of[r] + peer_flag_index(slot, kind, c->peer_rank);
+    if (!t.n) return HF6D_OK;
+    peer_signal_kernel<<<1, 32, 0, s.stream>>>(t, value);
+    CU_TRY(c, cudaGetLastError());
+    ++s.launches;
+    return HF6D_OK;
+}
+
+int peer_wait(hf6d_ctx* c, Slot& s, int slot, int kind, uint32_t value) {
+    PFN_streamWaitValue32 wait = get_stream_wait_value();
+    for (int r = 0; r < c->peer_world; ++r) {
+        if (r == c->peer_rank) continue;
+        uint32_t* flag = c->peer_flags + peer_flag_index(slot, kind, r);
+        if (wait) {
+            const CUresult e = wait(reinterpret_cast<CUstream>(s.stream), reinterpret_cast<CUdeviceptr>(flag), value,
+                                    CU_STREAM_WAIT_VALUE_GEQ);
+            if (e != CUDA_SUCCESS) return fail(c, HF6D_ECUDA, "cuStreamWaitValue32 failed (%d)", (int)e);
+        } else {
+            peer_wait_kernel<<<1, 32, 0, s.stream>>>(flag, 1, value, c->peer_timeout);
+            CU_TRY(c, cudaGetLastError());
+            ++s.launches;
+        }
+    }
+    return HF6D_OK;
+}
+
+inline int slot_index(const hf6d_ctx* c, const Slot& s) { return (int)(&s - c->slots.data()); }
+PeerMaps peer_maps_of(const hf6d_ctx* c, int slot) {
+    PeerMaps pm;
+    memset(&pm, 0, sizeof pm);
+    if (c->peer_on)
+        for (int r = 0; r < c->peer_world; ++r)
+            if (r != c->peer_rank) pm.base[pm.n++] = c->peer_maps[r][slot];
+    return pm;
+}
+LeafTables leaf_tables_of(const hf6d_ctx* c, const Slot& s, int slot) {
+    LeafTables lt;
+    memset(&lt, 0, sizeof lt);
+    lt.base[0] = s.leaf_ord;
+    lt.world = 1;
+    if (c->peer_on) {
+        lt.world = c->peer_world;
+        for (int r = 0; r < c->peer_world; ++r) lt.base[r] = r == c->peer_rank ? s.leaf_ord : c->peer_leaf[r][slot];
+    }
+    return lt;
+}
+
 int run_stage(hf6d_ctx* c, Slot& s, int stage) {
     const FrameGeom& g = c->g;
     const DevForest& f = c->dm.f;
@@ -468,7 +582,8 @@ int run_stage(hf6d_ctx* c, Slot& s, int stage) {
             const MapRect full{0, 0, g.H, g.W};
             const int kb = p.centers_blur_size, w = p.centers_nms_wsize;
             box_rows_kernel<<<dim3((g.H + BLUR_WARPS - 1) / BLUR_WARPS, K), BLUR_WARPS * 32,
-                              (size_t)BLUR_WARPS * (g.W + 1) * 8, st>>>(s.maps, s.map_tmp, md, full, full, kb, c->dm.class_mask);
+                              (size_t)BLUR_WARPS * (g.W + 1) * 8, st>>>(s.maps, s.map_tmp, md, full, full, kb, c->dm.class_mask,
+                                                                        peer_maps_of(c, slot_index(c, s)));
             LAUNCH_CHECK(c, s);
             box_cols_kernel<<<dim3((g.W + 127) / 128, (g.H + BLUR_COL_CHUNK - 1) / BLUR_COL_CHUNK, K), 128, 0, st>>>(
                 s.map_tmp, s.blurred, md, full, full, kb, 1.0 / ((double)kb * kb), c->dm.class_mask, s.bmax);
@@ -525,7 +640,8 @@ int run_stage(hf6d_ctx* c, Slot& s, int stage) {
                 // through list_n[n_lists + 1] (both zeroed above)
                 int* ctr = s.list_n + std::max(K, S);
                 const int wc_blocks = (int)std::min<long long>((items + VOTE_THREADS - 1) / VOTE_THREADS, (long long)c->sms * c->wc_ctas_per_sm);
-                window_entries_kernel<<<wc_blocks, VOTE_THREADS, cell_bytes, st>>>(f, g, switches_of(c, true), s.locs, s.depth, s.leaf_ord,
+                window_entries_kernel<<<wc_blocks, VOTE_THREADS, cell_bytes, st>>>(f, g, switches_of(c, true), s.locs, s.depth,
+                                                                                 leaf_tables_of(c, s, slot_index(c, s)),
                                                                                  s.counts, ct, half_win, n_groups, ctr, s.entries,
                                                                                  c->entry_cap, ctr + 1, s.win_cnt, s.zacc);
                 LAUNCH_CHECK(c, s);
@@ -559,7 +675,8 @@ int run_stage(hf6d_ctx* c, Slot& s, int stage) {
             const MapRect rout = c->yp_blur;
             const int kb = p.pose_blur_size, w = p.pose_nms_wsize;
             box_rows_kernel<<<dim3((rin.nr + BLUR_WARPS - 1) / BLUR_WARPS, S), BLUR_WARPS * 32,
-                              (size_t)BLUR_WARPS * (rin.nc + 1) * 8, st>>>(s.ypacc, s.yptmp, md, rin, rout, kb, rv.active);
+                              (size_t)BLUR_WARPS * (rin.nc + 1) * 8, st>>>(s.ypacc, s.yptmp, md, rin, rout, kb, rv.active,
+                                                                           PeerMaps{{}, 0});
             LAUNCH_CHECK(c, s);
             box_cols_kernel<<<dim3((rout.nc + 127) / 128, (rout.nr + BLUR_COL_CHUNK - 1) / BLUR_COL_CHUNK, S), 128, 0, st>>>(
                 s.yptmp, s.ypblur, md, rin, rout, kb, 1.0 / ((double)kb * kb), rv.active, s.bmax);
@@ -596,9 +713,17 @@ int run_range(hf6d_ctx* c, Slot& s, int first, int last) {
     for (int i = 0; i <= HF6D_STAGE_COUNT; ++i) s.ev_valid[i] = false;
     CU_TRY(c, cudaEventRecord(s.ev[first], s.stream));
     s.ev_valid[first] = true;
+    const int slot = slot_index(c, s);
     for (int st = first; st <= last; ++st) {
-        int r = run_stage(c, s, st);
-        if (r) return r;
+        int r;
+        if (c->peer_on && st == HF6D_STAGE_TRAVERSE) {  // the peers must be done with this slot's previous frame
+            if ((r = peer_wait(c, s, slot, PEER_FLAG_CONSUMED, s.peer_seq))) return r;
+            ++s.peer_seq;
+        }
+        if (c->peer_on && st == HF6D_STAGE_CENTRES && (r = peer_wait(c, s, slot, PEER_FLAG_READY, s.peer_seq))) return r;
+        if ((r = run_stage(c, s, st))) return r;
+        if (c->peer_on && st == HF6D_STAGE_VOTE && (r = peer_signal(c, s, slot, PEER_FLAG_READY, s.peer_seq))) return r;
+        if (c->peer_on && st == HF6D_STAGE_POSE && (r = peer_signal(c, s, slot, PEER_FLAG_CONSUMED, s.peer_seq))) return r;
         CU_TRY(c, cudaEventRecord(s.ev[st + 1], s.stream));
         s.ev_valid[st + 1] = true;
     }
@@ -978,6 +1103,9 @@ void hf6d_destroy(hf6d_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
+    if (c->peer_on || !c->peer_opened.empty()) hf6d_peer_detach(c);
+    if (c->peer_flags) cudaFree(c->peer_flags);
+    if (c->peer_timeout) cudaFree(c->peer_timeout);
     free_all(c);
     delete c;
 }
@@ -1038,6 +1166,119 @@ int hf6d_set_class_shard(hf6d_ctx* c, int rank, int world) {
     c->class_rank = rank;
     c->class_world = world;
     return upload_class_mask(c);
+}
+
+namespace {
+struct PeerBlob {  // what a rank publishes: POD, exchanged by the caller (torch.distributed all_gather, MPI, a file ...)
+    uint32_t magic;
+    int32_t n_slots, W, H, K, T, cap, device;
+    cudaIpcMemHandle_t flags;
+    cudaIpcMemHandle_t maps[HF6D_MAX_SLOTS];
+    cudaIpcMemHandle_t leaf[HF6D_MAX_SLOTS];
+};
+constexpr uint32_t PEER_MAGIC = 0x36644650u;  // "PFd6"
+}  // namespace
+
+size_t hf6d_peer_blob_bytes(void) { return sizeof(PeerBlob); }
+
+int hf6d_peer_export(hf6d_ctx* c, void* blob, size_t cap_bytes) {
+    if (!c || !blob) return HF6D_EINVAL;
+    if (cap_bytes < sizeof(PeerBlob)) return fail(c, HF6D_EINVAL, "peer blob needs %zu bytes", sizeof(PeerBlob));
+    if (c->n_slots > HF6D_MAX_SLOTS) return fail(c, HF6D_EINVAL, "peer exchange supports at most %d slots", HF6D_MAX_SLOTS);
+    CU_TRY(c, cudaSetDevice(c->device));
+    if (!c->peer_flags) {
+        const size_t n = (size_t)c->n_slots * 2 * HF6D_MAX_PEERS;
+        CU_TRY(c, cudaMalloc(reinterpret_cast<void**>(&c->peer_flags), n * 4));
+        CU_TRY(c, cudaMemset(c->peer_flags, 0, n * 4));
+        CU_TRY(c, cudaMalloc(reinterpret_cast<void**>(&c->peer_timeout), 4));
+        CU_TRY(c, cudaMemset(c->peer_timeout, 0, 4));
+    }
+    PeerBlob b;
+    memset(&b, 0, sizeof b);
+    b.magic = PEER_MAGIC;
+    b.n_slots = c->n_slots; b.W = c->g.W; b.H = c->g.H; b.K = c->hf.K; b.T = c->hf.T; b.cap = c->g.cap; b.device = c->device;
+    CU_TRY(c, cudaIpcGetMemHandle(&b.flags, c->peer_flags));
+    for (int i = 0; i < c->n_slots; ++i) {
+        CU_TRY(c, cudaIpcGetMemHandle(&b.maps[i], c->slots[i].maps));
+        CU_TRY(c, cudaIpcGetMemHandle(&b.leaf[i], c->slots[i].leaf_ord));
+    }
+    memcpy(blob, &b, sizeof b);
+    return HF6D_OK;
+}
+
+int hf6d_peer_detach(hf6d_ctx* c) {
+    if (!c) return HF6D_EINVAL;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    for (void* p : c->peer_opened) cudaIpcCloseMemHandle(p);
+    c->peer_opened.clear();
+    for (int r = 0; r < HF6D_MAX_PEERS; ++r) {
+        c->peer_maps[r].clear();
+        c->peer_leaf[r].clear();
+        c->peer_flags_of[r] = nullptr;
+    }
+    c->peer_on = false;
+    c->peer_world = 1;
+    c->peer_rank = 0;
+    return HF6D_OK;
+}
+
+int hf6d_peer_attach(hf6d_ctx* c, int rank, int world, const void* blobs, size_t bytes_each) {
+    if (!c || !blobs) return HF6D_EINVAL;
+    if (world < 2 || world > HF6D_MAX_PEERS || rank < 0 || rank >= world) return fail(c, HF6D_EINVAL, "bad peer group %d/%d", rank, world);
+    if (bytes_each != sizeof(PeerBlob)) return fail(c, HF6D_EINVAL, "peer blob size %zu, expected %zu", bytes_each, sizeof(PeerBlob));
+    if (!c->peer_flags) return fail(c, HF6D_ESTATE, "hf6d_peer_export must be called before hf6d_peer_attach");
+    if (c->peer_on) hf6d_peer_detach(c);
+    CU_TRY(c, cudaSetDevice(c->device));
+    const PeerBlob* all = static_cast<const PeerBlob*>(blobs);
+    for (int r = 0; r < world; ++r) {
+        const PeerBlob& b = all[r];
+        if (b.magic != PEER_MAGIC || b.n_slots != c->n_slots || b.W != c->g.W || b.H != c->g.H || b.K != c->hf.K ||
+            b.T != c->hf.T || b.cap != c->g.cap)
+            return fail(c, HF6D_EINVAL, "rank %d runs a different configuration (slots / frame size / forest)", r);
+    }
+    for (int r = 0; r < world; ++r) {
+        c->peer_maps[r].assign(c->n_slots, nullptr);
+        c->peer_leaf[r].assign(c->n_slots, nullptr);
+        if (r == rank) {
+            c->peer_flags_of[r] = c->peer_flags;
+            continue;
+        }
+        const PeerBlob& b = all[r];
+        if (b.device != c->device) {
+            int can = 0;
+            CU_TRY(c, cudaDeviceCanAccessPeer(&can, c->device, b.device));
+            if (!can) return fail(c, HF6D_ECUDA, "device %d cannot access device %d (no NVLink / P2P path)", c->device, b.device);
+        }
+        void* p = nullptr;
+        CU_TRY(c, cudaIpcOpenMemHandle(&p, b.flags, cudaIpcMemLazyEnablePeerAccess));
+        c->peer_opened.push_back(p);
+        c->peer_flags_of[r] = static_cast<uint32_t*>(p);
+        for (int i = 0; i < c->n_slots; ++i) {
+            CU_TRY(c, cudaIpcOpenMemHandle(&p, b.maps[i], cudaIpcMemLazyEnablePeerAccess));
+            c->peer_opened.push_back(p);
+            c->peer_maps[r][i] = static_cast<const unsigned long long*>(p);
+            CU_TRY(c, cudaIpcOpenMemHandle(&p, b.leaf[i], cudaIpcMemLazyEnablePeerAccess));
+            c->peer_opened.push_back(p);
+            c->peer_leaf[r][i] = static_cast<const int*>(p);
+        }
+    }
+    c->peer_rank = rank;
+    c->peer_world = world;
+    c->peer_on = true;
+    for (Slot& s : c->slots) s.peer_seq = 0;
+    CU_TRY(c, cudaMemset(c->peer_flags, 0, (size_t)c->n_slots * 2 * HF6D_MAX_PEERS * 4));
+    int r;
+    if ((r = hf6d_set_tree_shard(c, rank, world))) return r;
+    return hf6d_set_class_shard(c, rank, world);
+}
+
+int hf6d_peer_timed_out(hf6d_ctx* c) {
+    if (!c || !c->peer_timeout) return 0;
+    int v = 0;
+    cudaSetDevice(c->device);
+    if (cudaMemcpy(&v, c->peer_timeout, 4, cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+    return v;
 }
 
 int hf6d_set_encoder_mode(hf6d_ctx* c, int mode) {

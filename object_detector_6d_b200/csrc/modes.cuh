@@ -64,10 +64,18 @@ constexpr int BLUR_WARPS = 4;
 constexpr int ROW_BATCH = 4;   // 32-column groups loaded together by the row pass
 constexpr int COL_BATCH = 8;   // rows loaded together while the column pass builds its first window sum
 
+// Accumulators of the same layout that live in OTHER GPUs' memory (tree-sharded mode, csrc/hf6d_api.cu "peer exchange"):
+// the row pass adds them to its own while it loads them, so summing the ranks' vote maps over NVLink costs no kernel, no
+// staging buffer and no second pass -- only the maps of the classes this rank seeks ever cross the link.
+struct PeerMaps {
+    const unsigned long long* base[HF6D_MAX_PEERS - 1];
+    int n;
+};
+
 // tmp[m][r][c] = sum_k acc[m][r][reflect(c - kx/2 + k)]   for r in in.rows, c in out.cols  (tmp is in.nr x out.nc)
 __global__ void __launch_bounds__(BLUR_WARPS * 32)
 box_rows_kernel(const unsigned long long* __restrict__ acc, unsigned long long* __restrict__ tmp, MapDims md, MapRect in,
-                MapRect out, int kx, const uint8_t* __restrict__ map_active) {
+                MapRect out, int kx, const uint8_t* __restrict__ map_active, const __grid_constant__ PeerMaps peers) {
     extern __shared__ unsigned long long s_pre[];  // [BLUR_WARPS][in.nc + 1]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m = blockIdx.y;
@@ -84,6 +92,14 @@ box_rows_kernel(const unsigned long long* __restrict__ acc, unsigned long long* 
         for (int j = 0; j < ROW_BATCH; ++j) {
             const int c = c0 + j * 32 + lane;
             vv[j] = c < in.nc ? src[c] : 0ull;
+        }
+        for (int q = 0; q < peers.n; ++q) {  // the other ranks' partial sums of the same cells, read in place
+            const unsigned long long* psrc = peers.base[q] + ((size_t)m * in.nr + r) * in.nc;
+#pragma unroll
+            for (int j = 0; j < ROW_BATCH; ++j) {
+                const int c = c0 + j * 32 + lane;
+                if (c < in.nc) vv[j] += psrc[c];
+            }
         }
 #pragma unroll
         for (int j = 0; j < ROW_BATCH; ++j) {

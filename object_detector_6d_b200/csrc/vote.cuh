@@ -58,9 +58,16 @@ struct WarpItems {
 // Batches are handed out dynamically through a global counter (zeroed before the launch) when `next_batch` is given:
 // the work per batch varies a lot in the pose pass (votes cluster where the objects are), and a static stride leaves
 // most warps idle behind the few that own the busy batches.
+// Leaf tables of the ranks of a tree-sharded group (peer exchange): tree t is read from the table of the rank that
+// traversed it, base[t % world]; world == 1 means "the local table only".  Peer tables live in other GPUs' memory.
+struct LeafTables {
+    const int* base[HF6D_MAX_PEERS];
+    int world;
+};
+
 template <class Body>
 __device__ __forceinline__ void for_each_cast_vote(const DevForest& f, const FrameGeom& g, const int* __restrict__ locs,
-                                                   const uint16_t* __restrict__ depth, const int* __restrict__ leaf_ord,
+                                                   const uint16_t* __restrict__ depth, const LeafTables& lt,
                                                    int n_items, WarpItems& wi, int* next_batch, Body&& body) {
     const int lane = threadIdx.x & 31;
     const int warp0 = (blockIdx.x * VOTE_WARPS + (threadIdx.x >> 5)) * 32;
@@ -76,9 +83,9 @@ __device__ __forceinline__ void for_each_cast_vote(const DevForest& f, const Fra
         float tx = 0.f, ty = 0.f, tz = 0.f;
         const int item = base + lane;
         if (item < n_items) {
-            const int ord = leaf_ord[item];
-            if (ord >= 0) {  // -1: tree owned by another rank
-                const int p = item / f.T, t = item - p * f.T;
+            const int p = item / f.T, t = item - p * f.T;
+            const int ord = lt.base[lt.world > 1 ? t % lt.world : 0][item];
+            if (ord >= 0) {  // -1: tree owned by another rank (and no peer table given)
                 const int2 lv = __ldg(f.leaf_votes + __ldg(f.leaf_base + t) + ord);
                 vbeg = lv.x;
                 vcnt = lv.y;
@@ -121,12 +128,15 @@ __global__ void __launch_bounds__(VOTE_THREADS)
 vote_kernel(DevForest f, FrameGeom g, const __grid_constant__ ObjectSwitches sw, const int* __restrict__ locs,
             const uint16_t* __restrict__ depth, const int* __restrict__ leaf_ord, const int* __restrict__ counts,
             unsigned long long* __restrict__ maps) {
+    LeafTables lt;  // votes are cast for this rank's own trees only: the local table (foreign entries are -1)
+    lt.base[0] = leaf_ord;
+    lt.world = 1;
     __shared__ WarpItems s_items[VOTE_WARPS];
     __shared__ uint8_t s_detect[HF6D_MAX_CLASSES];
     if (threadIdx.x < HF6D_MAX_CLASSES) s_detect[threadIdx.x] = sw.should_detect[threadIdx.x];
     __syncthreads();
     const size_t HW = (size_t)g.H * g.W;
-    for_each_cast_vote(f, g, locs, depth, leaf_ord, counts[1] * f.T, s_items[threadIdx.x >> 5], nullptr,
+    for_each_cast_vote(f, g, locs, depth, lt, counts[1] * f.T, s_items[threadIdx.x >> 5], nullptr,
                        [&](bool valid, int vi, float tx, float ty, float tz) {
                            if (!valid) return;
                            const float4 v = __ldg(f.vote4 + vi);
@@ -217,7 +227,7 @@ constexpr unsigned ENTRY_INVALID = 0xFFFFFFFFu;
 // global atomics, so the result never depends on the capacity.
 __global__ void __launch_bounds__(VOTE_THREADS)
 window_entries_kernel(DevForest f, FrameGeom g, const __grid_constant__ ObjectSwitches sw, const int* __restrict__ locs,
-                      const uint16_t* __restrict__ depth, const int* __restrict__ leaf_ord,
+                      const uint16_t* __restrict__ depth, const __grid_constant__ LeafTables lt,
                       const int* __restrict__ counts, CentreTable ct, int half_win, int n_groups, int* next_batch,
                       uint4* __restrict__ entries, int entry_cap, int* __restrict__ n_reserved,
                       unsigned* __restrict__ cnt /*[S][n_groups]*/, unsigned long long* __restrict__ zacc /*[S][Z_BINS]*/) {
@@ -251,7 +261,7 @@ window_entries_kernel(DevForest f, FrameGeom g, const __grid_constant__ ObjectSw
     const int lane = threadIdx.x & 31;
     int blk_base = 0, blk_used = ENTRY_BLOCK;  // warp-uniform: the block this warp is filling (none yet)
     bool overflow = false;                     // the list is full: accumulate in place from now on
-    for_each_cast_vote(f, g, locs, depth, leaf_ord, counts[1] * f.T, s_items[threadIdx.x >> 5], next_batch,
+    for_each_cast_vote(f, g, locs, depth, lt, counts[1] * f.T, s_items[threadIdx.x >> 5], next_batch,
                        [&](bool valid, int vi, float tx, float ty, float tz) {
         unsigned mask = 0;
         int c = 0, uu = 0, vv = 0;

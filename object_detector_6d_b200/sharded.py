@@ -18,6 +18,12 @@ result whatever N is (the reference's float maps depend on the OpenMP schedule, 
 The exchange runs on the slot's own CUDA stream (NCCL is stream-ordered after the vote kernel; no host sync in between),
 and every frame slot has its own stream, so the exchange of frame i overlaps the encoder of frame i+1.
 `exchange()` itself is backend-agnostic: the CPU test-suite drives it with gloo at world_size 2.
+
+exchange="peer" (GPUs of one NVLink / NVSwitch box) drops the two all-reduces: the ranks map each other's maps and leaf
+tables once (CUDA IPC; torch.distributed only carries the handles), and the first kernels after the exchange point read
+them in place -- the blur's row pass sums the ranks' maps of THIS rank's classes while it loads them (half of a
+reduce-scatter's traffic, no all-gather at all), the pose stage reads a tree's leaf ordinals from the rank that traversed
+it -- with flags in peer memory as the only synchronisation (include/hf6d.h, hf6d_peer_attach).
 """
 from __future__ import annotations
 
@@ -48,7 +54,8 @@ def exchange(maps, leaf_table, group=None):
 class TreeShardedDetector:
     """This rank's libhf6d context plus the exchange.  Construct it on every rank after init_process_group."""
 
-    def __init__(self, forest_dir, weights_path, params=None, device=0, n_slots=2, group=None, shard_classes=True):
+    def __init__(self, forest_dir, weights_path, params=None, device=0, n_slots=2, group=None, shard_classes=True,
+                 exchange="nccl"):
         import torch
         import torch.distributed as dist
         self.torch = torch
@@ -60,6 +67,14 @@ class TreeShardedDetector:
         self.shard_classes = bool(shard_classes) and self.world > 1
         if self.shard_classes:
             self.det.set_class_shard(self.rank, self.world)
+        self.exchange_mode = exchange if self.world > 1 else "none"
+        if self.exchange_mode == "peer":
+            if not self.shard_classes:
+                raise ValueError("the peer exchange shards the classes as well")
+            blobs = [None] * self.world
+            dist.all_gather_object(blobs, self.det.peer_export(), group=group)
+            self.det.peer_attach(self.rank, self.world, blobs)
+            dist.barrier(group=group)  # every rank has mapped every buffer before anyone runs
         self.device = device
         self.streams = [torch.cuda.Stream(device=device) for _ in range(n_slots)]
         self.stream = self.streams[0]
@@ -83,6 +98,10 @@ class TreeShardedDetector:
     def run(self, slot=0):
         """Launch one frame (already uploaded / bound on `slot`) asynchronously on the slot's stream."""
         torch = self.torch
+        if self.exchange_mode == "peer":  # nothing to do here: the kernels read peer memory, flags order the ranks
+            self.det.run(slot, api.STAGE_SCAN, api.STAGE_POSE)
+            self._launches = self.det.launch_count(slot)
+            return
         with torch.cuda.stream(self.streams[slot]):
             self.det.run(slot, api.STAGE_SCAN, api.STAGE_VOTE)
             n = self.det.launch_count(slot)
@@ -111,6 +130,12 @@ class TreeShardedDetector:
         return getattr(self, "_launches", 0)
 
     def close(self):
+        if self.exchange_mode == "peer":
+            import torch.distributed as dist
+            self.torch.cuda.synchronize(self.device)
+            dist.barrier(group=self.group)  # nobody unmaps or frees while a peer may still read
+            self.det.peer_detach()
+            dist.barrier(group=self.group)
         for s in range(self.det.n_slots):
             self.det.set_stream(s, None)
         self._views = []

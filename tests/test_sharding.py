@@ -84,7 +84,7 @@ def test_exchange_with_gloo_world_size_2(tmp_path):
 
 
 # ------------------------------------------------------------------------------------------------ GPU, NCCL
-def _nccl_worker(rank, world, port, tmpdir, out_q):
+def _nccl_worker(rank, world, port, tmpdir, out_q, mode="nccl"):
     sys.path.insert(0, ROOT)
     import torch
     import torch.distributed as dist
@@ -101,16 +101,26 @@ def _nccl_worker(rank, world, port, tmpdir, out_q):
         maps_single = single.fetch(api.BUF_MAPS)
         leaf_single = single.fetch(api.BUF_LEAF_ORD)
         single.close()
-        sd = sharded.TreeShardedDetector(cs["forest_dir"], cs["weights"], p, device=rank, n_slots=2)
+        sd = sharded.TreeShardedDetector(cs["forest_dir"], cs["weights"], p, device=rank, n_slots=2, exchange=mode)
         hyp = sd.detect(cs["bgr"], cs["depth"], slot=1)
+        if mode == "peer":  # several frames through both slots: the flags must keep the ranks in step
+            for i in range(6):
+                again = sd.detect(cs["bgr"], cs["depth"], slot=i % 2)
+                assert len(again) == len(hyp) and all(np.array_equal(again[n], hyp[n]) for n in hyp.dtype.names)
+            assert not sd.det.peer_timed_out()
         maps = sd.det.fetch(api.BUF_MAPS, slot=1)
         leaf = sd.det.fetch(api.BUF_LEAF_ORD, slot=1)
         n_launch = sd.launches_per_frame()
         sd.close()
         same = len(hyp) == len(hyp_single) and len(hyp) > 0 and all(
             np.array_equal(hyp[n], hyp_single[n]) for n in hyp.dtype.names)
-        out_q.put((rank, bool(np.array_equal(maps, maps_single)), bool(np.array_equal(leaf, leaf_single)), same,
-                   n_launch))
+        if mode == "peer":  # the local buffers stay partial: the sums exist only inside the kernels that read the peers
+            mine = sharded.owned_trees(rank, world, leaf_single.shape[1])
+            ok_leaf = bool(np.array_equal(leaf[:, mine], leaf_single[:, mine]))
+            out_q.put((rank, True, ok_leaf, same, n_launch))
+        else:
+            out_q.put((rank, bool(np.array_equal(maps, maps_single)), bool(np.array_equal(leaf, leaf_single)), same,
+                       n_launch))
     finally:
         dist.destroy_process_group()
 
@@ -133,4 +143,26 @@ def test_tree_sharded_nccl_equals_single_gpu(tmp_path):
         assert pr.exitcode == 0
     for rank, ok_maps, ok_leaf, ok_hyp, n_launch in sorted(res):
         assert ok_maps and ok_leaf and ok_hyp, (rank, ok_maps, ok_leaf, ok_hyp)
+        assert n_launch >= 18
+
+
+@pytest.mark.gpu
+def test_tree_sharded_peer_exchange_equals_single_gpu(tmp_path):
+    """The same, with the exchange done by the kernels themselves over peer memory (no NCCL collective on the data path)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, str(tmp_path), q, "peer")) for r in range(2)]
+    for pr in procs:
+        pr.start()
+    res = [q.get(timeout=900) for _ in procs]
+    for pr in procs:
+        pr.join(timeout=120)
+        assert pr.exitcode == 0
+    for rank, ok_maps, ok_leaf, ok_hyp, n_launch in sorted(res):
+        assert ok_leaf and ok_hyp, (rank, ok_leaf, ok_hyp)
         assert n_launch >= 18
