@@ -308,12 +308,92 @@ def run_cuda(args, rank, world, local_rank):
                    "sample": f"{n_s} frames of the batch, all stages, OpenMP on all host cores"}
         det.close()
 
+        def build_line(tree):
+            """The JSON line from everything measured so far (also called by the watchdog of the tree-sharded arm)."""
+            frames_total = BATCH * args.steps * world
+            sec = ms_total * 1e-3
+            fps = frames_total / sec
+            ms_frame = ms_total / (BATCH * args.steps)
+            # stage rooflines from SURVEY.md §8(d)'s algorithmic work per frame
+            Pp = Pp_mean
+            votes_cast = Pp * T_TREES * VOTES
+            alg = {
+                "scan": (640 * 480 * 2 + Pp * 8, "hbm"),
+                "gather": (640 * 480 * 5 + Pp * 512, "hbm"),                 # frame once + bf16 A operand [P'][256]
+                "encode": (Pp * ENC_FLOP_PER_PATCH, "tensor"),
+                "traverse": (Pp * 800 * 4 + Pp * T_TREES * 4, "hbm"),
+                "vote": (Pp * T_TREES * 4 + votes_cast * 12 + K_CLASSES * 640 * 480 * 8, "hbm"),
+                "centres": (K_CLASSES * 640 * 480 * (8 + 4), "hbm"),
+                "pose": (2 * (Pp * T_TREES * 4 + votes_cast * 12), "hbm"),
+            }
+            stages = {}
+            for name, ms in zip(api.STAGE_NAMES, stage_ms):
+                work, bound = alg[name]
+                if ms <= 0:
+                    continue
+                if bound == "tensor":
+                    ach = work / (ms * 1e-3) / 1e12
+                    stages[name] = {"ms": float(ms), "bound": bound, "achieved": ach, "unit": "TFLOP/s", "frac": ach / peaks["tf_sustained"]}
+                else:
+                    ach = work / (ms * 1e-3) / 1e9
+                    stages[name] = {"ms": float(ms), "bound": bound, "achieved": ach, "unit": "GB/s", "frac": ach / peaks["hbm"]}
+            # dominant kernel: encoder layer 2 (K=1536 -> N=1024 padded; algorithmic 1500 x 1000), timed alone in the serial
+            # pass with the SM clock at its maximum -> the burst bf16 peak is the denominator (the sustained figure is for a
+            # kernel inside a long power-limited tensor step; this path spends ~1/3 of a frame on the tensor pipe)
+            l2_flop = 2.0 * Pp * 1500 * 1000
+            l2_ach = l2_flop / (enc_ms[1] * 1e-3) / 1e12 if enc_ms[1] > 0 else 0.0
+            traffic = None
+            try:
+                with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                    traffic = json.load(f).get("encoder_layer_2", {}).get("dram_bytes_per_launch")
+            except Exception:
+                pass
+            roofline = {"kernel": "encoder_layer_kernel<256,false,6,1,2,64,8> (layer 2: 1500->1000, CTA pairs, tcgen05 cta_group::2)",
+                        "bound": "tensor", "achieved": l2_ach,
+                        "peak": peaks["tf_burst"], "unit": "TFLOP/s", "frac": l2_ach / peaks["tf_burst"],
+                        "traffic": traffic, "peak_source": peaks["source"] + " (burst bf16: kernel timed alone, SM clock at max)",
+                        "frac_of_sustained_peak": l2_ach / peaks["tf_sustained"],
+                        "frac_of_nominal_dense_peak": l2_ach / 2250.0,
+                        "note": "achieved counts ALGORITHMIC flops (1500 x 1000 per patch; the kernel multiplies the padded 1536 x 1024); "
+                                "the measured peak is a cuBLAS bf16 GEMM on this pool's B200s, so a fraction near or above 1 means "
+                                "the kernel matches the library's throughput, not that it exceeds the hardware (nominal 2250 TFLOP/s)",
+                        "encoder_layer_ms": [float(x) for x in enc_ms],
+                        "encoder_stage_tflops": float(Pp * ENC_FLOP_PER_PATCH / (sum(enc_ms) * 1e-3) / 1e12) if sum(enc_ms) > 0 else 0.0}
+            e2e_fps = frames_total / e2e_s
+            line = {
+                "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": workload_config(stats, patches_per_frame=Pp, parallelism=f"frames x{world}" if world > 1 else "1 GPU"),
+                "ms_per_frame": ms_frame, "traversals_per_s": fps * Pp * T_TREES,
+                "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "timing": "wall clock around hf6d_submit/hf6d_wait with pinned host frames, device sync both sides",
+                        "hypotheses_per_frame": n_hyp / (BATCH * args.steps)},
+                "gpu_launches": launches,
+                "roofline": roofline, "stages": stages, "stages_note": "serial pass: one frame at a time, sum = %.3f ms/frame; "
+                "`value` runs %d frames in flight on separate streams" % (float(np.sum(stage_ms)), n_slots),
+                "cpu_baseline": cpu, "clocks": clocks,
+            }
+            if tree is not None:
+                line["tree_sharded"] = tree
+            return line
+
         # ---- the north star's multi-GPU mode: trees sharded over the ranks, ONE exchange step per frame (NCCL
         # all-reduce SUM of the Q16 vote maps + MAX of the leaf table), every rank works on the same frames
         tree = None
         if world > 1:
+            import threading
             from object_detector_6d_b200 import sharded
             tree_modes = {}
+            tree_done = threading.Event()
+
+            def watchdog():  # a rank that dies inside the exchange would leave the others waiting on its flags for ever
+                if not tree_done.wait(timeout=args.tree_timeout):
+                    if rank == 0:
+                        print(json.dumps(build_line({"unavailable": "the tree-sharded arm did not finish within %d s" % args.tree_timeout,
+                                                     "exchanges": tree_modes})), flush=True)
+                    os._exit(0)
+            threading.Thread(target=watchdog, daemon=True).start()
             for mode in ("peer", "nccl"):
                 try:
                     sd = sharded.TreeShardedDetector(forest_dir, wpath, p, device=local_rank, n_slots=n_slots, exchange=mode)
@@ -357,6 +437,7 @@ def run_cuda(args, rank, world, local_rank):
                 for s in range(n_slots):
                     sd.det.bind_frame(s, None, None)
                 sd.close()
+            tree_done.set()
             best = max((m for m in tree_modes if "frames_per_s" in tree_modes[m]), key=lambda m: tree_modes[m]["frames_per_s"])
             tree = dict(tree_modes[best])
             tree.update({
@@ -371,72 +452,7 @@ def run_cuda(args, rank, world, local_rank):
                         "pose stage read the other ranks' vote maps / leaf tables in place over NVLink (CUDA IPC, flags in peer "
                         "memory, no collective); 'nccl': all-reduce SUM of the maps + MAX of the leaf table" % n_slots})
 
-    frames_total = BATCH * args.steps * world
-    sec = ms_total * 1e-3
-    fps = frames_total / sec
-    ms_frame = ms_total / (BATCH * args.steps)
-    # stage rooflines from SURVEY.md §8(d)'s algorithmic work per frame
-    Pp = Pp_mean
-    votes_cast = Pp * T_TREES * VOTES
-    alg = {
-        "scan": (640 * 480 * 2 + Pp * 8, "hbm"),
-        "gather": (640 * 480 * 5 + Pp * 512, "hbm"),                 # frame once + bf16 A operand [P'][256]
-        "encode": (Pp * ENC_FLOP_PER_PATCH, "tensor"),
-        "traverse": (Pp * 800 * 4 + Pp * T_TREES * 4, "hbm"),
-        "vote": (Pp * T_TREES * 4 + votes_cast * 12 + K_CLASSES * 640 * 480 * 8, "hbm"),
-        "centres": (K_CLASSES * 640 * 480 * (8 + 4), "hbm"),
-        "pose": (2 * (Pp * T_TREES * 4 + votes_cast * 12), "hbm"),
-    }
-    stages = {}
-    for name, ms in zip(api.STAGE_NAMES, stage_ms):
-        work, bound = alg[name]
-        if ms <= 0:
-            continue
-        if bound == "tensor":
-            ach = work / (ms * 1e-3) / 1e12
-            stages[name] = {"ms": float(ms), "bound": bound, "achieved": ach, "unit": "TFLOP/s", "frac": ach / peaks["tf_sustained"]}
-        else:
-            ach = work / (ms * 1e-3) / 1e9
-            stages[name] = {"ms": float(ms), "bound": bound, "achieved": ach, "unit": "GB/s", "frac": ach / peaks["hbm"]}
-    # dominant kernel: encoder layer 2 (K=1536 -> N=1024 padded; algorithmic 1500 x 1000), timed alone in the serial
-    # pass with the SM clock at its maximum -> the burst bf16 peak is the denominator (the sustained figure is for a
-    # kernel inside a long power-limited tensor step; this path spends ~1/3 of a frame on the tensor pipe)
-    l2_flop = 2.0 * Pp * 1500 * 1000
-    l2_ach = l2_flop / (enc_ms[1] * 1e-3) / 1e12 if enc_ms[1] > 0 else 0.0
-    traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get("encoder_layer_2", {}).get("dram_bytes_per_launch")
-    except Exception:
-        pass
-    roofline = {"kernel": "encoder_layer_kernel<256,false,6,1,2,64,8> (layer 2: 1500->1000, CTA pairs, tcgen05 cta_group::2)",
-                "bound": "tensor", "achieved": l2_ach,
-                "peak": peaks["tf_burst"], "unit": "TFLOP/s", "frac": l2_ach / peaks["tf_burst"],
-                "traffic": traffic, "peak_source": peaks["source"] + " (burst bf16: kernel timed alone, SM clock at max)",
-                "frac_of_sustained_peak": l2_ach / peaks["tf_sustained"],
-                "frac_of_nominal_dense_peak": l2_ach / 2250.0,
-                "note": "achieved counts ALGORITHMIC flops (1500 x 1000 per patch; the kernel multiplies the padded 1536 x 1024); "
-                        "the measured peak is a cuBLAS bf16 GEMM on this pool's B200s, so a fraction near or above 1 means "
-                        "the kernel matches the library's throughput, not that it exceeds the hardware (nominal 2250 TFLOP/s)",
-                "encoder_layer_ms": [float(x) for x in enc_ms],
-                "encoder_stage_tflops": float(Pp * ENC_FLOP_PER_PATCH / (sum(enc_ms) * 1e-3) / 1e12) if sum(enc_ms) > 0 else 0.0}
-    e2e_fps = frames_total / e2e_s
-    line = {
-        "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": workload_config(stats, patches_per_frame=Pp, parallelism=f"frames x{world}" if world > 1 else "1 GPU"),
-        "ms_per_frame": ms_frame, "traversals_per_s": fps * Pp * T_TREES,
-        "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "timing": "wall clock around hf6d_submit/hf6d_wait with pinned host frames, device sync both sides",
-                "hypotheses_per_frame": n_hyp / (BATCH * args.steps)},
-        "gpu_launches": launches,
-        "roofline": roofline, "stages": stages, "stages_note": "serial pass: one frame at a time, sum = %.3f ms/frame; "
-        "`value` runs %d frames in flight on separate streams" % (float(np.sum(stage_ms)), n_slots),
-        "cpu_baseline": cpu, "clocks": clocks,
-    }
-    if tree is not None:
-        line["tree_sharded"] = tree
+        line = build_line(tree)
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -452,6 +468,7 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--slots", type=int, default=4, help="frames in flight (one stream + workspace each)")
+    ap.add_argument("--tree-timeout", type=int, default=240, help="seconds the tree-sharded arm (N > 1) may take")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

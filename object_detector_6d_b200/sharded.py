@@ -71,10 +71,25 @@ class TreeShardedDetector:
         if self.exchange_mode == "peer":
             if not self.shard_classes:
                 raise ValueError("the peer exchange shards the classes as well")
+            # all ranks attach or none does: a rank left out would never write the flags the others wait for
+            err = None
+            try:
+                blob = self.det.peer_export()
+            except Exception as e:  # noqa: BLE001
+                blob, err = b"", e
             blobs = [None] * self.world
-            dist.all_gather_object(blobs, self.det.peer_export(), group=group)
-            self.det.peer_attach(self.rank, self.world, blobs)
-            dist.barrier(group=group)  # every rank has mapped every buffer before anyone runs
+            dist.all_gather_object(blobs, blob, group=group)
+            if err is None and all(blobs):
+                try:
+                    self.det.peer_attach(self.rank, self.world, blobs)
+                except Exception as e:  # noqa: BLE001
+                    err = e
+            oks = [None] * self.world
+            dist.all_gather_object(oks, err is None and all(blobs), group=group)  # also: everyone has mapped everything
+            if not all(oks):
+                self.det.peer_detach()
+                self.det.close()
+                raise RuntimeError(f"peer exchange unavailable on rank(s) {[r for r, ok in enumerate(oks) if not ok]}: {err}")
         self.device = device
         self.streams = [torch.cuda.Stream(device=device) for _ in range(n_slots)]
         self.stream = self.streams[0]
