@@ -375,7 +375,7 @@ struct EncoderLayerLaunch {
 };
 
 template <int BLOCK_N, bool LAST, int STAGES, int EPI_BUFS, int PAIR, int CHUNK_BYTES, int EPI_WARPS>
-inline cudaError_t launch_encoder_layer_t(const EncoderLayerLaunch& L, const int* m_ptr, int sms, cudaStream_t st) {
+inline cudaError_t launch_encoder_layer_t(const EncoderLayerLaunch& L, const int* m_ptr, int sms, cudaStream_t st, bool probe) {
     auto kern = encoder_layer_kernel<BLOCK_N, LAST, STAGES, EPI_BUFS, PAIR, CHUNK_BYTES, EPI_WARPS>;
     using S = EncSmem<BLOCK_N, STAGES, EPI_BUFS, PAIR, CHUNK_BYTES, EPI_WARPS>;
     static int grid = 0;
@@ -399,6 +399,7 @@ inline cudaError_t launch_encoder_layer_t(const EncoderLayerLaunch& L, const int
             grid = std::min(n_clusters, sms / PAIR) * PAIR;
         }
     }
+    if (probe) return cudaSuccess;  // the kernel fits and (for pairs) the GPCs can co-schedule the clusters
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(S::THREADS);
@@ -458,11 +459,13 @@ inline EncoderConfig encoder_config(int block_n, bool last, bool short_k, int va
     return EncoderConfig{0, 0};
 }
 
-inline cudaError_t launch_encoder_layer(const EncoderLayerLaunch& L, const int* m_ptr, int sms, cudaStream_t st) {
+// probe = true: only check that this variant can run on the current device (shared memory opt-in, cluster occupancy).
+inline cudaError_t launch_encoder_layer(const EncoderLayerLaunch& L, const int* m_ptr, int sms, cudaStream_t st,
+                                        bool probe = false) {
     const int cls = encoder_shape_class(L.block_n, L.last, L.short_k);
 #define X(CLS, VAR, N, LAST, ST, EB, PAIR, CHUNK, EPI)                 \
     if (cls == CLS && L.variant == VAR && L.block_n == N)              \
-        return launch_encoder_layer_t<N, LAST, ST, EB, PAIR, CHUNK, EPI>(L, m_ptr, sms, st);
+        return launch_encoder_layer_t<N, LAST, ST, EB, PAIR, CHUNK, EPI>(L, m_ptr, sms, st, probe);
     HF6D_ENC_CONFIGS(X)
 #undef X
     return cudaErrorInvalidValue;

@@ -963,6 +963,21 @@ int finish_create(hf6d_ctx* c, int device, int n_slots) {
         if (sscanf(e, "%d,%d,%d", &v[0], &v[1], &v[2]) == 3)
             for (int l = 0; l < 3; ++l) c->enc_variant[l] = v[l];
     }
+    for (int l = 0; l < 3; ++l) {  // CTA pairs need co-schedulable clusters: fall back to stand-alone CTAs if they are not
+        EncoderLayerLaunch probe{};
+        probe.block_n = c->dm.block_n[l];
+        probe.last = l == 2;
+        probe.short_k = c->dm.k_pad[l] / ENC_BLOCK_K <= 6;
+        probe.variant = c->enc_variant[l];
+        if (launch_encoder_layer(probe, nullptr, c->sms, nullptr, true) != cudaSuccess) {
+            cudaGetLastError();
+            if (c->enc_variant[l] == 1) return fail(c, HF6D_ECUDA, "encoder layer %d: no kernel variant can run on this device", l);
+            c->enc_variant[l] = 1;
+            probe.variant = 1;
+            if (launch_encoder_layer(probe, nullptr, c->sms, nullptr, true) != cudaSuccess)
+                return fail(c, HF6D_ECUDA, "encoder layer %d: no kernel variant can run on this device", l);
+        }
+    }
     c->slots.resize(c->n_slots);
     for (Slot& s : c->slots) {
         memset(s.ev, 0, sizeof s.ev);

@@ -110,6 +110,24 @@ def test_encoder_within_tolerance(case, full_run):
     assert err.max() < ENC_ABS_TOL and err.mean() < ENC_MEAN_TOL
 
 
+@pytest.mark.parametrize("variants", ["1,1,1", "2,2,2", "3,3,3", "4,0,4"])
+def test_encoder_kernel_variants_agree(case, full_run, variants, monkeypatch):
+    """Every row of HF6D_ENC_CONFIGS (stand-alone CTAs, CTA pairs, ring depths, epilogue shapes) is the same arithmetic in a
+    different schedule: K is accumulated in the same order by the same MMA shape per output element, so the features
+    must be BIT-identical to the default variant's."""
+    from object_detector_6d_b200 import api
+    monkeypatch.setenv("HF6D_ENC_VARIANT", variants)
+    det = api.Detector(case["forest_dir"], case["weights"], to_api_params(case["params"]), device=0, n_slots=1)
+    try:
+        det.upload(0, case["bgr"], case["depth"])
+        det.run(0, api.STAGE_SCAN, api.STAGE_ENCODE)
+        feat = det.fetch(api.BUF_FEATURES)
+    finally:
+        det.close()
+    assert feat.shape == full_run["feat"].shape
+    assert np.array_equal(feat, full_run["feat"])
+
+
 def test_traverse_bitexact_on_oracle_features(case, full_run):
     """Stage-isolated: the fp32 oracle features injected -> every (patch, tree) leaf identical."""
     from object_detector_6d_b200 import api
