@@ -291,7 +291,7 @@ int alloc_slot(hf6d_ctx* c, Slot& s) {
     if ((r = dev_alloc(c, s.allocs, &s.blurred, HW * K))) return r;
     const int n_lists = std::max(K, S);
     if ((r = dev_alloc(c, s.allocs, &s.list, (size_t)n_lists * NMS_LIST_CAP))) return r;
-    if ((r = dev_alloc(c, s.allocs, &s.list_n, (size_t)n_lists + 2))) return r;  // +2: batch counter, reserved entries (pose pass)
+    if ((r = dev_alloc(c, s.allocs, &s.list_n, (size_t)n_lists + 3))) return r;  // +3: batch counter, reserved entries, accumulate-pass batch counter (pose)
     if ((r = dev_alloc(c, s.allocs, &s.entries, (size_t)c->entry_cap))) return r;
     const size_t yp = (size_t)c->reg.ny * c->reg.np;
     const size_t yp_tmp = (size_t)c->reg.ny * c->yp_blur.nc, yp_out = (size_t)c->yp_blur.nr * c->yp_blur.nc;
@@ -628,7 +628,7 @@ int run_stage(hf6d_ctx* c, Slot& s, int stage) {
                     LAUNCH_CHECK(c, s);
                 }
             }
-            CU_TRY(c, cudaMemsetAsync(s.list_n, 0, ((size_t)std::max(K, S) + 2) * 4, st));
+            CU_TRY(c, cudaMemsetAsync(s.list_n, 0, ((size_t)std::max(K, S) + 3) * 4, st));
             const long long items = (long long)g.cap * f.T;
             CentreTable ct{rv.centres, rv.active};
             const int half_win = p.centers_nms_wsize / 2;
@@ -656,7 +656,7 @@ int run_stage(hf6d_ctx* c, Slot& s, int stage) {
                     const int wa_grid = c->sms * (zs ? (int)std::max<size_t>(1, std::min<size_t>(2, (200 * 1024) / (zbytes + 24 * 1024))) : 2);
 #define HF6D_WA(SZ, GG)                                                                                                     \
     window_accumulate_kernel<SZ, GG><<<wa_grid, WA_THREADS, (SZ) ? zbytes : 0, st>>>(f, s.entries, c->entry_cap, ctr + 1, n_groups, \
-                                                                                   zt, s.win_cnt, s.zacc)
+                                                                                   zt, s.win_cnt, s.zacc, ctr + 2)
                     if (zs) { if (c->lanes_per_hit == 16) HF6D_WA(true, 16); else HF6D_WA(true, 32); }
                     else { if (c->lanes_per_hit == 16) HF6D_WA(false, 16); else HF6D_WA(false, 32); }
 #undef HF6D_WA

@@ -336,7 +336,7 @@ template <bool SMEM_Z, int G>
 __global__ void __launch_bounds__(WA_THREADS)
 window_accumulate_kernel(DevForest f, const uint4* __restrict__ entries, int entry_cap, const int* __restrict__ n_reserved,
                          int n_groups, const __grid_constant__ ZSlotTable zt, unsigned* __restrict__ cnt,
-                         unsigned long long* __restrict__ zacc) {
+                         unsigned long long* __restrict__ zacc, int* __restrict__ next_batch) {
     __shared__ WarpEntries s_we[WA_THREADS / 32];
     extern __shared__ unsigned s_z[];  // [zt.zoff[K]][Z_BINS]
     const int nz = zt.zoff[f.K];
@@ -348,8 +348,20 @@ window_accumulate_kernel(DevForest f, const uint4* __restrict__ entries, int ent
     const int lane = threadIdx.x & 31, sub = lane % G, part = lane / G;
     constexpr int PARTS = 32 / G;
     WarpEntries& we = s_we[threadIdx.x >> 5];
-    const int warp_id = (blockIdx.x * WA_THREADS + threadIdx.x) >> 5, n_warps = (gridDim.x * WA_THREADS) >> 5;
-    for (int base = warp_id * 32; base < n; base += n_warps * 32) {
+    // batches of 32 entries are handed out through a global counter (zeroed before the launch): the cost of a batch varies
+    // with its share of padding entries and the vote counts of its leaves, and a static stride left 28 % of the warp
+    // time waiting at the final barrier
+    constexpr int WA_GRAB = 4;  // 32-entry batches per grab: one atomic round trip per 128 entries
+    int grab = 0, left = 0;
+    for (;;) {
+        if (left == 0) {
+            if (lane == 0) grab = atomicAdd(next_batch, 1) * (32 * WA_GRAB);
+            grab = __shfl_sync(0xffffffffu, grab, 0);
+            left = WA_GRAB;
+        }
+        const int base = grab + (WA_GRAB - left) * 32;
+        --left;
+        if (base >= n) break;
         const uint4 e = entries[base + lane];  // n is a multiple of ENTRY_BLOCK, so base + lane < n
         float zz = -1.f;
         int4 grp = make_int4(0, 0, 0, 0);
