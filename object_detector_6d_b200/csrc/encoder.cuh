@@ -82,7 +82,7 @@ template <int BLOCK_N, bool LAST, int STAGES, int EPI_BUFS, int PAIR, int CHUNK_
 __global__ void __launch_bounds__((4 + EPI_WARPS) * 32, 1)
 encoder_layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmC, const float* __restrict__ bias,
-                     const int* __restrict__ m_ptr, int K, int n_pad) {
+                     const int* __restrict__ m_ptr, int K, int n_pad, int reverse_m) {
     using S = EncSmem<BLOCK_N, STAGES, EPI_BUFS, PAIR, CHUNK_BYTES, EPI_WARPS>;
     static_assert(PAIR == 1 || PAIR == 2, "stand-alone CTAs or CTA pairs");
     static_assert(EPI_WARPS % 4 == 0, "every TMEM lane quadrant needs the same number of epilogue warps");
@@ -110,6 +110,9 @@ encoder_layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     const int m_groups = (m_blocks + PAIR - 1) / PAIR;
     const int tiles = m_groups * n_blocks;
     const int first = blockIdx.x / PAIR, step = gridDim.x / PAIR;
+    // reverse_m: walk the m-blocks from the end.  The layers alternate direction so that each one starts on the rows its
+    // producer wrote LAST -- the part of the activation matrix (145-227 MB) that is still in the 126 MB L2.
+    auto m_group_of = [&](int g) { return reverse_m ? m_groups - 1 - g : g; };
 
     for (int i = threadIdx.x; i < n_pad; i += S::THREADS) s_bias[i] = bias[i];
 
@@ -150,7 +153,7 @@ encoder_layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         uint32_t phase = 0;
         const uint32_t full0 = PAIR > 1 ? ptx::mapa_shared(ptx::smem_u32(&full[0]), 0) : 0;  // the even CTA's barriers
         for (int t = first; t < tiles; t += step) {
-            const int mb = (t / n_blocks) * PAIR + cta_rank, nb = t % n_blocks;
+            const int mb = m_group_of(t / n_blocks) * PAIR + cta_rank, nb = t % n_blocks;
             for (int kb = 0; kb < k_blocks; ++kb) {
                 ptx::mbar_wait(&empty[stage], phase ^ 1);
                 uint8_t* sa = smem + stage * S::STAGE_BYTES;
@@ -232,7 +235,7 @@ encoder_layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int t = first; t < tiles; t += step) {
-            const int mb = (t / n_blocks) * PAIR + cta_rank, nb = t % n_blocks;
+            const int mb = m_group_of(t / n_blocks) * PAIR + cta_rank, nb = t % n_blocks;
             const int row0 = mb * ENC_BLOCK_M + q * 32;
             ptx::mbar_wait(&tfull[acc], acc_phase);
             ptx::tc_fence_after();
@@ -372,6 +375,7 @@ struct EncoderLayerLaunch {
     int K, n_pad, block_n;
     bool last, short_k;  // short_k: few K blocks per tile
     int variant;         // row of HF6D_ENC_CONFIGS for this layer's shape class
+    int reverse_m;       // walk the m-blocks from the end (see the kernel)
 };
 
 template <int BLOCK_N, bool LAST, int STAGES, int EPI_BUFS, int PAIR, int CHUNK_BYTES, int EPI_WARPS>
@@ -410,7 +414,7 @@ inline cudaError_t launch_encoder_layer_t(const EncoderLayerLaunch& L, const int
     attrs[0].val.clusterDim.x = PAIR; attrs[0].val.clusterDim.y = 1; attrs[0].val.clusterDim.z = 1;
     cfg.attrs = attrs;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kern, L.tmA, L.tmB, L.tmC, L.bias, m_ptr, L.K, L.n_pad);
+    return cudaLaunchKernelEx(&cfg, kern, L.tmA, L.tmB, L.tmC, L.bias, m_ptr, L.K, L.n_pad, L.reverse_m);
 }
 
 // The kernel configurations, one table for the launcher and for the slot's tensor maps (W box rows, output chunk width).

@@ -54,7 +54,8 @@ inline TraversePlan traverse_plan(int F, int T) {
 template <int NCH>
 __global__ void __launch_bounds__((TRV_MAX_BUFS + 1) * 32, 1)
 traverse_kernel(const float* __restrict__ features, DevForest f, const int* __restrict__ counts,
-                int* __restrict__ leaf_ord, int shard_rank, int shard_world, int n_bufs, int n_cache, int n_recs) {
+                int* __restrict__ leaf_ord, int shard_rank, int shard_world, int n_bufs, int n_cache, int n_recs,
+                int reverse) {
     extern __shared__ __align__(16) uint8_t trv_smem[];
     const int F = f.F, pitch = F + 4;
     PackedRecord* cache = reinterpret_cast<PackedRecord*>(trv_smem);  // [T][n_cache]
@@ -96,7 +97,7 @@ traverse_kernel(const float* __restrict__ features, DevForest f, const int* __re
         uint32_t phase = 0;
         for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
             ptx::mbar_wait(&empty[b], phase ^ 1);
-            const int p0 = tile * TRV_ROWS;
+            const int p0 = (reverse ? tiles - 1 - tile : tile) * TRV_ROWS;  // last rows first: see the consumers
             const int nrows = min(TRV_ROWS, Pp - p0);
             if (lane == 0) ptx::mbar_arrive_expect_tx(&full[b], (uint32_t)nrows * F * 4);
             __syncwarp();
@@ -110,7 +111,10 @@ traverse_kernel(const float* __restrict__ features, DevForest f, const int* __re
         const float* my = ring + ((size_t)warp * TRV_ROWS + row) * pitch;
         uint32_t phase = 0;
         for (int tile = blockIdx.x + warp * gridDim.x; tile < tiles; tile += n_bufs * gridDim.x) {
-            const int p0 = tile * TRV_ROWS;
+            // The rows are walked from the END of the matrix: the feature layer wrote them in ascending order just before
+            // this kernel, so the tail of the 227 MB is what the 126 MB L2 still holds -- reading it first turns those
+            // rows into L2 hits instead of letting the head's misses evict them.
+            const int p0 = (reverse ? tiles - 1 - tile : tile) * TRV_ROWS;
             const int nrows = min(TRV_ROWS, Pp - p0);
             // trees this rank does not own: mark, so that a max-reduce across ranks assembles the full table
             if (shard_world > 1) {

@@ -336,6 +336,10 @@ int alloc_slot(hf6d_ctx* c, Slot& s) {
         L.block_n = dm.block_n[l];
         L.short_k = short_k;
         L.variant = c->enc_variant[l];
+        // gather writes A0 ascending (36 MB: all of it stays in L2); layer 1 ascending -> layer 2 descending -> layer 3
+        // ascending -> traverse descending: every consumer starts where its producer stopped
+        static const bool snake = !(getenv("HF6D_SNAKE") && atoi(getenv("HF6D_SNAKE")) == 0);  // tuning override
+        L.reverse_m = snake && l == 1;
     }
     return HF6D_OK;
 }
@@ -557,15 +561,16 @@ int run_stage(hf6d_ctx* c, Slot& s, int stage) {
             const int n_owned = (f.T - c->shard_rank + c->shard_world - 1) / c->shard_world;
             const int per_slot = (n_owned + TRV_SLOTS - 1) / TRV_SLOTS;
             const int threads = (tp.n_bufs + 1) * 32, n_recs = (int)c->hf.recs.size();
+            static const int trv_reverse = !(getenv("HF6D_SNAKE") && atoi(getenv("HF6D_SNAKE")) == 0);  // see alloc_slot
             if (per_slot <= 1)
                 traverse_kernel<1><<<c->sms, threads, tp.smem, st>>>(s.feat, f, s.counts, s.leaf_ord, c->shard_rank, c->shard_world,
-                                                                   tp.n_bufs, tp.n_cache, n_recs);
+                                                                   tp.n_bufs, tp.n_cache, n_recs, trv_reverse);
             else if (per_slot <= 2)
                 traverse_kernel<2><<<c->sms, threads, tp.smem, st>>>(s.feat, f, s.counts, s.leaf_ord, c->shard_rank, c->shard_world,
-                                                                   tp.n_bufs, tp.n_cache, n_recs);
+                                                                   tp.n_bufs, tp.n_cache, n_recs, trv_reverse);
             else
                 traverse_kernel<4><<<c->sms, threads, tp.smem, st>>>(s.feat, f, s.counts, s.leaf_ord, c->shard_rank, c->shard_world,
-                                                                   tp.n_bufs, tp.n_cache, n_recs);
+                                                                   tp.n_bufs, tp.n_cache, n_recs, trv_reverse);
             LAUNCH_CHECK(c, s);
             break;
         }
