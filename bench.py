@@ -29,6 +29,9 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+# one hardware queue per stream (default 8): frame slots on aliased queues would serialise, and a slot waiting for a
+# peer's flag (tree-sharded mode) must never hold up another slot's kernels.  Read by the driver at CUDA initialisation.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 from object_detector_6d_b200 import synth  # noqa: E402
 

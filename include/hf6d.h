@@ -164,7 +164,9 @@ int hf6d_set_class_shard(hf6d_ctx* c, int rank, int world);
  * hf6d_run exchanges nothing through the host: the kernels after the exchange point read the peers' maps and leaf tables
  * in place over NVLink, and the ranks synchronise through flags in each other's memory (see "peer exchange" in
  * csrc/hf6d_api.cu).  hf6d_peer_attach also sets the tree shard and the class shard to rank/world.  Every rank must then
- * run the same frames on the same slots (whole frames, or SCAN..VOTE followed by CENTRES..POSE).  Replaces the
+ * run the same frames on the same slots (whole frames, or SCAN..VOTE followed by CENTRES..POSE), and the slots' streams
+ * should not share a hardware queue (CUDA_DEVICE_MAX_CONNECTIONS >= number of streams the process uses): a slot that
+ * waits for a peer's flag blocks its queue, and the peer may be waiting for a frame queued behind it.  Replaces the
  * reference's merge of per-thread vote maps and leaf lists, HoughForest/src/HFTest.cpp:645-654, across GPUs. */
 #define HF6D_MAX_SLOTS 16
 size_t hf6d_peer_blob_bytes(void);
