@@ -587,7 +587,7 @@ int run_stage(hf6d_ctx* c, Slot& s, int stage) {
             const MapRect full{0, 0, g.H, g.W};
             const int kb = p.centers_blur_size, w = p.centers_nms_wsize;
             box_rows_kernel<<<dim3((g.H + BLUR_WARPS - 1) / BLUR_WARPS, K), BLUR_WARPS * 32,
-                              (size_t)BLUR_WARPS * (g.W + 1) * 8, st>>>(s.maps, s.map_tmp, md, full, full, kb, c->dm.class_mask,
+                              box_rows_smem_bytes(g.W), st>>>(s.maps, s.map_tmp, md, full, full, kb, c->dm.class_mask,
                                                                         peer_maps_of(c, slot_index(c, s)));
             LAUNCH_CHECK(c, s);
             box_cols_kernel<<<dim3((g.W + 127) / 128, (g.H + BLUR_COL_CHUNK - 1) / BLUR_COL_CHUNK, K), 128, 0, st>>>(
@@ -680,7 +680,7 @@ int run_stage(hf6d_ctx* c, Slot& s, int stage) {
             const MapRect rout = c->yp_blur;
             const int kb = p.pose_blur_size, w = p.pose_nms_wsize;
             box_rows_kernel<<<dim3((rin.nr + BLUR_WARPS - 1) / BLUR_WARPS, S), BLUR_WARPS * 32,
-                              (size_t)BLUR_WARPS * (rin.nc + 1) * 8, st>>>(s.ypacc, s.yptmp, md, rin, rout, kb, rv.active,
+                              box_rows_smem_bytes(rin.nc), st>>>(s.ypacc, s.yptmp, md, rin, rout, kb, rv.active,
                                                                            PeerMaps{{}, 0});
             LAUNCH_CHECK(c, s);
             box_cols_kernel<<<dim3((rout.nc + 127) / 128, (rout.nr + BLUR_COL_CHUNK - 1) / BLUR_COL_CHUNK, S), 128, 0, st>>>(
@@ -949,7 +949,7 @@ int finish_create(hf6d_ctx* c, int device, int n_slots) {
                                                              cell_grid_bytes(p.W, p.H, p.centers_nms_wsize / 2, K)));
     c->wc_ctas_per_sm = std::max(1, c->wc_ctas_per_sm);
     CU_TRY(c, cudaFuncSetAttribute(box_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)((size_t)BLUR_WARPS * (std::max(p.W, HF6D_POSE_BINS) + 1) * 8)));
+                                   (int)box_rows_smem_bytes(std::max(p.W, HF6D_POSE_BINS))));
 
     {
         // worst case: every cast vote is an entry; budget 64 MB per frame slot (4 M entries), the overflow path stays exact

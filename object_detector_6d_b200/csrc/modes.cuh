@@ -61,7 +61,11 @@ clear_accumulators_kernel(const __grid_constant__ ClearPlan plan) {
 
 // ------------------------------------------------------------------------------------------------ box blur
 constexpr int BLUR_WARPS = 4;
-constexpr int ROW_BATCH = 4;   // 32-column groups loaded together by the row pass
+constexpr int ROW_RUN = 8;     // consecutive columns a lane sums serially in the row pass
+// The row pass keeps its prefix sums in shared memory with one slot skipped after every 8: lanes that write runs of 8
+// consecutive 8-byte entries would otherwise all hit the same four banks (stride 64 B); with the skew the stride is 72 B.
+__host__ __device__ __forceinline__ int pre_slot(int i) { return i + (i >> 3); }
+__host__ __device__ __forceinline__ size_t box_rows_smem_bytes(int nc) { return (size_t)BLUR_WARPS * (pre_slot(nc + 1) + 1) * 8; }
 constexpr int COL_BATCH = 8;   // rows loaded together while the column pass builds its first window sum
 
 // Accumulators of the same layout that live in OTHER GPUs' memory (tree-sharded mode, csrc/hf6d_api.cu "peer exchange"):
@@ -76,49 +80,49 @@ struct PeerMaps {
 __global__ void __launch_bounds__(BLUR_WARPS * 32)
 box_rows_kernel(const unsigned long long* __restrict__ acc, unsigned long long* __restrict__ tmp, MapDims md, MapRect in,
                 MapRect out, int kx, const uint8_t* __restrict__ map_active, const __grid_constant__ PeerMaps peers) {
-    extern __shared__ unsigned long long s_pre[];  // [BLUR_WARPS][in.nc + 1]
+    extern __shared__ unsigned long long s_pre[];  // [BLUR_WARPS][pre_slot(in.nc + 1) + 1]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m = blockIdx.y;
     if (map_active && !map_active[m]) return;
     const int r = blockIdx.x * BLUR_WARPS + warp;
     if (r >= in.nr) return;
-    unsigned long long* pre = s_pre + (size_t)warp * (in.nc + 1);
+    unsigned long long* pre = s_pre + (size_t)warp * (pre_slot(in.nc + 1) + 1);
     const unsigned long long* src = acc + ((size_t)m * in.nr + r) * in.nc;
+    // Inclusive prefix sums of the row into pre[1..nc]: a lane takes ROW_RUN CONSECUTIVE columns (64 contiguous bytes, so a
+    // warp still reads one contiguous 2 KB piece), sums them serially in registers, and only the 32 lane totals go through
+    // the shuffle scan -- one scan per 256 columns instead of one per 32.
     unsigned long long carry = 0;
-    if (lane == 0) pre[0] = 0;
-    for (int c0 = 0; c0 < in.nc; c0 += 32 * ROW_BATCH) {  // ROW_BATCH independent loads in flight per lane, then the scans
-        unsigned long long vv[ROW_BATCH];
+    if (lane == 0) pre[pre_slot(0)] = 0;
+    for (int c0 = 0; c0 < in.nc; c0 += 32 * ROW_RUN) {
+        const int cb = c0 + lane * ROW_RUN;
+        unsigned long long vv[ROW_RUN];
 #pragma unroll
-        for (int j = 0; j < ROW_BATCH; ++j) {
-            const int c = c0 + j * 32 + lane;
-            vv[j] = c < in.nc ? src[c] : 0ull;
-        }
+        for (int j = 0; j < ROW_RUN; ++j) vv[j] = cb + j < in.nc ? src[cb + j] : 0ull;
         for (int q = 0; q < peers.n; ++q) {  // the other ranks' partial sums of the same cells, read in place
             const unsigned long long* psrc = peers.base[q] + ((size_t)m * in.nr + r) * in.nc;
 #pragma unroll
-            for (int j = 0; j < ROW_BATCH; ++j) {
-                const int c = c0 + j * 32 + lane;
-                if (c < in.nc) vv[j] += psrc[c];
-            }
+            for (int j = 0; j < ROW_RUN; ++j)
+                if (cb + j < in.nc) vv[j] += psrc[cb + j];
         }
 #pragma unroll
-        for (int j = 0; j < ROW_BATCH; ++j) {
-            const int c = c0 + j * 32 + lane;
-            unsigned long long v = vv[j];
+        for (int j = 1; j < ROW_RUN; ++j) vv[j] += vv[j - 1];
+        unsigned long long tot = vv[ROW_RUN - 1];  // inclusive scan of the lane totals
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const unsigned long long n = __shfl_up_sync(0xffffffffu, v, o);
-                if (lane >= o) v += n;
-            }
-            if (c < in.nc) pre[c + 1] = carry + v;
-            carry += __shfl_sync(0xffffffffu, v, 31);
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long nb = __shfl_up_sync(0xffffffffu, tot, o);
+            if (lane >= o) tot += nb;
         }
+        const unsigned long long base = carry + tot - vv[ROW_RUN - 1];  // everything before this lane's run
+#pragma unroll
+        for (int j = 0; j < ROW_RUN; ++j)
+            if (cb + j < in.nc) pre[pre_slot(cb + j + 1)] = base + vv[j];
+        carry += __shfl_sync(0xffffffffu, tot, 31);
     }
     __syncwarp();
     auto seg = [&](int a, int b) -> unsigned long long {  // sum over global columns [a, b], clipped to the input rectangle
         a = max(a, in.c0);
         b = min(b, in.c0 + in.nc - 1);
-        return b >= a ? pre[b - in.c0 + 1] - pre[a - in.c0] : 0ull;
+        return b >= a ? pre[pre_slot(b - in.c0 + 1)] - pre[pre_slot(a - in.c0)] : 0ull;
     };
     unsigned long long* dst = tmp + ((size_t)m * in.nr + r) * out.nc;
     const int n = md.cols;
@@ -172,21 +176,37 @@ box_cols_kernel(const unsigned long long* __restrict__ tmp, float* __restrict__ 
     unsigned long long s = 0;
     {
         const int a = out.r0 + rbeg - ky / 2;
+        const bool interior = a >= 0 && a + ky - 1 < n && a - in.r0 >= 0 && a - in.r0 + ky - 1 < in.nr;
+        const unsigned long long* p0 = src + (size_t)(interior ? a - in.r0 : 0) * out.nc;
         for (int k0 = 0; k0 < ky; k0 += COL_BATCH) {  // batches of independent loads (a plain loop waits for every one)
             unsigned long long v[COL_BATCH];
 #pragma unroll
-            for (int i = 0; i < COL_BATCH; ++i) v[i] = k0 + i < ky ? at(a + k0 + i) : 0ull;
+            for (int i = 0; i < COL_BATCH; ++i)
+                v[i] = k0 + i < ky ? (interior ? p0[(size_t)(k0 + i) * out.nc] : at(a + k0 + i)) : 0ull;
 #pragma unroll
             for (int i = 0; i < COL_BATCH; ++i) s += v[i];
         }
     }
+    const double scale16 = scale * (1.0 / 65536.0);  // a power of two: (s / 65536) * scale == s * (scale / 65536) bit for bit
     for (int r0 = rbeg; r0 < rend; r0 += NMS_BLOCK) {  // one block row at a time: its 16 loads are issued together
         unsigned long long add[NMS_BLOCK], sub[NMS_BLOCK];
+        const int a0 = out.r0 + r0 - ky / 2;                          // global row leaving the window at step 0
+        const int lo = a0 - in.r0, hi = lo + NMS_BLOCK - 1 + ky;      // rectangle-local rows this block row touches
+        if (a0 >= 0 && a0 + NMS_BLOCK - 1 + ky < n && lo >= 0 && hi < in.nr) {
+            // interior (almost every block row): no reflection, no clipping -- two pointers and a constant stride
+            const unsigned long long* ps = src + (size_t)lo * out.nc;
+            const unsigned long long* pa = ps + (size_t)ky * out.nc;
 #pragma unroll
-        for (int i = 0; i < NMS_BLOCK; ++i) {
-            const int a = out.r0 + r0 + i - ky / 2;
-            add[i] = at(a + ky);
-            sub[i] = at(a);
+            for (int i = 0; i < NMS_BLOCK; ++i) {
+                add[i] = pa[(size_t)i * out.nc];
+                sub[i] = ps[(size_t)i * out.nc];
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < NMS_BLOCK; ++i) {
+                add[i] = at(a0 + i + ky);
+                sub[i] = at(a0 + i);
+            }
         }
         float best_v = 0.f;  // maximum of this column inside the block row (values are >= 0), topmost on ties
         int best_r = r0;
@@ -194,7 +214,7 @@ box_cols_kernel(const unsigned long long* __restrict__ tmp, float* __restrict__ 
         for (int i = 0; i < NMS_BLOCK; ++i) {
             const int r = r0 + i;
             if (r < rend) {
-                const float v = (float)(((double)s / 65536.0) * scale);
+                const float v = (float)((double)s * scale16);
                 if (live) dst[(size_t)r * out.nc] = v;
                 if (v > best_v) { best_v = v; best_r = r; }
                 s += add[i];
