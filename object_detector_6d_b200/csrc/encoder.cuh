@@ -419,7 +419,7 @@ inline cudaError_t launch_encoder_layer_t(const EncoderLayerLaunch& L, const int
 
 // The kernel configurations, one table for the launcher and for the slot's tensor maps (W box rows, output chunk width).
 //   shape class: 0 = hidden layer, short K (<= 6 k-blocks);  1 = hidden layer;  2 = feature layer N % 160 == 0;
-//                3 = feature layer, 256-wide tiles
+//                3 = feature layer, 256-wide tiles;  4 = feature layer, 208-wide tiles (pairs only)
 //   variant 0 is the default of its class; the others are kept for HF6D_ENC_VARIANT="a,b,c" (per layer) experiments and
 //   as the fallback when CTA pairs cannot be scheduled (variant 1: stand-alone CTAs, cta_group::1).
 #define HF6D_ENC_CONFIGS(X)                                        \
@@ -442,12 +442,14 @@ inline cudaError_t launch_encoder_layer_t(const EncoderLayerLaunch& L, const int
     X(2, 4, 160, true, 4, 2, 2, 128, 12)  /* 122.9 */              \
     X(2, 5, 160, true, 6, 1, 2, 128, 8)                            \
     X(2, 6, 160, true, 5, 1, 2, 128, 8)                            \
+    X(4, 0, 208, true, 6, 2, 2, 64, 8)                             \
+    X(4, 1, 208, true, 5, 4, 2, 64, 8)                             \
     X(3, 0, 256, true, 4, 2, 2, 64, 8)                             \
     X(3, 1, 256, true, 4, 1, 1, 64, 8)
 
 inline int encoder_shape_class(int block_n, bool last, bool short_k) {
     if (!last) return short_k ? 0 : 1;
-    return block_n == 160 ? 2 : 3;
+    return block_n == 160 ? 2 : block_n == 208 ? 4 : 3;
 }
 
 struct EncoderConfig {

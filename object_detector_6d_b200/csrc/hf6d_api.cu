@@ -234,6 +234,18 @@ int upload_model(hf6d_ctx* c) {
         const bool last = l == 2;
         if (last) {
             dm.block_n[l] = (L.out % 160 == 0) ? 160 : 256;
+            // 208-wide tiles when the layer fits four of them (the reference's 800 features): 4 % padded flops, but the A
+            // tile is re-read 4 times instead of 5 and the layer is bound by operand delivery (98 -> 94 us).  CTA pairs
+            // only, so the choice is made after probing them; HF6D_ENC_N3=160 keeps the narrow tiles.
+            const char* e3 = getenv("HF6D_ENC_N3");
+            if (L.out > 3 * 208 && L.out <= 4 * 208 && !(e3 && atoi(e3) != 208)) {
+                EncoderLayerLaunch probe{};
+                probe.block_n = 208;
+                probe.last = true;
+                probe.variant = 0;
+                if (launch_encoder_layer(probe, nullptr, c->sms, nullptr, true) == cudaSuccess) dm.block_n[l] = 208;
+                else cudaGetLastError();
+            }
             dm.n_pad[l] = round_up(L.out, dm.block_n[l]);
         } else {
             dm.block_n[l] = 256;

@@ -110,13 +110,15 @@ def test_encoder_within_tolerance(case, full_run):
     assert err.max() < ENC_ABS_TOL and err.mean() < ENC_MEAN_TOL
 
 
-@pytest.mark.parametrize("variants", ["1,1,1", "2,2,2", "3,3,3", "4,0,4"])
-def test_encoder_kernel_variants_agree(case, full_run, variants, monkeypatch):
+@pytest.mark.parametrize("variants,n3", [("1,1,1", "160"), ("2,2,2", "160"), ("3,3,3", "160"), ("4,0,4", "160"),
+                                         ("1,1,1", "208")])
+def test_encoder_kernel_variants_agree(case, full_run, variants, n3, monkeypatch):
     """Every row of HF6D_ENC_CONFIGS (stand-alone CTAs, CTA pairs, ring depths, epilogue shapes) is the same arithmetic in a
     different schedule: K is accumulated in the same order by the same MMA shape per output element, so the features
     must be BIT-identical to the default variant's."""
     from object_detector_6d_b200 import api
     monkeypatch.setenv("HF6D_ENC_VARIANT", variants)
+    monkeypatch.setenv("HF6D_ENC_N3", n3)  # feature-layer tile width: 160 (also the stand-alone-CTA fallback) or 208
     det = api.Detector(case["forest_dir"], case["weights"], to_api_params(case["params"]), device=0, n_slots=1)
     try:
         det.upload(0, case["bgr"], case["depth"])
