@@ -421,29 +421,33 @@ inline cudaError_t launch_encoder_layer_t(const EncoderLayerLaunch& L, const int
 //   shape class: 0 = hidden layer, short K (<= 6 k-blocks);  1 = hidden layer;  2 = feature layer N % 160 == 0;
 //                3 = feature layer, 256-wide tiles;  4 = feature layer, 208-wide tiles (pairs only)
 //   variant 0 is the default of its class; the others are kept for HF6D_ENC_VARIANT="a,b,c" (per layer) experiments and
-//   as the fallback when CTA pairs cannot be scheduled (variant 1: stand-alone CTAs, cta_group::1).
+//   as the fallback when CTA pairs cannot be scheduled (variant 1: stand-alone CTAs, cta_group::1; class 4 has none).
+//   Variant 0 is the PIPELINED default (contexts with several frame slots), variant 2 of classes 0 / 1 / 4 the one that is
+//   fastest alone (one more ring stage; one-slot contexts use it): with several frames in flight the smaller footprints
+//   (160-180 KB instead of 192-218 KB of shared memory) leave room for other frames' gather / vote / blur CTAs beside the
+//   persistent encoder CTA, which is worth +3-5 % frames/s for 2-5 % of encoder time.
 #define HF6D_ENC_CONFIGS(X)                                        \
-    /*  cls var  N   LAST  ST EB PAIR CHUNK EPI      B200, 70.9 k patches: us per layer */ \
-    X(0, 0, 256, false, 5, 1, 2, 128, 8)  /* 57.7 */               \
+    /*  cls var  N   LAST  ST EB PAIR CHUNK EPI      B200, 70.9 k patches: us per layer (alone) */ \
+    X(0, 0, 256, false, 4, 1, 2, 128, 8)  /* 59.5 */               \
     X(0, 1, 256, false, 3, 2, 1, 128, 8)  /* 65.5 */               \
-    X(0, 2, 256, false, 4, 2, 2, 128, 8)  /* 60.1 */               \
+    X(0, 2, 256, false, 5, 1, 2, 128, 8)  /* 57.7 */               \
     X(0, 3, 256, false, 4, 2, 2, 64, 16)  /* 59.6 */               \
     X(0, 4, 256, false, 6, 1, 2, 64, 8)   /* 63.7 */               \
-    X(0, 5, 256, false, 4, 1, 2, 128, 8)                           \
-    X(1, 0, 256, false, 6, 1, 2, 64, 8)   /* 129.0 */              \
+    X(0, 5, 256, false, 4, 2, 2, 128, 8)  /* 60.1 */               \
+    X(1, 0, 256, false, 5, 1, 2, 64, 8)   /* 131.5 */              \
     X(1, 1, 256, false, 4, 1, 1, 64, 8)   /* 151.6 */              \
-    X(1, 2, 256, false, 5, 2, 2, 64, 8)   /* 135.1 */              \
-    X(1, 3, 256, false, 4, 2, 2, 128, 8)  /* 146.2 */              \
-    X(1, 4, 256, false, 5, 1, 2, 64, 8)                            \
+    X(1, 2, 256, false, 6, 1, 2, 64, 8)   /* 129.0 */              \
+    X(1, 3, 256, false, 5, 2, 2, 64, 8)   /* 135.1 */              \
+    X(1, 4, 256, false, 4, 2, 2, 128, 8)  /* 146.2 */              \
     X(2, 0, 160, true, 7, 1, 2, 128, 8)   /* 98.3 */               \
     X(2, 1, 160, true, 4, 2, 1, 128, 8)   /* 118.8 */              \
     X(2, 2, 160, true, 5, 2, 2, 128, 8)   /* 104.5 */              \
     X(2, 3, 160, true, 7, 2, 2, 64, 8)    /* 98.5 */               \
     X(2, 4, 160, true, 4, 2, 2, 128, 12)  /* 122.9 */              \
-    X(2, 5, 160, true, 6, 1, 2, 128, 8)                            \
-    X(2, 6, 160, true, 5, 1, 2, 128, 8)                            \
-    X(4, 0, 208, true, 6, 2, 2, 64, 8)                             \
-    X(4, 1, 208, true, 5, 4, 2, 64, 8)                             \
+    X(4, 0, 208, true, 5, 2, 2, 64, 8)    /* 95.5 */               \
+    X(4, 1, 208, true, 5, 4, 2, 64, 8)    /* 96.2 */               \
+    X(4, 2, 208, true, 6, 2, 2, 64, 8)    /* 94.2 */               \
+    X(4, 3, 208, true, 4, 2, 2, 64, 8)    /* 113 */                \
     X(3, 0, 256, true, 4, 2, 2, 64, 8)                             \
     X(3, 1, 256, true, 4, 1, 1, 64, 8)
 

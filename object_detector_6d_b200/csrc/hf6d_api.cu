@@ -975,6 +975,13 @@ int finish_create(hf6d_ctx* c, int device, int n_slots) {
     }
     CU_TRY(c, cudaFuncSetAttribute(window_accumulate_kernel<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, WA_MAX_DYN_SMEM));
     CU_TRY(c, cudaFuncSetAttribute(window_accumulate_kernel<true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, WA_MAX_DYN_SMEM));
+    // Two sets of encoder kernels (HF6D_ENC_CONFIGS): a context with several frame slots is built for pipelining, where the
+    // smaller shared-memory footprints (variant 0) let other frames' CTAs run beside the persistent encoder CTA; a
+    // one-slot context runs one frame at a time, where the deeper operand rings (variant 2) are simply faster.
+    for (int l = 0; l < 3; ++l) {
+        const int cls = encoder_shape_class(c->dm.block_n[l], l == 2, c->dm.k_pad[l] / ENC_BLOCK_K <= 6);
+        c->enc_variant[l] = (c->n_slots == 1 && (cls == 0 || cls == 1 || cls == 4)) ? 2 : 0;
+    }
     if (const char* e = getenv("HF6D_ENC_VARIANT")) {
         int v[3];
         if (sscanf(e, "%d,%d,%d", &v[0], &v[1], &v[2]) == 3)

@@ -111,7 +111,7 @@ def test_encoder_within_tolerance(case, full_run):
 
 
 @pytest.mark.parametrize("variants,n3", [("1,1,1", "160"), ("2,2,2", "160"), ("3,3,3", "160"), ("4,0,4", "160"),
-                                         ("1,1,1", "208")])
+                                         ("5,4,0", "160"), ("2,2,2", "208"), ("1,1,1", "208")])
 def test_encoder_kernel_variants_agree(case, full_run, variants, n3, monkeypatch):
     """Every row of HF6D_ENC_CONFIGS (stand-alone CTAs, CTA pairs, ring depths, epilogue shapes) is the same arithmetic in a
     different schedule: K is accumulated in the same order by the same MMA shape per output element, so the features
