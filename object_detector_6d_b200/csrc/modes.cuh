@@ -88,22 +88,37 @@ box_rows_kernel(const unsigned long long* __restrict__ acc, unsigned long long* 
     if (r >= in.nr) return;
     unsigned long long* pre = s_pre + (size_t)warp * (pre_slot(in.nc + 1) + 1);
     const unsigned long long* src = acc + ((size_t)m * in.nr + r) * in.nc;
-    // Inclusive prefix sums of the row into pre[1..nc]: a lane takes ROW_RUN CONSECUTIVE columns (64 contiguous bytes, so a
-    // warp still reads one contiguous 2 KB piece), sums them serially in registers, and only the 32 lane totals go through
-    // the shuffle scan -- one scan per 256 columns instead of one per 32.
+    // Inclusive prefix sums of the row into pre[1..nc].  Loads are coalesced (lane l reads columns c0 + 32 j + l; the peers'
+    // maps cross NVLink, where a lane-private run of 8-byte loads would fetch every 32-byte sector eight times), the raw
+    // values pass through the prefix array so that each lane can then take ROW_RUN CONSECUTIVE columns, sum them serially in
+    // registers, and only the 32 lane totals go through the shuffle scan -- one scan per 256 columns instead of one per 32.
     unsigned long long carry = 0;
     if (lane == 0) pre[pre_slot(0)] = 0;
     for (int c0 = 0; c0 < in.nc; c0 += 32 * ROW_RUN) {
         const int cb = c0 + lane * ROW_RUN;
         unsigned long long vv[ROW_RUN];
 #pragma unroll
-        for (int j = 0; j < ROW_RUN; ++j) vv[j] = cb + j < in.nc ? src[cb + j] : 0ull;
+        for (int j = 0; j < ROW_RUN; ++j) {
+            const int c = c0 + j * 32 + lane;
+            vv[j] = c < in.nc ? src[c] : 0ull;
+        }
         for (int q = 0; q < peers.n; ++q) {  // the other ranks' partial sums of the same cells, read in place
             const unsigned long long* psrc = peers.base[q] + ((size_t)m * in.nr + r) * in.nc;
 #pragma unroll
-            for (int j = 0; j < ROW_RUN; ++j)
-                if (cb + j < in.nc) vv[j] += psrc[cb + j];
+            for (int j = 0; j < ROW_RUN; ++j) {
+                const int c = c0 + j * 32 + lane;
+                if (c < in.nc) vv[j] += psrc[c];
+            }
         }
+#pragma unroll
+        for (int j = 0; j < ROW_RUN; ++j) {
+            const int c = c0 + j * 32 + lane;
+            if (c < in.nc) pre[pre_slot(c + 1)] = vv[j];
+        }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < ROW_RUN; ++j) vv[j] = cb + j < in.nc ? pre[pre_slot(cb + j + 1)] : 0ull;
+        __syncwarp();  // every lane has its run before any lane overwrites slots with prefix sums
 #pragma unroll
         for (int j = 1; j < ROW_RUN; ++j) vv[j] += vv[j - 1];
         unsigned long long tot = vv[ROW_RUN - 1];  // inclusive scan of the lane totals
