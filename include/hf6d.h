@@ -136,7 +136,10 @@ typedef struct {
 void hf6d_default_params(hf6d_params* p);
 
 /* forest_dir: forest.txt + tree<N>.dat (HFBase.cpp:110-145).  weights_path: a V1 .caffemodel with layers encode1..3
- * (generate_scripts.sh:424-524) or the raw "HF6DW001" container.  n_slots frames may be in flight (>=1). */
+ * (generate_scripts.sh:424-524) or the raw "HF6DW001" container.  n_slots frames may be in flight (>=1): n_slots == 1 is
+ * the latency configuration (one frame at a time, the encoder kernels that are fastest alone), n_slots > 1 the throughput
+ * configuration (4 is enough to saturate a B200; encoder kernels with a smaller shared-memory footprint, so that the
+ * other frames' kernels run beside them).  Results are bit-identical in both. */
 int hf6d_create(const hf6d_params* p, const char* forest_dir, const char* weights_path, int device, int n_slots,
                 hf6d_ctx** out);
 /* Text-format DetectorOptions.Options file, as HoughForest --test --detector_options_file takes (HFTest.cpp:1155-1235).
