@@ -513,6 +513,25 @@ roll_from_counts_kernel(DevForest f, const unsigned* __restrict__ cnt, int n_gro
             if (src < 0) continue;
             const int4 grp = __ldg(reinterpret_cast<const int4*>(f.groups) + g0 + src);
             const int passes = (grp.w + G - 1) / G;
+            if (passes == 1) {
+                // the usual case (a group's votes fit the G lanes): every lane keeps its vote's bins in registers for all
+                // peaks instead of fetching them again per peak
+                const bool have = sub < grp.w;
+                const short4 bn = have ? __ldg(f.bins + grp.z + sub) : make_short4(0, 0, 0, 0);
+                const int Y = (int)bn.x + 360, P0 = (int)bn.y + 360, r = bn.z;
+                const int b0 = r + 360, b1 = r < 0 ? r + 720 : r;
+                for (int p = 0; p < np; ++p) {
+                    const int2 yp = __ldg(reinterpret_cast<const int2*>(pk.peak_yx) + s * pk.max_peaks + p);
+                    const bool in = have && Y >= yp.x - half_box && Y < yp.x + half_box && P0 >= yp.y - half_box && P0 < yp.y + half_box;
+                    const int inbox = __popc(__ballot_sync(gmask, in));
+                    if (inbox == 0 || !have) continue;
+                    const unsigned long long wk = (unsigned long long)(unsigned)grp.y * c_hits * (unsigned long long)inbox;
+                    unsigned long long* rs = racc + ((size_t)s * pk.max_peaks + p) * HF6D_POSE_BINS;
+                    if (b0 >= 0 && b0 < HF6D_POSE_BINS) atomicAdd(rs + b0, wk);
+                    if (b1 >= 0 && b1 < HF6D_POSE_BINS) atomicAdd(rs + b1, wk);
+                }
+                continue;
+            }
             for (int p = 0; p < np; ++p) {
                 const int Yp = __ldg(pk.peak_yx + (s * pk.max_peaks + p) * 2), Pp = __ldg(pk.peak_yx + (s * pk.max_peaks + p) * 2 + 1);
                 int inbox = 0;
