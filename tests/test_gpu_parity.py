@@ -130,6 +130,20 @@ def test_encoder_kernel_variants_agree(case, full_run, variants, n3, monkeypatch
     assert np.array_equal(feat, full_run["feat"])
 
 
+def test_latency_and_throughput_contexts_agree(case, full_run):
+    """A one-slot context (the encoder kernels that are fastest alone) and a multi-slot one (smaller footprints, so that
+    other frames' CTAs co-reside) must give the same frame result, bit for bit."""
+    from object_detector_6d_b200 import api
+    det = api.Detector(case["forest_dir"], case["weights"], to_api_params(case["params"]), device=0, n_slots=1)
+    try:
+        hyp = det.detect(case["bgr"], case["depth"])
+        feat = det.fetch(api.BUF_FEATURES)
+    finally:
+        det.close()
+    assert np.array_equal(feat, full_run["feat"])
+    assert len(hyp) == len(full_run["hyp"]) and all(np.array_equal(hyp[n], full_run["hyp"][n]) for n in hyp.dtype.names)
+
+
 def test_traverse_bitexact_on_oracle_features(case, full_run):
     """Stage-isolated: the fp32 oracle features injected -> every (patch, tree) leaf identical."""
     from object_detector_6d_b200 import api
