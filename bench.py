@@ -118,7 +118,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     from oracle import oracle as O
-    cores = os.cpu_count() or 1
+    cores = O.set_threads()  # all host cores, also under torchrun (which exports OMP_NUM_THREADS=1)
     with tempfile.TemporaryDirectory() as d:
         frames, layers, forest_dir, _, stats = make_workload(d, min(2, DISTINCT_FRAMES))
         forest = O.Forest(forest_dir)
@@ -304,6 +304,7 @@ def run_cuda(args, rank, world, local_rank):
         cpu = None
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
             from oracle import oracle as O
+            cpu_threads = O.set_threads()
             forest = O.Forest(forest_dir)
             po = O.default_params(fill_random=1, fill_seed=1)
             O.detect(forest, frames[0][0], frames[0][1], po, layers)  # warm
@@ -312,7 +313,7 @@ def run_cuda(args, rank, world, local_rank):
             for i in range(n_s):
                 O.detect(forest, frames[i][0], frames[i][1], po, layers)
             dt = time.perf_counter() - t0
-            cpu = {"value": n_s / dt, "unit": "frames/s", "cores": os.cpu_count() or 1, "kind": "port",
+            cpu = {"value": n_s / dt, "unit": "frames/s", "cores": cpu_threads, "kind": "port",
                    "sample": f"{n_s} frames of the batch, all stages, OpenMP on all host cores"}
         det.close()
 

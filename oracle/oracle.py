@@ -89,6 +89,17 @@ def lib():
     return _lib
 
 
+def set_threads(n: int | None = None) -> int:
+    """OpenMP threads of the oracle (default: all host cores).  torchrun exports OMP_NUM_THREADS=1 into every rank, which
+    would silently turn the 'all cores' CPU baseline into a single-threaded one; this goes through the OpenMP runtime the
+    oracle library is linked against, so it works after the environment has been read.  Returns the threads in use."""
+    lib()
+    omp = C.CDLL("libgomp.so.1")
+    omp.omp_set_num_threads(int(n or os.cpu_count() or 1))
+    omp.omp_get_max_threads.restype = C.c_int
+    return int(omp.omp_get_max_threads())
+
+
 def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
