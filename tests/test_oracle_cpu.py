@@ -237,3 +237,16 @@ def test_empty_and_far_frames(small):
     few[100:110, 100:110] = 700  # fewer valid centres than one batch: the reference drops the partial batch
     hyp, (P, Pp), _ = O.detect(small["forest"], small["bgr"], few, p, small["layers"])
     assert 0 < P < p.batch_size and Pp == 0 and len(hyp) == 0
+
+
+def test_cpu_baseline_uses_all_cores_even_under_torchrun(monkeypatch):
+    """torchrun exports OMP_NUM_THREADS=1 into every rank; the reference arm of bench.py must still time the oracle on all
+    host cores (it sets the thread count through the OpenMP runtime, not the environment)."""
+    import os
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, %r); from oracle import oracle as O; print(O.set_threads())"
+            % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, check=True).stdout
+    assert int(out.strip().splitlines()[-1]) == (os.cpu_count() or 1)
