@@ -11,7 +11,8 @@
 // integer (1/255 is folded into the first layer's weights).  The fp32 patches never exist in memory.
 //
 // Arithmetic is the oracle's, operation for operation (IEEE _rn intrinsics, no FMA contraction), including the strictly
-// sequential mean / variance accumulation order c -> row -> col of the reference, so the uint8 patches are bit-exact.
+// sequential mean / variance accumulation order c -> row -> col of the reference and the double-precision variance terms
+// its `pow(x - mean, 2) / N` compiles to (oracle choice C3), so the uint8 patches are bit-exact.
 #pragma once
 #include "common.cuh"
 
@@ -145,6 +146,40 @@ __device__ __forceinline__ void sequential_sums(const float (*term)[GATHER_ROW],
     }
 }
 
+// a / 3 correctly rounded without the IEEE division sequence (Markstein: y = RN(1/3), q = RN(a y), r = a - 3 q exactly,
+// q' = RN(q + r y)); tools/check_const_division.c compares it with a / 3.0 on 10^9 squares of floats.
+__device__ __forceinline__ double div3_rn(double a) {
+    const double y = 0x1.5555555555555p-2;
+    const double q = __dmul_rn(a, y);
+    return __fma_rn(__fma_rn(-3.0, q, a), y, q);
+}
+
+// The reference's variance accumulation (HFTest.cpp:527-534: `std += pow(x - mean, 2) / N`, which its toolchain evaluates
+// as pow(double, double): the float deviation squared in double, divided by (double)N, added to (double)std and narrowed
+// back to the float accumulator, element by element).  dev holds the float deviations x - mean; lanes as in
+// sequential_sums.  N = 192 = 3 * 64 and N = 64: the power of two is an exact scaling.
+__device__ __forceinline__ void sequential_variances(const float (*dev)[GATHER_ROW], float (*stat)[4]) {
+    if (threadIdx.x < 32) {
+        const int pl = threadIdx.x >> 1, which = threadIdx.x & 1;
+        const float* src = dev[pl] + (which ? GATHER_D_OFF : 0);
+        float m = 0.f;
+#pragma unroll 8
+        for (int j = 0; j < 64; ++j) {
+            const double d = (double)src[j], dd = __dmul_rn(d, d);
+            const double t = __dmul_rn(which ? dd : div3_rn(dd), 1.0 / 64.0);
+            m = __double2float_rn(__dadd_rn((double)m, t));
+        }
+        if (!which) {
+#pragma unroll 8
+            for (int j = 64; j < 192; ++j) {
+                const double d = (double)src[j];
+                m = __double2float_rn(__dadd_rn((double)m, __dmul_rn(div3_rn(__dmul_rn(d, d)), 1.0 / 64.0)));
+            }
+        }
+        stat[pl][2 + which] = m;
+    }
+}
+
 // 8 threads per patch (one per patch row), 16 patches per CTA.  ps == 8 only (the 256-input encoder).
 // a_out : bf16 [cap][256], CHW order, value = q (exact integer 0..255)
 // q_out : optional uint8 [cap][256] (debug capture / parity)
@@ -237,17 +272,14 @@ gather_normalise_kernel(const uint2* __restrict__ tex, FrameGeom g, const int* _
     sequential_sums(s_term, s_stat, 0);
     __syncthreads();
     const float mean_rgb = s_stat[pl][0], mean_d = s_stat[pl][1];
-    // ---- "std" (variance, never sqrt'ed; float d*d) (HFTest.cpp:527-534)
+    // ---- "std" (variance, never sqrt'ed; terms in double) (HFTest.cpp:527-534)
 #pragma unroll
     for (int ch = 0; ch < 4; ++ch)
 #pragma unroll
-        for (int tx = 0; tx < 8; ++tx) {
-            const float d = __fsub_rn(val[ch][tx], ch < 3 ? mean_rgb : mean_d);
-            const float dd = __fmul_rn(d, d);
-            s_term[pl][(ch < 3 ? ch * 64 : GATHER_D_OFF) + ty * 8 + tx] = ch < 3 ? div_const<192, 1>(dd) : __fmul_rn(dd, 1.0f / 64.0f);
-        }
+        for (int tx = 0; tx < 8; ++tx)
+            s_term[pl][(ch < 3 ? ch * 64 : GATHER_D_OFF) + ty * 8 + tx] = __fsub_rn(val[ch][tx], ch < 3 ? mean_rgb : mean_d);
     __syncthreads();
-    sequential_sums(s_term, s_stat, 2);
+    sequential_variances(s_term, s_stat);
     __syncthreads();
     if (!live) return;
     const float lim_rgb = __fmul_rn(3.0f, s_stat[pl][2]), lim_d = __fmul_rn(3.0f, s_stat[pl][3]);

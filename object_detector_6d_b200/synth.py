@@ -258,7 +258,7 @@ def calibration_features(bgr, depth, layers, n=8000, cam: Camera = Camera(), see
     return np.ascontiguousarray(h, np.float32)
 
 # ----------------------------------------------------------------------------------------------------- forests
-def _build_tree(rng, feats, max_depth, min_samples, K, votes_per_leaf):
+def _build_tree(rng, feats, max_depth, min_samples, K, votes_per_leaf, prob_quantum=0):
     """Level-wise random tree over a calibration batch.  Returns dict of node arrays (index 0 = root)."""
     N, F = feats.shape
     is_leaf, mode, f1, f2, thr, left, right, depth_of = [], [], [], [], [], [], [], []
@@ -329,6 +329,8 @@ def _build_tree(rng, feats, max_depth, min_samples, K, votes_per_leaf):
     nl = leaf_idx.size
     dom = rng.integers(0, K, nl)
     p_dom = rng.uniform(0.5, 1.0, nl).astype(np.float32)
+    if prob_quantum:  # dyadic class probabilities: float vote sums are then exact whatever the summation order
+        p_dom = (np.round(p_dom * prob_quantum) / prob_quantum).astype(np.float32)
     probs = np.zeros((nl, K), np.float32)
     if K > 1:
         rest = rng.random((nl, K)).astype(np.float32)
@@ -386,7 +388,7 @@ def _serialise_tree(rng, tree, K) -> bytes:
 
 def write_forest(folder: str, calib_features: np.ndarray, T: int = 4, K: int = 6, max_depth: int = 20,
                  votes_per_leaf: int = 16, seed: int = 7, min_samples: int = 2, patch_vox: int = 8,
-                 voxel_m: float = 0.005) -> dict:
+                 voxel_m: float = 0.005, prob_quantum: int = 0) -> dict:
     """Write forest.txt + tree<t>.dat.  Returns summary statistics."""
     os.makedirs(folder, exist_ok=True)
     feats = np.ascontiguousarray(calib_features, np.float32)
@@ -394,7 +396,7 @@ def write_forest(folder: str, calib_features: np.ndarray, T: int = 4, K: int = 6
     rng = np.random.default_rng(seed)
     stats = dict(T=T, K=K, F=F, leaves=[], nodes=[], mean_depth=[])
     for t in range(T):
-        tree = _build_tree(rng, feats, max_depth, min_samples, K, votes_per_leaf)
+        tree = _build_tree(rng, feats, max_depth, min_samples, K, votes_per_leaf, prob_quantum)
         with open(os.path.join(folder, f"tree{t}.dat"), "wb") as f:
             f.write(_serialise_tree(rng, tree, K))
         stats["leaves"].append(int(tree["leaf_idx"].size))

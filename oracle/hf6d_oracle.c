@@ -20,7 +20,13 @@
  *  C1 texture filter: software bilinear, fraction rounded to 8 bits (round-to-nearest), border texel = 0,
  *     S = ((w00*T00 + w10*T10) + w01*T01) + w11*T11 in fp32.  (For patch_vox = 8 the fraction is k/8: exact.)
  *  C2 border fill values: counter-based hash of (fill_seed, patch index) instead of clock64()-seeded cuRAND.
- *  C3 variance uses float (d*d), i.e. std::pow(float,int) of the reference's gnu++98 toolchain.
+ *  C3 the variance terms are evaluated in double: `std += pow(x - mean, 2) / N` (HFTest.cpp:527-534) is an unqualified call,
+ *     and on the reference's tested toolchain (README.md:16, Ubuntu 14.04 = gcc 4.8 / glibc 2.19, whose <math.h> puts only
+ *     the C functions in the global namespace) it binds to pow(double, double): the float deviation is squared in double
+ *     (exact), divided by (double)N, added to (double)std, and the sum narrowed back to the float accumulator -- per
+ *     element.  A present-day gcc in its default dialect evaluates the same expression in double as well (C++11
+ *     std::pow(float, int) promotes).  The means (`mean += x / N`, float / int) stay in float.  Pinned by
+ *     tests/test_ref_pins.py against the reference's own source compiled with a C-only <math.h>.
  *  C4 (unsigned char)(NaN) == 0 (x86 cvttss2si low byte).
  *  C5 encoder: fp32, fixed accumulation order (8 interleaved partial sums, pairwise combine), bias added last,
  *     sigmoid = 1/(1+expf(-x)).  Caffe/BLAS order is unknowable.
@@ -483,9 +489,9 @@ void hf6d_ref_normalise(const float* patches, int32_t P, int32_t ps, uint8_t* q)
                     pos++;
                 }
         float var_rgb = 0, var_d = 0; /* "std" in the source, never sqrt'ed */
-        for (int j = 0; j < n4; ++j) {
-            if (j < n3) { float d = buf[j] - mean_rgb; var_rgb += (d * d) / (float)n3; } /* C3 */
-            else { float d = buf[j] - mean_d; var_d += (d * d) / (float)n1; }
+        for (int j = 0; j < n4; ++j) { /* C3: pow(double, double), double division and addition, narrowed per element */
+            if (j < n3) { const double d = (double)(buf[j] - mean_rgb); var_rgb = (float)((double)var_rgb + (d * d) / (double)n3); }
+            else { const double d = (double)(buf[j] - mean_d); var_d = (float)((double)var_d + (d * d) / (double)n1); }
         }
         for (int j = 0; j < n4; ++j) {
             const float m = j < n3 ? mean_rgb : mean_d;
@@ -535,6 +541,20 @@ void hf6d_ref_encode(const uint8_t* q, int32_t P, int32_t n0, const float* W1, c
     dense_sigmoid(h1, P, n1, W2, b2, n2, h2);
     dense_sigmoid(h2, P, n2, W3, b3, n3, features);
     free(x);
+    free(h1);
+    free(h2);
+}
+
+/* The same three layers on fp32 inputs (the net input k/255.0f the reference builds at HFTest.cpp:565).  The
+ * reference-source pin library (oracle/ref_driver.cpp) installs this as its stand-in Caffe net's forward pass. */
+void hf6d_ref_encode_f32(const float* x, int32_t P, int32_t n0, const float* W1, const float* b1, int32_t n1,
+                         const float* W2, const float* b2, int32_t n2, const float* W3, const float* b3, int32_t n3,
+                         float* features) {
+    float* h1 = (float*)malloc(sizeof(float) * (size_t)P * n1);
+    float* h2 = (float*)malloc(sizeof(float) * (size_t)P * n2);
+    dense_sigmoid(x, P, n0, W1, b1, n1, h1);
+    dense_sigmoid(h1, P, n1, W2, b2, n2, h2);
+    dense_sigmoid(h2, P, n2, W3, b3, n3, features);
     free(h1);
     free(h2);
 }

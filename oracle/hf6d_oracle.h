@@ -79,6 +79,10 @@ void hf6d_ref_normalise(const float* patches, int32_t P, int32_t ps, uint8_t* q)
 void hf6d_ref_encode(const uint8_t* q, int32_t P, int32_t n0, const float* W1, const float* b1, int32_t n1,
                      const float* W2, const float* b2, int32_t n2, const float* W3, const float* b3, int32_t n3,
                      float* features);
+/* A4 on fp32 inputs x [P][n0] (the net input k/255.0f); same arithmetic as hf6d_ref_encode */
+void hf6d_ref_encode_f32(const float* x, int32_t P, int32_t n0, const float* W1, const float* b1, int32_t n1,
+                         const float* W2, const float* b2, int32_t n2, const float* W3, const float* b3, int32_t n3,
+                         float* features);
 /* A6: leaf_id [P][T] = leaf_id field of the file; leaf_ord [P][T] = file-order ordinal of the leaf inside its tree */
 void hf6d_ref_traverse(const hf6d_ref_forest* f, const float* features, int32_t P, int32_t* leaf_id, int32_t* leaf_ord);
 /* A7/A8: maps [K][H][W] u64 Q16 (zeroed here).  Returns number of votes cast (in or out of bounds). */

@@ -11,7 +11,7 @@ from oracle import oracle as O
 
 
 def make_case(tmpdir: str, *, K=3, T=4, seed=1, max_depth=14, votes_per_leaf=8, n_objects=6, cam=None, stride=2,
-              calib_patches=6000, fill_random=0, weights_seed=3, min_samples=2):
+              calib_patches=6000, fill_random=0, weights_seed=3, min_samples=2, prob_quantum=0):
     """Frame + encoder weights + forest (written to tmpdir) + oracle parameter block."""
     cam = cam or synth.Camera()
     bgr, depth = synth.render_frame(seed, cam, n_objects=n_objects)
@@ -24,7 +24,7 @@ def make_case(tmpdir: str, *, K=3, T=4, seed=1, max_depth=14, votes_per_leaf=8, 
     calib = O.encode(O.normalise(O.gather(bgr, depth, p, locs[sel])), layers)
     forest_dir = os.path.join(tmpdir, "forest")
     stats = synth.write_forest(forest_dir, calib, T=T, K=K, max_depth=max_depth, votes_per_leaf=votes_per_leaf,
-                               seed=7 + seed, min_samples=min_samples)
+                               seed=7 + seed, min_samples=min_samples, prob_quantum=prob_quantum)
     wpath = os.path.join(tmpdir, "weights.bin")
     synth.write_weights_raw(wpath, layers)
     return dict(bgr=bgr, depth=depth, layers=layers, params=p, forest_dir=forest_dir, weights=wpath, stats=stats,

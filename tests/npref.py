@@ -222,7 +222,7 @@ def quantise_normals(patches):
 
 # ------------------------------------------------------------------------------------------------ A3 normalise
 def normalise(patches):
-    """HFTest.cpp:500-570: HWC -> CHW, sequential float sums, variance (never sqrt'ed), clip, scale, truncate.
+    """HFTest.cpp:500-570: HWC -> CHW, sequential sums (means in float, variance terms in double), variance (never sqrt'ed), clip, scale, truncate.
     (unsigned char)(NaN) == 0 on x86."""
     P, ps = patches.shape[0], patches.shape[1]
     buf = np.ascontiguousarray(patches.transpose(0, 3, 1, 2)).reshape(P, 4 * ps * ps).astype(f32)
@@ -233,14 +233,17 @@ def normalise(patches):
     mean_d = np.zeros(P, f32)
     for j in range(n3, n3 + n1):
         mean_d = mean_d + buf[:, j] / f32(n1)
+    # `std += pow(x - mean, 2) / N`: pow(double, double) on the reference's toolchain -- the float deviation squared in
+    # double, divided by (double)N, added to (double)std, narrowed back to float for every element
+    f64 = np.float64
     var_rgb = np.zeros(P, f32)
     for j in range(n3):
-        dlt = buf[:, j] - mean_rgb
-        var_rgb = var_rgb + (dlt * dlt) / f32(n3)
+        dlt = (buf[:, j] - mean_rgb).astype(f64)
+        var_rgb = (var_rgb.astype(f64) + (dlt * dlt) / f64(n3)).astype(f32)
     var_d = np.zeros(P, f32)
     for j in range(n3, n3 + n1):
-        dlt = buf[:, j] - mean_d
-        var_d = var_d + (dlt * dlt) / f32(n1)
+        dlt = (buf[:, j] - mean_d).astype(f64)
+        var_d = (var_d.astype(f64) + (dlt * dlt) / f64(n1)).astype(f32)
     q = np.zeros((P, 4 * ps * ps), np.uint8)
     with np.errstate(divide="ignore", invalid="ignore"):
         for sl, m, var in ((slice(0, n3), mean_rgb, var_rgb), (slice(n3, n3 + n1), mean_d, var_d)):
