@@ -52,15 +52,73 @@ def load_peaks():
         return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback")
 
 
-def make_workload(tmpdir: str, n_frames: int, seed0: int = 1, T: int = T_TREES):
-    frames = [synth.render_frame(seed0 + i) for i in range(n_frames)]
+OBJECT_SEED = 1000    # the six procedural objects that stand in for meshes/*.ply (shape, size, albedo, texture)
+TRAIN_FRAMES = 4      # frames whose object patches (every pixel) train the forest: same objects, their own poses
+VIEWS, MIN_SAMPLES = 4, 8   # training views a labelled patch stands for / node size that stops splitting (-> ~16 votes per leaf)
+WORKLOAD_VERSION = 4  # bump when synth or the recipe below changes (invalidates the on-disk cache)
+
+
+def _build_workload(out: str, n_frames: int, seed0: int, T: int, forest: str):
     layers = synth.make_encoder_weights(3)
-    calib = synth.calibration_features(frames[0][0], frames[0][1], layers, n=30000)
-    forest_dir = os.path.join(tmpdir, f"forest_T{T}")
-    stats = synth.write_forest(forest_dir, calib, T=T, K=K_CLASSES, max_depth=MAX_DEPTH, votes_per_leaf=VOTES, seed=7)
-    wpath = os.path.join(tmpdir, "weights.bin")
-    synth.write_weights_raw(wpath, layers)
-    return frames, layers, forest_dir, wpath, stats
+    forest_dir = os.path.join(out, "forest")
+    if forest == "random":
+        frames = [synth.render_frame(seed0 + i) for i in range(n_frames)]
+        calib = synth.calibration_features(frames[0][0], frames[0][1], layers, n=30000)
+        stats = synth.write_forest(forest_dir, calib, T=T, K=K_CLASSES, max_depth=MAX_DEPTH, votes_per_leaf=VOTES, seed=7)
+    else:
+        scenes = [synth.render_scene(seed0 + i, OBJECT_SEED) for i in range(max(n_frames, TRAIN_FRAMES))]
+        frames = [(b, d) for b, d, _ in scenes[:n_frames]]
+        lab = [synth.labelled_patches(b, d, tr, layers, n=80000, seed=i, stride=1) for i, (b, d, tr) in enumerate(scenes[:TRAIN_FRAMES])]
+        feats, cls, votes = (np.concatenate([x[j] for x in lab]) for j in range(3))
+        stats = synth.write_trained_forest(forest_dir, feats, cls, votes, T=T, K=K_CLASSES, max_depth=MAX_DEPTH,
+                                           min_samples=MIN_SAMPLES, views=VIEWS, seed=7)
+        stats["training_samples"] = int(len(cls))
+    stats["forest"] = forest
+    synth.write_weights_raw(os.path.join(out, "weights.bin"), layers)
+    np.savez(os.path.join(out, "frames.npz"), bgr=np.stack([f[0] for f in frames]), depth=np.stack([f[1] for f in frames]))
+    with open(os.path.join(out, "stats.json"), "w") as f:
+        json.dump(stats, f)
+
+
+def make_workload(tmpdir: str, n_frames: int, seed0: int = 1, T: int = T_TREES, forest: str = "trained"):
+    """Frames + encoder weights + forest on disk.  forest = "trained": leaves hold the class distributions and the 6-DoF
+    votes of labelled object patches (synth.write_trained_forest) -- coherent votes, real Hough modes, the vote hot spots
+    a trained forest produces; "random": uniformly random votes, 16 per leaf (round 1's workload: no modes, maximal
+    scatter; kept for the stage-level parity tests and for continuity).
+
+    Building it takes ~40 s of numpy, so it is cached under the system temp directory, keyed by the recipe: the ranks of a
+    torchrun launch (and successive bench / test processes on one box) share one copy -- whoever creates the directory
+    builds, the others wait for its `done` marker.  `tmpdir` is unused when the cache can be used."""
+    key = f"hf6d_workload_v{WORKLOAD_VERSION}_{forest}_n{n_frames}_s{seed0}_T{T}"
+    root = os.path.join(tempfile.gettempdir(), key)
+    done = os.path.join(root, "done")
+    try:
+        os.makedirs(root)
+        owner = True
+    except FileExistsError:
+        owner = False
+    if owner:
+        try:
+            _build_workload(root, n_frames, seed0, T, forest)
+            open(done, "w").close()
+        except BaseException:
+            import shutil
+            shutil.rmtree(root, ignore_errors=True)
+            raise
+    else:
+        t0 = time.time()
+        while not os.path.exists(done):
+            if not os.path.isdir(root) or time.time() - t0 > 900:  # the builder failed or died: build privately
+                root = os.path.join(tmpdir, key)
+                os.makedirs(root, exist_ok=True)
+                _build_workload(root, n_frames, seed0, T, forest)
+                break
+            time.sleep(0.5)
+    z = np.load(os.path.join(root, "frames.npz"))
+    frames = [(np.ascontiguousarray(z["bgr"][i]), np.ascontiguousarray(z["depth"][i])) for i in range(n_frames)]
+    with open(os.path.join(root, "stats.json")) as f:
+        stats = json.load(f)
+    return frames, synth.make_encoder_weights(3), os.path.join(root, "forest"), os.path.join(root, "weights.bin"), stats
 
 
 class ClockSampler:
@@ -120,7 +178,7 @@ def run_reference(args, rank, world):
     from oracle import oracle as O
     cores = O.set_threads()  # all host cores, also under torchrun (which exports OMP_NUM_THREADS=1)
     with tempfile.TemporaryDirectory() as d:
-        frames, layers, forest_dir, _, stats = make_workload(d, min(2, DISTINCT_FRAMES))
+        frames, layers, forest_dir, _, stats = make_workload(d, DISTINCT_FRAMES, forest=args.forest)
         forest = O.Forest(forest_dir)
         p = O.default_params(fill_random=1, fill_seed=1)
         n_trav = 0
@@ -152,7 +210,7 @@ def run_reference(args, rank, world):
 def workload_config(stats, **extra):
     cfg = {"workload": "configs[1]: 6-object forest, batch of 64 synthetic cluttered 640x480 RGB-D frames",
            "frame": "640x480", "stride": 2, "classes": K_CLASSES, "trees": T_TREES, "mean_leaf_depth":
-           float(np.mean(stats["mean_depth"])), "votes_per_leaf": VOTES, "leaves": int(sum(stats["leaves"])),
+           float(np.mean(stats["mean_depth"])), "forest": stats.get("forest"), "leaves": int(sum(stats["leaves"])),
            "batch_frames": BATCH, "distinct_frames": DISTINCT_FRAMES, "fill": "random (are_objects_segmented: false)",
            "l2": "per-frame intermediates (0.9 GB) exceed the 126 MB L2; frames cycle through 8 distinct inputs"}
     cfg.update(extra)
@@ -173,7 +231,7 @@ def run_cuda(args, rank, world, local_rank):
     peaks = load_peaks()
 
     with tempfile.TemporaryDirectory() as d:
-        frames, layers, forest_dir, wpath, stats = make_workload(d, DISTINCT_FRAMES)
+        frames, layers, forest_dir, wpath, stats = make_workload(d, DISTINCT_FRAMES, forest=args.forest)
         p = api.default_params(fill_random=1, fill_seed=1)
         n_slots = args.slots
         det = api.Detector(forest_dir, wpath, p, device=local_rank, n_slots=n_slots)
@@ -247,12 +305,14 @@ def run_cuda(args, rank, world, local_rank):
         det1.bind_frame(0, None, None)
         det1.close()
         # patches per frame: exact, from the scan of every distinct frame
-        Pp_frames = []
+        Pp_frames, votes_frames = [], []
         for j in range(DISTINCT_FRAMES):
             det.bind_frame(0, bgr_all[j].data_ptr(), dep_all[j].data_ptr())
-            det.run(0, api.STAGE_SCAN, api.STAGE_SCAN)
+            det.run(0, api.STAGE_SCAN, api.STAGE_TRAVERSE)
             Pp_frames.append(det.counts(0)[1])
+            votes_frames.append(det.count_cast_votes(0))
         Pp_mean = float(np.mean([Pp_frames[i % DISTINCT_FRAMES] for i in range(BATCH)]))
+        votes_mean = float(np.mean([votes_frames[i % DISTINCT_FRAMES] for i in range(BATCH)]))
         for s in range(n_slots):
             det.bind_frame(s, None, None)
             det.set_stream(s, None)
@@ -325,7 +385,7 @@ def run_cuda(args, rank, world, local_rank):
             ms_frame = ms_total / (BATCH * args.steps)
             # stage rooflines from SURVEY.md §8(d)'s algorithmic work per frame
             Pp = Pp_mean
-            votes_cast = Pp * T_TREES * VOTES
+            votes_cast = votes_mean  # counted from the leaf tables of the frames (hf6d_count_cast_votes)
             alg = {
                 "scan": (640 * 480 * 2 + Pp * 8, "hbm"),
                 "gather": (640 * 480 * 5 + Pp * 512, "hbm"),                 # frame once + bf16 A operand [P'][256]
@@ -373,7 +433,8 @@ def run_cuda(args, rank, world, local_rank):
                 "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                "config": workload_config(stats, patches_per_frame=Pp, parallelism=f"frames x{world}" if world > 1 else "1 GPU"),
+                "config": workload_config(stats, patches_per_frame=Pp, votes_cast_per_frame=votes_cast,
+                                          parallelism=f"frames x{world}" if world > 1 else "1 GPU"),
                 "ms_per_frame": ms_frame, "traversals_per_s": fps * Pp * T_TREES,
                 "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "timing": "wall clock around hf6d_submit/hf6d_wait with pinned host frames, device sync both sides",
@@ -479,6 +540,8 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--slots", type=int, default=4, help="frames in flight (one stream + workspace each)")
+    ap.add_argument("--forest", default="trained", choices=["trained", "random"],
+                    help="synthetic forest: leaf payloads from labelled patches (coherent votes) or uniformly random votes")
     ap.add_argument("--tree-timeout", type=int, default=240, help="seconds the tree-sharded arm (N > 1) may take")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

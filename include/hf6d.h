@@ -177,8 +177,14 @@ int hf6d_peer_export(hf6d_ctx* c, void* blob, size_t cap_bytes);
 int hf6d_peer_attach(hf6d_ctx* c, int rank, int world, const void* blobs /* world blobs, rank order */, size_t bytes_each);
 int hf6d_peer_detach(hf6d_ctx* c);
 int hf6d_peer_timed_out(hf6d_ctx* c); /* 1 if a flag wait gave up (fallback wait kernel only); results are then invalid */
-/* Encoder arithmetic: 0 = bf16 operands (default), 1 = split-bf16 (hi+lo operands, 3 MMAs per product, ~fp32). */
+/* Encoder arithmetic (replaces Caffe's fp32 sgemm, HoughForest/src/HFTest.cpp:585-596):
+ *   0 = bf16 operands, fp32 accumulation (default: the throughput mode; features within 3e-2 of fp32);
+ *   1 = split bf16: every operand as hi + lo bf16 halves, a product as a_hi*w_hi + a_lo*w_hi + a_hi*w_lo on the same
+ *       tensor-core kernel (three passes over K), fp32 sigmoid -- features within ~3e-5 of an fp32 evaluation, i.e. as
+ *       close to the reference's as one fp32 summation order is to another; about 3x the encoder time.
+ * Synchronises the device; the first switch to mode 1 allocates the hi/lo activation buffers of every slot. */
 int hf6d_set_encoder_mode(hf6d_ctx* c, int mode);
+int hf6d_get_encoder_mode(const hf6d_ctx* c);
 int hf6d_set_debug_capture(hf6d_ctx* c, int on); /* keep HF6D_BUF_PATCH_U8 */
 
 /* ---------------------------------------------------------------------------------------------- host-only helpers */
@@ -234,6 +240,10 @@ int hf6d_encoder_layer_ms(hf6d_ctx* c, int slot, float* ms);
 int64_t hf6d_result_bytes(const hf6d_ctx* c);
 /* Number of kernels the last hf6d_run on this slot launched. */
 int hf6d_launch_count(const hf6d_ctx* c, int slot);
+/* Diagnostic (syncs the slot, host arithmetic): how many votes the slot's current leaf table casts -- the sum over its
+ * (patch, owned tree) pairs of the gated votes of the leaf reached (HFTest.cpp:191-214).  The bench derives the vote and
+ * pose stages' algorithmic bytes from it.  Returns the count, or < 0. */
+int64_t hf6d_count_cast_votes(hf6d_ctx* c, int slot);
 
 /* Diagnostic (not on the hot path): gathers the slot's P' patches through a real CUDA texture object built exactly as
  * the reference builds its texture (patch_extractor.cu:339-343, fill = 0) and copies them to the host as

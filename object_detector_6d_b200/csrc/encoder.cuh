@@ -67,6 +67,28 @@ __device__ __forceinline__ float sigmoid_accurate(float x) {
     return r;
 }
 
+// 1 / (1 + e^-x) in full fp32 (expf and an IEEE division): the split-bf16 mode's activation, where the tanh / ex2 forms'
+// 2^-11 .. 2^-21 relative error would be the largest error left.
+__device__ __forceinline__ float sigmoid_fp32(float x) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x))); }
+// y -> (hi, lo) bf16 with hi + lo = y to ~2^-17 relative
+__device__ __forceinline__ void split_pair_bf16(float y0, float y1, uint32_t& hi, uint32_t& lo) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(y0, y1);
+    const float2 hf = __bfloat1622float2(h);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(__fsub_rn(y0, hf.x), __fsub_rn(y1, hf.y));
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+// SPLIT (hf6d_set_encoder_mode(ctx, 1)): near-fp32 products out of bf16 tensor-core operands.  Every operand x is held as
+// two bf16 numbers x_hi = bf16(x), x_lo = bf16(x - x_hi), and a product a*w is accumulated (fp32, TMEM) as
+//     a_hi*w_hi + a_lo*w_hi + a_hi*w_lo            (a_lo*w_lo ~ 2^-18 |a w| is dropped)
+// -- three passes over K instead of one, expressed as ONE k-loop of n_seg * K / 64 blocks whose segments address different
+// column ranges of the operand matrices: A = [a_hi | a_lo] ([M][2K]), W = [w_hi | w_lo] ([N][2K]);
+//     segment 0: A cols [0,K) x W cols [0,K);  1: A [K,2K) x W [0,K);  2 (the last): A [0,K) x W [K,2K).
+// The first layer's input (quantised patch values 0..255) is exact in bf16, so it runs two segments (A x w_hi, A x w_lo).
+// Hidden layers store sigmoid(x) as hi and lo halves ([M][2 n_pad]: lo at column lo_off + n), the feature layer fp32.
+// Same ring, same barriers, same MMA shape as the bf16 mode; measured against the fp32 oracle in tests/test_gpu_e2e.py.
+//
 // LAST=false : out is bf16 [m_cap][n_pad], all BLOCK_N columns stored (padded columns hold sigma(0)=0.5 and meet
 //              zero weight columns in the next layer); `bias` holds 0.5*b (the tanh form wants x/2)
 // LAST=true  : out is fp32 [m_cap][n_valid]; columns >= n_valid are clipped by the TMA store
@@ -78,11 +100,11 @@ __device__ __forceinline__ float sigmoid_accurate(float x) {
 //                          producers' TMA loads complete on it (cp.async.bulk.tensor.cta_group::2)
 //                empty[s]  one per CTA: tcgen05.commit.cta_group::2 multicast frees the stage in both
 //                tfull[a]  one per CTA, same multicast commit; tempty[a] in the even CTA counts the epilogue warps of both
-template <int BLOCK_N, bool LAST, int STAGES, int EPI_BUFS, int PAIR, int CHUNK_BYTES, int EPI_WARPS>
+template <int BLOCK_N, bool LAST, int STAGES, int EPI_BUFS, int PAIR, int CHUNK_BYTES, int EPI_WARPS, bool SPLIT = false>
 __global__ void __launch_bounds__((4 + EPI_WARPS) * 32, 1)
 encoder_layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmC, const float* __restrict__ bias,
-                     const int* __restrict__ m_ptr, int K, int n_pad, int reverse_m) {
+                     const int* __restrict__ m_ptr, int K, int n_pad, int reverse_m, int n_seg, int lo_off) {
     using S = EncSmem<BLOCK_N, STAGES, EPI_BUFS, PAIR, CHUNK_BYTES, EPI_WARPS>;
     static_assert(PAIR == 1 || PAIR == 2, "stand-alone CTAs or CTA pairs");
     static_assert(EPI_WARPS % 4 == 0, "every TMEM lane quadrant needs the same number of epilogue warps");
@@ -104,7 +126,8 @@ encoder_layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     const int M = __shfl_sync(0xffffffffu, *m_ptr, 0);
     const int m_blocks = (M + ENC_BLOCK_M - 1) / ENC_BLOCK_M;
     const int n_blocks = n_pad / BLOCK_N;
-    const int k_blocks = K / ENC_BLOCK_K;
+    const int k_seg = K / ENC_BLOCK_K;                 // k-blocks per segment
+    const int k_blocks = (SPLIT ? n_seg : 1) * k_seg;  // k-blocks per tile
     // tile schedule: work item -> (m-block group, n-block); both CTAs of a pair walk the same items
     const int cta_rank = PAIR > 1 ? (int)ptx::cluster_ctarank() : 0;
     const int m_groups = (m_blocks + PAIR - 1) / PAIR;
@@ -155,19 +178,28 @@ encoder_layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         for (int t = first; t < tiles; t += step) {
             const int mb = m_group_of(t / n_blocks) * PAIR + cta_rank, nb = t % n_blocks;
             for (int kb = 0; kb < k_blocks; ++kb) {
+                // operand columns of this k-block: the bf16 mode walks both matrices in step; the split mode's segments
+                // pair (a_hi, w_hi), (a_lo, w_hi), (a_hi, w_lo) -- the last segment reads the lo half of W, the middle one
+                // of three the lo half of A
+                int ka = kb, kw = kb;
+                if constexpr (SPLIT) {
+                    const int seg = kb / k_seg, j = kb - seg * k_seg;
+                    ka = (n_seg == 3 && seg == 1) ? k_seg + j : j;
+                    kw = (seg == n_seg - 1) ? k_seg + j : j;
+                }
                 ptx::mbar_wait(&empty[stage], phase ^ 1);
                 uint8_t* sa = smem + stage * S::STAGE_BYTES;
                 uint8_t* sb = sa + S::A_BYTES;
                 if (ptx::elect_one()) {
                     if constexpr (PAIR > 1) {
                         if (cta_rank == 0) ptx::mbar_arrive_expect_tx(&full[stage], PAIR * S::STAGE_BYTES);
-                        ptx::tma_load_2d_pair(sa, &tmA, full0 + stage * 8, kb * ENC_BLOCK_K, mb * ENC_BLOCK_M);
-                        ptx::tma_load_2d_pair(sb, &tmB, full0 + stage * 8, kb * ENC_BLOCK_K,
+                        ptx::tma_load_2d_pair(sa, &tmA, full0 + stage * 8, ka * ENC_BLOCK_K, mb * ENC_BLOCK_M);
+                        ptx::tma_load_2d_pair(sb, &tmB, full0 + stage * 8, kw * ENC_BLOCK_K,
                                               nb * BLOCK_N + cta_rank * (BLOCK_N / 2));
                     } else {
                         ptx::mbar_arrive_expect_tx(&full[stage], S::STAGE_BYTES);
-                        ptx::tma_load_2d(sa, &tmA, &full[stage], kb * ENC_BLOCK_K, mb * ENC_BLOCK_M);
-                        ptx::tma_load_2d(sb, &tmB, &full[stage], kb * ENC_BLOCK_K, nb * BLOCK_N);
+                        ptx::tma_load_2d(sa, &tmA, &full[stage], ka * ENC_BLOCK_K, mb * ENC_BLOCK_M);
+                        ptx::tma_load_2d(sb, &tmB, &full[stage], kw * ENC_BLOCK_K, nb * BLOCK_N);
                     }
                 }
                 __syncwarp();
@@ -262,8 +294,18 @@ encoder_layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                     }
                 }
                 uint32_t o[UNITS * 4];
+                uint32_t o_lo[(SPLIT && !LAST) ? UNITS * 4 : 1];  // split mode, hidden layers: the lo halves of the same chunk
                 const uint32_t bias_addr = ptx::smem_u32(s_bias + col);  // broadcast reads, 16 bytes each
-                if constexpr (!LAST) {
+                if constexpr (!LAST && SPLIT) {
+#pragma unroll
+                    for (int j = 0; j < CHUNK_COLS / 4; ++j) {
+                        const float4 b = ptx::ld_shared_f4(bias_addr + 16 * j);
+                        split_pair_bf16(sigmoid_fp32(__fadd_rn(__uint_as_float(v[4 * j]), b.x)),
+                                        sigmoid_fp32(__fadd_rn(__uint_as_float(v[4 * j + 1]), b.y)), o[2 * j], o_lo[2 * j]);
+                        split_pair_bf16(sigmoid_fp32(__fadd_rn(__uint_as_float(v[4 * j + 2]), b.z)),
+                                        sigmoid_fp32(__fadd_rn(__uint_as_float(v[4 * j + 3]), b.w)), o[2 * j + 1], o_lo[2 * j + 1]);
+                    }
+                } else if constexpr (!LAST) {
 #pragma unroll
                     for (int j = 0; j < CHUNK_COLS / 4; ++j) {
                         const float4 b = ptx::ld_shared_f4(bias_addr + 16 * j);
@@ -276,25 +318,38 @@ encoder_layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 #pragma unroll
                     for (int j = 0; j < CHUNK_COLS / 4; ++j) {
                         const float4 b = ptx::ld_shared_f4(bias_addr + 16 * j);
-                        o[4 * j] = __float_as_uint(sigmoid_accurate(__uint_as_float(v[4 * j]) + b.x));
-                        o[4 * j + 1] = __float_as_uint(sigmoid_accurate(__uint_as_float(v[4 * j + 1]) + b.y));
-                        o[4 * j + 2] = __float_as_uint(sigmoid_accurate(__uint_as_float(v[4 * j + 2]) + b.z));
-                        o[4 * j + 3] = __float_as_uint(sigmoid_accurate(__uint_as_float(v[4 * j + 3]) + b.w));
+                        if constexpr (SPLIT) {
+                            o[4 * j] = __float_as_uint(sigmoid_fp32(__fadd_rn(__uint_as_float(v[4 * j]), b.x)));
+                            o[4 * j + 1] = __float_as_uint(sigmoid_fp32(__fadd_rn(__uint_as_float(v[4 * j + 1]), b.y)));
+                            o[4 * j + 2] = __float_as_uint(sigmoid_fp32(__fadd_rn(__uint_as_float(v[4 * j + 2]), b.z)));
+                            o[4 * j + 3] = __float_as_uint(sigmoid_fp32(__fadd_rn(__uint_as_float(v[4 * j + 3]), b.w)));
+                        } else {
+                            o[4 * j] = __float_as_uint(sigmoid_accurate(__uint_as_float(v[4 * j]) + b.x));
+                            o[4 * j + 1] = __float_as_uint(sigmoid_accurate(__uint_as_float(v[4 * j + 1]) + b.y));
+                            o[4 * j + 2] = __float_as_uint(sigmoid_accurate(__uint_as_float(v[4 * j + 2]) + b.z));
+                            o[4 * j + 3] = __float_as_uint(sigmoid_accurate(__uint_as_float(v[4 * j + 3]) + b.w));
+                        }
                     }
                 }
-                const uint32_t buf = stage_base + (uint32_t)(it % EPI_BUFS) * S::EPI_BUF_BYTES;
-                if (it >= EPI_BUFS) {  // the TMA store that last used this buffer must have read it
-                    if (ptx::elect_one()) ptx::tma_store_wait_read<EPI_BUFS - 1>();  // always the same lane: bulk groups are per thread
-                    __syncwarp();
-                }
+                // one staged chunk + TMA store per half (the bf16 mode and the feature layer have a single "half")
 #pragma unroll
-                for (int u = 0; u < UNITS; ++u)
-                    ptx::st_shared_v4(buf + row_off + (((uint32_t)u ^ sw) << 4), o[4 * u], o[4 * u + 1], o[4 * u + 2], o[4 * u + 3]);
-                ptx::fence_proxy_async();
-                __syncwarp();
-                if (ptx::elect_one()) {
-                    ptx::tma_store_2d(&tmC, reinterpret_cast<const void*>(smem + (buf - ptx::smem_u32(smem))), col, row0);
-                    ptx::tma_store_commit();
+                for (int half = 0; half < ((SPLIT && !LAST) ? 2 : 1); ++half) {
+                    const uint32_t* ov = half ? o_lo : o;
+                    const uint32_t buf = stage_base + (uint32_t)(it % EPI_BUFS) * S::EPI_BUF_BYTES;
+                    if (it >= EPI_BUFS) {  // the TMA store that last used this buffer must have read it
+                        if (ptx::elect_one()) ptx::tma_store_wait_read<EPI_BUFS - 1>();  // always the same lane: bulk groups are per thread
+                        __syncwarp();
+                    }
+#pragma unroll
+                    for (int u = 0; u < UNITS; ++u)
+                        ptx::st_shared_v4(buf + row_off + (((uint32_t)u ^ sw) << 4), ov[4 * u], ov[4 * u + 1], ov[4 * u + 2], ov[4 * u + 3]);
+                    ptx::fence_proxy_async();
+                    __syncwarp();
+                    if (ptx::elect_one()) {
+                        ptx::tma_store_2d(&tmC, reinterpret_cast<const void*>(smem + (buf - ptx::smem_u32(smem))), col + half * lo_off, row0);
+                        ptx::tma_store_commit();
+                    }
+                    if (half + 1 < ((SPLIT && !LAST) ? 2 : 1)) ++it;
                 }
             }
             if (sub >= TILE_CHUNKS) {  // a warp without any chunk still has to release the accumulator
@@ -371,16 +426,18 @@ inline bool make_out_map(CUtensorMap* map, void* base, uint64_t rows, uint64_t c
 
 struct EncoderLayerLaunch {
     CUtensorMap tmA, tmB, tmC;  // tmB: box of block_n / pair rows; tmC: boxes of 32 rows x chunk bytes
-    const float* bias;          // hidden layers: 0.5 * b
-    int K, n_pad, block_n;
+    const float* bias;          // hidden layers: 0.5 * b (bf16 mode), b (split mode)
+    int K, n_pad, block_n;      // K: columns of ONE half of the operands in split mode
     bool last, short_k;  // short_k: few K blocks per tile
     int variant;         // row of HF6D_ENC_CONFIGS for this layer's shape class
     int reverse_m;       // walk the m-blocks from the end (see the kernel)
+    bool split;          // split-bf16 arithmetic (see the kernel): variant then selects pairs (0) or stand-alone CTAs (1)
+    int n_seg, lo_off;   // split: k segments (2: exact A, 3: hi/lo A); column offset of the lo halves in the hidden output
 };
 
-template <int BLOCK_N, bool LAST, int STAGES, int EPI_BUFS, int PAIR, int CHUNK_BYTES, int EPI_WARPS>
+template <int BLOCK_N, bool LAST, int STAGES, int EPI_BUFS, int PAIR, int CHUNK_BYTES, int EPI_WARPS, bool SPLIT = false>
 inline cudaError_t launch_encoder_layer_t(const EncoderLayerLaunch& L, const int* m_ptr, int sms, cudaStream_t st, bool probe) {
-    auto kern = encoder_layer_kernel<BLOCK_N, LAST, STAGES, EPI_BUFS, PAIR, CHUNK_BYTES, EPI_WARPS>;
+    auto kern = encoder_layer_kernel<BLOCK_N, LAST, STAGES, EPI_BUFS, PAIR, CHUNK_BYTES, EPI_WARPS, SPLIT>;
     using S = EncSmem<BLOCK_N, STAGES, EPI_BUFS, PAIR, CHUNK_BYTES, EPI_WARPS>;
     static int grid = 0;
     if (!grid) {
@@ -414,7 +471,8 @@ inline cudaError_t launch_encoder_layer_t(const EncoderLayerLaunch& L, const int
     attrs[0].val.clusterDim.x = PAIR; attrs[0].val.clusterDim.y = 1; attrs[0].val.clusterDim.z = 1;
     cfg.attrs = attrs;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kern, L.tmA, L.tmB, L.tmC, L.bias, m_ptr, L.K, L.n_pad, L.reverse_m);
+    return cudaLaunchKernelEx(&cfg, kern, L.tmA, L.tmB, L.tmC, L.bias, m_ptr, L.K, L.n_pad, L.reverse_m, SPLIT ? L.n_seg : 1,
+                              L.lo_off);
 }
 
 // The kernel configurations, one table for the launcher and for the slot's tensor maps (W box rows, output chunk width).
@@ -451,6 +509,19 @@ inline cudaError_t launch_encoder_layer_t(const EncoderLayerLaunch& L, const int
     X(3, 0, 256, true, 4, 2, 2, 64, 8)                             \
     X(3, 1, 256, true, 4, 1, 1, 64, 8)
 
+// Split-bf16 mode (hf6d_set_encoder_mode 1): one configuration per tile shape -- it is the accuracy mode, three passes over
+// K, so there is no tuning table.  EPI_BUFS = 2: a hidden-layer chunk is staged and stored twice (hi and lo halves).
+//   variant 0 = CTA pairs, variant 1 = stand-alone CTAs (devices that cannot co-schedule clusters; no 208-wide tiles).
+#define HF6D_ENC_SPLIT_CONFIGS(X)                  \
+    /*  var  N   LAST  ST EB PAIR CHUNK EPI */     \
+    X(0, 256, false, 4, 2, 2, 128, 8)              \
+    X(0, 208, true, 5, 2, 2, 64, 8)                \
+    X(0, 160, true, 5, 2, 2, 128, 8)               \
+    X(0, 256, true, 4, 2, 2, 64, 8)                \
+    X(1, 256, false, 3, 2, 1, 128, 8)              \
+    X(1, 160, true, 4, 2, 1, 128, 8)               \
+    X(1, 256, true, 3, 2, 1, 64, 8)
+
 inline int encoder_shape_class(int block_n, bool last, bool short_k) {
     if (!last) return short_k ? 0 : 1;
     return block_n == 160 ? 2 : block_n == 208 ? 4 : 3;
@@ -460,7 +531,14 @@ struct EncoderConfig {
     int pair, chunk_bytes;
 };
 // pair == 0: no such variant
-inline EncoderConfig encoder_config(int block_n, bool last, bool short_k, int variant) {
+inline EncoderConfig encoder_config(int block_n, bool last, bool short_k, int variant, bool split = false) {
+    if (split) {
+#define X(VAR, N, LAST, ST, EB, PAIR, CHUNK, EPI) \
+    if (variant == VAR && block_n == N && last == LAST) return EncoderConfig{PAIR, CHUNK};
+        HF6D_ENC_SPLIT_CONFIGS(X)
+#undef X
+        return EncoderConfig{0, 0};
+    }
     const int cls = encoder_shape_class(block_n, last, short_k);
 #define X(CLS, VAR, N, LAST, ST, EB, PAIR, CHUNK, EPI) \
     if (cls == CLS && variant == VAR && block_n == N) return EncoderConfig{PAIR, CHUNK};
@@ -472,6 +550,14 @@ inline EncoderConfig encoder_config(int block_n, bool last, bool short_k, int va
 // probe = true: only check that this variant can run on the current device (shared memory opt-in, cluster occupancy).
 inline cudaError_t launch_encoder_layer(const EncoderLayerLaunch& L, const int* m_ptr, int sms, cudaStream_t st,
                                         bool probe = false) {
+    if (L.split) {
+#define X(VAR, N, LAST, ST, EB, PAIR, CHUNK, EPI)                   \
+    if (L.variant == VAR && L.block_n == N && L.last == LAST)       \
+        return launch_encoder_layer_t<N, LAST, ST, EB, PAIR, CHUNK, EPI, true>(L, m_ptr, sms, st, probe);
+        HF6D_ENC_SPLIT_CONFIGS(X)
+#undef X
+        return cudaErrorInvalidValue;
+    }
     const int cls = encoder_shape_class(L.block_n, L.last, L.short_k);
 #define X(CLS, VAR, N, LAST, ST, EB, PAIR, CHUNK, EPI)                 \
     if (cls == CLS && L.variant == VAR && L.block_n == N)              \

@@ -42,6 +42,9 @@ struct DeviceModel {
     __nv_bfloat16* W[3] = {nullptr, nullptr, nullptr};
     float* b[3] = {nullptr, nullptr, nullptr};
     int n_in[3], n_out[3], k_pad[3], n_pad[3], block_n[3];
+    // split-bf16 mode (hf6d_set_encoder_mode 1), uploaded on first use: [n_pad][2 * k_pad] = (w_hi | w_lo), plain biases
+    __nv_bfloat16* Ws[3] = {nullptr, nullptr, nullptr};
+    float* bs[3] = {nullptr, nullptr, nullptr};
     uint8_t* sep_ok = nullptr;
     uint8_t* class_mask = nullptr;  // [HF6D_MAX_CLASSES] classes whose centres / poses this context seeks
 };
@@ -80,6 +83,10 @@ struct Slot {
     uint8_t* res_dev = nullptr;
     uint8_t* res_host = nullptr;  // pinned
     EncoderLayerLaunch enc[3];
+    // split-bf16 mode: hidden activations as (hi | lo) halves [cap][2 * n_pad], allocated on first use
+    __nv_bfloat16 *H1s = nullptr, *H2s = nullptr;
+    EncoderLayerLaunch enc_split[3];
+    bool split_ready = false;
     uint32_t peer_seq = 0;  // frames this slot has pushed through the peer exchange (both flags carry it)
     bool busy = false;  // submit/wait bookkeeping
     int ticket = -1;
@@ -559,8 +566,9 @@ int run_stage(hf6d_ctx* c, Slot& s, int stage) {
         }
         case HF6D_STAGE_ENCODE: {
             CU_TRY(c, cudaEventRecord(s.ev_enc[0], st));
+            if (c->encoder_mode == 1 && !s.split_ready) return fail(c, HF6D_ESTATE, "split encoder buffers missing");
             for (int l = 0; l < 3; ++l) {
-                cudaError_t e = launch_encoder_layer(s.enc[l], s.counts + 1, c->sms, st);
+                cudaError_t e = launch_encoder_layer(c->encoder_mode == 1 ? s.enc_split[l] : s.enc[l], s.counts + 1, c->sms, st);
                 if (e != cudaSuccess) return fail(c, HF6D_ECUDA, "encoder layer %d launch: %s", l, cudaGetErrorString(e));
                 ++s.launches;
                 CU_TRY(c, cudaEventRecord(s.ev_enc[l + 1], st));
@@ -1320,12 +1328,87 @@ int hf6d_peer_timed_out(hf6d_ctx* c) {
     return v;
 }
 
+namespace {
+// Split-bf16 encoder state: weights as (hi | lo) bf16 halves, per-slot (hi | lo) hidden activations and tensor maps.
+int ensure_split_encoder(hf6d_ctx* c) {
+    DeviceModel& dm = c->dm;
+    int r;
+    if (!dm.Ws[0]) {
+        for (int l = 0; l < 3; ++l) {
+            const HostLayer& L = c->layers[l];
+            const size_t kp = (size_t)dm.k_pad[l];
+            std::vector<__nv_bfloat16> w((size_t)dm.n_pad[l] * 2 * kp, __float2bfloat16(0.f));
+            for (int n = 0; n < L.out; ++n)
+                for (int k = 0; k < L.in; ++k) {
+                    float v = L.W[(size_t)n * L.in + k];
+                    if (l == 0) v = v / 255.0f;  // the A operand of the first layer holds q itself
+                    const __nv_bfloat16 hi = __float2bfloat16(v);
+                    w[(size_t)n * 2 * kp + k] = hi;
+                    w[(size_t)n * 2 * kp + kp + k] = __float2bfloat16(v - __bfloat162float(hi));
+                }
+            std::vector<float> b(dm.n_pad[l], 0.f);
+            for (int n = 0; n < L.out; ++n) b[n] = L.b[n];
+            const __nv_bfloat16* wp = nullptr;
+            const float* bp = nullptr;
+            if ((r = dev_upload(c, dm.allocs, &wp, w))) return r;
+            if ((r = dev_upload(c, dm.allocs, &bp, b))) return r;
+            dm.Ws[l] = const_cast<__nv_bfloat16*>(wp);
+            dm.bs[l] = const_cast<float*>(bp);
+        }
+    }
+    const FrameGeom& g = c->g;
+    for (Slot& s : c->slots) {
+        if (s.split_ready) continue;
+        if ((r = dev_alloc(c, s.allocs, &s.H1s, (size_t)g.cap * 2 * dm.n_pad[0]))) return r;
+        if ((r = dev_alloc(c, s.allocs, &s.H2s, (size_t)g.cap * 2 * dm.n_pad[1]))) return r;
+        const void* a_in[3] = {s.A0, s.H1s, s.H2s};
+        void* outs[3] = {s.H1s, s.H2s, s.feat};
+        for (int l = 0; l < 3; ++l) {
+            EncoderLayerLaunch& L = s.enc_split[l];
+            memset(&L, 0, sizeof L);
+            L.split = true;
+            L.last = l == 2;
+            L.variant = c->enc_variant[l] == 1 ? 1 : 0;  // stand-alone CTAs only where pairs cannot be scheduled
+            L.block_n = dm.block_n[l];
+            const EncoderConfig cfg = encoder_config(L.block_n, L.last, false, L.variant, true);
+            if (!cfg.pair) return fail(c, HF6D_EINVAL, "split encoder: no kernel for layer %d (N tile %d, variant %d)", l, L.block_n, L.variant);
+            const uint64_t a_cols = l == 0 ? (uint64_t)dm.k_pad[0] : 2ull * dm.k_pad[l];
+            if (!make_bf16_kmajor_map(&L.tmA, a_in[l], (uint64_t)g.cap, a_cols, ENC_BLOCK_M) ||
+                !make_bf16_kmajor_map(&L.tmB, dm.Ws[l], (uint64_t)dm.n_pad[l], 2ull * dm.k_pad[l], (uint32_t)(L.block_n / cfg.pair)) ||
+                !make_out_map(&L.tmC, outs[l], (uint64_t)g.cap, (uint64_t)(L.last ? c->hf.F : 2 * dm.n_pad[l]), L.last ? 4 : 2, cfg.chunk_bytes))
+                return fail(c, HF6D_ECUDA, "cuTensorMapEncodeTiled failed for split encoder layer %d", l);
+            L.bias = dm.bs[l];
+            L.K = dm.k_pad[l];
+            L.n_pad = dm.n_pad[l];
+            L.short_k = false;
+            L.reverse_m = s.enc[l].reverse_m;
+            L.n_seg = l == 0 ? 2 : 3;
+            L.lo_off = L.last ? 0 : dm.n_pad[l];
+            if (launch_encoder_layer(L, nullptr, c->sms, nullptr, true) != cudaSuccess) {
+                cudaGetLastError();
+                return fail(c, HF6D_ECUDA, "split encoder layer %d cannot run on this device", l);
+            }
+        }
+        s.split_ready = true;
+    }
+    return HF6D_OK;
+}
+}  // namespace
+
 int hf6d_set_encoder_mode(hf6d_ctx* c, int mode) {
     if (!c) return HF6D_EINVAL;
-    if (mode != 0) return fail(c, HF6D_EINVAL, "encoder mode %d not available", mode);
+    if (mode != 0 && mode != 1) return fail(c, HF6D_EINVAL, "encoder mode %d: 0 = bf16 operands, 1 = split bf16 (hi + lo)", mode);
+    CU_TRY(c, cudaSetDevice(c->device));
+    CU_TRY(c, cudaDeviceSynchronize());
+    if (mode == 1) {
+        const int r = ensure_split_encoder(c);
+        if (r) return r;
+    }
     c->encoder_mode = mode;
     return HF6D_OK;
 }
+
+int hf6d_get_encoder_mode(const hf6d_ctx* c) { return c ? c->encoder_mode : HF6D_EINVAL; }
 
 int hf6d_set_debug_capture(hf6d_ctx* c, int on) {
     if (!c) return HF6D_EINVAL;
@@ -1571,6 +1654,26 @@ int64_t hf6d_result_bytes(const hf6d_ctx* c) { return c ? (int64_t)c->rl.total :
 int hf6d_launch_count(const hf6d_ctx* c, int slot) {
     if (!c || slot < 0 || slot >= c->n_slots) return HF6D_EINVAL;
     return c->slots[slot].launches;
+}
+
+int64_t hf6d_count_cast_votes(hf6d_ctx* c, int slot) {
+    int r = check_slot(c, slot);
+    if (r) return r;
+    Slot& s = c->slots[slot];
+    CU_TRY(c, cudaSetDevice(c->device));
+    CU_TRY(c, cudaStreamSynchronize(s.stream));
+    int counts[2];
+    CU_TRY(c, cudaMemcpy(counts, s.counts, 8, cudaMemcpyDeviceToHost));
+    const size_t Pp = (size_t)std::min(counts[1], c->g.cap), T = (size_t)c->hf.T;
+    std::vector<int> ord(Pp * T);
+    if (Pp) CU_TRY(c, cudaMemcpy(ord.data(), s.leaf_ord, Pp * T * 4, cudaMemcpyDeviceToHost));
+    int64_t n = 0;
+    for (size_t i = 0; i < Pp; ++i)
+        for (size_t t = 0; t < T; ++t) {
+            const int o = ord[i * T + t];
+            if (o >= 0) n += c->hf.leaf_vcnt[(size_t)c->hf.leaf_base[t] + o];
+        }
+    return n;
 }
 
 void hf6d_pose_from_tuple(const hf6d_params* p, int cx, int cy, float z, int yaw_deg, int pitch_deg, int roll_deg,

@@ -62,12 +62,27 @@ def _texture(local, base, kind, freq):
 def render_frame(seed: int, cam: Camera = Camera(), n_objects: int = 6, table: bool = True):
     """Ray-cast a cluttered table-top scene.  Returns (bgr uint8 [H,W,3], depth_mm uint16 [H,W])."""
     rng = np.random.default_rng(seed)
+    bgr, depth, _ = _render(rng, rng, cam, n_objects, table)
+    return bgr, depth
+
+
+def render_scene(frame_seed: int, object_seed: int, cam: Camera = Camera(), n_objects: int = 6, table: bool = True):
+    """The same ray-caster with the object SET fixed by object_seed (shape, size, albedo, texture: the stand-ins for
+    meshes/*.ply) and only the poses drawn from frame_seed -- frames of one scene family, as a detector is trained and
+    tested on.  Returns (bgr, depth_mm, truth) with truth = dict(obj_id int8 [H,W] (-1: table / background),
+    R [n,3,3] object -> camera rotations, centre [n,3] object centres in the camera frame [m])."""
+    return _render(np.random.default_rng(object_seed), np.random.default_rng(frame_seed), cam, n_objects, table)
+
+
+def _render(rng, rng_pose, cam, n_objects, table):
     H, W = cam.H, cam.W
     v, u = np.mgrid[0:H, 0:W]
     d = np.stack([(u - cam.cx) / cam.fx, (v - cam.cy) / cam.fy, np.ones((H, W))], -1).reshape(-1, 3)
     N = d.shape[0]
     tbest = np.full(N, np.inf)
     color = np.full((N, 3), 255.0)  # white background (renderer .cpp:260)
+    obj_id = np.full(N, -1, np.int8)
+    truth_R, truth_c = [], []
     light = np.array([0.3, -0.6, -0.74])
     light /= np.linalg.norm(light)
 
@@ -93,11 +108,13 @@ def render_frame(seed: int, cam: Camera = Camera(), n_objects: int = 6, table: b
         size = rng.uniform(0.05, 0.2, 3)
         if n_objects == 1:
             centre = np.array([0.0, 0.0, 0.7])  # C1: one object, centred, 0.7 m
-            R = _rot_axis(rng.normal(size=3), rng.uniform(0, 6.283))
+            R = _rot_axis(rng_pose.normal(size=3), rng_pose.uniform(0, 6.283))
         else:
-            a, b = rng.uniform(-0.33, 0.33), rng.uniform(-0.22, 0.22)
-            R = np.stack([ex, -n_pl, ez], 1) @ _rot_axis([0, 1, 0], rng.uniform(0, 6.283))
+            a, b = rng_pose.uniform(-0.33, 0.33), rng_pose.uniform(-0.22, 0.22)
+            R = np.stack([ex, -n_pl, ez], 1) @ _rot_axis([0, 1, 0], rng_pose.uniform(0, 6.283))
             centre = p0 + a * ex + b * ez + n_pl * (size[1] * 0.5)
+        truth_R.append(R)
+        truth_c.append(centre)
         base = rng.uniform(40, 230, 3)
         tkind, freq = int(rng.integers(0, 3)), rng.uniform(15, 60)
         o = -(R.T @ centre)  # ray origin in object frame
@@ -142,11 +159,13 @@ def render_frame(seed: int, cam: Camera = Camera(), n_objects: int = 6, table: b
         col = np.clip(_texture(pl, base, tkind, freq) * shade[:, None], 0, 255)
         tbest = np.where(ok, t, tbest)
         color = np.where(ok[:, None], col, color)
+        obj_id = np.where(ok, np.int8(k), obj_id)
 
     depth = np.where(np.isfinite(tbest), np.rint(tbest * 1000.0), 0)  # z == t because d.z == 1
     depth = np.clip(depth, 0, 65535).astype(np.uint16).reshape(H, W)
     bgr = np.ascontiguousarray(np.clip(np.rint(color), 0, 255).astype(np.uint8).reshape(H, W, 3))
-    return bgr, depth
+    truth = dict(obj_id=obj_id.reshape(H, W), R=np.array(truth_R), centre=np.array(truth_c))
+    return bgr, depth, truth
 
 
 # ------------------------------------------------------------------------------------------------ encoder weights
@@ -222,12 +241,17 @@ def calibration_features(bgr, depth, layers, n=8000, cam: Camera = Camera(), see
     Only used to draw split thresholds for synthetic forests from a realistic feature distribution; it is NOT a
     restatement of the product path (no bilinear filter, no sequential sums) and nothing checks against it."""
     rng = np.random.default_rng(seed)
-    H, W = depth.shape
     ys, xs = np.nonzero((depth > 0) & (depth < dist_thr * 1000))
     if ys.size == 0:
         return np.zeros((0, layers[-1][0].shape[0]), np.float32)
     sel = rng.choice(ys.size, size=min(n, ys.size), replace=False)
-    ys, xs = ys[sel], xs[sel]
+    return _patch_features(bgr, depth, ys[sel], xs[sel], layers, cam, patch_vox, voxel_m, max_range)[0]
+
+
+def _patch_features(bgr, depth, ys, xs, layers, cam, patch_vox=8, voxel_m=0.005, max_range=0.25):
+    """Approximate encoder features of the patches centred at (xs, ys); returns (features, ys, xs) of the patches that
+    lie inside the image."""
+    H, W = depth.shape
     dc = depth[ys, xs].astype(np.float32) / 1000.0
     a = (patch_vox * voxel_m / dc * cam.fx).astype(np.int64)
     ok = (xs - a // 2 >= 0) & (ys - a // 2 >= 0) & (xs - a // 2 + a - 1 < W) & (ys - a // 2 + a - 1 < H) & (a > 0)
@@ -255,10 +279,45 @@ def calibration_features(bgr, depth, layers, n=8000, cam: Camera = Camera(), see
     h = out.astype(np.float32)
     for Wm, b in layers:
         h = 1.0 / (1.0 + np.exp(-(h @ Wm.T + b)))
-    return np.ascontiguousarray(h, np.float32)
+    return np.ascontiguousarray(h, np.float32), ys, xs
+
+
+def euler_from_rotation(R):
+    """(yaw, pitch, roll) with R = diag(1,-1,-1) Rz(yaw) Ry(pitch) Rx(roll): the convention of the forest's votes
+    (HoughForest/src/HFTest.cpp:41-80) and of the pre-ICP pose (MeshUtils.cpp:29-59, 423-440)."""
+    M = np.diag([1.0, -1.0, -1.0]) @ np.asarray(R, np.float64)
+    return np.arctan2(M[1, 0], M[0, 0]), -np.arcsin(np.clip(M[2, 0], -1.0, 1.0)), np.arctan2(M[2, 1], M[2, 2])
+
+
+def labelled_patches(bgr, depth, truth, layers, n=15000, cam: Camera = Camera(), seed=0, stride=2, dist_thr=1.5):
+    """Training samples for a synthetic Hough forest from one rendered frame with ground truth: patches centred on object
+    pixels of the stride grid, each with its (approximate) encoder feature vector, its class, and the 6-DoF vote a trainer
+    would store for it (HoughForest/src/HFTrain.cpp:124, 198-202): the object's yaw / pitch / roll in the camera frame and the
+    position of the patch in the object frame, so that  R (-x, -y, -z) + t  (HFTest.cpp:41-102) is the object centre.
+    Returns (features [m,F] f32, cls [m] int, votes [m,6] f32)."""
+    rng = np.random.default_rng(seed)
+    oid = truth["obj_id"]
+    grid = np.zeros(depth.shape, bool)
+    grid[::stride, ::stride] = True
+    ys, xs = np.nonzero(grid & (oid >= 0) & (depth > 0) & (depth < dist_thr * 1000))
+    if ys.size == 0:
+        return np.zeros((0, layers[-1][0].shape[0]), np.float32), np.zeros(0, np.int64), np.zeros((0, 6), np.float32)
+    sel = rng.choice(ys.size, size=min(n, ys.size), replace=False)
+    feats, ys, xs = _patch_features(bgr, depth, ys[sel], xs[sel], layers, cam)
+    cls = oid[ys, xs].astype(np.int64)
+    z = depth[ys, xs].astype(np.float64) / 1000.0
+    t = np.stack([(xs - cam.cx) * z / cam.fx, (ys - cam.cy) * z / cam.fy, z], 1)
+    votes = np.zeros((len(ys), 6), np.float32)
+    for k in range(truth["R"].shape[0]):
+        m = cls == k
+        if not m.any():
+            continue
+        votes[m, :3] = euler_from_rotation(truth["R"][k])
+        votes[m, 3:] = (t[m] - truth["centre"][k]) @ truth["R"][k]  # R^T (t - c): the patch in the object frame
+    return feats, cls, votes
 
 # ----------------------------------------------------------------------------------------------------- forests
-def _build_tree(rng, feats, max_depth, min_samples, K, votes_per_leaf, prob_quantum=0):
+def _build_tree(rng, feats, max_depth, min_samples, K, votes_per_leaf, prob_quantum=0, balanced=False):
     """Level-wise random tree over a calibration batch.  Returns dict of node arrays (index 0 = root)."""
     N, F = feats.shape
     is_leaf, mode, f1, f2, thr, left, right, depth_of = [], [], [], [], [], [], [], []
@@ -292,19 +351,47 @@ def _build_tree(rng, feats, max_depth, min_samples, K, votes_per_leaf, prob_quan
         if nodes.size == 0:
             break
         s_, c_ = starts[split], counts[split]
-        m = rng.integers(0, 2, nodes.size)
-        a = rng.integers(0, F, nodes.size)
-        b = rng.integers(0, F, nodes.size)
-        # threshold ~ U(min, max) of the test's values over the node's samples, as the trainer draws it
-        # (HoughForest/src/HFTrain.cpp:365-386: rand()/RAND_MAX * range + min)
+        # A test is drawn the way the trainer draws it (HoughForest/src/HFTrain.cpp:365-386: random measure mode and
+        # features, threshold = rand()/RAND_MAX * range + min over the node's samples).  The trainer keeps the best of many
+        # such tests by information gain, so a test that cannot separate the node's samples (range 0: identical feature
+        # values, which flat synthetic surfaces produce in bulk) is never kept: here the widest of a few candidates is taken,
+        # and a node none of them can split stays a leaf, like the trainer's unsplittable nodes.
         seg_id = np.repeat(np.arange(nodes.size), c_)
         seg_smp = order[np.concatenate([np.arange(s, s + c) for s, c in zip(s_, c_)])]
-        seg_val = np.where(m[seg_id] == 0, feats[seg_smp, a[seg_id]] - feats[seg_smp, b[seg_id]],
-                           feats[seg_smp, a[seg_id]]).astype(np.float32)
         starts_rel = np.concatenate([[0], np.cumsum(c_)[:-1]])
-        vmin = np.minimum.reduceat(seg_val, starts_rel)
-        vmax = np.maximum.reduceat(seg_val, starts_rel)
-        th = (rng.random(nodes.size).astype(np.float32) * (vmax - vmin) + vmin).astype(np.float32)
+        m = np.zeros(nodes.size, np.int64)
+        a = np.zeros(nodes.size, np.int64)
+        b = np.zeros(nodes.size, np.int64)
+        vmin = np.zeros(nodes.size, np.float32)
+        vmax = np.zeros(nodes.size, np.float32)
+        for cand in range(4):
+            m_c = rng.integers(0, 2, nodes.size)
+            a_c = rng.integers(0, F, nodes.size)
+            b_c = rng.integers(0, F, nodes.size)
+            seg_val = np.where(m_c[seg_id] == 0, feats[seg_smp, a_c[seg_id]] - feats[seg_smp, b_c[seg_id]],
+                               feats[seg_smp, a_c[seg_id]]).astype(np.float32)
+            lo_c = np.minimum.reduceat(seg_val, starts_rel)
+            hi_c = np.maximum.reduceat(seg_val, starts_rel)
+            better = (hi_c - lo_c) > (vmax - vmin) if cand else np.ones(nodes.size, bool)
+            m, a, b = np.where(better, m_c, m), np.where(better, a_c, a), np.where(better, b_c, b)
+            vmin, vmax = np.where(better, lo_c, vmin), np.where(better, hi_c, vmax)
+        if balanced:
+            # the trainer keeps the best of tests_per_node x thresholds_per_test candidates by information gain
+            # (HoughForest/src/main.cpp:16-18), which favours even splits: here the median of three sample values
+            seg_val = np.where(m[seg_id] == 0, feats[seg_smp, a[seg_id]] - feats[seg_smp, b[seg_id]],
+                               feats[seg_smp, a[seg_id]]).astype(np.float32)
+            # ... placed half way to the next different value, so that no training sample sits ON a threshold
+            pick = starts_rel[:, None] + (rng.random((nodes.size, 3)) * c_[:, None]).astype(np.int64)
+            srt = np.sort(seg_val[pick], axis=1)
+            other = np.where(srt[:, 2] > srt[:, 1], srt[:, 2], np.where(srt[:, 0] < srt[:, 1], srt[:, 0], vmax))
+            other = np.where(other == srt[:, 1], vmin, other)
+            th = (srt[:, 1].astype(np.float64) * 0.5 + other.astype(np.float64) * 0.5).astype(np.float32)
+        else:
+            th = (rng.random(nodes.size).astype(np.float32) * (vmax - vmin) + vmin).astype(np.float32)
+        ok = (vmax > vmin) & (th > vmin)  # both children receive a sample
+        nodes, m, a, b, th = nodes[ok], m[ok], a[ok], b[ok], th[ok]
+        if nodes.size == 0:
+            break
         base = new_nodes(2 * nodes.size, d + 1)
         lch = base + 2 * np.arange(nodes.size)
         for i, n in enumerate(nodes):
@@ -339,7 +426,7 @@ def _build_tree(rng, feats, max_depth, min_samples, K, votes_per_leaf, prob_quan
         probs = rest
     probs[np.arange(nl), dom] = p_dom if K > 1 else 1.0
     sample_depth = float(np.mean(np.array(depth_of)[node_of])) if N else 0.0
-    return dict(sample_depth=sample_depth, is_leaf=is_leaf, mode=np.array(mode, np.int32), f1=np.array(f1, np.int32), f2=np.array(f2, np.int32),
+    return dict(node_of=node_of, sample_depth=sample_depth, is_leaf=is_leaf, mode=np.array(mode, np.int32), f1=np.array(f1, np.int32), f2=np.array(f2, np.int32),
                 thr=np.array(thr, np.float32), left=np.array(left, np.int64), right=np.array(right, np.int64),
                 leaf_idx=leaf_idx, dom=dom, probs=probs, n_nodes=n_nodes, votes_per_leaf=votes_per_leaf)
 
@@ -356,6 +443,8 @@ def _random_votes(rng, n):
 def _serialise_tree(rng, tree, K) -> bytes:
     """Pre-order, left first (HFBase.cpp:4-38).  leaf_id values are a random permutation: the trainer numbers leaves
     in hash-map order (HFTrain.cpp:167), not file order."""
+    if "leaf_votes" in tree:
+        return _serialise_trained_tree(rng, tree, K)
     out = bytearray()
     leaf_pos = {int(n): i for i, n in enumerate(tree["leaf_idx"])}
     ids = rng.permutation(len(leaf_pos)).astype(np.int32)
@@ -384,6 +473,92 @@ def _serialise_tree(rng, tree, K) -> bytes:
             stack.append(int(right[n]))
             stack.append(int(left[n]))
     return bytes(out)
+
+
+def _serialise_trained_tree(rng, tree, K) -> bytes:
+    """As _serialise_tree, with the leaf payloads of write_trained_forest: probs [nl][K], leaf_votes[li][c] = [m,6]."""
+    out = bytearray()
+    leaf_pos = {int(n): i for i, n in enumerate(tree["leaf_idx"])}
+    ids = rng.permutation(len(leaf_pos)).astype(np.int32)
+    stack = [0]
+    is_leaf, mode, f1, f2, thr = tree["is_leaf"], tree["mode"], tree["f1"], tree["f2"], tree["thr"]
+    left, right = tree["left"], tree["right"]
+    file_order = 0
+    empty = np.zeros((0, 6), np.float32)
+    while stack:
+        n = stack.pop()
+        if is_leaf[n]:
+            li = leaf_pos[n]
+            out += struct.pack("<Bi", 1, int(ids[file_order]))
+            file_order += 1
+            out += np.ascontiguousarray(tree["probs"][li], np.float32).tobytes()
+            for c in range(K):
+                v = tree["leaf_votes"][li].get(c, empty)
+                out += struct.pack("<i", len(v))
+                out += np.ascontiguousarray(v, np.float32).tobytes()
+        else:
+            out += struct.pack("<Biiif", 0, int(mode[n]), int(f1[n]), int(f2[n]), float(thr[n]))
+            stack.append(int(right[n]))
+            stack.append(int(left[n]))
+    return bytes(out)
+
+
+def write_trained_forest(folder: str, feats: np.ndarray, cls: np.ndarray, votes: np.ndarray, T: int = 4, K: int = 6,
+                         max_depth: int = 20, min_samples: int = 2, views: int = 16, max_votes: int = 64, seed: int = 7,
+                         angle_jitter_deg: float = 3.0, offset_jitter_m: float = 0.002, patch_vox: int = 8,
+                         voxel_m: float = 0.005) -> dict:
+    """A Hough forest with the payload a trained one has, from labelled samples (labelled_patches): random balanced trees
+    as in write_forest, but every leaf holds the class distribution of the samples that reach it and, per class, the 6-DoF
+    votes of those samples (HFTrain.cpp:124, 198-202 stores every training sample's).  Each sample stands for `views`
+    training views of the same surface point from neighbouring camera poses -- what the reference's tessellated-sphere
+    renderings provide -- i.e. `views` votes jittered by a few degrees / millimetres.  Unlike write_forest's uniformly random
+    votes these are COHERENT: they pile up on the true object centres and poses, so the Hough maps have real modes (and the
+    vote scatter has the hot spots a real forest produces).  Returns summary statistics."""
+    os.makedirs(folder, exist_ok=True)
+    feats = np.ascontiguousarray(feats, np.float32)
+    F = feats.shape[1]
+    rng = np.random.default_rng(seed)
+    stats = dict(T=T, K=K, F=F, leaves=[], nodes=[], mean_depth=[], votes=[], trained=True)
+    order_all = None
+    for t in range(T):
+        tree = _build_tree(rng, feats, max_depth, min_samples, K, 0, balanced=True)
+        leaf_idx = tree["leaf_idx"]
+        pos = np.full(tree["n_nodes"], -1, np.int64)
+        pos[leaf_idx] = np.arange(leaf_idx.size)
+        li_of = pos[tree["node_of"]]
+        probs = np.zeros((leaf_idx.size, K), np.float32)
+        np.add.at(probs, (li_of, cls), 1.0)
+        tot = probs.sum(1, keepdims=True)
+        probs = np.where(tot > 0, probs / np.maximum(tot, 1), 0).astype(np.float32)
+        order = np.lexsort((cls, li_of))
+        keys = li_of[order] * K + cls[order]
+        bounds = np.flatnonzero(np.concatenate([[True], keys[1:] != keys[:-1], [True]]))
+        leaf_votes = [dict() for _ in range(leaf_idx.size)]
+        n_votes = 0
+        for b0, b1 in zip(bounds[:-1], bounds[1:]):
+            smp = order[b0:b1]
+            li, c = int(li_of[smp[0]]), int(cls[smp[0]])
+            v = np.repeat(votes[smp], views, axis=0)
+            v[:, :3] += rng.normal(0, np.deg2rad(angle_jitter_deg), v[:, :3].shape).astype(np.float32)
+            v[:, 3:] += rng.normal(0, offset_jitter_m, v[:, 3:].shape).astype(np.float32)
+            v[:, 0] = (v[:, 0] + np.pi) % (2 * np.pi) - np.pi
+            v[:, 1] = np.clip(v[:, 1], -np.pi / 2, np.pi / 2)
+            v[:, 2] = (v[:, 2] + np.pi) % (2 * np.pi) - np.pi
+            if len(v) > max_votes:
+                v = v[rng.choice(len(v), max_votes, replace=False)]
+            leaf_votes[li][c] = v.astype(np.float32)
+            n_votes += len(v)
+        tree["probs"] = probs
+        tree["leaf_votes"] = leaf_votes
+        with open(os.path.join(folder, f"tree{t}.dat"), "wb") as f:
+            f.write(_serialise_tree(rng, tree, K))
+        stats["leaves"].append(int(leaf_idx.size))
+        stats["nodes"].append(int(tree["n_nodes"]))
+        stats["mean_depth"].append(round(tree["sample_depth"], 2))
+        stats["votes"].append(n_votes)
+    with open(os.path.join(folder, "forest.txt"), "w") as f:
+        f.write(f"{T} {K} {F} {patch_vox} {voxel_m:g}\n")
+    return stats
 
 
 def write_forest(folder: str, calib_features: np.ndarray, T: int = 4, K: int = 6, max_depth: int = 20,
