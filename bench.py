@@ -2,17 +2,22 @@
 """bench.py -- HoughForest test-time detection path on B200 (BASELINE.json metric: frames/s and patch-tree
 traversals/s per 640x480 RGB-D frame).
 
-  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (libhf6d.so through its C ABI)
-  python bench.py --impl reference --gpus N --steps K ...  # the reference's algorithm on the host cores (CPU oracle)
+  python bench.py --gpus N --steps K --warmup W [--config c2]    # this repo's CUDA path (libhf6d.so through its C ABI)
+  python bench.py --impl reference --gpus N --steps K ...        # the reference's algorithm on the host cores (CPU oracle)
 
-A "step" is one pass of the hot path (scan -> gather -> encode -> traverse -> vote -> centres -> pose) over one batch
-of BATCH synthetic frames (BASELINE.json configs[1]: 6-object forest, T=4, depth ~20, 16 votes per leaf, 64 cluttered
-640x480 frames).  One JSON line on stdout (rank 0).
+A "step" is one pass of the hot path (scan -> gather -> encode -> traverse -> vote -> centres -> pose) over one batch of
+BATCH synthetic frames.  One JSON line on stdout (rank 0).  --config picks BASELINE.json's configuration:
+
+  c1  configs[0]  1-object forest, one 640x480 frame, are_objects_segmented: true
+  c2  configs[1]  6-object forest, T = 4, batch of 64 cluttered 640x480 frames            <- default, the headline
+  c3  configs[2]  6-object forest with T = 8 trees (sharded over the GPUs when N > 1)
+  c4  configs[3]  1280x960 frames, stride 2, batches of 64 out of a 1024-frame stream
+  c5  configs[4]  forest-scale sweep: T 10..80, depth 15..25, 1..64 votes per leaf (random-vote forests)
 
 Multi-GPU (torchrun, one rank per GPU): frames are independent (the reference's frame loop carries no state,
-HFTest.cpp:1238), so ranks take their own batch -- weak scaling, no data-path collective -- and additionally the
-tree-sharded mode the north star names (trees t % N == rank, vote maps summed with NCCL before mode seeking) is run and
-reported under "tree_sharded".
+HFTest.cpp:1238), so ranks take their own batch -- weak scaling, no data-path collective -- and additionally the sharded
+single-stream mode the north star names is run and reported under "sharded" (every rank works on the SAME frames; its
+hypotheses are compared with a one-GPU run of the same frames: "bit_identical").
 """
 from __future__ import annotations
 
@@ -30,16 +35,35 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 # one hardware queue per stream (default 8): frame slots on aliased queues would serialise, and a slot waiting for a
-# peer's flag (tree-sharded mode) must never hold up another slot's kernels.  Read by the driver at CUDA initialisation.
+# peer's flag (sharded mode) must never hold up another slot's kernels.  Read by the driver at CUDA initialisation.
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 from object_detector_6d_b200 import synth  # noqa: E402
 
-BATCH = 64            # frames per step (configs[1])
-DISTINCT_FRAMES = 8   # rendered once (the numpy ray-caster takes ~2 s per frame); the batch cycles through them
+BATCH = 64            # frames per step
+DISTINCT_FRAMES = 8   # rendered once (the numpy ray-caster takes ~1 s per frame); the batch cycles through them
 K_CLASSES, T_TREES, MAX_DEPTH, VOTES = 6, 4, 20, 16
 ENC_FLOP_PER_PATCH = 2 * (256 * 1500 + 1500 * 1000 + 1000 * 800)
 METRIC = "frames/s (640x480 RGB-D, HoughForest --test hot path)"
+
+OBJECT_SEED = 1000    # the procedural objects that stand in for meshes/*.ply (shape, size, albedo, texture)
+TRAIN_FRAMES = 4      # frames whose object patches train the forest: same objects, their own poses
+VIEWS, MIN_SAMPLES = 4, 8   # training views a labelled patch stands for / node size that stops splitting (-> ~16 votes per leaf)
+WORKLOAD_VERSION = 5  # bump when synth or the recipes below change (invalidates the on-disk cache)
+
+CONFIGS = {
+    "c1": dict(name="configs[0]: 1-object forest, one synthetic 640x480 RGB-D frame, are_objects_segmented: true",
+               scale=1, K=1, T=4, n_objects=1, fill_random=0, distinct=1, forest="trained"),
+    "c2": dict(name="configs[1]: 6-object forest, batch of 64 synthetic cluttered 640x480 RGB-D frames",
+               scale=1, K=6, T=4, n_objects=6, fill_random=1, distinct=DISTINCT_FRAMES, forest="trained"),
+    "c3": dict(name="configs[2]: 6-object forest with 8 trees (sharded over the GPUs when N > 1), 640x480",
+               scale=1, K=6, T=8, n_objects=6, fill_random=1, distinct=DISTINCT_FRAMES, forest="trained"),
+    "c4": dict(name="configs[3]: dense sampling at stride 2 on synthetic 1280x960 frames, batches of 64 of a 1024-frame stream",
+               scale=2, K=6, T=4, n_objects=6, fill_random=1, distinct=4, forest="trained"),
+    "c5": dict(name="configs[4]: forest-scale sweep (random-vote forests), 6 objects, 640x480", scale=1, K=6, T=80, n_objects=6,
+               fill_random=1, distinct=2, forest="random", max_depth=25, votes=64,
+               sweep=[dict(T=10, D=15, V=1), dict(T=20, D=20, V=4), dict(T=40, D=20, V=16)]),
+}
 
 
 def load_peaks():
@@ -52,25 +76,23 @@ def load_peaks():
         return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback")
 
 
-OBJECT_SEED = 1000    # the six procedural objects that stand in for meshes/*.ply (shape, size, albedo, texture)
-TRAIN_FRAMES = 4      # frames whose object patches (every pixel) train the forest: same objects, their own poses
-VIEWS, MIN_SAMPLES = 4, 8   # training views a labelled patch stands for / node size that stops splitting (-> ~16 votes per leaf)
-WORKLOAD_VERSION = 4  # bump when synth or the recipe below changes (invalidates the on-disk cache)
-
-
-def _build_workload(out: str, n_frames: int, seed0: int, T: int, forest: str):
+# ------------------------------------------------------------------------------------------------ workload
+def _build_workload(out: str, n_frames: int, seed0: int, T: int, forest: str, scale: int, K: int, n_objects: int,
+                    max_depth: int, votes: int):
+    cam = synth.Camera.scaled(scale) if scale != 1 else synth.Camera()
     layers = synth.make_encoder_weights(3)
     forest_dir = os.path.join(out, "forest")
     if forest == "random":
-        frames = [synth.render_frame(seed0 + i) for i in range(n_frames)]
-        calib = synth.calibration_features(frames[0][0], frames[0][1], layers, n=30000)
-        stats = synth.write_forest(forest_dir, calib, T=T, K=K_CLASSES, max_depth=MAX_DEPTH, votes_per_leaf=VOTES, seed=7)
+        frames = [synth.render_frame(seed0 + i, cam, n_objects=n_objects) for i in range(n_frames)]
+        calib = synth.calibration_features(frames[0][0], frames[0][1], layers, n=30000, cam=cam)
+        stats = synth.write_forest(forest_dir, calib, T=T, K=K, max_depth=max_depth, votes_per_leaf=votes, seed=7)
     else:
-        scenes = [synth.render_scene(seed0 + i, OBJECT_SEED) for i in range(max(n_frames, TRAIN_FRAMES))]
+        scenes = [synth.render_scene(seed0 + i, OBJECT_SEED, cam, n_objects=n_objects) for i in range(max(n_frames, TRAIN_FRAMES))]
         frames = [(b, d) for b, d, _ in scenes[:n_frames]]
-        lab = [synth.labelled_patches(b, d, tr, layers, n=80000, seed=i, stride=1) for i, (b, d, tr) in enumerate(scenes[:TRAIN_FRAMES])]
-        feats, cls, votes = (np.concatenate([x[j] for x in lab]) for j in range(3))
-        stats = synth.write_trained_forest(forest_dir, feats, cls, votes, T=T, K=K_CLASSES, max_depth=MAX_DEPTH,
+        lab = [synth.labelled_patches(b, d, tr, layers, n=80000, cam=cam, seed=i, stride=scale)
+               for i, (b, d, tr) in enumerate(scenes[:TRAIN_FRAMES])]
+        feats, cls, vts = (np.concatenate([x[j] for x in lab]) for j in range(3))
+        stats = synth.write_trained_forest(forest_dir, feats, cls, vts, T=T, K=K, max_depth=max_depth,
                                            min_samples=MIN_SAMPLES, views=VIEWS, seed=7)
         stats["training_samples"] = int(len(cls))
     stats["forest"] = forest
@@ -80,18 +102,20 @@ def _build_workload(out: str, n_frames: int, seed0: int, T: int, forest: str):
         json.dump(stats, f)
 
 
-def make_workload(tmpdir: str, n_frames: int, seed0: int = 1, T: int = T_TREES, forest: str = "trained"):
+def make_workload(tmpdir: str, n_frames: int, seed0: int = 1, T: int = T_TREES, forest: str = "trained", scale: int = 1,
+                  K: int = K_CLASSES, n_objects: int = 6, max_depth: int = MAX_DEPTH, votes: int = VOTES):
     """Frames + encoder weights + forest on disk.  forest = "trained": leaves hold the class distributions and the 6-DoF
     votes of labelled object patches (synth.write_trained_forest) -- coherent votes, real Hough modes, the vote hot spots
-    a trained forest produces; "random": uniformly random votes, 16 per leaf (round 1's workload: no modes, maximal
-    scatter; kept for the stage-level parity tests and for continuity).
+    a trained forest produces; "random": uniformly random votes (round 1's workload: no modes, maximal scatter; kept for
+    the stage-level parity tests, the forest sweep and for continuity).
 
     Building it takes ~40 s of numpy, so it is cached under the system temp directory, keyed by the recipe: the ranks of a
     torchrun launch (and successive bench / test processes on one box) share one copy -- whoever creates the directory
-    builds, the others wait for its `done` marker.  `tmpdir` is unused when the cache can be used."""
-    key = f"hf6d_workload_v{WORKLOAD_VERSION}_{forest}_n{n_frames}_s{seed0}_T{T}"
+    builds, the others wait for its `done` marker.  `tmpdir` is only used when the cache cannot be."""
+    key = f"hf6d_workload_v{WORKLOAD_VERSION}_{forest}_n{n_frames}_s{seed0}_T{T}_x{scale}_K{K}_o{n_objects}_D{max_depth}_V{votes}"
     root = os.path.join(tempfile.gettempdir(), key)
     done = os.path.join(root, "done")
+    args = (n_frames, seed0, T, forest, scale, K, n_objects, max_depth, votes)
     try:
         os.makedirs(root)
         owner = True
@@ -99,7 +123,7 @@ def make_workload(tmpdir: str, n_frames: int, seed0: int = 1, T: int = T_TREES, 
         owner = False
     if owner:
         try:
-            _build_workload(root, n_frames, seed0, T, forest)
+            _build_workload(root, *args)
             open(done, "w").close()
         except BaseException:
             import shutil
@@ -111,7 +135,7 @@ def make_workload(tmpdir: str, n_frames: int, seed0: int = 1, T: int = T_TREES, 
             if not os.path.isdir(root) or time.time() - t0 > 900:  # the builder failed or died: build privately
                 root = os.path.join(tmpdir, key)
                 os.makedirs(root, exist_ok=True)
-                _build_workload(root, n_frames, seed0, T, forest)
+                _build_workload(root, *args)
                 break
             time.sleep(0.5)
     z = np.load(os.path.join(root, "frames.npz"))
@@ -119,6 +143,29 @@ def make_workload(tmpdir: str, n_frames: int, seed0: int = 1, T: int = T_TREES, 
     with open(os.path.join(root, "stats.json")) as f:
         stats = json.load(f)
     return frames, synth.make_encoder_weights(3), os.path.join(root, "forest"), os.path.join(root, "weights.bin"), stats
+
+
+def config_workload(cfg, tmpdir, **over):
+    kw = dict(T=cfg["T"], forest=cfg["forest"], scale=cfg["scale"], K=cfg["K"], n_objects=cfg["n_objects"],
+              max_depth=cfg.get("max_depth", MAX_DEPTH), votes=cfg.get("votes", VOTES))
+    kw.update(over)
+    return make_workload(tmpdir, cfg["distinct"], **kw)
+
+
+def workload_config(cfg, stats):
+    """The `config` object of the JSON line: identical in both arms (the driver compares them key by key)."""
+    W, H = 640 * cfg["scale"], 480 * cfg["scale"]
+    return {"workload": cfg["name"], "frame": f"{W}x{H}", "stride": 2, "classes": cfg["K"], "trees": int(stats["T"]),
+            "forest": stats.get("forest"), "leaves": int(sum(stats["leaves"])),
+            "mean_leaf_depth": float(np.mean(stats["mean_depth"])), "batch_frames": BATCH, "distinct_frames": cfg["distinct"],
+            "fill": "random (are_objects_segmented: false)" if cfg["fill_random"] else "zero (are_objects_segmented: true)",
+            "l2": "per-frame intermediates (0.9 GB at 640x480) exceed the 126 MB L2; the batch cycles through the distinct frames"}
+
+
+def params_for(cfg, api_or_oracle):
+    s = cfg["scale"]
+    return api_or_oracle.default_params(W=640 * s, H=480 * s, fx=575.0 * s, fy=575.0 * s, cx=320.0 * s - 0.5, cy=240.0 * s - 0.5,
+                                        fill_random=cfg["fill_random"], fill_seed=1)
 
 
 class ClockSampler:
@@ -169,55 +216,107 @@ class ClockSampler:
         return out
 
 
-# ------------------------------------------------------------------------------------------------ reference arm
-def run_reference(args, rank, world):
-    """The reference's CPU algorithm for the path (its own binary cannot be built here: SURVEY.md F5), i.e. the oracle
-    port, OpenMP over all host cores.  One step = one frame of the batch (bounded sample)."""
-    if rank != 0:
-        return
+# ------------------------------------------------------------------------------------------------ CPU arms
+def cpu_port_baseline(cfg, frames, layers, forest_dir, n_frames, warm=True):
+    """The oracle port (oracle/hf6d_oracle.c: the reference's algorithm, OpenMP over all host cores, votes cast in
+    parallel and merged like HFTest.cpp:601-656) on `n_frames` frames of the workload.  Returns (frames/s, threads,
+    per-stage seconds per frame, patch-tree traversals per second)."""
     from oracle import oracle as O
     cores = O.set_threads()  # all host cores, also under torchrun (which exports OMP_NUM_THREADS=1)
-    with tempfile.TemporaryDirectory() as d:
-        frames, layers, forest_dir, _, stats = make_workload(d, DISTINCT_FRAMES, forest=args.forest)
+    forest = O.Forest(forest_dir)
+    p = params_for(cfg, O)
+    if warm:
+        O.detect(forest, frames[0][0], frames[0][1], p, layers)
+    stage = np.zeros(6)
+    n_trav = 0
+    t0 = time.perf_counter()
+    for i in range(n_frames):
+        _, (P, Pp), st = O.detect(forest, frames[i % len(frames)][0], frames[i % len(frames)][1], p, layers)
+        n_trav += Pp * forest.T
+        stage += st
+    dt = time.perf_counter() - t0
+    return n_frames / dt, cores, {k: float(v / n_frames) for k, v in
+                                   zip(("gather", "normalise", "encode", "traverse", "vote+modes", "total"), stage)}, n_trav / dt
+
+
+def reference_source_sample(cfg, frames, layers, forest_dir, wpath):
+    """The reference's OWN code for the path (oracle/_ref: HFTest::test_image compiled from /root/reference against stand-in
+    headers) next to the port, on a bounded sample: the central quarter of one frame, the same forest and weights, all host
+    cores.  None when the prebuilt library did not travel."""
+    try:
+        from oracle import oracle as O
+        from oracle import refsrc as R
+        if not R.available():
+            return None
+        s = cfg["scale"]
+        W, H = 320 * s, 240 * s
+        bgr = np.ascontiguousarray(frames[0][0][H // 2:H // 2 + H, W // 2:W // 2 + W])
+        dep = np.ascontiguousarray(frames[0][1][H // 2:H // 2 + H, W // 2:W // 2 + W])
+        p = O.default_params(W=W, H=H, fx=575.0 * s, fy=575.0 * s, cx=W / 2 - 0.5, cy=H / 2 - 0.5,
+                             fill_random=cfg["fill_random"], fill_seed=1)
+        cores = O.set_threads()
         forest = O.Forest(forest_dir)
-        p = O.default_params(fill_random=1, fill_seed=1)
-        n_trav = 0
-        for i in range(args.warmup):
-            O.detect(forest, frames[i % len(frames)][0], frames[i % len(frames)][1], p, layers)
+        ref = R.Reference(forest_dir, wpath)
         t0 = time.perf_counter()
-        stage = np.zeros(6)
-        for i in range(args.steps):
-            _, (P, Pp), st = O.detect(forest, frames[i % len(frames)][0], frames[i % len(frames)][1], p, layers)
-            n_trav += Pp * forest.T
-            stage += st
+        rh = ref.test_image(bgr, dep, p, n_threads=cores)
+        t_ref = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        oh, _, _ = O.detect(forest, bgr, dep, p, layers)
+        t_port = time.perf_counter() - t0
+        return {"sample": f"central {W}x{H} crop of one frame, same forest and weights, {cores} threads",
+                "reference_source_s": t_ref, "port_s": t_port, "port_speedup_over_reference_source": t_ref / t_port,
+                "hypotheses": [len(rh), len(oh)],
+                "note": "HFTest::test_image compiled unmodified from the reference tree (oracle/build_ref.py); its encoder is "
+                        "the port's (Caffe is absent), everything else -- hash maps, Eigen products per vote, per-batch map "
+                        "merges -- is the reference's own code"}
+    except Exception as e:  # noqa: BLE001
+        return {"unavailable": str(e).splitlines()[0][:200]}
+
+
+def run_reference(args, rank, world):
+    """The reference's CPU algorithm for the path (its own binary cannot be built here: DESIGN.md section 2), i.e. the oracle
+    port on all host cores.  One step = one frame of the batch (bounded sample)."""
+    if rank != 0:
+        return
+    cfg = CONFIGS[args.config]
+    with tempfile.TemporaryDirectory() as d:
+        frames, layers, forest_dir, wpath, stats = config_workload(cfg, d)
+        for _ in range(min(args.warmup, 1)):
+            cpu_port_baseline(cfg, frames, layers, forest_dir, 1, warm=False)
+        t0 = time.perf_counter()
+        fps, cores, stage, trav = cpu_port_baseline(cfg, frames, layers, forest_dir, args.steps, warm=False)
         dt = time.perf_counter() - t0
-    fps = args.steps / dt
+        refsrc = reference_source_sample(cfg, frames, layers, forest_dir, wpath)
     line = {
         "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(stats, sample="1 frame per step"),
-        "traversals_per_s": n_trav / dt,
+        "config": workload_config(cfg, stats),
+        "step_definition": "one frame of the batch per step (bounded sample of the same workload)",
+        "traversals_per_s": trav,
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
                          "sample": f"{args.steps} frames of the batch, one per step, all stages, OpenMP on {cores} threads",
-                         "stage_s_per_frame": {k: float(v / args.steps) for k, v in
-                                               zip(("gather", "normalise", "encode", "traverse", "vote+modes", "total"), stage)}},
+                         "stage_s_per_frame": stage, "reference_source": refsrc},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
 
-def workload_config(stats, **extra):
-    cfg = {"workload": "configs[1]: 6-object forest, batch of 64 synthetic cluttered 640x480 RGB-D frames",
-           "frame": "640x480", "stride": 2, "classes": K_CLASSES, "trees": T_TREES, "mean_leaf_depth":
-           float(np.mean(stats["mean_depth"])), "forest": stats.get("forest"), "leaves": int(sum(stats["leaves"])),
-           "batch_frames": BATCH, "distinct_frames": DISTINCT_FRAMES, "fill": "random (are_objects_segmented: false)",
-           "l2": "per-frame intermediates (0.9 GB) exceed the 126 MB L2; frames cycle through 8 distinct inputs"}
-    cfg.update(extra)
-    return cfg
-
-
 # ------------------------------------------------------------------------------------------------ CUDA arm
+def stage_work(cfg, Pp, votes_cast, T, K):
+    """ALGORITHMIC bytes / flops of one frame per stage (what the rooflines divide by)."""
+    W, H = 640 * cfg["scale"], 480 * cfg["scale"]
+    return {
+        "scan": (W * H * 2 + Pp * 8, "hbm"),                                   # depth once + patch centres
+        "gather": (W * H * 5 + Pp * 256, "hbm"),                               # frame once + uint8 patches
+        "encode": (Pp * ENC_FLOP_PER_PATCH, "tensor"),
+        "traverse": (Pp * 800 * 4 + Pp * T * 4, "hbm"),                        # fp32 features once + leaf ids
+        "vote": (Pp * T * 4 + votes_cast * 28 + K * W * H * 4, "hbm"),         # leaf ids + 28 B per vote + maps once
+        "centres": (K * W * H * 4 * 2, "hbm"),                                 # blur + NMS: maps read + written
+        "pose": (Pp * T * 4 + votes_cast * 28, "hbm"),                         # the votes once more (HFTest.cpp:757-802)
+    }
+
+
 def run_cuda(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -229,12 +328,17 @@ def run_cuda(args, rank, world, local_rank):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     peaks = load_peaks()
+    cfg = CONFIGS[args.config]
+    distinct = cfg["distinct"]
+    W, H = 640 * cfg["scale"], 480 * cfg["scale"]
 
     with tempfile.TemporaryDirectory() as d:
-        frames, layers, forest_dir, wpath, stats = make_workload(d, DISTINCT_FRAMES, forest=args.forest)
-        p = api.default_params(fill_random=1, fill_seed=1)
+        frames, layers, forest_dir, wpath, stats = config_workload(cfg, d)
+        p = params_for(cfg, api)
         n_slots = args.slots
         det = api.Detector(forest_dir, wpath, p, device=local_rank, n_slots=n_slots)
+        det.set_encoder_mode(args.encoder_mode)
+        T, K = det.T, det.K
 
         # ---- device-resident inputs
         bgr_all = torch.from_numpy(np.stack([f[0] for f in frames])).cuda()
@@ -250,7 +354,7 @@ def run_cuda(args, rank, world, local_rank):
             launches = 0
             for i in range(BATCH):
                 s = i % n_slots
-                j = i % DISTINCT_FRAMES
+                j = i % distinct
                 det.bind_frame(s, bgr_all[j].data_ptr(), dep_all[j].data_ptr())
                 det.run(s)
                 launches += det.launch_count(s)
@@ -286,33 +390,40 @@ def run_cuda(args, rank, world, local_rank):
         main.synchronize()
         torch.cuda.synchronize()
         ms_total = e0.elapsed_time(e1)
-        counts = [det.counts(s) for s in range(n_slots)]
-        # per-stage times: a serial pass (one frame at a time, nothing else on the GPU) so a stage's events bracket only
-        # its kernels.  It runs on a ONE-slot context -- the library's latency configuration, whose encoder kernels are the
-        # ones that are fastest alone (one more ring stage than the pipelined context's, see HF6D_ENC_CONFIGS)
+
+        # ---- per-stage times: serial passes (one frame at a time, nothing else on the GPU) so that a stage's events bracket
+        # only its kernels.  (a) on the pipelined context itself -- the kernels the headline runs; (b) on a ONE-slot context,
+        # the library's latency configuration, whose encoder kernels trade co-residency for one more ring stage.
+        def serial_pass(dd, nd=distinct):
+            st_acc, enc_acc, n_ser = np.zeros(api.STAGE_COUNT), np.zeros(3), 0
+            for rep in range(2):
+                for j in range(nd):
+                    dd.bind_frame(0, bgr_all[j].data_ptr(), dep_all[j].data_ptr())
+                    dd.run(0)
+                    dd.sync(0)
+                    if rep:
+                        st_acc += dd.stage_ms(0)
+                        enc_acc += dd.encoder_layer_ms(0)
+                        n_ser += 1
+            return st_acc / n_ser, enc_acc / n_ser
+
+        stage_ms, enc_ms = serial_pass(det)
         det1 = api.Detector(forest_dir, wpath, p, device=local_rank, n_slots=1)
-        st_acc, enc_acc, n_ser = np.zeros(api.STAGE_COUNT), np.zeros(3), 0
-        for rep in range(2):
-            for j in range(DISTINCT_FRAMES):
-                det1.bind_frame(0, bgr_all[j].data_ptr(), dep_all[j].data_ptr())
-                det1.run(0)
-                det1.sync(0)
-                if rep:
-                    st_acc += det1.stage_ms(0)
-                    enc_acc += det1.encoder_layer_ms(0)
-                    n_ser += 1
-        stage_ms, enc_ms = st_acc / n_ser, enc_acc / n_ser
+        det1.set_encoder_mode(args.encoder_mode)
+        stage_ms1, enc_ms1 = serial_pass(det1)
+        det1.set_encoder_mode(1 - args.encoder_mode)  # the other encoder mode on the latency context, for the record
+        _, enc_ms_other = serial_pass(det1)
         det1.bind_frame(0, None, None)
         det1.close()
-        # patches per frame: exact, from the scan of every distinct frame
+        # patches and votes per frame: exact, from the scan / leaf tables of every distinct frame
         Pp_frames, votes_frames = [], []
-        for j in range(DISTINCT_FRAMES):
+        for j in range(distinct):
             det.bind_frame(0, bgr_all[j].data_ptr(), dep_all[j].data_ptr())
             det.run(0, api.STAGE_SCAN, api.STAGE_TRAVERSE)
             Pp_frames.append(det.counts(0)[1])
             votes_frames.append(det.count_cast_votes(0))
-        Pp_mean = float(np.mean([Pp_frames[i % DISTINCT_FRAMES] for i in range(BATCH)]))
-        votes_mean = float(np.mean([votes_frames[i % DISTINCT_FRAMES] for i in range(BATCH)]))
+        Pp_mean = float(np.mean([Pp_frames[i % distinct] for i in range(BATCH)]))
+        votes_mean = float(np.mean([votes_frames[i % distinct] for i in range(BATCH)]))
         for s in range(n_slots):
             det.bind_frame(s, None, None)
             det.set_stream(s, None)
@@ -322,16 +433,16 @@ def run_cuda(args, rank, world, local_rank):
             ms_total = float(t.item())
 
         # ---- end to end through the public API: pinned host frames -> hf6d_submit / hf6d_wait -> host hypotheses
-        pin_b = [api.PinnedArray((480, 640, 3), np.uint8) for _ in range(DISTINCT_FRAMES)]
-        pin_d = [api.PinnedArray((480, 640), np.uint16) for _ in range(DISTINCT_FRAMES)]
-        for j in range(DISTINCT_FRAMES):
+        pin_b = [api.PinnedArray((H, W, 3), np.uint8) for _ in range(distinct)]
+        pin_d = [api.PinnedArray((H, W), np.uint16) for _ in range(distinct)]
+        for j in range(distinct):
             pin_b[j].array[...] = frames[j][0]
             pin_d[j].array[...] = frames[j][1]
 
         def step_e2e():
             tickets, nh = [], 0
             for i in range(BATCH):
-                j = i % DISTINCT_FRAMES
+                j = i % distinct
                 if len(tickets) == n_slots:
                     nh += len(det.wait(tickets.pop(0)))
                 tickets.append(det.submit(pin_b[j].array, pin_d[j].array))
@@ -358,74 +469,82 @@ def run_cuda(args, rank, world, local_rank):
         for a in pin_b + pin_d:
             a.free()
         d2h = BATCH * det.result_bytes()
-        h2d = BATCH * (640 * 480 * 5)
+        h2d = BATCH * (W * H * 5)
+
+        # ---- c5: the forest sweep (serial frame time per forest; the line's value is the heaviest corner, measured above)
+        sweep = None
+        if cfg.get("sweep") and rank == 0:
+            sweep = []
+            for sw in cfg["sweep"]:
+                _, _, fdir, wp, st = make_workload(d, cfg["distinct"], T=sw["T"], forest="random", scale=cfg["scale"], K=cfg["K"],
+                                                   n_objects=cfg["n_objects"], max_depth=sw["D"], votes=sw["V"])
+                dd = api.Detector(fdir, wp, p, device=local_rank, n_slots=1)
+                sm, _ = serial_pass(dd, 1)
+                dd.bind_frame(0, bgr_all[0].data_ptr(), dep_all[0].data_ptr())
+                dd.run(0, api.STAGE_SCAN, api.STAGE_TRAVERSE)
+                nv = dd.count_cast_votes(0)
+                dd.bind_frame(0, None, None)
+                dd.close()
+                sweep.append({"trees": sw["T"], "max_depth": sw["D"], "votes_per_leaf": sw["V"], "leaves": int(sum(st["leaves"])),
+                              "votes_cast_per_frame": int(nv), "serial_ms_per_frame": float(np.sum(sm)),
+                              "stage_ms": {n: float(v) for n, v in zip(api.STAGE_NAMES, sm)}})
 
         # ---- CPU baseline (rank 0, N == 1 only): the oracle port on a bounded sample, all host cores
         cpu = None
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
-            from oracle import oracle as O
-            cpu_threads = O.set_threads()
-            forest = O.Forest(forest_dir)
-            po = O.default_params(fill_random=1, fill_seed=1)
-            O.detect(forest, frames[0][0], frames[0][1], po, layers)  # warm
             n_s = 2
-            t0 = time.perf_counter()
-            for i in range(n_s):
-                O.detect(forest, frames[i][0], frames[i][1], po, layers)
-            dt = time.perf_counter() - t0
-            cpu = {"value": n_s / dt, "unit": "frames/s", "cores": cpu_threads, "kind": "port",
-                   "sample": f"{n_s} frames of the batch, all stages, OpenMP on all host cores"}
+            fps_cpu, cores, stage_cpu, _ = cpu_port_baseline(cfg, frames, layers, forest_dir, n_s)
+            cpu = {"value": fps_cpu, "unit": "frames/s", "cores": cores, "kind": "port",
+                   "sample": f"{n_s} frames of the batch, all stages, OpenMP on all host cores", "stage_s_per_frame": stage_cpu,
+                   "reference_source": reference_source_sample(cfg, frames, layers, forest_dir, wpath)}
         det.close()
 
-        def build_line(tree):
-            """The JSON line from everything measured so far (also called by the watchdog of the tree-sharded arm)."""
+        def build_line(sharded):
+            """The JSON line from everything measured so far (also called by the watchdog of the sharded arm)."""
             frames_total = BATCH * args.steps * world
             sec = ms_total * 1e-3
             fps = frames_total / sec
             ms_frame = ms_total / (BATCH * args.steps)
-            # stage rooflines from SURVEY.md §8(d)'s algorithmic work per frame
             Pp = Pp_mean
-            votes_cast = votes_mean  # counted from the leaf tables of the frames (hf6d_count_cast_votes)
-            alg = {
-                "scan": (640 * 480 * 2 + Pp * 8, "hbm"),
-                "gather": (640 * 480 * 5 + Pp * 512, "hbm"),                 # frame once + bf16 A operand [P'][256]
-                "encode": (Pp * ENC_FLOP_PER_PATCH, "tensor"),
-                "traverse": (Pp * 800 * 4 + Pp * T_TREES * 4, "hbm"),
-                "vote": (Pp * T_TREES * 4 + votes_cast * 12 + K_CLASSES * 640 * 480 * 8, "hbm"),
-                "centres": (K_CLASSES * 640 * 480 * (8 + 4), "hbm"),
-                "pose": (2 * (Pp * T_TREES * 4 + votes_cast * 12), "hbm"),
-            }
-            stages = {}
-            for name, ms in zip(api.STAGE_NAMES, stage_ms):
-                work, bound = alg[name]
-                if ms <= 0:
-                    continue
-                if bound == "tensor":
-                    ach = work / (ms * 1e-3) / 1e12
-                    stages[name] = {"ms": float(ms), "bound": bound, "achieved": ach, "unit": "TFLOP/s", "frac": ach / peaks["tf_sustained"]}
-                else:
-                    ach = work / (ms * 1e-3) / 1e9
-                    stages[name] = {"ms": float(ms), "bound": bound, "achieved": ach, "unit": "GB/s", "frac": ach / peaks["hbm"]}
+            alg = stage_work(cfg, Pp, votes_mean, T, K)
+
+            def table(ms_vec):
+                out = {}
+                for name, ms in zip(api.STAGE_NAMES, ms_vec):
+                    work, bound = alg[name]
+                    if ms <= 0:
+                        continue
+                    if bound == "tensor":
+                        ach = work / (ms * 1e-3) / 1e12
+                        out[name] = {"ms": float(ms), "bound": bound, "achieved": ach, "unit": "TFLOP/s", "frac": ach / peaks["tf_sustained"]}
+                    else:
+                        ach = work / (ms * 1e-3) / 1e9
+                        out[name] = {"ms": float(ms), "bound": bound, "achieved": ach, "unit": "GB/s", "frac": ach / peaks["hbm"]}
+                return out
             # dominant kernel: encoder layer 2 (K=1536 -> N=1024 padded; algorithmic 1500 x 1000), timed alone in the serial
-            # pass with the SM clock at its maximum -> the burst bf16 peak is the denominator (the sustained figure is for a
-            # kernel inside a long power-limited tensor step; this path spends ~1/3 of a frame on the tensor pipe)
-            l2_flop = 2.0 * Pp * 1500 * 1000
+            # pass of the PIPELINED context (the kernel variant `value` and `e2e` run) with the SM clock at its maximum -> the
+            # burst bf16 peak is the denominator; the one-slot context's variant alongside
+            l2_flop = 2.0 * Pp * 1500 * 1000 * (3 if args.encoder_mode == 1 else 1)
             l2_ach = l2_flop / (enc_ms[1] * 1e-3) / 1e12 if enc_ms[1] > 0 else 0.0
+            l2_ach1 = l2_flop / (enc_ms1[1] * 1e-3) / 1e12 if enc_ms1[1] > 0 else 0.0
             traffic = None
             try:
                 with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
                     traffic = json.load(f).get("encoder_layer_2", {}).get("dram_bytes_per_launch")
             except Exception:
                 pass
-            roofline = {"kernel": "encoder_layer_kernel<256,false,6,1,2,64,8> (layer 2: 1500->1000, CTA pairs, tcgen05 cta_group::2; one-slot context)",
+            roofline = {"kernel": "encoder_layer_kernel, layer 2 (1500 -> 1000, CTA pairs, tcgen05 cta_group::2), the variant of the "
+                                  f"{n_slots}-slot context the headline runs",
                         "bound": "tensor", "achieved": l2_ach,
                         "peak": peaks["tf_burst"], "unit": "TFLOP/s", "frac": l2_ach / peaks["tf_burst"],
                         "traffic": traffic, "peak_source": peaks["source"] + " (burst bf16: kernel timed alone, SM clock at max)",
                         "frac_of_sustained_peak": l2_ach / peaks["tf_sustained"],
                         "frac_of_nominal_dense_peak": l2_ach / 2250.0,
-                        "note": "achieved counts ALGORITHMIC flops (1500 x 1000 per patch; the kernel multiplies the padded 1536 x 1024); "
-                                "the measured peak is a cuBLAS bf16 GEMM on this pool's B200s, so a fraction near or above 1 means "
-                                "the kernel matches the library's throughput, not that it exceeds the hardware (nominal 2250 TFLOP/s)",
+                        "one_slot_context": {"achieved": l2_ach1, "frac": l2_ach1 / peaks["tf_burst"],
+                                             "encoder_layer_ms": [float(x) for x in enc_ms1]},
+                        "note": "achieved counts ALGORITHMIC flops (1500 x 1000 per patch; the kernel multiplies the padded 1536 x 1024; "
+                                "x3 in the split-bf16 mode); the measured peak is a cuBLAS bf16 GEMM on this pool's B200s, so a fraction "
+                                "near 1 means the kernel matches the library's throughput (nominal dense peak 2250 TFLOP/s)",
                         "encoder_layer_ms": [float(x) for x in enc_ms],
                         "encoder_stage_tflops": float(Pp * ENC_FLOP_PER_PATCH / (sum(enc_ms) * 1e-3) / 1e12) if sum(enc_ms) > 0 else 0.0}
             e2e_fps = frames_total / e2e_s
@@ -433,103 +552,126 @@ def run_cuda(args, rank, world, local_rank):
                 "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                "config": workload_config(stats, patches_per_frame=Pp, votes_cast_per_frame=votes_cast,
-                                          parallelism=f"frames x{world}" if world > 1 else "1 GPU"),
-                "ms_per_frame": ms_frame, "traversals_per_s": fps * Pp * T_TREES,
+                "config": workload_config(cfg, stats),
+                "parallelism": f"frames x{world}" if world > 1 else "1 GPU", "frames_in_flight": n_slots,
+                "patches_per_frame": Pp, "votes_cast_per_frame": votes_mean,
+                "encoder_mode": {"mode": args.encoder_mode,
+                                 "name": "bf16 operands" if args.encoder_mode == 0 else "split bf16 (hi + lo operands, ~fp32)",
+                                 "other_mode_encoder_layer_ms": [float(x) for x in enc_ms_other],
+                                 "parity": "profiles/r02_parity.json (end to end against the fp32 oracle, both modes)"},
+                "ms_per_frame": ms_frame, "traversals_per_s": fps * Pp * T,
                 "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "timing": "wall clock around hf6d_submit/hf6d_wait with pinned host frames, device sync both sides",
                         "hypotheses_per_frame": n_hyp / (BATCH * args.steps)},
                 "gpu_launches": launches,
-                "roofline": roofline, "stages": stages, "stages_note": "serial pass: one frame at a time on a one-slot context (5/6/6-stage encoder "
-                "rings), sum = %.3f ms/frame; `value` and `e2e` run %d frames in flight on separate streams of a %d-slot context, whose "
-                "encoder kernels trade one ring stage (4/5/5) for room beside them: other frames' CTAs co-reside, +3-5 %% frames/s"
-                % (float(np.sum(stage_ms)), n_slots, n_slots),
+                "roofline": roofline, "stages": table(stage_ms), "stages_one_slot_context": table(stage_ms1),
+                "stages_note": "serial passes (one frame at a time): `stages` on the %d-slot context whose kernels `value` and `e2e` run "
+                               "(sum %.3f ms/frame), `stages_one_slot_context` on the latency configuration (sum %.3f); algorithmic work per "
+                               "SURVEY.md 8(d)" % (n_slots, float(np.sum(stage_ms)), float(np.sum(stage_ms1))),
                 "cpu_baseline": cpu, "clocks": clocks,
             }
-            if tree is not None:
-                line["tree_sharded"] = tree
+            if sweep is not None:
+                line["sweep"] = sweep
+            if sharded is not None:
+                line["sharded"] = sharded
             return line
 
-        # ---- the north star's multi-GPU mode: trees sharded over the ranks, ONE exchange step per frame (NCCL
-        # all-reduce SUM of the Q16 vote maps + MAX of the leaf table), every rank works on the same frames
-        tree = None
+        # ---- the north star's multi-GPU mode: ONE stream of frames, the work of every frame split over the ranks
+        sharded = None
         if world > 1:
-            import threading
-            from object_detector_6d_b200 import sharded
-            tree_modes = {}
-            tree_done = threading.Event()
-
-            def watchdog():  # a rank that dies inside the exchange would leave the others waiting on its flags for ever
-                if not tree_done.wait(timeout=args.tree_timeout):
-                    if rank == 0:
-                        print(json.dumps(build_line({"unavailable": "the tree-sharded arm did not finish within %d s" % args.tree_timeout,
-                                                     "exchanges": tree_modes})), flush=True)
-                    os._exit(0)
-            threading.Thread(target=watchdog, daemon=True).start()
-            for mode in ("peer", "nccl"):
-                try:
-                    sd = sharded.TreeShardedDetector(forest_dir, wpath, p, device=local_rank, n_slots=n_slots, exchange=mode)
-                except Exception as e:  # e.g. no P2P path between the GPUs: the NCCL exchange still runs
-                    tree_modes[mode] = {"unavailable": str(e).splitlines()[0][:200]}
-                    continue
-                for s in range(n_slots):
-                    sd.det.bind_frame(s, bgr_all[0].data_ptr(), dep_all[0].data_ptr())
-
-                def step_tree():
-                    for i in range(BATCH):
-                        s = i % n_slots
-                        j = i % DISTINCT_FRAMES
-                        sd.det.bind_frame(s, bgr_all[j].data_ptr(), dep_all[j].data_ptr())
-                        sd.run(s)
-
-                main_t = torch.cuda.Stream()
-                for _ in range(args.warmup):
-                    step_tree()
-                torch.cuda.synchronize()
-                dist.barrier()
-                torch.cuda.synchronize()
-                t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                t0e.record(main_t)
-                for st_ in sd.streams:
-                    st_.wait_event(t0e)
-                for _ in range(args.steps):
-                    step_tree()
-                for st_ in sd.streams:
-                    ev = torch.cuda.Event()
-                    ev.record(st_)
-                    main_t.wait_event(ev)
-                t1e.record(main_t)
-                main_t.synchronize()
-                t = torch.tensor([t0e.elapsed_time(t1e)], device="cuda")
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                ms_tree = float(t.item())
-                tree_modes[mode] = {"frames_per_s": BATCH * args.steps / (ms_tree * 1e-3), "ms_per_frame": ms_tree / (BATCH * args.steps),
-                                    "kernel_launches_per_frame": sd.launches_per_frame()}
-                trees_per_rank, classes_per_rank = len(sd.trees), len(sd.classes)
-                for s in range(n_slots):
-                    sd.det.bind_frame(s, None, None)
-                sd.close()
-            tree_done.set()
-            best = max((m for m in tree_modes if "frames_per_s" in tree_modes[m]), key=lambda m: tree_modes[m]["frames_per_s"])
-            tree = dict(tree_modes[best])
-            tree.update({
-                "exchange": best, "exchanges": tree_modes,
-                "trees_per_rank": trees_per_rank, "classes_per_rank": classes_per_rank,
-                "exchange_bytes_per_frame": {"nccl": int(K_CLASSES * 640 * 480 * 8 + counts[0][1] * T_TREES * 4),
-                                             "peer": int((world - 1) * classes_per_rank * 640 * 480 * 8
-                                                         + counts[0][1] * (T_TREES - trees_per_rank) * 4)},
-                "scaling": "strong (same frames on every rank, trees t % N == rank)",
-                "note": "scan/gather/encode are replicated (every rank needs all features); traverse+vote are sharded by tree, "
-                        "centres+pose by class after the exchange; %d frames in flight.  exchange 'peer': the blur's row pass and the "
-                        "pose stage read the other ranks' vote maps / leaf tables in place over NVLink (CUDA IPC, flags in peer "
-                        "memory, no collective); 'nccl': all-reduce SUM of the maps + MAX of the leaf table" % n_slots})
-
-        line = build_line(tree)
+            sharded = run_sharded(args, cfg, det_params=p, forest_dir=forest_dir, wpath=wpath, frames=frames, bgr_all=bgr_all,
+                                  dep_all=dep_all, rank=rank, world=world, local_rank=local_rank, build_line=build_line)
+        line = build_line(sharded)
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def run_sharded(args, cfg, det_params, forest_dir, wpath, frames, bgr_all, dep_all, rank, world, local_rank, build_line):
+    """Every rank works on the SAME frames (strong scaling of one stream) through
+    object_detector_6d_b200.sharded.TreeShardedDetector, with its "peer" and "nccl" exchanges.  The hypotheses of the sharded
+    run are gathered and compared with a one-GPU run of the same frames."""
+    import threading
+    import torch
+    import torch.distributed as dist
+    from object_detector_6d_b200 import api, sharded
+    n_slots, distinct = args.slots, cfg["distinct"]
+    modes = {}
+    done = threading.Event()
+
+    def watchdog():  # a rank that dies inside the exchange would leave the others waiting on its flags
+        if not done.wait(timeout=args.tree_timeout):
+            if rank == 0:
+                print(json.dumps(build_line({"unavailable": "the sharded arm did not finish within %d s" % args.tree_timeout,
+                                             "exchanges": modes})), flush=True)
+            os._exit(0)
+    threading.Thread(target=watchdog, daemon=True).start()
+    # the one-GPU answer for the comparison
+    ref = api.Detector(forest_dir, wpath, det_params, device=local_rank, n_slots=1)
+    ref_h = [ref.detect(frames[j][0], frames[j][1]) for j in range(min(distinct, 2))]
+    ref.close()
+    info = {}
+    for mode in ("peer", "nccl"):
+        try:
+            sd = sharded.TreeShardedDetector(forest_dir, wpath, det_params, device=local_rank, n_slots=n_slots, exchange=mode)
+        except Exception as e:  # e.g. no P2P path between the GPUs: the NCCL exchange still runs
+            modes[mode] = {"unavailable": str(e).splitlines()[0][:200]}
+            continue
+        same = True
+        for j in range(len(ref_h)):
+            h = sd.detect(frames[j][0], frames[j][1])
+            same &= len(h) == len(ref_h[j]) and all(np.array_equal(h[n], ref_h[j][n]) for n in h.dtype.names)
+        for s in range(n_slots):
+            sd.det.bind_frame(s, bgr_all[0].data_ptr(), dep_all[0].data_ptr())
+
+        def step():
+            for i in range(BATCH):
+                s = i % n_slots
+                j = i % distinct
+                sd.det.bind_frame(s, bgr_all[j].data_ptr(), dep_all[j].data_ptr())
+                sd.run(s)
+
+        main_t = torch.cuda.Stream()
+        for _ in range(args.warmup):
+            step()
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0e.record(main_t)
+        for st_ in sd.streams:
+            st_.wait_event(t0e)
+        for _ in range(args.steps):
+            step()
+        for st_ in sd.streams:
+            ev = torch.cuda.Event()
+            ev.record(st_)
+            main_t.wait_event(ev)
+        t1e.record(main_t)
+        main_t.synchronize()
+        t = torch.tensor([t0e.elapsed_time(t1e)], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        ok = torch.tensor([1 if same else 0], device="cuda")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        modes[mode] = {"frames_per_s": BATCH * args.steps / (ms * 1e-3), "ms_per_frame": ms / (BATCH * args.steps),
+                       "kernel_launches_per_frame": sd.launches_per_frame(), "bit_identical": bool(ok.item())}
+        info = {"trees_per_rank": len(sd.trees), "classes_per_rank": len(sd.classes)}
+        for s in range(n_slots):
+            sd.det.bind_frame(s, None, None)
+        sd.close()
+    done.set()
+    good = [m for m in modes if "frames_per_s" in modes[m]]
+    if not good:
+        return {"unavailable": "no exchange mode could run", "exchanges": modes}
+    best = max(good, key=lambda m: modes[m]["frames_per_s"])
+    out = dict(modes[best])
+    out.update(info)
+    out.update({"exchange": best, "exchanges": modes,
+                "scaling": "strong (one stream: the same frames on every rank)", "frames_in_flight": n_slots})
+    return out
 
 
 def main():
@@ -538,11 +680,12 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--slots", type=int, default=4, help="frames in flight (one stream + workspace each)")
-    ap.add_argument("--forest", default="trained", choices=["trained", "random"],
-                    help="synthetic forest: leaf payloads from labelled patches (coherent votes) or uniformly random votes")
-    ap.add_argument("--tree-timeout", type=int, default=240, help="seconds the tree-sharded arm (N > 1) may take")
+    ap.add_argument("--encoder-mode", type=int, default=0, choices=[0, 1],
+                    help="0: bf16 tensor-core operands (the headline), 1: split bf16 (~fp32 products, 3x the encoder time)")
+    ap.add_argument("--tree-timeout", type=int, default=240, help="seconds the sharded arm (N > 1) may take")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

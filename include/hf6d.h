@@ -166,17 +166,24 @@ int hf6d_set_class_shard(hf6d_ctx* c, int rank, int world);
  * the caller hands every rank all blobs (any transport: torch.distributed all_gather, MPI, a file), and from then on
  * hf6d_run exchanges nothing through the host: the kernels after the exchange point read the peers' maps and leaf tables
  * in place over NVLink, and the ranks synchronise through flags in each other's memory (see "peer exchange" in
- * csrc/hf6d_api.cu).  hf6d_peer_attach also sets the tree shard and the class shard to rank/world.  Every rank must then
- * run the same frames on the same slots (whole frames, or SCAN..VOTE followed by CENTRES..POSE), and the slots' streams
- * should not share a hardware queue (CUDA_DEVICE_MAX_CONNECTIONS >= number of streams the process uses): a slot that
- * waits for a peer's flag blocks its queue, and the peer may be waiting for a frame queued behind it.  Replaces the
- * reference's merge of per-thread vote maps and leaf lists, HoughForest/src/HFTest.cpp:645-654, across GPUs. */
+ * csrc/hf6d_api.cu).  hf6d_peer_attach also sets the tree shard and the class shard to rank/world.  Contract:
+ *  - the ranks of a group export, attach (and later detach) TOGETHER, with a barrier of the caller's transport between
+ *    hf6d_peer_attach on every rank and the first hf6d_run on any (a rank must not signal into memory a peer has not mapped
+ *    yet) and another one before hf6d_peer_detach / hf6d_destroy (nobody unmaps while a peer may still read);
+ *  - every rank then runs the same frames on the same slots, in the same split: whole frames (SCAN..POSE), or SCAN..VOTE
+ *    followed by CENTRES..POSE.  Any other sub-range (e.g. POSE alone on one rank) breaks the flag sequence;
+ *  - the slots' streams should not share a hardware queue (CUDA_DEVICE_MAX_CONNECTIONS >= number of streams the process
+ *    uses): a slot that waits for a peer's flag blocks its queue, and the peer may be waiting for a frame queued behind it;
+ *  - waits are bounded: hf6d_sync / hf6d_collect / hf6d_wait give up after HF6D_PEER_TIMEOUT_MS (default 20000) with
+ *    HF6D_ECUDA and hf6d_peer_timed_out() == 1 when a peer never answers; the context must then be destroyed.  A frame
+ *    whose enqueue fails half way does not count towards the slot's sequence number.
+ * Replaces the reference's merge of per-thread vote maps and leaf lists, HoughForest/src/HFTest.cpp:645-654, across GPUs. */
 #define HF6D_MAX_SLOTS 16
 size_t hf6d_peer_blob_bytes(void);
 int hf6d_peer_export(hf6d_ctx* c, void* blob, size_t cap_bytes);
 int hf6d_peer_attach(hf6d_ctx* c, int rank, int world, const void* blobs /* world blobs, rank order */, size_t bytes_each);
 int hf6d_peer_detach(hf6d_ctx* c);
-int hf6d_peer_timed_out(hf6d_ctx* c); /* 1 if a flag wait gave up (fallback wait kernel only); results are then invalid */
+int hf6d_peer_timed_out(hf6d_ctx* c); /* 1 if a flag wait gave up (host-side deadline or the fallback wait kernel); results are then invalid */
 /* Encoder arithmetic (replaces Caffe's fp32 sgemm, HoughForest/src/HFTest.cpp:585-596):
  *   0 = bf16 operands, fp32 accumulation (default: the throughput mode; features within 3e-2 of fp32);
  *   1 = split bf16: every operand as hi + lo bf16 halves, a product as a_hi*w_hi + a_lo*w_hi + a_hi*w_lo on the same

@@ -36,6 +36,7 @@ struct DevForest {
     const int32_t* vgroup;     // per vote: its group (read only for votes that land in a centre window)
     const int2* leaf_votes;    // per leaf: (first vote, number of gated votes) over all its groups (contiguous)
     const short4* bins;        // per vote: integer-degree yaw, pitch, roll bins (HFTest.cpp:779-780, :863)
+    const float2* oz_range;    // per group: (min, max) of its votes' oz; (inf, -inf) when unordered (a NaN among them)
 };
 
 // x86 cvttss2si semantics: NaN / out of range -> INT_MIN (CUDA's cast saturates and maps NaN to 0).

@@ -47,7 +47,7 @@ __global__ void scan_count_kernel(const uint16_t* __restrict__ depth, FrameGeom 
 // One warp per stride-grid row: exclusive offset = sum of the counts of earlier rows, then ballot compaction.
 // counts[0] = P, counts[1] = P' = floor(P / batch) * batch (the reference drops the partial batch, HFTest.cpp:433).
 __global__ void scan_compact_kernel(const uint16_t* __restrict__ depth, FrameGeom g, const int* __restrict__ row_count,
-                                    int* __restrict__ locs, int* __restrict__ counts) {
+                                    int* __restrict__ locs, int* __restrict__ counts, int* __restrict__ row_off) {
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= g.gh) return;
@@ -66,6 +66,7 @@ __global__ void scan_compact_kernel(const uint16_t* __restrict__ depth, FrameGeo
         counts[0] = total;
         counts[1] = (total / g.batch) * g.batch;
     }
+    if (lane == 0 && row_off) row_off[row] = before;  // index of the row's first patch (gather_tile_kernel)
     const int h = row * g.stride;
     int pos = before;
     for (int c0 = 0; c0 < g.gw; c0 += 32) {
@@ -282,6 +283,213 @@ gather_normalise_kernel(const uint2* __restrict__ tex, FrameGeom g, const int* _
     sequential_variances(s_term, s_stat);
     __syncthreads();
     if (!live) return;
+    const float lim_rgb = __fmul_rn(3.0f, s_stat[pl][2]), lim_d = __fmul_rn(3.0f, s_stat[pl][3]);
+    // ---- clip to +-3 "std", scale to [0.1, 0.9], quantise (HFTest.cpp:538-565); NaN (lim == 0) -> 0
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) {
+        const float m = ch < 3 ? mean_rgb : mean_d;
+        const float lim = ch < 3 ? lim_rgb : lim_d;
+        uint32_t qb[8];
+#pragma unroll
+        for (int tx = 0; tx < 8; ++tx) {
+            float x = __fsub_rn(val[ch][tx], m);
+            if (x > lim) x = lim;
+            if (x < -lim) x = -lim;
+            x = __fdiv_rn(x, lim);
+            x = __fadd_rn(__fmul_rn(__fadd_rn(x, 1.0f), 0.4f), 0.1f);
+            qb[tx] = (uint32_t)(f2i_x86(__fmul_rn(x, 255.0f)) & 0xFF);
+        }
+        const size_t o = (size_t)p * 256 + ch * 64 + ty * 8;
+        uint32_t pk[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            __nv_bfloat162 h2 = __floats2bfloat162_rn((float)qb[2 * k], (float)qb[2 * k + 1]);
+            pk[k] = *reinterpret_cast<uint32_t*>(&h2);
+        }
+        *reinterpret_cast<uint4*>(a_out + o) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        if (q_out) {
+            const uint32_t lo = qb[0] | (qb[1] << 8) | (qb[2] << 16) | (qb[3] << 24);
+            const uint32_t hi = qb[4] | (qb[5] << 8) | (qb[6] << 16) | (qb[7] << 24);
+            *reinterpret_cast<uint2*>(q_out + o) = make_uint2(lo, hi);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ tiled gather
+// gather_normalise_kernel above issues 256 scattered 8-byte loads per patch (ncu, round 1: 1.1e7 load sectors = 366 MB of L1
+// traffic for a 2.4 MB texel array) and runs the sequential statistics of 16 patches on one warp while the CTA's other three
+// wait.  gather_tile_kernel is the same arithmetic, reorganised around what neighbouring patches share:
+//   * a CTA takes up to 32 CONSECUTIVE patches of one stride-grid row (grid = row segments x rows; scan_compact_kernel
+//     publishes the index of every row's first patch): their footprints overlap almost completely, so the CTA loads the
+//     bounding box of all of them into shared memory once -- coalesced rows of 8-byte texels, zero outside the image (the
+//     texture unit's border mode) -- and every bilinear tap is a shared-memory read;
+//   * the strictly sequential sums (HFTest.cpp:508-534) are one lane per chain: warp 0 runs the 32 colour chains, warp 1
+//     the 32 depth chains (uniform trip counts, conflict-free rows), everything else of the patch stays in registers;
+//   * a segment whose bounding box does not fit the tile (a row interrupted by holes, patches much larger than planned for)
+//     takes its taps from global memory like the old kernel.
+constexpr int GT_PATCHES = 32;
+constexpr int GT_THREADS = GT_PATCHES * 8;
+constexpr int GT_PITCH = 257;   // floats per patch row of the value buffer: 1 (mod 32), one bank per lane in the chains
+constexpr int GT_VAL_BYTES = GT_PATCHES * GT_PITCH * 4;
+
+template <bool STAGED>
+__device__ __forceinline__ uint2 gt_texel(const uint2* __restrict__ tex, const uint2* s_tile, const FrameGeom& g, int x, int y,
+                                          int tx0, int ty0, int pitch) {
+    if (STAGED) return s_tile[(y - ty0) * pitch + (x - tx0)];
+    return (x >= 0 && x < g.W && y >= 0 && y < g.H) ? __ldg(tex + (size_t)y * g.W + x) : make_uint2(0u, 0u);
+}
+
+// The 8 samples of patch row ty (same operations, same order as gather_normalise_kernel).
+template <bool STAGED>
+__device__ __forceinline__ void gt_sample_row(const uint2* __restrict__ tex, const uint2* s_tile, const FrameGeom& g, int x0, int y0,
+                                              float step, float dc, int ty, const float fill[4], int tx0, int ty0, int pitch,
+                                              float (&val)[4][8]) {
+    const float v = __fadd_rn((float)y0, __fmul_rn((float)ty, step));
+    const float fv = floorf(v);
+    const int j = (int)fv;
+    const float c = frac8(__fsub_rn(v, fv)), nc = __fsub_rn(1.0f, c);
+#pragma unroll
+    for (int tx = 0; tx < 8; ++tx) {
+        const float u = __fadd_rn((float)x0, __fmul_rn((float)tx, step));
+        const float fu = floorf(u);
+        const int i = (int)fu;
+        const float al = frac8(__fsub_rn(u, fu)), na = __fsub_rn(1.0f, al);
+        Bilerp b;
+        b.w00 = __fmul_rn(na, nc);
+        b.w10 = __fmul_rn(al, nc);
+        b.w01 = __fmul_rn(na, c);
+        b.w11 = __fmul_rn(al, c);
+        const uint2 q00 = gt_texel<STAGED>(tex, s_tile, g, i, j, tx0, ty0, pitch), q10 = gt_texel<STAGED>(tex, s_tile, g, i + 1, j, tx0, ty0, pitch);
+        const uint2 q01 = gt_texel<STAGED>(tex, s_tile, g, i, j + 1, tx0, ty0, pitch), q11 = gt_texel<STAGED>(tex, s_tile, g, i + 1, j + 1, tx0, ty0, pitch);
+        const float d = div_const<1000, 1>(blend(b, (float)q00.y, (float)q10.y, (float)q01.y, (float)q11.y));
+        if (d > 0.f) {
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch)
+                val[ch][tx] = blend(b, div_const<255, 1>((float)((q00.x >> (8 * ch)) & 0xFFu)),
+                                    div_const<255, 1>((float)((q10.x >> (8 * ch)) & 0xFFu)),
+                                    div_const<255, 1>((float)((q01.x >> (8 * ch)) & 0xFFu)),
+                                    div_const<255, 1>((float)((q11.x >> (8 * ch)) & 0xFFu)));
+            float td = __fadd_rn(__fdiv_rn(__fsub_rn(d, dc), g.range), 0.5f);
+            if (td > 1.0f) td = 1.0f;
+            if (td < 0.0f) td = 0.0f;
+            val[3][tx] = td;
+        } else {
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) val[ch][tx] = fill[ch];
+        }
+    }
+}
+
+// grid = (ceil(gw / GT_PATCHES), gh); dynamic shared memory = max(tile_cap_texels * 8, GT_VAL_BYTES).
+__global__ void __launch_bounds__(GT_THREADS)
+gather_tile_kernel(const uint2* __restrict__ tex, FrameGeom g, const int* __restrict__ locs, const int* __restrict__ counts,
+                   const int* __restrict__ row_count, const int* __restrict__ row_off, int tile_cap_texels,
+                   __nv_bfloat16* __restrict__ a_out, uint8_t* __restrict__ q_out) {
+    extern __shared__ __align__(16) uint8_t gt_smem[];
+    uint2* s_tile = reinterpret_cast<uint2*>(gt_smem);
+    float* s_val = reinterpret_cast<float*>(gt_smem);  // overlays the tile once every tap has been read
+    __shared__ int s_box[4];                           // x min, y min, x max, y max of the segment's footprints
+    __shared__ float s_stat[GT_PATCHES][4];            // mean_rgb, mean_d, var_rgb, var_d
+
+    const int row = blockIdx.y, seg0 = blockIdx.x * GT_PATCHES;
+    const int n_row = row_count[row];
+    if (seg0 >= n_row) return;
+    const int Pp = counts[1];
+    const int p0 = row_off[row] + seg0;
+    if (p0 >= Pp) return;
+    const int n_here = min(min(GT_PATCHES, n_row - seg0), Pp - p0);
+    const int pl = threadIdx.x >> 3, ty = threadIdx.x & 7;
+    const int p = p0 + pl;
+    const bool live = pl < n_here;
+    if (threadIdx.x == 0) { s_box[0] = INT_MAX; s_box[1] = INT_MAX; s_box[2] = INT_MIN; s_box[3] = INT_MIN; }
+    __syncthreads();
+
+    int x0 = 0, y0 = 0;
+    float step = 0.f, dc = 0.f;
+    float fill[4] = {0.f, 0.f, 0.f, 0.f};
+    if (live) {
+        const int2 ctr = *reinterpret_cast<const int2*>(locs + 2 * p);
+        dc = div_const<1000, 1>((float)tex[(size_t)ctr.y * g.W + ctr.x].y);  // exact texel fetch, patch_extractor.cu:253
+        const int a = adaptive_size(g, dc);
+        x0 = ctr.x - a / 2;
+        y0 = ctr.y - a / 2;
+        step = __fdiv_rn((float)a, (float)g.ps);
+        if (g.fill_random) {
+            const unsigned long long z = mix64(g.fill_seed + 0x9E3779B97F4A7C15ULL * (unsigned long long)(p + 1));
+            fill[2] = div_const<255, 1>((float)((z & 0xFFFF) % 255));
+            fill[1] = div_const<255, 1>((float)(((z >> 16) & 0xFFFF) % 255));
+            fill[0] = div_const<255, 1>((float)(((z >> 32) & 0xFFFF) % 255));
+            fill[3] = div_const<255, 1>((float)(((z >> 48) & 0xFFFF) % 255));
+        }
+        // texels this thread's row of samples touches: columns floor(u_0) .. floor(u_7) + 1, rows floor(v) .. floor(v) + 1
+        const int xa = x0, xb = (int)floorf(__fadd_rn((float)x0, __fmul_rn(7.0f, step))) + 1;
+        const int ya = (int)floorf(__fadd_rn((float)y0, __fmul_rn((float)ty, step))), yb = ya + 1;
+        atomicMin(&s_box[0], xa);
+        atomicMin(&s_box[1], ya);
+        atomicMax(&s_box[2], xb);
+        atomicMax(&s_box[3], yb);
+    }
+    __syncthreads();
+    const int tx0 = s_box[0], ty0 = s_box[1];
+    const int tw = s_box[2] - tx0 + 1, th = s_box[3] - ty0 + 1;
+    const int pitch = tw | 1;  // odd: the rows of one patch spread over the banks
+    const bool staged = (long long)pitch * th <= (long long)tile_cap_texels;
+    if (staged) {
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        for (int r = warp; r < th; r += GT_THREADS / 32) {
+            const int y = ty0 + r;
+            const bool row_in = y >= 0 && y < g.H;
+            const uint2* src = tex + (size_t)(row_in ? y : 0) * g.W;
+            for (int x = lane; x < tw; x += 32) {
+                const int gx = tx0 + x;
+                s_tile[r * pitch + x] = (row_in && gx >= 0 && gx < g.W) ? __ldg(src + gx) : make_uint2(0u, 0u);  // border texel = 0
+            }
+        }
+    }
+    __syncthreads();
+
+    float val[4][8];
+    if (live) {
+        if (staged) gt_sample_row<true>(tex, s_tile, g, x0, y0, step, dc, ty, fill, tx0, ty0, pitch, val);
+        else gt_sample_row<false>(tex, s_tile, g, x0, y0, step, dc, ty, fill, tx0, ty0, pitch, val);
+    } else {
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch)
+#pragma unroll
+            for (int tx = 0; tx < 8; ++tx) val[ch][tx] = 0.f;
+    }
+    __syncthreads();  // every tap has been read: the tile's memory becomes the value buffer
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch)
+#pragma unroll
+        for (int tx = 0; tx < 8; ++tx) s_val[pl * GT_PITCH + ch * 64 + ty * 8 + tx] = val[ch][tx];
+    __syncthreads();
+    // ---- the reference's sequential sums, one lane per chain: warp 0 = colour (192 terms), warp 1 = depth (64 terms)
+    if (threadIdx.x < 64) {
+        const int cp = threadIdx.x & 31, which = threadIdx.x >> 5;
+        const float* src = s_val + cp * GT_PITCH + which * 192;
+        const int n_terms = which ? 64 : 192;
+        float m = 0.f;  // means: `mean += x / N` in float (HFTest.cpp:508-524)
+        if (which) {
+#pragma unroll 16
+            for (int j = 0; j < 64; ++j) m = __fadd_rn(m, __fmul_rn(src[j], 1.0f / 64.0f));
+        } else {
+#pragma unroll 16
+            for (int j = 0; j < 192; ++j) m = __fadd_rn(m, div_const<192, 1>(src[j]));
+        }
+        float var = 0.f;  // "std": `std += pow(x - mean, 2) / N` in double, narrowed per element (oracle choice C3, :527-534)
+#pragma unroll 8
+        for (int j = 0; j < n_terms; ++j) {
+            const double d = (double)__fsub_rn(src[j], m), dd = __dmul_rn(d, d);
+            const double t = __dmul_rn(which ? dd : div3_rn(dd), 1.0 / 64.0);
+            var = __double2float_rn(__dadd_rn((double)var, t));
+        }
+        s_stat[cp][which] = m;
+        s_stat[cp][2 + which] = var;
+    }
+    __syncthreads();
+    if (!live) return;
+    const float mean_rgb = s_stat[pl][0], mean_d = s_stat[pl][1];
     const float lim_rgb = __fmul_rn(3.0f, s_stat[pl][2]), lim_d = __fmul_rn(3.0f, s_stat[pl][3]);
     // ---- clip to +-3 "std", scale to [0.1, 0.9], quantise (HFTest.cpp:538-565); NaN (lim == 0) -> 0
 #pragma unroll

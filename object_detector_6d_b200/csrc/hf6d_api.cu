@@ -6,7 +6,9 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <thread>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -31,6 +33,7 @@ namespace {
 thread_local std::string g_create_error;
 
 constexpr int WA_MAX_DYN_SMEM = 200 * 1024;  // shared-memory z histograms of window_accumulate_kernel
+constexpr int WS_MAX_DYN_SMEM = 192 * 1024;  // ... and of window_stream_kernel (31 KB of static shared memory beside them)
 constexpr int MAX_YP = 16;    // upper bound for max_yaw_pitch_hypotheses
 constexpr int MAX_ROLL = 8;   // upper bound for max_roll_hypotheses
 
@@ -64,6 +67,7 @@ struct Slot {
     cudaEvent_t ev_enc[4] = {nullptr, nullptr, nullptr, nullptr};
     bool ev_enc_valid = false;
     int* row_count = nullptr;
+    int* row_off = nullptr;  // [gh] index of the first patch of every stride-grid row (gather_tile_kernel)
     int* counts = nullptr;  // [2] inside the result block
     int* locs = nullptr;
     __nv_bfloat16 *A0 = nullptr, *H1 = nullptr, *H2 = nullptr;
@@ -79,6 +83,12 @@ struct Slot {
     unsigned long long* bmax = nullptr;  // [maps][block rows][block cols] key-maxima of 8x8 blocks (NMS)
     uint4* entries = nullptr;     // window entries of the pose stage: {vote, class << 16 | window mask, pixel depth, -}
     unsigned* win_cnt = nullptr;  // [S][n_groups] window entries per (slot, vote group)
+    // vote stream path of the pose stage (vote.cuh, window_stream_kernel)
+    uint2* vstream = nullptr;     // one record per cast vote, written by the vote kernel
+    int* stream_n = nullptr;      // records in the stream
+    uint2* pairs = nullptr;       // distinct (slot, group) pairs of the frame
+    bool stream_valid = false;    // the stream holds the votes of the slot's current leaf table
+    bool cnt_dirty = true;        // win_cnt may hold non-zero counters (the stream path leaves it zeroed behind itself)
     // result block (one D2H)
     uint8_t* res_dev = nullptr;
     uint8_t* res_host = nullptr;  // pinned
@@ -116,6 +126,10 @@ struct hf6d_ctx {
     int lanes_per_hit = 32;      // lanes that share one (slot, group) pair: 16 when no vote group holds more than 16 votes
     int wc_ctas_per_sm = 1;      // resident CTAs of window_entries_kernel per SM
     int entry_cap = 0;           // capacity of a frame slot's window-entry list (entries beyond it are accumulated in place)
+    bool gather_tiled = true;    // gather_tile_kernel (shared-memory staged texel tiles); HF6D_GATHER=direct: the per-tap loads
+    int gather_tile_texels = 0, gather_smem = 0;
+    bool use_stream = false;     // pose stage reads the vote stream instead of enumerating the votes again
+    int stream_cap = 0, pair_cap = 0;
     int shard_rank = 0, shard_world = 1;
     int class_rank = 0, class_world = 1;  // centres + pose only for classes k % class_world == class_rank
     // peer exchange (tree-sharded mode over NVLink peer memory, hf6d_peer_attach)
@@ -127,6 +141,7 @@ struct hf6d_ctx {
     std::vector<const int*> peer_leaf[HF6D_MAX_PEERS];                // [rank][slot]
     std::vector<void*> peer_opened;                                   // cudaIpcOpenMemHandle results
     int* peer_timeout = nullptr;                                      // set by the fallback wait kernel when it gives up
+    bool peer_wait_expired = false;                                   // a bounded host-side wait ran out (sync_stream_bounded)
     int encoder_mode = 0;
     // per encoder layer: row of HF6D_ENC_CONFIGS within the layer's shape class (0 = default: CTA pairs, cta_group::2;
     // 1 = stand-alone CTAs).  Tuning switch: HF6D_ENC_VARIANT="a,b,c".
@@ -224,6 +239,11 @@ int upload_model(hf6d_ctx* c) {
         for (size_t i = 0; i < bins.size(); ++i) bins[i] = make_short4(hf.yaw[i], hf.pitch[i], hf.roll[i], 0);
         if ((r = dev_upload(c, dm.allocs, &dm.f.bins, bins))) return r;
     }
+    {
+        std::vector<float2> rg(hf.groups.size());
+        for (size_t i = 0; i < rg.size(); ++i) rg[i] = make_float2(hf.g_ozmin[i], hf.g_ozmax[i]);
+        if ((r = dev_upload(c, dm.allocs, &dm.f.oz_range, rg))) return r;
+    }
     std::vector<uint8_t> sep;
     build_sep_table(sep);
     const uint8_t* sp = nullptr;
@@ -298,6 +318,7 @@ int alloc_slot(hf6d_ctx* c, Slot& s) {
     if ((r = dev_alloc(c, s.allocs, &s.tex, HW))) return r;
     if (c->p.patch_mode == 1 && (r = dev_alloc(c, s.allocs, &s.normals, HW))) return r;
     if ((r = dev_alloc(c, s.allocs, &s.row_count, (size_t)g.gh))) return r;
+    if ((r = dev_alloc(c, s.allocs, &s.row_off, (size_t)g.gh))) return r;
     if ((r = dev_alloc(c, s.allocs, &s.locs, (size_t)g.cap * 2))) return r;
     if ((r = dev_alloc(c, s.allocs, &s.A0, (size_t)g.cap * c->dm.k_pad[0]))) return r;
     if ((r = dev_alloc(c, s.allocs, &s.q_u8, (size_t)g.cap * c->dm.n_in[0]))) return r;
@@ -310,7 +331,12 @@ int alloc_slot(hf6d_ctx* c, Slot& s) {
     if ((r = dev_alloc(c, s.allocs, &s.blurred, HW * K))) return r;
     const int n_lists = std::max(K, S);
     if ((r = dev_alloc(c, s.allocs, &s.list, (size_t)n_lists * NMS_LIST_CAP))) return r;
-    if ((r = dev_alloc(c, s.allocs, &s.list_n, (size_t)n_lists + 3))) return r;  // +3: batch counter, reserved entries, accumulate-pass batch counter (pose)
+    if ((r = dev_alloc(c, s.allocs, &s.list_n, (size_t)n_lists + 8))) return r;  // +0..2: batch counter, reserved entries, accumulate-pass batch counter; +3..5: stream chunk counter, finished CTAs, (slot, group) pairs (pose)
+    if (c->use_stream) {
+        if ((r = dev_alloc(c, s.allocs, &s.vstream, (size_t)c->stream_cap))) return r;
+        if ((r = dev_alloc(c, s.allocs, &s.stream_n, (size_t)4))) return r;
+        if ((r = dev_alloc(c, s.allocs, &s.pairs, (size_t)c->pair_cap))) return r;
+    }
     if ((r = dev_alloc(c, s.allocs, &s.entries, (size_t)c->entry_cap))) return r;
     const size_t yp = (size_t)c->reg.ny * c->reg.np;
     const size_t yp_tmp = (size_t)c->reg.ny * c->yp_blur.nc, yp_out = (size_t)c->yp_blur.nr * c->yp_blur.nc;
@@ -326,6 +352,8 @@ int alloc_slot(hf6d_ctx* c, Slot& s) {
     if ((r = dev_alloc(c, s.allocs, &s.racc, (size_t)S * MAX_YP * HF6D_POSE_BINS))) return r;
     if ((r = dev_alloc(c, s.allocs, &s.res_dev, c->rl.total))) return r;
     CU_TRY(c, cudaMemset(s.res_dev, 0, c->rl.total));
+    CU_TRY(c, cudaMemset(s.win_cnt, 0, (size_t)S * c->hf.groups.size() * 4));
+    s.cnt_dirty = false;
     CU_TRY(c, cudaMemset(s.leaf_ord, 0xFF, (size_t)g.cap * T * 4));
     CU_TRY(c, cudaMemset(s.A0, 0, (size_t)g.cap * c->dm.k_pad[0] * 2));
     CU_TRY(c, cudaMallocHost(reinterpret_cast<void**>(&s.res_host), c->rl.total));
@@ -513,6 +541,28 @@ int peer_wait(hf6d_ctx* c, Slot& s, int slot, int kind, uint32_t value) {
     return HF6D_OK;
 }
 
+// cudaStreamSynchronize with a deadline while the peer exchange is on: a stream that waits for a peer's flag (stream memory
+// operation: no kernel, hence no in-kernel timeout) would otherwise block the host for ever if that peer died or skipped a
+// frame.  HF6D_PEER_TIMEOUT_MS (default 20000).  On expiry the stream is still blocked: the context must be destroyed.
+int sync_stream_bounded(hf6d_ctx* c, cudaStream_t st) {
+    if (!c->peer_on) {
+        CU_TRY(c, cudaStreamSynchronize(st));
+        return HF6D_OK;
+    }
+    static const long timeout_ms = getenv("HF6D_PEER_TIMEOUT_MS") ? atol(getenv("HF6D_PEER_TIMEOUT_MS")) : 20000;
+    const auto t0 = std::chrono::steady_clock::now();
+    for (;;) {
+        const cudaError_t e = cudaStreamQuery(st);
+        if (e == cudaSuccess) return HF6D_OK;
+        if (e != cudaErrorNotReady) return fail(c, HF6D_ECUDA, "cudaStreamQuery: %s", cudaGetErrorString(e));
+        if (std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now() - t0).count() > timeout_ms) {
+            c->peer_wait_expired = true;
+            return fail(c, HF6D_ECUDA, "peer exchange: no answer from a peer within %ld ms (the slot's stream is still waiting; destroy the context)", timeout_ms);
+        }
+        std::this_thread::yield();
+    }
+}
+
 inline int slot_index(const hf6d_ctx* c, const Slot& s) { return (int)(&s - c->slots.data()); }
 PeerMaps peer_maps_of(const hf6d_ctx* c, int slot) {
     PeerMaps pm;
@@ -546,7 +596,7 @@ int run_stage(hf6d_ctx* c, Slot& s, int stage) {
             const int blocks = (g.gh + 7) / 8;
             scan_count_kernel<<<blocks, 256, 0, st>>>(s.depth, g, s.row_count);
             LAUNCH_CHECK(c, s);
-            scan_compact_kernel<<<blocks, 256, 0, st>>>(s.depth, g, s.row_count, s.locs, s.counts);
+            scan_compact_kernel<<<blocks, 256, 0, st>>>(s.depth, g, s.row_count, s.locs, s.counts, s.row_off);
             LAUNCH_CHECK(c, s);
             break;
         }
@@ -558,7 +608,10 @@ int run_stage(hf6d_ctx* c, Slot& s, int stage) {
                 LAUNCH_CHECK(c, s);
                 gather_normals_kernel<<<g.cap / GATHER_PATCHES_PER_CTA, GATHER_THREADS, 0, st>>>(
                     s.tex, s.normals, g, s.locs, s.counts, s.A0, c->debug_capture ? s.q_u8 : nullptr);
-            } else
+            } else if (c->gather_tiled)
+                gather_tile_kernel<<<dim3((g.gw + GT_PATCHES - 1) / GT_PATCHES, g.gh), GT_THREADS, c->gather_smem, st>>>(
+                    s.tex, g, s.locs, s.counts, s.row_count, s.row_off, c->gather_tile_texels, s.A0, c->debug_capture ? s.q_u8 : nullptr);
+            else
                 gather_normalise_kernel<<<g.cap / GATHER_PATCHES_PER_CTA, GATHER_THREADS, 0, st>>>(
                     s.tex, g, s.locs, s.counts, s.A0, c->debug_capture ? s.q_u8 : nullptr);
             LAUNCH_CHECK(c, s);
@@ -598,8 +651,16 @@ int run_stage(hf6d_ctx* c, Slot& s, int stage) {
             CU_TRY(c, cudaMemsetAsync(s.maps, 0, (size_t)K * g.W * g.H * 8, st));
             const long long items = (long long)g.cap * f.T;
             const int blocks = (int)std::min<long long>((items + VOTE_THREADS - 1) / VOTE_THREADS, (long long)c->sms * 8);
-            vote_kernel<<<blocks, VOTE_THREADS, 0, st>>>(f, g, switches_of(c), s.locs, s.depth, s.leaf_ord, s.counts, s.maps);
+            // the vote stream serves the pose stage of THIS context: with sharded trees the windows need the other ranks' votes
+            const bool streaming = c->use_stream && c->shard_world == 1 && !c->peer_on;
+            VoteStream vs{nullptr, nullptr, 0};
+            if (streaming) {
+                CU_TRY(c, cudaMemsetAsync(s.stream_n, 0, 4, st));
+                vs = VoteStream{s.vstream, s.stream_n, c->stream_cap};
+            }
+            vote_kernel<<<blocks, VOTE_THREADS, 0, st>>>(f, g, switches_of(c), s.locs, s.depth, s.leaf_ord, s.counts, s.maps, vs);
             LAUNCH_CHECK(c, s);
+            s.stream_valid = streaming;
             break;
         }
         case HF6D_STAGE_CENTRES: {
@@ -635,35 +696,66 @@ int run_stage(hf6d_ctx* c, Slot& s, int stage) {
         case HF6D_STAGE_POSE: {
             const size_t yp = (size_t)c->reg.ny * c->reg.np;
             const int max_yp = p.max_yaw_pitch_hypotheses, max_roll = p.max_roll_hypotheses;
-            // clear only the accumulator slots a class can use (slot = class * HF6D_MAX_CENTRES + centre rank): one launch
+            const int n_groups = (int)c->hf.groups.size();
+            // Two implementations of pass A (HFTest.cpp:742-802).  The stream path needs the vote stream the vote kernel wrote
+            // for this slot's current leaf table; sharded contexts, huge forests (stream over budget) and stage-isolated runs
+            // that replaced the leaf table after voting use the enumeration path.  Both give identical accumulators.
+            const bool stream_path = c->use_stream && s.stream_valid && c->shard_world == 1 && !c->peer_on;
+            // clear only the accumulator slots a class can use (slot = class * HF6D_MAX_CENTRES + centre rank): one launch.
+            // The (slot, group) counters are left zeroed by the stream path itself (its roll pass zeroes what it visited).
             {
                 ClearPlan cp;
                 memset(&cp, 0, sizeof cp);
                 cp.base[0] = s.zacc;    cp.slot_bytes[0] = (unsigned long long)HF6D_Z_BINS * 8;
                 cp.base[1] = s.ypacc;   cp.slot_bytes[1] = (unsigned long long)yp * 8;
                 cp.base[2] = s.racc;    cp.slot_bytes[2] = (unsigned long long)max_yp * HF6D_POSE_BINS * 8;
-                cp.base[3] = s.win_cnt; cp.slot_bytes[3] = (unsigned long long)c->hf.groups.size() * 4;
+                cp.base[3] = stream_path ? nullptr : s.win_cnt; cp.slot_bytes[3] = (unsigned long long)n_groups * 4;
                 bool any = false;
                 for (int k = 0; k < K; ++k) {
                     cp.n_slots[k] = seeks_class(c, k) ? c->objects[k].max_location_hypotheses : 0;
                     any |= cp.n_slots[k] > 0;
                 }
                 if (any) {
-                    clear_accumulators_kernel<<<dim3(c->sms, K, 4), 256, 0, st>>>(cp);
+                    clear_accumulators_kernel<<<dim3(c->sms, K, stream_path ? 3 : 4), 256, 0, st>>>(cp);
                     LAUNCH_CHECK(c, s);
                 }
+                if (stream_path && s.cnt_dirty) {  // the enumeration path (or nothing yet) used the table last: all of it, once
+                    CU_TRY(c, cudaMemsetAsync(s.win_cnt, 0, (size_t)S * n_groups * 4, st));
+                    s.cnt_dirty = false;
+                }
+                if (!stream_path) s.cnt_dirty = true;
             }
-            CU_TRY(c, cudaMemsetAsync(s.list_n, 0, ((size_t)std::max(K, S) + 3) * 4, st));
+            CU_TRY(c, cudaMemsetAsync(s.list_n, 0, ((size_t)std::max(K, S) + 8) * 4, st));
             const long long items = (long long)g.cap * f.T;
             CentreTable ct{rv.centres, rv.active};
             const int half_win = p.centers_nms_wsize / 2;
-            const int n_groups = (int)c->hf.groups.size();
             const size_t cell_bytes = cell_grid_bytes(g.W, g.H, half_win, K);
             const int table_blocks = c->sms * 8;
-            {
+            int* ctr = s.list_n + std::max(K, S);
+            ZSlotTable zt;
+            memset(&zt, 0, sizeof zt);
+            for (int k = 0; k < K; ++k)
+                zt.zoff[k + 1] = (int16_t)(zt.zoff[k] + (seeks_class(c, k) ? c->objects[k].max_location_hypotheses : 0));
+            const size_t zbytes = (size_t)zt.zoff[K] * HF6D_Z_BINS * 4;
+            const PairList pl{s.pairs, ctr + 5, c->pair_cap};
+            if (stream_path) {
+                const VoteStream vs{s.vstream, s.stream_n, c->stream_cap};
+                const size_t dyn = ((zbytes + 15) & ~(size_t)15) + cell_bytes;
+#define HF6D_WS(GG)                                                                                                         \
+    window_stream_kernel<GG><<<c->sms, WA_THREADS, dyn, st>>>(f, g, switches_of(c, true), vs, s.depth, ct, half_win, n_groups, zt, \
+                                                             s.win_cnt, pl, s.zacc, ctr + 3, ctr + 4, 20 /* HFTest.cpp:745 */,     \
+                                                             rv.active, rv.mode_z)
+                if (c->lanes_per_hit == 16) HF6D_WS(16); else HF6D_WS(32);
+#undef HF6D_WS
+                LAUNCH_CHECK(c, s);
+                if (c->lanes_per_hit == 16)
+                    yawpitch_from_pairs_kernel<16><<<table_blocks, TABLE_THREADS, 0, st>>>(f, s.win_cnt, n_groups, pl, rv.active, c->reg, s.ypacc);
+                else
+                    yawpitch_from_pairs_kernel<32><<<table_blocks, TABLE_THREADS, 0, st>>>(f, s.win_cnt, n_groups, pl, rv.active, c->reg, s.ypacc);
+                LAUNCH_CHECK(c, s);
+            } else {
                 // one resident wave; batches of 32 items are handed out through list_n[n_lists], list space is reserved
                 // through list_n[n_lists + 1] (both zeroed above)
-                int* ctr = s.list_n + std::max(K, S);
                 const int wc_blocks = (int)std::min<long long>((items + VOTE_THREADS - 1) / VOTE_THREADS, (long long)c->sms * c->wc_ctas_per_sm);
                 window_entries_kernel<<<wc_blocks, VOTE_THREADS, cell_bytes, st>>>(f, g, switches_of(c, true), s.locs, s.depth,
                                                                                  leaf_tables_of(c, s, slot_index(c, s)),
@@ -671,11 +763,6 @@ int run_stage(hf6d_ctx* c, Slot& s, int stage) {
                                                                                  c->entry_cap, ctr + 1, s.win_cnt, s.zacc);
                 LAUNCH_CHECK(c, s);
                 if (c->entry_cap >= ENTRY_BLOCK) {
-                    ZSlotTable zt;
-                    memset(&zt, 0, sizeof zt);
-                    for (int k = 0; k < K; ++k)
-                        zt.zoff[k + 1] = (int16_t)(zt.zoff[k] + (seeks_class(c, k) ? c->objects[k].max_location_hypotheses : 0));
-                    const size_t zbytes = (size_t)zt.zoff[K] * HF6D_Z_BINS * 4;
                     static const bool smem_z_ok = !(getenv("HF6D_WA_SMEM_Z") && atoi(getenv("HF6D_WA_SMEM_Z")) == 0);  // tuning override
                     const bool zs = smem_z_ok && zbytes <= (size_t)WA_MAX_DYN_SMEM;
                     const int wa_grid = c->sms * (zs ? (int)std::max<size_t>(1, std::min<size_t>(2, (200 * 1024) / (zbytes + 24 * 1024))) : 2);
@@ -685,16 +772,16 @@ int run_stage(hf6d_ctx* c, Slot& s, int stage) {
                     if (zs) { if (c->lanes_per_hit == 16) HF6D_WA(true, 16); else HF6D_WA(true, 32); }
                     else { if (c->lanes_per_hit == 16) HF6D_WA(false, 16); else HF6D_WA(false, 32); }
 #undef HF6D_WA
+                    LAUNCH_CHECK(c, s);
                 }
+                if (c->lanes_per_hit == 16)
+                    yawpitch_from_counts_kernel<16><<<table_blocks, TABLE_THREADS, 0, st>>>(f, s.win_cnt, n_groups, rv.active, S, c->reg, s.ypacc);
+                else
+                    yawpitch_from_counts_kernel<32><<<table_blocks, TABLE_THREADS, 0, st>>>(f, s.win_cnt, n_groups, rv.active, S, c->reg, s.ypacc);
+                LAUNCH_CHECK(c, s);
+                z_mode_kernel<<<S, 128, 0, st>>>(s.zacc, 20 /* HFTest.cpp:745 */, rv.active, rv.mode_z);
+                LAUNCH_CHECK(c, s);
             }
-            LAUNCH_CHECK(c, s);
-            if (c->lanes_per_hit == 16)
-                yawpitch_from_counts_kernel<16><<<table_blocks, TABLE_THREADS, 0, st>>>(f, s.win_cnt, n_groups, rv.active, S, c->reg, s.ypacc);
-            else
-                yawpitch_from_counts_kernel<32><<<table_blocks, TABLE_THREADS, 0, st>>>(f, s.win_cnt, n_groups, rv.active, S, c->reg, s.ypacc);
-            LAUNCH_CHECK(c, s);
-            z_mode_kernel<<<S, 128, 0, st>>>(s.zacc, 20 /* HFTest.cpp:745 */, rv.active, rv.mode_z);
-            LAUNCH_CHECK(c, s);
             const MapDims md{HF6D_POSE_BINS, HF6D_POSE_BINS};
             const MapRect rin{c->reg.y0, c->reg.p0, c->reg.ny, c->reg.np};
             const MapRect rout = c->yp_blur;
@@ -716,7 +803,12 @@ int run_stage(hf6d_ctx* c, Slot& s, int stage) {
                                                    rv.n_peaks, rv.peak_yx, rv.peak_score);
             LAUNCH_CHECK(c, s);
             PeakTable pk{rv.n_peaks, rv.peak_yx, max_yp};
-            if (c->lanes_per_hit == 16)
+            if (stream_path) {
+                if (c->lanes_per_hit == 16)
+                    roll_from_pairs_kernel<16><<<table_blocks, TABLE_THREADS, 0, st>>>(f, s.win_cnt, n_groups, pl, pk, p.pose_blur_size / 2, s.racc);
+                else
+                    roll_from_pairs_kernel<32><<<table_blocks, TABLE_THREADS, 0, st>>>(f, s.win_cnt, n_groups, pl, pk, p.pose_blur_size / 2, s.racc);
+            } else if (c->lanes_per_hit == 16)
                 roll_from_counts_kernel<16><<<table_blocks, TABLE_THREADS, 0, st>>>(f, s.win_cnt, n_groups, S, pk, p.pose_blur_size / 2, s.racc);
             else
                 roll_from_counts_kernel<32><<<table_blocks, TABLE_THREADS, 0, st>>>(f, s.win_cnt, n_groups, S, pk, p.pose_blur_size / 2, s.racc);
@@ -732,7 +824,23 @@ int run_stage(hf6d_ctx* c, Slot& s, int stage) {
     return HF6D_OK;
 }
 
+int run_range_impl(hf6d_ctx* c, Slot& s, int first, int last);
+
 int run_range(hf6d_ctx* c, Slot& s, int first, int last) {
+    const uint32_t seq0 = s.peer_seq;
+    const int r = run_range_impl(c, s, first, last);
+    if (r && c->peer_on) {
+        // a frame that was not enqueued completely must not count: drain what was enqueued (bounded: a peer may never answer)
+        // and put the slot's sequence number back, so that this rank stays in step with its peers
+        const std::string err = c->err;
+        sync_stream_bounded(c, s.stream);
+        s.peer_seq = seq0;
+        c->err = err;
+    }
+    return r;
+}
+
+int run_range_impl(hf6d_ctx* c, Slot& s, int first, int last) {
     if (first < 0 || last >= HF6D_STAGE_COUNT || first > last) return fail(c, HF6D_EINVAL, "bad stage range %d..%d", first, last);
     s.launches = 0;
     for (int i = 0; i <= HF6D_STAGE_COUNT; ++i) s.ev_valid[i] = false;
@@ -757,7 +865,10 @@ int run_range(hf6d_ctx* c, Slot& s, int first, int last) {
 
 int collect_host(hf6d_ctx* c, Slot& s, hf6d_hypothesis* out, int cap, int* n_out) {
     CU_TRY(c, cudaMemcpyAsync(s.res_host, s.res_dev, c->rl.total, cudaMemcpyDeviceToHost, s.stream));
-    CU_TRY(c, cudaStreamSynchronize(s.stream));
+    {
+        const int r = sync_stream_bounded(c, s.stream);
+        if (r) return r;
+    }
     ResView rv = view_of(c, s.res_host);
     const int K = c->hf.K, max_yp = c->p.max_yaw_pitch_hypotheses, max_roll = c->p.max_roll_hypotheses;
     int n = 0;
@@ -980,6 +1091,41 @@ int finish_create(hf6d_ctx* c, int device, int n_slots) {
         long long cap_entries = std::min<long long>(worst, 4LL << 20);
         if (const char* e = getenv("HF6D_ENTRY_CAP")) cap_entries = std::max(0LL, atoll(e));  // tests force the overflow path
         c->entry_cap = (int)cap_entries;
+    }
+    {
+        // Texel tile of the gather: the footprints of GT_PATCHES consecutive centres of a row at the closest range planned
+        // for (0.5 m); segments that need more (closer surfaces, rows broken by holes) read their taps from global memory.
+        const int amax = (int)((float)p.patch_vox * p.voxel_m / 0.5f * g.focal);
+        const long long w = (long long)(GT_PATCHES - 1) * p.stride + amax + 2, h = amax + 3;
+        long long bytes = std::max<long long>((w | 1) * h * 8, GT_VAL_BYTES);
+        bytes = std::min<long long>(bytes, 100 * 1024);
+        c->gather_smem = (int)bytes;
+        c->gather_tile_texels = (int)(bytes / 8);
+        const char* e = getenv("HF6D_GATHER");
+        c->gather_tiled = !(e && !strcmp(e, "direct"));
+        CU_TRY(c, cudaFuncSetAttribute(gather_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, c->gather_smem));
+    }
+    {
+        // Vote stream for the pose stage: worst case one record per (patch, tree, vote of the largest leaf), one pair per (slot,
+        // group).  Budget 512 MB / 256 MB per frame slot; frames beyond the 13-bit pixel fields, forests beyond the budget
+        // and HF6D_POSE_STREAM=0 (tuning switch; the tests run both paths) use the enumeration path.
+        long long max_leaf_votes = 1;
+        for (size_t i = 0; i < c->hf.leaf_vcnt.size(); ++i) max_leaf_votes = std::max<long long>(max_leaf_votes, c->hf.leaf_vcnt[i]);
+        const long long records = (long long)g.cap * c->hf.T * max_leaf_votes;
+        const long long pairs = (long long)c->S * (long long)c->hf.groups.size();
+        size_t zmax = 0;
+        for (int k = 0; k < K; ++k) zmax += (size_t)HF6D_MAX_CENTRES * HF6D_Z_BINS * 4;
+        const size_t dyn = zmax + cell_grid_bytes(p.W, p.H, p.centers_nms_wsize / 2, K) + 16;
+        const char* e = getenv("HF6D_POSE_STREAM");
+        c->use_stream = !(e && atoi(e) == 0) && p.W + 2 * STREAM_BIAS <= STREAM_COORD_MAX && p.H + 2 * STREAM_BIAS <= STREAM_COORD_MAX &&
+                        p.centers_nms_wsize / 2 <= STREAM_BIAS && records <= (64LL << 20) && pairs <= (32LL << 20) &&
+                        dyn <= (size_t)WS_MAX_DYN_SMEM;
+        c->stream_cap = c->use_stream ? (int)std::max<long long>(records, 1) : 0;
+        c->pair_cap = c->use_stream ? (int)std::max<long long>(pairs, 1) : 0;
+        if (c->use_stream) {
+            CU_TRY(c, cudaFuncSetAttribute(window_stream_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_MAX_DYN_SMEM));
+            CU_TRY(c, cudaFuncSetAttribute(window_stream_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_MAX_DYN_SMEM));
+        }
     }
     CU_TRY(c, cudaFuncSetAttribute(window_accumulate_kernel<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, WA_MAX_DYN_SMEM));
     CU_TRY(c, cudaFuncSetAttribute(window_accumulate_kernel<true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, WA_MAX_DYN_SMEM));
@@ -1204,6 +1350,7 @@ int hf6d_set_tree_shard(hf6d_ctx* c, int rank, int world) {
     if (world < 1 || rank < 0 || rank >= world) return fail(c, HF6D_EINVAL, "bad tree shard %d/%d", rank, world);
     c->shard_rank = rank;
     c->shard_world = world;
+    for (Slot& s : c->slots) s.stream_valid = false;
     return HF6D_OK;
 }
 
@@ -1313,8 +1460,10 @@ int hf6d_peer_attach(hf6d_ctx* c, int rank, int world, const void* blobs, size_t
     c->peer_rank = rank;
     c->peer_world = world;
     c->peer_on = true;
-    for (Slot& s : c->slots) s.peer_seq = 0;
-    CU_TRY(c, cudaMemset(c->peer_flags, 0, (size_t)c->n_slots * 2 * HF6D_MAX_PEERS * 4));
+    // The flag block is NOT cleared here and the slots' sequence numbers keep counting: a peer that attached earlier may
+    // already have signalled into this rank's flags, and erasing that would leave this rank waiting for ever.  The flags were
+    // zeroed once when the block was created (hf6d_peer_export); every rank of a group counts the same frames, so the numbers
+    // stay in step across detach / attach cycles of the whole group.
     int r;
     if ((r = hf6d_set_tree_shard(c, rank, world))) return r;
     return hf6d_set_class_shard(c, rank, world);
@@ -1322,6 +1471,7 @@ int hf6d_peer_attach(hf6d_ctx* c, int rank, int world, const void* blobs, size_t
 
 int hf6d_peer_timed_out(hf6d_ctx* c) {
     if (!c || !c->peer_timeout) return 0;
+    if (c->peer_wait_expired) return 1;
     int v = 0;
     cudaSetDevice(c->device);
     if (cudaMemcpy(&v, c->peer_timeout, 4, cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
@@ -1432,6 +1582,7 @@ int hf6d_upload(hf6d_ctx* c, int slot, const uint8_t* bgr, const uint16_t* depth
     CU_TRY(c, cudaSetDevice(c->device));
     s.bgr = s.own_bgr;
     s.depth = s.own_depth;
+    s.stream_valid = false;
     CU_TRY(c, cudaMemcpyAsync(s.bgr, bgr, HW * 3, cudaMemcpyHostToDevice, s.stream));
     CU_TRY(c, cudaMemcpyAsync(s.depth, depth_mm, HW * 2, cudaMemcpyHostToDevice, s.stream));
     return HF6D_OK;
@@ -1442,6 +1593,7 @@ int hf6d_bind_frame(hf6d_ctx* c, int slot, const void* d_bgr, const void* d_dept
     if (r) return r;
     Slot& s = c->slots[slot];
     if ((d_bgr == nullptr) != (d_depth_mm == nullptr)) return fail(c, HF6D_EINVAL, "bind both planes or neither");
+    s.stream_valid = false;
     s.bgr = d_bgr ? const_cast<uint8_t*>(static_cast<const uint8_t*>(d_bgr)) : s.own_bgr;
     s.depth = d_depth_mm ? const_cast<uint16_t*>(static_cast<const uint16_t*>(d_depth_mm)) : s.own_depth;
     return HF6D_OK;
@@ -1469,8 +1621,7 @@ int hf6d_run(hf6d_ctx* c, int slot, int first_stage, int last_stage) {
 int hf6d_sync(hf6d_ctx* c, int slot) {
     int r = check_slot(c, slot);
     if (r) return r;
-    CU_TRY(c, cudaStreamSynchronize(c->slots[slot].stream));
-    return HF6D_OK;
+    return sync_stream_bounded(c, c->slots[slot].stream);
 }
 
 int hf6d_collect(hf6d_ctx* c, int slot, hf6d_hypothesis* out, int cap, int* n_out) {
@@ -1549,6 +1700,7 @@ int hf6d_inject(hf6d_ctx* c, int slot, int what, const void* src, size_t bytes) 
     if (bytes > b.bytes) return fail(c, HF6D_EINVAL, "buffer %d holds %zu bytes, got %zu", what, b.bytes, bytes);
     CU_TRY(c, cudaStreamSynchronize(s.stream));
     CU_TRY(c, cudaMemcpy(b.ptr, src, bytes, cudaMemcpyHostToDevice));
+    s.stream_valid = false;  // whatever was injected, the vote stream no longer describes the slot
     return HF6D_OK;
 }
 

@@ -273,7 +273,7 @@ std::string out_stem(const std::string& filename) {
 struct Flags {
     bool test = false, train = false, other_mode = false, help = false, stage_times = false, check_inputs = false;
     std::string options_file, output_folder;
-    int device = -1;
+    int device = -1, encoder_mode = 0;
 };
 
 bool parse_bool(const std::string& v) { return !(v == "false" || v == "0" || v == "no" || v == "f" || v == "n"); }
@@ -305,6 +305,7 @@ bool parse_flags(int argc, char** argv, Flags& fl, std::string& err) {
         else if (a == "output_folder" || a == "output_dir") { if (!need(fl.output_folder)) return false; }  // README spelling
         else if (a == "device") { if (!need(tmp)) return false; fl.device = atoi(tmp.c_str()); }
         else if (a == "stage_times") fl.stage_times = has_val ? parse_bool(val) : true;
+        else if (a == "encoder_mode") { if (!need(tmp)) return false; fl.encoder_mode = atoi(tmp.c_str()); }
         else if (a == "check_inputs") fl.check_inputs = has_val ? parse_bool(val) : true;
         else if (a == "show_scene" || a == "visualize_hypotheses" || a == "noshow_scene" || a == "novisualize_hypotheses") {}
         else if (a == "help" || a == "h") fl.help = true;
@@ -319,6 +320,7 @@ bool parse_flags(int argc, char** argv, Flags& fl, std::string& err) {
 
 const char* kUsage =
     "usage: HoughForest --test --detector_options_file=<options.txt> [--output_folder=<dir>] [--device=<n>] [--stage_times]\n"
+    "                   [--encoder_mode=0|1]   0: bf16 tensor-core operands (default), 1: split bf16, ~fp32 (3x encoder time)\n"
     "       `rgb_path depth_path` pairs are read from stdin until EOF; results go to <dir><stem>_res.txt / _res.png\n"
     "       HoughForest --check_inputs   decode the stdin pairs only and print size + FNV-1a checksum of each frame\n";
 
@@ -435,6 +437,14 @@ int main(int argc, char** argv) {
                 std::cerr << "HoughForest: cannot create the detector: " << hf6d_last_error(nullptr) << std::endl;
                 return 3;
             }
+            if (fl.encoder_mode && hf6d_set_encoder_mode(ctx, fl.encoder_mode)) {
+                std::cerr << "HoughForest: " << hf6d_last_error(ctx) << std::endl;
+                return 3;
+            }
+            // the reference refines every hypothesis with ICP and ranks by MeshUtils' final score before it writes _res.txt
+            // (HFTest.cpp:927-934, :1261-1311); this path ends where MeshUtils begins, and says so
+            std::cout << "Note: poses are the pre-ICP Hough hypotheses (ICP refinement and hypothesis scoring are not part of this "
+                         "library); ranked by pose_score_coeff * pose score + location_score_coeff * location score" << std::endl;
         }
         to_bgr8(rgb_img, bgr);
         if (!to_depth16(depth_img, depth, err)) {
@@ -454,13 +464,13 @@ int main(int argc, char** argv) {
         int32_t counts[2] = {0, 0};
         hf6d_fetch(ctx, 0, HF6D_BUF_COUNTS, counts, sizeof counts);
         std::cout << "Number of patches: " << counts[0] << std::endl;  // HFTest.cpp:427
+        std::vector<hf6d_centre_list> centre_lists((size_t)forest.K);
+        hf6d_fetch(ctx, 0, HF6D_BUF_CENTRES, centre_lists.data(), centre_lists.size() * sizeof(hf6d_centre_list));
         for (int k = 0; k < forest.K; ++k) {
             if (!objects[k].should_detect) continue;
-            int centres = 0, last_cx = -1, last_cy = -1;
-            for (int i = 0; i < n; ++i)
-                if (hyp[i].cls == k && (hyp[i].cx != last_cx || hyp[i].cy != last_cy)) { ++centres; last_cx = hyp[i].cx; last_cy = hyp[i].cy; }
             std::cout << "Generating Hypotheses for class: " << objects[k].name << std::endl;  // HFTest.cpp:697
-            std::cout << "max locations: " << centres << std::endl;                             // HFTest.cpp:712
+            // max_loc_h = min(max_location_hypotheses, number of centre maxima), HFTest.cpp:710-712
+            std::cout << "max locations: " << centre_lists[k].n << std::endl;
         }
         std::cout << "Total execution time: " << secs << "sec" << std::endl;  // HFTest.cpp:986
         if (fl.stage_times) {

@@ -62,6 +62,7 @@ struct HostForest {
     std::vector<int16_t> yaw, pitch, roll;  // integer-degree bins (HFTest.cpp:779-780, :863), saturated to +-30000
     std::vector<int32_t> vgroup;            // [votes] vote -> its group
     std::vector<int32_t> leaf_vbeg, leaf_vcnt;  // [L] all gated votes of a leaf are contiguous: first vote, count
+    std::vector<float> g_ozmin, g_ozmax;        // [groups] smallest / largest oz of the group's votes (z-histogram shortcut)
     int64_t n_internal = 0;
 };
 
@@ -278,6 +279,21 @@ inline bool load_forest(const std::string& dir, HostForest& hf, std::string& err
                 hf.recs.push_back(r);
             }
         }
+    }
+    hf.g_ozmin.resize(hf.groups.size());
+    hf.g_ozmax.resize(hf.groups.size());
+    for (size_t gi = 0; gi < hf.groups.size(); ++gi) {
+        const VoteGroup& vg = hf.groups[gi];
+        float lo = INFINITY, hi = -INFINITY;
+        bool ordered = true;  // a NaN offset compares false everywhere: such a group never takes the shortcut
+        for (int q = 0; q < vg.vcnt; ++q) {
+            const float z = hf.oz[(size_t)vg.vbeg + q];
+            if (!(z == z)) ordered = false;
+            lo = z < lo ? z : lo;
+            hi = z > hi ? z : hi;
+        }
+        hf.g_ozmin[gi] = ordered ? lo : INFINITY;
+        hf.g_ozmax[gi] = ordered ? hi : -INFINITY;
     }
     if (hf.nodes.empty()) hf.nodes.push_back(PackedNode{0, 0.f, -1, -1});  // keep device arrays non-empty
     if (hf.recs.empty()) { PackedRecord r; memset(&r, 0, sizeof r); hf.recs.push_back(r); }

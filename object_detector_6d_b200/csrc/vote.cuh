@@ -41,6 +41,7 @@ __device__ __forceinline__ void project(const FrameGeom& g, float x, float y, fl
 }
 
 constexpr int VOTE_THREADS = 256;
+constexpr int TABLE_THREADS = 256;  // the kernels that turn (slot, group) counters into yaw/pitch and roll votes
 constexpr int VOTE_WARPS = VOTE_THREADS / 32;
 
 // Per-warp staging of one batch of 32 (patch, tree) items: inclusive prefix of their vote counts and what a vote needs
@@ -65,10 +66,28 @@ struct LeafTables {
     int world;
 };
 
+// The vote stream: one 8-byte record per cast vote, {vote index, (u + 64) | (v + 64) << 13 | class << 26}, written by the
+// vote kernel in the order it enumerates the votes (a warp reserves the exact space of its batch with one atomic, its lanes
+// write consecutive records) and read back by the pose stage (window_stream_kernel), which therefore does not enumerate,
+// look up and project the votes a second time.  u, v are clamped to [-64, 8127]: a vote outside that range cannot lie in any
+// centre window (windows are at most 128 wide and centred inside the image; frames wider than 8000 px use the old path).
+constexpr int STREAM_BIAS = 64, STREAM_COORD_MAX = 8191;
+struct VoteStream {
+    uint2* rec;   // nullptr: no stream
+    int* n;       // records reserved so far (zeroed before the vote kernel)
+    int cap;
+};
+__device__ __forceinline__ unsigned stream_pack(int u, int v, int cls) {
+    const unsigned uu = (unsigned)min(max(u + STREAM_BIAS, 0), STREAM_COORD_MAX);
+    const unsigned vv = (unsigned)min(max(v + STREAM_BIAS, 0), STREAM_COORD_MAX);
+    return uu | (vv << 13) | ((unsigned)cls << 26);
+}
+
+// body(valid, vote index, tx, ty, tz, pos): pos = position of the vote in the stream (stream_n given) or -1.
 template <class Body>
 __device__ __forceinline__ void for_each_cast_vote(const DevForest& f, const FrameGeom& g, const int* __restrict__ locs,
                                                    const uint16_t* __restrict__ depth, const LeafTables& lt,
-                                                   int n_items, WarpItems& wi, int* next_batch, Body&& body) {
+                                                   int n_items, WarpItems& wi, int* next_batch, int* stream_n, Body&& body) {
     const int lane = threadIdx.x & 31;
     const int warp0 = (blockIdx.x * VOTE_WARPS + (threadIdx.x >> 5)) * 32;
     const int stride = gridDim.x * VOTE_THREADS;
@@ -105,6 +124,11 @@ __device__ __forceinline__ void for_each_cast_vote(const DevForest& f, const Fra
             if (lane >= o) incl += n;
         }
         const int total = __shfl_sync(0xffffffffu, incl, 31);
+        int sbase = -1;
+        if (stream_n && total > 0) {
+            if (lane == 0) sbase = atomicAdd(stream_n, total);
+            sbase = __shfl_sync(0xffffffffu, sbase, 0);
+        }
         __syncwarp();  // the previous batch's readers are done
         wi.incl[lane] = incl;
         wi.geo[lane] = make_float4(tx, ty, tz, __int_as_float(vbeg - (incl - vcnt)));
@@ -119,7 +143,7 @@ __device__ __forceinline__ void for_each_cast_vote(const DevForest& f, const Fra
                     if (wi.incl[lo + s - 1] <= j) lo += s;
             }
             const float4 ge = wi.geo[lo];
-            body(valid, __float_as_int(ge.w) + j, ge.x, ge.y, ge.z);
+            body(valid, __float_as_int(ge.w) + j, ge.x, ge.y, ge.z, sbase < 0 ? -1 : sbase + j);
         }
     }
 }
@@ -127,7 +151,7 @@ __device__ __forceinline__ void for_each_cast_vote(const DevForest& f, const Fra
 __global__ void __launch_bounds__(VOTE_THREADS)
 vote_kernel(DevForest f, FrameGeom g, const __grid_constant__ ObjectSwitches sw, const int* __restrict__ locs,
             const uint16_t* __restrict__ depth, const int* __restrict__ leaf_ord, const int* __restrict__ counts,
-            unsigned long long* __restrict__ maps) {
+            unsigned long long* __restrict__ maps, VoteStream stream) {
     LeafTables lt;  // votes are cast for this rank's own trees only: the local table (foreign entries are -1)
     lt.base[0] = leaf_ord;
     lt.world = 1;
@@ -136,17 +160,19 @@ vote_kernel(DevForest f, FrameGeom g, const __grid_constant__ ObjectSwitches sw,
     if (threadIdx.x < HF6D_MAX_CLASSES) s_detect[threadIdx.x] = sw.should_detect[threadIdx.x];
     __syncthreads();
     const size_t HW = (size_t)g.H * g.W;
-    for_each_cast_vote(f, g, locs, depth, lt, counts[1] * f.T, s_items[threadIdx.x >> 5], nullptr,
-                       [&](bool valid, int vi, float tx, float ty, float tz) {
+    for_each_cast_vote(f, g, locs, depth, lt, counts[1] * f.T, s_items[threadIdx.x >> 5], nullptr, stream.rec ? stream.n : nullptr,
+                       [&](bool valid, int vi, float tx, float ty, float tz, int pos) {
                            if (!valid) return;
                            const float4 v = __ldg(f.vote4 + vi);
                            const unsigned meta = __float_as_uint(v.w);
                            const int cls = (int)(meta & 31u);
-                           if (!s_detect[cls]) return;
-                           int uu, vv;
-                           project(g, __fadd_rn(v.x, tx), __fadd_rn(v.y, ty), __fadd_rn(v.z, tz), uu, vv);
-                           if (uu >= 0 && uu < g.W && vv >= 0 && vv < g.H)
-                               atomicAdd(maps + (size_t)cls * HW + (size_t)vv * g.W + uu, (unsigned long long)(meta >> 5));
+                           int uu = -STREAM_BIAS, vv = -STREAM_BIAS;  // a class that is not detected: a record no window holds
+                           if (s_detect[cls]) {
+                               project(g, __fadd_rn(v.x, tx), __fadd_rn(v.y, ty), __fadd_rn(v.z, tz), uu, vv);
+                               if (uu >= 0 && uu < g.W && vv >= 0 && vv < g.H)
+                                   atomicAdd(maps + (size_t)cls * HW + (size_t)vv * g.W + uu, (unsigned long long)(meta >> 5));
+                           }
+                           if (pos >= 0 && pos < stream.cap) stream.rec[pos] = make_uint2((unsigned)vi, stream_pack(uu, vv, cls));
                        });
 }
 
@@ -261,8 +287,8 @@ window_entries_kernel(DevForest f, FrameGeom g, const __grid_constant__ ObjectSw
     const int lane = threadIdx.x & 31;
     int blk_base = 0, blk_used = ENTRY_BLOCK;  // warp-uniform: the block this warp is filling (none yet)
     bool overflow = false;                     // the list is full: accumulate in place from now on
-    for_each_cast_vote(f, g, locs, depth, lt, counts[1] * f.T, s_items[threadIdx.x >> 5], next_batch,
-                       [&](bool valid, int vi, float tx, float ty, float tz) {
+    for_each_cast_vote(f, g, locs, depth, lt, counts[1] * f.T, s_items[threadIdx.x >> 5], next_batch, nullptr,
+                       [&](bool valid, int vi, float tx, float ty, float tz, int) {
         unsigned mask = 0;
         int c = 0, uu = 0, vv = 0;
         if (valid) {
@@ -414,10 +440,327 @@ window_accumulate_kernel(DevForest f, const uint4* __restrict__ entries, int ent
     }
 }
 
+// ------------------------------------------------------------------------------------------------ pose pass A, fused
+// window_stream_kernel does in one launch what window_entries_kernel + window_accumulate_kernel + z_mode_kernel do in three,
+// and reads the votes from the vote stream instead of enumerating them again:
+//   * every lane takes one stream record (vote, pixel, class), looks the pixel up in the cell grid and tests the few
+//     candidate windows exactly; hits go to a per-warp ring in shared memory;
+//   * whenever the ring holds 32 entries the warp processes them together: lane i owns entry i (group lookup, the
+//     (slot, group) counter), then G lanes walk one entry's leaf votes for the z histogram (HFTest.cpp:766-775);
+//   * a trained forest's votes are coherent -- the votes of one leaf land on the same few pixels and in the same z bin --
+//     so both updates are aggregated inside the warp before they become atomics: entries with the same (group, windows)
+//     are counted once (__match_any_sync), and a G-lane walk whose votes all fall into one z bin adds them in one atomic
+//     (profiles/r02_pose_before_ncu.txt: 10 shared-memory wavefronts per atomic instruction without it);
+//   * the first increment of a (slot, group) counter appends the pair to a list: the yaw/pitch and roll passes walk that
+//     list instead of scanning the dense S x groups counter table (44 MB at configs[1]), and the roll pass, the last
+//     reader, zeroes the counters it visits, so the table is never cleared wholesale either;
+//   * the last CTA to finish runs the z mode seeking (HFTest.cpp:803-812) for every slot.
+struct WarpRing {
+    unsigned vi[64], cm[64];
+    float zz[64];
+};
+struct PairList {
+    uint2* pairs;   // (slot, group), each (slot, group) at most once per frame
+    int* n;
+    int cap;
+};
+
+// z mode of one slot by one warp: NMS (1 wide, z_nms tall) over the 300-bin histogram, highest score, earliest on ties.
+__device__ __forceinline__ void z_mode_warp(const unsigned long long* __restrict__ zacc_s, int z_nms, float* zf /*[Z_BINS] smem*/,
+                                            uint8_t* active_s, float* mode_z_s) {
+    const int lane = threadIdx.x & 31;
+    for (int i = lane; i < HF6D_Z_BINS; i += 32) zf[i] = (float)((double)__ldcg(zacc_s + i) / 65536.0);
+    __syncwarp();
+    unsigned long long best = 0;
+    const int n_top = HF6D_Z_BINS - 2 * z_nms + 2;  // tops 0 .. rows-2*wy+1
+    for (int top = lane; top < n_top; top += 32) {
+        int brow = top;
+        float bv = zf[top];
+        for (int r = top + 1; r < top + z_nms; ++r)
+            if (zf[r] > bv) { bv = zf[r]; brow = r; }
+        if (bv != 0.f && brow == top + z_nms / 2)
+            best = max(best, ((unsigned long long)__float_as_uint(bv) << 32) | (unsigned long long)(0xFFFFu - (unsigned)brow));
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if (lane == 0) {
+        if (best == 0) *active_s = 0;
+        else *mode_z_s = __fmul_rn((float)(0xFFFF - (int)(best & 0xFFFFu)), 0.01f);
+    }
+    __syncwarp();
+}
+
+constexpr int WS_ROWS = 4;  // stream rows (of 32 records) a warp grabs at a time
+template <int G>
+__global__ void __launch_bounds__(WA_THREADS)
+window_stream_kernel(DevForest f, FrameGeom g, const __grid_constant__ ObjectSwitches sw, VoteStream stream,
+                     const uint16_t* __restrict__ depth, CentreTable ct, int half_win, int n_groups,
+                     const __grid_constant__ ZSlotTable zt, unsigned* __restrict__ cnt, PairList pl,
+                     unsigned long long* __restrict__ zacc, int* __restrict__ next_chunk, int* __restrict__ done,
+                     int z_nms, uint8_t* __restrict__ active, float* __restrict__ mode_z) {
+    __shared__ SharedCentres sc;
+    __shared__ WarpRing s_ring[WA_THREADS / 32];
+    __shared__ unsigned s_classes;
+    __shared__ int s_last;
+    extern __shared__ __align__(16) uint8_t ws_smem[];
+    const int nz = zt.zoff[f.K];
+    unsigned* s_z = reinterpret_cast<unsigned*>(ws_smem);                                       // [nz][Z_BINS]
+    uint16_t* s_cells = reinterpret_cast<uint16_t*>(ws_smem + (((size_t)nz * HF6D_Z_BINS * 4 + 15) & ~(size_t)15));  // [K][gy][gx]
+    load_centres(sc, ct, f.K);
+    const CellGrid cg = make_cell_grid(g.W, g.H, half_win);
+    const int cells_per_class = cg.gx * cg.gy;
+    const int S = f.K * HF6D_MAX_CENTRES;
+    for (int i = threadIdx.x; i < nz * HF6D_Z_BINS; i += WA_THREADS) s_z[i] = 0u;
+    for (int i = threadIdx.x; i < f.K * cells_per_class; i += WA_THREADS) s_cells[i] = 0;
+    if (threadIdx.x == 0) s_classes = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < S; i += WA_THREADS) {
+        const int c = i / HF6D_MAX_CENTRES, k = i % HF6D_MAX_CENTRES;
+        if (k >= sc.ctr[c].n || !sc.act[c][k] || !sw.should_detect[c]) continue;
+        atomicOr(&s_classes, 1u << c);
+        const int x_lo = sc.ctr[c].c[k].x - half_win, y_lo = sc.ctr[c].c[k].y - half_win;
+        const int cx0 = max(0, (x_lo - cg.x0) >> cg.shift), cx1 = min(cg.gx - 1, (x_lo + 2 * half_win - 1 - cg.x0) >> cg.shift);
+        const int cy0 = max(0, (y_lo - cg.y0) >> cg.shift), cy1 = min(cg.gy - 1, (y_lo + 2 * half_win - 1 - cg.y0) >> cg.shift);
+        for (int cyi = cy0; cyi <= cy1; ++cyi)
+            for (int cxi = cx0; cxi <= cx1; ++cxi) {
+                const int idx = c * cells_per_class + cyi * cg.gx + cxi;
+                atomicOr(reinterpret_cast<unsigned*>(s_cells) + (idx >> 1), (1u << k) << ((idx & 1) * 16));
+            }
+    }
+    __syncthreads();
+    const unsigned classes = s_classes;
+    const int lane = threadIdx.x & 31;
+    WarpRing& ring = s_ring[threadIdx.x >> 5];
+    const int n = min(*stream.n, stream.cap);
+
+    // One warp-wide, pre-aggregated update of the shared z histograms: lanes with `on` add `add` to bin `idx` (a position in
+    // s_z); lanes that hit the same bin are summed in registers and their leader issues one atomic (a trained forest sends
+    // every entry of an object's window into the same one or two bins: without this a warp-wide atomic serialises 32-fold).
+    auto add_z = [&](bool on, int idx, unsigned add, int slot_global, int zb) {
+        const unsigned peers = __match_any_sync(0xffffffffu, on ? (unsigned)idx : (0x80000000u | (unsigned)lane));
+        const unsigned sum = __reduce_add_sync(peers, on ? add : 0u);
+        if (on && lane == __ffs(peers) - 1) {
+            const unsigned old = atomicAdd(s_z + idx, sum);
+            if (old + sum < old) atomicAdd(zacc + (size_t)slot_global * HF6D_Z_BINS + zb, 1ull << 32);
+        }
+    };
+    // bin of one vote of a leaf for a window pixel at depth zj (HFTest.cpp:770-775), unclamped / -1 outside the histogram
+    auto z_bin_raw = [&](float oz, float zj) { return f2i_x86(div_const<1, 100>(__fadd_rn(oz, zj))); };  // integer part only
+    auto z_bin = [&](float oz, float zj) {
+        const int zb = z_bin_raw(oz, zj);
+        return (zb < 0 || zb >= HF6D_Z_BINS) ? -1 : zb;
+    };
+
+    // the ring's entries [head, head + n_e), n_e <= 32, ONE LANE PER ENTRY: counters, pair list, z histograms
+    auto process = [&](int head, int n_e) {
+        const bool have = lane < n_e;
+        unsigned cm = 0;
+        float zz = -1.f;
+        int gi = 0;
+        int4 grp = make_int4(0, 0, 0, 0);
+        float2 ozr = make_float2(0.f, 0.f);
+        if (have) {
+            const int at = (head + lane) & 63;
+            cm = ring.cm[at];
+            zz = ring.zz[at];
+            gi = __ldg(f.vgroup + (int)ring.vi[at]);
+            grp = __ldg(reinterpret_cast<const int4*>(f.groups) + gi);  // cls, w, vbeg, vcnt
+            ozr = __ldg(f.oz_range + gi);
+        }
+        // entries with the same group in the same windows (the votes of one leaf cast by one patch, typically): one update
+        const unsigned long long key = have ? (((unsigned long long)(unsigned)gi << 16) | (cm & 0xFFFFu)) : (~0ull - (unsigned)lane);
+        const unsigned peers = __match_any_sync(0xffffffffu, key);
+        if (have && lane == __ffs(peers) - 1) {
+            const int c = (int)(cm >> 16);
+            const unsigned mult = (unsigned)__popc(peers);
+            for (unsigned m = cm & 0xFFFFu; m; m &= m - 1) {
+                const int slot = c * HF6D_MAX_CENTRES + __ffs(m) - 1;
+                if (atomicAdd(cnt + (size_t)slot * n_groups + gi, mult) == 0u) {  // first entry of this (slot, group)
+                    const int at = atomicAdd(pl.n, 1);
+                    if (at < pl.cap) pl.pairs[at] = make_uint2((unsigned)slot, (unsigned)gi);
+                }
+            }
+        }
+        // z histograms (HFTest.cpp:766-775): every vote of the entry's leaf, with the window pixel's depth as the patch centre.
+        // The bin is monotonic in the vote's oz, so when the smallest and the largest oz of the group fall into the same bin
+        // all its votes do: such entries are finished here, a lane each, without reading a vote.
+        const int c = (int)(cm >> 16);
+        const bool wants = have && zz >= 0.f && grp.w > 0;
+        int lo = 0, hi = 1;
+        if (wants) { lo = z_bin_raw(ozr.x, zz); hi = z_bin_raw(ozr.y, zz); }
+        const bool same = wants && lo == hi && !(ozr.x > ozr.y);  // (inf, -inf) marks an unordered group: always walked
+        const bool same_in = same && lo >= 0 && lo < HF6D_Z_BINS;
+        const unsigned wins = __reduce_or_sync(0xffffffffu, same_in ? (cm & 0xFFFFu) : 0u);
+        for (unsigned m = wins; m; m &= m - 1) {  // warp-uniform loop over the window ranks any such entry lies in
+            const int k = __ffs(m) - 1;
+            const bool on = same_in && ((cm >> k) & 1u);
+            add_z(on, (zt.zoff[c] + k) * HF6D_Z_BINS + lo, (unsigned)grp.y * (unsigned)grp.w, c * HF6D_MAX_CENTRES + k, lo);
+        }
+        // The others: the whole warp walks one entry's leaf votes at a time, lane q on vote q (coalesced), the loads of WALK
+        // entries issued together so that their latency is paid once per batch and not once per entry.
+        unsigned walk = __ballot_sync(0xffffffffu, wants && !same);
+        constexpr int WALK = 8;
+        while (walk) {
+            int src[WALK];
+            float ozv[WALK][2];
+            int vn_[WALK];
+#pragma unroll
+            for (int u = 0; u < WALK; ++u) {
+                src[u] = walk ? __ffs(walk) - 1 : -1;
+                if (walk) walk &= walk - 1;
+                const int from = max(src[u], 0);
+                const int vb = __shfl_sync(0xffffffffu, grp.z, from);
+                vn_[u] = src[u] < 0 ? 0 : __shfl_sync(0xffffffffu, grp.w, from);
+                ozv[u][0] = lane < vn_[u] ? __ldg(f.oz + vb + lane) : 0.f;
+                ozv[u][1] = lane + 32 < vn_[u] ? __ldg(f.oz + vb + lane + 32) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < WALK; ++u) {
+                if (src[u] < 0) break;  // warp-uniform
+                const float zj = __shfl_sync(0xffffffffu, zz, src[u]);
+                const unsigned w = (unsigned)__shfl_sync(0xffffffffu, grp.y, src[u]), cmj = __shfl_sync(0xffffffffu, cm, src[u]);
+                const int vb = __shfl_sync(0xffffffffu, grp.z, src[u]);
+                const int cj = (int)(cmj >> 16);
+                for (int q0 = 0; q0 < vn_[u]; q0 += 32) {
+                    const int q = q0 + lane;
+                    int zb = -1;
+                    if (q < vn_[u]) zb = z_bin(q0 == 0 ? ozv[u][0] : (q0 == 32 ? ozv[u][1] : __ldg(f.oz + vb + q)), zj);
+                    const unsigned in = __ballot_sync(0xffffffffu, zb >= 0);
+                    if (!in) continue;
+                    const int zb0 = __shfl_sync(0xffffffffu, zb, __ffs(in) - 1);
+                    const bool uniform = __ballot_sync(0xffffffffu, zb >= 0 && zb != zb0) == 0u;
+                    unsigned add = w;
+                    bool mine = zb >= 0;
+                    if (uniform) {  // one atomic for the 32 votes
+                        mine = lane == __ffs(in) - 1;
+                        add = w * (unsigned)__popc(in);
+                    }
+                    if (!mine) continue;
+                    for (unsigned m = cmj & 0xFFFFu; m; m &= m - 1) {
+                        const int k = __ffs(m) - 1;
+                        const unsigned old = atomicAdd(s_z + (zt.zoff[cj] + k) * HF6D_Z_BINS + zb, add);
+                        if (old + add < old) atomicAdd(zacc + (size_t)(cj * HF6D_MAX_CENTRES + k) * HF6D_Z_BINS + zb, 1ull << 32);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    };
+
+    int head = 0, pending = 0;  // warp-uniform ring state
+    for (;;) {
+        int chunk = 0;
+        if (lane == 0) chunk = atomicAdd(next_chunk, 1);
+        chunk = __shfl_sync(0xffffffffu, chunk, 0);
+        const int base = chunk * (32 * WS_ROWS);
+        if (base >= n) break;
+        uint2 rec[WS_ROWS];
+#pragma unroll
+        for (int r = 0; r < WS_ROWS; ++r) {
+            const int i = base + r * 32 + lane;
+            rec[r] = i < n ? __ldcs(stream.rec + i) : make_uint2(0u, 0u);  // read once: streaming load
+        }
+#pragma unroll
+        for (int r = 0; r < WS_ROWS; ++r) {
+            unsigned mask = 0;
+            const int c = (int)(rec[r].y >> 26);
+            const int uu = (int)(rec[r].y & 8191u) - STREAM_BIAS, vv = (int)((rec[r].y >> 13) & 8191u) - STREAM_BIAS;
+            if (base + r * 32 + lane < n && ((classes >> c) & 1u)) {
+                const int cxi = (uu - cg.x0) >> cg.shift, cyi = (vv - cg.y0) >> cg.shift;
+                unsigned cand = 0;
+                if (cxi >= 0 && cxi < cg.gx && cyi >= 0 && cyi < cg.gy) cand = s_cells[c * cells_per_class + cyi * cg.gx + cxi];
+                while (cand) {  // exact test for the few centres whose window touches the cell
+                    const int k = __ffs(cand) - 1;
+                    cand &= cand - 1;
+                    const int ccx = sc.ctr[c].c[k].x, ccy = sc.ctr[c].c[k].y;
+                    const bool hit = vv >= ccy - half_win && vv < ccy + half_win && uu >= ccx - half_win && uu < ccx + half_win;
+                    mask |= (unsigned)hit << k;
+                }
+            }
+            const unsigned hl = __ballot_sync(0xffffffffu, mask != 0);
+            if (!hl) continue;
+            if (mask) {
+                float zz = -1.f;
+                if (vv >= 0 && vv < g.H && uu >= 0 && uu < g.W) {  // the reference reads out of bounds here
+                    const unsigned d = depth[(size_t)vv * g.W + uu];
+                    if (d != 0) zz = div_const<1000, 1>((float)d);
+                }
+                const int at = (head + pending + __popc(hl & ((1u << lane) - 1u))) & 63;
+                ring.vi[at] = rec[r].x;
+                ring.cm[at] = ((unsigned)c << 16) | mask;
+                ring.zz[at] = zz;
+            }
+            pending += __popc(hl);
+            __syncwarp();
+            if (pending >= 32) {
+                process(head, 32);
+                head = (head + 32) & 63;
+                pending -= 32;
+            }
+        }
+    }
+    if (pending) process(head, pending);
+
+    __syncthreads();
+    for (int c = 0; c < f.K; ++c) {
+        const int n_k = zt.zoff[c + 1] - zt.zoff[c];
+        for (int i = threadIdx.x; i < n_k * HF6D_Z_BINS; i += WA_THREADS) {
+            const unsigned v = s_z[zt.zoff[c] * HF6D_Z_BINS + i];
+            if (v) atomicAdd(zacc + (size_t)c * HF6D_MAX_CENTRES * HF6D_Z_BINS + i, (unsigned long long)v);
+        }
+    }
+    // the last CTA to get here has every CTA's histogram flushes behind it: z mode seeking for all slots
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(done, 1) == (int)gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    // the shared histograms' memory is free now: one 300-float scratch row per warp, as many warps as there are rows
+    const int warp = threadIdx.x >> 5, warps = min(WA_THREADS / 32, nz);
+    float* zf = reinterpret_cast<float*>(ws_smem) + warp * HF6D_Z_BINS;
+    if (warp < warps)
+        for (int s = warp; s < S; s += warps)
+            if (active[s]) z_mode_warp(zacc + (size_t)s * HF6D_Z_BINS, z_nms, zf, active + s, mode_z + s);
+}
+
+// Pass A.2 / B on the pair list: as yawpitch_from_counts_kernel / roll_from_counts_kernel below, but G lanes take one
+// listed (slot, group) pair at a time instead of scanning the dense counter table.
+template <int G>
+__global__ void __launch_bounds__(TABLE_THREADS)
+yawpitch_from_pairs_kernel(DevForest f, const unsigned* __restrict__ cnt, int n_groups, PairList pl,
+                           const uint8_t* __restrict__ active, PoseRegion reg, unsigned long long* __restrict__ ypacc) {
+    const int lane = threadIdx.x & 31, sub = lane % G;
+    const size_t yp_slot = (size_t)reg.ny * reg.np;
+    const int n = min(*pl.n, pl.cap);
+    const int stride = gridDim.x * TABLE_THREADS / G;
+    for (int e = (blockIdx.x * TABLE_THREADS + threadIdx.x) / G; e < n; e += stride) {
+        const uint2 pr = __ldg(pl.pairs + e);
+        const int s = (int)pr.x, gi = (int)pr.y;
+        if (!active[s]) continue;
+        const unsigned c_hits = __ldcg(cnt + (size_t)s * n_groups + gi);
+        const int4 grp = __ldg(reinterpret_cast<const int4*>(f.groups) + gi);
+        const unsigned long long wk = (unsigned long long)(unsigned)grp.y * c_hits;
+        unsigned long long* yps = ypacc + (size_t)s * yp_slot;
+        for (int q = sub; q < grp.w; q += G) {
+            const short4 bn = __ldg(f.bins + grp.z + q);
+            const int yaw = bn.x, pit = bn.y;
+            const int sy = yaw < 0 ? -1 : 1, sp = pit < 0 ? -1 : 1;  // copysign(1, (float)int): sign(0) = +1
+#pragma unroll
+            for (int k1 = 0; k1 < 2; ++k1)
+#pragma unroll
+                for (int k2 = 0; k2 < 2; ++k2) {
+                    const int ry = yaw - sy * k1 * 360 + 360 - reg.y0, rp = pit - sp * k2 * 360 + 360 - reg.p0;
+                    if (ry < 0 || ry >= reg.ny || rp < 0 || rp >= reg.np) continue;
+                    atomicAdd(yps + (size_t)ry * reg.np + rp, wk);
+                }
+        }
+    }
+}
+
 // Pass A.2: yaw/pitch maps from the (slot, group) entry counts: every entry re-walks all votes of its leaf
 // (HFTest.cpp:763-791), so a group adds  count * w  at each of its votes' bins (and their +-360 wrap copies).
 // A warp reads 32 consecutive counters, then G lanes take one non-zero (slot, group) pair each.
-constexpr int TABLE_THREADS = 256;
 template <int G>
 __global__ void __launch_bounds__(TABLE_THREADS)
 yawpitch_from_counts_kernel(DevForest f, const unsigned* __restrict__ cnt, int n_groups, const uint8_t* __restrict__ active,
@@ -554,6 +897,73 @@ roll_from_counts_kernel(DevForest f, const unsigned* __restrict__ cnt, int n_gro
                     if (b0 >= 0 && b0 < HF6D_POSE_BINS) atomicAdd(rs + b0, wk);
                     if (b1 >= 0 && b1 < HF6D_POSE_BINS) atomicAdd(rs + b1, wk);
                 }
+            }
+        }
+    }
+}
+
+// The roll histograms from the pair list (see window_stream_kernel): G lanes per listed (slot, group) pair.  Last reader of
+// the pair's counter: zeroes it for the next frame.
+template <int G>
+__global__ void __launch_bounds__(TABLE_THREADS)
+roll_from_pairs_kernel(DevForest f, unsigned* __restrict__ cnt, int n_groups, PairList pl, PeakTable pk, int half_box,
+                       unsigned long long* __restrict__ racc /*[S][max_peaks][POSE_BINS]*/) {
+    const int lane = threadIdx.x & 31, sub = lane % G, part = lane / G;
+    const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << (part * G));
+    const int n = min(*pl.n, pl.cap);
+    const int stride = gridDim.x * TABLE_THREADS / G;
+    for (int e = (blockIdx.x * TABLE_THREADS + threadIdx.x) / G; e < n; e += stride) {
+        const uint2 pr = __ldg(pl.pairs + e);
+        const int s = (int)pr.x, gi = (int)pr.y;
+        unsigned c_hits = 0;
+        if (sub == 0) {
+            unsigned* cp = cnt + (size_t)s * n_groups + gi;
+            c_hits = __ldcg(cp);
+            *cp = 0u;  // last reader: the table is zero again for the next frame
+        }
+        c_hits = __shfl_sync(gmask, c_hits, part * G);
+        const int np = __ldg(pk.n_peaks + s);
+        if (np == 0) continue;
+        const int4 grp = __ldg(reinterpret_cast<const int4*>(f.groups) + gi);
+        const int passes = (grp.w + G - 1) / G;
+        if (passes == 1) {
+            const bool have = sub < grp.w;
+            const short4 bn = have ? __ldg(f.bins + grp.z + sub) : make_short4(0, 0, 0, 0);
+            const int Y = (int)bn.x + 360, P0 = (int)bn.y + 360, r = bn.z;
+            const int b0 = r + 360, b1 = r < 0 ? r + 720 : r;
+            for (int p = 0; p < np; ++p) {
+                const int2 yp = __ldg(reinterpret_cast<const int2*>(pk.peak_yx) + s * pk.max_peaks + p);
+                const bool in = have && Y >= yp.x - half_box && Y < yp.x + half_box && P0 >= yp.y - half_box && P0 < yp.y + half_box;
+                const int inbox = __popc(__ballot_sync(gmask, in));
+                if (inbox == 0 || !have) continue;
+                const unsigned long long wk = (unsigned long long)(unsigned)grp.y * c_hits * (unsigned long long)inbox;
+                unsigned long long* rs = racc + ((size_t)s * pk.max_peaks + p) * HF6D_POSE_BINS;
+                if (b0 >= 0 && b0 < HF6D_POSE_BINS) atomicAdd(rs + b0, wk);
+                if (b1 >= 0 && b1 < HF6D_POSE_BINS) atomicAdd(rs + b1, wk);
+            }
+            continue;
+        }
+        for (int p = 0; p < np; ++p) {
+            const int Yp = __ldg(pk.peak_yx + (s * pk.max_peaks + p) * 2), Pp = __ldg(pk.peak_yx + (s * pk.max_peaks + p) * 2 + 1);
+            int inbox = 0;
+            for (int ps = 0; ps < passes; ++ps) {
+                const int q = ps * G + sub;
+                bool in = false;
+                if (q < grp.w) {
+                    const short4 bn = __ldg(f.bins + grp.z + q);
+                    const int Y = (int)bn.x + 360, P0 = (int)bn.y + 360;
+                    in = Y >= Yp - half_box && Y < Yp + half_box && P0 >= Pp - half_box && P0 < Pp + half_box;
+                }
+                inbox += __popc(__ballot_sync(gmask, in));
+            }
+            if (inbox == 0) continue;
+            const unsigned long long wk = (unsigned long long)(unsigned)grp.y * c_hits * (unsigned long long)inbox;
+            unsigned long long* rs = racc + ((size_t)s * pk.max_peaks + p) * HF6D_POSE_BINS;
+            for (int q = sub; q < grp.w; q += G) {
+                const int r = __ldg(f.bins + grp.z + q).z;
+                const int b0 = r + 360, b1 = r < 0 ? r + 720 : r;
+                if (b0 >= 0 && b0 < HF6D_POSE_BINS) atomicAdd(rs + b0, wk);
+                if (b1 >= 0 && b1 < HF6D_POSE_BINS) atomicAdd(rs + b1, wk);
             }
         }
     }

@@ -632,14 +632,16 @@ static void entry_push(entry_list* l, int u, int v, const ref_node* leaf) {
     l->n++;
 }
 
-/* Casts the votes of every processed patch; entries (the reference's center_leaf_map, HFTest.cpp:208-211) optional. */
-static int64_t cast_votes(const hf6d_ref_forest* f, const int32_t* leaf_ord, const int32_t* locs,
-                          const uint16_t* depth, int32_t P, const hf6d_ref_params* p, const uint8_t* should_detect,
-                          uint64_t* maps, entry_list* entries /*[K] or NULL*/) {
+/* Casts the votes of every processed patch; entries (the reference's center_leaf_map, HFTest.cpp:208-211) optional.
+ * Threads take contiguous patch ranges with their own maps and entry lists, merged in thread order, as the reference votes
+ * inside an OpenMP loop and merges per-thread maps (HFTest.cpp:601-656).  Integer sums: the result does not depend on the
+ * number of threads, and the merged entry lists are in patch order whatever it is. */
+static int64_t cast_votes_range(const hf6d_ref_forest* f, const int32_t* leaf_ord, const int32_t* locs, const uint16_t* depth,
+                                int32_t i0, int32_t i1, const hf6d_ref_params* p, const uint8_t* should_detect, uint64_t* maps,
+                                entry_list* entries /*[K] or NULL*/) {
     const int W = p->W, H = p->H, K = f->K, T = f->T;
     int64_t cast = 0;
-    if (maps) memset(maps, 0, sizeof(uint64_t) * (size_t)K * W * H);
-    for (int i = 0; i < P; ++i) {
+    for (int i = i0; i < i1; ++i) {
         const int px = locs[2 * i], py = locs[2 * i + 1];
         const uint16_t d = depth[(size_t)py * W + px]; /* HFTest.cpp:628 */
         for (int t = 0; t < T; ++t) {
@@ -665,6 +667,64 @@ static int64_t cast_votes(const hf6d_ref_forest* f, const int32_t* leaf_ord, con
     return cast;
 }
 
+static int64_t cast_votes(const hf6d_ref_forest* f, const int32_t* leaf_ord, const int32_t* locs,
+                          const uint16_t* depth, int32_t P, const hf6d_ref_params* p, const uint8_t* should_detect,
+                          uint64_t* maps, entry_list* entries /*[K] or NULL*/) {
+    const int K = f->K;
+    const size_t map_n = (size_t)K * p->W * p->H;
+    if (maps) memset(maps, 0, sizeof(uint64_t) * map_n);
+    int nt = 1;
+#ifdef _OPENMP
+    nt = omp_get_max_threads();
+#endif
+    if (nt > P / 256) nt = P / 256 > 0 ? P / 256 : 1;
+    if (nt <= 1) return cast_votes_range(f, leaf_ord, locs, depth, 0, P, p, should_detect, maps, entries);
+    uint64_t** tmaps = (uint64_t**)calloc(nt, sizeof(uint64_t*));
+    entry_list* tent = (entry_list*)calloc((size_t)nt * K, sizeof(entry_list));
+    int64_t* tcast = (int64_t*)calloc(nt, sizeof(int64_t));
+#pragma omp parallel num_threads(nt)
+    {
+        int th = 0;
+#ifdef _OPENMP
+        th = omp_get_thread_num();
+#endif
+        const int32_t i0 = (int32_t)((int64_t)P * th / nt), i1 = (int32_t)((int64_t)P * (th + 1) / nt);
+        if (maps) tmaps[th] = (uint64_t*)calloc(map_n, sizeof(uint64_t));
+        tcast[th] = cast_votes_range(f, leaf_ord, locs, depth, i0, i1, p, should_detect, maps ? tmaps[th] : NULL,
+                                     entries ? tent + (size_t)th * K : NULL);
+    }
+    int64_t cast = 0;
+    for (int th = 0; th < nt; ++th) cast += tcast[th];
+    if (maps) {
+#pragma omp parallel for schedule(static)
+        for (int64_t i = 0; i < (int64_t)map_n; ++i) {
+            uint64_t sum = 0;
+            for (int th = 0; th < nt; ++th) sum += tmaps[th][i];
+            maps[i] = sum;
+        }
+        for (int th = 0; th < nt; ++th) free(tmaps[th]);
+    }
+    if (entries)
+        for (int c = 0; c < K; ++c) {
+            int64_t total = entries[c].n;
+            for (int th = 0; th < nt; ++th) total += tent[(size_t)th * K + c].n;
+            if (total > entries[c].cap) {
+                entries[c].cap = total;
+                entries[c].e = (vote_entry*)realloc(entries[c].e, sizeof(vote_entry) * (size_t)(total > 0 ? total : 1));
+            }
+            for (int th = 0; th < nt; ++th) {  /* thread order = patch order */
+                entry_list* l = &tent[(size_t)th * K + c];
+                if (l->n) memcpy(entries[c].e + entries[c].n, l->e, sizeof(vote_entry) * (size_t)l->n);
+                entries[c].n += l->n;
+                free(l->e);
+            }
+        }
+    free(tmaps);
+    free(tent);
+    free(tcast);
+    return cast;
+}
+
 int64_t hf6d_ref_vote(const hf6d_ref_forest* f, const int32_t* leaf_ord, const int32_t* locs, const uint16_t* depth,
                       int32_t P, const hf6d_ref_params* p, const uint8_t* should_detect, uint64_t* maps) {
     return cast_votes(f, leaf_ord, locs, depth, P, p, should_detect, maps, NULL);
@@ -681,23 +741,39 @@ static inline int reflect101(int i, int n) {
 }
 
 void hf6d_ref_blur(const uint64_t* acc, int32_t rows, int32_t cols, int32_t kx, int32_t ky, float* out) {
-    /* C9.  Anchor = kernel centre (k/2), BORDER_REFLECT_101 (cv::blur defaults). */
+    /* C9.  Anchor = kernel centre (k/2), BORDER_REFLECT_101 (cv::blur defaults).  Window sums as running sums (what
+     * cv::blur's RowSum / ColumnSum do); the sums are integers, so they equal the plain k-term sums exactly. */
     const double scale = 1.0 / (double)(kx * ky);
     uint64_t* tmp = (uint64_t*)malloc(sizeof(uint64_t) * (size_t)rows * cols);
 #pragma omp parallel for schedule(static)
-    for (int r = 0; r < rows; ++r)
+    for (int r = 0; r < rows; ++r) {
+        const uint64_t* a = acc + (size_t)r * cols;
+        uint64_t s = 0;
+        for (int k = 0; k < kx; ++k) s += a[reflect101(-(kx / 2) + k, cols)];
         for (int c = 0; c < cols; ++c) {
-            uint64_t s = 0;
-            for (int k = 0; k < kx; ++k) s += acc[(size_t)r * cols + reflect101(c - kx / 2 + k, cols)];
             tmp[(size_t)r * cols + c] = s;
+            s += a[reflect101(c + 1 - kx / 2 + kx - 1, cols)];
+            s -= a[reflect101(c - kx / 2, cols)];
         }
+    }
 #pragma omp parallel for schedule(static)
-    for (int r = 0; r < rows; ++r)
-        for (int c = 0; c < cols; ++c) {
-            uint64_t s = 0;
-            for (int k = 0; k < ky; ++k) s += tmp[(size_t)reflect101(r - ky / 2 + k, rows) * cols + c];
-            out[(size_t)r * cols + c] = (float)(((double)s / 65536.0) * scale);
+    for (int c0 = 0; c0 < cols; c0 += 64) { /* a strip of columns per task: rows are walked contiguously */
+        const int c1 = c0 + 64 < cols ? c0 + 64 : cols;
+        uint64_t s[64];
+        for (int c = c0; c < c1; ++c) {
+            s[c - c0] = 0;
+            for (int k = 0; k < ky; ++k) s[c - c0] += tmp[(size_t)reflect101(-(ky / 2) + k, rows) * cols + c];
         }
+        for (int r = 0; r < rows; ++r) {
+            const uint64_t* add = tmp + (size_t)reflect101(r + 1 - ky / 2 + ky - 1, rows) * cols;
+            const uint64_t* sub = tmp + (size_t)reflect101(r - ky / 2, rows) * cols;
+            for (int c = c0; c < c1; ++c) {
+                out[(size_t)r * cols + c] = (float)(((double)s[c - c0] / 65536.0) * scale);
+                s[c - c0] += add[c];
+                s[c - c0] -= sub[c];
+            }
+        }
+    }
     free(tmp);
 }
 
@@ -720,29 +796,37 @@ static nms_hit* nms_run(const float* in, int rows, int cols, int wx, int wy, int
     *count = 0;
     if (cols - wx + 1 <= 0 || rows - wy + 1 <= 0) return NULL;
     const int ncol = cols - wx + 1;
+    /* pass 1: position of the first maximum of every horizontal window, by a monotonic queue like the reference's deque
+     * (HFTest.cpp:232-243: an element is dropped from the back only by a strictly larger one, so the front is the
+     * leftmost maximum) */
     int32_t* argx = (int32_t*)malloc(sizeof(int32_t) * (size_t)rows * ncol);
-    for (int i = 0; i < rows; ++i)
-        for (int j = 0; j < ncol; ++j) {
-            int best = j;
-            float bv = in[(size_t)i * cols + j];
-            for (int k = 1; k < wx; ++k) {
-                float v = in[(size_t)i * cols + j + k];
-                if (v > bv) { bv = v; best = j + k; }
-            }
-            argx[(size_t)i * ncol + j] = best;
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < rows; ++i) {
+        int32_t* q = (int32_t*)malloc(sizeof(int32_t) * (size_t)cols);
+        int qh = 0, qt = 0;
+        const float* row = in + (size_t)i * cols;
+        for (int j = 0; j < cols; ++j) {
+            if (qt > qh && q[qh] == j - wx) ++qh;
+            while (qt > qh && row[q[qt - 1]] < row[j]) --qt;
+            q[qt++] = j;
+            if (j >= wx - 1) argx[(size_t)i * ncol + j - wx + 1] = q[qh];
         }
+        free(q);
+    }
     int cap = 256, n = 0;
     nms_hit* hits = (nms_hit*)malloc(sizeof(nms_hit) * cap);
-    const int last_i = rows - wy; /* inclusive */
-    for (int j = 0; j < ncol; ++j)
-        for (int i = wy - 1; i <= last_i; ++i) {
-            const int top = i - wy + 1;
-            int brow = top;
-            float bv = in[(size_t)top * cols + argx[(size_t)top * ncol + j]];
-            for (int r = top + 1; r <= i; ++r) {
-                float v = in[(size_t)r * cols + argx[(size_t)r * ncol + j]];
-                if (v > bv) { bv = v; brow = r; }
-            }
+    const int last_i = rows - wy; /* inclusive: the reference's vertical pass stops here (HFTest.cpp:247) */
+    int32_t* q = (int32_t*)malloc(sizeof(int32_t) * (size_t)rows);
+    for (int j = 0; j < ncol; ++j) {
+        int qh = 0, qt = 0; /* rows of the column's window, values in[r][argx[r][j]]: the front is the topmost maximum */
+        for (int i = 0; i <= last_i; ++i) {
+            const float v = in[(size_t)i * cols + argx[(size_t)i * ncol + j]];
+            if (qt > qh && q[qh] == i - wy) ++qh;
+            while (qt > qh && in[(size_t)q[qt - 1] * cols + argx[(size_t)q[qt - 1] * ncol + j]] < v) --qt;
+            q[qt++] = i;
+            if (i < wy - 1) continue;
+            const int top = i - wy + 1, brow = q[qh];
+            const float bv = in[(size_t)brow * cols + argx[(size_t)brow * ncol + j]];
             const int bcol = argx[(size_t)brow * ncol + j];
             const int ccx = j + wx / 2, ccy = top + wy / 2;
             if (bv != 0 && brow == ccy && bcol == ccx) {
@@ -751,6 +835,8 @@ static nms_hit* nms_run(const float* in, int rows, int cols, int wx, int wy, int
                 ++n;
             }
         }
+    }
+    free(q);
     free(argx);
     qsort(hits, n, sizeof(nms_hit), nms_cmp);
     *count = n;
@@ -787,8 +873,38 @@ static void pose_from_tuple(const hf6d_ref_params* p, int cx, int cy, float z, i
 
 typedef struct { int32_t Y, Pp; const ref_node* leaf; } roll_entry;
 
+/* The reference's center_leaf_map is a hash map from a pixel to the leaves that voted for it (HFTest.cpp:208-211), read
+ * back pixel by pixel over a centre's window (:757-762).  Here: the entries of one class sorted by pixel (stable counting
+ * sort, so a pixel keeps its insertion order) over the image plus a margin of half a window -- votes may land outside the
+ * image and still inside a window. */
+typedef struct {
+    int32_t x0, y0, gw, gh; /* pixel of cell (0,0), grid size */
+    int64_t* start;         /* [gw*gh + 1] */
+    vote_entry* sorted;
+} entry_index;
+
+static void entry_index_build(entry_index* ix, const entry_list* l, int W, int H, int half) {
+    ix->x0 = -half; ix->y0 = -half; ix->gw = W + 2 * half; ix->gh = H + 2 * half;
+    const int64_t cells = (int64_t)ix->gw * ix->gh;
+    ix->start = (int64_t*)calloc((size_t)cells + 1, sizeof(int64_t));
+    ix->sorted = (vote_entry*)malloc(sizeof(vote_entry) * (size_t)(l->n > 0 ? l->n : 1));
+    for (int64_t e = 0; e < l->n; ++e) {
+        const int64_t cx = (int64_t)l->e[e].u - ix->x0, cy = (int64_t)l->e[e].v - ix->y0;
+        if (cx >= 0 && cx < ix->gw && cy >= 0 && cy < ix->gh) ix->start[cy * ix->gw + cx + 1]++;
+    }
+    for (int64_t i = 0; i < cells; ++i) ix->start[i + 1] += ix->start[i];
+    int64_t* fill = (int64_t*)malloc(sizeof(int64_t) * (size_t)cells);
+    memcpy(fill, ix->start, sizeof(int64_t) * (size_t)cells);
+    for (int64_t e = 0; e < l->n; ++e) {
+        const int64_t cx = (int64_t)l->e[e].u - ix->x0, cy = (int64_t)l->e[e].v - ix->y0;
+        if (cx >= 0 && cx < ix->gw && cy >= 0 && cy < ix->gh) ix->sorted[fill[cy * ix->gw + cx]++] = l->e[e];
+    }
+    free(fill);
+}
+static void entry_index_free(entry_index* ix) { free(ix->start); free(ix->sorted); }
+
 static int hypotheses_for_centre(const hf6d_ref_params* p, int c, const uint16_t* depth,
-                                 const entry_list* entries, int ctr_x, int ctr_y, float loc_score,
+                                 const entry_index* ix, int ctr_x, int ctr_y, float loc_score,
                                  hf6d_ref_hypothesis* out, int cap) {
     const int W = p->W, H = p->H;
     const int half = p->centers_nms_wsize / 2;
@@ -802,10 +918,12 @@ static int hypotheses_for_centre(const hf6d_ref_params* p, int c, const uint16_t
     roll_entry* rl = NULL;
     int64_t rn = 0, rcap = 0;
 
-    for (int64_t e = 0; e < entries->n; ++e) {
-        const int col = entries->e[e].u, row = entries->e[e].v;
-        if (row < ctr_y - half || row >= ctr_y + half || col < ctr_x - half || col >= ctr_x + half) continue;
-        const ref_node* leaf = entries->e[e].leaf;
+    for (int row = ctr_y - half; row < ctr_y + half; ++row)
+      for (int col = ctr_x - half; col < ctr_x + half; ++col) { /* HFTest.cpp:757-762 */
+        const int64_t gx = (int64_t)col - ix->x0, gy = (int64_t)row - ix->y0;
+        if (gx < 0 || gx >= ix->gw || gy < 0 || gy >= ix->gh) continue;
+      for (int64_t e = ix->start[gy * ix->gw + gx]; e < ix->start[gy * ix->gw + gx + 1]; ++e) {
+        const ref_node* leaf = ix->sorted[e].leaf;
         const uint32_t w = qweight(leaf->class_prob[c]);
         const int inside = row >= 0 && row < H && col >= 0 && col < W; /* reference reads out of bounds: skip */
         const uint16_t dpix = inside ? depth[(size_t)row * W + col] : 0;
@@ -837,7 +955,8 @@ static int hypotheses_for_centre(const hf6d_ref_params* p, int c, const uint16_t
                     }
                 }
         }
-    }
+      }
+      }
 
     /* mode of z: NMS (1 wide, 20 tall) on the 300x1 histogram, HFTest.cpp:803-812 */
     float zf[HF6D_REF_Z_BINS];
@@ -931,6 +1050,8 @@ int32_t hf6d_ref_hypotheses(const hf6d_ref_forest* f, const int32_t* leaf_ord, c
     for (int c = 0; c < K; ++c) {
         if (should_detect && !should_detect[c]) continue;
         hf6d_ref_blur(M + (size_t)c * W * H, H, W, p->centers_blur_size, p->centers_blur_size, blurred);
+        entry_index ix;
+        entry_index_build(&ix, &entries[c], W, H, p->centers_nms_wsize / 2 + 1);
         int nc = 0;
         nms_hit* ch = nms_run(blurred, H, W, p->centers_nms_wsize, p->centers_nms_wsize, &nc);
         int max_loc = max_location_hypotheses ? max_location_hypotheses[c] : 12;
@@ -942,7 +1063,7 @@ int32_t hf6d_ref_hypotheses(const hf6d_ref_forest* f, const int32_t* leaf_ord, c
 #pragma omp parallel for schedule(dynamic)
         for (int k = 0; k < max_loc; ++k) {
             if (ch[k].score / ch[0].score < p->min_location_score_ratio) continue; /* HFTest.cpp:726 */
-            counts[k] = hypotheses_for_centre(p, c, depth, &entries[c], ch[k].x, ch[k].y, ch[k].score,
+            counts[k] = hypotheses_for_centre(p, c, depth, &ix, ch[k].x, ch[k].y, ch[k].score,
                                               tmp + (size_t)k * 32, 32);
             if (counts[k] > 32) counts[k] = 32;
         }
@@ -954,6 +1075,7 @@ int32_t hf6d_ref_hypotheses(const hf6d_ref_forest* f, const int32_t* leaf_ord, c
         free(tmp);
         free(counts);
         free(ch);
+        entry_index_free(&ix);
     }
     free(blurred);
     free(maps);

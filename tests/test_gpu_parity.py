@@ -61,10 +61,13 @@ def test_scan_bitexact(case, full_run):
     assert np.array_equal(full_run["locs"], locs)
 
 
+@pytest.mark.parametrize("kernel", ["tiled", "direct"])
 @pytest.mark.parametrize("fill_random", [0, 1])
-def test_gather_normalise_bitexact(case, fill_random):
-    """uint8 CHW patches: software texture filter + sequential mean / variance + NaN->0 quantisation."""
+def test_gather_normalise_bitexact(case, fill_random, kernel, monkeypatch):
+    """uint8 CHW patches: software texture filter + sequential mean / variance + NaN->0 quantisation.  Both gather kernels:
+    the shared-memory staged tiles (default) and the per-tap global loads (HF6D_GATHER=direct, also every tile's fallback)."""
     import ctypes as C
+    monkeypatch.setenv("HF6D_GATHER", kernel)
     from object_detector_6d_b200 import api
     from oracle import oracle as O
     p = O.Params()
@@ -311,18 +314,48 @@ def test_software_filter_equals_the_texture_unit(case):
     assert frac < 1e-3
 
 
-@pytest.mark.parametrize("cap", [0, 777])
-def test_window_entry_list_overflow_is_exact(case, full_run, cap, monkeypatch):
-    """The pose stage lists window entries in a fixed-capacity buffer; entries that do not fit are accumulated in place.
-    Forcing a tiny capacity must not change a single bit of the result."""
+@pytest.mark.parametrize("cap", [None, 0, 777])
+def test_enumeration_path_of_the_pose_stage_is_exact(case, full_run, cap, monkeypatch):
+    """The pose stage has two implementations of its first pass: reading the vote stream the vote kernel wrote (default) and
+    enumerating the votes again from the leaf table (sharded contexts, forests beyond the stream budget; HF6D_POSE_STREAM=0
+    forces it).  The enumeration path lists window entries in a fixed-capacity buffer and accumulates in place what does not
+    fit.  Neither the path nor the capacity may change a single bit of the result."""
     from object_detector_6d_b200 import api
-    monkeypatch.setenv("HF6D_ENTRY_CAP", str(cap))
+    monkeypatch.setenv("HF6D_POSE_STREAM", "0")
+    if cap is not None:
+        monkeypatch.setenv("HF6D_ENTRY_CAP", str(cap))
     det = api.Detector(case["forest_dir"], case["weights"], to_api_params(case["params"]), device=0, n_slots=1)
     try:
         hyp = det.detect(case["bgr"], case["depth"])
     finally:
         det.close()
     _same_hyps(hyp, full_run["hyp"])
+
+
+def test_pose_rerun_and_replaced_leaf_table(case, full_run):
+    """Stage-isolated runs around the vote stream: POSE alone twice (the stream and the zeroed counters are reused), then a
+    leaf table injected after voting (the stream no longer describes the slot: the enumeration path must take over)."""
+    from object_detector_6d_b200 import api
+    from oracle import oracle as O
+    det = case["det"]
+    det.upload(1, case["bgr"], case["depth"])
+    det.run(1)
+    for _ in range(2):
+        det.run(1, api.STAGE_CENTRES, api.STAGE_POSE)
+        _same_hyps(det.collect(1), full_run["hyp"])
+    # another leaf table: tree 0's leaves of every patch shifted by one patch
+    leaf = full_run["leaf"].copy()
+    leaf[1:, 0] = full_run["leaf"][:-1, 0]
+    det.inject(api.BUF_LEAF_ORD, leaf, slot=1)
+    det.run(1, api.STAGE_VOTE, api.STAGE_CENTRES)
+    det.inject(api.BUF_LEAF_ORD, leaf, slot=1)  # same table again, but injected AFTER the vote stage
+    det.run(1, api.STAGE_POSE, api.STAGE_POSE)
+    hyp = det.collect(1)
+    Pp = full_run["counts"][1]
+    ref = O.hypotheses(case["forest"], leaf, full_run["locs"][:Pp], case["depth"], case["params"])
+    _same_hyps(hyp, ref)
+    det.run(1, api.STAGE_VOTE, api.STAGE_POSE)  # and the stream path on the same table
+    _same_hyps(det.collect(1), ref)
 
 
 def test_class_shards_concatenate_to_the_full_list(case, full_run):
