@@ -411,8 +411,11 @@ def run_cuda(args, rank, world, local_rank):
         det1 = api.Detector(forest_dir, wpath, p, device=local_rank, n_slots=1)
         det1.set_encoder_mode(args.encoder_mode)
         stage_ms1, enc_ms1 = serial_pass(det1)
-        det1.set_encoder_mode(1 - args.encoder_mode)  # the other encoder mode on the latency context, for the record
-        _, enc_ms_other = serial_pass(det1)
+        enc_ms_other = {}
+        for m in (0, 1, 2):  # the other encoder modes on the latency context, for the record
+            if m != args.encoder_mode:
+                det1.set_encoder_mode(m)
+                enc_ms_other[("bf16", "split_bf16", "fp16")[m]] = [float(x) for x in serial_pass(det1)[1]]
         det1.bind_frame(0, None, None)
         det1.close()
         # patches and votes per frame: exact, from the scan / leaf tables of every distinct frame
@@ -556,8 +559,8 @@ def run_cuda(args, rank, world, local_rank):
                 "parallelism": f"frames x{world}" if world > 1 else "1 GPU", "frames_in_flight": n_slots,
                 "patches_per_frame": Pp, "votes_cast_per_frame": votes_mean,
                 "encoder_mode": {"mode": args.encoder_mode,
-                                 "name": "bf16 operands" if args.encoder_mode == 0 else "split bf16 (hi + lo operands, ~fp32)",
-                                 "other_mode_encoder_layer_ms": [float(x) for x in enc_ms_other],
+                                 "name": ("bf16 operands", "split bf16 (hi + lo operands, ~fp32)", "fp16 operands")[args.encoder_mode],
+                                 "other_modes_encoder_layer_ms": enc_ms_other,
                                  "parity": "profiles/r02_parity.json (end to end against the fp32 oracle, both modes)"},
                 "ms_per_frame": ms_frame, "traversals_per_s": fps * Pp * T,
                 "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -612,10 +615,11 @@ def run_sharded(args, cfg, det_params, forest_dir, wpath, frames, bgr_all, dep_a
     ref = api.Detector(forest_dir, wpath, det_params, device=local_rank, n_slots=1)
     ref_h = [ref.detect(frames[j][0], frames[j][1]) for j in range(min(distinct, 2))]
     ref.close()
-    info = {}
-    for mode in ("peer", "nccl"):
+    for split, exch in (("patches", "peer"), ("patches", "nccl"), ("trees", "peer")):
+        mode = f"{split}/{exch}"
         try:
-            sd = sharded.TreeShardedDetector(forest_dir, wpath, det_params, device=local_rank, n_slots=n_slots, exchange=mode)
+            sd = sharded.TreeShardedDetector(forest_dir, wpath, det_params, device=local_rank, n_slots=n_slots, exchange=exch,
+                                             split=split)
         except Exception as e:  # e.g. no P2P path between the GPUs: the NCCL exchange still runs
             modes[mode] = {"unavailable": str(e).splitlines()[0][:200]}
             continue
@@ -658,7 +662,7 @@ def run_sharded(args, cfg, det_params, forest_dir, wpath, frames, bgr_all, dep_a
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         modes[mode] = {"frames_per_s": BATCH * args.steps / (ms * 1e-3), "ms_per_frame": ms / (BATCH * args.steps),
                        "kernel_launches_per_frame": sd.launches_per_frame(), "bit_identical": bool(ok.item())}
-        info = {"trees_per_rank": len(sd.trees), "classes_per_rank": len(sd.classes)}
+        modes[mode].update({"trees_per_rank": len(sd.trees), "classes_per_rank": len(sd.classes)})
         for s in range(n_slots):
             sd.det.bind_frame(s, None, None)
         sd.close()
@@ -668,8 +672,11 @@ def run_sharded(args, cfg, det_params, forest_dir, wpath, frames, bgr_all, dep_a
         return {"unavailable": "no exchange mode could run", "exchanges": modes}
     best = max(good, key=lambda m: modes[m]["frames_per_s"])
     out = dict(modes[best])
-    out.update(info)
-    out.update({"exchange": best, "exchanges": modes,
+    out.update({"mode": best, "modes": modes,
+                "note": "split/exchange: 'patches' = every rank gathers, encodes, traverses and votes its share of the frame's patches "
+                        "(scan replicated), 'trees' = the north star's tree split (scan, gather and encode replicated); 'peer' = the "
+                        "consumers read the other ranks' vote maps / leaf tables in place over NVLink (flags in peer memory, no "
+                        "collective), 'nccl' = all-reduce SUM of the maps + MAX of the leaf table; centres + pose sharded by class",
                 "scaling": "strong (one stream: the same frames on every rank)", "frames_in_flight": n_slots})
     return out
 
@@ -683,8 +690,9 @@ def main():
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--slots", type=int, default=4, help="frames in flight (one stream + workspace each)")
-    ap.add_argument("--encoder-mode", type=int, default=0, choices=[0, 1],
-                    help="0: bf16 tensor-core operands (the headline), 1: split bf16 (~fp32 products, 3x the encoder time)")
+    ap.add_argument("--encoder-mode", type=int, default=0, choices=[0, 1, 2],
+                    help="0: bf16 tensor-core operands (the headline), 1: split bf16 (~fp32 products, 3x the encoder time), "
+                         "2: fp16 operands (same rate as 0)")
     ap.add_argument("--tree-timeout", type=int, default=240, help="seconds the sharded arm (N > 1) may take")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -157,6 +157,15 @@ int hf6d_set_fill_seed(hf6d_ctx* c, uint64_t seed);
  * The caller sums HF6D_BUF_MAPS across ranks (NCCL all-reduce, uint64 sum) and max-reduces HF6D_BUF_LEAF_ORD between
  * hf6d_run(.., VOTE) and hf6d_run(CENTRES, ..). */
 int hf6d_set_tree_shard(hf6d_ctx* c, int rank, int world);
+/* Patch sharding (one stream of frames over several GPUs, the split that scales: the encoder is 0.3 of a frame and shards with
+ * the patches, not with the trees): this context gathers, encodes, traverses (every tree) and votes only its share of the
+ * frame's patches -- rank r of `world` takes the 128-patch row blocks [B*r/world, B*(r+1)/world) of the frame's B blocks, in
+ * the reference's patch order (its batches of 100 run in an OpenMP loop, HFTest.cpp:612).  The scan is replicated.  Between
+ * hf6d_run(.., VOTE) and hf6d_run(CENTRES, ..) the caller sums HF6D_BUF_MAPS and max-reduces HF6D_BUF_LEAF_ORD across the
+ * ranks, exactly as for hf6d_set_tree_shard (rows of other ranks' patches are -1), or uses the peer exchange below. */
+int hf6d_set_patch_shard(hf6d_ctx* c, int rank, int world);
+/* What hf6d_peer_attach shards: 0 = trees (default), 1 = patches.  Call before hf6d_peer_attach. */
+int hf6d_set_peer_split(hf6d_ctx* c, int split);
 /* Class sharding of the stages after the exchange: this context seeks centres and poses (HF6D_STAGE_CENTRES, _POSE)
  * only for classes k with k % world == rank; votes are still cast for every detected class.  The hypothesis lists of
  * the ranks, concatenated in class order, equal the unsharded list. */
@@ -189,6 +198,10 @@ int hf6d_peer_timed_out(hf6d_ctx* c); /* 1 if a flag wait gave up (host-side dea
  *   1 = split bf16: every operand as hi + lo bf16 halves, a product as a_hi*w_hi + a_lo*w_hi + a_hi*w_lo on the same
  *       tensor-core kernel (three passes over K), fp32 sigmoid -- features within ~3e-5 of an fp32 evaluation, i.e. as
  *       close to the reference's as one fp32 summation order is to another; about 3x the encoder time.
+ *   2 = fp16 operands, fp32 accumulation: the same kernel at the same tensor-core rate with 11-bit instead of 8-bit
+ *       significands (every operand of this net is bounded: patch values 0..255, sigmoid outputs, weights of a few units;
+ *       the first layer's 1/255 moves from the weights to the accumulator so that small weights stay normal numbers).
+ *       Features within ~2e-3 of fp32.  Not what BASELINE's north star names (bf16), hence not the default.
  * Synchronises the device; the first switch to mode 1 allocates the hi/lo activation buffers of every slot. */
 int hf6d_set_encoder_mode(hf6d_ctx* c, int mode);
 int hf6d_get_encoder_mode(const hf6d_ctx* c);

@@ -24,7 +24,7 @@ MAX_CENTRES = 16
 EXPORTS = (
     "hf6d_default_params", "hf6d_create", "hf6d_create_from_options", "hf6d_destroy", "hf6d_last_error",
     "hf6d_get_params", "hf6d_model", "hf6d_set_objects", "hf6d_get_objects", "hf6d_set_fill_seed",
-    "hf6d_set_tree_shard", "hf6d_set_class_shard", "hf6d_peer_blob_bytes", "hf6d_peer_export", "hf6d_peer_attach",
+    "hf6d_set_tree_shard", "hf6d_set_patch_shard", "hf6d_set_peer_split", "hf6d_set_class_shard", "hf6d_peer_blob_bytes", "hf6d_peer_export", "hf6d_peer_attach",
     "hf6d_peer_detach", "hf6d_peer_timed_out", "hf6d_set_encoder_mode", "hf6d_get_encoder_mode", "hf6d_set_debug_capture", "hf6d_detect", "hf6d_submit",
     "hf6d_wait", "hf6d_host_alloc", "hf6d_host_free", "hf6d_upload", "hf6d_run", "hf6d_sync", "hf6d_collect",
     "hf6d_fetch", "hf6d_inject", "hf6d_device_ptr", "hf6d_set_stream", "hf6d_stage_ms", "hf6d_launch_count",
@@ -102,6 +102,8 @@ def load():
     L.hf6d_get_objects.argtypes = [vp, C.POINTER(ObjectOptions), i32]
     L.hf6d_set_fill_seed.argtypes = [vp, C.c_uint64]
     L.hf6d_set_tree_shard.argtypes = [vp, i32, i32]
+    L.hf6d_set_patch_shard.argtypes = [vp, i32, i32]
+    L.hf6d_set_peer_split.argtypes = [vp, i32]
     L.hf6d_set_class_shard.argtypes = [vp, i32, i32]
     L.hf6d_peer_blob_bytes.argtypes = []
     L.hf6d_peer_blob_bytes.restype = C.c_size_t
@@ -286,6 +288,14 @@ class Detector:
     def set_tree_shard(self, rank: int, world: int):
         self._ck(self._L.hf6d_set_tree_shard(self._h, rank, world))
 
+    def set_patch_shard(self, rank: int, world: int):
+        """Gather .. vote only this rank's share of the frame's patches (128-patch row blocks, reference patch order)."""
+        self._ck(self._L.hf6d_set_patch_shard(self._h, rank, world))
+
+    def set_peer_split(self, split: int):
+        """What peer_attach shards: 0 = trees, 1 = patches."""
+        self._ck(self._L.hf6d_set_peer_split(self._h, split))
+
     def set_class_shard(self, rank: int, world: int):
         self._ck(self._L.hf6d_set_class_shard(self._h, rank, world))
 
@@ -312,7 +322,8 @@ class Detector:
         return bool(self._L.hf6d_peer_timed_out(self._h))
 
     def set_encoder_mode(self, mode: int):
-        """0 = bf16 operands (throughput), 1 = split bf16 hi + lo operands (~fp32 products, about 3x the encoder time)."""
+        """0 = bf16 operands (throughput), 1 = split bf16 hi + lo operands (~fp32 products, about 3x the encoder time),
+        2 = fp16 operands (same kernel and rate as 0, 8x finer significands)."""
         self._ck(self._L.hf6d_set_encoder_mode(self._h, int(mode)))
 
     def encoder_mode(self) -> int:

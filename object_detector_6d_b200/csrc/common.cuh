@@ -37,6 +37,7 @@ struct DevForest {
     const int2* leaf_votes;    // per leaf: (first vote, number of gated votes) over all its groups (contiguous)
     const short4* bins;        // per vote: integer-degree yaw, pitch, roll bins (HFTest.cpp:779-780, :863)
     const float2* oz_range;    // per group: (min, max) of its votes' oz; (inf, -inf) when unordered (a NaN among them)
+    const float* oz_sorted;    // per vote: oz, ascending within every ordered group
 };
 
 // x86 cvttss2si semantics: NaN / out of range -> INT_MIN (CUDA's cast saturates and maps NaN to 0).
@@ -62,6 +63,24 @@ __device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
     z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
     z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
     return z ^ (z >> 31);
+}
+
+// Patch sharding (one stream of frames over several GPUs): rank r of `world` gathers, encodes, traverses and votes the patches
+// [lo, hi) of the frame's P' processed patches.  The cuts fall on multiples of 128 patches, the encoder's row-block size.
+struct PatchShard {
+    int rank, world;  // world == 1: everything
+};
+__host__ __device__ __forceinline__ void patch_shard_range(int Pp, PatchShard ps, int& lo, int& hi) {
+    const int mb = (Pp + 127) / 128;
+    lo = min(Pp, (int)((long long)mb * ps.rank / ps.world) * 128);
+    hi = min(Pp, (int)((long long)mb * (ps.rank + 1) / ps.world) * 128);
+}
+// the rank whose range holds patch p
+__device__ __forceinline__ int patch_shard_owner(int Pp, int world, int p) {
+    const int mb = (Pp + 127) / 128, b = p >> 7;
+    int r = 0;
+    while (r + 1 < world && (int)((long long)mb * (r + 1) / world) <= b) ++r;
+    return r;
 }
 
 // patch_extractor.cu:257 / :378 -- ((ps*vox)/d)*f in fp32, truncated

@@ -58,6 +58,14 @@ __device__ __forceinline__ uint32_t sigmoid_pair_bf16(float h0, float h1) {
     const __nv_bfloat162 b = __floats2bfloat162_rn(fmaf(0.5f, t0, 0.5f), fmaf(0.5f, t1, 0.5f));
     return *reinterpret_cast<const uint32_t*>(&b);
 }
+// the same with fp16 results (encoder mode 2: fp16 operands, 11-bit significands instead of bf16's 8)
+__device__ __forceinline__ uint32_t sigmoid_pair_f16(float h0, float h1) {
+    float t0, t1;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(h0));
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(h1));
+    const __half2 b = __floats2half2_rn(fmaf(0.5f, t0, 0.5f), fmaf(0.5f, t1, 0.5f));
+    return *reinterpret_cast<const uint32_t*>(&b);
+}
 __device__ __forceinline__ float sigmoid_accurate(float x) {
     // 1/(1+e^-x) with ex2.approx and rcp.approx: two MUFU ops, relative error ~2^-21 -- three orders of magnitude below
     // the bf16 operand rounding of the GEMM that feeds it.  Used for the feature layer the forest thresholds.
@@ -104,7 +112,8 @@ template <int BLOCK_N, bool LAST, int STAGES, int EPI_BUFS, int PAIR, int CHUNK_
 __global__ void __launch_bounds__((4 + EPI_WARPS) * 32, 1)
 encoder_layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmC, const float* __restrict__ bias,
-                     const int* __restrict__ m_ptr, int K, int n_pad, int reverse_m, int n_seg, int lo_off) {
+                     const int* __restrict__ m_ptr, int K, int n_pad, int reverse_m, int n_seg, int lo_off, int shard_rank,
+                     int shard_world, int fp16, float in_scale) {
     using S = EncSmem<BLOCK_N, STAGES, EPI_BUFS, PAIR, CHUNK_BYTES, EPI_WARPS>;
     static_assert(PAIR == 1 || PAIR == 2, "stand-alone CTAs or CTA pairs");
     static_assert(EPI_WARPS % 4 == 0, "every TMEM lane quadrant needs the same number of epilogue warps");
@@ -124,7 +133,10 @@ encoder_layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     const int lane = threadIdx.x & 31;
 
     const int M = __shfl_sync(0xffffffffu, *m_ptr, 0);
-    const int m_blocks = (M + ENC_BLOCK_M - 1) / ENC_BLOCK_M;
+    // patch sharding: this rank's row blocks [mb_lo, mb_lo + m_blocks) of the frame's ceil(M / 128) (common.cuh, PatchShard)
+    const int m_blocks_all = (M + ENC_BLOCK_M - 1) / ENC_BLOCK_M;
+    const int mb_lo = (int)((long long)m_blocks_all * shard_rank / shard_world);
+    const int m_blocks = (int)((long long)m_blocks_all * (shard_rank + 1) / shard_world) - mb_lo;
     const int n_blocks = n_pad / BLOCK_N;
     const int k_seg = K / ENC_BLOCK_K;                 // k-blocks per segment
     const int k_blocks = (SPLIT ? n_seg : 1) * k_seg;  // k-blocks per tile
@@ -136,6 +148,7 @@ encoder_layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     // reverse_m: walk the m-blocks from the end.  The layers alternate direction so that each one starts on the rows its
     // producer wrote LAST -- the part of the activation matrix (145-227 MB) that is still in the 126 MB L2.
     auto m_group_of = [&](int g) { return reverse_m ? m_groups - 1 - g : g; };
+    // (the m-block index below is relative to mb_lo: `mb_lo +` is added where it becomes a row coordinate)
 
     for (int i = threadIdx.x; i < n_pad; i += S::THREADS) s_bias[i] = bias[i];
 
@@ -176,7 +189,7 @@ encoder_layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         uint32_t phase = 0;
         const uint32_t full0 = PAIR > 1 ? ptx::mapa_shared(ptx::smem_u32(&full[0]), 0) : 0;  // the even CTA's barriers
         for (int t = first; t < tiles; t += step) {
-            const int mb = m_group_of(t / n_blocks) * PAIR + cta_rank, nb = t % n_blocks;
+            const int mb = mb_lo + m_group_of(t / n_blocks) * PAIR + cta_rank, nb = t % n_blocks;
             for (int kb = 0; kb < k_blocks; ++kb) {
                 // operand columns of this k-block: the bf16 mode walks both matrices in step; the split mode's segments
                 // pair (a_hi, w_hi), (a_lo, w_hi), (a_hi, w_lo) -- the last segment reads the lo half of W, the middle one
@@ -209,7 +222,9 @@ encoder_layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     } else if (warp == 1) {
         // ------------------------------------------------------------ MMA issuer (the even CTA of a pair; one lane issues)
         if (cta_rank == 0) {
-            constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(ENC_BLOCK_M * PAIR, BLOCK_N);
+            // operand format: bf16, or fp16 in encoder mode 2 (same tiles, same rate; only the descriptor's format fields differ)
+            const uint32_t idesc = fp16 ? ptx::make_idesc_bf16_f32(ENC_BLOCK_M * PAIR, BLOCK_N, true)
+                                        : ptx::make_idesc_bf16_f32(ENC_BLOCK_M * PAIR, BLOCK_N, false);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -267,7 +282,7 @@ encoder_layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int t = first; t < tiles; t += step) {
-            const int mb = m_group_of(t / n_blocks) * PAIR + cta_rank, nb = t % n_blocks;
+            const int mb = mb_lo + m_group_of(t / n_blocks) * PAIR + cta_rank, nb = t % n_blocks;
             const int row0 = mb * ENC_BLOCK_M + q * 32;
             ptx::mbar_wait(&tfull[acc], acc_phase);
             ptx::tc_fence_after();
@@ -306,13 +321,25 @@ encoder_layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                                         sigmoid_fp32(__fadd_rn(__uint_as_float(v[4 * j + 3]), b.w)), o[2 * j + 1], o_lo[2 * j + 1]);
                     }
                 } else if constexpr (!LAST) {
+                    // x/2 = acc * (in_scale / 2) + b/2: in_scale is 1 except for the first layer of the fp16 mode, whose
+                    // weights are NOT pre-divided by 255 (they would drop into fp16's subnormals)
+                    const float hs = 0.5f * in_scale;
+                    if (fp16) {
 #pragma unroll
-                    for (int j = 0; j < CHUNK_COLS / 4; ++j) {
-                        const float4 b = ptx::ld_shared_f4(bias_addr + 16 * j);
-                        o[2 * j] = sigmoid_pair_bf16(fmaf(__uint_as_float(v[4 * j]), 0.5f, b.x),
-                                                     fmaf(__uint_as_float(v[4 * j + 1]), 0.5f, b.y));
-                        o[2 * j + 1] = sigmoid_pair_bf16(fmaf(__uint_as_float(v[4 * j + 2]), 0.5f, b.z),
-                                                         fmaf(__uint_as_float(v[4 * j + 3]), 0.5f, b.w));
+                        for (int j = 0; j < CHUNK_COLS / 4; ++j) {
+                            const float4 b = ptx::ld_shared_f4(bias_addr + 16 * j);
+                            o[2 * j] = sigmoid_pair_f16(fmaf(__uint_as_float(v[4 * j]), hs, b.x), fmaf(__uint_as_float(v[4 * j + 1]), hs, b.y));
+                            o[2 * j + 1] = sigmoid_pair_f16(fmaf(__uint_as_float(v[4 * j + 2]), hs, b.z), fmaf(__uint_as_float(v[4 * j + 3]), hs, b.w));
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < CHUNK_COLS / 4; ++j) {
+                            const float4 b = ptx::ld_shared_f4(bias_addr + 16 * j);
+                            o[2 * j] = sigmoid_pair_bf16(fmaf(__uint_as_float(v[4 * j]), 0.5f, b.x),
+                                                         fmaf(__uint_as_float(v[4 * j + 1]), 0.5f, b.y));
+                            o[2 * j + 1] = sigmoid_pair_bf16(fmaf(__uint_as_float(v[4 * j + 2]), 0.5f, b.z),
+                                                             fmaf(__uint_as_float(v[4 * j + 3]), 0.5f, b.w));
+                        }
                     }
                 } else {
 #pragma unroll
@@ -433,6 +460,9 @@ struct EncoderLayerLaunch {
     int reverse_m;       // walk the m-blocks from the end (see the kernel)
     bool split;          // split-bf16 arithmetic (see the kernel): variant then selects pairs (0) or stand-alone CTAs (1)
     int n_seg, lo_off;   // split: k segments (2: exact A, 3: hi/lo A); column offset of the lo halves in the hidden output
+    int shard_rank, shard_world;  // patch sharding: the row blocks this rank encodes (0 / 0 or 1 = all)
+    int fp16;                     // operands are fp16 instead of bf16 (encoder mode 2)
+    float in_scale;               // hidden layers: accumulator scale before the bias (0 = 1.0; 1/255 for fp16 layer 1)
 };
 
 template <int BLOCK_N, bool LAST, int STAGES, int EPI_BUFS, int PAIR, int CHUNK_BYTES, int EPI_WARPS, bool SPLIT = false>
@@ -472,7 +502,8 @@ inline cudaError_t launch_encoder_layer_t(const EncoderLayerLaunch& L, const int
     cfg.attrs = attrs;
     cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kern, L.tmA, L.tmB, L.tmC, L.bias, m_ptr, L.K, L.n_pad, L.reverse_m, SPLIT ? L.n_seg : 1,
-                              L.lo_off);
+                              L.lo_off, L.shard_world > 1 ? L.shard_rank : 0, L.shard_world > 1 ? L.shard_world : 1, L.fp16,
+                              L.in_scale == 0.f ? 1.0f : L.in_scale);
 }
 
 // The kernel configurations, one table for the launcher and for the slot's tensor maps (W box rows, output chunk width).

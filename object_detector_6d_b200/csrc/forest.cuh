@@ -55,7 +55,7 @@ template <int NCH>
 __global__ void __launch_bounds__((TRV_MAX_BUFS + 1) * 32, 1)
 traverse_kernel(const float* __restrict__ features, DevForest f, const int* __restrict__ counts,
                 int* __restrict__ leaf_ord, int shard_rank, int shard_world, int n_bufs, int n_cache, int n_recs,
-                int reverse) {
+                int reverse, PatchShard pshard) {
     extern __shared__ __align__(16) uint8_t trv_smem[];
     const int F = f.F, pitch = F + 4;
     PackedRecord* cache = reinterpret_cast<PackedRecord*>(trv_smem);  // [T][n_cache]
@@ -64,8 +64,9 @@ traverse_kernel(const float* __restrict__ features, DevForest f, const int* __re
     uint64_t* empty = full + TRV_MAX_BUFS;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int Pp = counts[1];
-    const int tiles = (Pp + TRV_ROWS - 1) / TRV_ROWS;
+    int p_lo, Pp;  // patch sharding: rows [p_lo, Pp) (p_lo is a multiple of 128, so of TRV_ROWS); tiles are counted from p_lo
+    patch_shard_range(counts[1], pshard, p_lo, Pp);
+    const int tiles = (Pp - p_lo + TRV_ROWS - 1) / TRV_ROWS;
     const int n_owned = (f.T - shard_rank + shard_world - 1) / shard_world;
 
     for (int i = threadIdx.x; i < n_bufs * TRV_ROWS; i += blockDim.x) {
@@ -97,7 +98,7 @@ traverse_kernel(const float* __restrict__ features, DevForest f, const int* __re
         uint32_t phase = 0;
         for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
             ptx::mbar_wait(&empty[b], phase ^ 1);
-            const int p0 = (reverse ? tiles - 1 - tile : tile) * TRV_ROWS;  // last rows first: see the consumers
+            const int p0 = p_lo + (reverse ? tiles - 1 - tile : tile) * TRV_ROWS;  // last rows first: see the consumers
             const int nrows = min(TRV_ROWS, Pp - p0);
             if (lane == 0) ptx::mbar_arrive_expect_tx(&full[b], (uint32_t)nrows * F * 4);
             __syncwarp();
@@ -114,7 +115,7 @@ traverse_kernel(const float* __restrict__ features, DevForest f, const int* __re
             // The rows are walked from the END of the matrix: the feature layer wrote them in ascending order just before
             // this kernel, so the tail of the 227 MB is what the 126 MB L2 still holds -- reading it first turns those
             // rows into L2 hits instead of letting the head's misses evict them.
-            const int p0 = (reverse ? tiles - 1 - tile : tile) * TRV_ROWS;
+            const int p0 = p_lo + (reverse ? tiles - 1 - tile : tile) * TRV_ROWS;
             const int nrows = min(TRV_ROWS, Pp - p0);
             // trees this rank does not own: mark, so that a max-reduce across ranks assembles the full table
             if (shard_world > 1) {

@@ -14,6 +14,8 @@
 // sequential mean / variance accumulation order c -> row -> col of the reference and the double-precision variance terms
 // its `pow(x - mean, 2) / N` compiles to (oracle choice C3), so the uint8 patches are bit-exact.
 #pragma once
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace hf6d {
@@ -82,6 +84,16 @@ __global__ void scan_compact_kernel(const uint16_t* __restrict__ depth, FrameGeo
         }
         pos += __popc(m);
     }
+}
+
+// Two quantised values 0..255 as the encoder's A operand: exact integers in bf16 (8-bit significand: up to 256) or fp16.
+__device__ __forceinline__ uint32_t pack_q_pair(uint32_t q0, uint32_t q1, int fp16) {
+    if (fp16) {
+        const __half2 h = __floats2half2_rn((float)q0, (float)q1);
+        return *reinterpret_cast<const uint32_t*>(&h);
+    }
+    const __nv_bfloat162 h = __floats2bfloat162_rn((float)q0, (float)q1);
+    return *reinterpret_cast<const uint32_t*>(&h);
 }
 
 // Software restatement of the texture fetch the reference uses (3-D float texture, unnormalised coordinates,
@@ -186,16 +198,17 @@ __device__ __forceinline__ void sequential_variances(const float (*dev)[GATHER_R
 // q_out : optional uint8 [cap][256] (debug capture / parity)
 __global__ void __launch_bounds__(GATHER_THREADS)
 gather_normalise_kernel(const uint2* __restrict__ tex, FrameGeom g, const int* __restrict__ locs,
-                        const int* __restrict__ counts,
-                        __nv_bfloat16* __restrict__ a_out, uint8_t* __restrict__ q_out) {
+                        const int* __restrict__ counts, PatchShard shard,
+                        __nv_bfloat16* __restrict__ a_out, uint8_t* __restrict__ q_out, int a_fp16) {
     __shared__ float s_term[GATHER_PATCHES_PER_CTA][GATHER_ROW];
     __shared__ float s_stat[GATHER_PATCHES_PER_CTA][4];  // mean_rgb, mean_d, var_rgb, var_d
 
-    const int Pp = counts[1];
+    int p_lo, Pp;  // this rank's patches [p_lo, Pp): cuts on multiples of 128, so a CTA's 16 patches are all in or all out
+    patch_shard_range(counts[1], shard, p_lo, Pp);
     const int pl = threadIdx.x >> 3;
     const int ty = threadIdx.x & 7;
     const int p = blockIdx.x * GATHER_PATCHES_PER_CTA + pl;
-    if (blockIdx.x * GATHER_PATCHES_PER_CTA >= Pp) return;  // whole CTA out of range
+    if (blockIdx.x * GATHER_PATCHES_PER_CTA >= Pp || (blockIdx.x + 1) * GATHER_PATCHES_PER_CTA <= p_lo) return;  // whole CTA out of range
     const bool live = p < Pp;
 
     float val[4][8];
@@ -302,10 +315,7 @@ gather_normalise_kernel(const uint2* __restrict__ tex, FrameGeom g, const int* _
         const size_t o = (size_t)p * 256 + ch * 64 + ty * 8;
         uint32_t pk[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            __nv_bfloat162 h2 = __floats2bfloat162_rn((float)qb[2 * k], (float)qb[2 * k + 1]);
-            pk[k] = *reinterpret_cast<uint32_t*>(&h2);
-        }
+        for (int k = 0; k < 4; ++k) pk[k] = pack_q_pair(qb[2 * k], qb[2 * k + 1], a_fp16);
         *reinterpret_cast<uint4*>(a_out + o) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         if (q_out) {
             const uint32_t lo = qb[0] | (qb[1] << 8) | (qb[2] << 16) | (qb[3] << 24);
@@ -383,8 +393,8 @@ __device__ __forceinline__ void gt_sample_row(const uint2* __restrict__ tex, con
 // grid = (ceil(gw / GT_PATCHES), gh); dynamic shared memory = max(tile_cap_texels * 8, GT_VAL_BYTES).
 __global__ void __launch_bounds__(GT_THREADS)
 gather_tile_kernel(const uint2* __restrict__ tex, FrameGeom g, const int* __restrict__ locs, const int* __restrict__ counts,
-                   const int* __restrict__ row_count, const int* __restrict__ row_off, int tile_cap_texels,
-                   __nv_bfloat16* __restrict__ a_out, uint8_t* __restrict__ q_out) {
+                   const int* __restrict__ row_count, const int* __restrict__ row_off, int tile_cap_texels, PatchShard shard,
+                   __nv_bfloat16* __restrict__ a_out, uint8_t* __restrict__ q_out, int a_fp16) {
     extern __shared__ __align__(16) uint8_t gt_smem[];
     uint2* s_tile = reinterpret_cast<uint2*>(gt_smem);
     float* s_val = reinterpret_cast<float*>(gt_smem);  // overlays the tile once every tap has been read
@@ -394,13 +404,15 @@ gather_tile_kernel(const uint2* __restrict__ tex, FrameGeom g, const int* __rest
     const int row = blockIdx.y, seg0 = blockIdx.x * GT_PATCHES;
     const int n_row = row_count[row];
     if (seg0 >= n_row) return;
-    const int Pp = counts[1];
+    int p_lo, Pp;  // this rank's patches [p_lo, Pp)
+    patch_shard_range(counts[1], shard, p_lo, Pp);
     const int p0 = row_off[row] + seg0;
     if (p0 >= Pp) return;
     const int n_here = min(min(GT_PATCHES, n_row - seg0), Pp - p0);
+    if (p0 + n_here <= p_lo) return;
     const int pl = threadIdx.x >> 3, ty = threadIdx.x & 7;
     const int p = p0 + pl;
-    const bool live = pl < n_here;
+    const bool live = pl < n_here && p >= p_lo;
     if (threadIdx.x == 0) { s_box[0] = INT_MAX; s_box[1] = INT_MAX; s_box[2] = INT_MIN; s_box[3] = INT_MIN; }
     __syncthreads();
 
@@ -509,10 +521,7 @@ gather_tile_kernel(const uint2* __restrict__ tex, FrameGeom g, const int* __rest
         const size_t o = (size_t)p * 256 + ch * 64 + ty * 8;
         uint32_t pk[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            __nv_bfloat162 h2 = __floats2bfloat162_rn((float)qb[2 * k], (float)qb[2 * k + 1]);
-            pk[k] = *reinterpret_cast<uint32_t*>(&h2);
-        }
+        for (int k = 0; k < 4; ++k) pk[k] = pack_q_pair(qb[2 * k], qb[2 * k + 1], a_fp16);
         *reinterpret_cast<uint4*>(a_out + o) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         if (q_out) {
             const uint32_t lo = qb[0] | (qb[1] << 8) | (qb[2] << 16) | (qb[3] << 24);

@@ -3,6 +3,7 @@
 // There is deliberately no CPU path in this file: without a usable sm_100 device every compute entry point fails.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -48,6 +49,8 @@ struct DeviceModel {
     // split-bf16 mode (hf6d_set_encoder_mode 1), uploaded on first use: [n_pad][2 * k_pad] = (w_hi | w_lo), plain biases
     __nv_bfloat16* Ws[3] = {nullptr, nullptr, nullptr};
     float* bs[3] = {nullptr, nullptr, nullptr};
+    // fp16 mode (hf6d_set_encoder_mode 2), uploaded on first use: fp16 weights [n_pad][k_pad]; layer 1 NOT divided by 255
+    __half* Wh[3] = {nullptr, nullptr, nullptr};
     uint8_t* sep_ok = nullptr;
     uint8_t* class_mask = nullptr;  // [HF6D_MAX_CLASSES] classes whose centres / poses this context seeks
 };
@@ -97,6 +100,8 @@ struct Slot {
     __nv_bfloat16 *H1s = nullptr, *H2s = nullptr;
     EncoderLayerLaunch enc_split[3];
     bool split_ready = false;
+    EncoderLayerLaunch enc_fp16[3];  // fp16 mode: the bf16 launches with the weight map and the operand format replaced
+    bool fp16_ready = false;
     uint32_t peer_seq = 0;  // frames this slot has pushed through the peer exchange (both flags carry it)
     bool busy = false;  // submit/wait bookkeeping
     int ticket = -1;
@@ -132,6 +137,8 @@ struct hf6d_ctx {
     int stream_cap = 0, pair_cap = 0;
     int shard_rank = 0, shard_world = 1;
     int class_rank = 0, class_world = 1;  // centres + pose only for classes k % class_world == class_rank
+    PatchShard pshard{0, 1};              // gather .. vote only for this rank's patches (hf6d_set_patch_shard)
+    int peer_split = 0;                   // what hf6d_peer_attach shards: 0 = trees, 1 = patches
     // peer exchange (tree-sharded mode over NVLink peer memory, hf6d_peer_attach)
     bool peer_on = false;
     int peer_rank = 0, peer_world = 1;
@@ -219,6 +226,7 @@ int upload_model(hf6d_ctx* c) {
     if ((r = dev_upload(c, dm.allocs, &dm.f.group_off, hf.group_off))) return r;
     if ((r = dev_upload(c, dm.allocs, &dm.f.groups, hf.groups))) return r;
     if ((r = dev_upload(c, dm.allocs, &dm.f.oz, hf.oz))) return r;
+    if ((r = dev_upload(c, dm.allocs, &dm.f.oz_sorted, hf.oz_sorted))) return r;
     if ((r = dev_upload(c, dm.allocs, &dm.f.vgroup, hf.vgroup))) return r;
     {
         std::vector<float4> v4(hf.ox.size());
@@ -577,8 +585,11 @@ LeafTables leaf_tables_of(const hf6d_ctx* c, const Slot& s, int slot) {
     memset(&lt, 0, sizeof lt);
     lt.base[0] = s.leaf_ord;
     lt.world = 1;
+    lt.patch_world = 1;
+    lt.shard = PatchShard{0, 1};  // the pose stage enumerates every patch
     if (c->peer_on) {
-        lt.world = c->peer_world;
+        if (c->peer_split == 1) lt.patch_world = c->peer_world;
+        else lt.world = c->peer_world;
         for (int r = 0; r < c->peer_world; ++r) lt.base[r] = r == c->peer_rank ? s.leaf_ord : c->peer_leaf[r][slot];
     }
     return lt;
@@ -603,6 +614,7 @@ int run_stage(hf6d_ctx* c, Slot& s, int stage) {
         case HF6D_STAGE_GATHER: {
             pack_frame_kernel<<<(g.W * g.H + 255) / 256, 256, 0, st>>>(s.bgr, s.depth, g.W * g.H, s.tex);
             LAUNCH_CHECK(c, s);
+            if (c->p.patch_mode == 1 && c->pshard.world > 1) return fail(c, HF6D_EINVAL, "patch sharding is not available in patch_mode 1");
             if (c->p.patch_mode == 1) {
                 normals_kernel<<<(g.W * g.H + 255) / 256, 256, 0, st>>>(s.depth, g.W, g.H, c->p.normals_focal, s.normals);
                 LAUNCH_CHECK(c, s);
@@ -610,18 +622,23 @@ int run_stage(hf6d_ctx* c, Slot& s, int stage) {
                     s.tex, s.normals, g, s.locs, s.counts, s.A0, c->debug_capture ? s.q_u8 : nullptr);
             } else if (c->gather_tiled)
                 gather_tile_kernel<<<dim3((g.gw + GT_PATCHES - 1) / GT_PATCHES, g.gh), GT_THREADS, c->gather_smem, st>>>(
-                    s.tex, g, s.locs, s.counts, s.row_count, s.row_off, c->gather_tile_texels, s.A0, c->debug_capture ? s.q_u8 : nullptr);
+                    s.tex, g, s.locs, s.counts, s.row_count, s.row_off, c->gather_tile_texels, c->pshard, s.A0, c->debug_capture ? s.q_u8 : nullptr,
+                    c->encoder_mode == 2);
             else
                 gather_normalise_kernel<<<g.cap / GATHER_PATCHES_PER_CTA, GATHER_THREADS, 0, st>>>(
-                    s.tex, g, s.locs, s.counts, s.A0, c->debug_capture ? s.q_u8 : nullptr);
+                    s.tex, g, s.locs, s.counts, c->pshard, s.A0, c->debug_capture ? s.q_u8 : nullptr, c->encoder_mode == 2);
             LAUNCH_CHECK(c, s);
             break;
         }
         case HF6D_STAGE_ENCODE: {
             CU_TRY(c, cudaEventRecord(s.ev_enc[0], st));
             if (c->encoder_mode == 1 && !s.split_ready) return fail(c, HF6D_ESTATE, "split encoder buffers missing");
+            if (c->encoder_mode == 2 && !s.fp16_ready) return fail(c, HF6D_ESTATE, "fp16 encoder state missing");
             for (int l = 0; l < 3; ++l) {
-                cudaError_t e = launch_encoder_layer(c->encoder_mode == 1 ? s.enc_split[l] : s.enc[l], s.counts + 1, c->sms, st);
+                EncoderLayerLaunch& L = c->encoder_mode == 1 ? s.enc_split[l] : c->encoder_mode == 2 ? s.enc_fp16[l] : s.enc[l];
+                L.shard_rank = c->pshard.rank;
+                L.shard_world = c->pshard.world;
+                cudaError_t e = launch_encoder_layer(L, s.counts + 1, c->sms, st);
                 if (e != cudaSuccess) return fail(c, HF6D_ECUDA, "encoder layer %d launch: %s", l, cudaGetErrorString(e));
                 ++s.launches;
                 CU_TRY(c, cudaEventRecord(s.ev_enc[l + 1], st));
@@ -634,16 +651,18 @@ int run_stage(hf6d_ctx* c, Slot& s, int stage) {
             const int n_owned = (f.T - c->shard_rank + c->shard_world - 1) / c->shard_world;
             const int per_slot = (n_owned + TRV_SLOTS - 1) / TRV_SLOTS;
             const int threads = (tp.n_bufs + 1) * 32, n_recs = (int)c->hf.recs.size();
+            if (c->pshard.world > 1)  // rows of other ranks' patches: "not traversed here" (-1), as for trees that are not owned
+                CU_TRY(c, cudaMemsetAsync(s.leaf_ord, 0xFF, (size_t)g.cap * f.T * 4, st));
             static const int trv_reverse = !(getenv("HF6D_SNAKE") && atoi(getenv("HF6D_SNAKE")) == 0);  // see alloc_slot
             if (per_slot <= 1)
                 traverse_kernel<1><<<c->sms, threads, tp.smem, st>>>(s.feat, f, s.counts, s.leaf_ord, c->shard_rank, c->shard_world,
-                                                                   tp.n_bufs, tp.n_cache, n_recs, trv_reverse);
+                                                                   tp.n_bufs, tp.n_cache, n_recs, trv_reverse, c->pshard);
             else if (per_slot <= 2)
                 traverse_kernel<2><<<c->sms, threads, tp.smem, st>>>(s.feat, f, s.counts, s.leaf_ord, c->shard_rank, c->shard_world,
-                                                                   tp.n_bufs, tp.n_cache, n_recs, trv_reverse);
+                                                                   tp.n_bufs, tp.n_cache, n_recs, trv_reverse, c->pshard);
             else
                 traverse_kernel<4><<<c->sms, threads, tp.smem, st>>>(s.feat, f, s.counts, s.leaf_ord, c->shard_rank, c->shard_world,
-                                                                   tp.n_bufs, tp.n_cache, n_recs, trv_reverse);
+                                                                   tp.n_bufs, tp.n_cache, n_recs, trv_reverse, c->pshard);
             LAUNCH_CHECK(c, s);
             break;
         }
@@ -652,13 +671,13 @@ int run_stage(hf6d_ctx* c, Slot& s, int stage) {
             const long long items = (long long)g.cap * f.T;
             const int blocks = (int)std::min<long long>((items + VOTE_THREADS - 1) / VOTE_THREADS, (long long)c->sms * 8);
             // the vote stream serves the pose stage of THIS context: with sharded trees the windows need the other ranks' votes
-            const bool streaming = c->use_stream && c->shard_world == 1 && !c->peer_on;
+            const bool streaming = c->use_stream && c->shard_world == 1 && c->pshard.world == 1 && !c->peer_on;
             VoteStream vs{nullptr, nullptr, 0};
             if (streaming) {
                 CU_TRY(c, cudaMemsetAsync(s.stream_n, 0, 4, st));
                 vs = VoteStream{s.vstream, s.stream_n, c->stream_cap};
             }
-            vote_kernel<<<blocks, VOTE_THREADS, 0, st>>>(f, g, switches_of(c), s.locs, s.depth, s.leaf_ord, s.counts, s.maps, vs);
+            vote_kernel<<<blocks, VOTE_THREADS, 0, st>>>(f, g, switches_of(c), s.locs, s.depth, s.leaf_ord, s.counts, s.maps, vs, c->pshard);
             LAUNCH_CHECK(c, s);
             s.stream_valid = streaming;
             break;
@@ -700,7 +719,7 @@ int run_stage(hf6d_ctx* c, Slot& s, int stage) {
             // Two implementations of pass A (HFTest.cpp:742-802).  The stream path needs the vote stream the vote kernel wrote
             // for this slot's current leaf table; sharded contexts, huge forests (stream over budget) and stage-isolated runs
             // that replaced the leaf table after voting use the enumeration path.  Both give identical accumulators.
-            const bool stream_path = c->use_stream && s.stream_valid && c->shard_world == 1 && !c->peer_on;
+            const bool stream_path = c->use_stream && s.stream_valid && c->shard_world == 1 && c->pshard.world == 1 && !c->peer_on;
             // clear only the accumulator slots a class can use (slot = class * HF6D_MAX_CENTRES + centre rank): one launch.
             // The (slot, group) counters are left zeroed by the stream path itself (its roll pass zeroes what it visited).
             {
@@ -1354,6 +1373,22 @@ int hf6d_set_tree_shard(hf6d_ctx* c, int rank, int world) {
     return HF6D_OK;
 }
 
+int hf6d_set_patch_shard(hf6d_ctx* c, int rank, int world) {
+    if (!c) return HF6D_EINVAL;
+    if (world < 1 || rank < 0 || rank >= world) return fail(c, HF6D_EINVAL, "bad patch shard %d/%d", rank, world);
+    c->pshard = PatchShard{rank, world};
+    for (Slot& s : c->slots) s.stream_valid = false;
+    return HF6D_OK;
+}
+
+int hf6d_set_peer_split(hf6d_ctx* c, int split) {
+    if (!c) return HF6D_EINVAL;
+    if (split != 0 && split != 1) return fail(c, HF6D_EINVAL, "peer split %d: 0 = trees, 1 = patches", split);
+    if (c->peer_on) return fail(c, HF6D_ESTATE, "hf6d_set_peer_split must be called before hf6d_peer_attach");
+    c->peer_split = split;
+    return HF6D_OK;
+}
+
 int hf6d_set_class_shard(hf6d_ctx* c, int rank, int world) {
     if (!c) return HF6D_EINVAL;
     if (world < 1 || rank < 0 || rank >= world) return fail(c, HF6D_EINVAL, "bad class shard %d/%d", rank, world);
@@ -1465,7 +1500,13 @@ int hf6d_peer_attach(hf6d_ctx* c, int rank, int world, const void* blobs, size_t
     // zeroed once when the block was created (hf6d_peer_export); every rank of a group counts the same frames, so the numbers
     // stay in step across detach / attach cycles of the whole group.
     int r;
-    if ((r = hf6d_set_tree_shard(c, rank, world))) return r;
+    if (c->peer_split == 1) {
+        if ((r = hf6d_set_tree_shard(c, 0, 1))) return r;
+        if ((r = hf6d_set_patch_shard(c, rank, world))) return r;
+    } else {
+        if ((r = hf6d_set_patch_shard(c, 0, 1))) return r;
+        if ((r = hf6d_set_tree_shard(c, rank, world))) return r;
+    }
     return hf6d_set_class_shard(c, rank, world);
 }
 
@@ -1543,18 +1584,56 @@ int ensure_split_encoder(hf6d_ctx* c) {
     }
     return HF6D_OK;
 }
+// fp16 encoder state: fp16 weights (same padded shapes as the bf16 ones) and per-slot launches that differ from the bf16 ones
+// in the weight tensor map, the operand format and -- first layer -- the 1/255 applied to the accumulator instead of W.
+int ensure_fp16_encoder(hf6d_ctx* c) {
+    DeviceModel& dm = c->dm;
+    int r;
+    if (c->p.patch_mode == 1) return fail(c, HF6D_EINVAL, "encoder mode 2 is not available in patch_mode 1");
+    if (!dm.Wh[0]) {
+        for (int l = 0; l < 3; ++l) {
+            const HostLayer& L = c->layers[l];
+            std::vector<__half> w((size_t)dm.n_pad[l] * dm.k_pad[l], __float2half(0.f));
+            for (int n = 0; n < L.out; ++n)
+                for (int k = 0; k < L.in; ++k) w[(size_t)n * dm.k_pad[l] + k] = __float2half(L.W[(size_t)n * L.in + k]);
+            const __half* wp = nullptr;
+            if ((r = dev_upload(c, dm.allocs, &wp, w))) return r;
+            dm.Wh[l] = const_cast<__half*>(wp);
+        }
+    }
+    for (Slot& s : c->slots) {
+        if (s.fp16_ready) continue;
+        for (int l = 0; l < 3; ++l) {
+            EncoderLayerLaunch& L = s.enc_fp16[l];
+            L = s.enc[l];
+            const EncoderConfig cfg = encoder_config(L.block_n, L.last, L.short_k, L.variant);
+            if (!make_bf16_kmajor_map(&L.tmB, dm.Wh[l], (uint64_t)dm.n_pad[l], (uint64_t)dm.k_pad[l], (uint32_t)(L.block_n / cfg.pair)))
+                return fail(c, HF6D_ECUDA, "cuTensorMapEncodeTiled failed for fp16 encoder layer %d", l);
+            L.fp16 = 1;
+            L.in_scale = l == 0 ? 1.0f / 255.0f : 1.0f;
+        }
+        s.fp16_ready = true;
+    }
+    return HF6D_OK;
+}
 }  // namespace
 
 int hf6d_set_encoder_mode(hf6d_ctx* c, int mode) {
     if (!c) return HF6D_EINVAL;
-    if (mode != 0 && mode != 1) return fail(c, HF6D_EINVAL, "encoder mode %d: 0 = bf16 operands, 1 = split bf16 (hi + lo)", mode);
+    if (mode < 0 || mode > 2)
+        return fail(c, HF6D_EINVAL, "encoder mode %d: 0 = bf16 operands, 1 = split bf16 (hi + lo), 2 = fp16 operands", mode);
     CU_TRY(c, cudaSetDevice(c->device));
     CU_TRY(c, cudaDeviceSynchronize());
     if (mode == 1) {
         const int r = ensure_split_encoder(c);
         if (r) return r;
     }
+    if (mode == 2) {
+        const int r = ensure_fp16_encoder(c);
+        if (r) return r;
+    }
     c->encoder_mode = mode;
+    for (Slot& s : c->slots) s.stream_valid = false;
     return HF6D_OK;
 }
 

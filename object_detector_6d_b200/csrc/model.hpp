@@ -4,6 +4,7 @@
 //   text-format DetectorOptions     HoughForest/include/proto/detector_options.proto, HFTest.cpp:1155-1235
 // Plain C++ (no CUDA), compiled with -ffp-contract=off so the vote pre-rotation below rounds exactly as written.
 #pragma once
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -63,6 +64,7 @@ struct HostForest {
     std::vector<int32_t> vgroup;            // [votes] vote -> its group
     std::vector<int32_t> leaf_vbeg, leaf_vcnt;  // [L] all gated votes of a leaf are contiguous: first vote, count
     std::vector<float> g_ozmin, g_ozmax;        // [groups] smallest / largest oz of the group's votes (z-histogram shortcut)
+    std::vector<float> oz_sorted;               // [votes] oz again, ascending within every group (counting votes per z bin)
     int64_t n_internal = 0;
 };
 
@@ -294,6 +296,12 @@ inline bool load_forest(const std::string& dir, HostForest& hf, std::string& err
         }
         hf.g_ozmin[gi] = ordered ? lo : INFINITY;
         hf.g_ozmax[gi] = ordered ? hi : -INFINITY;
+    }
+    hf.oz_sorted = hf.oz;
+    for (size_t gi = 0; gi < hf.groups.size(); ++gi) {
+        const VoteGroup& vg = hf.groups[gi];
+        if (hf.g_ozmin[gi] <= hf.g_ozmax[gi])  // ordered groups only (the others are walked vote by vote)
+            std::sort(hf.oz_sorted.begin() + vg.vbeg, hf.oz_sorted.begin() + vg.vbeg + vg.vcnt);
     }
     if (hf.nodes.empty()) hf.nodes.push_back(PackedNode{0, 0.f, -1, -1});  // keep device arrays non-empty
     if (hf.recs.empty()) { PackedRecord r; memset(&r, 0, sizeof r); hf.recs.push_back(r); }

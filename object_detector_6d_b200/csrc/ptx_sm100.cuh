@@ -253,13 +253,13 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
     return d;
 }
 
-// Instruction descriptor, kind::f16: D=f32, A=B=bf16, both K-major, dense, no negate.
-__host__ __device__ constexpr uint32_t make_idesc_bf16_f32(int m, int n) {
-    return (1u << 4)                      // c_format  = F32
-           | (1u << 7)                    // a_format  = BF16
-           | (1u << 10)                   // b_format  = BF16
-           | ((uint32_t)(n >> 3) << 17)   // n_dim
-           | ((uint32_t)(m >> 4) << 24);  // m_dim
+// Instruction descriptor, kind::f16: D=f32, A=B=bf16 (or, fp16 = true, A=B=f16), both K-major, dense, no negate.
+__host__ __device__ constexpr uint32_t make_idesc_bf16_f32(int m, int n, bool fp16 = false) {
+    return (1u << 4)                        // c_format  = F32
+           | ((fp16 ? 0u : 1u) << 7)        // a_format  = BF16 (1) / F16 (0)
+           | ((fp16 ? 0u : 1u) << 10)       // b_format  = BF16 (1) / F16 (0)
+           | ((uint32_t)(n >> 3) << 17)     // n_dim
+           | ((uint32_t)(m >> 4) << 24);    // m_dim
 }
 
 }  // namespace ptx

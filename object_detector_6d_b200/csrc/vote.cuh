@@ -61,9 +61,14 @@ struct WarpItems {
 // most warps idle behind the few that own the busy batches.
 // Leaf tables of the ranks of a tree-sharded group (peer exchange): tree t is read from the table of the rank that
 // traversed it, base[t % world]; world == 1 means "the local table only".  Peer tables live in other GPUs' memory.
+// patch_world > 1: the ranks share the PATCHES instead (PatchShard): patch p is read from the table of the rank whose range
+// holds it, and `shard` restricts the enumeration to this rank's own patches (the vote kernel) or to everything (the pose
+// stage, which needs every rank's votes for its classes).
 struct LeafTables {
     const int* base[HF6D_MAX_PEERS];
     int world;
+    int patch_world;
+    PatchShard shard;  // items enumerated: this rank's patches (world > 1) or all (world == 1)
 };
 
 // The vote stream: one 8-byte record per cast vote, {vote index, (u + 64) | (v + 64) << 13 | class << 26}, written by the
@@ -89,13 +94,21 @@ __device__ __forceinline__ void for_each_cast_vote(const DevForest& f, const Fra
                                                    const uint16_t* __restrict__ depth, const LeafTables& lt,
                                                    int n_items, WarpItems& wi, int* next_batch, int* stream_n, Body&& body) {
     const int lane = threadIdx.x & 31;
-    const int warp0 = (blockIdx.x * VOTE_WARPS + (threadIdx.x >> 5)) * 32;
+    const int Pp_all = n_items / f.T;
+    int item_lo = 0;
+    if (lt.shard.world > 1) {  // patch sharding: only this rank's patches
+        int p_lo, p_hi;
+        patch_shard_range(n_items / f.T, lt.shard, p_lo, p_hi);
+        item_lo = p_lo * f.T;
+        n_items = p_hi * f.T;
+    }
+    const int warp0 = item_lo + (blockIdx.x * VOTE_WARPS + (threadIdx.x >> 5)) * 32;
     const int stride = gridDim.x * VOTE_THREADS;
     for (int base = warp0;; base += stride) {
         if (next_batch) {
             int b = 0;
             if (lane == 0) b = atomicAdd(next_batch, 1);
-            base = __shfl_sync(0xffffffffu, b, 0) * 32;
+            base = item_lo + __shfl_sync(0xffffffffu, b, 0) * 32;
         }
         if (base >= n_items) break;
         int vbeg = 0, vcnt = 0;
@@ -103,7 +116,7 @@ __device__ __forceinline__ void for_each_cast_vote(const DevForest& f, const Fra
         const int item = base + lane;
         if (item < n_items) {
             const int p = item / f.T, t = item - p * f.T;
-            const int ord = lt.base[lt.world > 1 ? t % lt.world : 0][item];
+            const int ord = lt.base[lt.patch_world > 1 ? patch_shard_owner(Pp_all, lt.patch_world, p) : (lt.world > 1 ? t % lt.world : 0)][item];
             if (ord >= 0) {  // -1: tree owned by another rank (and no peer table given)
                 const int2 lv = __ldg(f.leaf_votes + __ldg(f.leaf_base + t) + ord);
                 vbeg = lv.x;
@@ -151,10 +164,12 @@ __device__ __forceinline__ void for_each_cast_vote(const DevForest& f, const Fra
 __global__ void __launch_bounds__(VOTE_THREADS)
 vote_kernel(DevForest f, FrameGeom g, const __grid_constant__ ObjectSwitches sw, const int* __restrict__ locs,
             const uint16_t* __restrict__ depth, const int* __restrict__ leaf_ord, const int* __restrict__ counts,
-            unsigned long long* __restrict__ maps, VoteStream stream) {
-    LeafTables lt;  // votes are cast for this rank's own trees only: the local table (foreign entries are -1)
+            unsigned long long* __restrict__ maps, VoteStream stream, PatchShard pshard) {
+    LeafTables lt;  // votes are cast for this rank's own trees / patches only: the local table (foreign entries are -1)
     lt.base[0] = leaf_ord;
     lt.world = 1;
+    lt.patch_world = 1;
+    lt.shard = pshard;
     __shared__ WarpItems s_items[VOTE_WARPS];
     __shared__ uint8_t s_detect[HF6D_MAX_CLASSES];
     if (threadIdx.x < HF6D_MAX_CLASSES) s_detect[threadIdx.x] = sw.should_detect[threadIdx.x];
@@ -490,7 +505,7 @@ __device__ __forceinline__ void z_mode_warp(const unsigned long long* __restrict
     __syncwarp();
 }
 
-constexpr int WS_ROWS = 4;  // stream rows (of 32 records) a warp grabs at a time
+constexpr int WS_ROWS = 8;  // stream rows (of 32 records) a warp grabs at a time
 template <int G>
 __global__ void __launch_bounds__(WA_THREADS)
 window_stream_kernel(DevForest f, FrameGeom g, const __grid_constant__ ObjectSwitches sw, VoteStream stream,
@@ -533,17 +548,6 @@ window_stream_kernel(DevForest f, FrameGeom g, const __grid_constant__ ObjectSwi
     WarpRing& ring = s_ring[threadIdx.x >> 5];
     const int n = min(*stream.n, stream.cap);
 
-    // One warp-wide, pre-aggregated update of the shared z histograms: lanes with `on` add `add` to bin `idx` (a position in
-    // s_z); lanes that hit the same bin are summed in registers and their leader issues one atomic (a trained forest sends
-    // every entry of an object's window into the same one or two bins: without this a warp-wide atomic serialises 32-fold).
-    auto add_z = [&](bool on, int idx, unsigned add, int slot_global, int zb) {
-        const unsigned peers = __match_any_sync(0xffffffffu, on ? (unsigned)idx : (0x80000000u | (unsigned)lane));
-        const unsigned sum = __reduce_add_sync(peers, on ? add : 0u);
-        if (on && lane == __ffs(peers) - 1) {
-            const unsigned old = atomicAdd(s_z + idx, sum);
-            if (old + sum < old) atomicAdd(zacc + (size_t)slot_global * HF6D_Z_BINS + zb, 1ull << 32);
-        }
-    };
     // bin of one vote of a leaf for a window pixel at depth zj (HFTest.cpp:770-775), unclamped / -1 outside the histogram
     auto z_bin_raw = [&](float oz, float zj) { return f2i_x86(div_const<1, 100>(__fadd_rn(oz, zj))); };  // integer part only
     auto z_bin = [&](float oz, float zj) {
@@ -581,66 +585,49 @@ window_stream_kernel(DevForest f, FrameGeom g, const __grid_constant__ ObjectSwi
                 }
             }
         }
-        // z histograms (HFTest.cpp:766-775): every vote of the entry's leaf, with the window pixel's depth as the patch centre.
-        // The bin is monotonic in the vote's oz, so when the smallest and the largest oz of the group fall into the same bin
-        // all its votes do: such entries are finished here, a lane each, without reading a vote.
-        const int c = (int)(cm >> 16);
+        // z histograms (HFTest.cpp:766-775): every vote of the entry's leaf lands in bin floor((oz + zz) / 0.01), zz = the window
+        // pixel's depth standing in for the patch centre.  The bin is monotonic in oz, so with the group's oz values sorted the
+        // votes of one bin are a contiguous run: the lane finds the run boundaries by bisection (the same float operations as
+        // the reference, evaluated on the candidate vote) and adds weight x run length once per bin -- one bin for most
+        // entries of a trained leaf, two when the leaf straddles a boundary -- instead of visiting every vote.
         const bool wants = have && zz >= 0.f && grp.w > 0;
-        int lo = 0, hi = 1;
-        if (wants) { lo = z_bin_raw(ozr.x, zz); hi = z_bin_raw(ozr.y, zz); }
-        const bool same = wants && lo == hi && !(ozr.x > ozr.y);  // (inf, -inf) marks an unordered group: always walked
-        const bool same_in = same && lo >= 0 && lo < HF6D_Z_BINS;
-        const unsigned wins = __reduce_or_sync(0xffffffffu, same_in ? (cm & 0xFFFFu) : 0u);
-        for (unsigned m = wins; m; m &= m - 1) {  // warp-uniform loop over the window ranks any such entry lies in
-            const int k = __ffs(m) - 1;
-            const bool on = same_in && ((cm >> k) & 1u);
-            add_z(on, (zt.zoff[c] + k) * HF6D_Z_BINS + lo, (unsigned)grp.y * (unsigned)grp.w, c * HF6D_MAX_CENTRES + k, lo);
-        }
-        // The others: the whole warp walks one entry's leaf votes at a time, lane q on vote q (coalesced), the loads of WALK
-        // entries issued together so that their latency is paid once per batch and not once per entry.
-        unsigned walk = __ballot_sync(0xffffffffu, wants && !same);
-        constexpr int WALK = 8;
-        while (walk) {
-            int src[WALK];
-            float ozv[WALK][2];
-            int vn_[WALK];
-#pragma unroll
-            for (int u = 0; u < WALK; ++u) {
-                src[u] = walk ? __ffs(walk) - 1 : -1;
-                if (walk) walk &= walk - 1;
-                const int from = max(src[u], 0);
-                const int vb = __shfl_sync(0xffffffffu, grp.z, from);
-                vn_[u] = src[u] < 0 ? 0 : __shfl_sync(0xffffffffu, grp.w, from);
-                ozv[u][0] = lane < vn_[u] ? __ldg(f.oz + vb + lane) : 0.f;
-                ozv[u][1] = lane + 32 < vn_[u] ? __ldg(f.oz + vb + lane + 32) : 0.f;
-            }
-#pragma unroll
-            for (int u = 0; u < WALK; ++u) {
-                if (src[u] < 0) break;  // warp-uniform
-                const float zj = __shfl_sync(0xffffffffu, zz, src[u]);
-                const unsigned w = (unsigned)__shfl_sync(0xffffffffu, grp.y, src[u]), cmj = __shfl_sync(0xffffffffu, cm, src[u]);
-                const int vb = __shfl_sync(0xffffffffu, grp.z, src[u]);
-                const int cj = (int)(cmj >> 16);
-                for (int q0 = 0; q0 < vn_[u]; q0 += 32) {
-                    const int q = q0 + lane;
-                    int zb = -1;
-                    if (q < vn_[u]) zb = z_bin(q0 == 0 ? ozv[u][0] : (q0 == 32 ? ozv[u][1] : __ldg(f.oz + vb + q)), zj);
-                    const unsigned in = __ballot_sync(0xffffffffu, zb >= 0);
-                    if (!in) continue;
-                    const int zb0 = __shfl_sync(0xffffffffu, zb, __ffs(in) - 1);
-                    const bool uniform = __ballot_sync(0xffffffffu, zb >= 0 && zb != zb0) == 0u;
-                    unsigned add = w;
-                    bool mine = zb >= 0;
-                    if (uniform) {  // one atomic for the 32 votes
-                        mine = lane == __ffs(in) - 1;
-                        add = w * (unsigned)__popc(in);
+        // (ordered: no NaN among the offsets; bounded: the bin stays inside the range where float -> int is monotonic)
+        if (wants && !(ozr.x > ozr.y) && fabsf(ozr.x) < 1e6f && fabsf(ozr.y) < 1e6f) {
+            const int c = (int)(cm >> 16);
+            const float* ozs = f.oz_sorted + grp.z;
+            const int hi = z_bin_raw(ozr.y, zz);
+            int b = z_bin_raw(ozr.x, zz), prev = 0;
+            while (prev < grp.w) {
+                int idx = grp.w;  // first vote beyond bin b
+                if (b < hi) {
+                    int lo_i = prev, hi_i = grp.w;  // invariant: bin(lo_i - 1) <= b < bin(hi_i)
+                    while (lo_i < hi_i) {
+                        const int mid = (lo_i + hi_i) >> 1;
+                        if (z_bin_raw(__ldg(ozs + mid), zz) > b) hi_i = mid; else lo_i = mid + 1;
                     }
-                    if (!mine) continue;
-                    for (unsigned m = cmj & 0xFFFFu; m; m &= m - 1) {
+                    idx = lo_i;
+                }
+                if (idx > prev && b >= 0 && b < HF6D_Z_BINS) {
+                    const unsigned add = (unsigned)grp.y * (unsigned)(idx - prev);
+                    for (unsigned m = cm & 0xFFFFu; m; m &= m - 1) {
                         const int k = __ffs(m) - 1;
-                        const unsigned old = atomicAdd(s_z + (zt.zoff[cj] + k) * HF6D_Z_BINS + zb, add);
-                        if (old + add < old) atomicAdd(zacc + (size_t)(cj * HF6D_MAX_CENTRES + k) * HF6D_Z_BINS + zb, 1ull << 32);
+                        const unsigned old = atomicAdd(s_z + (zt.zoff[c] + k) * HF6D_Z_BINS + b, add);
+                        if (old + add < old) atomicAdd(zacc + (size_t)(c * HF6D_MAX_CENTRES + k) * HF6D_Z_BINS + b, 1ull << 32);
                     }
+                }
+                if (idx >= grp.w) break;
+                prev = idx;
+                b = z_bin_raw(__ldg(ozs + idx), zz);  // the next occupied bin
+            }
+        } else if (wants) {  // a group with a NaN or absurd offset (never in a sane forest): vote by vote
+            const int c = (int)(cm >> 16);
+            for (int q = 0; q < grp.w; ++q) {
+                const int zb = z_bin(__ldg(f.oz + grp.z + q), zz);
+                if (zb < 0) continue;
+                for (unsigned m = cm & 0xFFFFu; m; m &= m - 1) {
+                    const int k = __ffs(m) - 1;
+                    const unsigned old = atomicAdd(s_z + (zt.zoff[c] + k) * HF6D_Z_BINS + zb, (unsigned)grp.y);
+                    if (old + (unsigned)grp.y < old) atomicAdd(zacc + (size_t)(c * HF6D_MAX_CENTRES + k) * HF6D_Z_BINS + zb, 1ull << 32);
                 }
             }
         }
@@ -904,6 +891,58 @@ roll_from_counts_kernel(DevForest f, const unsigned* __restrict__ cnt, int n_gro
 
 // The roll histograms from the pair list (see window_stream_kernel): G lanes per listed (slot, group) pair.  Last reader of
 // the pair's counter: zeroes it for the next frame.
+// One listed pair's contribution to the roll histograms of its slot's peaks; bn0 = the bins of vote `sub` (first pass).
+template <int G>
+__device__ __forceinline__ void roll_pair(const DevForest& f, int s, const int4& grp, unsigned c_hits, int np, const short4& bn0,
+                                          const PeakTable& pk, int half_box, unsigned long long* __restrict__ racc, int sub,
+                                          unsigned gmask) {
+    const int passes = (grp.w + G - 1) / G;
+    if (passes == 1) {
+        // the usual case (a group's votes fit the G lanes): every lane keeps its vote's bins in registers for all peaks
+        const bool have = sub < grp.w;
+        const int Y = (int)bn0.x + 360, P0 = (int)bn0.y + 360, r = bn0.z;
+        const int b0 = r + 360, b1 = r < 0 ? r + 720 : r;
+        for (int p = 0; p < np; ++p) {
+            const int2 yp = __ldg(reinterpret_cast<const int2*>(pk.peak_yx) + s * pk.max_peaks + p);
+            const bool in = have && Y >= yp.x - half_box && Y < yp.x + half_box && P0 >= yp.y - half_box && P0 < yp.y + half_box;
+            const int inbox = __popc(__ballot_sync(gmask, in));
+            if (inbox == 0 || !have) continue;
+            const unsigned long long wk = (unsigned long long)(unsigned)grp.y * c_hits * (unsigned long long)inbox;
+            unsigned long long* rs = racc + ((size_t)s * pk.max_peaks + p) * HF6D_POSE_BINS;
+            if (b0 >= 0 && b0 < HF6D_POSE_BINS) atomicAdd(rs + b0, wk);
+            if (b1 >= 0 && b1 < HF6D_POSE_BINS) atomicAdd(rs + b1, wk);
+        }
+        return;
+    }
+    for (int p = 0; p < np; ++p) {
+        const int Yp = __ldg(pk.peak_yx + (s * pk.max_peaks + p) * 2), Pp = __ldg(pk.peak_yx + (s * pk.max_peaks + p) * 2 + 1);
+        int inbox = 0;
+        for (int ps = 0; ps < passes; ++ps) {
+            const int q = ps * G + sub;
+            bool in = false;
+            if (q < grp.w) {
+                const short4 bn = ps == 0 ? bn0 : __ldg(f.bins + grp.z + q);
+                const int Y = (int)bn.x + 360, P0 = (int)bn.y + 360;
+                in = Y >= Yp - half_box && Y < Yp + half_box && P0 >= Pp - half_box && P0 < Pp + half_box;
+            }
+            inbox += __popc(__ballot_sync(gmask, in));
+        }
+        if (inbox == 0) continue;
+        const unsigned long long wk = (unsigned long long)(unsigned)grp.y * c_hits * (unsigned long long)inbox;
+        unsigned long long* rs = racc + ((size_t)s * pk.max_peaks + p) * HF6D_POSE_BINS;
+        for (int q = sub; q < grp.w; q += G) {
+            const int r = q == sub ? bn0.z : __ldg(f.bins + grp.z + q).z;
+            const int b0 = r + 360, b1 = r < 0 ? r + 720 : r;
+            if (b0 >= 0 && b0 < HF6D_POSE_BINS) atomicAdd(rs + b0, wk);
+            if (b1 >= 0 && b1 < HF6D_POSE_BINS) atomicAdd(rs + b1, wk);
+        }
+    }
+}
+
+// The roll histograms from the pair list (see window_stream_kernel): G lanes per listed (slot, group) pair, two pairs per
+// step -- a pair is a chain of three dependent loads (pair -> counter / group -> votes) and the kernel is bound by their
+// latency (ncu: 12 % issue utilisation at full occupancy with one pair per step).  Last reader of a pair's counter: zeroes
+// it for the next frame.
 template <int G>
 __global__ void __launch_bounds__(TABLE_THREADS)
 roll_from_pairs_kernel(DevForest f, unsigned* __restrict__ cnt, int n_groups, PairList pl, PeakTable pk, int half_box,
@@ -912,60 +951,29 @@ roll_from_pairs_kernel(DevForest f, unsigned* __restrict__ cnt, int n_groups, Pa
     const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << (part * G));
     const int n = min(*pl.n, pl.cap);
     const int stride = gridDim.x * TABLE_THREADS / G;
-    for (int e = (blockIdx.x * TABLE_THREADS + threadIdx.x) / G; e < n; e += stride) {
-        const uint2 pr = __ldg(pl.pairs + e);
-        const int s = (int)pr.x, gi = (int)pr.y;
-        unsigned c_hits = 0;
+    for (int e0 = (blockIdx.x * TABLE_THREADS + threadIdx.x) / G; e0 < n; e0 += 2 * stride) {
+        const int e1 = e0 + stride;
+        const bool two = e1 < n;  // uniform within the G lanes
+        const uint2 pr0 = __ldg(pl.pairs + e0), pr1 = two ? __ldg(pl.pairs + e1) : make_uint2(0u, 0u);
+        const int s0 = (int)pr0.x, g0 = (int)pr0.y, s1 = (int)pr1.x, g1 = (int)pr1.y;
+        unsigned c0 = 0, c1 = 0;
         if (sub == 0) {
-            unsigned* cp = cnt + (size_t)s * n_groups + gi;
-            c_hits = __ldcg(cp);
-            *cp = 0u;  // last reader: the table is zero again for the next frame
+            unsigned* cp0 = cnt + (size_t)s0 * n_groups + g0;
+            unsigned* cp1 = cnt + (size_t)s1 * n_groups + g1;
+            c0 = __ldcg(cp0);
+            if (two) c1 = __ldcg(cp1);
+            *cp0 = 0u;  // last reader: the table is zero again for the next frame
+            if (two) *cp1 = 0u;
         }
-        c_hits = __shfl_sync(gmask, c_hits, part * G);
-        const int np = __ldg(pk.n_peaks + s);
-        if (np == 0) continue;
-        const int4 grp = __ldg(reinterpret_cast<const int4*>(f.groups) + gi);
-        const int passes = (grp.w + G - 1) / G;
-        if (passes == 1) {
-            const bool have = sub < grp.w;
-            const short4 bn = have ? __ldg(f.bins + grp.z + sub) : make_short4(0, 0, 0, 0);
-            const int Y = (int)bn.x + 360, P0 = (int)bn.y + 360, r = bn.z;
-            const int b0 = r + 360, b1 = r < 0 ? r + 720 : r;
-            for (int p = 0; p < np; ++p) {
-                const int2 yp = __ldg(reinterpret_cast<const int2*>(pk.peak_yx) + s * pk.max_peaks + p);
-                const bool in = have && Y >= yp.x - half_box && Y < yp.x + half_box && P0 >= yp.y - half_box && P0 < yp.y + half_box;
-                const int inbox = __popc(__ballot_sync(gmask, in));
-                if (inbox == 0 || !have) continue;
-                const unsigned long long wk = (unsigned long long)(unsigned)grp.y * c_hits * (unsigned long long)inbox;
-                unsigned long long* rs = racc + ((size_t)s * pk.max_peaks + p) * HF6D_POSE_BINS;
-                if (b0 >= 0 && b0 < HF6D_POSE_BINS) atomicAdd(rs + b0, wk);
-                if (b1 >= 0 && b1 < HF6D_POSE_BINS) atomicAdd(rs + b1, wk);
-            }
-            continue;
-        }
-        for (int p = 0; p < np; ++p) {
-            const int Yp = __ldg(pk.peak_yx + (s * pk.max_peaks + p) * 2), Pp = __ldg(pk.peak_yx + (s * pk.max_peaks + p) * 2 + 1);
-            int inbox = 0;
-            for (int ps = 0; ps < passes; ++ps) {
-                const int q = ps * G + sub;
-                bool in = false;
-                if (q < grp.w) {
-                    const short4 bn = __ldg(f.bins + grp.z + q);
-                    const int Y = (int)bn.x + 360, P0 = (int)bn.y + 360;
-                    in = Y >= Yp - half_box && Y < Yp + half_box && P0 >= Pp - half_box && P0 < Pp + half_box;
-                }
-                inbox += __popc(__ballot_sync(gmask, in));
-            }
-            if (inbox == 0) continue;
-            const unsigned long long wk = (unsigned long long)(unsigned)grp.y * c_hits * (unsigned long long)inbox;
-            unsigned long long* rs = racc + ((size_t)s * pk.max_peaks + p) * HF6D_POSE_BINS;
-            for (int q = sub; q < grp.w; q += G) {
-                const int r = __ldg(f.bins + grp.z + q).z;
-                const int b0 = r + 360, b1 = r < 0 ? r + 720 : r;
-                if (b0 >= 0 && b0 < HF6D_POSE_BINS) atomicAdd(rs + b0, wk);
-                if (b1 >= 0 && b1 < HF6D_POSE_BINS) atomicAdd(rs + b1, wk);
-            }
-        }
+        const int np0 = __ldg(pk.n_peaks + s0), np1 = two ? __ldg(pk.n_peaks + s1) : 0;
+        const int4 grp0 = __ldg(reinterpret_cast<const int4*>(f.groups) + g0);
+        const int4 grp1 = two ? __ldg(reinterpret_cast<const int4*>(f.groups) + g1) : make_int4(0, 0, 0, 0);
+        const short4 bn0 = (np0 && sub < grp0.w) ? __ldg(f.bins + grp0.z + sub) : make_short4(0, 0, 0, 0);
+        const short4 bn1 = (np1 && sub < grp1.w) ? __ldg(f.bins + grp1.z + sub) : make_short4(0, 0, 0, 0);
+        c0 = __shfl_sync(gmask, c0, part * G);
+        c1 = __shfl_sync(gmask, c1, part * G);
+        if (np0) roll_pair<G>(f, s0, grp0, c0, np0, bn0, pk, half_box, racc, sub, gmask);
+        if (np1) roll_pair<G>(f, s1, grp1, c1, np1, bn1, pk, half_box, racc, sub, gmask);
     }
 }
 

@@ -1,4 +1,15 @@
-"""Tree-sharded detection across the GPUs of one box: one process per GPU, torch.distributed for the plumbing.
+"""One stream of frames sharded across the GPUs of one box: one process per GPU, torch.distributed for the plumbing.
+
+Two splits of a frame's work (TreeShardedDetector(split=...)):
+
+  "trees"    the north star's: rank r owns trees {t : t % N == r} (below).  Scan, gather and encode are REPLICATED (every
+             rank needs every patch's features), so the gain stops at ~1.4x however many GPUs there are.
+  "patches"  rank r owns a contiguous share of the frame's patches (128-patch row blocks, in the reference's patch order --
+             its batches of 100 already run in an OpenMP loop, HFTest.cpp:612): gather, encode, traverse (all trees; the
+             forest is a few MB) and vote shard with them, only the scan (0.02 ms) is replicated.  Same exchange, same
+             class-sharded mode seeking afterwards.  This is the split that scales.
+
+The rest of this text describes the tree split; the patch split differs only in what a rank's partial maps / leaf table hold.
 
 The reference's voting loop runs trees outermost (HoughForest/src/HFTest.cpp:177) and trees interact only through the
 per-class vote maps and the centre->leaf back-map, so rank r of N owns trees {t : t % N == r}:
@@ -37,6 +48,13 @@ def owned_trees(rank: int, world: int, T: int):
     return [t for t in range(T) if t % world == rank]
 
 
+def owned_patches(rank: int, world: int, Pp: int):
+    """[lo, hi) of the frame's Pp processed patches that rank `rank` gathers, encodes, traverses and votes (the rule
+    hf6d_set_patch_shard implements on the device side: cuts on multiples of 128 patches)."""
+    mb = (Pp + 127) // 128
+    return min(Pp, mb * rank // world * 128), min(Pp, mb * (rank + 1) // world * 128)
+
+
 def exchange(maps, leaf_table, group=None):
     """The path's one exchange step: in-place SUM of the vote maps and MAX of the leaf table across the group.
 
@@ -55,15 +73,22 @@ class TreeShardedDetector:
     """This rank's libhf6d context plus the exchange.  Construct it on every rank after init_process_group."""
 
     def __init__(self, forest_dir, weights_path, params=None, device=0, n_slots=2, group=None, shard_classes=True,
-                 exchange="nccl"):
+                 exchange="nccl", split="trees"):
         import torch
         import torch.distributed as dist
+        if split not in ("trees", "patches"):
+            raise ValueError("split must be 'trees' or 'patches'")
         self.torch = torch
         self.group = group
+        self.split = split
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.det = api.Detector(forest_dir, weights_path, params, device=device, n_slots=n_slots)
-        self.det.set_tree_shard(self.rank, self.world)
+        if split == "patches":
+            self.det.set_patch_shard(self.rank, self.world)
+            self.det.set_peer_split(1)
+        else:
+            self.det.set_tree_shard(self.rank, self.world)
         self.shard_classes = bool(shard_classes) and self.world > 1
         if self.shard_classes:
             self.det.set_class_shard(self.rank, self.world)
@@ -102,7 +127,7 @@ class TreeShardedDetector:
 
     @property
     def trees(self):
-        return owned_trees(self.rank, self.world, self.det.T)
+        return list(range(self.det.T)) if self.split == "patches" else owned_trees(self.rank, self.world, self.det.T)
 
     @property
     def classes(self):

@@ -3,7 +3,7 @@ its OWN fp32 encoder (the reference's Caffe forward is fp32 sgemm, HoughForest/s
 
 Every other GPU test isolates the encoder by feeding the oracle the GPU's feature matrix; this one does not.  It answers
 the north star's acceptance clause -- leaf indices and final poses against the reference CPU path on identical inputs --
-for both encoder modes, and writes the numbers to gpurun_out/r02_parity.json (committed under profiles/):
+for the three encoder modes (bf16 operands, split bf16, fp16 operands), and writes the numbers to gpurun_out/r02_parity.json (committed under profiles/):
 
   leaf agreement          fraction of (patch, tree) pairs that reach the same leaf
   tuples reproduced       fraction of the oracle's hypothesis tuples (class, centre px, z cm, yaw/pitch/roll deg) that the
@@ -113,10 +113,10 @@ def report(workload):
     rep = {"workload": "BASELINE configs[1]: 6-object forest trained on labelled synthetic patches (T=4, depth<=20, ~16 votes per "
                        "leaf, coherent votes), 640x480, fill random; %d frames" % len(workload["frames"]), "forest": workload["stats"],
            "oracle": "oracle/hf6d_oracle.c with its own fp32 encoder (8 interleaved partial sums, expf sigmoid)", "frames": []}
-    runs = {0: _gpu_run(workload, 0), 1: _gpu_run(workload, 1)}
+    runs = {0: _gpu_run(workload, 0), 1: _gpu_run(workload, 1), 2: _gpu_run(workload, 2)}
     for i, ref in enumerate(workload["refs"]):
         row = {"patches": int(ref["feat"].shape[0])}
-        for mode, name in ((0, "gpu_bf16"), (1, "gpu_split_bf16")):
+        for mode, name in ((0, "gpu_bf16"), (1, "gpu_split_bf16"), (2, "gpu_fp16")):
             g = runs[mode][i]
             assert np.array_equal(g["q"], ref["q"]), "quantised patches must be bit-exact before the encoder"
             row[name] = _compare(name, g["feat"], g["leaf"], g["hyp"], ref)
@@ -155,6 +155,15 @@ def test_bf16_encoder_end_to_end_numbers_are_published(report):
         assert r["leaf_agreement"] >= BF16_LEAF_AGREEMENT
         assert r["feature_max_abs_err"] < 3e-2
         assert r["tuples_within_one_bin"] > 0.5
+
+
+def test_fp16_encoder_end_to_end_numbers_are_published(report):
+    """Mode 2 (fp16 operands, the same kernel and rate as bf16): 11-bit significands, so it must sit between the two."""
+    for row in report["frames"]:
+        r, b = row["gpu_fp16"], row["gpu_bf16"]
+        assert r["feature_max_abs_err"] < 4e-3 and r["feature_mean_abs_err"] < b["feature_mean_abs_err"] / 4
+        assert r["leaf_agreement"] > b["leaf_agreement"]
+        assert r["tuples_reproduced"] >= b["tuples_reproduced"]
 
 
 def test_split_mode_is_deterministic_and_switchable(workload):

@@ -26,7 +26,18 @@ def test_owned_trees_partition():
             assert max(len(x) for x in parts) - min(len(x) for x in parts) <= 1
 
 
-def _gloo_worker(rank, world, port, tmpdir, out_q):
+def test_owned_patches_partition():
+    from object_detector_6d_b200.sharded import owned_patches
+    for Pp in (0, 100, 128, 129, 70900, 290600):
+        for world in (1, 2, 3, 4, 8):
+            parts = [owned_patches(r, world, Pp) for r in range(world)]
+            assert parts[0][0] == 0 and parts[-1][1] == Pp
+            for (a0, a1), (b0, b1) in zip(parts, parts[1:]):
+                assert a1 == b0 and a0 <= a1
+            assert all(lo % 128 == 0 for lo, _ in parts)
+
+
+def _gloo_worker(rank, world, port, tmpdir, out_q, split="trees"):
     sys.path.insert(0, ROOT)
     import torch
     import torch.distributed as dist
@@ -45,10 +56,14 @@ def _gloo_worker(rank, world, port, tmpdir, out_q):
         Pp = (len(locs) // p.batch_size) * p.batch_size
         feats = O.encode(O.normalise(O.gather(cs["bgr"], cs["depth"], p, locs[:Pp])), cs["layers"])
         _, ords = O.traverse(forest, feats)
-        # this rank's shard: foreign trees are -1, exactly what traverse_kernel writes on the device
-        mine = sharded.owned_trees(rank, world, forest.T)
+        # this rank's shard: foreign trees / patches are -1, exactly what the device leaves in its leaf table
         part = np.full_like(ords, -1)
-        part[:, mine] = ords[:, mine]
+        if split == "patches":
+            lo, hi = sharded.owned_patches(rank, world, Pp)
+            part[lo:hi] = ords[lo:hi]
+        else:
+            mine = sharded.owned_trees(rank, world, forest.T)
+            part[:, mine] = ords[:, mine]
         maps_part, _ = O.vote(forest, part, locs[:Pp], cs["depth"], p)
         t_maps = torch.from_numpy(maps_part.view(np.int64).copy())
         t_leaf = torch.from_numpy(part.copy())
@@ -65,13 +80,14 @@ def _gloo_worker(rank, world, port, tmpdir, out_q):
         dist.destroy_process_group()
 
 
-def test_exchange_with_gloo_world_size_2(tmp_path):
-    """Each rank votes only its own trees (oracle arithmetic); after the exchange both hold the full maps / table."""
+@pytest.mark.parametrize("split", ["trees", "patches"])
+def test_exchange_with_gloo_world_size_2(tmp_path, split):
+    """Each rank votes only its own trees / patches (oracle arithmetic); after the exchange both hold the full maps / table."""
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, str(tmp_path), q)) for r in range(2)]
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, str(tmp_path), q, split)) for r in range(2)]
     for pr in procs:
         pr.start()
     res = [q.get(timeout=600) for _ in procs]
@@ -84,7 +100,7 @@ def test_exchange_with_gloo_world_size_2(tmp_path):
 
 
 # ------------------------------------------------------------------------------------------------ GPU, NCCL
-def _nccl_worker(rank, world, port, tmpdir, out_q, mode="nccl"):
+def _nccl_worker(rank, world, port, tmpdir, out_q, mode="nccl", split="trees"):
     sys.path.insert(0, ROOT)
     import torch
     import torch.distributed as dist
@@ -101,7 +117,7 @@ def _nccl_worker(rank, world, port, tmpdir, out_q, mode="nccl"):
         maps_single = single.fetch(api.BUF_MAPS)
         leaf_single = single.fetch(api.BUF_LEAF_ORD)
         single.close()
-        sd = sharded.TreeShardedDetector(cs["forest_dir"], cs["weights"], p, device=rank, n_slots=2, exchange=mode)
+        sd = sharded.TreeShardedDetector(cs["forest_dir"], cs["weights"], p, device=rank, n_slots=2, exchange=mode, split=split)
         hyp = sd.detect(cs["bgr"], cs["depth"], slot=1)
         if mode == "peer":  # several frames through both slots: the flags must keep the ranks in step
             for i in range(6):
@@ -115,8 +131,12 @@ def _nccl_worker(rank, world, port, tmpdir, out_q, mode="nccl"):
         same = len(hyp) == len(hyp_single) and len(hyp) > 0 and all(
             np.array_equal(hyp[n], hyp_single[n]) for n in hyp.dtype.names)
         if mode == "peer":  # the local buffers stay partial: the sums exist only inside the kernels that read the peers
-            mine = sharded.owned_trees(rank, world, leaf_single.shape[1])
-            ok_leaf = bool(np.array_equal(leaf[:, mine], leaf_single[:, mine]))
+            if split == "patches":
+                lo, hi = sharded.owned_patches(rank, world, leaf_single.shape[0])
+                ok_leaf = bool(np.array_equal(leaf[lo:hi], leaf_single[lo:hi]))
+            else:
+                mine = sharded.owned_trees(rank, world, leaf_single.shape[1])
+                ok_leaf = bool(np.array_equal(leaf[:, mine], leaf_single[:, mine]))
             out_q.put((rank, True, ok_leaf, same, n_launch))
         else:
             out_q.put((rank, bool(np.array_equal(maps, maps_single)), bool(np.array_equal(leaf, leaf_single)), same,
@@ -126,7 +146,8 @@ def _nccl_worker(rank, world, port, tmpdir, out_q, mode="nccl"):
 
 
 @pytest.mark.gpu
-def test_tree_sharded_nccl_equals_single_gpu(tmp_path):
+@pytest.mark.parametrize("split", ["trees", "patches"])
+def test_tree_sharded_nccl_equals_single_gpu(tmp_path, split):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
@@ -134,7 +155,7 @@ def test_tree_sharded_nccl_equals_single_gpu(tmp_path):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, str(tmp_path), q)) for r in range(2)]
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, str(tmp_path), q, "nccl", split)) for r in range(2)]
     for pr in procs:
         pr.start()
     res = [q.get(timeout=900) for _ in procs]
@@ -147,7 +168,8 @@ def test_tree_sharded_nccl_equals_single_gpu(tmp_path):
 
 
 @pytest.mark.gpu
-def test_tree_sharded_peer_exchange_equals_single_gpu(tmp_path):
+@pytest.mark.parametrize("split", ["trees", "patches"])
+def test_tree_sharded_peer_exchange_equals_single_gpu(tmp_path, split):
     """The same, with the exchange done by the kernels themselves over peer memory (no NCCL collective on the data path)."""
     import torch
     if torch.cuda.device_count() < 2:
@@ -156,7 +178,7 @@ def test_tree_sharded_peer_exchange_equals_single_gpu(tmp_path):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, str(tmp_path), q, "peer")) for r in range(2)]
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, str(tmp_path), q, "peer", split)) for r in range(2)]
     for pr in procs:
         pr.start()
     res = [q.get(timeout=900) for _ in procs]
