@@ -695,6 +695,9 @@ def main():
                          "2: fp16 operands (same rate as 0)")
     ap.add_argument("--tree-timeout", type=int, default=240, help="seconds the sharded arm (N > 1) may take")
     args = ap.parse_args()
+    if os.environ.get("HF6D_BENCH_WATCHDOG"):  # debugging aid: dump every thread's stack and exit if the run takes this long
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ["HF6D_BENCH_WATCHDOG"]), exit=True)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
