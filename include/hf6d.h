@@ -274,6 +274,78 @@ int64_t hf6d_debug_texture_gather(hf6d_ctx* c, int slot, float* dst, size_t cap_
 void hf6d_pose_from_tuple(const hf6d_params* p, int cx, int cy, float z, int yaw_deg, int pitch_deg, int roll_deg,
                           float pose[16]);
 
+/* ---------------------------------------------------------------------------------------------- refinement
+ * What HFTest::test_image does with every hypothesis tuple after the Hough stage (HoughForest/src/HFTest.cpp:922-994) and what
+ * HFTest::DetectObjects does with the result (HFTest.cpp:1261-1303):
+ *
+ *   reference interface                                              replaced by
+ *   MeshUtils::setIntrinsics / setReg / setGroupReg / set*Threshold /
+ *     setClusteringOptions / useColorSimilarity / searchSingle*      hf6d_set_refine_params   (HFTest.cpp:1203-1225)
+ *   MeshUtils::insertObjectFromPLY   HoughForest/include/MeshUtils.h:213  hf6d_load_object_ply / hf6d_set_object_model
+ *   MeshUtils::setScene              HoughForest/src/MeshUtils.cpp:340     hf6d_refine (first step, on the slot's frame)
+ *   MeshUtils::icp                   MeshUtils.cpp:423                     hf6d_refine (pose refinement of every tuple)
+ *   MeshUtils::evaluate_hypothesis   MeshUtils.cpp:629                     hf6d_refine (scores + acceptance)
+ *   MeshUtils::optimize_hypotheses   MeshUtils.cpp:1160                    hf6d_refine (selection)
+ *   the instance cap of the output loop  HFTest.cpp:1269-1273              hf6d_detection.rank
+ *
+ * The arithmetic the reference leaves to PCL 1.7 (VoxelGrid, NormalEstimation, KdTree, IterativeClosestPoint) is restated
+ * from PCL's published algorithms; oracle/refine.py lists the choices.  All of it runs on the GPU; the host enumerates the
+ * solution vectors of a hypothesis group (MeshUtils::get_next_solution_vector) and picks the best from the GPU's counts. */
+typedef struct {
+    float scene_leaf_m, object_leaf_m;   /* VoxelGrid leaf sizes (MeshUtils.h:140-141: 0.005) */
+    float normals_radius_m;              /* MeshUtils.cpp:198: 0.03 */
+    float nn_search_radius_m;            /* MeshUtils.h:127: 0.01 -- search radius of objects without their own, and the divisor of the depth score */
+    float occlusion_threshold_m;         /* MeshUtils.h:128: 0.02 */
+    float similarity_coeff, inliers_coeff, clutter_coeff, location_score_coeff, pose_score_coeff;  /* Options.*_coeff */
+    float group_total_explain_coeff, group_common_explain_coeff;
+    float inliers_threshold, clutter_threshold, final_score_threshold;
+    float cluster_eps_angle_threshold, cluster_curvature_threshold, cluster_tolerance_near, cluster_tolerance_far;
+    int32_t cluster_min_points;
+    int32_t use_color_similarity, use_normal_similarity;
+    int32_t search_single_object_instance, search_single_object_in_group;
+    int32_t default_icp_iterations;      /* detector_options.proto:11: 60 */
+} hf6d_refine_params;
+
+typedef struct {
+    int32_t hypothesis;                  /* index into the hypothesis list handed to hf6d_refine */
+    int32_t cls;
+    float pose[16];                      /* refined 4x4, row-major, camera frame (the Hough pose when ICP did not converge) */
+    float similarity, inliers_ratio, clutter, location_score, pose_score, final_score;  /* MeshUtils::HypothesisEvaluation */
+    int32_t icp_converged, icp_iterations;
+    int32_t visible, inliers, explained; /* visible model points, points with a scene neighbour, scene points explained */
+    int32_t accepted;                    /* evaluate_hypothesis returned true */
+    int32_t selected;                    /* chosen by optimize_hypotheses */
+    int32_t rank;                        /* position in the output of DetectObjects (final score order, at most `instances`
+                                            per object), -1 when not written */
+} hf6d_detection;
+
+typedef enum {
+    HF6D_RBUF_SCENE_POINTS = 0,   /* float[S][4] = x, y, z, bits r | g << 8 | b << 16: the down-sampled scene after normals_not_nan */
+    HF6D_RBUF_SCENE_NORMALS = 1,  /* float[S][4] = nx, ny, nz, curvature */
+    HF6D_RBUF_SCENE_LABELS = 2,   /* int32[S] smooth-cluster id, -1 = none */
+    HF6D_RBUF_CLUSTER_SIZES = 3,  /* int32[n_clusters] */
+    HF6D_RBUF_MODEL_POINTS = 4,   /* float[M][4] of object `arg` (down-sampled, normals_not_nan applied) */
+    HF6D_RBUF_MODEL_NORMALS = 5   /* float[M][4] of object `arg`: normals re-estimated on that cloud (NaN rows are dropped by the scoring) */
+} hf6d_refine_buffer;
+
+void hf6d_default_refine_params(hf6d_refine_params* p);
+int hf6d_set_refine_params(hf6d_ctx* c, const hf6d_refine_params* p); /* before the models are set: they depend on the leaf size */
+int hf6d_get_refine_params(const hf6d_ctx* c, hf6d_refine_params* out);
+/* Vertices of the object's mesh as MeshUtils::getPointCloudFromPLY reads them: xyz float[n][3] metres (object frame),
+ * rgb uint8[n][3].  nn_search_radius / icp_iterations: ObjectOptions values, -1 = not given (MeshUtils.h:239-245). */
+int hf6d_set_object_model(hf6d_ctx* c, int cls, const float* xyz, const uint8_t* rgb, int n, float nn_search_radius,
+                          int icp_iterations);
+int hf6d_load_object_ply(hf6d_ctx* c, int cls, const char* ply_path, float nn_search_radius, int icp_iterations);
+/* Refines and scores the n hypotheses (as hf6d_collect / hf6d_wait / hf6d_detect returned them) against the frame the slot
+ * still holds (hf6d_detect: slot 0; ticket t: slot t % n_slots, until the next submit reuses it), then selects.  Writes one
+ * hf6d_detection per hypothesis, in input order.  Synchronous.  Every detected class needs a model. */
+int hf6d_refine(hf6d_ctx* c, int slot, const hf6d_hypothesis* hyps, int n, hf6d_detection* out, int cap, int* n_out);
+/* Milliseconds of the last hf6d_refine: ms[0] scene (cloud, VoxelGrid, normals, clusters), ms[1] ICP, ms[2] scoring,
+ * ms[3] joint optimisation (GPU kernels + host enumeration). */
+int hf6d_refine_ms(hf6d_ctx* c, float ms[4]);
+/* Copies a buffer of the last hf6d_refine (or of a model) to the host; returns bytes written, or < 0. */
+int64_t hf6d_refine_fetch(hf6d_ctx* c, int what, int arg, void* dst, size_t cap_bytes);
+
 #ifdef __cplusplus
 }
 #endif

@@ -30,6 +30,8 @@ EXPORTS = (
     "hf6d_fetch", "hf6d_inject", "hf6d_device_ptr", "hf6d_set_stream", "hf6d_stage_ms", "hf6d_launch_count",
     "hf6d_pose_from_tuple", "hf6d_count_cast_votes", "hf6d_bind_frame", "hf6d_encoder_layer_ms", "hf6d_result_bytes",
     "hf6d_parse_options", "hf6d_inspect_forest", "hf6d_inspect_weights", "hf6d_debug_texture_gather",
+    "hf6d_default_refine_params", "hf6d_set_refine_params", "hf6d_get_refine_params", "hf6d_set_object_model",
+    "hf6d_load_object_ply", "hf6d_refine", "hf6d_refine_ms", "hf6d_refine_fetch",
 )
 
 
@@ -60,6 +62,26 @@ class Options(C.Structure):
                 ("caffe_weights", C.c_char * 1024), ("caffe_definition", C.c_char * 1024),
                 ("location_score_coeff", C.c_float), ("pose_score_coeff", C.c_float)]
 
+
+class RefineParams(C.Structure):
+    """hf6d_refine_params: MeshUtils' settings (HoughForest/include/MeshUtils.h:115-156, HFTest.cpp:1203-1225)."""
+    _fields_ = [("scene_leaf_m", C.c_float), ("object_leaf_m", C.c_float), ("normals_radius_m", C.c_float),
+                ("nn_search_radius_m", C.c_float), ("occlusion_threshold_m", C.c_float), ("similarity_coeff", C.c_float),
+                ("inliers_coeff", C.c_float), ("clutter_coeff", C.c_float), ("location_score_coeff", C.c_float),
+                ("pose_score_coeff", C.c_float), ("group_total_explain_coeff", C.c_float),
+                ("group_common_explain_coeff", C.c_float), ("inliers_threshold", C.c_float), ("clutter_threshold", C.c_float),
+                ("final_score_threshold", C.c_float), ("cluster_eps_angle_threshold", C.c_float),
+                ("cluster_curvature_threshold", C.c_float), ("cluster_tolerance_near", C.c_float),
+                ("cluster_tolerance_far", C.c_float), ("cluster_min_points", C.c_int32), ("use_color_similarity", C.c_int32),
+                ("use_normal_similarity", C.c_int32), ("search_single_object_instance", C.c_int32),
+                ("search_single_object_in_group", C.c_int32), ("default_icp_iterations", C.c_int32)]
+
+
+DETECTION_DTYPE = np.dtype([("hypothesis", "<i4"), ("cls", "<i4"), ("pose", "<f4", (16,)), ("similarity", "<f4"),
+                            ("inliers_ratio", "<f4"), ("clutter", "<f4"), ("location_score", "<f4"), ("pose_score", "<f4"),
+                            ("final_score", "<f4"), ("icp_converged", "<i4"), ("icp_iterations", "<i4"), ("visible", "<i4"),
+                            ("inliers", "<i4"), ("explained", "<i4"), ("accepted", "<i4"), ("selected", "<i4"), ("rank", "<i4")])
+RBUF_SCENE_POINTS, RBUF_SCENE_NORMALS, RBUF_SCENE_LABELS, RBUF_CLUSTER_SIZES, RBUF_MODEL_POINTS, RBUF_MODEL_NORMALS = range(6)
 
 HYP_DTYPE = np.dtype([("cls", "<i4"), ("cx", "<i4"), ("cy", "<i4"), ("z", "<f4"), ("yaw_deg", "<i4"),
                       ("pitch_deg", "<i4"), ("roll_deg", "<i4"), ("loc_score", "<f4"), ("yawpitch_score", "<f4"),
@@ -145,6 +167,16 @@ def load():
     L.hf6d_parse_options.argtypes = [C.c_char_p, C.POINTER(Options), C.POINTER(ObjectOptions), i32]
     L.hf6d_inspect_forest.argtypes = [C.c_char_p, C.POINTER(ModelInfo)]
     L.hf6d_inspect_weights.argtypes = [C.c_char_p, C.POINTER(C.c_int32)]
+    L.hf6d_default_refine_params.argtypes = [C.POINTER(RefineParams)]
+    L.hf6d_default_refine_params.restype = None
+    L.hf6d_set_refine_params.argtypes = [vp, C.POINTER(RefineParams)]
+    L.hf6d_get_refine_params.argtypes = [vp, C.POINTER(RefineParams)]
+    L.hf6d_set_object_model.argtypes = [vp, i32, vp, vp, i32, C.c_float, i32]
+    L.hf6d_load_object_ply.argtypes = [vp, i32, C.c_char_p, C.c_float, i32]
+    L.hf6d_refine.argtypes = [vp, i32, vp, i32, vp, i32, C.POINTER(i32)]
+    L.hf6d_refine_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    L.hf6d_refine_fetch.argtypes = [vp, i32, i32, vp, C.c_size_t]
+    L.hf6d_refine_fetch.restype = i64
     _lib = L
     return L
 
@@ -238,6 +270,53 @@ class Detector:
         self.n_slots = n_slots
         self.T, self.K, self.F = self.model.T, self.model.K, self.model.F
         self.W, self.H = self.params.W, self.params.H
+
+    # ------------------------------------------------------------------ stage REFINE
+    def refine_params(self) -> RefineParams:
+        p = RefineParams()
+        self._ck(self._L.hf6d_get_refine_params(self._h, C.byref(p)))
+        return p
+
+    def set_refine_params(self, p: RefineParams = None, **kw):
+        """MeshUtils::setReg / setGroupReg / set*Threshold / setClusteringOptions / ... (HFTest.cpp:1203-1225)."""
+        p = p if p is not None else self.refine_params()
+        for k, v in kw.items():
+            setattr(p, k, v)
+        self._ck(self._L.hf6d_set_refine_params(self._h, C.byref(p)))
+
+    def set_object_model(self, cls: int, xyz, rgb, nn_search_radius: float = -1.0, icp_iterations: int = -1):
+        """MeshUtils::insertObjectFromPLY (MeshUtils.h:213-247) from vertices in memory."""
+        xyz = np.ascontiguousarray(xyz, np.float32).reshape(-1, 3)
+        rgb = np.ascontiguousarray(rgb, np.uint8).reshape(-1, 3)
+        assert len(xyz) == len(rgb)
+        self._ck(self._L.hf6d_set_object_model(self._h, cls, xyz.ctypes.data, rgb.ctypes.data, len(xyz), nn_search_radius,
+                                               icp_iterations))
+
+    def load_object_ply(self, cls: int, path: str, nn_search_radius: float = -1.0, icp_iterations: int = -1):
+        self._ck(self._L.hf6d_load_object_ply(self._h, cls, path.encode(), nn_search_radius, icp_iterations))
+
+    def refine(self, hyps, slot: int = 0):
+        """ICP + evaluate_hypothesis + optimize_hypotheses for the hypotheses of the frame the slot holds
+        (HFTest.cpp:922-994, 1261-1273).  Returns a DETECTION_DTYPE array, one row per hypothesis."""
+        hyps = np.ascontiguousarray(hyps, HYP_DTYPE)
+        out = np.zeros(max(len(hyps), 1), DETECTION_DTYPE)
+        n = C.c_int(0)
+        self._ck(self._L.hf6d_refine(self._h, slot, hyps.ctypes.data, len(hyps), out.ctypes.data, len(out), C.byref(n)))
+        return out[:n.value]
+
+    def refine_ms(self):
+        ms = (C.c_float * 4)()
+        self._ck(self._L.hf6d_refine_ms(self._h, ms))
+        return dict(zip(("scene", "icp", "score", "optimise"), (float(x) for x in ms)))
+
+    def refine_fetch(self, what: int, arg: int = 0):
+        cap = max(self.W * self.H, 1 << 20) * 16
+        buf = np.zeros(cap, np.uint8)
+        n = self._ck(self._L.hf6d_refine_fetch(self._h, what, arg, buf.ctypes.data, cap))
+        raw = buf[:n]
+        if what in (RBUF_SCENE_LABELS, RBUF_CLUSTER_SIZES):
+            return raw.view(np.int32).copy()
+        return raw.view(np.float32).reshape(-1, 4).copy()
 
     # ------------------------------------------------------------------ plumbing
     def _ck(self, rc):

@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cfloat>
 #include <chrono>
 #include <cmath>
 #include <thread>
@@ -24,6 +25,7 @@
 #include "gather.cuh"
 #include "model.hpp"
 #include "modes.cuh"
+#include "refine.cuh"
 #include "texture_check.cuh"
 #include "vote.cuh"
 
@@ -114,8 +116,11 @@ struct ResultLayout {
 
 }  // namespace
 
+struct hf6d_refiner;  // stage REFINE (refine_api.inc), created on first use
+
 struct hf6d_ctx {
     hf6d_params p{};
+    hf6d_refiner* rf = nullptr;
     int device = 0, n_slots = 1, sms = 148;
     HostForest hf;
     std::vector<HostLayer> layers;
@@ -409,6 +414,8 @@ void free_all(hf6d_ctx* c) {
     }
     for (void* p : c->dm.allocs) cudaFree(p);
 }
+
+void rf_free(hf6d_refiner* r);  // refine_api.inc
 
 // Classes whose centres and poses this context seeks: detected AND owned under the class shard (votes are cast for every
 // detected class regardless, because the summed maps of a class need the votes of all ranks' trees).
@@ -1318,6 +1325,7 @@ void hf6d_destroy(hf6d_ctx* c) {
     if (c->peer_on || !c->peer_opened.empty()) hf6d_peer_detach(c);
     if (c->peer_flags) cudaFree(c->peer_flags);
     if (c->peer_timeout) cudaFree(c->peer_timeout);
+    rf_free(c->rf);
     free_all(c);
     delete c;
 }
@@ -1923,3 +1931,5 @@ void hf6d_pose_from_tuple(const hf6d_params* p, int cx, int cy, float z, int yaw
 }
 
 }  // extern "C"
+
+#include "refine_api.inc"

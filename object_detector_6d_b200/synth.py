@@ -168,6 +168,60 @@ def _render(rng, rng_pose, cam, n_objects, table):
     return bgr, depth, truth
 
 
+# ------------------------------------------------------------------------------------------------ object models (PLY)
+def object_models(object_seed: int, n_objects: int = 6, spacing: float = 0.002):
+    """Surface point clouds of the procedural solids render_scene draws for `object_seed` -- the stand-ins for the reference's
+    meshes/*.ply (vertices with colour, object frame, metres; README.md:42-51).  Replays the object draws of _render (kind,
+    size, albedo, texture) and samples every face on a `spacing` lattice.  Returns a list of (xyz float32 [n,3], rgb uint8
+    [n,3]); `R p + centre` with the frame's truth maps a model point into the camera frame."""
+    rng = np.random.default_rng(object_seed)
+    out = []
+    for _ in range(n_objects):
+        kind = int(rng.integers(0, 2))
+        size = rng.uniform(0.05, 0.2, 3)
+        base = rng.uniform(40, 230, 3)
+        tkind, freq = int(rng.integers(0, 3)), rng.uniform(15, 60)
+        pts = []
+        if kind == 0:
+            hs = size * 0.5
+            for ax in range(3):
+                a, b = [k for k in range(3) if k != ax]
+                ga = np.arange(-hs[a], hs[a] + 1e-9, spacing)
+                gb = np.arange(-hs[b], hs[b] + 1e-9, spacing)
+                A, B = np.meshgrid(ga, gb, indexing="ij")
+                for sgn in (-1.0, 1.0):
+                    q = np.zeros(A.shape + (3,))
+                    q[..., a], q[..., b], q[..., ax] = A, B, sgn * hs[ax]
+                    pts.append(q.reshape(-1, 3))
+        else:
+            r, hh = size[0] * 0.5, size[1] * 0.5
+            n_ang = max(8, int(np.ceil(2 * np.pi * r / spacing)))
+            ang = np.arange(n_ang) * (2 * np.pi / n_ang)
+            ys = np.arange(-hh, hh + 1e-9, spacing)
+            A, Y = np.meshgrid(ang, ys, indexing="ij")
+            pts.append(np.stack([r * np.cos(A), Y, r * np.sin(A)], -1).reshape(-1, 3))
+            g = np.arange(-r, r + 1e-9, spacing)
+            X, Z = np.meshgrid(g, g, indexing="ij")
+            inside = X * X + Z * Z <= r * r
+            for sgn in (-1.0, 1.0):
+                pts.append(np.stack([X[inside], np.full(inside.sum(), sgn * hh), Z[inside]], -1))
+        xyz = np.concatenate(pts).astype(np.float32)
+        col = np.clip(_texture(xyz.astype(np.float64), base, tkind, freq) * 0.8, 0, 255)  # albedo x a mean shade; BGR like the frames
+        out.append((xyz, np.ascontiguousarray(np.rint(col[:, ::-1]).astype(np.uint8))))
+    return out
+
+
+def write_ply(path: str, xyz: np.ndarray, rgb: np.ndarray) -> None:
+    """ASCII PLY with `x y z r g b a` per vertex, the only layout MeshUtils::getPointCloudFromPLY reads
+    (HoughForest/src/MeshUtils.cpp:68-114)."""
+    with open(path, "w") as f:
+        f.write("ply\nformat ascii 1.0\nelement vertex %d\nproperty float x\nproperty float y\nproperty float z\n"
+                "property uchar red\nproperty uchar green\nproperty uchar blue\nproperty uchar alpha\n"
+                "element face 0\nproperty list uchar int vertex_indices\nend_header\n" % len(xyz))
+        for (x, y, z), (r, g, b) in zip(xyz.tolist(), rgb.tolist()):
+            f.write("%.6f %.6f %.6f %d %d %d 255\n" % (x, y, z, r, g, b))
+
+
 # ------------------------------------------------------------------------------------------------ encoder weights
 def make_encoder_weights(seed: int, dims=ENCODER_DIMS):
     """[(W [out,in] f32, b [out] f32)] x3 with the net's own fillers: gaussian std 1, `sparse: 40`, zero bias
