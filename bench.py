@@ -492,6 +492,31 @@ def run_cuda(args, rank, world, local_rank):
                               "votes_cast_per_frame": int(nv), "serial_ms_per_frame": float(np.sum(sm)),
                               "stage_ms": {n: float(v) for n, v in zip(api.STAGE_NAMES, sm)}})
 
+        # ---- the step after the hot path, reported beside it, not inside `value`: ICP + hypothesis scoring +
+        # joint optimisation of the frame's hypotheses through hf6d_refine, with the procedural objects as the mesh files
+        refine = None
+        if rank == 0 and cfg["forest"] == "trained" and not args.no_refine:
+            try:
+                dr = api.Detector(forest_dir, wpath, p, device=local_rank, n_slots=1)
+                for k, (xyz, rgb) in enumerate(synth.object_models(OBJECT_SEED, cfg["n_objects"])[:K]):
+                    dr.set_object_model(k, xyz, rgb, 0.015, 60)  # generate_scripts.sh:169-170
+                rows = []
+                for j in range(2 * min(distinct, 2)):  # the first pass allocates; the second is reported
+                    hyp = dr.detect(frames[j % distinct][0], frames[j % distinct][1])
+                    dets = dr.refine(hyp)
+                    rows.append((len(hyp), int(dets["accepted"].sum()), int((dets["rank"] >= 0).sum()), dr.refine_ms()))
+                dr.close()
+                rows = rows[len(rows) // 2:]
+                refine = {"hypotheses_per_frame": float(np.mean([r[0] for r in rows])),
+                          "accepted_per_frame": float(np.mean([r[1] for r in rows])),
+                          "written_per_frame": float(np.mean([r[2] for r in rows])),
+                          "ms_per_frame": {k: float(np.mean([r[3][k] for r in rows])) for k in rows[0][3]},
+                          "note": "hf6d_refine (MeshUtils::setScene + icp + evaluate_hypothesis + optimize_hypotheses on the GPU, "
+                                  "nn_search_radius 0.015, 60 ICP iterations); not part of `value` / `e2e`, whose path ends with the "
+                                  "Hough hypotheses as BASELINE.json's north star defines it"}
+            except Exception as e:  # the hot-path line must not depend on the next-row stage
+                refine = {"unavailable": str(e).splitlines()[0][:200]}
+
         # ---- CPU baseline (rank 0, N == 1 only): the oracle port on a bounded sample, all host cores
         cpu = None
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -575,6 +600,8 @@ def run_cuda(args, rank, world, local_rank):
             }
             if sweep is not None:
                 line["sweep"] = sweep
+            if refine is not None:
+                line["refine"] = refine
             if sharded is not None:
                 line["sharded"] = sharded
             return line
@@ -689,6 +716,7 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-refine", action="store_true", help="skip the ICP / scoring stage report (SURVEY.md 8(f)1)")
     ap.add_argument("--slots", type=int, default=4, help="frames in flight (one stream + workspace each)")
     ap.add_argument("--encoder-mode", type=int, default=0, choices=[0, 1, 2],
                     help="0: bf16 tensor-core operands (the headline), 1: split bf16 (~fp32 products, 3x the encoder time), "

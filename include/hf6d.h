@@ -325,7 +325,8 @@ typedef enum {
     HF6D_RBUF_SCENE_LABELS = 2,   /* int32[S] smooth-cluster id, -1 = none */
     HF6D_RBUF_CLUSTER_SIZES = 3,  /* int32[n_clusters] */
     HF6D_RBUF_MODEL_POINTS = 4,   /* float[M][4] of object `arg` (down-sampled, normals_not_nan applied) */
-    HF6D_RBUF_MODEL_NORMALS = 5   /* float[M][4] of object `arg`: normals re-estimated on that cloud (NaN rows are dropped by the scoring) */
+    HF6D_RBUF_MODEL_NORMALS = 5,  /* float[M][4] of object `arg`: normals re-estimated on that cloud (NaN rows are dropped by the scoring) */
+    HF6D_RBUF_MODEL_VERTICES = 6  /* float[n][3] of object `arg`: the mesh vertices as read (what MeshUtils::renderObject projects) */
 } hf6d_refine_buffer;
 
 void hf6d_default_refine_params(hf6d_refine_params* p);
@@ -336,6 +337,10 @@ int hf6d_get_refine_params(const hf6d_ctx* c, hf6d_refine_params* out);
 int hf6d_set_object_model(hf6d_ctx* c, int cls, const float* xyz, const uint8_t* rgb, int n, float nn_search_radius,
                           int icp_iterations);
 int hf6d_load_object_ply(hf6d_ctx* c, int cls, const char* ply_path, float nn_search_radius, int icp_iterations);
+/* For a context made by hf6d_create_from_options: inserts the mesh_file of every object with should_detect, with the object's
+ * nn_search_radius and icp_iterations, as DetectObjects does (HFTest.cpp:1227-1233); the MeshUtils settings of the options file
+ * (HFTest.cpp:1203-1225) are already the context's refine parameters.  HF6D_EIO names the first mesh that cannot be read. */
+int hf6d_load_option_models(hf6d_ctx* c);
 /* Refines and scores the n hypotheses (as hf6d_collect / hf6d_wait / hf6d_detect returned them) against the frame the slot
  * still holds (hf6d_detect: slot 0; ticket t: slot t % n_slots, until the next submit reuses it), then selects.  Writes one
  * hf6d_detection per hypothesis, in input order.  Synchronous.  Every detected class needs a model. */
@@ -343,7 +348,7 @@ int hf6d_refine(hf6d_ctx* c, int slot, const hf6d_hypothesis* hyps, int n, hf6d_
 /* Milliseconds of the last hf6d_refine: ms[0] scene (cloud, VoxelGrid, normals, clusters), ms[1] ICP, ms[2] scoring,
  * ms[3] joint optimisation (GPU kernels + host enumeration). */
 int hf6d_refine_ms(hf6d_ctx* c, float ms[4]);
-/* Copies a buffer of the last hf6d_refine (or of a model) to the host; returns bytes written, or < 0. */
+/* Copies a buffer of the last hf6d_refine (or of a model) to the host; returns bytes written, or < 0.  dst == NULL: the size. */
 int64_t hf6d_refine_fetch(hf6d_ctx* c, int what, int arg, void* dst, size_t cap_bytes);
 
 #ifdef __cplusplus

@@ -31,7 +31,7 @@ EXPORTS = (
     "hf6d_pose_from_tuple", "hf6d_count_cast_votes", "hf6d_bind_frame", "hf6d_encoder_layer_ms", "hf6d_result_bytes",
     "hf6d_parse_options", "hf6d_inspect_forest", "hf6d_inspect_weights", "hf6d_debug_texture_gather",
     "hf6d_default_refine_params", "hf6d_set_refine_params", "hf6d_get_refine_params", "hf6d_set_object_model",
-    "hf6d_load_object_ply", "hf6d_refine", "hf6d_refine_ms", "hf6d_refine_fetch",
+    "hf6d_load_object_ply", "hf6d_load_option_models", "hf6d_refine", "hf6d_refine_ms", "hf6d_refine_fetch",
 )
 
 
@@ -81,7 +81,8 @@ DETECTION_DTYPE = np.dtype([("hypothesis", "<i4"), ("cls", "<i4"), ("pose", "<f4
                             ("inliers_ratio", "<f4"), ("clutter", "<f4"), ("location_score", "<f4"), ("pose_score", "<f4"),
                             ("final_score", "<f4"), ("icp_converged", "<i4"), ("icp_iterations", "<i4"), ("visible", "<i4"),
                             ("inliers", "<i4"), ("explained", "<i4"), ("accepted", "<i4"), ("selected", "<i4"), ("rank", "<i4")])
-RBUF_SCENE_POINTS, RBUF_SCENE_NORMALS, RBUF_SCENE_LABELS, RBUF_CLUSTER_SIZES, RBUF_MODEL_POINTS, RBUF_MODEL_NORMALS = range(6)
+RBUF_SCENE_POINTS, RBUF_SCENE_NORMALS, RBUF_SCENE_LABELS, RBUF_CLUSTER_SIZES, RBUF_MODEL_POINTS, RBUF_MODEL_NORMALS, \
+    RBUF_MODEL_VERTICES = range(7)
 
 HYP_DTYPE = np.dtype([("cls", "<i4"), ("cx", "<i4"), ("cy", "<i4"), ("z", "<f4"), ("yaw_deg", "<i4"),
                       ("pitch_deg", "<i4"), ("roll_deg", "<i4"), ("loc_score", "<f4"), ("yawpitch_score", "<f4"),
@@ -173,6 +174,7 @@ def load():
     L.hf6d_get_refine_params.argtypes = [vp, C.POINTER(RefineParams)]
     L.hf6d_set_object_model.argtypes = [vp, i32, vp, vp, i32, C.c_float, i32]
     L.hf6d_load_object_ply.argtypes = [vp, i32, C.c_char_p, C.c_float, i32]
+    L.hf6d_load_option_models.argtypes = [vp]
     L.hf6d_refine.argtypes = [vp, i32, vp, i32, vp, i32, C.POINTER(i32)]
     L.hf6d_refine_ms.argtypes = [vp, C.POINTER(C.c_float)]
     L.hf6d_refine_fetch.argtypes = [vp, i32, i32, vp, C.c_size_t]
@@ -295,6 +297,10 @@ class Detector:
     def load_object_ply(self, cls: int, path: str, nn_search_radius: float = -1.0, icp_iterations: int = -1):
         self._ck(self._L.hf6d_load_object_ply(self._h, cls, path.encode(), nn_search_radius, icp_iterations))
 
+    def load_option_models(self):
+        """MeshUtils::insertObjectFromPLY for every detected object of the options file (HFTest.cpp:1227-1233)."""
+        self._ck(self._L.hf6d_load_option_models(self._h))
+
     def refine(self, hyps, slot: int = 0):
         """ICP + evaluate_hypothesis + optimize_hypotheses for the hypotheses of the frame the slot holds
         (HFTest.cpp:922-994, 1261-1273).  Returns a DETECTION_DTYPE array, one row per hypothesis."""
@@ -310,13 +316,13 @@ class Detector:
         return dict(zip(("scene", "icp", "score", "optimise"), (float(x) for x in ms)))
 
     def refine_fetch(self, what: int, arg: int = 0):
-        cap = max(self.W * self.H, 1 << 20) * 16
-        buf = np.zeros(cap, np.uint8)
+        cap = self._ck(self._L.hf6d_refine_fetch(self._h, what, arg, None, 0))
+        buf = np.zeros(max(cap, 1), np.uint8)
         n = self._ck(self._L.hf6d_refine_fetch(self._h, what, arg, buf.ctypes.data, cap))
         raw = buf[:n]
         if what in (RBUF_SCENE_LABELS, RBUF_CLUSTER_SIZES):
             return raw.view(np.int32).copy()
-        return raw.view(np.float32).reshape(-1, 4).copy()
+        return raw.view(np.float32).reshape(-1, 3 if what == RBUF_MODEL_VERTICES else 4).copy()
 
     # ------------------------------------------------------------------ plumbing
     def _ck(self, rc):

@@ -121,6 +121,12 @@ struct hf6d_refiner;  // stage REFINE (refine_api.inc), created on first use
 struct hf6d_ctx {
     hf6d_params p{};
     hf6d_refiner* rf = nullptr;
+    // object_options of the options file the context was created from (hf6d_load_option_models)
+    std::vector<std::string> mesh_files;
+    std::vector<float> obj_nn_search_radius;
+    std::vector<int> obj_icp_iterations;
+    hf6d_refine_params option_refine{};
+    bool has_option_refine = false;
     int device = 0, n_slots = 1, sms = 148;
     HostForest hf;
     std::vector<HostLayer> layers;
@@ -1259,6 +1265,11 @@ int hf6d_create_from_options(const char* options_path, int W, int H, int device,
     hf6d_ctx* c = new hf6d_ctx();
     c->p = p;
     c->objects = o.objects;
+    c->mesh_files = o.mesh_files;
+    c->obj_nn_search_radius = o.nn_search_radius;
+    c->obj_icp_iterations = o.icp_iterations;
+    c->option_refine = o.refine;
+    c->has_option_refine = true;
     int r = HF6D_OK;
     if (!load_forest(o.forest_folder, c->hf, err)) r = fail(nullptr, HF6D_EIO, "%s", err.c_str());
     else if (!load_weights(o.caffe_weights, c->layers, err)) r = fail(nullptr, HF6D_EIO, "%s", err.c_str());

@@ -19,6 +19,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -357,6 +358,25 @@ struct Ranked {
     int index;
 };
 
+// MeshUtils::renderObject with alpha = 1 (MeshUtils.cpp:503-538, called from HFTest.cpp:1299): every pixel that a mesh vertex
+// projects onto in front of the scene (or where the scene has no depth) gets a saturated green channel.  With alpha = 1 the
+// reference's per-point update `g = alpha + (1 - alpha) * G / 255; G = min(g * 255 + g, 255)` is 255 whatever the order.  The
+// object's name (cv::putText) is not drawn.
+void render_object(uint8_t* bgr, const uint16_t* depth, int W, int H, const hf6d_params& p, const std::vector<float>& xyz,
+                   const float pose[16]) {
+    for (size_t i = 0; i + 2 < xyz.size(); i += 3) {
+        const float x = pose[0] * xyz[i] + pose[1] * xyz[i + 1] + pose[2] * xyz[i + 2] + pose[3];
+        const float y = pose[4] * xyz[i] + pose[5] * xyz[i + 1] + pose[6] * xyz[i + 2] + pose[7];
+        const float z = pose[8] * xyz[i] + pose[9] * xyz[i + 1] + pose[10] * xyz[i + 2] + pose[11];
+        const float rowf = y * p.fy / z + p.cy, colf = x * p.fx / z + p.cx;
+        if (!(std::fabs(rowf) < 1e9f) || !(std::fabs(colf) < 1e9f)) continue;
+        const int row = (int)rowf, col = (int)colf;
+        if (row < 0 || row >= H || col < 0 || col >= W) continue;
+        const uint16_t d = depth[(size_t)row * W + col];
+        if (d == 0 || z < (float)d / 1000.0f) bgr[((size_t)row * W + col) * 3 + 1] = 255;
+    }
+}
+
 }  // namespace
 
 int main(int argc, char** argv) {
@@ -409,6 +429,9 @@ int main(int argc, char** argv) {
     uint8_t* bgr = nullptr;
     uint16_t* depth = nullptr;
     std::vector<hf6d_hypothesis> hyp(HF6D_MAX_CLASSES * HF6D_MAX_CENTRES * HF6D_MAX_HYPOTHESES_PER_CENTRE);
+    std::vector<hf6d_detection> det(hyp.size());
+    std::vector<std::vector<float>> vertices;  // per object: the mesh vertices (MeshUtils::renderObject projects them)
+    bool refined = false;
     int rc = 0;
 
     std::string rgb_fname, depth_fname;
@@ -441,10 +464,25 @@ int main(int argc, char** argv) {
                 std::cerr << "HoughForest: " << hf6d_last_error(ctx) << std::endl;
                 return 3;
             }
-            // the reference refines every hypothesis with ICP and ranks by MeshUtils' final score before it writes _res.txt
-            // (HFTest.cpp:927-934, :1261-1311); this path ends where MeshUtils begins, and says so
-            std::cout << "Note: poses are the pre-ICP Hough hypotheses (ICP refinement and hypothesis scoring are not part of this "
-                         "library); ranked by pose_score_coeff * pose score + location_score_coeff * location score" << std::endl;
+            // MeshUtils::insertObjectFromPLY for every detected object (HFTest.cpp:1227-1233).  With the meshes the frame goes
+            // through ICP, hypothesis scoring and the joint optimisation exactly where the reference runs them
+            // (HFTest.cpp:927-934, :990-994) and _res.txt holds the refined poses; without them (the reference aborts on a
+            // missing mesh) the Hough hypotheses are written, and the output says so.
+            refined = hf6d_load_option_models(ctx) == 0;
+            if (!refined) {
+                std::cout << "Note: " << hf6d_last_error(ctx) << " -- poses are the pre-ICP Hough hypotheses, ranked by "
+                             "pose_score_coeff * pose score + location_score_coeff * location score" << std::endl;
+            } else {
+                vertices.assign((size_t)forest.K, std::vector<float>());
+                for (int k = 0; k < forest.K; ++k) {
+                    if (!objects[k].should_detect) continue;
+                    const int64_t bytes = hf6d_refine_fetch(ctx, HF6D_RBUF_MODEL_VERTICES, k, nullptr, 0);
+                    if (bytes > 0) {
+                        vertices[k].resize((size_t)bytes / 4);
+                        hf6d_refine_fetch(ctx, HF6D_RBUF_MODEL_VERTICES, k, vertices[k].data(), (size_t)bytes);
+                    }
+                }
+            }
         }
         to_bgr8(rgb_img, bgr);
         if (!to_depth16(depth_img, depth, err)) {
@@ -480,6 +518,55 @@ int main(int argc, char** argv) {
                 for (int s = 0; s < HF6D_STAGE_COUNT; ++s) std::cout << "  stage " << names[s] << ": " << ms[s] << " ms" << std::endl;
         }
 
+        const std::string stem = out_stem(rgb_fname);
+        const std::string out_fname = fl.output_folder + stem + "_res.txt";
+        if (refined) {
+            // HFTest.cpp:927-934 + :990-994: ICP, evaluate_hypothesis, optimize_hypotheses; then DetectObjects' output loop
+            int nd = 0;
+            if (hf6d_refine(ctx, 0, hyp.data(), n, det.data(), (int)det.size(), &nd)) {
+                std::cerr << "HoughForest: refinement failed on " << rgb_fname << ": " << hf6d_last_error(ctx) << std::endl;
+                rc = 3;
+                break;
+            }
+            if (fl.stage_times) {
+                float ms[4];
+                static const char* names[4] = {"scene", "icp", "score", "optimise"};
+                if (!hf6d_refine_ms(ctx, ms))
+                    for (int s2 = 0; s2 < 4; ++s2) std::cout << "  stage refine/" << names[s2] << ": " << ms[s2] << " ms" << std::endl;
+            }
+            std::vector<int> by_rank;
+            for (int i = 0; i < nd; ++i)
+                if (det[i].rank >= 0) {
+                    if ((int)by_rank.size() <= det[i].rank) by_rank.resize((size_t)det[i].rank + 1, -1);
+                    by_rank[det[i].rank] = i;
+                }
+            std::ofstream fout(out_fname.c_str());
+            if (!fout) {
+                std::cerr << "Check failed: Cannot write to output file " << out_fname << std::endl;
+                rc = 1;
+                break;
+            }
+            std::cout << "Writing info to: " << out_fname << std::endl;
+            std::vector<int> hcounter((size_t)forest.K, 0);
+            int total_found = 0;
+            for (int i : by_rank) {
+                if (i < 0) continue;
+                const hf6d_detection& d = det[i];
+                ++hcounter[d.cls];
+                ++total_found;
+                fout << objects[d.cls].name << "(" << hcounter[d.cls] << ")" << ": " << std::endl;
+                fout << eigen_format(d.pose) << std::endl;
+                fout << std::endl;
+                render_object(bgr, depth, ctx_w, ctx_h, opt.params, vertices[d.cls], d.pose);
+            }
+            fout.close();
+            const std::string rgb_out_fname = fl.output_folder + stem + "_res.png";
+            std::cout << "Writing result image to: " << rgb_out_fname << std::endl;
+            if (!write_png_rgb(rgb_out_fname, bgr, ctx_w, ctx_h)) std::cerr << "cannot write " << rgb_out_fname << std::endl;
+            std::cout << "Detection finished. Total objects found: " << total_found << std::endl;
+            continue;
+        }
+
         // HFTest.cpp:1261: sort by final score, descending (stable here, so equal scores keep emission order)
         std::vector<Ranked> order((size_t)n);
         for (int i = 0; i < n; ++i) {
@@ -488,8 +575,6 @@ int main(int argc, char** argv) {
         }
         std::stable_sort(order.begin(), order.end(), [](const Ranked& a, const Ranked& b) { return a.final_score > b.final_score; });
 
-        const std::string stem = out_stem(rgb_fname);
-        const std::string out_fname = fl.output_folder + stem + "_res.txt";
         std::ofstream fout(out_fname.c_str());
         if (!fout) {
             std::cerr << "Check failed: Cannot write to output file " << out_fname << std::endl;

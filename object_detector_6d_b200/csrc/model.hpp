@@ -428,6 +428,10 @@ inline bool load_weights(const std::string& path, std::vector<HostLayer>& layers
 struct HostOptions {
     std::vector<hf6d_object> objects;
     std::vector<std::string> mesh_files;
+    std::vector<float> nn_search_radius;   // per object, -1 = not given (MeshUtils.h:239-245)
+    std::vector<int> icp_iterations;       // per object, -1 = not given
+    hf6d_refine_params refine;             // the MeshUtils settings of HFTest.cpp:1203-1225 (proto defaults until a key sets them)
+    bool refine_defaults_set = false;
     std::string forest_folder, caffe_definition, caffe_weights;
     int stride = 4, gpu = -1, num_threads = 4, batch_size = 100;  // proto defaults (detector_options.proto:23-27)
     float max_depth_range = 0.25f, fx = 575.f, fy = 575.f, cx = 319.5f, cy = 239.5f, distance_threshold = 1.5f;
@@ -442,6 +446,7 @@ class OptionsParser {
   public:
     explicit OptionsParser(const std::string& text) : s_(text) {}
     bool parse(HostOptions& o, std::string& err) {
+        if (!o.refine_defaults_set) { refine_defaults(o.refine); o.refine_defaults_set = true; }
         while (true) {
             skip();
             if (p_ >= s_.size()) break;
@@ -459,6 +464,8 @@ class OptionsParser {
                 ob.should_detect = 1; ob.max_location_hypotheses = 12; ob.instances = 1;
                 std::string mesh;
                 bool has_name = false;
+                float nn_radius = 0.01f;  // proto defaults (detector_options.proto:10-11): an object always carries both
+                int icp_iters = 60;
                 while (true) {
                     skip();
                     if (p_ >= s_.size()) return fail(err, "unterminated object_options block");
@@ -474,13 +481,17 @@ class OptionsParser {
                     else if (k2 == "instances") ob.instances = atoi(v.c_str());
                     else if (k2 == "max_location_hypotheses") ob.max_location_hypotheses = atoi(v.c_str());
                     else if (k2 == "should_detect") { if (!boolean(v, ob.should_detect)) return fail(err, "bad bool for should_detect"); }
-                    else if (k2 == "nn_search_radius" || k2 == "icp_iterations" || k2 == "align_z_axis") {}
+                    else if (k2 == "nn_search_radius") nn_radius = strtof(v.c_str(), nullptr);
+                    else if (k2 == "icp_iterations") icp_iters = atoi(v.c_str());
+                    else if (k2 == "align_z_axis") {}
                     else return fail(err, "unknown field object_options." + k2);
                     sep();
                 }
                 if (!has_name) return fail(err, "object_options without a name");
                 o.objects.push_back(ob);
                 o.mesh_files.push_back(mesh);
+                o.nn_search_radius.push_back(nn_radius);
+                o.icp_iterations.push_back(icp_iters);
             } else {
                 if (peek() != ':') return fail(err, "expected ':' after " + key);
                 ++p_;
@@ -501,9 +512,15 @@ class OptionsParser {
                 else if (key == "cy") o.cy = strtof(v.c_str(), nullptr);
                 else if (key == "distance_threshold") o.distance_threshold = strtof(v.c_str(), nullptr);
                 else if (key == "are_objects_segmented") { if (!boolean(v, b)) return fail(err, "bad bool for " + key); o.are_objects_segmented = b != 0; }
-                else if (key == "location_score_coeff") o.location_score_coeff = strtof(v.c_str(), nullptr);
-                else if (key == "pose_score_coeff") o.pose_score_coeff = strtof(v.c_str(), nullptr);
-                else if (is_downstream_key(key)) {}  // ICP / scoring / clustering options: parsed, not used by this path
+                else if (key == "location_score_coeff") o.refine.location_score_coeff = o.location_score_coeff = strtof(v.c_str(), nullptr);
+                else if (key == "pose_score_coeff") o.refine.pose_score_coeff = o.pose_score_coeff = strtof(v.c_str(), nullptr);
+                else if (key == "search_single_object_instance" || key == "search_single_object_in_group" || key == "use_color_similarity") {
+                    if (!boolean(v, b)) return fail(err, "bad bool for " + key);
+                    (key == "search_single_object_instance" ? o.refine.search_single_object_instance
+                     : key == "search_single_object_in_group" ? o.refine.search_single_object_in_group
+                                                              : o.refine.use_color_similarity) = b;
+                } else if (float* f = refine_float(o.refine, key)) *f = strtof(v.c_str(), nullptr);
+                else if (key == "cluster_min_points") o.refine.cluster_min_points = atoi(v.c_str());
                 else return fail(err, "unknown field " + key);
             }
             sep();
@@ -516,14 +533,32 @@ class OptionsParser {
     }
 
   private:
-    static bool is_downstream_key(const std::string& k) {
-        static const char* keys[] = {"search_single_object_instance", "search_single_object_in_group", "use_color_similarity",
-            "similarity_coeff", "inliers_coeff", "clutter_coeff", "location_score_coeff", "pose_score_coeff",
-            "group_total_explain_coeff", "group_common_explain_coeff", "inliers_threshold", "clutter_threshold",
-            "final_score_threshold", "cluster_eps_angle_threshold", "cluster_min_points", "cluster_curvature_threshold",
-            "cluster_tolerance_near", "cluster_tolerance_far"};
-        for (const char* s : keys) if (k == s) return true;
-        return false;
+    // MeshUtils' members as DetectObjects sets them from the options (HFTest.cpp:1203-1225; detector_options.proto:33-66)
+    static void refine_defaults(hf6d_refine_params& r) {
+        memset(&r, 0, sizeof r);
+        r.scene_leaf_m = 0.005f; r.object_leaf_m = 0.005f; r.normals_radius_m = 0.03f; r.nn_search_radius_m = 0.01f;
+        r.occlusion_threshold_m = 0.02f;
+        r.similarity_coeff = 10.f; r.inliers_coeff = 2.5f; r.clutter_coeff = 1.4f; r.location_score_coeff = 1.f; r.pose_score_coeff = 0.7f;
+        r.group_total_explain_coeff = 0.5f; r.group_common_explain_coeff = 0.3f;
+        r.inliers_threshold = 0.6f; r.clutter_threshold = 0.6f; r.final_score_threshold = 10.f;
+        r.cluster_eps_angle_threshold = 0.05f; r.cluster_curvature_threshold = 0.1f; r.cluster_tolerance_near = 0.03f;
+        r.cluster_tolerance_far = 0.05f; r.cluster_min_points = 5;
+        r.use_color_similarity = 1; r.use_normal_similarity = 1; r.default_icp_iterations = 60;
+    }
+    static float* refine_float(hf6d_refine_params& r, const std::string& k) {
+        if (k == "similarity_coeff") return &r.similarity_coeff;
+        if (k == "inliers_coeff") return &r.inliers_coeff;
+        if (k == "clutter_coeff") return &r.clutter_coeff;
+        if (k == "group_total_explain_coeff") return &r.group_total_explain_coeff;
+        if (k == "group_common_explain_coeff") return &r.group_common_explain_coeff;
+        if (k == "inliers_threshold") return &r.inliers_threshold;
+        if (k == "clutter_threshold") return &r.clutter_threshold;
+        if (k == "final_score_threshold") return &r.final_score_threshold;
+        if (k == "cluster_eps_angle_threshold") return &r.cluster_eps_angle_threshold;
+        if (k == "cluster_curvature_threshold") return &r.cluster_curvature_threshold;
+        if (k == "cluster_tolerance_near") return &r.cluster_tolerance_near;
+        if (k == "cluster_tolerance_far") return &r.cluster_tolerance_far;
+        return nullptr;
     }
     char peek() const { return p_ < s_.size() ? s_[p_] : '\0'; }
     void skip() {

@@ -813,21 +813,21 @@ __global__ void rf_common_kernel(const unsigned* __restrict__ explained, int wor
     if (threadIdx.x == 0) { common[a * n + b] = s_sum; common[b * n + a] = s_sum; }
 }
 
-// Per solution of a group (a subset of its <= 64 members as a bit mask): scene points explained by at least one chosen member
-// and the surplus of multiply explained ones (MeshUtils.cpp:982-996).  members[i] = hypothesis of group member i.  Grid =
-// solutions; counts[2 * s] = total, counts[2 * s + 1] = common cost.
+// Per solution of a group (a subset of its members as a bit vector of `sol_words` 32-bit words): scene points explained by at
+// least one chosen member and the surplus of multiply explained ones (MeshUtils.cpp:982-996).  members[i] = hypothesis of group
+// member i.  Grid = solutions; counts[2 * s] = total, counts[2 * s + 1] = common cost.
 __global__ void rf_solution_kernel(const unsigned* __restrict__ explained, int words_per_hyp, const int* __restrict__ members,
-                                   int n_members, const unsigned long long* __restrict__ solutions, int* __restrict__ counts) {
+                                   int n_members, const unsigned* __restrict__ solutions, int sol_words, int* __restrict__ counts) {
     __shared__ int s_tot, s_com;
     if (threadIdx.x == 0) { s_tot = 0; s_com = 0; }
     __syncthreads();
-    const unsigned long long sol = solutions[blockIdx.x];
+    const unsigned* sol = solutions + (size_t)blockIdx.x * sol_words;
     int tot = 0, com = 0;
     for (int w = threadIdx.x; w < words_per_hyp; w += blockDim.x) {
         unsigned any = 0;  // points explained so far
         int surplus = 0;
         for (int i = 0; i < n_members; ++i) {
-            if (!((sol >> i) & 1ull)) continue;
+            if (!((sol[i >> 5] >> (i & 31)) & 1u)) continue;
             const unsigned e = explained[(size_t)members[i] * words_per_hyp + w];
             surplus += __popc(any & e);  // every further explanation of an already explained point costs one
             any |= e;

@@ -638,11 +638,12 @@ def write_forest(folder: str, calib_features: np.ndarray, T: int = 4, K: int = 6
 
 # ------------------------------------------------------------------------------------------------ options file
 def write_options(path: str, forest_folder: str, weights_path: str, K: int, cam: Camera = Camera(), stride: int = 2,
-                  segmented: bool = True, definition: str = "patch_autoencoder_half.prototxt", extra: str = "") -> None:
+                  segmented: bool = True, definition: str = "patch_autoencoder_half.prototxt", extra: str = "",
+                  mesh_dir: str = "meshes") -> None:
     """Text-format DetectorOptions.Options as generate_scripts.sh:541-572 emits it."""
     lines = []
     for k in range(K):
-        lines.append(f'object_options {{\n  name: "obj{k}"\n  mesh_file: "meshes/obj{k}.ply"\n  instances: 1\n'
+        lines.append(f'object_options {{\n  name: "obj{k}"\n  mesh_file: "{mesh_dir}/obj{k}.ply"\n  instances: 1\n'
                      f"  nn_search_radius: 0.01\n  icp_iterations: 60\n  max_location_hypotheses: 12\n"
                      f"  should_detect: true\n}}")
     lines += [f'caffe_definition: "{definition}"', f'caffe_weights: "{weights_path}"',

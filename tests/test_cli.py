@@ -161,3 +161,53 @@ def test_cli_end_to_end_matches_the_c_abi(cli, tmp_path):
         img = cv2.imread(str(out / f"frame{i}_res.png"))
         assert np.array_equal(img, bgr)
     det.close()
+
+
+@pytest.mark.gpu
+def test_cli_writes_refined_poses_when_the_meshes_exist(cli, tmp_path):
+    """With the objects' PLY files in place the CLI runs ICP + scoring + joint optimisation (HFTest.cpp:927-934, :990-994) and
+    writes what hf6d_refine ranks (HFTest.cpp:1261-1303), and the overlay of MeshUtils::renderObject."""
+    from tests.helpers import make_case
+    cam = synth.Camera(320, 240, 287.5, 287.5, 159.5, 119.5)
+    cs = make_case(str(tmp_path), K=2, T=2, seed=5, max_depth=10, votes_per_leaf=4, cam=cam, calib_patches=3000)
+    mesh_dir = tmp_path / "meshes"
+    mesh_dir.mkdir()
+    for k, (xyz, rgb) in enumerate(synth.object_models(1000, 2, spacing=0.004)):
+        synth.write_ply(str(mesh_dir / f"obj{k}.ply"), xyz, rgb)
+    opt = tmp_path / "detector_options.proto"
+    # thresholds opened up: the forest of this case votes at random, and something should reach the output; one instance per
+    # group, because with ~200 accepted random poses in one group the subsets the reference enumerates (MeshUtils.cpp:969-972)
+    # are astronomically many -- hf6d_refine refuses beyond 2^20, the reference would not return
+    synth.write_options(str(opt), cs["forest_dir"], cs["weights"], K=2, cam=cam, segmented=True, mesh_dir=str(mesh_dir),
+                        extra="final_score_threshold: -1000\ninliers_threshold: 0\nclutter_threshold: 2\nsimilarity_coeff: 8\n"
+                              "search_single_object_in_group: true")
+    cv2.imwrite(str(tmp_path / "frame0.png"), cs["bgr"])
+    cv2.imwrite(str(tmp_path / "frame0_depth.png"), cs["depth"])
+    out = tmp_path / "out"
+    out.mkdir()
+    r = run(cli, ["--test", f"--detector_options_file={opt}", f"--output_folder={out}", "--stage_times"],
+            f"{tmp_path / 'frame0.png'} {tmp_path / 'frame0_depth.png'}\n")
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "pre-ICP" not in r.stdout and "stage refine/icp" in r.stdout
+
+    o, objs = api.parse_options(str(opt))
+    det = api.Detector(options_path=str(opt), frame_size=(320, 240), device=0)
+    assert abs(det.refine_params().similarity_coeff - 8.0) < 1e-6 and det.refine_params().final_score_threshold == -1000.0
+    det.load_option_models()
+    hyp = det.detect(cs["bgr"], cs["depth"])
+    dets = det.refine(hyp)
+    ranked = dets[dets["rank"] >= 0]
+    ranked = ranked[np.argsort(ranked["rank"])]
+    assert len(ranked) > 0
+    want, seen = [], {}
+    for d in ranked:
+        c = int(d["cls"])
+        seen[c] = seen.get(c, 0) + 1
+        assert seen[c] <= objs[c]["instances"]
+        want.append(f"{objs[c]['name']}({seen[c]}): \n{eigen_format(d['pose'])}\n\n")
+    assert (out / "frame0_res.txt").read_text() == "".join(want)
+    img = cv2.imread(str(out / "frame0_res.png"))
+    changed = np.any(img != cs["bgr"], axis=2)
+    assert changed.any() and np.all(img[changed][:, 1] == 255)  # renderObject with alpha = 1: green saturated, B and R untouched
+    assert np.array_equal(img[..., 0], cs["bgr"][..., 0]) and np.array_equal(img[..., 2], cs["bgr"][..., 2])
+    det.close()
