@@ -1,4 +1,9 @@
-/* hf6d CPU oracle -- TEST INFRASTRUCTURE ONLY (see hf6d_oracle.h).  PARITY UNPINNED (no reference golden vectors exist).
+/* hf6d CPU oracle -- TEST INFRASTRUCTURE ONLY (see hf6d_oracle.h).  PINNED to the reference's own sources: HFBase.cpp,
+ * HFTest.cpp, patch_extractor.cu, surface_normals.cu and the head of MeshUtils::icp, compiled where they lie under
+ * /root/reference against stand-in headers (oracle/build_ref.py -> oracle/_ref/), agree with this file bit for bit on seeded
+ * inputs, the whole per-frame path included (tests/test_ref_pins.py).  Still UNPINNED, because the arithmetic lives in absent
+ * third-party code: the encoder (Caffe / BLAS summation order, choice C5), the texture unit's filter (C1, checked on the B200),
+ * cv::blur's accumulation (C9, checked against cv2), the clock-seeded fill (C2).  The reference holds no golden vectors.
  *
  * Restates, stage by stage, what `HoughForest --test` computes for one RGB-D frame:
  *   A1  texture build                 HoughForest/src/HFTest.cpp:370-379
