@@ -181,8 +181,10 @@ int hf6d_set_class_shard(hf6d_ctx* c, int rank, int world);
  *    yet) and another one before hf6d_peer_detach / hf6d_destroy (nobody unmaps while a peer may still read);
  *  - every rank then runs the same frames on the same slots, in the same split: whole frames (SCAN..POSE), or SCAN..VOTE
  *    followed by CENTRES..POSE.  Any other sub-range (e.g. POSE alone on one rank) breaks the flag sequence;
- *  - the slots' streams should not share a hardware queue (CUDA_DEVICE_MAX_CONNECTIONS >= number of streams the process
- *    uses): a slot that waits for a peer's flag blocks its queue, and the peer may be waiting for a frame queued behind it;
+ *  - the slots' streams must not share a hardware queue (CUDA_DEVICE_MAX_CONNECTIONS >= number of streams the process
+ *    uses): a slot that waits for a peer's flag blocks its queue, and the peer may be waiting for a frame queued behind it.
+ *    hf6d_peer_attach checks the variable (the driver reads it once, at initialisation) and fails with HF6D_ESTATE when it
+ *    allows fewer queues than n_slots + 1, instead of leaving a deadlock for later;
  *  - waits are bounded: hf6d_sync / hf6d_collect / hf6d_wait give up after HF6D_PEER_TIMEOUT_MS (default 20000) with
  *    HF6D_ECUDA and hf6d_peer_timed_out() == 1 when a peer never answers; the context must then be destroyed.  A frame
  *    whose enqueue fails half way does not count towards the slot's sequence number.

@@ -1478,6 +1478,18 @@ int hf6d_peer_attach(hf6d_ctx* c, int rank, int world, const void* blobs, size_t
     if (!c->peer_flags) return fail(c, HF6D_ESTATE, "hf6d_peer_export must be called before hf6d_peer_attach");
     if (c->peer_on) hf6d_peer_detach(c);
     CU_TRY(c, cudaSetDevice(c->device));
+    {
+        // A slot that waits for a peer's flag blocks its hardware queue; if two slots' streams alias one queue, the frame the
+        // peer is waiting for can be stuck behind that wait (include/hf6d.h, peer contract).  The number of queues is fixed when
+        // the driver initialises, from CUDA_DEVICE_MAX_CONNECTIONS (default 8): with more slots than queues the exchange is
+        // refused here instead of deadlocking later.
+        const char* e = getenv("CUDA_DEVICE_MAX_CONNECTIONS");
+        const int queues = e && atoi(e) > 0 ? atoi(e) : 8;
+        if (c->n_slots > 1 && c->n_slots + 1 > queues)
+            return fail(c, HF6D_ESTATE, "peer exchange with %d frame slots needs CUDA_DEVICE_MAX_CONNECTIONS >= %d in the environment "
+                        "before CUDA initialises (it is %d): streams that share a hardware queue can deadlock on the peer flags",
+                        c->n_slots, c->n_slots + 1, queues);
+    }
     const PeerBlob* all = static_cast<const PeerBlob*>(blobs);
     for (int r = 0; r < world; ++r) {
         const PeerBlob& b = all[r];

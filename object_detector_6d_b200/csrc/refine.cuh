@@ -180,7 +180,7 @@ __global__ void rf_centroid_kernel(RfAccum a, const int* __restrict__ n_pts, flo
 // ---------------------------------------------------------------------------------------------- neighbour walk
 // f(index) for every point whose VOXEL lies in the box of voxels that the ball (q, r) touches, in ascending index order; the
 // caller tests the distance.  A point is the centroid of its voxel's samples, so it lies inside its voxel.
-template <class F>
+template <bool PREFETCH = false, class F>
 __device__ __forceinline__ void rf_for_box(const RfGrid& g, const unsigned* __restrict__ bits, const unsigned* __restrict__ prefix,
                                            float qx, float qy, float qz, float r, F&& f) {
     const int i0 = max(0, (int)floorf((qx - r) * g.inv) - g.bx), i1 = min(g.dx - 1, (int)floorf((qx + r) * g.inv) - g.bx);
@@ -188,21 +188,51 @@ __device__ __forceinline__ void rf_for_box(const RfGrid& g, const unsigned* __re
     const int k0 = max(0, (int)floorf((qz - r) * g.inv) - g.bz), k1 = min(g.dz - 1, (int)floorf((qz + r) * g.inv) - g.bz);
     if (i0 > i1 || j0 > j1 || k0 > k1) return;
     const int w0 = i0 >> 5, w1 = i1 >> 5, wpr = g.dx >> 5;
+    const unsigned m0 = 0xffffffffu << (i0 & 31), m1 = 0xffffffffu >> (31 - (i1 & 31));
+    auto visit = [&](long long at, unsigned full, unsigned m) {
+        if (!m) return;
+        const unsigned base = __ldg(prefix + at);
+        while (m) {
+            const int b = __ffs(m) - 1;
+            m &= m - 1;
+            f((int)(base + (unsigned)__popc(full & ((1u << b) - 1u))));
+        }
+    };
+    if (PREFETCH && w1 - w0 <= 1) {
+        // ICP's form, for the usual case (boxes narrower than 32 voxels): a row of the box is one or two words.  The words of four rows are
+        // fetched before any is looked at -- the walk is a chain of dependent L2 loads otherwise, and its latency, not its
+        // instruction count, is what an ICP iteration waits for (ncu: half of all stall samples at the iteration's barriers;
+        // 21 -> 14 ms per frame).  The one-pass kernels (normals, clusters, scoring) have the parallelism to hide it and lose
+        // more to the extra registers than they gain.
+        const bool two = w1 > w0;
+        for (int k = k0; k <= k1; ++k)
+            for (int jb = j0; jb <= j1; jb += 4) {
+                unsigned a[4], c[4];
+                long long row[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const bool in = jb + q <= j1;
+                    row[q] = ((long long)k * g.dy + (in ? jb + q : jb)) * wpr;
+                    a[q] = in ? __ldg(bits + row[q] + w0) : 0u;
+                    c[q] = in && two ? __ldg(bits + row[q] + w1) : 0u;
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    visit(row[q] + w0, a[q], two ? a[q] & m0 : a[q] & m0 & m1);
+                    visit(row[q] + w1, c[q], c[q] & m1);
+                }
+            }
+        return;
+    }
     for (int k = k0; k <= k1; ++k)
         for (int j = j0; j <= j1; ++j) {
             const long long row = ((long long)k * g.dy + j) * wpr;
             for (int w = w0; w <= w1; ++w) {
                 const unsigned full = __ldg(bits + row + w);
                 unsigned m = full;
-                if (w == w0) m &= 0xffffffffu << (i0 & 31);
-                if (w == w1) m &= 0xffffffffu >> (31 - (i1 & 31));
-                if (!m) continue;
-                const unsigned base = __ldg(prefix + row + w);
-                while (m) {
-                    const int b = __ffs(m) - 1;
-                    m &= m - 1;
-                    f((int)(base + (unsigned)__popc(full & ((1u << b) - 1u))));
-                }
+                if (w == w0) m &= m0;
+                if (w == w1) m &= m1;
+                visit(row + w, full, m);
             }
         }
 }
@@ -210,6 +240,46 @@ __device__ __forceinline__ void rf_for_box(const RfGrid& g, const unsigned* __re
 __device__ __forceinline__ float rf_dist2(float ax, float ay, float az, float bx, float by, float bz) {
     const float dx = __fsub_rn(ax, bx), dy = __fsub_rn(ay, by), dz = __fsub_rn(az, bz);
     return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
+// ---------------------------------------------------------------------------------------------- reach map
+// The voxel bitmap dilated by R voxels along every axis (a cube of 2R + 1 voxels, three separable passes of word operations):
+// bit v is set when some occupied voxel lies within R voxels of v in every coordinate.  A query point whose voxel has a clear
+// bit has no scene point within R voxel sizes (every point lies inside its voxel), so the far side of a solid object and most
+// of a misplaced hypothesis are answered "no neighbour" by one bit test instead of a walk over the whole search box.
+struct RfReach {
+    const unsigned* dil;  // dilated bitmap, the layout of the voxel bitmap; nullptr: no shortcut
+    float reach;          // R * leaf: radii up to this may use the shortcut
+};
+
+// along x: a row is dx / 32 consecutive words
+__global__ void rf_dilate_x_kernel(const unsigned* __restrict__ in, RfGrid g, int R, unsigned* __restrict__ out) {
+    const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= g.words) return;
+    const int wpr = g.dx >> 5;
+    const int wi = (int)(w % wpr);
+    const unsigned c = in[w], l = wi > 0 ? in[w - 1] : 0u, r = wi + 1 < wpr ? in[w + 1] : 0u;
+    unsigned v = c;
+    for (int s = 1; s <= R; ++s) v |= (c << s) | (l >> (32 - s)) | (c >> s) | (r << (32 - s));
+    out[w] = v;
+}
+// along y (stride = words per row, extent dy) or z (stride = words per slice, extent dz)
+__global__ void rf_dilate_axis_kernel(const unsigned* __restrict__ in, long long words, long long stride, int extent, int R,
+                                      unsigned* __restrict__ out) {
+    const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= words) return;
+    const int pos = (int)((w / stride) % extent);
+    unsigned v = 0;
+    for (int d = -R; d <= R; ++d)
+        if (pos + d >= 0 && pos + d < extent) v |= in[w + d * stride];
+    out[w] = v;
+}
+
+// false: certainly no scene point within re.reach of (x, y, z).  Points outside the grid say true (the walk decides).
+__device__ __forceinline__ bool rf_maybe_near(const RfGrid& g, const RfReach& re, float x, float y, float z) {
+    long long v;
+    if (!rf_voxel(g, x, y, z, v)) return true;
+    return (__ldg(re.dil + (v >> 5)) >> (v & 31)) & 1u;
 }
 
 // ---------------------------------------------------------------------------------------------- small dense eigen-solvers
@@ -478,7 +548,7 @@ __device__ __forceinline__ double rf_block_sum(double v, double* s_red) {
 // Rotation that maximises sum q_i . (R p_i) from the cross-covariance H = sum p q^T (Horn 1987): the eigenvector of the largest
 // eigenvalue of a symmetric 4x4 built from H is the unit quaternion.  Same optimum as the SVD solution with the determinant
 // correction (pcl::TransformationEstimationSVD), always a proper rotation.
-__device__ void rf_rotation_from_covariance(const double H[3][3], double R[3][3]) {
+__device__ __noinline__ void rf_rotation_from_covariance(const double H[3][3], double R[3][3]) {
     double a[4][4], v[4][4];
     const double Sxx = H[0][0], Sxy = H[0][1], Sxz = H[0][2], Syx = H[1][0], Syy = H[1][1], Syz = H[1][2], Szx = H[2][0],
                  Szy = H[2][1], Szz = H[2][2];
@@ -505,6 +575,9 @@ __device__ void rf_rotation_from_covariance(const double H[3][3], double R[3][3]
 // writes the new transform and the loop state into every CTA's shared memory.  Two cluster barriers per iteration, no global
 // memory traffic, no host round trip.
 constexpr int RF_ICP_CLUSTER = 4;
+#ifndef RF_ICP_MIN_CTAS
+#define RF_ICP_MIN_CTAS 4  // registers capped at 64: the serial solve of CTA 0 spills, every other thread gains occupancy
+#endif
 
 struct RfIcpShared {
     double T[12];      // current total increment (3x4): p_now = T p_0, p_0 = pose0 * model point
@@ -513,11 +586,11 @@ struct RfIcpShared {
     int iter;
 };
 
-__global__ void __cluster_dims__(RF_ICP_CLUSTER, 1, 1) __launch_bounds__(RF_THREADS)
+__global__ void __cluster_dims__(RF_ICP_CLUSTER, 1, 1) __launch_bounds__(RF_THREADS, RF_ICP_MIN_CTAS)
 rf_icp_kernel(const float* __restrict__ pose0 /*[n][16]*/, const int* __restrict__ cls, const RfModel* __restrict__ models,
               const float4* __restrict__ mpts, const float4* __restrict__ spts, const int* __restrict__ n_scene, RfGrid g,
-              const unsigned* __restrict__ bits, const unsigned* __restrict__ prefix, int* __restrict__ nn_cache /*[n][nn_stride]*/,
-              int nn_stride, RfIcpOut* __restrict__ out) {
+              const unsigned* __restrict__ bits, const unsigned* __restrict__ prefix, RfReach co,
+              int* __restrict__ nn_cache /*[n][nn_stride]*/, int nn_stride, RfIcpOut* __restrict__ out) {
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
     __shared__ RfIcpShared sh;
@@ -556,8 +629,12 @@ rf_icp_kernel(const float* __restrict__ pose0 /*[n][16]*/, const int* __restrict
             // The nearest scene point moves little between iterations: the previous one bounds the search (it is itself a
             // candidate, so the nearest point is no further away) -- after the first iteration the walk covers a box of a few
             // voxels instead of the whole correspondence distance.  The result is the same point either way.
-            float reach = m.max_dist;
             int* cache = nn_cache + (size_t)h * nn_stride + k;
+            if (co.dil && m.max_dist <= co.reach && !rf_maybe_near(g, co, fx, fy, fz)) {  // nothing within reach
+                *cache = -1;
+                continue;
+            }
+            float reach = m.max_dist;
             const int pj = sh.iter > 0 ? *cache : -1;
             if (pj >= 0) {
                 const float4 sp = __ldg(spts + pj);
@@ -566,7 +643,7 @@ rf_icp_kernel(const float* __restrict__ pose0 /*[n][16]*/, const int* __restrict
             }
             float best = 3.4e38f;
             int bj = -1;
-            rf_for_box(g, bits, prefix, fx, fy, fz, reach, [&](int j) {
+            rf_for_box<true>(g, bits, prefix, fx, fy, fz, reach, [&](int j) {
                 const float4 sp = __ldg(spts + j);
                 const float d2 = rf_dist2(sp.x, sp.y, sp.z, fx, fy, fz);
                 if (d2 < best) { best = d2; bj = j; }
@@ -674,7 +751,7 @@ rf_evaluate_kernel(const RfIcpOut* __restrict__ icp, const int* __restrict__ cls
                    const float4* __restrict__ mnrm, const uint16_t* __restrict__ depth, const float4* __restrict__ spts,
                    const float4* __restrict__ snrm, const int* __restrict__ label, const int* __restrict__ csize,
                    const int* __restrict__ n_clusters, int cl_cap, RfGrid g, const unsigned* __restrict__ bits,
-                   const unsigned* __restrict__ prefix, RfScoreParams sp, int words_per_hyp, unsigned* __restrict__ explained,
+                   const unsigned* __restrict__ prefix, RfReach co, RfScoreParams sp, int words_per_hyp, unsigned* __restrict__ explained,
                    int* __restrict__ scene_cl /*[n][cl_cap]*/, int* __restrict__ model_cl, RfEval* __restrict__ out) {
     __shared__ double s_red[RF_THREADS / 32];
     __shared__ int s_cnt[4];  // visible, inliers, not_in_cluster, explained
@@ -724,6 +801,7 @@ rf_evaluate_kernel(const RfIcpOut* __restrict__ icp, const int* __restrict__ cls
         const float mr = (float)(mc & 255u), mg = (float)((mc >> 8) & 255u), mb = (float)((mc >> 16) & 255u);
         float best = 0.f, best_d2 = 3.4e38f;
         int best_id = -1, found = 0;
+        if (co.dil && m.radius <= co.reach && !rf_maybe_near(g, co, x, y, z)) continue;  // visible, no scene point in reach
         rf_for_box(g, bits, prefix, x, y, z, m.radius, [&](int j) {
             const float4 q = __ldg(spts + j);
             const float d2 = rf_dist2(q.x, q.y, q.z, x, y, z);
