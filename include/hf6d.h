@@ -353,6 +353,48 @@ int hf6d_refine_ms(hf6d_ctx* c, float ms[4]);
 /* Copies a buffer of the last hf6d_refine (or of a model) to the host; returns bytes written, or < 0.  dst == NULL: the size. */
 int64_t hf6d_refine_fetch(hf6d_ctx* c, int what, int arg, void* dst, size_t cap_bytes);
 
+/* ---------------------------------------------------------------------------------------------- training
+ * `HoughForest --train` (HoughForest/src/main.cpp:41-66): HFTrain::train (HoughForest/src/HFTrain.cpp:1199-1265) on the GPU.
+ *
+ *   reference interface                                       replaced by
+ *   HFTrain::setNumTrees / setMinSamples / setTestsPerNode /
+ *     setThresPerTest / setStartTreeNo / setPatchSizeInVoxels /
+ *     setVoxelSizeInM              HFTrain.h:66-118           hf6d_train_params
+ *   HFTrain::setInputPatchesFilename + getTrainSet  HFTrain.cpp:14-67   hf6d_train_forest (the training-vector file
+ *                                                             train_patch_generator writes: int32 K, int32 F, then records
+ *                                                             {int32 class, float yaw pitch roll x y z, float[F]})
+ *   HFTrain::train                 HFTrain.cpp:1199           hf6d_train_forest / hf6d_train_forest_mem
+ *   forest.txt + tree<N>.dat       HFTrain.cpp:1225-1231, HFBase.cpp:4-38   written to output_folder, read back by hf6d_create
+ *
+ * The reference draws every random number from rand() seeded with the clock, inside OpenMP threads: its forests are not
+ * reproducible.  Here the draws come from a counter-based generator keyed by `seed`; for a given seed the forest is the same
+ * bit for bit on every run (oracle/train.py restates the algorithm with the same draws and is the checker).  No CPU path. */
+typedef struct {
+    int32_t trees;                /* --trees (3) */
+    int32_t min_samples;          /* --min_samples (30): a child with at most this many samples is a leaf */
+    int32_t tests_per_node;       /* --tests_per_node (30) */
+    int32_t thresholds_per_test;  /* --thresholds_per_test (10) */
+    int32_t start_tree_no;        /* --start_tree_no (0): files tree<start> .. tree<start + trees - 1> */
+    int32_t patch_size_in_voxels; /* --patch_size_in_voxels: only copied into forest.txt */
+    float voxel_size_in_m;        /* --voxel_size_in_m: only copied into forest.txt */
+    uint64_t seed;
+    int32_t device;
+} hf6d_train_params;
+
+typedef struct {
+    int64_t nodes, leaves;        /* over all trees */
+    int32_t max_depth;
+    int32_t training_samples;     /* per tree: int(2/3 * samples), HFTrain.cpp:1143 */
+    float train_ms;               /* GPU time of all trees (CUDA events), file writing included */
+} hf6d_train_stats;
+
+void hf6d_default_train_params(hf6d_train_params* p);
+/* input_file: the training vectors (see above); output_folder must exist.  stats may be NULL.  Errors: hf6d_last_error(NULL). */
+int hf6d_train_forest(const hf6d_train_params* p, const char* input_file, const char* output_folder, hf6d_train_stats* stats);
+/* The same from memory: cls int32[n] in [0, K), dof float[n][6] = yaw, pitch, roll, x, y, z, features float[n][F]. */
+int hf6d_train_forest_mem(const hf6d_train_params* p, int n, int K, int F, const int32_t* cls, const float* dof,
+                          const float* features, const char* output_folder, hf6d_train_stats* stats);
+
 #ifdef __cplusplus
 }
 #endif

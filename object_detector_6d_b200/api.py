@@ -32,6 +32,7 @@ EXPORTS = (
     "hf6d_parse_options", "hf6d_inspect_forest", "hf6d_inspect_weights", "hf6d_debug_texture_gather",
     "hf6d_default_refine_params", "hf6d_set_refine_params", "hf6d_get_refine_params", "hf6d_set_object_model",
     "hf6d_load_object_ply", "hf6d_load_option_models", "hf6d_refine", "hf6d_refine_ms", "hf6d_refine_fetch",
+    "hf6d_default_train_params", "hf6d_train_forest", "hf6d_train_forest_mem",
 )
 
 
@@ -75,6 +76,18 @@ class RefineParams(C.Structure):
                 ("cluster_tolerance_far", C.c_float), ("cluster_min_points", C.c_int32), ("use_color_similarity", C.c_int32),
                 ("use_normal_similarity", C.c_int32), ("search_single_object_instance", C.c_int32),
                 ("search_single_object_in_group", C.c_int32), ("default_icp_iterations", C.c_int32)]
+
+
+class TrainParams(C.Structure):
+    """hf6d_train_params: the --train flags of the reference's main.cpp:13-25."""
+    _fields_ = [("trees", C.c_int32), ("min_samples", C.c_int32), ("tests_per_node", C.c_int32),
+                ("thresholds_per_test", C.c_int32), ("start_tree_no", C.c_int32), ("patch_size_in_voxels", C.c_int32),
+                ("voxel_size_in_m", C.c_float), ("seed", C.c_uint64), ("device", C.c_int32)]
+
+
+class TrainStats(C.Structure):
+    _fields_ = [("nodes", C.c_int64), ("leaves", C.c_int64), ("max_depth", C.c_int32), ("training_samples", C.c_int32),
+                ("train_ms", C.c_float)]
 
 
 DETECTION_DTYPE = np.dtype([("hypothesis", "<i4"), ("cls", "<i4"), ("pose", "<f4", (16,)), ("similarity", "<f4"),
@@ -168,6 +181,10 @@ def load():
     L.hf6d_parse_options.argtypes = [C.c_char_p, C.POINTER(Options), C.POINTER(ObjectOptions), i32]
     L.hf6d_inspect_forest.argtypes = [C.c_char_p, C.POINTER(ModelInfo)]
     L.hf6d_inspect_weights.argtypes = [C.c_char_p, C.POINTER(C.c_int32)]
+    L.hf6d_default_train_params.argtypes = [C.POINTER(TrainParams)]
+    L.hf6d_default_train_params.restype = None
+    L.hf6d_train_forest.argtypes = [C.POINTER(TrainParams), C.c_char_p, C.c_char_p, C.POINTER(TrainStats)]
+    L.hf6d_train_forest_mem.argtypes = [C.POINTER(TrainParams), i32, i32, i32, vp, vp, vp, C.c_char_p, C.POINTER(TrainStats)]
     L.hf6d_default_refine_params.argtypes = [C.POINTER(RefineParams)]
     L.hf6d_default_refine_params.restype = None
     L.hf6d_set_refine_params.argtypes = [vp, C.POINTER(RefineParams)]
@@ -189,6 +206,29 @@ def default_params(**kw) -> Params:
     for k, v in kw.items():
         setattr(p, k, v)
     return p
+
+
+def train_forest(out_dir: str, cls=None, dof=None, features=None, K: int = 0, input_file: str | None = None, **kw) -> TrainStats:
+    """HFTrain::train on the GPU (HoughForest/src/HFTrain.cpp:1199-1265): writes forest.txt + tree<N>.dat into out_dir.
+    Either input_file (the reference's training-vector file) or cls / dof / features arrays.  kw: TrainParams fields."""
+    L = load()
+    p = TrainParams()
+    L.hf6d_default_train_params(C.byref(p))
+    for k, v in kw.items():
+        setattr(p, k, v)
+    st = TrainStats()
+    os.makedirs(out_dir, exist_ok=True)
+    if input_file is not None:
+        rc = L.hf6d_train_forest(C.byref(p), input_file.encode(), out_dir.encode(), C.byref(st))
+    else:
+        cls = np.ascontiguousarray(cls, np.int32)
+        dof = np.ascontiguousarray(dof, np.float32).reshape(len(cls), 6)
+        features = np.ascontiguousarray(features, np.float32).reshape(len(cls), -1)
+        rc = L.hf6d_train_forest_mem(C.byref(p), len(cls), K, features.shape[1], cls.ctypes.data, dof.ctypes.data,
+                                     features.ctypes.data, out_dir.encode(), C.byref(st))
+    if rc < 0:
+        raise Hf6dError(rc, (L.hf6d_last_error(None) or b"").decode())
+    return st
 
 
 def _ck_host(rc):

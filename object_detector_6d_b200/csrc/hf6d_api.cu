@@ -26,6 +26,7 @@
 #include "model.hpp"
 #include "modes.cuh"
 #include "refine.cuh"
+#include "train.cuh"
 #include "texture_check.cuh"
 #include "vote.cuh"
 
@@ -1956,3 +1957,4 @@ void hf6d_pose_from_tuple(const hf6d_params* p, int cx, int cy, float z, int yaw
 }  // extern "C"
 
 #include "refine_api.inc"
+#include "train_api.inc"

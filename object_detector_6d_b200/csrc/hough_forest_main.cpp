@@ -275,6 +275,11 @@ struct Flags {
     bool test = false, train = false, other_mode = false, help = false, stage_times = false, check_inputs = false;
     std::string options_file, output_folder;
     int device = -1, encoder_mode = 0;
+    // --train (main.cpp:13-25)
+    std::string input, output = ".";
+    int trees = 3, min_samples = 30, tests_per_node = 30, thresholds_per_test = 10, start_tree_no = 0, patch_size_in_voxels = -1;
+    double voxel_size_in_m = -1;
+    unsigned long long seed = 1;
 };
 
 bool parse_bool(const std::string& v) { return !(v == "false" || v == "0" || v == "no" || v == "f" || v == "n"); }
@@ -310,10 +315,18 @@ bool parse_flags(int argc, char** argv, Flags& fl, std::string& err) {
         else if (a == "check_inputs") fl.check_inputs = has_val ? parse_bool(val) : true;
         else if (a == "show_scene" || a == "visualize_hypotheses" || a == "noshow_scene" || a == "novisualize_hypotheses") {}
         else if (a == "help" || a == "h") fl.help = true;
-        else if (a == "input" || a == "output" || a == "trees" || a == "min_samples" || a == "tests_per_node" ||
-                 a == "thresholds_per_test" || a == "threads_per_tree" || a == "threads_for_parallel_trees" ||
-                 a == "start_tree_no" || a == "patch_size_in_voxels" || a == "voxel_size_in_m" || a == "logtostderr" ||
-                 a == "v" || a == "minloglevel") { if (!need(tmp)) return false; }  // training / glog flags: accepted, unused
+        else if (a == "input") { if (!need(fl.input)) return false; }
+        else if (a == "output") { if (!need(fl.output)) return false; }
+        else if (a == "trees") { if (!need(tmp)) return false; fl.trees = atoi(tmp.c_str()); }
+        else if (a == "min_samples") { if (!need(tmp)) return false; fl.min_samples = atoi(tmp.c_str()); }
+        else if (a == "tests_per_node") { if (!need(tmp)) return false; fl.tests_per_node = atoi(tmp.c_str()); }
+        else if (a == "thresholds_per_test") { if (!need(tmp)) return false; fl.thresholds_per_test = atoi(tmp.c_str()); }
+        else if (a == "start_tree_no") { if (!need(tmp)) return false; fl.start_tree_no = atoi(tmp.c_str()); }
+        else if (a == "patch_size_in_voxels") { if (!need(tmp)) return false; fl.patch_size_in_voxels = atoi(tmp.c_str()); }
+        else if (a == "voxel_size_in_m") { if (!need(tmp)) return false; fl.voxel_size_in_m = atof(tmp.c_str()); }
+        else if (a == "seed") { if (!need(tmp)) return false; fl.seed = strtoull(tmp.c_str(), nullptr, 10); }
+        else if (a == "threads_per_tree" || a == "threads_for_parallel_trees" || a == "logtostderr" || a == "v" ||
+                 a == "minloglevel") { if (!need(tmp)) return false; }  // CPU threading / glog flags: accepted, unused
         else { err = "unknown command line flag '" + a + "'"; return false; }
     }
     return true;
@@ -323,7 +336,10 @@ const char* kUsage =
     "usage: HoughForest --test --detector_options_file=<options.txt> [--output_folder=<dir>] [--device=<n>] [--stage_times]\n"
     "                   [--encoder_mode=0|1]   0: bf16 tensor-core operands (default), 1: split bf16, ~fp32 (3x encoder time)\n"
     "       `rgb_path depth_path` pairs are read from stdin until EOF; results go to <dir><stem>_res.txt / _res.png\n"
-    "       HoughForest --check_inputs   decode the stdin pairs only and print size + FNV-1a checksum of each frame\n";
+    "       HoughForest --check_inputs   decode the stdin pairs only and print size + FNV-1a checksum of each frame\n"
+    "       HoughForest --train --input=<training vectors> --output=<forest dir> --patch_size_in_voxels=<n> --voxel_size_in_m=<m>\n"
+    "                   [--trees=3] [--min_samples=30] [--tests_per_node=30] [--thresholds_per_test=10] [--start_tree_no=0]\n"
+    "                   [--seed=1] [--device=<n>]   trains on the GPU; forest.txt + tree<N>.dat as the reference writes them\n";
 
 uint64_t fnv1a(const void* data, size_t n) {
     const uint8_t* p = static_cast<const uint8_t*>(data);
@@ -387,9 +403,36 @@ int main(int argc, char** argv) {
         return 1;
     }
     if (fl.help) { std::cout << kUsage; return 0; }
-    if (fl.train || fl.other_mode) {
-        std::cerr << "HoughForest: only --test is built here (forest training is out of scope, DESIGN.md section 6)\n";
+    if (fl.other_mode) {
+        std::cerr << "HoughForest: --learn_transitions / --save_forest_map have no implementation in the reference either (main.cpp:11-12)\n";
         return 2;
+    }
+    if (fl.train) {  // main.cpp:41-66
+        const char* bad = fl.input.empty() ? "No input file specified"
+                          : fl.output.empty() ? "No output folder specified"
+                          : fl.trees <= 0 ? "You should train at least one tree"
+                          : fl.min_samples <= 0 ? "min_samples should be greater than zero"
+                          : fl.tests_per_node <= 0 ? "There should be at least one test per node"
+                          : fl.thresholds_per_test <= 0 ? "There should be at least one threshold per test"
+                          : fl.patch_size_in_voxels <= 0 ? "You should specify the Patch Size in Voxels (--patch_size_in_voxels)"
+                          : fl.voxel_size_in_m <= 0 ? "Shoud should specify the Voxel Size in Meters (--voxel_size_in_m)" : nullptr;
+        if (bad) { std::cerr << "Check failed: " << bad << std::endl; return 1; }
+        hf6d_train_params tp;
+        hf6d_default_train_params(&tp);
+        tp.trees = fl.trees; tp.min_samples = fl.min_samples; tp.tests_per_node = fl.tests_per_node;
+        tp.thresholds_per_test = fl.thresholds_per_test; tp.start_tree_no = fl.start_tree_no;
+        tp.patch_size_in_voxels = fl.patch_size_in_voxels; tp.voxel_size_in_m = (float)fl.voxel_size_in_m;
+        tp.seed = fl.seed; tp.device = std::max(fl.device, 0);
+        std::cout << "Thread 0: Reading input..." << std::endl;  // HFTrain.cpp:1214
+        hf6d_train_stats st;
+        if (hf6d_train_forest(&tp, fl.input.c_str(), fl.output.c_str(), &st)) {
+            std::cerr << "HoughForest: training failed: " << hf6d_last_error(nullptr) << std::endl;
+            return 3;
+        }
+        for (int t = tp.start_tree_no; t < tp.start_tree_no + tp.trees; ++t) std::cout << "Tree " << t << " saved" << std::endl;
+        std::cout << tp.trees << " trees, " << st.training_samples << " training samples each, " << st.nodes << " nodes, " << st.leaves
+                  << " leaves, depth " << st.max_depth << ", " << st.train_ms / 1000.0 << "sec on the GPU" << std::endl;
+        return 0;
     }
     if (fl.check_inputs) return check_inputs();
     if (!fl.test) return 0;  // main.cpp:70-76: nothing to do without a mode flag

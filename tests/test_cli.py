@@ -47,8 +47,12 @@ def test_flags_and_modes(cli):
     assert run(cli, []).returncode == 0                       # no mode flag: nothing to do (main.cpp:70-76)
     r = run(cli, ["--test"])
     assert r.returncode == 1 and "detector_options_file" in r.stderr
-    r = run(cli, ["--train", "--input", "x", "--output=y", "--trees", "4"])
-    assert r.returncode == 2 and "only --test" in r.stderr
+    r = run(cli, ["--train", "--input", "x", "--output=y", "--trees", "4"])       # main.cpp:41-51: the flag checks of --train
+    assert r.returncode == 1 and "Patch Size in Voxels" in r.stderr
+    r = run(cli, ["--train", "--output=y", "--patch_size_in_voxels=8", "--voxel_size_in_m=0.005"])
+    assert r.returncode == 1 and "No input file specified" in r.stderr
+    r = run(cli, ["--learn_transitions"])
+    assert r.returncode == 2
     r = run(cli, ["--bogus_flag"])
     assert r.returncode == 1 and "unknown command line flag" in r.stderr
     assert "usage" in run(cli, ["-help"]).stdout
@@ -211,3 +215,31 @@ def test_cli_writes_refined_poses_when_the_meshes_exist(cli, tmp_path):
     assert changed.any() and np.all(img[changed][:, 1] == 255)  # renderObject with alpha = 1: green saturated, B and R untouched
     assert np.array_equal(img[..., 0], cs["bgr"][..., 0]) and np.array_equal(img[..., 2], cs["bgr"][..., 2])
     det.close()
+
+
+def test_train_mode_needs_a_gpu_or_reports_the_file(cli, tmp_path):
+    """--train goes to hf6d_train_forest: a missing input is reported from the C ABI; without a device it fails loudly."""
+    r = run(cli, ["--train", f"--input={tmp_path / 'absent.forest'}", f"--output={tmp_path}", "--patch_size_in_voxels=8",
+                  "--voxel_size_in_m=0.005"])
+    assert r.returncode == 3 and "Could not open file" in r.stderr
+
+
+@pytest.mark.gpu
+def test_cli_trains_the_forest_the_c_abi_trains(cli, tmp_path):
+    from oracle import train as T
+    from tests.test_train import make_samples
+    cls, dof, feat = make_samples(2000, 2, 32, seed=8)
+    src = tmp_path / "patches.forest"
+    T.write_patches_file(str(src), 2, cls, dof, feat)
+    out = tmp_path / "cli"
+    out.mkdir()
+    r = run(cli, ["--train", f"--input={src}", f"--output={out}", "--trees=2", "--min_samples=20", "--tests_per_node=6",
+                  "--thresholds_per_test=4", "--patch_size_in_voxels=8", "--voxel_size_in_m=0.005", "--seed=5",
+                  "--threads_per_tree=8"])
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "Tree 1 saved" in r.stdout
+    ref = tmp_path / "abi"
+    api.train_forest(str(ref), input_file=str(src), trees=2, min_samples=20, tests_per_node=6, thresholds_per_test=4, seed=5)
+    assert (out / "forest.txt").read_text() == (ref / "forest.txt").read_text() == "2 2 32 8 0.005\n"
+    for t in range(2):
+        assert (out / f"tree{t}.dat").read_bytes() == (ref / f"tree{t}.dat").read_bytes()
