@@ -8,13 +8,19 @@
 // format, blank line -- HFTest.cpp:1264-1290) and `<output_folder><stem>_res.png`, and prints the reference's progress
 // lines to stdout.  Unreadable images are reported and skipped (HFTest.cpp:1242-1251).
 //
-// Scope: ICP, hypothesis verification and the joint optimisation are not part of this path, so the
-// poses written are the *pre-ICP* poses (HFTest.cpp:922-924 + MeshUtils.cpp:423-440) and hypotheses are ranked by the
-// Hough terms of the reference's final score, pose_score * pose_score_coeff + location_score * location_score_coeff
-// (MeshUtils.cpp:780-784) with pose_score = (yaw-pitch score + roll score) / 2 (HFTest.cpp:934).  The result image is
-// the input colour image (the mesh overlay needs the renderer).
+// With the objects' mesh files in place every hypothesis goes through ICP, hypothesis scoring and the joint
+// optimisation on the GPU (hf6d_refine) and the poses written are the refined ones of the selected hypotheses, in final-score
+// order, at most `instances` per object, with MeshUtils::renderObject's overlay on the result image -- the reference's output.
+// Without the meshes (the reference aborts there) the *pre-ICP* poses (HFTest.cpp:922-924 + MeshUtils.cpp:423-440) are written,
+// ranked by the Hough terms of the reference's final score, pose_score * pose_score_coeff + location_score *
+// location_score_coeff (MeshUtils.cpp:780-784), and the program says so.
 //
-// Host code only: every frame goes through hf6d_submit / hf6d_wait; there is no CPU detection path in this file.
+//   HoughForest --train --input=<training vectors> --output=<dir> --patch_size_in_voxels=8 --voxel_size_in_m=0.005 [...]
+//
+// trains a forest on the GPU (main.cpp:41-66, HFTrain::train) and writes forest.txt + tree<N>.dat.
+//
+// Host code only: every frame goes through hf6d_submit / hf6d_wait (+ hf6d_refine), training through hf6d_train_forest; there
+// is no CPU detection or training path in this file.
 #include <zlib.h>
 
 #include <algorithm>
