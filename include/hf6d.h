@@ -173,8 +173,8 @@ int hf6d_set_class_shard(hf6d_ctx* c, int rank, int world);
 /* Peer exchange: the tree-sharded mode without a collective library, for the GPUs of one NVLink / NVSwitch box (one
  * process per GPU).  Every rank publishes a small blob (CUDA IPC handles of its vote maps, leaf tables and flag block),
  * the caller hands every rank all blobs (any transport: torch.distributed all_gather, MPI, a file), and from then on
- * hf6d_run exchanges nothing through the host: the kernels after the exchange point read the peers' maps and leaf tables
- * in place over NVLink, and the ranks synchronise through flags in each other's memory (see "peer exchange" in
+ * hf6d_run exchanges nothing through the host: the kernels after the exchange point read the peers' maps, vote streams (or
+ * leaf tables, when a rank keeps no stream) in place over NVLink, and the ranks synchronise through flags in each other's memory (see "peer exchange" in
  * csrc/hf6d_api.cu).  hf6d_peer_attach also sets the tree shard and the class shard to rank/world.  Contract:
  *  - the ranks of a group export, attach (and later detach) TOGETHER, with a barrier of the caller's transport between
  *    hf6d_peer_attach on every rank and the first hf6d_run on any (a rank must not signal into memory a peer has not mapped

@@ -158,6 +158,9 @@ struct hf6d_ctx {
     uint32_t* peer_flags_of[HF6D_MAX_PEERS] = {};                     // every rank's flag block (own entry = own block)
     std::vector<const unsigned long long*> peer_maps[HF6D_MAX_PEERS]; // [rank][slot]
     std::vector<const int*> peer_leaf[HF6D_MAX_PEERS];                // [rank][slot]
+    std::vector<const uint2*> peer_vstream[HF6D_MAX_PEERS];           // [rank][slot] the peers' vote streams (pose stage)
+    std::vector<const int*> peer_stream_n[HF6D_MAX_PEERS];            // [rank][slot]
+    bool peer_streams = false;                                        // every rank of the group publishes its vote stream
     std::vector<void*> peer_opened;                                   // cudaIpcOpenMemHandle results
     int* peer_timeout = nullptr;                                      // set by the fallback wait kernel when it gives up
     bool peer_wait_expired = false;                                   // a bounded host-side wait ran out (sync_stream_bounded)
@@ -684,8 +687,9 @@ int run_stage(hf6d_ctx* c, Slot& s, int stage) {
             CU_TRY(c, cudaMemsetAsync(s.maps, 0, (size_t)K * g.W * g.H * 8, st));
             const long long items = (long long)g.cap * f.T;
             const int blocks = (int)std::min<long long>((items + VOTE_THREADS - 1) / VOTE_THREADS, (long long)c->sms * 8);
-            // the vote stream serves the pose stage of THIS context: with sharded trees the windows need the other ranks' votes
-            const bool streaming = c->use_stream && c->shard_world == 1 && c->pshard.world == 1 && !c->peer_on;
+            // with a peer group the windows need the other ranks' votes too: they are read from the peers' streams in place
+            const bool streaming = c->use_stream && ((c->shard_world == 1 && c->pshard.world == 1 && !c->peer_on) ||
+                                                     (c->peer_on && c->peer_streams));
             VoteStream vs{nullptr, nullptr, 0};
             if (streaming) {
                 CU_TRY(c, cudaMemsetAsync(s.stream_n, 0, 4, st));
@@ -733,7 +737,8 @@ int run_stage(hf6d_ctx* c, Slot& s, int stage) {
             // Two implementations of pass A (HFTest.cpp:742-802).  The stream path needs the vote stream the vote kernel wrote
             // for this slot's current leaf table; sharded contexts, huge forests (stream over budget) and stage-isolated runs
             // that replaced the leaf table after voting use the enumeration path.  Both give identical accumulators.
-            const bool stream_path = c->use_stream && s.stream_valid && c->shard_world == 1 && c->pshard.world == 1 && !c->peer_on;
+            const bool stream_path = c->use_stream && s.stream_valid &&
+                                     ((c->shard_world == 1 && c->pshard.world == 1 && !c->peer_on) || (c->peer_on && c->peer_streams));
             // clear only the accumulator slots a class can use (slot = class * HF6D_MAX_CENTRES + centre rank): one launch.
             // The (slot, group) counters are left zeroed by the stream path itself (its roll pass zeroes what it visited).
             {
@@ -772,7 +777,21 @@ int run_stage(hf6d_ctx* c, Slot& s, int stage) {
             const size_t zbytes = (size_t)zt.zoff[K] * HF6D_Z_BINS * 4;
             const PairList pl{s.pairs, ctr + 5, c->pair_cap};
             if (stream_path) {
-                const VoteStream vs{s.vstream, s.stream_n, c->stream_cap};
+                StreamSet vs;
+                memset(&vs, 0, sizeof vs);
+                vs.cap = c->stream_cap;
+                if (c->peer_on) {  // every rank's stream: the votes of the whole frame, each once
+                    const int si = slot_index(c, s);
+                    vs.world = c->peer_world;
+                    for (int r = 0; r < c->peer_world; ++r) {
+                        vs.rec[r] = r == c->peer_rank ? s.vstream : c->peer_vstream[r][si];
+                        vs.n[r] = r == c->peer_rank ? s.stream_n : c->peer_stream_n[r][si];
+                    }
+                } else {
+                    vs.world = 1;
+                    vs.rec[0] = s.vstream;
+                    vs.n[0] = s.stream_n;
+                }
                 const size_t dyn = ((zbytes + 15) & ~(size_t)15) + cell_bytes;
 #define HF6D_WS(GG)                                                                                                         \
     window_stream_kernel<GG><<<c->sms, WA_THREADS, dyn, st>>>(f, g, switches_of(c, true), vs, s.depth, ct, half_win, n_groups, zt, \
@@ -1424,6 +1443,9 @@ struct PeerBlob {  // what a rank publishes: POD, exchanged by the caller (torch
     cudaIpcMemHandle_t flags;
     cudaIpcMemHandle_t maps[HF6D_MAX_SLOTS];
     cudaIpcMemHandle_t leaf[HF6D_MAX_SLOTS];
+    int32_t stream_cap;  // 0: this rank has no vote stream (then nobody uses the streams)
+    cudaIpcMemHandle_t vstream[HF6D_MAX_SLOTS];
+    cudaIpcMemHandle_t stream_n[HF6D_MAX_SLOTS];
 };
 constexpr uint32_t PEER_MAGIC = 0x36644650u;  // "PFd6"
 }  // namespace
@@ -1450,7 +1472,12 @@ int hf6d_peer_export(hf6d_ctx* c, void* blob, size_t cap_bytes) {
     for (int i = 0; i < c->n_slots; ++i) {
         CU_TRY(c, cudaIpcGetMemHandle(&b.maps[i], c->slots[i].maps));
         CU_TRY(c, cudaIpcGetMemHandle(&b.leaf[i], c->slots[i].leaf_ord));
+        if (c->use_stream) {
+            CU_TRY(c, cudaIpcGetMemHandle(&b.vstream[i], c->slots[i].vstream));
+            CU_TRY(c, cudaIpcGetMemHandle(&b.stream_n[i], c->slots[i].stream_n));
+        }
     }
+    b.stream_cap = c->use_stream ? c->stream_cap : 0;
     memcpy(blob, &b, sizeof b);
     return HF6D_OK;
 }
@@ -1498,9 +1525,15 @@ int hf6d_peer_attach(hf6d_ctx* c, int rank, int world, const void* blobs, size_t
             b.T != c->hf.T || b.cap != c->g.cap)
             return fail(c, HF6D_EINVAL, "rank %d runs a different configuration (slots / frame size / forest)", r);
     }
+    // the pose stage reads every rank's vote stream in place when all of them keep one of the same capacity; otherwise it
+    // enumerates the votes again from the ranks' leaf tables (HF6D_PEER_STREAMS=0 forces that, for the tests)
+    c->peer_streams = c->use_stream && !(getenv("HF6D_PEER_STREAMS") && atoi(getenv("HF6D_PEER_STREAMS")) == 0);
+    for (int r = 0; r < world; ++r) c->peer_streams = c->peer_streams && all[r].stream_cap == c->stream_cap;
     for (int r = 0; r < world; ++r) {
         c->peer_maps[r].assign(c->n_slots, nullptr);
         c->peer_leaf[r].assign(c->n_slots, nullptr);
+        c->peer_vstream[r].assign(c->n_slots, nullptr);
+        c->peer_stream_n[r].assign(c->n_slots, nullptr);
         if (r == rank) {
             c->peer_flags_of[r] = c->peer_flags;
             continue;
@@ -1522,6 +1555,14 @@ int hf6d_peer_attach(hf6d_ctx* c, int rank, int world, const void* blobs, size_t
             CU_TRY(c, cudaIpcOpenMemHandle(&p, b.leaf[i], cudaIpcMemLazyEnablePeerAccess));
             c->peer_opened.push_back(p);
             c->peer_leaf[r][i] = static_cast<const int*>(p);
+            if (c->peer_streams) {
+                CU_TRY(c, cudaIpcOpenMemHandle(&p, b.vstream[i], cudaIpcMemLazyEnablePeerAccess));
+                c->peer_opened.push_back(p);
+                c->peer_vstream[r][i] = static_cast<const uint2*>(p);
+                CU_TRY(c, cudaIpcOpenMemHandle(&p, b.stream_n[i], cudaIpcMemLazyEnablePeerAccess));
+                c->peer_opened.push_back(p);
+                c->peer_stream_n[r][i] = static_cast<const int*>(p);
+            }
         }
     }
     c->peer_rank = rank;

@@ -82,6 +82,13 @@ struct VoteStream {
     int* n;       // records reserved so far (zeroed before the vote kernel)
     int cap;
 };
+// The streams the pose stage reads: its own, or -- one stream of frames sharded over the GPUs of a box (peer exchange) -- the
+// stream of every rank, the peers' in place over NVLink: together they hold every vote of the frame exactly once.
+struct StreamSet {
+    const uint2* rec[HF6D_MAX_PEERS];
+    const int* n[HF6D_MAX_PEERS];
+    int world, cap;
+};
 __device__ __forceinline__ unsigned stream_pack(int u, int v, int cls) {
     const unsigned uu = (unsigned)min(max(u + STREAM_BIAS, 0), STREAM_COORD_MAX);
     const unsigned vv = (unsigned)min(max(v + STREAM_BIAS, 0), STREAM_COORD_MAX);
@@ -508,7 +515,7 @@ __device__ __forceinline__ void z_mode_warp(const unsigned long long* __restrict
 constexpr int WS_ROWS = 8;  // stream rows (of 32 records) a warp grabs at a time
 template <int G>
 __global__ void __launch_bounds__(WA_THREADS)
-window_stream_kernel(DevForest f, FrameGeom g, const __grid_constant__ ObjectSwitches sw, VoteStream stream,
+window_stream_kernel(DevForest f, FrameGeom g, const __grid_constant__ ObjectSwitches sw, const __grid_constant__ StreamSet ss,
                      const uint16_t* __restrict__ depth, CentreTable ct, int half_win, int n_groups,
                      const __grid_constant__ ZSlotTable zt, unsigned* __restrict__ cnt, PairList pl,
                      unsigned long long* __restrict__ zacc, int* __restrict__ next_chunk, int* __restrict__ done,
@@ -517,6 +524,7 @@ window_stream_kernel(DevForest f, FrameGeom g, const __grid_constant__ ObjectSwi
     __shared__ WarpRing s_ring[WA_THREADS / 32];
     __shared__ unsigned s_classes;
     __shared__ int s_last;
+    __shared__ int s_sn[HF6D_MAX_PEERS], s_sbase[HF6D_MAX_PEERS + 1];  // records and first chunk of every stream
     extern __shared__ __align__(16) uint8_t ws_smem[];
     const int nz = zt.zoff[f.K];
     unsigned* s_z = reinterpret_cast<unsigned*>(ws_smem);                                       // [nz][Z_BINS]
@@ -527,7 +535,16 @@ window_stream_kernel(DevForest f, FrameGeom g, const __grid_constant__ ObjectSwi
     const int S = f.K * HF6D_MAX_CENTRES;
     for (int i = threadIdx.x; i < nz * HF6D_Z_BINS; i += WA_THREADS) s_z[i] = 0u;
     for (int i = threadIdx.x; i < f.K * cells_per_class; i += WA_THREADS) s_cells[i] = 0;
-    if (threadIdx.x == 0) s_classes = 0;
+    if (threadIdx.x == 0) {
+        s_classes = 0;
+        int chunks = 0;
+        for (int r = 0; r < ss.world; ++r) {
+            s_sn[r] = min(*ss.n[r], ss.cap);
+            s_sbase[r] = chunks;
+            chunks += (s_sn[r] + 32 * WS_ROWS - 1) / (32 * WS_ROWS);
+        }
+        for (int r = ss.world; r <= HF6D_MAX_PEERS; ++r) s_sbase[r] = chunks;
+    }
     __syncthreads();
     for (int i = threadIdx.x; i < S; i += WA_THREADS) {
         const int c = i / HF6D_MAX_CENTRES, k = i % HF6D_MAX_CENTRES;
@@ -546,7 +563,7 @@ window_stream_kernel(DevForest f, FrameGeom g, const __grid_constant__ ObjectSwi
     const unsigned classes = s_classes;
     const int lane = threadIdx.x & 31;
     WarpRing& ring = s_ring[threadIdx.x >> 5];
-    const int n = min(*stream.n, stream.cap);
+    const int total_chunks = s_sbase[HF6D_MAX_PEERS];
 
     // bin of one vote of a leaf for a window pixel at depth zj (HFTest.cpp:770-775), unclamped / -1 outside the histogram
     auto z_bin_raw = [&](float oz, float zj) { return f2i_x86(div_const<1, 100>(__fadd_rn(oz, zj))); };  // integer part only
@@ -639,13 +656,17 @@ window_stream_kernel(DevForest f, FrameGeom g, const __grid_constant__ ObjectSwi
         int chunk = 0;
         if (lane == 0) chunk = atomicAdd(next_chunk, 1);
         chunk = __shfl_sync(0xffffffffu, chunk, 0);
-        const int base = chunk * (32 * WS_ROWS);
-        if (base >= n) break;
+        if (chunk >= total_chunks) break;
+        int which = 0;  // the stream this chunk belongs to
+        while (which + 1 < ss.world && chunk >= s_sbase[which + 1]) ++which;
+        const int base = (chunk - s_sbase[which]) * (32 * WS_ROWS);
+        const int n = s_sn[which];
+        const uint2* __restrict__ srec = ss.rec[which];
         uint2 rec[WS_ROWS];
 #pragma unroll
         for (int r = 0; r < WS_ROWS; ++r) {
             const int i = base + r * 32 + lane;
-            rec[r] = i < n ? __ldcs(stream.rec + i) : make_uint2(0u, 0u);  // read once: streaming load
+            rec[r] = i < n ? __ldcs(srec + i) : make_uint2(0u, 0u);  // read once: streaming load
         }
 #pragma unroll
         for (int r = 0; r < WS_ROWS; ++r) {
