@@ -240,7 +240,7 @@ def smooth_clusters(xyz, nrm, curv, p: RefineParams):
                     continue
                 dot = F32(F32(F32(nrm[s, 0] * nrm[j, 0]) + F32(nrm[s, 1] * nrm[j, 1])) + F32(nrm[s, 2] * nrm[j, 2]))
                 with np.errstate(invalid="ignore"):
-                    ok = abs(np.arccos(np.float64(dot))) < p.cluster_eps_angle  # R5: NaN -> False
+                    ok = abs(np.arccos(np.float64(dot))) < np.float64(F32(p.cluster_eps_angle))  # float member widened; R5: NaN -> False
                 if ok:
                     processed[j] = True
                     queue.append(int(j))
