@@ -1,12 +1,4 @@
 mkdir -p gpurun_out
-for c in c2 c3; do
-HF6D_BENCH_WATCHDOG=500 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29531 bench.py --gpus 4 --steps 3 --warmup 3 --no-refine --config $c > gpurun_out/r02k_bench_4gpu_$c.json 2> gpurun_out/r02k_bench_4gpu_$c.err
-done
-python - <<'P'
-import json
-for c in ['c2','c3']:
-  for line in open(f'gpurun_out/r02k_bench_4gpu_{c}.json'):
-    if line.startswith('{'):
-        d=json.loads(line); print(c, d['value'], d['e2e']['value'])
-        for m,v in d['sharded']['modes'].items(): print(m, v.get('frames_per_s'), v.get('bit_identical'))
-P
+timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/r02n_pytest_all.log 2>&1; tail -6 gpurun_out/r02n_pytest_all.log
+HF6D_BENCH_WATCHDOG=500 timeout 600 python bench.py > gpurun_out/r02n_bench.json 2> gpurun_out/r02n_bench.err; tail -c 300 gpurun_out/r02n_bench.err; head -c 200 gpurun_out/r02n_bench.json
+timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r02n_bench_ref.json 2> gpurun_out/r02n_bench_ref.err; head -c 300 gpurun_out/r02n_bench_ref.json
