@@ -1,4 +1,10 @@
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/r02n_pytest_all.log 2>&1; tail -6 gpurun_out/r02n_pytest_all.log
-HF6D_BENCH_WATCHDOG=500 timeout 600 python bench.py > gpurun_out/r02n_bench.json 2> gpurun_out/r02n_bench.err; tail -c 300 gpurun_out/r02n_bench.err; head -c 200 gpurun_out/r02n_bench.json
-timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r02n_bench_ref.json 2> gpurun_out/r02n_bench_ref.err; head -c 300 gpurun_out/r02n_bench_ref.json
+HF6D_BENCH_WATCHDOG=500 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29541 bench.py --gpus 8 --steps 3 --warmup 3 > gpurun_out/r02o_bench_8gpu.json 2> gpurun_out/r02o_bench_8gpu.err
+python - <<'P'
+import json
+for line in open('gpurun_out/r02o_bench_8gpu.json'):
+    if line.startswith('{'):
+        d=json.loads(line); print(d['value'], d['e2e']['value'])
+        for m,v in d.get('sharded',{}).get('modes',{}).items(): print(m, v.get('frames_per_s'), v.get('bit_identical'), v.get('unavailable'))
+P
+tail -c 400 gpurun_out/r02o_bench_8gpu.err
