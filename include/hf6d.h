@@ -395,6 +395,51 @@ int hf6d_train_forest(const hf6d_train_params* p, const char* input_file, const 
 int hf6d_train_forest_mem(const hf6d_train_params* p, int n, int K, int F, const int32_t* cls, const float* dof,
                           const float* features, const char* output_folder, hf6d_train_stats* stats);
 
+/* ---------------------------------------------------------------------------------------------- view renderer
+ * `PatchGen --render` (PatchGen/src/main.cpp:62-81): RenderViewsTesselatedSphere::generateViews
+ * (PatchGen/src/render_views_tesselated_sphere_mod.cpp:140-342) without VTK / OpenGL -- the reference's camera geometry
+ * (tessellated-sphere directions, heights, in-plane rotations, view-up rule, area-weighted focal point, 45.3105 degree view
+ * angle) and output contract (8-bit colour on white, uint16 millimetre depth with 0 = no surface, the 4 x 4 view transform
+ * of pose<N>.txt), pixels from a z-buffer triangle rasteriser on the GPU.
+ *
+ *   reference interface                                            replaced by
+ *   setPlyFileName / setTesselationLevel / setInPlaceCamRotations /
+ *     setLightings / setHeight / setStartHeight / setAboveZ / setBelowZ /
+ *     setRenderAround0 / setObjectRadius / setResolution   .h:85-150   hf6d_render_params + hf6d_renderer_create*
+ *   generateViews' camera loop                              .cpp:255-340   hf6d_renderer_view_count / hf6d_renderer_view
+ *   render_win->Render() + save_rendering's buffers         .cpp:60-104    hf6d_render
+ *
+ * Shading, fill rule and depth precision are OpenGL's in the reference and therefore choices here (oracle/render.py V1-V4). */
+typedef struct {
+    int32_t W, H;                 /* 640 x 480 */
+    float view_angle_deg;         /* vertical view angle, 45.3105 -> f = 575 px at H = 480 */
+    int32_t tesselation_level;    /* --tessel_level (1) */
+    int32_t use_vertices;         /* camera on the sphere's vertices (1, the class default) or face centres */
+    int32_t in_place_rotations;   /* --inPlaceCamRot (24) */
+    int32_t lightings;            /* --lightings (3): every view is rendered with ambient = 0, 0.1, .. */
+    int32_t heights;              /* --numHeights (4) */
+    float height_step;            /* --heightStep (0.25 m) */
+    float start_height;           /* --startHeight (0.3 m) */
+    int32_t above_z, below_z, render_around_0;
+    float object_radius;          /* --object_radius (-1: the mesh's largest extent) */
+    int32_t device;
+} hf6d_render_params;
+
+typedef struct hf6d_renderer hf6d_renderer;
+void hf6d_default_render_params(hf6d_render_params* p);
+/* ASCII PLY with coloured vertices and faces (polygons are fanned), or the mesh from memory: xyz float[n][3], rgb uint8[n][3],
+ * faces int32[m][3].  Errors: hf6d_last_error(NULL).  No CPU path. */
+int hf6d_renderer_create_ply(const hf6d_render_params* p, const char* ply_path, hf6d_renderer** out);
+int hf6d_renderer_create(const hf6d_render_params* p, const float* xyz, const uint8_t* rgb, int n_vertices, const int32_t* faces,
+                         int n_faces, hf6d_renderer** out);
+void hf6d_renderer_destroy(hf6d_renderer* r);
+/* Camera poses of generateViews in its order (direction, height, in-plane rotation); each is rendered `lightings` times by the
+ * reference.  pose: row-major 4 x 4 world -> camera, camera looking down -z, y up (what pose<N>.txt holds). */
+int hf6d_renderer_view_count(const hf6d_renderer* r);
+int hf6d_renderer_view(const hf6d_renderer* r, int view, double pose[16]);
+/* One view with any pose: bgr uint8[H][W][3] (row 0 = top), depth_mm uint16[H][W].  ambient = lighting index * 0.1. */
+int hf6d_render(hf6d_renderer* r, const double pose[16], float ambient, uint8_t* bgr, uint16_t* depth_mm);
+
 #ifdef __cplusplus
 }
 #endif

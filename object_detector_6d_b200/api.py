@@ -33,6 +33,8 @@ EXPORTS = (
     "hf6d_default_refine_params", "hf6d_set_refine_params", "hf6d_get_refine_params", "hf6d_set_object_model",
     "hf6d_load_object_ply", "hf6d_load_option_models", "hf6d_refine", "hf6d_refine_ms", "hf6d_refine_fetch",
     "hf6d_default_train_params", "hf6d_train_forest", "hf6d_train_forest_mem",
+    "hf6d_default_render_params", "hf6d_renderer_create_ply", "hf6d_renderer_create", "hf6d_renderer_destroy",
+    "hf6d_renderer_view_count", "hf6d_renderer_view", "hf6d_render",
 )
 
 
@@ -83,6 +85,14 @@ class TrainParams(C.Structure):
     _fields_ = [("trees", C.c_int32), ("min_samples", C.c_int32), ("tests_per_node", C.c_int32),
                 ("thresholds_per_test", C.c_int32), ("start_tree_no", C.c_int32), ("patch_size_in_voxels", C.c_int32),
                 ("voxel_size_in_m", C.c_float), ("seed", C.c_uint64), ("device", C.c_int32)]
+
+
+class RenderParams(C.Structure):
+    """hf6d_render_params: the --render flags of PatchGen/src/main.cpp:22-49."""
+    _fields_ = [("W", C.c_int32), ("H", C.c_int32), ("view_angle_deg", C.c_float), ("tesselation_level", C.c_int32),
+                ("use_vertices", C.c_int32), ("in_place_rotations", C.c_int32), ("lightings", C.c_int32), ("heights", C.c_int32),
+                ("height_step", C.c_float), ("start_height", C.c_float), ("above_z", C.c_int32), ("below_z", C.c_int32),
+                ("render_around_0", C.c_int32), ("object_radius", C.c_float), ("device", C.c_int32)]
 
 
 class TrainStats(C.Structure):
@@ -181,6 +191,15 @@ def load():
     L.hf6d_parse_options.argtypes = [C.c_char_p, C.POINTER(Options), C.POINTER(ObjectOptions), i32]
     L.hf6d_inspect_forest.argtypes = [C.c_char_p, C.POINTER(ModelInfo)]
     L.hf6d_inspect_weights.argtypes = [C.c_char_p, C.POINTER(C.c_int32)]
+    L.hf6d_default_render_params.argtypes = [C.POINTER(RenderParams)]
+    L.hf6d_default_render_params.restype = None
+    L.hf6d_renderer_create_ply.argtypes = [C.POINTER(RenderParams), C.c_char_p, C.POINTER(vp)]
+    L.hf6d_renderer_create.argtypes = [C.POINTER(RenderParams), vp, vp, i32, vp, i32, C.POINTER(vp)]
+    L.hf6d_renderer_destroy.argtypes = [vp]
+    L.hf6d_renderer_destroy.restype = None
+    L.hf6d_renderer_view_count.argtypes = [vp]
+    L.hf6d_renderer_view.argtypes = [vp, i32, C.POINTER(C.c_double)]
+    L.hf6d_render.argtypes = [vp, C.POINTER(C.c_double), C.c_float, vp, vp]
     L.hf6d_default_train_params.argtypes = [C.POINTER(TrainParams)]
     L.hf6d_default_train_params.restype = None
     L.hf6d_train_forest.argtypes = [C.POINTER(TrainParams), C.c_char_p, C.c_char_p, C.POINTER(TrainStats)]
@@ -229,6 +248,57 @@ def train_forest(out_dir: str, cls=None, dof=None, features=None, K: int = 0, in
     if rc < 0:
         raise Hf6dError(rc, (L.hf6d_last_error(None) or b"").decode())
     return st
+
+
+class Renderer:
+    """RenderViewsTesselatedSphere (PatchGen/src/render_views_tesselated_sphere_mod.cpp) on the GPU: hf6d_renderer_*."""
+
+    def __init__(self, xyz=None, rgb=None, faces=None, ply_path: str | None = None, **kw):
+        self._L = load()
+        self.params = RenderParams()
+        self._L.hf6d_default_render_params(C.byref(self.params))
+        for k, v in kw.items():
+            setattr(self.params, k, v)
+        self._h = C.c_void_p()
+        if ply_path is not None:
+            rc = self._L.hf6d_renderer_create_ply(C.byref(self.params), ply_path.encode(), C.byref(self._h))
+        else:
+            xyz = np.ascontiguousarray(xyz, np.float32).reshape(-1, 3)
+            rgb = np.ascontiguousarray(rgb, np.uint8).reshape(-1, 3)
+            faces = np.ascontiguousarray(faces, np.int32).reshape(-1, 3)
+            rc = self._L.hf6d_renderer_create(C.byref(self.params), xyz.ctypes.data, rgb.ctypes.data, len(xyz), faces.ctypes.data,
+                                              len(faces), C.byref(self._h))
+        if rc:
+            raise Hf6dError(rc, (self._L.hf6d_last_error(None) or b"").decode())
+
+    def view_count(self) -> int:
+        return self._L.hf6d_renderer_view_count(self._h)
+
+    def view(self, i: int) -> np.ndarray:
+        m = (C.c_double * 16)()
+        if self._L.hf6d_renderer_view(self._h, i, m):
+            raise Hf6dError(-1, (self._L.hf6d_last_error(None) or b"").decode())
+        return np.array(m, np.float64).reshape(4, 4)
+
+    def render(self, pose, ambient: float = 0.0):
+        m = (C.c_double * 16)(*np.asarray(pose, np.float64).reshape(-1))
+        bgr = np.zeros((self.params.H, self.params.W, 3), np.uint8)
+        depth = np.zeros((self.params.H, self.params.W), np.uint16)
+        rc = self._L.hf6d_render(self._h, m, ambient, bgr.ctypes.data, depth.ctypes.data)
+        if rc:
+            raise Hf6dError(rc, (self._L.hf6d_last_error(None) or b"").decode())
+        return bgr, depth
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.hf6d_renderer_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def _ck_host(rc):

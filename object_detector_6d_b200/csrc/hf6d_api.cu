@@ -7,6 +7,9 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <array>
+#include <map>
+#include <set>
 #include <cfloat>
 #include <chrono>
 #include <cmath>
@@ -27,6 +30,7 @@
 #include "modes.cuh"
 #include "refine.cuh"
 #include "train.cuh"
+#include "render.cuh"
 #include "texture_check.cuh"
 #include "vote.cuh"
 
@@ -1999,3 +2003,4 @@ void hf6d_pose_from_tuple(const hf6d_params* p, int cx, int cy, float z, int yaw
 
 #include "refine_api.inc"
 #include "train_api.inc"
+#include "render_api.inc"

@@ -242,6 +242,43 @@ bool write_png_rgb(const std::string& path, const uint8_t* bgr, int w, int h) {
     return (bool)f;
 }
 
+// 16-bit grey PNG (the renderer's depth<N>.png: millimetres, cv::imwrite of a CV_16U image)
+bool write_png_gray16(const std::string& path, const uint16_t* px, int w, int h) {
+    std::vector<uint8_t> raw(((size_t)w * 2 + 1) * h);
+    for (int y = 0; y < h; ++y) {
+        uint8_t* line = &raw[((size_t)w * 2 + 1) * y];
+        line[0] = 0;
+        for (int x = 0; x < w; ++x) {
+            const uint16_t v = px[(size_t)y * w + x];
+            line[1 + 2 * x] = (uint8_t)(v >> 8);
+            line[2 + 2 * x] = (uint8_t)v;
+        }
+    }
+    uLongf zlen = compressBound((uLong)raw.size());
+    std::vector<uint8_t> z(zlen);
+    if (compress2(z.data(), &zlen, raw.data(), (uLong)raw.size(), 1) != Z_OK) return false;
+    std::ofstream f(path.c_str(), std::ios::binary);
+    if (!f) return false;
+    auto chunk = [&](const char* type, const uint8_t* body, uint32_t len) {
+        uint8_t hdr[8] = {(uint8_t)(len >> 24), (uint8_t)(len >> 16), (uint8_t)(len >> 8), (uint8_t)len,
+                          (uint8_t)type[0], (uint8_t)type[1], (uint8_t)type[2], (uint8_t)type[3]};
+        uLong crc = crc32(0L, hdr + 4, 4);
+        if (len) crc = crc32(crc, body, len);
+        const uint8_t tail[4] = {(uint8_t)(crc >> 24), (uint8_t)(crc >> 16), (uint8_t)(crc >> 8), (uint8_t)crc};
+        f.write(reinterpret_cast<const char*>(hdr), 8);
+        if (len) f.write(reinterpret_cast<const char*>(body), len);
+        f.write(reinterpret_cast<const char*>(tail), 4);
+    };
+    static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
+    f.write(reinterpret_cast<const char*>(sig), 8);
+    const uint8_t ihdr[13] = {(uint8_t)(w >> 24), (uint8_t)(w >> 16), (uint8_t)(w >> 8), (uint8_t)w,
+                              (uint8_t)(h >> 24), (uint8_t)(h >> 16), (uint8_t)(h >> 8), (uint8_t)h, 16, 0, 0, 0, 0};
+    chunk("IHDR", ihdr, 13);
+    chunk("IDAT", z.data(), (uint32_t)zlen);
+    chunk("IEND", nullptr, 0);
+    return (bool)f;
+}
+
 // ------------------------------------------------------------------------------------------------ text output
 // Eigen's `operator<<` for a Matrix4f with the default IOFormat: stream precision (6 significant digits), every
 // coefficient right-aligned to the widest one, one space between columns, '\n' between rows (HFTest.cpp:1286).
@@ -286,6 +323,10 @@ struct Flags {
     int trees = 3, min_samples = 30, tests_per_node = 30, thresholds_per_test = 10, start_tree_no = 0, patch_size_in_voxels = -1;
     double voxel_size_in_m = -1;
     unsigned long long seed = 1;
+    // --render (PatchGen/src/main.cpp:15-49)
+    bool render = false, above_z = false, below_z = false, render_around_0 = false;
+    int tessel_level = 1, in_place_rot = 24, lightings = 3, num_heights = 4;
+    double height_step = 0.25, start_height = 0.3, object_radius = -1.0;
 };
 
 bool parse_bool(const std::string& v) { return !(v == "false" || v == "0" || v == "no" || v == "f" || v == "n"); }
@@ -331,6 +372,17 @@ bool parse_flags(int argc, char** argv, Flags& fl, std::string& err) {
         else if (a == "patch_size_in_voxels") { if (!need(tmp)) return false; fl.patch_size_in_voxels = atoi(tmp.c_str()); }
         else if (a == "voxel_size_in_m") { if (!need(tmp)) return false; fl.voxel_size_in_m = atof(tmp.c_str()); }
         else if (a == "seed") { if (!need(tmp)) return false; fl.seed = strtoull(tmp.c_str(), nullptr, 10); }
+        else if (a == "render") fl.render = has_val ? parse_bool(val) : true;
+        else if (a == "tessel_level") { if (!need(tmp)) return false; fl.tessel_level = atoi(tmp.c_str()); }
+        else if (a == "inPlaceCamRot") { if (!need(tmp)) return false; fl.in_place_rot = atoi(tmp.c_str()); }
+        else if (a == "lightings") { if (!need(tmp)) return false; fl.lightings = atoi(tmp.c_str()); }
+        else if (a == "numHeights") { if (!need(tmp)) return false; fl.num_heights = atoi(tmp.c_str()); }
+        else if (a == "heightStep") { if (!need(tmp)) return false; fl.height_step = atof(tmp.c_str()); }
+        else if (a == "startHeight") { if (!need(tmp)) return false; fl.start_height = atof(tmp.c_str()); }
+        else if (a == "object_radius") { if (!need(tmp)) return false; fl.object_radius = atof(tmp.c_str()); }
+        else if (a == "above_z") fl.above_z = has_val ? parse_bool(val) : true;
+        else if (a == "below_z") fl.below_z = has_val ? parse_bool(val) : true;
+        else if (a == "render_around_0") fl.render_around_0 = has_val ? parse_bool(val) : true;
         else if (a == "threads_per_tree" || a == "threads_for_parallel_trees" || a == "logtostderr" || a == "v" ||
                  a == "minloglevel") { if (!need(tmp)) return false; }  // CPU threading / glog flags: accepted, unused
         else { err = "unknown command line flag '" + a + "'"; return false; }
@@ -345,7 +397,10 @@ const char* kUsage =
     "       HoughForest --check_inputs   decode the stdin pairs only and print size + FNV-1a checksum of each frame\n"
     "       HoughForest --train --input=<training vectors> --output=<forest dir> --patch_size_in_voxels=<n> --voxel_size_in_m=<m>\n"
     "                   [--trees=3] [--min_samples=30] [--tests_per_node=30] [--thresholds_per_test=10] [--start_tree_no=0]\n"
-    "                   [--seed=1] [--device=<n>]   trains on the GPU; forest.txt + tree<N>.dat as the reference writes them\n";
+    "                   [--seed=1] [--device=<n>]   trains on the GPU; forest.txt + tree<N>.dat as the reference writes them\n"
+    "       HoughForest --render --input=<mesh.ply> --output=<dir> [--tessel_level=1] [--inPlaceCamRot=24] [--lightings=3]\n"
+    "                   [--numHeights=4] [--heightStep=0.25] [--startHeight=0.3] [--above_z] [--below_z] [--render_around_0]\n"
+    "                   [--object_radius=<m>]   PatchGen --render on the GPU: rgb<N>.png depth<N>.png pose<N>.txt per view\n";
 
 uint64_t fnv1a(const void* data, size_t n) {
     const uint8_t* p = static_cast<const uint8_t*>(data);
@@ -412,6 +467,53 @@ int main(int argc, char** argv) {
     if (fl.other_mode) {
         std::cerr << "HoughForest: --learn_transitions / --save_forest_map have no implementation in the reference either (main.cpp:11-12)\n";
         return 2;
+    }
+    if (fl.render) {  // PatchGen/src/main.cpp:62-81
+        if (fl.input.empty() || fl.output.empty()) { std::cerr << "Check failed: --render needs --input=<mesh.ply> and --output=<dir>" << std::endl; return 1; }
+        if (fl.tessel_level <= 0) { std::cerr << "Check failed: FLAGS_tessel_level > 0" << std::endl; return 1; }
+        if (fl.in_place_rot <= 0) { std::cerr << "Check failed: FLAGS_inPlaceCamRot > 0" << std::endl; return 1; }
+        hf6d_render_params rp;
+        hf6d_default_render_params(&rp);
+        rp.tesselation_level = fl.tessel_level; rp.in_place_rotations = fl.in_place_rot; rp.lightings = fl.lightings;
+        rp.heights = fl.num_heights; rp.height_step = (float)fl.height_step; rp.start_height = (float)fl.start_height;
+        rp.above_z = fl.above_z; rp.below_z = fl.below_z; rp.render_around_0 = fl.render_around_0;
+        rp.object_radius = (float)fl.object_radius; rp.device = std::max(fl.device, 0);
+        hf6d_renderer* rd = nullptr;
+        if (hf6d_renderer_create_ply(&rp, fl.input.c_str(), &rd)) {
+            std::cerr << "HoughForest: cannot render " << fl.input << ": " << hf6d_last_error(nullptr) << std::endl;
+            return 3;
+        }
+        const int nv = hf6d_renderer_view_count(rd);
+        std::cout << "Total number of viewpoints: " << (long long)nv * rp.lightings << std::endl;  // .cpp:239-240
+        std::vector<uint8_t> img((size_t)rp.W * rp.H * 3);
+        std::vector<uint16_t> dep((size_t)rp.W * rp.H);
+        int fcounter = 0, rc2 = 0;
+        for (int v = 0; v < nv && !rc2; ++v) {
+            double pose[16];
+            hf6d_renderer_view(rd, v, pose);
+            for (int light = 0; light < rp.lightings; ++light, ++fcounter) {  // SetAmbient(light * 0.1), .cpp:315
+                if (hf6d_render(rd, pose, (float)(light * 0.1), img.data(), dep.data())) {
+                    std::cerr << "HoughForest: " << hf6d_last_error(nullptr) << std::endl;
+                    rc2 = 3;
+                    break;
+                }
+                const std::string n = std::to_string(fcounter);
+                if (!write_png_rgb(fl.output + "/rgb" + n + ".png", img.data(), rp.W, rp.H) ||
+                    !write_png_gray16(fl.output + "/depth" + n + ".png", dep.data(), rp.W, rp.H)) {
+                    std::cerr << "Check failed: cannot write into " << fl.output << std::endl;
+                    rc2 = 1;
+                    break;
+                }
+                std::ofstream fpose((fl.output + "/pose" + n + ".txt").c_str());  // the view transform, .cpp:126-137
+                for (int i = 0; i < 4; ++i) {
+                    for (int j = 0; j < 4; ++j) { fpose << pose[4 * i + j]; if (j != 3) fpose << " "; }
+                    fpose << std::endl;
+                }
+            }
+        }
+        hf6d_renderer_destroy(rd);
+        if (!rc2) std::cout << "Rendered " << fcounter << " views into " << fl.output << std::endl;
+        return rc2;
     }
     if (fl.train) {  // main.cpp:41-66
         const char* bad = fl.input.empty() ? "No input file specified"

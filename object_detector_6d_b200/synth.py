@@ -211,6 +211,73 @@ def object_models(object_seed: int, n_objects: int = 6, spacing: float = 0.002):
     return out
 
 
+def object_meshes(object_seed: int, n_objects: int = 6, spacing: float = 0.004):
+    """The solids of object_models as triangle meshes (vertices on a `spacing` lattice per face, two triangles per lattice
+    cell, outward winding): what the reference's renderer reads from meshes/*.ply.  Returns [(xyz f32 [n,3], rgb u8 [n,3],
+    faces i32 [m,3])]."""
+    rng = np.random.default_rng(object_seed)
+    out = []
+    for _ in range(n_objects):
+        kind = int(rng.integers(0, 2))
+        size = rng.uniform(0.05, 0.2, 3)
+        base = rng.uniform(40, 230, 3)
+        tkind, freq = int(rng.integers(0, 3)), rng.uniform(15, 60)
+        verts, faces = [], []
+
+        def add_grid(P, flip):  # P: [na, nb, 3] lattice of one face
+            na, nb = P.shape[:2]
+            off = sum(len(v) for v in verts)
+            verts.append(P.reshape(-1, 3))
+            idx = off + np.arange(na * nb).reshape(na, nb)
+            a, b, c, d = idx[:-1, :-1].ravel(), idx[1:, :-1].ravel(), idx[1:, 1:].ravel(), idx[:-1, 1:].ravel()
+            t = np.concatenate([np.stack([a, b, c], 1), np.stack([a, c, d], 1)])
+            faces.append(t[:, ::-1] if flip else t)
+
+        if kind == 0:
+            hs = size * 0.5
+            for ax in range(3):
+                a, b = [k for k in range(3) if k != ax]
+                ga = np.linspace(-hs[a], hs[a], max(2, int(np.ceil(2 * hs[a] / spacing)) + 1))
+                gb = np.linspace(-hs[b], hs[b], max(2, int(np.ceil(2 * hs[b] / spacing)) + 1))
+                A, B = np.meshgrid(ga, gb, indexing="ij")
+                for sgn in (-1.0, 1.0):
+                    q = np.zeros(A.shape + (3,))
+                    q[..., a], q[..., b], q[..., ax] = A, B, sgn * hs[ax]
+                    n = np.cross(q[1, 0] - q[0, 0], q[0, 1] - q[0, 0])  # normal of the (a, b, c) winding
+                    add_grid(q, flip=bool(n[ax] * sgn < 0))
+        else:
+            r, hh = size[0] * 0.5, size[1] * 0.5
+            n_ang = max(8, int(np.ceil(2 * np.pi * r / spacing)))
+            ang = np.linspace(0, 2 * np.pi, n_ang + 1)
+            ys = np.linspace(-hh, hh, max(2, int(np.ceil(2 * hh / spacing)) + 1))
+            A, Y = np.meshgrid(ang, ys, indexing="ij")
+            side = np.stack([r * np.cos(A), Y, r * np.sin(A)], -1)
+            n = np.cross(side[1, 0] - side[0, 0], side[0, 1] - side[0, 0])
+            add_grid(side, flip=bool(np.dot(n, side[0, 0] * [1, 0, 1]) < 0))
+            rad = np.linspace(0, r, max(2, int(np.ceil(r / spacing)) + 1))
+            Rr, Aa = np.meshgrid(rad, ang, indexing="ij")
+            for sgn in (-1.0, 1.0):
+                cap = np.stack([Rr * np.cos(Aa), np.full(Rr.shape, sgn * hh), Rr * np.sin(Aa)], -1)
+                n = np.cross(cap[1, 0] - cap[0, 0], cap[1, 1] - cap[1, 0])
+                add_grid(cap, flip=bool(n[1] * sgn < 0))
+        xyz = np.concatenate(verts).astype(np.float32)
+        col = np.clip(_texture(xyz.astype(np.float64), base, tkind, freq) * 0.8, 0, 255)
+        out.append((xyz, np.ascontiguousarray(np.rint(col[:, ::-1]).astype(np.uint8)), np.concatenate(faces).astype(np.int32)))
+    return out
+
+
+def write_ply_mesh(path: str, xyz: np.ndarray, rgb: np.ndarray, faces: np.ndarray) -> None:
+    """ASCII PLY with coloured vertices and triangles, readable by vtkPLYReader and by MeshUtils::getPointCloudFromPLY."""
+    with open(path, "w") as f:
+        f.write("ply\nformat ascii 1.0\nelement vertex %d\nproperty float x\nproperty float y\nproperty float z\n"
+                "property uchar red\nproperty uchar green\nproperty uchar blue\nproperty uchar alpha\n"
+                "element face %d\nproperty list uchar int vertex_indices\nend_header\n" % (len(xyz), len(faces)))
+        for (x, y, z), (r, g, b) in zip(xyz.tolist(), rgb.tolist()):
+            f.write("%.6f %.6f %.6f %d %d %d 255\n" % (x, y, z, r, g, b))
+        for a, b, c in faces.tolist():
+            f.write("3 %d %d %d\n" % (a, b, c))
+
+
 def write_ply(path: str, xyz: np.ndarray, rgb: np.ndarray) -> None:
     """ASCII PLY with `x y z r g b a` per vertex, the only layout MeshUtils::getPointCloudFromPLY reads
     (HoughForest/src/MeshUtils.cpp:68-114)."""

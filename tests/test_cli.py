@@ -243,3 +243,34 @@ def test_cli_trains_the_forest_the_c_abi_trains(cli, tmp_path):
     assert (out / "forest.txt").read_text() == (ref / "forest.txt").read_text() == "2 2 32 8 0.005\n"
     for t in range(2):
         assert (out / f"tree{t}.dat").read_bytes() == (ref / f"tree{t}.dat").read_bytes()
+
+
+def test_render_mode_flags(cli, tmp_path):
+    r = run(cli, ["--render"])
+    assert r.returncode == 1 and "--input" in r.stderr
+    r = run(cli, ["--render", f"--input={tmp_path / 'absent.ply'}", f"--output={tmp_path}"])
+    assert r.returncode == 3 and "not found" in r.stderr
+
+
+@pytest.mark.gpu
+def test_cli_renders_the_views_the_c_abi_renders(cli, tmp_path):
+    """PatchGen --render (PatchGen/src/main.cpp:62-81): rgb<N>.png, depth<N>.png, pose<N>.txt per view and lighting."""
+    xyz, rgb, faces = synth.object_meshes(1000, 1, 0.008)[0]
+    mesh = tmp_path / "obj.ply"
+    synth.write_ply_mesh(str(mesh), xyz, rgb, faces)
+    out = tmp_path / "views"
+    out.mkdir()
+    r = run(cli, ["--render", f"--input={mesh}", f"--output={out}", "--tessel_level=1", "--inPlaceCamRot=1", "--numHeights=1",
+                  "--lightings=2", "--above_z"])
+    assert r.returncode == 0, r.stdout + r.stderr
+    rd = api.Renderer(ply_path=str(mesh), tesselation_level=1, in_place_rotations=1, heights=1, lightings=2, above_z=1)
+    n = rd.view_count()
+    assert f"Total number of viewpoints: {2 * n}" in r.stdout and len(list(out.glob("rgb*.png"))) == 2 * n
+    for v in (0, n - 1):
+        for light in range(2):
+            k = 2 * v + light
+            bgr, depth = rd.render(rd.view(v), np.float32(light * 0.1))
+            assert np.array_equal(cv2.imread(str(out / f"rgb{k}.png")), bgr)
+            assert np.array_equal(cv2.imread(str(out / f"depth{k}.png"), cv2.IMREAD_UNCHANGED), depth)
+            np.testing.assert_allclose(np.loadtxt(str(out / f"pose{k}.txt")), rd.view(v), rtol=1e-5, atol=1e-6)
+    rd.close()
