@@ -440,6 +440,62 @@ int hf6d_renderer_view(const hf6d_renderer* r, int view, double pose[16]);
 /* One view with any pose: bgr uint8[H][W][3] (row 0 = top), depth_mm uint16[H][W].  ambient = lighting index * 0.1. */
 int hf6d_render(hf6d_renderer* r, const double pose[16], float ambient, uint8_t* bgr, uint16_t* depth_mm);
 
+/* ---------------------------------------------------------------------------------------------- patch database + training vectors
+ * The files between PatchGen and HoughForest --train, in the reference's own formats, so that either side of a reference
+ * training run can be swapped for this library:
+ *
+ *   reference                                                                   replaced by
+ *   mdb_env_open / mdb_put / mdb_txn_commit of "%04d_%08d" -> caffe::Datum       hf6d_patchdb_create / _put / _close
+ *     patch_generator.cpp:479-493, 562-580 (read back by Caffe's DATA layer)
+ *   mdb_cursor_get(MDB_FIRST / MDB_NEXT) + Datum::ParseFromArray                 hf6d_patchdb_open / _next
+ *     train_patch_generator.cpp:33-52, 79-101
+ *   patch_generator::get_yaw_pitch_roll_from_rot_mat + get_object_coords        hf6d_patch_annotation
+ *     patch_generator.cpp:20-56 (one line of patch_annotation_lmdb.txt)
+ *   patch_extractor_gpu::extract_patches_rgbd + the normalisation of            hf6d_create_extractor, then hf6d_upload +
+ *     insert_patches_to_db_rgbd (patch_generator.cpp:382-470: the same            hf6d_run(SCAN..GATHER) + hf6d_fetch(LOCS /
+ *     arithmetic as HFTest.cpp:500-570)                                           PATCH_U8): the Datum bytes
+ *   train_patch_generator::generate_train_patches                               hf6d_generate_train_vectors (hf6d_encode_patches
+ *     train_patch_generator.cpp:22-200                                            per batch of database entries)
+ *
+ * data.mdb is LMDB's format version 1 with 4096-byte pages (lmdb 0.9.x on x86-64), written as one compact committed tree;
+ * the reader follows the current meta page of any such file.  Keys must be put in ascending order (patch_generator's are).
+ * Host code, except hf6d_encode_patches / hf6d_generate_train_vectors, whose encoder has no CPU path. */
+typedef struct hf6d_patchdb hf6d_patchdb;
+int hf6d_patchdb_create(const char* folder, hf6d_patchdb** out); /* folder must exist and hold no data.mdb */
+int hf6d_patchdb_open(const char* folder, hf6d_patchdb** out);
+/* One patch: data = uint8[channels][height][width]; label = object index (Datum.label). */
+int hf6d_patchdb_put(hf6d_patchdb* db, const char* key, int channels, int height, int width, int label, const uint8_t* data);
+int64_t hf6d_patchdb_entries(const hf6d_patchdb* db);
+/* Next entry in key order: 1 = filled, 0 = end of the database, < 0 = error.  dims = {channels, height, width, label};
+ * *n_data = bytes of Datum.data (copied when they fit cap_bytes, HF6D_EINVAL when they do not). */
+int hf6d_patchdb_next(hf6d_patchdb* db, char key[64], int32_t dims[4], uint8_t* data, size_t cap_bytes, size_t* n_data);
+int hf6d_patchdb_close(hf6d_patchdb* db); /* a writer commits here; frees the handle either way */
+
+/* (yaw, pitch, roll, x, y, z) of a patch centred on pixel (x, y) with depth_mm, seen under the view transform `pose`
+ * (row-major 4 x 4, what pose<N>.txt holds): the vote the forest is trained on.  Focal length from the vertical view angle. */
+void hf6d_patch_annotation(int W, int H, float view_angle_deg, int x, int y, uint16_t depth_mm, const float pose[16],
+                           float out[6]);
+
+/* A context that only extracts patches and encodes them: no forest is read (TRAVERSE and later stages vote for nothing);
+ * weights_path may be NULL when only SCAN..GATHER will run (the auto-encoder does not exist yet when patches are generated).
+ * p->patch_vox and p->voxel_m are taken from p (there is no forest.txt to overrule them). */
+int hf6d_create_extractor(const hf6d_params* p, const char* weights_path, int device, hf6d_ctx** out);
+int hf6d_patch_capacity(const hf6d_ctx* c); /* most patches one frame / one hf6d_encode_patches call can hold */
+/* The encoder over caller-held quantised patches (uint8[n][C*ps*ps], CHW: Datum.data): features float[n][F]. */
+int hf6d_encode_patches(hf6d_ctx* c, int slot, const uint8_t* patches, int n, float* features);
+
+typedef struct {
+    int64_t entries;   /* in the database */
+    int64_t written;   /* training vectors written: batch_size * floor((entries - 1) / batch_size) -- the reference stops
+                          at the batch in which the cursor reaches the end (train_patch_generator.cpp:98-106) */
+    int32_t classes, feature_length;
+    float encode_ms;
+} hf6d_trainvec_stats;
+/* lmdb_folder: data.mdb + patch_annotation_lmdb.txt.  output_file: int32 K, int32 F, then per patch int32 object, float
+ * yaw pitch roll x y z, float[F] (what hf6d_train_forest reads).  stats may be NULL.  Errors: hf6d_last_error(NULL). */
+int hf6d_generate_train_vectors(const char* weights_path, const char* lmdb_folder, const char* output_file, int batch_size,
+                                int device, int encoder_mode, hf6d_trainvec_stats* stats);
+
 #ifdef __cplusplus
 }
 #endif

@@ -35,6 +35,8 @@ EXPORTS = (
     "hf6d_default_train_params", "hf6d_train_forest", "hf6d_train_forest_mem",
     "hf6d_default_render_params", "hf6d_renderer_create_ply", "hf6d_renderer_create", "hf6d_renderer_destroy",
     "hf6d_renderer_view_count", "hf6d_renderer_view", "hf6d_render",
+    "hf6d_patchdb_create", "hf6d_patchdb_open", "hf6d_patchdb_put", "hf6d_patchdb_entries", "hf6d_patchdb_next", "hf6d_patchdb_close",
+    "hf6d_patch_annotation", "hf6d_create_extractor", "hf6d_patch_capacity", "hf6d_encode_patches", "hf6d_generate_train_vectors",
 )
 
 
@@ -98,6 +100,11 @@ class RenderParams(C.Structure):
 class TrainStats(C.Structure):
     _fields_ = [("nodes", C.c_int64), ("leaves", C.c_int64), ("max_depth", C.c_int32), ("training_samples", C.c_int32),
                 ("train_ms", C.c_float)]
+
+
+class TrainVecStats(C.Structure):
+    _fields_ = [("entries", C.c_int64), ("written", C.c_int64), ("classes", C.c_int32), ("feature_length", C.c_int32),
+                ("encode_ms", C.c_float)]
 
 
 DETECTION_DTYPE = np.dtype([("hypothesis", "<i4"), ("cls", "<i4"), ("pose", "<f4", (16,)), ("similarity", "<f4"),
@@ -215,6 +222,19 @@ def load():
     L.hf6d_refine_ms.argtypes = [vp, C.POINTER(C.c_float)]
     L.hf6d_refine_fetch.argtypes = [vp, i32, i32, vp, C.c_size_t]
     L.hf6d_refine_fetch.restype = i64
+    L.hf6d_patchdb_create.argtypes = [C.c_char_p, C.POINTER(vp)]
+    L.hf6d_patchdb_open.argtypes = [C.c_char_p, C.POINTER(vp)]
+    L.hf6d_patchdb_put.argtypes = [vp, C.c_char_p, i32, i32, i32, i32, vp]
+    L.hf6d_patchdb_entries.argtypes = [vp]
+    L.hf6d_patchdb_entries.restype = i64
+    L.hf6d_patchdb_next.argtypes = [vp, C.c_char_p, C.POINTER(C.c_int32), vp, C.c_size_t, C.POINTER(C.c_size_t)]
+    L.hf6d_patchdb_close.argtypes = [vp]
+    L.hf6d_patch_annotation.argtypes = [i32, i32, C.c_float, i32, i32, C.c_uint16, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    L.hf6d_patch_annotation.restype = None
+    L.hf6d_create_extractor.argtypes = [C.POINTER(Params), C.c_char_p, i32, C.POINTER(vp)]
+    L.hf6d_patch_capacity.argtypes = [vp]
+    L.hf6d_encode_patches.argtypes = [vp, i32, vp, i32, vp]
+    L.hf6d_generate_train_vectors.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, i32, i32, i32, C.POINTER(TrainVecStats)]
     _lib = L
     return L
 
@@ -306,6 +326,65 @@ def _ck_host(rc):
         raise Hf6dError(rc, (load().hf6d_last_error(None) or b"").decode())
 
 
+class PatchDb:
+    """The reference's LMDB patch database (PatchGen/src/patch_generator.cpp:479-493, train_patch_generator.cpp:33-101):
+    hf6d_patchdb_*.  mode "w": put() in ascending key order, close() commits; mode "r": iterate (key, dims, data)."""
+
+    def __init__(self, folder: str, mode: str = "r"):
+        self._L = load()
+        self._h = C.c_void_p()
+        fn = self._L.hf6d_patchdb_create if mode == "w" else self._L.hf6d_patchdb_open
+        _ck_host(fn(folder.encode(), C.byref(self._h)))
+
+    def put(self, key: str, data, label: int):
+        data = np.ascontiguousarray(data, np.uint8)
+        ch, h, w = data.shape
+        _ck_host(self._L.hf6d_patchdb_put(self._h, key.encode(), ch, h, w, label, data.ctypes.data))
+
+    def entries(self) -> int:
+        return self._L.hf6d_patchdb_entries(self._h)
+
+    def __iter__(self):
+        key = C.create_string_buffer(64)
+        dims = (C.c_int32 * 4)()
+        buf = np.zeros(1 << 20, np.uint8)
+        n = C.c_size_t()
+        while True:
+            rc = self._L.hf6d_patchdb_next(self._h, key, dims, buf.ctypes.data, buf.nbytes, C.byref(n))
+            _ck_host(rc)
+            if rc == 0:
+                return
+            yield key.value.decode(), tuple(dims), buf[:n.value].copy()
+
+    def close(self):
+        if getattr(self, "_h", None):
+            h, self._h = self._h, None
+            _ck_host(self._L.hf6d_patchdb_close(h))
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def patch_annotation(W, H, x, y, depth_mm, pose, view_angle_deg: float = 45.3105) -> np.ndarray:
+    """One line of patch_annotation_lmdb.txt: (yaw, pitch, roll, x, y, z) (patch_generator.cpp:20-56).  Host arithmetic."""
+    m = (C.c_float * 16)(*np.asarray(pose, np.float32).reshape(-1))
+    out = (C.c_float * 6)()
+    load().hf6d_patch_annotation(W, H, view_angle_deg, int(x), int(y), int(depth_mm), m, out)
+    return np.array(out, np.float32)
+
+
+def generate_train_vectors(weights_path: str, lmdb_folder: str, output_file: str, batch_size: int = 1, device: int = 0,
+                           encoder_mode: int = 0) -> TrainVecStats:
+    """train_patch_generator::generate_train_patches (PatchGen/src/train_patch_generator.cpp:22-200), encoder on the GPU."""
+    st = TrainVecStats()
+    _ck_host(load().hf6d_generate_train_vectors(weights_path.encode(), lmdb_folder.encode(), output_file.encode(), batch_size,
+                                                device, encoder_mode, C.byref(st)))
+    return st
+
+
 def parse_options(path: str):
     """Host-only: a DetectorOptions text file -> (Options, [object dicts]).  Raises Hf6dError on a malformed file."""
     o = Options()
@@ -363,10 +442,13 @@ class Detector:
     """
 
     def __init__(self, forest_dir=None, weights_path=None, params: Params | None = None, device: int = 0,
-                 n_slots: int = 1, options_path: str | None = None, frame_size=None):
+                 n_slots: int = 1, options_path: str | None = None, frame_size=None, extractor: bool = False):
         self._L = load()
         self._h = C.c_void_p()
-        if options_path is not None:
+        if extractor:  # no forest: patches (SCAN..GATHER) and, with weights, features (hf6d_create_extractor)
+            rc = self._L.hf6d_create_extractor(C.byref(params), weights_path.encode() if weights_path else None, device,
+                                               C.byref(self._h))
+        elif options_path is not None:
             W, H = frame_size or (640, 480)
             rc = self._L.hf6d_create_from_options(options_path.encode(), W, H, device, n_slots, C.byref(self._h))
         else:
@@ -529,6 +611,16 @@ class Detector:
         if n < 0:
             self._ck(n)
         return n
+
+    def patch_capacity(self) -> int:
+        return self._L.hf6d_patch_capacity(self._h)
+
+    def encode_patches(self, patches, slot: int = 0) -> np.ndarray:
+        """The encoder over caller-held quantised patches uint8[n][C*ps*ps] (Datum.data): float[n][F]."""
+        patches = np.ascontiguousarray(patches, np.uint8).reshape(len(patches), -1)
+        out = np.zeros((len(patches), self.F), np.float32)
+        self._ck(self._L.hf6d_encode_patches(self._h, slot, patches.ctypes.data, len(patches), out.ctypes.data))
+        return out
 
     def set_debug_capture(self, on: bool):
         self._ck(self._L.hf6d_set_debug_capture(self._h, int(on)))

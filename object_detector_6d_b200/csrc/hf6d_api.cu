@@ -31,6 +31,7 @@
 #include "refine.cuh"
 #include "train.cuh"
 #include "render.cuh"
+#include "patchdb.hpp"
 #include "texture_check.cuh"
 #include "vote.cuh"
 
@@ -2004,3 +2005,4 @@ void hf6d_pose_from_tuple(const hf6d_params* p, int cx, int cy, float z, int yaw
 #include "refine_api.inc"
 #include "train_api.inc"
 #include "render_api.inc"
+#include "patchdb_api.inc"

@@ -327,6 +327,11 @@ struct Flags {
     bool render = false, above_z = false, below_z = false, render_around_0 = false;
     int tessel_level = 1, in_place_rot = 24, lightings = 3, num_heights = 4;
     double height_step = 0.25, start_height = 0.3, object_radius = -1.0;
+    // --genpatches / --gentrainpatches (PatchGen/src/main.cpp:16-37)
+    bool genpatches = false, gentrainpatches = false, lmdb = false, binfile = false, no_random_values = false, use_surface_normals = false;
+    int patch_size = 20, stride = 10, gpu = -1, batch_size = 1;
+    double voxel_size = 0.001, distance_threshold = 3.0, max_depth_range_in_m = 0.25, percent = 1.0;
+    std::string caffe_definition, caffe_weights;
 };
 
 bool parse_bool(const std::string& v) { return !(v == "false" || v == "0" || v == "no" || v == "f" || v == "n"); }
@@ -383,6 +388,22 @@ bool parse_flags(int argc, char** argv, Flags& fl, std::string& err) {
         else if (a == "above_z") fl.above_z = has_val ? parse_bool(val) : true;
         else if (a == "below_z") fl.below_z = has_val ? parse_bool(val) : true;
         else if (a == "render_around_0") fl.render_around_0 = has_val ? parse_bool(val) : true;
+        else if (a == "genpatches") fl.genpatches = has_val ? parse_bool(val) : true;
+        else if (a == "gentrainpatches") fl.gentrainpatches = has_val ? parse_bool(val) : true;
+        else if (a == "lmdb") fl.lmdb = has_val ? parse_bool(val) : true;
+        else if (a == "binfile") fl.binfile = has_val ? parse_bool(val) : true;
+        else if (a == "no_random_values") fl.no_random_values = has_val ? parse_bool(val) : true;
+        else if (a == "use_surface_normals") fl.use_surface_normals = has_val ? parse_bool(val) : true;
+        else if (a == "patch_size") { if (!need(tmp)) return false; fl.patch_size = atoi(tmp.c_str()); }
+        else if (a == "stride") { if (!need(tmp)) return false; fl.stride = atoi(tmp.c_str()); }
+        else if (a == "gpu") { if (!need(tmp)) return false; fl.gpu = atoi(tmp.c_str()); }
+        else if (a == "batch_size") { if (!need(tmp)) return false; fl.batch_size = atoi(tmp.c_str()); }
+        else if (a == "voxel_size") { if (!need(tmp)) return false; fl.voxel_size = atof(tmp.c_str()); }
+        else if (a == "distance_threshold") { if (!need(tmp)) return false; fl.distance_threshold = atof(tmp.c_str()); }
+        else if (a == "max_depth_range_in_m") { if (!need(tmp)) return false; fl.max_depth_range_in_m = atof(tmp.c_str()); }
+        else if (a == "percent") { if (!need(tmp)) return false; fl.percent = atof(tmp.c_str()); }
+        else if (a == "caffe_definition") { if (!need(fl.caffe_definition)) return false; }
+        else if (a == "caffe_weights") { if (!need(fl.caffe_weights)) return false; }
         else if (a == "threads_per_tree" || a == "threads_for_parallel_trees" || a == "logtostderr" || a == "v" ||
                  a == "minloglevel") { if (!need(tmp)) return false; }  // CPU threading / glog flags: accepted, unused
         else { err = "unknown command line flag '" + a + "'"; return false; }
@@ -400,7 +421,13 @@ const char* kUsage =
     "                   [--seed=1] [--device=<n>]   trains on the GPU; forest.txt + tree<N>.dat as the reference writes them\n"
     "       HoughForest --render --input=<mesh.ply> --output=<dir> [--tessel_level=1] [--inPlaceCamRot=24] [--lightings=3]\n"
     "                   [--numHeights=4] [--heightStep=0.25] [--startHeight=0.3] [--above_z] [--below_z] [--render_around_0]\n"
-    "                   [--object_radius=<m>]   PatchGen --render on the GPU: rgb<N>.png depth<N>.png pose<N>.txt per view\n";
+    "                   [--object_radius=<m>]   PatchGen --render on the GPU: rgb<N>.png depth<N>.png pose<N>.txt per view\n"
+    "       HoughForest --genpatches --input=<view dir of object 0>,<of object 1>,.. --output=<dir> [--lmdb | --binfile]\n"
+    "                   [--patch_size=20] [--voxel_size=0.001] [--stride=10] [--no_random_values] [--distance_threshold=3]\n"
+    "                   [--max_depth_range_in_m=0.25] [--percent=1] [--seed=1]   PatchGen --genpatches: data.mdb (LMDB, Datum\n"
+    "                   per patch) + patch_annotation_lmdb.txt + patch_info_lmdb.txt, patches extracted on the GPU\n"
+    "       HoughForest --gentrainpatches --caffe_weights=<weights> --input=<lmdb dir> --output=<training vectors>\n"
+    "                   [--batch_size=1] [--gpu=0] [--encoder_mode=0|1|2]   PatchGen --gentrainpatches, encoder on the GPU\n";
 
 uint64_t fnv1a(const void* data, size_t n) {
     const uint8_t* p = static_cast<const uint8_t*>(data);
@@ -513,6 +540,149 @@ int main(int argc, char** argv) {
         }
         hf6d_renderer_destroy(rd);
         if (!rc2) std::cout << "Rendered " << fcounter << " views into " << fl.output << std::endl;
+        return rc2;
+    }
+    if (fl.gentrainpatches) {  // PatchGen/src/main.cpp:117-136
+        if (fl.caffe_weights.empty()) { std::cerr << "Check failed: FLAGS_caffe_weights.size() > 0 No caffe weights model defined." << std::endl; return 1; }
+        if (fl.input.empty()) { std::cerr << "Check failed: FLAGS_input.size() > 0 No input lmdb specified." << std::endl; return 1; }
+        if (fl.output.empty() || fl.output == ".") { std::cerr << "Check failed: FLAGS_output.size() > 0 No output file specified." << std::endl; return 1; }
+        // --caffe_definition is accepted and unused: the layer shapes are in the weights file (encode1..3)
+        hf6d_trainvec_stats st;
+        const int dev = fl.gpu >= 0 ? fl.gpu : std::max(fl.device, 0);  // the reference's --gpu=-1 means Caffe on the CPU; there is no CPU path here
+        if (hf6d_generate_train_vectors(fl.caffe_weights.c_str(), fl.input.c_str(), fl.output.c_str(), fl.batch_size, dev, fl.encoder_mode, &st)) {
+            std::cerr << "HoughForest: " << hf6d_last_error(nullptr) << std::endl;
+            return 3;
+        }
+        std::cout << "Total patches: " << st.written << std::endl;  // train_patch_generator.cpp:197
+        return 0;
+    }
+    if (fl.genpatches) {  // PatchGen/src/main.cpp:83-115, patch_generator::generatePatches_rgbd
+        std::vector<std::string> folders;
+        {
+            std::string cur;
+            for (char ch : fl.input + ",") {  // boost::split(.., is_any_of(", "))
+                if (ch == ',' || ch == ' ') { if (!cur.empty()) folders.push_back(cur); cur.clear(); }
+                else cur += ch;
+            }
+        }
+        if (folders.empty()) { std::cerr << "Check failed: input_object_folders_.size() != 0 No input objects specified" << std::endl; return 1; }
+        if (fl.use_surface_normals) {
+            std::cerr << "HoughForest: --use_surface_normals reads surface_normals<N>.bin files no renderer writes (the reference keeps the flag 'always set to false', PatchGen/src/main.cpp:41-42)" << std::endl;
+            return 2;
+        }
+        if (!fl.lmdb && !fl.binfile) { std::cout << "No output method specified, using lmdb by default" << std::endl; fl.lmdb = true; }
+        if (!fl.lmdb && !fl.no_random_values) {
+            std::cerr << "HoughForest: --binfile holds the float patches of the texture gather, which has no random fill: add --no_random_values" << std::endl;
+            return 2;
+        }
+        const std::string kind = fl.lmdb ? "lmdb" : "bin";
+        std::ofstream finfo((fl.output + "/patch_info_" + kind + ".txt").c_str());
+        if (!finfo) { std::cerr << "Check failed: finfo Cannot open file " << fl.output << "/patch_info_" << kind << ".txt for writing." << std::endl; return 1; }
+        std::ofstream fannot((fl.output + "/patch_annotation_" + kind + ".txt").c_str());
+        if (!fannot) { std::cerr << "Check failed: fannot Cannot open file " << fl.output << "/patch_annotation_" << kind << ".txt for writing." << std::endl; return 1; }
+        fannot << folders.size() << std::endl;
+        hf6d_patchdb* db = nullptr;
+        if (fl.lmdb && hf6d_patchdb_create(fl.output.c_str(), &db)) {
+            std::cerr << "Check failed: mdb_open failed. Does the lmdb already exist? (" << hf6d_last_error(nullptr) << ")" << std::endl;
+            return 1;
+        }
+        const float voxel = (float)fl.voxel_size, range = (float)fl.max_depth_range_in_m;
+        finfo << "Patch size in voxels: " << fl.patch_size << std::endl;
+        finfo << "Voxel size in m: " << voxel << std::endl;
+        finfo << "Stride in pixels: " << fl.stride << std::endl;
+        finfo << "Max Depth Range: " << range << std::endl;
+        hf6d_ctx* ex = nullptr;
+        int W = 0, H = 0, rc2 = 0;
+        const int ps = fl.patch_size, n_in = 4 * ps * ps;
+        std::vector<uint8_t> bgr, q;
+        std::vector<uint16_t> depth;
+        std::vector<int32_t> locs;
+        std::vector<float> fpatches;
+        long long total = 0;
+        auto keep = [&](int obj, int file, int i) {  // `rand() % 100 <= percent * 100` (patch_extractor.cu:378) with counted draws
+            if (fl.percent >= 1.0) return true;
+            uint64_t x = fl.seed * 0x9E3779B97F4A7C15ull + ((uint64_t)obj << 48 ^ (uint64_t)file << 24 ^ (uint64_t)i);
+            x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull; x ^= x >> 27; x *= 0x94D049BB133111EBull; x ^= x >> 31;
+            return (double)(x % 100) <= fl.percent * 100;
+        };
+        for (size_t obj = 0; obj < folders.size() && !rc2; ++obj) {
+            const std::string name = folders[obj].substr(folders[obj].find_last_of('/') + 1);
+            std::cout << "Creating patches for object: " << name << std::endl;
+            std::ofstream fbin;
+            if (!fl.lmdb) {
+                fbin.open((fl.output + "/" + name + ".bin").c_str(), std::ios::out | std::ios::binary);
+                if (!fbin) { std::cerr << "Check failed: fout Output file " << fl.output << "/" << name << " cannot be openned." << std::endl; rc2 = 1; break; }
+                fbin.write((const char*)&ps, 4); fbin.write((const char*)&voxel, 4); fbin.write((const char*)&range, 4);
+            }
+            long long n_obj = 0;
+            int patch_id = 0;
+            for (int file = 0;; ++file) {
+                const std::string base = folders[obj] + "/", n = std::to_string(file);
+                Image rgb, dep;
+                std::string err;
+                if (!load_image(base + "rgb" + n + ".png", rgb, err)) break;  // cv::imread(..).empty(): the end of the views
+                if (!load_image(base + "depth" + n + ".png", dep, err)) { std::cerr << "Check failed: !depth.empty() File " << base << "depth" << n << ".png not exist, while the rgb file does." << std::endl; rc2 = 1; break; }
+                std::ifstream fpose((base + "pose" + n + ".txt").c_str());
+                float pose[16];
+                bool pose_ok = (bool)fpose;
+                for (int k = 0; k < 16 && pose_ok; ++k) pose_ok = (bool)(fpose >> pose[k]);
+                if (!pose_ok) { std::cerr << "Check failed: fpose File " << base << "pose" << n << ".txt not exist, while the rgb and depth files does." << std::endl; rc2 = 1; break; }
+                if (!ex) {
+                    W = rgb.w; H = rgb.h;
+                    hf6d_params p;
+                    hf6d_default_params(&p);
+                    p.W = W; p.H = H; p.stride = fl.stride;
+                    p.fx = p.fy = (float)H / 2.0f / (float)tan((double)(45.3105f / 180.0f * 3.141592f / 2.0f));  // getFocalLength, patch_generator.h:43-45
+                    p.cx = (float)W / 2.0f - 0.5f; p.cy = (float)H / 2.0f - 0.5f;
+                    p.patch_vox = ps; p.voxel_m = voxel; p.max_depth_range_m = range; p.distance_threshold_m = (float)fl.distance_threshold;
+                    p.fill_random = !fl.no_random_values; p.fill_seed = fl.seed; p.batch_size = 1; p.patch_mode = 0;
+                    if (hf6d_create_extractor(&p, nullptr, std::max(fl.device, 0), &ex)) { std::cerr << "HoughForest: " << hf6d_last_error(nullptr) << std::endl; rc2 = 3; break; }
+                    bgr.resize((size_t)W * H * 3); depth.resize((size_t)W * H);
+                    const size_t cap = (size_t)hf6d_patch_capacity(ex);
+                    q.resize(cap * n_in); locs.resize(cap * 2);
+                }
+                if (rgb.w != W || rgb.h != H || dep.w != W || dep.h != H) { std::cerr << "HoughForest: " << base << "rgb" << n << ".png is not " << W << " x " << H << " like the first view" << std::endl; rc2 = 1; break; }
+                to_bgr8(rgb, bgr.data());
+                if (!to_depth16(dep, depth.data(), err)) { std::cerr << "HoughForest: " << base << "depth" << n << ".png: " << err << std::endl; rc2 = 1; break; }
+                int counts[2] = {0, 0};
+                if (hf6d_upload(ex, 0, bgr.data(), depth.data()) || hf6d_run(ex, 0, HF6D_STAGE_SCAN, HF6D_STAGE_GATHER) ||
+                    hf6d_fetch(ex, 0, HF6D_BUF_COUNTS, counts, sizeof counts) < 0 ||
+                    hf6d_fetch(ex, 0, HF6D_BUF_LOCS, locs.data(), locs.size() * 4) < 0 ||
+                    hf6d_fetch(ex, 0, HF6D_BUF_PATCH_U8, q.data(), q.size()) < 0) {
+                    std::cerr << "HoughForest: " << hf6d_last_error(ex) << std::endl; rc2 = 3; break;
+                }
+                const int P = counts[1];
+                if (!fl.lmdb) {
+                    fpatches.resize((size_t)P * n_in);
+                    if (P && hf6d_debug_texture_gather(ex, 0, fpatches.data(), fpatches.size() * 4) < 0) { std::cerr << "HoughForest: " << hf6d_last_error(ex) << std::endl; rc2 = 3; break; }
+                }
+                int kept = 0;
+                for (int i = 0; i < P && !rc2; ++i) {
+                    if (!keep((int)obj, file, i)) continue;
+                    ++kept;
+                    if (!fl.lmdb) { fbin.write((const char*)&fpatches[(size_t)i * n_in], (std::streamsize)n_in * 4); continue; }
+                    char key[20];
+                    snprintf(key, sizeof key, "%04d_%08d", (int)obj, patch_id++);
+                    if (hf6d_patchdb_put(db, key, 4, ps, ps, (int)obj, &q[(size_t)i * n_in])) { std::cerr << "Check failed: mdb_put failed (" << hf6d_last_error(nullptr) << ")" << std::endl; rc2 = 1; break; }
+                    const int x = locs[2 * i], y = locs[2 * i + 1];
+                    float a[6];
+                    hf6d_patch_annotation(W, H, 45.3105f, x, y, depth[(size_t)y * W + x], pose, a);
+                    fannot << key << " " << a[0] << " " << a[1] << " " << a[2] << " " << a[3] << " " << a[4] << " " << a[5] << std::endl;
+                }
+                n_obj += kept;
+                std::cout << "Extracted patches from file: " << file + 1 << "\r";
+            }
+            total += n_obj;
+            std::cout << std::endl;
+            std::cout << "Patches for " << name << ": " << n_obj << std::endl;
+            finfo << "Patches for " << name << ": " << n_obj << std::endl;
+        }
+        if (ex) hf6d_destroy(ex);
+        if (db && hf6d_patchdb_close(db) && !rc2) { std::cerr << "Check failed: mdb_txn_commit failed (" << hf6d_last_error(nullptr) << ")" << std::endl; rc2 = 1; }
+        if (!rc2) {
+            std::cout << "Finished! Total patches: " << total << std::endl;
+            finfo << "Total patches: " << total << std::endl;
+        }
         return rc2;
     }
     if (fl.train) {  // main.cpp:41-66

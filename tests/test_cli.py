@@ -274,3 +274,111 @@ def test_cli_renders_the_views_the_c_abi_renders(cli, tmp_path):
             assert np.array_equal(cv2.imread(str(out / f"depth{k}.png"), cv2.IMREAD_UNCHANGED), depth)
             np.testing.assert_allclose(np.loadtxt(str(out / f"pose{k}.txt")), rd.view(v), rtol=1e-5, atol=1e-6)
     rd.close()
+
+
+def test_patch_generation_flags(cli, tmp_path):
+    r = run(cli, ["--genpatches", f"--output={tmp_path}"])
+    assert r.returncode == 1 and "No input objects specified" in r.stderr
+    r = run(cli, ["--genpatches", "--input=a,b", f"--output={tmp_path}", "--use_surface_normals"])
+    assert r.returncode == 2 and "surface_normals" in r.stderr
+    r = run(cli, ["--genpatches", "--binfile", "--input=a", f"--output={tmp_path}"])
+    assert r.returncode == 2 and "--no_random_values" in r.stderr
+    r = run(cli, ["--gentrainpatches", "--input=x", "--output=y"])
+    assert r.returncode == 1 and "No caffe weights model defined" in r.stderr
+    r = run(cli, ["--gentrainpatches", "--caffe_weights=w", "--output=y"])
+    assert r.returncode == 1 and "No input lmdb specified" in r.stderr
+    r = run(cli, ["--gentrainpatches", "--caffe_weights=w", f"--input={tmp_path / 'absent'}", "--output=y"])
+    assert r.returncode == 3 and "cannot open" in r.stderr
+    # no views at all: an empty but valid database and the reference's bookkeeping files (no device is touched)
+    out = tmp_path / "db"
+    out.mkdir()
+    r = run(cli, ["--genpatches", f"--input={tmp_path / 'obj0'}, {tmp_path / 'obj1'}", f"--output={out}"])
+    assert r.returncode == 0 and "using lmdb by default" in r.stdout and "Finished! Total patches: 0" in r.stdout
+    assert (out / "patch_annotation_lmdb.txt").read_text() == "2\n"
+    assert "Patches for obj1: 0" in (out / "patch_info_lmdb.txt").read_text()
+    from oracle import patchdb as OP
+    assert OP.read_lmdb(str(out)) == []
+    r = run(cli, ["--genpatches", f"--input={tmp_path / 'obj0'}", f"--output={out}"])
+    assert r.returncode == 1 and "Does the lmdb already exist?" in r.stderr
+
+
+@pytest.mark.gpu
+def test_cli_patch_database_chain(cli, tmp_path):
+    """PatchGen --render -> --genpatches --lmdb -> --gentrainpatches -> HoughForest --train, every file in the reference's
+    format: the database read by the independent reader, Datum bytes = the oracle's gather + normalisation of the view,
+    annotation lines = the numpy restatement, training vectors = the fp32 oracle encoder of the stored patches."""
+    from oracle import oracle as OR
+    from oracle import patchdb as OP
+    folders = []
+    for o in range(2):
+        xyz, rgb, faces = synth.object_meshes(1000 + o, 1, 0.008)[0]
+        mesh = tmp_path / f"obj{o}.ply"
+        synth.write_ply_mesh(str(mesh), xyz, rgb, faces)
+        d = tmp_path / f"object{o}"
+        d.mkdir()
+        r = run(cli, ["--render", f"--input={mesh}", f"--output={d}", "--tessel_level=1", "--inPlaceCamRot=1", "--numHeights=1",
+                      "--lightings=1", "--above_z"])
+        assert r.returncode == 0, r.stdout + r.stderr
+        folders.append(str(d))
+    db = tmp_path / "patches"
+    db.mkdir()
+    r = run(cli, ["--genpatches", "--lmdb", "--input=" + ",".join(folders), f"--output={db}", "--patch_size=8", "--voxel_size=0.005",
+                  "--stride=4", "--no_random_values", "--max_depth_range_in_m=0.25"])
+    assert r.returncode == 0, r.stdout + r.stderr
+    entries = OP.read_lmdb(str(db))
+    annot = (db / "patch_annotation_lmdb.txt").read_text().split("\n")
+    assert annot[0] == "2" and len(annot) == len(entries) + 2
+    focal = np.float32(240.0) / np.float32(np.tan(np.float64(np.float32(45.3105) / np.float32(180.0) * np.float32(3.141592) / np.float32(2.0))))
+    p = OR.default_params(W=640, H=480, stride=4, fx=float(focal), fy=float(focal), cx=319.5, cy=239.5, patch_vox=8, voxel_m=0.005,
+                          max_depth_range_m=0.25, distance_threshold_m=3.0, fill_random=0, batch_size=1)
+    e = 0
+    per_obj = []
+    for o, d in enumerate(folders):
+        pid = 0
+        v = 0
+        while os.path.exists(f"{d}/rgb{v}.png"):
+            bgr = cv2.imread(f"{d}/rgb{v}.png")
+            depth = cv2.imread(f"{d}/depth{v}.png", cv2.IMREAD_UNCHANGED)
+            pose = np.loadtxt(f"{d}/pose{v}.txt").astype(np.float32)
+            locs = OR.scan_centres(depth, p)
+            q = OR.normalise(OR.gather(bgr, depth, p, locs))
+            for i in range(len(locs)):
+                key, val = entries[e]
+                assert key == b"%04d_%08d" % (o, pid)
+                assert val == OP.datum_bytes(4, 8, 8, q[i].tobytes(), o), (o, v, i)
+                x, y = locs[i]
+                want = OP.annotation(640, 480, x, y, depth[y, x], pose)
+                got = annot[1 + e].split(" ")
+                assert got[0] == key.decode()
+                np.testing.assert_allclose(np.array(got[1:], np.float64), want, rtol=2e-5, atol=2e-6)
+                e += 1
+                pid += 1
+            v += 1
+        assert v > 0
+        per_obj.append(pid)
+    assert e == len(entries) and min(per_obj) > 50
+    info = (db / "patch_info_lmdb.txt").read_text()
+    assert f"Patches for object1: {per_obj[1]}" in info and f"Total patches: {e}" in info and "Voxel size in m: 0.005" in info
+    # training vectors
+    layers = synth.make_encoder_weights(3)
+    w = str(tmp_path / "w.bin")
+    synth.write_weights_raw(w, layers)
+    vec = tmp_path / "patches.forest"
+    r = run(cli, ["--gentrainpatches", f"--caffe_weights={w}", "--caffe_definition=unused.prototxt", f"--input={db}", f"--output={vec}",
+                  "--batch_size=1", "--gpu=0", "--encoder_mode=1"])
+    assert r.returncode == 0 and f"Total patches: {e - 1}" in r.stdout, r.stdout + r.stderr
+    raw = vec.read_bytes()
+    rec = np.frombuffer(raw[8:], np.uint8).reshape(e - 1, 28 + 3200)
+    assert np.frombuffer(raw[:8], "<i4").tolist() == [2, 800]
+    assert np.array_equal(rec[:, :4].copy().view("<i4")[:, 0], [int(k[:4]) for k, _ in entries[:-1]])
+    q_all = np.stack([np.frombuffer(OP.parse_datum(v)["data"], np.uint8) for _, v in entries[:-1]])
+    assert np.abs(rec[:, 28:].copy().view("<f4") - OR.encode(q_all, layers)).max() < 1e-4
+    dof = rec[:, 4:28].copy().view("<f4")
+    np.testing.assert_array_equal(dof, np.array([[np.float32(t) for t in a.split(" ")[1:]] for a in annot[1:e]], np.float32))
+    # and the forest trainer takes the file
+    forest = tmp_path / "forest"
+    forest.mkdir()
+    r = run(cli, ["--train", f"--input={vec}", f"--output={forest}", "--trees=1", "--patch_size_in_voxels=8", "--voxel_size_in_m=0.005",
+                  "--min_samples=20", "--tests_per_node=8", "--thresholds_per_test=4"])
+    assert r.returncode == 0 and (forest / "tree0.dat").exists(), r.stdout + r.stderr
+    assert (forest / "forest.txt").read_text().split()[:3] == ["1", "2", "800"]
