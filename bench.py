@@ -303,14 +303,15 @@ def run_reference(args, rank, world):
 
 
 # ------------------------------------------------------------------------------------------------ CUDA arm
-def stage_work(cfg, Pp, votes_cast, T, K):
-    """ALGORITHMIC bytes / flops of one frame per stage (what the rooflines divide by)."""
+def stage_work(cfg, Pp, votes_cast, T, K, feature_bytes=4):
+    """ALGORITHMIC bytes / flops of one frame per stage (what the rooflines divide by).  The feature rows
+    are counted at the width they are stored in (4 bytes in SURVEY.md; 2 with fp16 feature rows, hf6d_set_feature_storage)."""
     W, H = 640 * cfg["scale"], 480 * cfg["scale"]
     return {
         "scan": (W * H * 2 + Pp * 8, "hbm"),                                   # depth once + patch centres
         "gather": (W * H * 5 + Pp * 256, "hbm"),                               # frame once + uint8 patches
         "encode": (Pp * ENC_FLOP_PER_PATCH, "tensor"),
-        "traverse": (Pp * 800 * 4 + Pp * T * 4, "hbm"),                        # fp32 features once + leaf ids
+        "traverse": (Pp * 800 * feature_bytes + Pp * T * 4, "hbm"),            # feature rows once + leaf ids
         "vote": (Pp * T * 4 + votes_cast * 28 + K * W * H * 4, "hbm"),         # leaf ids + 28 B per vote + maps once
         "centres": (K * W * H * 4 * 2, "hbm"),                                 # blur + NMS: maps read + written
         "pose": (Pp * T * 4 + votes_cast * 28, "hbm"),                         # the votes once more (HFTest.cpp:757-802)
@@ -338,6 +339,9 @@ def run_cuda(args, rank, world, local_rank):
         n_slots = args.slots
         det = api.Detector(forest_dir, wpath, p, device=local_rank, n_slots=n_slots)
         det.set_encoder_mode(args.encoder_mode)
+        if args.feature_storage is not None:
+            det.set_feature_storage(args.feature_storage)
+        feature_storage = det.feature_storage() if args.encoder_mode != 1 else 0  # the split mode always stores fp32 rows
         T, K = det.T, det.K
 
         # ---- device-resident inputs
@@ -410,6 +414,8 @@ def run_cuda(args, rank, world, local_rank):
         stage_ms, enc_ms = serial_pass(det)
         det1 = api.Detector(forest_dir, wpath, p, device=local_rank, n_slots=1)
         det1.set_encoder_mode(args.encoder_mode)
+        if args.feature_storage is not None:
+            det1.set_feature_storage(args.feature_storage)
         stage_ms1, enc_ms1 = serial_pass(det1)
         enc_ms_other = {}
         for m in (0, 1, 2):  # the other encoder modes on the latency context, for the record
@@ -534,7 +540,7 @@ def run_cuda(args, rank, world, local_rank):
             fps = frames_total / sec
             ms_frame = ms_total / (BATCH * args.steps)
             Pp = Pp_mean
-            alg = stage_work(cfg, Pp, votes_mean, T, K)
+            alg = stage_work(cfg, Pp, votes_mean, T, K, feature_bytes=2 if feature_storage else 4)
 
             def table(ms_vec):
                 out = {}
@@ -586,7 +592,11 @@ def run_cuda(args, rank, world, local_rank):
                 "encoder_mode": {"mode": args.encoder_mode,
                                  "name": ("bf16 operands", "split bf16 (hi + lo operands, ~fp32)", "fp16 operands")[args.encoder_mode],
                                  "other_modes_encoder_layer_ms": enc_ms_other,
-                                 "parity": "profiles/r02_parity.json (end to end against the fp32 oracle, both modes)"},
+                                 "parity": "profiles/r02_parity.json (end to end against the fp32 oracle, every mode and both "
+                                           "feature storages)"},
+                "feature_storage": {"storage": feature_storage,
+                                    "name": ("fp32 rows", "fp16 rows (feature layer rounds its fp32 sigmoid once; the traversal compares "
+                                             "the exact widening)")[feature_storage]},
                 "ms_per_frame": ms_frame, "traversals_per_s": fps * Pp * T,
                 "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "timing": "wall clock around hf6d_submit/hf6d_wait with pinned host frames, device sync both sides",
@@ -718,6 +728,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-refine", action="store_true", help="skip the ICP / scoring stage report (SURVEY.md 8(f)1)")
     ap.add_argument("--slots", type=int, default=4, help="frames in flight (one stream + workspace each)")
+    ap.add_argument("--feature-storage", type=int, default=None, choices=[0, 1],
+                    help="0 = fp32 feature rows, 1 = fp16 rows (default: the library's, 1 where the feature layer supports it)")
     ap.add_argument("--encoder-mode", type=int, default=0, choices=[0, 1, 2],
                     help="0: bf16 tensor-core operands (the headline), 1: split bf16 (~fp32 products, 3x the encoder time), "
                          "2: fp16 operands (same rate as 0)")

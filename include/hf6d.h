@@ -103,7 +103,7 @@ typedef enum {
     HF6D_BUF_COUNTS = 0,   /* int32[2]  = P (valid centres), P' (processed) */
     HF6D_BUF_LOCS = 1,     /* int32[P][2] = (x, y) */
     HF6D_BUF_PATCH_U8 = 2, /* uint8[P'][C*ps*ps] quantised CHW patches, C = 4 or 6 (only when debug capture is on) */
-    HF6D_BUF_FEATURES = 3, /* float[P'][F] */
+    HF6D_BUF_FEATURES = 3, /* float[P'][F] (feature storage 1: the fp32 widening of the stored fp16 rows) */
     HF6D_BUF_LEAF_ORD = 4, /* int32[P'][T]: file-order ordinal of the leaf inside its tree; -1 for trees not owned */
     HF6D_BUF_MAPS = 5,     /* uint64[K][H][W] Q16 vote sums */
     HF6D_BUF_BLURRED = 6,  /* float[K][H][W] */
@@ -207,6 +207,20 @@ int hf6d_peer_timed_out(hf6d_ctx* c); /* 1 if a flag wait gave up (host-side dea
  * Synchronises the device; the first switch to mode 1 allocates the hi/lo activation buffers of every slot. */
 int hf6d_set_encoder_mode(hf6d_ctx* c, int mode);
 int hf6d_get_encoder_mode(const hf6d_ctx* c);
+/* Feature storage between the encoder and the forest (the reference keeps the Caffe output blob in fp32 and reads it in
+ * HFTest::get_leaf, HoughForest/src/HFTest.cpp:144-163, 595-628):
+ *   0 = fp32 rows, float[P'][F];
+ *   1 = fp16 rows: the feature layer of encoder modes 0 / 2 rounds its fp32 sigmoid once to fp16 and the traversal reads
+ *       those rows (half the HBM bytes of both kernels; sigmoid outputs lie in (0,1), the rounding is <= 2.5e-4, two orders
+ *       below the bf16 operand error of mode 0).  Every leaf test compares the exact fp32 widening of the stored half, and
+ *       that widening is what HF6D_BUF_FEATURES returns (hf6d_fetch / hf6d_device_ptr / hf6d_encode_patches), so everything
+ *       downstream stays bit-exact on the handed-out values.  Features injected with hf6d_inject are fp32 rows and are
+ *       traversed as such.  Encoder mode 1 (the near-fp32 mode) always stores fp32.
+ * Default: 1 where the feature layer has a kernel for it (F a multiple of 160, or 256-wide feature tiles), else 0;
+ * HF6D_FEATURES=fp32 in the environment makes 0 the default.  Synchronises the device; the first switch to 1 allocates the
+ * fp16 rows of every slot. */
+int hf6d_set_feature_storage(hf6d_ctx* c, int storage);
+int hf6d_get_feature_storage(const hf6d_ctx* c);
 int hf6d_set_debug_capture(hf6d_ctx* c, int on); /* keep HF6D_BUF_PATCH_U8 */
 
 /* ---------------------------------------------------------------------------------------------- host-only helpers */

@@ -25,7 +25,8 @@ EXPORTS = (
     "hf6d_default_params", "hf6d_create", "hf6d_create_from_options", "hf6d_destroy", "hf6d_last_error",
     "hf6d_get_params", "hf6d_model", "hf6d_set_objects", "hf6d_get_objects", "hf6d_set_fill_seed",
     "hf6d_set_tree_shard", "hf6d_set_patch_shard", "hf6d_set_peer_split", "hf6d_set_class_shard", "hf6d_peer_blob_bytes", "hf6d_peer_export", "hf6d_peer_attach",
-    "hf6d_peer_detach", "hf6d_peer_timed_out", "hf6d_set_encoder_mode", "hf6d_get_encoder_mode", "hf6d_set_debug_capture", "hf6d_detect", "hf6d_submit",
+    "hf6d_peer_detach", "hf6d_peer_timed_out", "hf6d_set_encoder_mode", "hf6d_get_encoder_mode", "hf6d_set_feature_storage", "hf6d_get_feature_storage",
+    "hf6d_set_debug_capture", "hf6d_detect", "hf6d_submit",
     "hf6d_wait", "hf6d_host_alloc", "hf6d_host_free", "hf6d_upload", "hf6d_run", "hf6d_sync", "hf6d_collect",
     "hf6d_fetch", "hf6d_inject", "hf6d_device_ptr", "hf6d_set_stream", "hf6d_stage_ms", "hf6d_launch_count",
     "hf6d_pose_from_tuple", "hf6d_count_cast_votes", "hf6d_bind_frame", "hf6d_encoder_layer_ms", "hf6d_result_bytes",
@@ -166,6 +167,8 @@ def load():
     L.hf6d_peer_timed_out.argtypes = [vp]
     L.hf6d_set_encoder_mode.argtypes = [vp, i32]
     L.hf6d_get_encoder_mode.argtypes = [vp]
+    L.hf6d_set_feature_storage.argtypes = [vp, i32]
+    L.hf6d_get_feature_storage.argtypes = [vp]
     L.hf6d_count_cast_votes.restype = C.c_int64
     L.hf6d_count_cast_votes.argtypes = [vp, i32]
     L.hf6d_set_debug_capture.argtypes = [vp, i32]
@@ -605,6 +608,13 @@ class Detector:
 
     def encoder_mode(self) -> int:
         return int(self._L.hf6d_get_encoder_mode(self._h))
+
+    def set_feature_storage(self, storage: int):
+        """0 = fp32 feature rows, 1 = fp16 rows written by the feature layer and read by the traversal (modes 0 / 2)."""
+        self._ck(self._L.hf6d_set_feature_storage(self._h, int(storage)))
+
+    def feature_storage(self) -> int:
+        return int(self._L.hf6d_get_feature_storage(self._h))
 
     def count_cast_votes(self, slot: int = 0) -> int:
         n = int(self._L.hf6d_count_cast_votes(self._h, slot))

@@ -83,6 +83,14 @@ __device__ __forceinline__ int patch_shard_owner(int Pp, int world, int p) {
     return r;
 }
 
+// Blocking host -> device copy whose data is IN device memory on return.  A plain cudaMemcpy from pageable memory returns once
+// the bytes are staged; the DMA may still be in flight, and the kernels that read the destination run on non-blocking streams
+// that do not order themselves behind the legacy stream -- so wait for the legacy stream as well.
+inline cudaError_t memcpy_h2d_done(void* dst, const void* src, size_t bytes) {
+    const cudaError_t e = cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice);
+    return e != cudaSuccess ? e : cudaStreamSynchronize(cudaStreamLegacy);
+}
+
 // patch_extractor.cu:257 / :378 -- ((ps*vox)/d)*f in fp32, truncated
 __device__ __forceinline__ int adaptive_size(const FrameGeom& g, float depth_m) {
     return (int)__fmul_rn(__fdiv_rn(__fmul_rn((float)g.ps, g.vox), depth_m), g.focal);

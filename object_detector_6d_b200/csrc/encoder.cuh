@@ -100,6 +100,7 @@ __device__ __forceinline__ void split_pair_bf16(float y0, float y1, uint32_t& hi
 // LAST=false : out is bf16 [m_cap][n_pad], all BLOCK_N columns stored (padded columns hold sigma(0)=0.5 and meet
 //              zero weight columns in the next layer); `bias` holds 0.5*b (the tanh form wants x/2)
 // LAST=true  : out is fp32 [m_cap][n_valid]; columns >= n_valid are clipped by the TMA store
+// OUT16      : (LAST only) out is fp16 [m_cap][n_valid] -- the feature storage the traversal can read at half the HBM bytes
 // tmC is the output tensor map: boxes of 32 rows x CHUNK_BYTES, swizzle = CHUNK_BYTES.
 // PAIR = 2   : the two CTAs of a cluster take the m-blocks 2*g and 2*g + 1 of the SAME n-block (a missing last m-block is
 //              computed on whatever the padded rows hold and clipped by the TMA store).  tmB has a box of BLOCK_N / 2 rows:
@@ -108,7 +109,8 @@ __device__ __forceinline__ void split_pair_bf16(float y0, float y1, uint32_t& hi
 //                          producers' TMA loads complete on it (cp.async.bulk.tensor.cta_group::2)
 //                empty[s]  one per CTA: tcgen05.commit.cta_group::2 multicast frees the stage in both
 //                tfull[a]  one per CTA, same multicast commit; tempty[a] in the even CTA counts the epilogue warps of both
-template <int BLOCK_N, bool LAST, int STAGES, int EPI_BUFS, int PAIR, int CHUNK_BYTES, int EPI_WARPS, bool SPLIT = false>
+template <int BLOCK_N, bool LAST, int STAGES, int EPI_BUFS, int PAIR, int CHUNK_BYTES, int EPI_WARPS, bool SPLIT = false,
+          bool OUT16 = false>
 __global__ void __launch_bounds__((4 + EPI_WARPS) * 32, 1)
 encoder_layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const __grid_constant__ CUtensorMap tmC, const float* __restrict__ bias,
@@ -117,6 +119,7 @@ encoder_layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     using S = EncSmem<BLOCK_N, STAGES, EPI_BUFS, PAIR, CHUNK_BYTES, EPI_WARPS>;
     static_assert(PAIR == 1 || PAIR == 2, "stand-alone CTAs or CTA pairs");
     static_assert(EPI_WARPS % 4 == 0, "every TMEM lane quadrant needs the same number of epilogue warps");
+    static_assert(!OUT16 || (LAST && !SPLIT), "fp16 storage is for the feature layer of the bf16 / fp16 operand modes");
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
@@ -268,7 +271,7 @@ encoder_layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const int q = warp & 3;               // TMEM lane quadrant this warp may touch
         const int sub = (warp - 4) >> 2;      // the warps of a quadrant take the column chunks round-robin
         constexpr int SUBS = EPI_WARPS / 4;
-        constexpr int CHUNK_COLS = CHUNK_BYTES / (LAST ? 4 : 2);  // output columns per staged chunk
+        constexpr int CHUNK_COLS = CHUNK_BYTES / ((LAST && !OUT16) ? 4 : 2);  // output columns per staged chunk
         constexpr int TILE_CHUNKS = BLOCK_N / CHUNK_COLS;
         constexpr int UNITS = CHUNK_BYTES / 16;                   // 16-byte units per staged row
         static_assert(BLOCK_N % CHUNK_COLS == 0, "the tile must be a whole number of chunks");
@@ -340,6 +343,17 @@ encoder_layer_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                             o[2 * j + 1] = sigmoid_pair_bf16(fmaf(__uint_as_float(v[4 * j + 2]), 0.5f, b.z),
                                                              fmaf(__uint_as_float(v[4 * j + 3]), 0.5f, b.w));
                         }
+                    }
+                } else if constexpr (OUT16) {  // the feature layer stored as fp16 (feature storage 1): same sigmoid, half the bytes
+#pragma unroll
+                    for (int j = 0; j < CHUNK_COLS / 4; ++j) {
+                        const float4 b = ptx::ld_shared_f4(bias_addr + 16 * j);
+                        const __half2 p0 = __floats2half2_rn(sigmoid_accurate(__uint_as_float(v[4 * j]) + b.x),
+                                                             sigmoid_accurate(__uint_as_float(v[4 * j + 1]) + b.y));
+                        const __half2 p1 = __floats2half2_rn(sigmoid_accurate(__uint_as_float(v[4 * j + 2]) + b.z),
+                                                             sigmoid_accurate(__uint_as_float(v[4 * j + 3]) + b.w));
+                        o[2 * j] = *reinterpret_cast<const uint32_t*>(&p0);
+                        o[2 * j + 1] = *reinterpret_cast<const uint32_t*>(&p1);
                     }
                 } else {
 #pragma unroll
@@ -462,12 +476,14 @@ struct EncoderLayerLaunch {
     int n_seg, lo_off;   // split: k segments (2: exact A, 3: hi/lo A); column offset of the lo halves in the hidden output
     int shard_rank, shard_world;  // patch sharding: the row blocks this rank encodes (0 / 0 or 1 = all)
     int fp16;                     // operands are fp16 instead of bf16 (encoder mode 2)
+    bool out16;                   // feature layer only: fp16 output (HF6D_ENC_OUT16_CONFIGS)
     float in_scale;               // hidden layers: accumulator scale before the bias (0 = 1.0; 1/255 for fp16 layer 1)
 };
 
-template <int BLOCK_N, bool LAST, int STAGES, int EPI_BUFS, int PAIR, int CHUNK_BYTES, int EPI_WARPS, bool SPLIT = false>
+template <int BLOCK_N, bool LAST, int STAGES, int EPI_BUFS, int PAIR, int CHUNK_BYTES, int EPI_WARPS, bool SPLIT = false,
+          bool OUT16 = false>
 inline cudaError_t launch_encoder_layer_t(const EncoderLayerLaunch& L, const int* m_ptr, int sms, cudaStream_t st, bool probe) {
-    auto kern = encoder_layer_kernel<BLOCK_N, LAST, STAGES, EPI_BUFS, PAIR, CHUNK_BYTES, EPI_WARPS, SPLIT>;
+    auto kern = encoder_layer_kernel<BLOCK_N, LAST, STAGES, EPI_BUFS, PAIR, CHUNK_BYTES, EPI_WARPS, SPLIT, OUT16>;
     using S = EncSmem<BLOCK_N, STAGES, EPI_BUFS, PAIR, CHUNK_BYTES, EPI_WARPS>;
     static int grid = 0;
     if (!grid) {
@@ -553,6 +569,17 @@ inline cudaError_t launch_encoder_layer_t(const EncoderLayerLaunch& L, const int
     X(1, 160, true, 4, 2, 1, 128, 8)               \
     X(1, 256, true, 3, 2, 1, 64, 8)
 
+// Feature layer with fp16 output (feature storage 1): 32-column chunks (64-byte store boxes), so the tile is 160 or 256 wide.
+//   variant 0 = CTA pairs, pipelined footprint; 1 = stand-alone CTAs; 2 = CTA pairs, deepest ring (one-slot contexts).
+#define HF6D_ENC_OUT16_CONFIGS(X)                  \
+    /*  var  N   ST EB PAIR CHUNK EPI */           \
+    X(0, 160, 5, 2, 2, 64, 8)                      \
+    X(1, 160, 4, 2, 1, 64, 8)                      \
+    X(2, 160, 7, 2, 2, 64, 8)                      \
+    X(0, 256, 4, 2, 2, 64, 8)                      \
+    X(1, 256, 3, 2, 1, 64, 8)                      \
+    X(2, 256, 4, 2, 2, 64, 8)
+
 inline int encoder_shape_class(int block_n, bool last, bool short_k) {
     if (!last) return short_k ? 0 : 1;
     return block_n == 160 ? 2 : block_n == 208 ? 4 : 3;
@@ -562,7 +589,14 @@ struct EncoderConfig {
     int pair, chunk_bytes;
 };
 // pair == 0: no such variant
-inline EncoderConfig encoder_config(int block_n, bool last, bool short_k, int variant, bool split = false) {
+inline EncoderConfig encoder_config(int block_n, bool last, bool short_k, int variant, bool split = false, bool out16 = false) {
+    if (out16) {
+#define X(VAR, N, ST, EB, PAIR, CHUNK, EPI) \
+    if (variant == VAR && block_n == N && last) return EncoderConfig{PAIR, CHUNK};
+        HF6D_ENC_OUT16_CONFIGS(X)
+#undef X
+        return EncoderConfig{0, 0};
+    }
     if (split) {
 #define X(VAR, N, LAST, ST, EB, PAIR, CHUNK, EPI) \
     if (variant == VAR && block_n == N && last == LAST) return EncoderConfig{PAIR, CHUNK};
@@ -581,6 +615,14 @@ inline EncoderConfig encoder_config(int block_n, bool last, bool short_k, int va
 // probe = true: only check that this variant can run on the current device (shared memory opt-in, cluster occupancy).
 inline cudaError_t launch_encoder_layer(const EncoderLayerLaunch& L, const int* m_ptr, int sms, cudaStream_t st,
                                         bool probe = false) {
+    if (L.out16) {
+#define X(VAR, N, ST, EB, PAIR, CHUNK, EPI)                         \
+    if (L.variant == VAR && L.block_n == N && L.last && !L.split)   \
+        return launch_encoder_layer_t<N, true, ST, EB, PAIR, CHUNK, EPI, false, true>(L, m_ptr, sms, st, probe);
+        HF6D_ENC_OUT16_CONFIGS(X)
+#undef X
+        return cudaErrorInvalidValue;
+    }
     if (L.split) {
 #define X(VAR, N, LAST, ST, EB, PAIR, CHUNK, EPI)                   \
     if (L.variant == VAR && L.block_n == N && L.last == LAST)       \

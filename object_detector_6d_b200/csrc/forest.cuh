@@ -36,9 +36,12 @@ struct TraversePlan {
     int n_cache;     // records cached per tree
     size_t smem;     // dynamic shared memory
 };
-inline TraversePlan traverse_plan(int F, int T) {
+// Shared-memory row of one patch: F features + a constant-zero slot (fp32: 4 floats, fp16: 8 halves -- rows stay 16-byte
+// aligned for the bulk copies).
+inline int traverse_pitch(int F, int elem_bytes) { return F + 16 / elem_bytes; }
+inline TraversePlan traverse_plan(int F, int T, int elem_bytes = 4) {
     TraversePlan p;
-    const size_t buf = (size_t)TRV_ROWS * (F + 4) * 4;
+    const size_t buf = (size_t)TRV_ROWS * traverse_pitch(F, elem_bytes) * elem_bytes;
     p.n_cache = (int)std::min<size_t>(85, TRV_CACHE_BYTES / (sizeof(PackedRecord) * (size_t)std::max(T, 1)));  // 85 = 4 record levels
     const size_t cache = (size_t)p.n_cache * T * sizeof(PackedRecord);
     const size_t avail = 220 * 1024 - cache - 512;
@@ -51,15 +54,20 @@ inline TraversePlan traverse_plan(int F, int T) {
 // 1-D TMA bulk copy per row, completion on the buffer's `full` mbarrier); warps 0..n_bufs-1 each own one ring buffer:
 // wait for it, descend its 8 rows through the owned trees, hand it back through the `empty` mbarrier.  With ~56 rows
 // resident per SM the loads never pause for the descents and the descents never wait for a whole tile.
-template <int NCH>
+// FT = float: the reference's fp32 features; FT = __half: feature storage 1 (the feature layer wrote fp16; the value compared
+// is the fp32 widening of the stored half, i.e. exactly what hf6d_fetch returns for the row).
+__device__ __forceinline__ float trv_value(float v) { return v; }
+__device__ __forceinline__ float trv_value(__half v) { return __half2float(v); }
+template <int NCH, class FT = float>
 __global__ void __launch_bounds__((TRV_MAX_BUFS + 1) * 32, 1)
-traverse_kernel(const float* __restrict__ features, DevForest f, const int* __restrict__ counts,
+traverse_kernel(const FT* __restrict__ features, DevForest f, const int* __restrict__ counts,
                 int* __restrict__ leaf_ord, int shard_rank, int shard_world, int n_bufs, int n_cache, int n_recs,
                 int reverse, PatchShard pshard) {
     extern __shared__ __align__(16) uint8_t trv_smem[];
-    const int F = f.F, pitch = F + 4;
+    constexpr int ZPAD = 16 / (int)sizeof(FT);
+    const int F = f.F, pitch = F + ZPAD;
     PackedRecord* cache = reinterpret_cast<PackedRecord*>(trv_smem);  // [T][n_cache]
-    float* ring = reinterpret_cast<float*>(trv_smem + (size_t)n_cache * f.T * sizeof(PackedRecord));
+    FT* ring = reinterpret_cast<FT*>(trv_smem + (size_t)n_cache * f.T * sizeof(PackedRecord));
     uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)n_bufs * TRV_ROWS * pitch);
     uint64_t* empty = full + TRV_MAX_BUFS;
 
@@ -71,7 +79,7 @@ traverse_kernel(const float* __restrict__ features, DevForest f, const int* __re
 
     for (int i = threadIdx.x; i < n_bufs * TRV_ROWS; i += blockDim.x) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) ring[(size_t)i * pitch + F + k] = 0.0f;  // the constant-zero feature slot
+        for (int k = 0; k < ZPAD; ++k) ring[(size_t)i * pitch + F + k] = FT(0.0f);  // the constant-zero feature slot
     }
     {   // top records of every tree (16-byte words; a tree shorter than n_cache just caches a neighbour's records, unused)
         const uint4* src = reinterpret_cast<const uint4*>(f.recs);
@@ -100,16 +108,16 @@ traverse_kernel(const float* __restrict__ features, DevForest f, const int* __re
             ptx::mbar_wait(&empty[b], phase ^ 1);
             const int p0 = p_lo + (reverse ? tiles - 1 - tile : tile) * TRV_ROWS;  // last rows first: see the consumers
             const int nrows = min(TRV_ROWS, Pp - p0);
-            if (lane == 0) ptx::mbar_arrive_expect_tx(&full[b], (uint32_t)nrows * F * 4);
+            if (lane == 0) ptx::mbar_arrive_expect_tx(&full[b], (uint32_t)nrows * F * (uint32_t)sizeof(FT));
             __syncwarp();
             if (lane < nrows)
-                ptx::bulk_load_1d(ring + ((size_t)b * TRV_ROWS + lane) * pitch, features + (size_t)(p0 + lane) * F, F * 4, &full[b]);
+                ptx::bulk_load_1d(ring + ((size_t)b * TRV_ROWS + lane) * pitch, features + (size_t)(p0 + lane) * F, F * (int)sizeof(FT), &full[b]);
             if (++b == n_bufs) { b = 0; phase ^= 1; }
         }
     } else if (warp < n_bufs) {
         // ------------------------------------------------------------ consumers: warp w owns ring buffer w
         const int row = lane % TRV_ROWS, slot = lane / TRV_ROWS;
-        const float* my = ring + ((size_t)warp * TRV_ROWS + row) * pitch;
+        const FT* my = ring + ((size_t)warp * TRV_ROWS + row) * pitch;
         uint32_t phase = 0;
         for (int tile = blockIdx.x + warp * gridDim.x; tile < tiles; tile += n_bufs * gridDim.x) {
             // The rows are walked from the END of the matrix: the feature layer wrote them in ascending order just before
@@ -156,11 +164,11 @@ traverse_kernel(const float* __restrict__ features, DevForest f, const int* __re
 #pragma unroll
                         for (int c = 0; c < NCH; ++c)
                             if (e[c] >= 0) {
-                                const float v0 = __fsub_rn(my[ra[c].x & 0xFFFFu], my[ra[c].x >> 16]);
+                                const float v0 = __fsub_rn(trv_value(my[ra[c].x & 0xFFFFu]), trv_value(my[ra[c].x >> 16]));
                                 const bool right0 = !(v0 < __uint_as_float(ra[c].w));
                                 const unsigned t1 = right0 ? ra[c].z : ra[c].y;
                                 const float thr1 = __uint_as_float(right0 ? rb[c].y : rb[c].x);
-                                const float v1 = __fsub_rn(my[t1 & 0xFFFFu], my[t1 >> 16]);
+                                const float v1 = __fsub_rn(trv_value(my[t1 & 0xFFFFu]), trv_value(my[t1 >> 16]));
                                 const bool right1 = !(v1 < thr1);
                                 e[c] = right0 ? (int)(right1 ? rc[c].y : rc[c].x) : (int)(right1 ? rb[c].w : rb[c].z);
                                 any |= e[c] >= 0;

@@ -110,6 +110,12 @@ struct Slot {
     bool split_ready = false;
     EncoderLayerLaunch enc_fp16[3];  // fp16 mode: the bf16 launches with the weight map and the operand format replaced
     bool fp16_ready = false;
+    // feature storage 1 (hf6d_ctx::feat16): the feature layer writes fp16 rows, the traversal reads them; `feat` (fp32) is then
+    // filled on demand only (hf6d_fetch, hf6d_device_ptr, hf6d_encode_patches) or by hf6d_inject
+    __half* feat16 = nullptr;
+    EncoderLayerLaunch enc16[2];     // feature-layer launches with fp16 output: [0] bf16 operands, [1] fp16 operands
+    bool enc16_fp16_ready = false;
+    bool feat_is16 = false;          // the slot's current features live in feat16
     uint32_t peer_seq = 0;  // frames this slot has pushed through the peer exchange (both flags carry it)
     bool busy = false;  // submit/wait bookkeeping
     int ticket = -1;
@@ -170,6 +176,11 @@ struct hf6d_ctx {
     int* peer_timeout = nullptr;                                      // set by the fallback wait kernel when it gives up
     bool peer_wait_expired = false;                                   // a bounded host-side wait ran out (sync_stream_bounded)
     int encoder_mode = 0;
+    // Feature storage: 0 = fp32 rows (the reference's type), 1 = fp16 rows written by the feature layer of the bf16 / fp16
+    // operand modes and read by the traversal (half the HBM bytes of both; the split mode always stores fp32).
+    // HF6D_FEATURES=fp16 (tuning switch, read at create); needs F % 8 == 0 and a 160- or 256-wide feature tile.
+    bool feat16 = false;
+    int feat16_block_n = 0, feat16_variant = 0;
     // per encoder layer: row of HF6D_ENC_CONFIGS within the layer's shape class (0 = default: CTA pairs, cta_group::2;
     // 1 = stand-alone CTAs).  Tuning switch: HF6D_ENC_VARIANT="a,b,c".
     int enc_variant[3] = {0, 0, 0};
@@ -213,7 +224,7 @@ int dev_upload(hf6d_ctx* c, std::vector<void*>& owner, const T** out, const std:
     T* p = nullptr;
     int r = dev_alloc(c, owner, &p, v.size());
     if (r) return r;
-    if (!v.empty()) CU_TRY(c, cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    if (!v.empty()) CU_TRY(c, memcpy_h2d_done(p, v.data(), v.size() * sizeof(T)));
     *out = p;
     return HF6D_OK;
 }
@@ -451,7 +462,7 @@ int upload_class_mask(hf6d_ctx* c) {
     memset(m, 0, sizeof m);
     for (int k = 0; k < c->hf.K && k < (int)c->objects.size(); ++k) m[k] = seeks_class(c, k) ? 1 : 0;
     if (c->dm.class_mask) {
-        cudaError_t e = cudaMemcpy(c->dm.class_mask, m, sizeof m, cudaMemcpyHostToDevice);
+        cudaError_t e = memcpy_h2d_done(c->dm.class_mask, m, sizeof m);
         if (e != cudaSuccess) { c->err = std::string("cudaMemcpy(class mask): ") + cudaGetErrorString(e); return HF6D_ECUDA; }
     }
     return HF6D_OK;
@@ -657,7 +668,9 @@ int run_stage(hf6d_ctx* c, Slot& s, int stage) {
             if (c->encoder_mode == 1 && !s.split_ready) return fail(c, HF6D_ESTATE, "split encoder buffers missing");
             if (c->encoder_mode == 2 && !s.fp16_ready) return fail(c, HF6D_ESTATE, "fp16 encoder state missing");
             for (int l = 0; l < 3; ++l) {
-                EncoderLayerLaunch& L = c->encoder_mode == 1 ? s.enc_split[l] : c->encoder_mode == 2 ? s.enc_fp16[l] : s.enc[l];
+                const bool to16 = l == 2 && c->feat16 && c->encoder_mode != 1;
+                EncoderLayerLaunch& L = to16 ? s.enc16[c->encoder_mode == 2] : c->encoder_mode == 1 ? s.enc_split[l]
+                                        : c->encoder_mode == 2 ? s.enc_fp16[l] : s.enc[l];
                 L.shard_rank = c->pshard.rank;
                 L.shard_world = c->pshard.world;
                 cudaError_t e = launch_encoder_layer(L, s.counts + 1, c->sms, st);
@@ -666,25 +679,30 @@ int run_stage(hf6d_ctx* c, Slot& s, int stage) {
                 CU_TRY(c, cudaEventRecord(s.ev_enc[l + 1], st));
             }
             s.ev_enc_valid = true;
+            s.feat_is16 = c->feat16 && c->encoder_mode != 1;
             break;
         }
         case HF6D_STAGE_TRAVERSE: {
-            const TraversePlan tp = traverse_plan(f.F, f.T);
+            const TraversePlan tp = traverse_plan(f.F, f.T, s.feat_is16 ? 2 : 4);
             const int n_owned = (f.T - c->shard_rank + c->shard_world - 1) / c->shard_world;
             const int per_slot = (n_owned + TRV_SLOTS - 1) / TRV_SLOTS;
             const int threads = (tp.n_bufs + 1) * 32, n_recs = (int)c->hf.recs.size();
             if (c->pshard.world > 1)  // rows of other ranks' patches: "not traversed here" (-1), as for trees that are not owned
                 CU_TRY(c, cudaMemsetAsync(s.leaf_ord, 0xFF, (size_t)g.cap * f.T * 4, st));
             static const int trv_reverse = !(getenv("HF6D_SNAKE") && atoi(getenv("HF6D_SNAKE")) == 0);  // see alloc_slot
-            if (per_slot <= 1)
-                traverse_kernel<1><<<c->sms, threads, tp.smem, st>>>(s.feat, f, s.counts, s.leaf_ord, c->shard_rank, c->shard_world,
-                                                                   tp.n_bufs, tp.n_cache, n_recs, trv_reverse, c->pshard);
-            else if (per_slot <= 2)
-                traverse_kernel<2><<<c->sms, threads, tp.smem, st>>>(s.feat, f, s.counts, s.leaf_ord, c->shard_rank, c->shard_world,
-                                                                   tp.n_bufs, tp.n_cache, n_recs, trv_reverse, c->pshard);
-            else
-                traverse_kernel<4><<<c->sms, threads, tp.smem, st>>>(s.feat, f, s.counts, s.leaf_ord, c->shard_rank, c->shard_world,
-                                                                   tp.n_bufs, tp.n_cache, n_recs, trv_reverse, c->pshard);
+#define HF6D_TRV(NCH, FT, FEAT)                                                                                              \
+    traverse_kernel<NCH, FT><<<c->sms, threads, tp.smem, st>>>(FEAT, f, s.counts, s.leaf_ord, c->shard_rank, c->shard_world, \
+                                                               tp.n_bufs, tp.n_cache, n_recs, trv_reverse, c->pshard)
+            if (s.feat_is16) {
+                if (per_slot <= 1) HF6D_TRV(1, __half, s.feat16);
+                else if (per_slot <= 2) HF6D_TRV(2, __half, s.feat16);
+                else HF6D_TRV(4, __half, s.feat16);
+            } else {
+                if (per_slot <= 1) HF6D_TRV(1, float, s.feat);
+                else if (per_slot <= 2) HF6D_TRV(2, float, s.feat);
+                else HF6D_TRV(4, float, s.feat);
+            }
+#undef HF6D_TRV
             LAUNCH_CHECK(c, s);
             break;
         }
@@ -969,6 +987,25 @@ int check_slot(hf6d_ctx* c, int slot) {
     return HF6D_OK;
 }
 
+// Feature storage 1: the fp32 view of the slot's features (what hf6d_fetch / hf6d_device_ptr / hf6d_encode_patches hand out)
+// is produced on demand from the fp16 rows the traversal reads -- an exact widening, so the caller sees the values the leaf
+// tests compared.
+__global__ void widen_features_kernel(const __half* __restrict__ src, const int* __restrict__ counts, int cap, int F,
+                                      float* __restrict__ dst) {
+    const long long n = (long long)min(counts[1], cap) * F / 2;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float2 v = __half22float2(reinterpret_cast<const __half2*>(src)[i]);
+        reinterpret_cast<float2*>(dst)[i] = v;
+    }
+}
+int features_fp32(hf6d_ctx* c, Slot& s) {
+    if (!s.feat_is16) return HF6D_OK;
+    widen_features_kernel<<<c->sms * 8, 256, 0, s.stream>>>(s.feat16, s.counts, c->g.cap, c->hf.F, s.feat);
+    CU_TRY(c, cudaGetLastError());
+    CU_TRY(c, cudaStreamSynchronize(s.stream));
+    return HF6D_OK;
+}
+
 struct BufInfo {
     void* ptr;
     size_t bytes;  // capacity
@@ -995,6 +1032,8 @@ int buffer_of(hf6d_ctx* c, Slot& s, int what, BufInfo& b) {
     }
     return HF6D_OK;
 }
+
+int ensure_feat16(hf6d_ctx* c);
 
 int finish_create(hf6d_ctx* c, int device, int n_slots) {
     int ndev = 0;
@@ -1128,6 +1167,12 @@ int finish_create(hf6d_ctx* c, int device, int n_slots) {
     CU_TRY(c, cudaFuncSetAttribute(traverse_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)traverse_plan(c->hf.F, c->hf.T).smem));
     CU_TRY(c, cudaFuncSetAttribute(traverse_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)traverse_plan(c->hf.F, c->hf.T).smem));
     CU_TRY(c, cudaFuncSetAttribute(traverse_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)traverse_plan(c->hf.F, c->hf.T).smem));
+    if (c->hf.F % 8 == 0) {  // the fp16-row instances (feature storage 1)
+        const int sm16 = (int)traverse_plan(c->hf.F, c->hf.T, 2).smem;
+        CU_TRY(c, cudaFuncSetAttribute(traverse_kernel<1, __half>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm16));
+        CU_TRY(c, cudaFuncSetAttribute(traverse_kernel<2, __half>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm16));
+        CU_TRY(c, cudaFuncSetAttribute(traverse_kernel<4, __half>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm16));
+    }
     if (cell_grid_bytes(p.W, p.H, p.centers_nms_wsize / 2, K) > 96 * 1024)
         return fail(c, HF6D_EINVAL, "frame too large for the centre-window lookup grid");
     if ((long long)g.cap * c->hf.T >= (1LL << 31)) return fail(c, HF6D_EINVAL, "patches x trees exceeds 2^31");
@@ -1217,6 +1262,14 @@ int finish_create(hf6d_ctx* c, int device, int n_slots) {
     for (Slot& s : c->slots) {
         memset(s.ev, 0, sizeof s.ev);
         if ((r = alloc_slot(c, s))) return r;
+    }
+    {   // feature storage: fp16 rows wherever the feature layer has a kernel for them; HF6D_FEATURES=fp32 keeps the fp32 rows
+        const char* e = getenv("HF6D_FEATURES");
+        if (!(e && !strcmp(e, "fp32"))) {
+            if (ensure_feat16(c) == HF6D_OK) c->feat16 = true;
+            else if (e && !strcmp(e, "fp16")) return HF6D_EINVAL;  // asked for explicitly: say why not (c->err)
+            else c->err.clear();
+        }
     }
     CU_TRY(c, cudaDeviceSynchronize());
     return HF6D_OK;
@@ -1692,9 +1745,85 @@ int ensure_fp16_encoder(hf6d_ctx* c) {
         }
         s.fp16_ready = true;
     }
+    return c->feat16_block_n ? ensure_feat16(c) : HF6D_OK;  // the fp16-operand feature layer with fp16 output, where that exists
+}
+}  // namespace
+
+extern "C++" {
+namespace {
+// Feature storage 1: per-slot fp16 feature rows and the feature-layer launches that write them (bf16 operands; fp16 operands
+// once encoder mode 2 has been set up).  Idempotent.
+int ensure_feat16(hf6d_ctx* c) {
+    DeviceModel& dm = c->dm;
+    const FrameGeom& g = c->g;
+    const int F = c->hf.F;
+    int r;
+    if (!c->feat16_block_n) {
+        if (F % 8 || !(F % 160 == 0 || dm.block_n[2] == 256))
+            return fail(c, HF6D_EINVAL, "fp16 feature rows need a feature length that is a multiple of 8 and of 160, or 256-wide feature tiles (F = %d)", F);
+        const int block_n = F % 160 == 0 ? 160 : 256;
+        EncoderLayerLaunch probe{};
+        probe.block_n = block_n;
+        probe.last = true;
+        probe.out16 = true;
+        probe.variant = c->enc_variant[2] == 1 ? 1 : (c->n_slots == 1 ? 2 : 0);
+        if (launch_encoder_layer(probe, nullptr, c->sms, nullptr, true) != cudaSuccess) {
+            cudaGetLastError();
+            probe.variant = 1;
+            if (launch_encoder_layer(probe, nullptr, c->sms, nullptr, true) != cudaSuccess) {
+                cudaGetLastError();
+                return fail(c, HF6D_ECUDA, "fp16 feature rows: no kernel variant can run on this device");
+            }
+        }
+        c->feat16_variant = probe.variant;
+        c->feat16_block_n = block_n;
+    }
+    for (Slot& s : c->slots) {
+        if (!s.feat16) {
+            if ((r = dev_alloc(c, s.allocs, &s.feat16, (size_t)g.cap * F))) return r;
+            EncoderLayerLaunch& L = s.enc16[0];
+            L = s.enc[2];
+            L.out16 = true;
+            L.block_n = c->feat16_block_n;
+            L.variant = c->feat16_variant;
+            L.n_pad = round_up(F, L.block_n);
+            const EncoderConfig cfg = encoder_config(L.block_n, true, false, L.variant, false, true);
+            if (!cfg.pair) return fail(c, HF6D_EINVAL, "fp16 feature rows: no kernel variant %d for %d-wide tiles", L.variant, L.block_n);
+            if (!make_bf16_kmajor_map(&L.tmB, dm.W[2], (uint64_t)dm.n_pad[2], (uint64_t)dm.k_pad[2], (uint32_t)(L.block_n / cfg.pair)) ||
+                !make_out_map(&L.tmC, s.feat16, (uint64_t)g.cap, (uint64_t)F, 2, cfg.chunk_bytes))
+                return fail(c, HF6D_ECUDA, "cuTensorMapEncodeTiled failed for the fp16 feature layer");
+        }
+        if (s.fp16_ready && !s.enc16_fp16_ready) {
+            EncoderLayerLaunch& L = s.enc16[1];
+            L = s.enc16[0];
+            const EncoderConfig cfg = encoder_config(L.block_n, true, false, L.variant, false, true);
+            if (!make_bf16_kmajor_map(&L.tmB, dm.Wh[2], (uint64_t)dm.n_pad[2], (uint64_t)dm.k_pad[2], (uint32_t)(L.block_n / cfg.pair)))
+                return fail(c, HF6D_ECUDA, "cuTensorMapEncodeTiled failed for the fp16 feature layer (fp16 operands)");
+            L.fp16 = 1;
+            L.in_scale = 1.0f;
+            s.enc16_fp16_ready = true;
+        }
+    }
     return HF6D_OK;
 }
 }  // namespace
+}  // extern "C++" (declared before finish_create)
+
+int hf6d_set_feature_storage(hf6d_ctx* c, int storage) {
+    if (!c) return HF6D_EINVAL;
+    if (storage != 0 && storage != 1) return fail(c, HF6D_EINVAL, "feature storage %d: 0 = fp32 rows, 1 = fp16 rows", storage);
+    CU_TRY(c, cudaSetDevice(c->device));
+    CU_TRY(c, cudaDeviceSynchronize());
+    if (storage == 1) {
+        const int r = ensure_feat16(c);
+        if (r) return r;
+    }
+    c->feat16 = storage == 1;
+    for (Slot& s : c->slots) s.stream_valid = false;
+    return HF6D_OK;
+}
+
+int hf6d_get_feature_storage(const hf6d_ctx* c) { return c ? (c->feat16 ? 1 : 0) : HF6D_EINVAL; }
 
 int hf6d_set_encoder_mode(hf6d_ctx* c, int mode) {
     if (!c) return HF6D_EINVAL;
@@ -1830,6 +1959,7 @@ int64_t hf6d_fetch(hf6d_ctx* c, int slot, int what, void* dst, size_t cap_bytes)
     CU_TRY(c, cudaStreamSynchronize(s.stream));
     BufInfo b;
     if ((r = buffer_of(c, s, what, b))) return r;
+    if (what == HF6D_BUF_FEATURES && (r = features_fp32(c, s))) return r;
     size_t bytes = b.bytes;
     if (what == HF6D_BUF_LOCS || what == HF6D_BUF_PATCH_U8 || what == HF6D_BUF_FEATURES || what == HF6D_BUF_LEAF_ORD) {
         int counts[2];
@@ -1856,7 +1986,8 @@ int hf6d_inject(hf6d_ctx* c, int slot, int what, const void* src, size_t bytes) 
     if ((r = buffer_of(c, s, what, b))) return r;
     if (bytes > b.bytes) return fail(c, HF6D_EINVAL, "buffer %d holds %zu bytes, got %zu", what, b.bytes, bytes);
     CU_TRY(c, cudaStreamSynchronize(s.stream));
-    CU_TRY(c, cudaMemcpy(b.ptr, src, bytes, cudaMemcpyHostToDevice));
+    CU_TRY(c, memcpy_h2d_done(b.ptr, src, bytes));
+    if (what == HF6D_BUF_FEATURES) s.feat_is16 = false;  // injected features are fp32 rows: the traversal reads those
     s.stream_valid = false;  // whatever was injected, the vote stream no longer describes the slot
     return HF6D_OK;
 }
@@ -1866,6 +1997,12 @@ int hf6d_device_ptr(hf6d_ctx* c, int slot, int what, void** ptr, size_t* bytes) 
     if (r) return r;
     BufInfo b;
     if ((r = buffer_of(c, c->slots[slot], what, b))) return r;
+    if (what == HF6D_BUF_FEATURES) {  // the caller gets (and may overwrite) the fp32 rows: they are the slot's features from here on
+        Slot& s = c->slots[slot];
+        CU_TRY(c, cudaSetDevice(c->device));
+        if ((r = features_fp32(c, s))) return r;
+        s.feat_is16 = false;
+    }
     if (ptr) *ptr = b.ptr;
     if (bytes) *bytes = b.bytes;
     return HF6D_OK;

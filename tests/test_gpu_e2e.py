@@ -89,7 +89,7 @@ def workload(tmp_path_factory):
     return dict(frames=frames, layers=layers, forest_dir=forest_dir, weights=wpath, stats=stats, forest=forest, params=p, refs=refs)
 
 
-def _gpu_run(workload, mode):
+def _gpu_run(workload, mode, storage=None):
     from object_detector_6d_b200 import api
     from tests.helpers import to_api_params
     det = api.Detector(workload["forest_dir"], workload["weights"], to_api_params(workload["params"]), device=0, n_slots=1)
@@ -98,6 +98,9 @@ def _gpu_run(workload, mode):
     try:
         det.set_encoder_mode(mode)
         assert det.encoder_mode() == mode
+        if storage is not None:
+            det.set_feature_storage(storage)
+            assert det.feature_storage() == storage
         for bgr, depth in workload["frames"]:
             hyp = det.detect(bgr, depth)
             out.append(dict(hyp=hyp, feat=det.fetch(api.BUF_FEATURES), leaf=det.fetch(api.BUF_LEAF_ORD), q=det.fetch(api.BUF_PATCH_U8),
@@ -113,10 +116,13 @@ def report(workload):
     rep = {"workload": "BASELINE configs[1]: 6-object forest trained on labelled synthetic patches (T=4, depth<=20, ~16 votes per "
                        "leaf, coherent votes), 640x480, fill random; %d frames" % len(workload["frames"]), "forest": workload["stats"],
            "oracle": "oracle/hf6d_oracle.c with its own fp32 encoder (8 interleaved partial sums, expf sigmoid)", "frames": []}
-    runs = {0: _gpu_run(workload, 0), 1: _gpu_run(workload, 1), 2: _gpu_run(workload, 2)}
+    # modes 0 / 2 as they run by default (fp16 feature rows, hf6d_set_feature_storage 1) and with the reference's fp32 rows
+    runs = {0: _gpu_run(workload, 0), 1: _gpu_run(workload, 1), 2: _gpu_run(workload, 2),
+            3: _gpu_run(workload, 0, storage=0), 4: _gpu_run(workload, 2, storage=0)}
+    rep["feature_storage"] = "gpu_bf16 / gpu_fp16: fp16 feature rows (the default); *_fp32_rows: hf6d_set_feature_storage(ctx, 0)"
     for i, ref in enumerate(workload["refs"]):
         row = {"patches": int(ref["feat"].shape[0])}
-        for mode, name in ((0, "gpu_bf16"), (1, "gpu_split_bf16"), (2, "gpu_fp16")):
+        for mode, name in ((0, "gpu_bf16"), (1, "gpu_split_bf16"), (2, "gpu_fp16"), (3, "gpu_bf16_fp32_rows"), (4, "gpu_fp16_fp32_rows")):
             g = runs[mode][i]
             assert np.array_equal(g["q"], ref["q"]), "quantised patches must be bit-exact before the encoder"
             row[name] = _compare(name, g["feat"], g["leaf"], g["hyp"], ref)
@@ -164,6 +170,17 @@ def test_fp16_encoder_end_to_end_numbers_are_published(report):
         assert r["feature_max_abs_err"] < 4e-3 and r["feature_mean_abs_err"] < b["feature_mean_abs_err"] / 4
         assert r["leaf_agreement"] > b["leaf_agreement"]
         assert r["tuples_reproduced"] >= b["tuples_reproduced"]
+
+
+def test_fp16_feature_rows_cost_no_parity(report):
+    """Feature storage 1 (the default of modes 0 / 2) against storage 0 on the same frames: rounding the sigmoid once to fp16
+    (<= 2.5e-4) sits two orders below mode 0's operand error, so leaves and tuples against the fp32 oracle must not move
+    by more than noise."""
+    for row in report["frames"]:
+        for a, b in (("gpu_bf16", "gpu_bf16_fp32_rows"), ("gpu_fp16", "gpu_fp16_fp32_rows")):
+            assert abs(row[a]["feature_max_abs_err"] - row[b]["feature_max_abs_err"]) < 5e-4
+            assert row[a]["leaf_agreement"] > row[b]["leaf_agreement"] - 0.005
+            assert row[a]["tuples_within_one_bin"] > row[b]["tuples_within_one_bin"] - 0.1
 
 
 def test_split_mode_is_deterministic_and_switchable(workload):
