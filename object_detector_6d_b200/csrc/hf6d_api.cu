@@ -158,6 +158,7 @@ struct hf6d_ctx {
     int gather_tile_texels = 0, gather_smem = 0;
     bool use_stream = false;     // pose stage reads the vote stream instead of enumerating the votes again
     int stream_cap = 0, pair_cap = 0;
+    int ws_rows = 4, ws_kmax = 1;  // window_stream_kernel: rows per chunk (2 / 4), largest chunk range (HF6D_WS_TUNE="rows,k_max")
     int shard_rank = 0, shard_world = 1;
     int class_rank = 0, class_world = 1;  // centres + pose only for classes k % class_world == class_rank
     PatchShard pshard{0, 1};              // gather .. vote only for this rank's patches (hf6d_set_patch_shard)
@@ -816,11 +817,12 @@ int run_stage(hf6d_ctx* c, Slot& s, int stage) {
                     vs.n[0] = s.stream_n;
                 }
                 const size_t dyn = ((zbytes + 15) & ~(size_t)15) + cell_bytes;
-#define HF6D_WS(GG)                                                                                                         \
-    window_stream_kernel<GG><<<c->sms, WA_THREADS, dyn, st>>>(f, g, switches_of(c, true), vs, s.depth, ct, half_win, n_groups, zt, \
+#define HF6D_WS(GG, RR)                                                                                                         \
+    window_stream_kernel<GG, RR><<<c->sms, WA_THREADS, dyn, st>>>(f, g, switches_of(c, true), vs, s.depth, ct, half_win, n_groups, zt, \
                                                              s.win_cnt, pl, s.zacc, ctr + 3, ctr + 4, 20 /* HFTest.cpp:745 */,     \
-                                                             rv.active, rv.mode_z)
-                if (c->lanes_per_hit == 16) HF6D_WS(16); else HF6D_WS(32);
+                                                             rv.active, rv.mode_z, c->ws_kmax)
+                if (c->ws_rows == 2) { if (c->lanes_per_hit == 16) HF6D_WS(16, 2); else HF6D_WS(32, 2); }
+                else { if (c->lanes_per_hit == 16) HF6D_WS(16, 4); else HF6D_WS(32, 4); }
 #undef HF6D_WS
                 LAUNCH_CHECK(c, s);
                 if (c->lanes_per_hit == 16)
@@ -1222,11 +1224,20 @@ int finish_create(hf6d_ctx* c, int device, int n_slots) {
         c->use_stream = !(e && atoi(e) == 0) && p.W + 2 * STREAM_BIAS <= STREAM_COORD_MAX && p.H + 2 * STREAM_BIAS <= STREAM_COORD_MAX &&
                         p.centers_nms_wsize / 2 <= STREAM_BIAS && records <= (64LL << 20) && pairs <= (32LL << 20) &&
                         dyn <= (size_t)WS_MAX_DYN_SMEM;
+        if (const char* t = getenv("HF6D_WS_TUNE")) {
+            int a = 0, b = 0;
+            if (sscanf(t, "%d,%d", &a, &b) == 2 && (a == 2 || a == 4) && b >= 1 && b <= 64) {
+                c->ws_rows = a;
+                c->ws_kmax = b;
+            }
+        }
         c->stream_cap = c->use_stream ? (int)std::max<long long>(records, 1) : 0;
         c->pair_cap = c->use_stream ? (int)std::max<long long>(pairs, 1) : 0;
         if (c->use_stream) {
-            CU_TRY(c, cudaFuncSetAttribute(window_stream_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_MAX_DYN_SMEM));
-            CU_TRY(c, cudaFuncSetAttribute(window_stream_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_MAX_DYN_SMEM));
+            CU_TRY(c, (cudaFuncSetAttribute(window_stream_kernel<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_MAX_DYN_SMEM)));
+            CU_TRY(c, (cudaFuncSetAttribute(window_stream_kernel<32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_MAX_DYN_SMEM)));
+            CU_TRY(c, (cudaFuncSetAttribute(window_stream_kernel<16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_MAX_DYN_SMEM)));
+            CU_TRY(c, (cudaFuncSetAttribute(window_stream_kernel<32, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_MAX_DYN_SMEM)));
         }
     }
     CU_TRY(c, cudaFuncSetAttribute(window_accumulate_kernel<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, WA_MAX_DYN_SMEM));
@@ -1767,6 +1778,7 @@ int ensure_feat16(hf6d_ctx* c) {
         probe.last = true;
         probe.out16 = true;
         probe.variant = c->enc_variant[2] == 1 ? 1 : (c->n_slots == 1 ? 2 : 0);
+        if (const char* e = getenv("HF6D_FEAT16_VARIANT")) probe.variant = atoi(e);  // tuning override (row of HF6D_ENC_OUT16_CONFIGS)
         if (launch_encoder_layer(probe, nullptr, c->sms, nullptr, true) != cudaSuccess) {
             cudaGetLastError();
             probe.variant = 1;

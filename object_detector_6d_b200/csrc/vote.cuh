@@ -479,7 +479,7 @@ window_accumulate_kernel(DevForest f, const uint4* __restrict__ entries, int ent
 //   * the last CTA to finish runs the z mode seeking (HFTest.cpp:803-812) for every slot.
 struct WarpRing {
     unsigned vi[64], cm[64];
-    float zz[64];
+    int pix[64];  // y * W + x of the window pixel the vote landed on, -1 outside the image (its depth is read in process())
 };
 struct PairList {
     uint2* pairs;   // (slot, group), each (slot, group) at most once per frame
@@ -512,14 +512,27 @@ __device__ __forceinline__ void z_mode_warp(const unsigned long long* __restrict
     __syncwarp();
 }
 
-constexpr int WS_ROWS = 8;  // stream rows (of 32 records) a warp grabs at a time
-template <int G>
+// Scheduling.  The kernel is a set of per-warp chains of dependent L2 round trips (chunk counter -> records -> window pixel's
+// depth -> vote group -> group record -> counter atomic) at 32 warps per SM, and the work per record varies by orders of
+// magnitude (background votes miss every window; a vote inside one drags its leaf's z offsets through a bisection), so
+//   * a chunk is ROWS rows of 32 records; the records of the NEXT chunk are requested before the current one is examined,
+//     the window pixel's depth is read together with the vote group, and the pair-list append waits for the counter's old
+//     value until the lane's next batch (settle);
+//   * chunks are handed out in ranges of clamp(remaining / (2 x warps), 1, k_max) chunks through one counter; a warp's first
+//     range is its own index (no atomic), a request is issued at the first chunk of a range and looked at before its last.
+//     Measured (profiles/r02_ws_tune.json): granularity decides -- k_max = 1 with 128-record chunks is fastest (pose stage
+//     0.278 ms), ranges of 4 chunks cost 10 %, of 8 chunks 30 %: the last warp keeps its CTA, and with it the kernel, waiting
+//     (12.9 % of the stall samples sit at the final barrier even so); the same-address atomics are not the limit.
+//   * leaves whose sorted z offsets straddle several 1 cm bins are binned by bisection per occupied bin; one linear pass
+//     over the list was measured slower at every list length (same file), as were 64-record chunks.
+// HF6D_WS_TUNE="rows,k_max" (rows 2 or 4).
+template <int G, int WS_ROWS>
 __global__ void __launch_bounds__(WA_THREADS)
 window_stream_kernel(DevForest f, FrameGeom g, const __grid_constant__ ObjectSwitches sw, const __grid_constant__ StreamSet ss,
                      const uint16_t* __restrict__ depth, CentreTable ct, int half_win, int n_groups,
                      const __grid_constant__ ZSlotTable zt, unsigned* __restrict__ cnt, PairList pl,
                      unsigned long long* __restrict__ zacc, int* __restrict__ next_chunk, int* __restrict__ done,
-                     int z_nms, uint8_t* __restrict__ active, float* __restrict__ mode_z) {
+                     int z_nms, uint8_t* __restrict__ active, float* __restrict__ mode_z, int k_max) {
     __shared__ SharedCentres sc;
     __shared__ WarpRing s_ring[WA_THREADS / 32];
     __shared__ unsigned s_classes;
@@ -572,8 +585,24 @@ window_stream_kernel(DevForest f, FrameGeom g, const __grid_constant__ ObjectSwi
         return (zb < 0 || zb >= HF6D_Z_BINS) ? -1 : zb;
     };
 
+    // A (slot, group) counter that was zero before this lane's increment makes the lane append the pair to the list -- but the
+    // atomic's return value is a full L2 round trip away, so it is looked at when the lane's NEXT batch starts (or after the
+    // last one): pend_old is the value the counter held (non-zero = nothing to do), pend_slot / pend_gi the pair.
+    unsigned pend_old = 1u;
+    int pend_slot = 0, pend_gi = 0;
+    auto settle = [&]() {  // called by the whole warp: one list reservation for all of its new pairs
+        const unsigned fresh = __ballot_sync(0xffffffffu, pend_old == 0u);  // lanes whose increment was the pair's first
+        if (fresh) {
+            int at = 0;
+            if (lane == __ffs(fresh) - 1) at = atomicAdd(pl.n, __popc(fresh));
+            at = __shfl_sync(0xffffffffu, at, __ffs(fresh) - 1) + __popc(fresh & ((1u << lane) - 1u));
+            if (pend_old == 0u && at < pl.cap) pl.pairs[at] = make_uint2((unsigned)pend_slot, (unsigned)pend_gi);
+        }
+        pend_old = 1u;
+    };
     // the ring's entries [head, head + n_e), n_e <= 32, ONE LANE PER ENTRY: counters, pair list, z histograms
     auto process = [&](int head, int n_e) {
+        settle();
         const bool have = lane < n_e;
         unsigned cm = 0;
         float zz = -1.f;
@@ -583,10 +612,13 @@ window_stream_kernel(DevForest f, FrameGeom g, const __grid_constant__ ObjectSwi
         if (have) {
             const int at = (head + lane) & 63;
             cm = ring.cm[at];
-            zz = ring.zz[at];
+            const int pix = ring.pix[at];
+            unsigned d = 0;
+            if (pix >= 0) d = depth[pix];  // in flight together with the group lookup (the reference reads out of bounds here)
             gi = __ldg(f.vgroup + (int)ring.vi[at]);
             grp = __ldg(reinterpret_cast<const int4*>(f.groups) + gi);  // cls, w, vbeg, vcnt
             ozr = __ldg(f.oz_range + gi);
+            if (d != 0) zz = div_const<1000, 1>((float)d);
         }
         // entries with the same group in the same windows (the votes of one leaf cast by one patch, typically): one update
         const unsigned long long key = have ? (((unsigned long long)(unsigned)gi << 16) | (cm & 0xFFFFu)) : (~0ull - (unsigned)lane);
@@ -594,7 +626,12 @@ window_stream_kernel(DevForest f, FrameGeom g, const __grid_constant__ ObjectSwi
         if (have && lane == __ffs(peers) - 1) {
             const int c = (int)(cm >> 16);
             const unsigned mult = (unsigned)__popc(peers);
-            for (unsigned m = cm & 0xFFFFu; m; m &= m - 1) {
+            unsigned m = cm & 0xFFFFu;
+            // the first (usually the only) window of the entry: increment now, examine the old value later (settle)
+            pend_slot = c * HF6D_MAX_CENTRES + __ffs(m) - 1;
+            pend_gi = gi;
+            pend_old = atomicAdd(cnt + (size_t)pend_slot * n_groups + gi, mult);
+            for (m &= m - 1; m; m &= m - 1) {  // a pixel inside several overlapping windows: the others right away
                 const int slot = c * HF6D_MAX_CENTRES + __ffs(m) - 1;
                 if (atomicAdd(cnt + (size_t)slot * n_groups + gi, mult) == 0u) {  // first entry of this (slot, group)
                     const int at = atomicAdd(pl.n, 1);
@@ -614,6 +651,19 @@ window_stream_kernel(DevForest f, FrameGeom g, const __grid_constant__ ObjectSwi
             const float* ozs = f.oz_sorted + grp.z;
             const int hi = z_bin_raw(ozr.y, zz);
             int b = z_bin_raw(ozr.x, zz), prev = 0;
+            auto add_run = [&](int bin, int votes) {  // `votes` votes of the leaf fall into `bin`
+                if (bin < 0 || bin >= HF6D_Z_BINS) return;
+                const unsigned add = (unsigned)grp.y * (unsigned)votes;
+                for (unsigned m = cm & 0xFFFFu; m; m &= m - 1) {
+                    const int k = __ffs(m) - 1;
+                    const unsigned old = atomicAdd(s_z + (zt.zoff[c] + k) * HF6D_Z_BINS + bin, add);
+                    if (old + add < old) atomicAdd(zacc + (size_t)(c * HF6D_MAX_CENTRES + k) * HF6D_Z_BINS + bin, 1ull << 32);
+                }
+            };
+            if (b == hi) {  // the whole leaf in one bin
+                add_run(b, grp.w);
+                prev = grp.w;
+            }
             while (prev < grp.w) {
                 int idx = grp.w;  // first vote beyond bin b
                 if (b < hi) {
@@ -652,21 +702,48 @@ window_stream_kernel(DevForest f, FrameGeom g, const __grid_constant__ ObjectSwi
     };
 
     int head = 0, pending = 0;  // warp-uniform ring state
-    for (;;) {
-        int chunk = 0;
-        if (lane == 0) chunk = atomicAdd(next_chunk, 1);
-        chunk = __shfl_sync(0xffffffffu, chunk, 0);
-        if (chunk >= total_chunks) break;
+    // the records of chunk `chunk` (zero records beyond the end of its stream: class 0, pixel (-64, -64), never a hit)
+    auto load_chunk = [&](int chunk, uint2 (&rec)[WS_ROWS], int& base, int& n) {
         int which = 0;  // the stream this chunk belongs to
         while (which + 1 < ss.world && chunk >= s_sbase[which + 1]) ++which;
-        const int base = (chunk - s_sbase[which]) * (32 * WS_ROWS);
-        const int n = s_sn[which];
+        base = (chunk - s_sbase[which]) * (32 * WS_ROWS);
+        n = s_sn[which];
         const uint2* __restrict__ srec = ss.rec[which];
-        uint2 rec[WS_ROWS];
 #pragma unroll
         for (int r = 0; r < WS_ROWS; ++r) {
             const int i = base + r * 32 + lane;
             rec[r] = i < n ? __ldcs(srec + i) : make_uint2(0u, 0u);  // read once: streaming load
+        }
+    };
+    const int n_warps_all = (int)gridDim.x * (WA_THREADS / 32);
+    auto range_size = [&](int claimed) { return min(max((total_chunks - claimed) / (2 * n_warps_all), 1), k_max); };
+    const int k0 = range_size(0);
+    const int dyn0 = n_warps_all * k0;  // first chunk handed out by the counter
+    int cur_c = ((int)blockIdx.x * (WA_THREADS / 32) + (threadIdx.x >> 5)) * k0, cur_end = min(cur_c + k0, total_chunks);
+    int nxt_c = total_chunks, nxt_end = total_chunks, seen = dyn0, req = 0, raw = 0;
+    bool first_of_range = true;
+    uint2 nxt[WS_ROWS];
+    int nbase = 0, nn = 0;
+    if (cur_c < total_chunks) load_chunk(cur_c, nxt, nbase, nn);
+    while (cur_c < total_chunks) {
+        uint2 rec[WS_ROWS];
+#pragma unroll
+        for (int r = 0; r < WS_ROWS; ++r) rec[r] = nxt[r];
+        const int base = nbase, n = nn;
+        if (first_of_range) {  // ask for the next range now ...
+            req = range_size(seen);
+            if (lane == 0) raw = atomicAdd(next_chunk, req);
+        }
+        const bool last_of_range = cur_c + 1 >= cur_end;
+        if (last_of_range) {   // ... and look at the answer before this range's last chunk
+            nxt_c = min(dyn0 + __shfl_sync(0xffffffffu, raw, 0), total_chunks);
+            nxt_end = min(nxt_c + req, total_chunks);
+            seen = nxt_end;
+        }
+        {   // the chunk after this one: its records are in flight while this one is examined
+            const int f = last_of_range ? nxt_c : cur_c + 1;
+            nn = 0;
+            if (f < total_chunks) load_chunk(f, nxt, nbase, nn);
         }
 #pragma unroll
         for (int r = 0; r < WS_ROWS; ++r) {
@@ -688,15 +765,10 @@ window_stream_kernel(DevForest f, FrameGeom g, const __grid_constant__ ObjectSwi
             const unsigned hl = __ballot_sync(0xffffffffu, mask != 0);
             if (!hl) continue;
             if (mask) {
-                float zz = -1.f;
-                if (vv >= 0 && vv < g.H && uu >= 0 && uu < g.W) {  // the reference reads out of bounds here
-                    const unsigned d = depth[(size_t)vv * g.W + uu];
-                    if (d != 0) zz = div_const<1000, 1>((float)d);
-                }
                 const int at = (head + pending + __popc(hl & ((1u << lane) - 1u))) & 63;
                 ring.vi[at] = rec[r].x;
                 ring.cm[at] = ((unsigned)c << 16) | mask;
-                ring.zz[at] = zz;
+                ring.pix[at] = (vv >= 0 && vv < g.H && uu >= 0 && uu < g.W) ? vv * g.W + uu : -1;
             }
             pending += __popc(hl);
             __syncwarp();
@@ -706,8 +778,16 @@ window_stream_kernel(DevForest f, FrameGeom g, const __grid_constant__ ObjectSwi
                 pending -= 32;
             }
         }
+        first_of_range = last_of_range;
+        if (last_of_range) {
+            cur_c = nxt_c;
+            cur_end = nxt_end;
+        } else {
+            ++cur_c;
+        }
     }
     if (pending) process(head, pending);
+    settle();
 
     __syncthreads();
     for (int c = 0; c < f.K; ++c) {
