@@ -48,13 +48,17 @@ constexpr int VOTE_WARPS = VOTE_THREADS / 32;
 // from its item -- the back-projected patch centre (HFTest.cpp:83-88) and the offset that turns a position in the
 // batch's flattened vote list into a vote index.
 struct WarpItems {
-    int incl[32];
+    int owner[32];   // item whose first vote is vote j0 + i of the current block of 32 votes
     float4 geo[32];  // tx, ty, tz, bits: vbeg - exclusive prefix
 };
 
 // Vote-parallel enumeration of every vote the reference casts (HFTest.cpp:177-214): a warp takes 32 (patch, tree) items,
 // prefix-sums their leaves' vote counts, and then walks the flattened vote list 32 votes at a time -- one vote per lane
-// whatever the votes-per-leaf distribution is; a lane finds its item by a 5-step binary search in shared memory.
+// whatever the votes-per-leaf distribution is.  A lane finds its item from the items' START positions: the items that begin
+// inside the current block of 32 votes OR their bit into one mask (REDUX) and leave their index at that position; a vote
+// belongs to the item at the highest set bit at or below its lane, or to the block's first owner if there is none.  (A
+// 5-step binary search over the prefix sums in shared memory was 20 % of the vote kernel's stall samples:
+// profiles/r02d_vote_hot_lines.txt.)
 // body(valid, vote index, tx, ty, tz) is called by all 32 lanes (converged), so it may use warp collectives.
 // Batches are handed out dynamically through a global counter (zeroed before the launch) when `next_batch` is given:
 // the work per batch varies a lot in the pose pass (votes cluster where the objects are), and a static stride leaves
@@ -150,25 +154,28 @@ __device__ __forceinline__ void for_each_cast_vote(const DevForest& f, const Fra
             sbase = __shfl_sync(0xffffffffu, sbase, 0);
         }
         __syncwarp();  // the previous batch's readers are done
-        wi.incl[lane] = incl;
         wi.geo[lane] = make_float4(tx, ty, tz, __int_as_float(vbeg - (incl - vcnt)));
-        __syncwarp();
+        const int start = vcnt > 0 ? incl - vcnt : 0x3fffffff;  // this item's first vote (an item without votes owns none)
         for (int j0 = 0; j0 < total; j0 += 32) {
             const int j = j0 + lane;
             const bool valid = j < total;
-            int lo = 0;  // smallest i with incl[i] > j
-            if (valid) {
-#pragma unroll
-                for (int s = 16; s; s >>= 1)
-                    if (wi.incl[lo + s - 1] <= j) lo += s;
-            }
+            const unsigned sp = (unsigned)(start - j0);
+            const bool starts_here = sp < 32u;
+            const unsigned starts = __reduce_or_sync(0xffffffffu, starts_here ? (1u << sp) : 0u);
+            // owner of the votes before the block's first start: the last item that began earlier (starts ascend with the index)
+            const int own0 = (31 - __clz(__ballot_sync(0xffffffffu, start < j0))) & 31;
+            if (starts_here) wi.owner[sp] = lane;
+            __syncwarp();
+            const unsigned below = starts & (0xffffffffu >> (31 - lane));
+            const int lo = below ? wi.owner[31 - __clz(below)] : own0;  // smallest i with incl[i] > j
             const float4 ge = wi.geo[lo];
+            __syncwarp();  // every lane has read its owner before the next block's items overwrite the slots
             body(valid, __float_as_int(ge.w) + j, ge.x, ge.y, ge.z, sbase < 0 ? -1 : sbase + j);
         }
     }
 }
 
-__global__ void __launch_bounds__(VOTE_THREADS)
+__global__ void __launch_bounds__(VOTE_THREADS, 8)  // the grid is 8 CTAs per SM: all of them resident (32 registers)
 vote_kernel(DevForest f, FrameGeom g, const __grid_constant__ ObjectSwitches sw, const int* __restrict__ locs,
             const uint16_t* __restrict__ depth, const int* __restrict__ leaf_ord, const int* __restrict__ counts,
             unsigned long long* __restrict__ maps, VoteStream stream, PatchShard pshard) {
