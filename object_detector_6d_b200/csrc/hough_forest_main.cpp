@@ -317,7 +317,7 @@ std::string out_stem(const std::string& filename) {
 struct Flags {
     bool test = false, train = false, other_mode = false, help = false, stage_times = false, check_inputs = false;
     std::string options_file, output_folder;
-    int device = -1, encoder_mode = 0;
+    int device = -1, encoder_mode = 0, feature_storage = -1;  // -1: the library's default
     // --train (main.cpp:13-25)
     std::string input, output = ".";
     int trees = 3, min_samples = 30, tests_per_node = 30, thresholds_per_test = 10, start_tree_no = 0, patch_size_in_voxels = -1;
@@ -364,6 +364,7 @@ bool parse_flags(int argc, char** argv, Flags& fl, std::string& err) {
         else if (a == "device") { if (!need(tmp)) return false; fl.device = atoi(tmp.c_str()); }
         else if (a == "stage_times") fl.stage_times = has_val ? parse_bool(val) : true;
         else if (a == "encoder_mode") { if (!need(tmp)) return false; fl.encoder_mode = atoi(tmp.c_str()); }
+        else if (a == "feature_storage") { if (!need(tmp)) return false; fl.feature_storage = atoi(tmp.c_str()); }
         else if (a == "check_inputs") fl.check_inputs = has_val ? parse_bool(val) : true;
         else if (a == "show_scene" || a == "visualize_hypotheses" || a == "noshow_scene" || a == "novisualize_hypotheses") {}
         else if (a == "help" || a == "h") fl.help = true;
@@ -413,7 +414,9 @@ bool parse_flags(int argc, char** argv, Flags& fl, std::string& err) {
 
 const char* kUsage =
     "usage: HoughForest --test --detector_options_file=<options.txt> [--output_folder=<dir>] [--device=<n>] [--stage_times]\n"
-    "                   [--encoder_mode=0|1]   0: bf16 tensor-core operands (default), 1: split bf16, ~fp32 (3x encoder time)\n"
+    "                   [--encoder_mode=0|1|2] 0: bf16 tensor-core operands (default), 1: split bf16, ~fp32 (3x encoder time),\n"
+    "                                          2: fp16 operands\n"
+    "                   [--feature_storage=0|1] feature rows between encoder and forest: 0 fp32, 1 fp16 (default where supported)\n"
     "       `rgb_path depth_path` pairs are read from stdin until EOF; results go to <dir><stem>_res.txt / _res.png\n"
     "       HoughForest --check_inputs   decode the stdin pairs only and print size + FNV-1a checksum of each frame\n"
     "       HoughForest --train --input=<training vectors> --output=<forest dir> --patch_size_in_voxels=<n> --voxel_size_in_m=<m>\n"
@@ -781,7 +784,8 @@ int main(int argc, char** argv) {
                 std::cerr << "HoughForest: cannot create the detector: " << hf6d_last_error(nullptr) << std::endl;
                 return 3;
             }
-            if (fl.encoder_mode && hf6d_set_encoder_mode(ctx, fl.encoder_mode)) {
+            if ((fl.encoder_mode && hf6d_set_encoder_mode(ctx, fl.encoder_mode)) ||
+                (fl.feature_storage >= 0 && hf6d_set_feature_storage(ctx, fl.feature_storage))) {
                 std::cerr << "HoughForest: " << hf6d_last_error(ctx) << std::endl;
                 return 3;
             }
