@@ -116,6 +116,16 @@ struct Slot {
     EncoderLayerLaunch enc16[2];     // feature-layer launches with fp16 output: [0] bf16 operands, [1] fp16 operands
     bool enc16_fp16_ready = false;
     bool feat_is16 = false;          // the slot's current features live in feat16
+    // CUDA graph of one whole frame (HF6D_GRAPH=1): captured from the slot's own launches once a full eager frame has run with
+    // the same frame pointers and context configuration, replayed while both stay the same (run_range)
+    cudaGraphExec_t graph_exec = nullptr;
+    const void *graph_bgr = nullptr, *graph_depth = nullptr;
+    uint64_t graph_epoch = 0;
+    int graph_launches = 0;
+    bool capturing = false;          // run_stage / run_range_impl are being captured: no event records
+    bool last_full_valid = false;    // the slot's previous run was a whole frame (eager or replayed) with the key below
+    const void *last_bgr = nullptr, *last_depth = nullptr;
+    uint64_t last_epoch = 0;
     uint32_t peer_seq = 0;  // frames this slot has pushed through the peer exchange (both flags carry it)
     bool busy = false;  // submit/wait bookkeeping
     int ticket = -1;
@@ -176,6 +186,8 @@ struct hf6d_ctx {
     std::vector<void*> peer_opened;                                   // cudaIpcOpenMemHandle results
     int* peer_timeout = nullptr;                                      // set by the fallback wait kernel when it gives up
     bool peer_wait_expired = false;                                   // a bounded host-side wait ran out (sync_stream_bounded)
+    bool use_graph = false;   // HF6D_GRAPH=1: whole frames are replayed from a CUDA graph per slot (one launch instead of 22 + memsets)
+    uint64_t epoch = 1;       // bumped by every call that changes what a frame's launches look like
     int encoder_mode = 0;
     // Feature storage: 0 = fp32 rows (the reference's type), 1 = fp16 rows written by the feature layer of the bf16 / fp16
     // operand modes and read by the traversal (half the HBM bytes of both; the split mode always stores fp32).
@@ -437,6 +449,7 @@ void free_all(hf6d_ctx* c) {
         if (s.res_host) cudaFreeHost(s.res_host);
         for (int i = 0; i <= HF6D_STAGE_COUNT; ++i) if (s.ev[i]) cudaEventDestroy(s.ev[i]);
         for (int i = 0; i < 4; ++i) if (s.ev_enc[i]) cudaEventDestroy(s.ev_enc[i]);
+        if (s.graph_exec) cudaGraphExecDestroy(s.graph_exec);
         if (s.own_stream) cudaStreamDestroy(s.own_stream);
     }
     for (void* p : c->dm.allocs) cudaFree(p);
@@ -665,7 +678,7 @@ int run_stage(hf6d_ctx* c, Slot& s, int stage) {
             break;
         }
         case HF6D_STAGE_ENCODE: {
-            CU_TRY(c, cudaEventRecord(s.ev_enc[0], st));
+            if (!s.capturing) CU_TRY(c, cudaEventRecord(s.ev_enc[0], st));
             if (c->encoder_mode == 1 && !s.split_ready) return fail(c, HF6D_ESTATE, "split encoder buffers missing");
             if (c->encoder_mode == 2 && !s.fp16_ready) return fail(c, HF6D_ESTATE, "fp16 encoder state missing");
             for (int l = 0; l < 3; ++l) {
@@ -677,9 +690,9 @@ int run_stage(hf6d_ctx* c, Slot& s, int stage) {
                 cudaError_t e = launch_encoder_layer(L, s.counts + 1, c->sms, st);
                 if (e != cudaSuccess) return fail(c, HF6D_ECUDA, "encoder layer %d launch: %s", l, cudaGetErrorString(e));
                 ++s.launches;
-                CU_TRY(c, cudaEventRecord(s.ev_enc[l + 1], st));
+                if (!s.capturing) CU_TRY(c, cudaEventRecord(s.ev_enc[l + 1], st));
             }
-            s.ev_enc_valid = true;
+            s.ev_enc_valid = !s.capturing;
             s.feat_is16 = c->feat16 && c->encoder_mode != 1;
             break;
         }
@@ -903,7 +916,67 @@ int run_stage(hf6d_ctx* c, Slot& s, int stage) {
 
 int run_range_impl(hf6d_ctx* c, Slot& s, int first, int last);
 
+// One whole frame as a CUDA graph.  Capture needs nothing but the launches themselves: every kernel reads its sizes from
+// device memory (patch count, centre lists, pair list), so the graph of one frame is the graph of every frame with the same
+// frame buffers and the same context configuration.  Event records are left out (hf6d_stage_ms / hf6d_encoder_layer_ms
+// report zeros for replayed frames).
+int capture_frame(hf6d_ctx* c, Slot& s) {
+    if (s.graph_exec) {
+        cudaGraphExecDestroy(s.graph_exec);
+        s.graph_exec = nullptr;
+    }
+    CU_TRY(c, cudaStreamBeginCapture(s.stream, cudaStreamCaptureModeThreadLocal));
+    s.capturing = true;
+    const int r = run_range_impl(c, s, 0, HF6D_STAGE_COUNT - 1);
+    s.capturing = false;
+    cudaGraph_t graph = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(s.stream, &graph);
+    if (r || e != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        if (r) return r;
+        return fail(c, HF6D_ECUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(e));
+    }
+    const cudaError_t ei = cudaGraphInstantiate(&s.graph_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ei != cudaSuccess) {
+        s.graph_exec = nullptr;
+        return fail(c, HF6D_ECUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(ei));
+    }
+    s.graph_bgr = s.bgr;
+    s.graph_depth = s.depth;
+    s.graph_epoch = c->epoch;
+    s.graph_launches = s.launches;
+    return HF6D_OK;
+}
+
 int run_range(hf6d_ctx* c, Slot& s, int first, int last) {
+    const bool whole = first == 0 && last == HF6D_STAGE_COUNT - 1;
+    if (whole && c->use_graph && !c->peer_on && c->shard_world == 1 && c->pshard.world == 1) {
+        // replay only what an eager frame has just established: same buffers, same configuration, and the host-side state the
+        // launches depend on (vote stream valid, counter table clean, feature storage) left by a whole frame
+        if (s.last_full_valid && s.last_bgr == s.bgr && s.last_depth == s.depth && s.last_epoch == c->epoch && !s.cnt_dirty) {
+            if (!s.graph_exec || s.graph_bgr != s.bgr || s.graph_depth != s.depth || s.graph_epoch != c->epoch) {
+                if (capture_frame(c, s) != HF6D_OK) {  // this context cannot capture: stay eager from here on
+                    c->use_graph = false;
+                    s.last_full_valid = false;
+                    return run_range_impl(c, s, first, last);
+                }
+            }
+            CU_TRY(c, cudaGraphLaunch(s.graph_exec, s.stream));
+            s.launches = s.graph_launches;
+            for (int i = 0; i <= HF6D_STAGE_COUNT; ++i) s.ev_valid[i] = false;
+            s.ev_enc_valid = false;
+            return HF6D_OK;
+        }
+        const int r = run_range_impl(c, s, first, last);
+        s.last_full_valid = r == HF6D_OK;
+        s.last_bgr = s.bgr;
+        s.last_depth = s.depth;
+        s.last_epoch = c->epoch;
+        return r;
+    }
+    s.last_full_valid = false;
     const uint32_t seq0 = s.peer_seq;
     const int r = run_range_impl(c, s, first, last);
     if (r && c->peer_on) {
@@ -921,8 +994,10 @@ int run_range_impl(hf6d_ctx* c, Slot& s, int first, int last) {
     if (first < 0 || last >= HF6D_STAGE_COUNT || first > last) return fail(c, HF6D_EINVAL, "bad stage range %d..%d", first, last);
     s.launches = 0;
     for (int i = 0; i <= HF6D_STAGE_COUNT; ++i) s.ev_valid[i] = false;
-    CU_TRY(c, cudaEventRecord(s.ev[first], s.stream));
-    s.ev_valid[first] = true;
+    if (!s.capturing) {
+        CU_TRY(c, cudaEventRecord(s.ev[first], s.stream));
+        s.ev_valid[first] = true;
+    }
     const int slot = slot_index(c, s);
     for (int st = first; st <= last; ++st) {
         int r;
@@ -934,8 +1009,10 @@ int run_range_impl(hf6d_ctx* c, Slot& s, int first, int last) {
         if ((r = run_stage(c, s, st))) return r;
         if (c->peer_on && st == HF6D_STAGE_VOTE && (r = peer_signal(c, s, slot, PEER_FLAG_READY, s.peer_seq))) return r;
         if (c->peer_on && st == HF6D_STAGE_POSE && (r = peer_signal(c, s, slot, PEER_FLAG_CONSUMED, s.peer_seq))) return r;
-        CU_TRY(c, cudaEventRecord(s.ev[st + 1], s.stream));
-        s.ev_valid[st + 1] = true;
+        if (!s.capturing) {
+            CU_TRY(c, cudaEventRecord(s.ev[st + 1], s.stream));
+            s.ev_valid[st + 1] = true;
+        }
     }
     return HF6D_OK;
 }
@@ -1274,6 +1351,7 @@ int finish_create(hf6d_ctx* c, int device, int n_slots) {
         memset(s.ev, 0, sizeof s.ev);
         if ((r = alloc_slot(c, s))) return r;
     }
+    c->use_graph = getenv("HF6D_GRAPH") && atoi(getenv("HF6D_GRAPH")) != 0;
     {   // feature storage: fp16 rows wherever the feature layer has a kernel for them; HF6D_FEATURES=fp32 keeps the fp32 rows
         const char* e = getenv("HF6D_FEATURES");
         if (!(e && !strcmp(e, "fp32"))) {
@@ -1451,6 +1529,7 @@ int hf6d_model(const hf6d_ctx* c, hf6d_model_info* out) {
 
 int hf6d_set_objects(hf6d_ctx* c, const hf6d_object* objs, int n) {
     if (!c || !objs) return HF6D_EINVAL;
+    ++c->epoch;  // a captured frame (HF6D_GRAPH) no longer describes this context
     if (n != c->hf.K) return fail(c, HF6D_EINVAL, "Number of objects (%d) does not match the number of classes in the forest (%d)", n, c->hf.K);
     for (int k = 0; k < n; ++k)
         if (objs[k].max_location_hypotheses < 0 || objs[k].max_location_hypotheses > HF6D_MAX_CENTRES)
@@ -1467,6 +1546,7 @@ int hf6d_get_objects(const hf6d_ctx* c, hf6d_object* objs, int cap) {
 
 int hf6d_set_fill_seed(hf6d_ctx* c, uint64_t seed) {
     if (!c) return HF6D_EINVAL;
+    ++c->epoch;  // a captured frame (HF6D_GRAPH) no longer describes this context
     c->p.fill_seed = seed;
     c->g.fill_seed = seed;
     return HF6D_OK;
@@ -1474,6 +1554,7 @@ int hf6d_set_fill_seed(hf6d_ctx* c, uint64_t seed) {
 
 int hf6d_set_tree_shard(hf6d_ctx* c, int rank, int world) {
     if (!c) return HF6D_EINVAL;
+    ++c->epoch;
     if (world < 1 || rank < 0 || rank >= world) return fail(c, HF6D_EINVAL, "bad tree shard %d/%d", rank, world);
     c->shard_rank = rank;
     c->shard_world = world;
@@ -1483,6 +1564,7 @@ int hf6d_set_tree_shard(hf6d_ctx* c, int rank, int world) {
 
 int hf6d_set_patch_shard(hf6d_ctx* c, int rank, int world) {
     if (!c) return HF6D_EINVAL;
+    ++c->epoch;
     if (world < 1 || rank < 0 || rank >= world) return fail(c, HF6D_EINVAL, "bad patch shard %d/%d", rank, world);
     c->pshard = PatchShard{rank, world};
     for (Slot& s : c->slots) s.stream_valid = false;
@@ -1491,6 +1573,7 @@ int hf6d_set_patch_shard(hf6d_ctx* c, int rank, int world) {
 
 int hf6d_set_peer_split(hf6d_ctx* c, int split) {
     if (!c) return HF6D_EINVAL;
+    ++c->epoch;
     if (split != 0 && split != 1) return fail(c, HF6D_EINVAL, "peer split %d: 0 = trees, 1 = patches", split);
     if (c->peer_on) return fail(c, HF6D_ESTATE, "hf6d_set_peer_split must be called before hf6d_peer_attach");
     c->peer_split = split;
@@ -1499,6 +1582,7 @@ int hf6d_set_peer_split(hf6d_ctx* c, int split) {
 
 int hf6d_set_class_shard(hf6d_ctx* c, int rank, int world) {
     if (!c) return HF6D_EINVAL;
+    ++c->epoch;
     if (world < 1 || rank < 0 || rank >= world) return fail(c, HF6D_EINVAL, "bad class shard %d/%d", rank, world);
     c->class_rank = rank;
     c->class_world = world;
@@ -1823,6 +1907,7 @@ int ensure_feat16(hf6d_ctx* c) {
 
 int hf6d_set_feature_storage(hf6d_ctx* c, int storage) {
     if (!c) return HF6D_EINVAL;
+    ++c->epoch;  // a captured frame (HF6D_GRAPH) no longer describes this context
     if (storage != 0 && storage != 1) return fail(c, HF6D_EINVAL, "feature storage %d: 0 = fp32 rows, 1 = fp16 rows", storage);
     CU_TRY(c, cudaSetDevice(c->device));
     CU_TRY(c, cudaDeviceSynchronize());
@@ -1839,6 +1924,7 @@ int hf6d_get_feature_storage(const hf6d_ctx* c) { return c ? (c->feat16 ? 1 : 0)
 
 int hf6d_set_encoder_mode(hf6d_ctx* c, int mode) {
     if (!c) return HF6D_EINVAL;
+    ++c->epoch;  // a captured frame (HF6D_GRAPH) no longer describes this context
     if (mode < 0 || mode > 2)
         return fail(c, HF6D_EINVAL, "encoder mode %d: 0 = bf16 operands, 1 = split bf16 (hi + lo), 2 = fp16 operands", mode);
     CU_TRY(c, cudaSetDevice(c->device));
@@ -1860,6 +1946,7 @@ int hf6d_get_encoder_mode(const hf6d_ctx* c) { return c ? c->encoder_mode : HF6D
 
 int hf6d_set_debug_capture(hf6d_ctx* c, int on) {
     if (!c) return HF6D_EINVAL;
+    ++c->epoch;  // a captured frame (HF6D_GRAPH) no longer describes this context
     c->debug_capture = on ? 1 : 0;
     return HF6D_OK;
 }
@@ -2000,6 +2087,7 @@ int hf6d_inject(hf6d_ctx* c, int slot, int what, const void* src, size_t bytes) 
     CU_TRY(c, cudaStreamSynchronize(s.stream));
     CU_TRY(c, memcpy_h2d_done(b.ptr, src, bytes));
     if (what == HF6D_BUF_FEATURES) s.feat_is16 = false;  // injected features are fp32 rows: the traversal reads those
+    s.last_full_valid = false;
     s.stream_valid = false;  // whatever was injected, the vote stream no longer describes the slot
     return HF6D_OK;
 }
@@ -2015,6 +2103,7 @@ int hf6d_device_ptr(hf6d_ctx* c, int slot, int what, void** ptr, size_t* bytes) 
         if ((r = features_fp32(c, s))) return r;
         s.feat_is16 = false;
     }
+    c->slots[slot].last_full_valid = false;  // the caller may write through the pointer
     if (ptr) *ptr = b.ptr;
     if (bytes) *bytes = b.bytes;
     return HF6D_OK;
