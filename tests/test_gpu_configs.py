@@ -1,4 +1,4 @@
-"""GPU parity at the sizes and forest shapes BASELINE.json names (configs[1], [3], [4]) -- the per-stage tests in
+"""GPU parity at the sizes and forest shapes BASELINE.json names (configs[0], [1], [3], [4]) -- the per-stage tests in
 test_gpu_parity.py run one small case; these run the whole path at full size.
 
 For every configuration the CUDA path (through the C ABI) must agree with the oracle BIT FOR BIT on: patch centres,
@@ -58,6 +58,22 @@ def _check_case(cs, n_slots=2, sample=4000):
         return dict(P=P, Pp=Pp, n_cast=n_cast, n_hyp=len(hyp), maps=maps, feat=feat)
     finally:
         det.close()
+
+
+def test_config_c1_one_object_segmented(tmp_path):
+    """configs[0] (the reference's own CPU-runnable case): a 1-object forest, one object in the frame,
+    `are_objects_segmented: true` -- samples without depth keep the constant fill (HFTest.cpp:1235, patch_extractor.cu:238-249),
+    K = 1 exercises the single-class paths of the vote / centre / pose kernels (one map, 16 accumulator slots)."""
+    cs = make_case(str(tmp_path), K=1, T=4, seed=4, max_depth=16, votes_per_leaf=12, n_objects=1, calib_patches=6000, fill_random=0)
+    # segmented input: no depth (and black) outside an ellipse around the image centre, so patches on its rim mix measured
+    # samples with the constant fill
+    H, W = cs["depth"].shape
+    yy, xx = np.mgrid[0:H, 0:W]
+    outside = ((xx - W / 2) / (0.36 * W)) ** 2 + ((yy - H / 2) / (0.40 * H)) ** 2 > 1.0
+    cs["depth"] = np.where(outside, 0, cs["depth"]).astype(np.uint16)
+    cs["bgr"] = np.where(outside[..., None], 0, cs["bgr"]).astype(np.uint8)
+    out = _check_case(cs)
+    assert 5000 < out["Pp"] < 60000 and out["n_hyp"] > 0
 
 
 def test_config_c2_six_objects_full_frame(tmp_path):
