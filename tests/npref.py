@@ -467,3 +467,122 @@ def blur_reference(acc_q16, k):
     H, W = m.shape
     s = cs[k:k + H, k:k + W] - cs[0:H, k:k + W] - cs[k:k + H, 0:W] + cs[0:H, 0:W]
     return (s * (1.0 / (k * k))).astype(f32)
+
+
+# ------------------------------------------------------------------------------------------------ A10 - A12 pose seeking
+def _d2i(x: float) -> int:
+    """C double -> int conversion (truncation toward zero)."""
+    import math
+    return int(math.trunc(x)) if math.isfinite(x) and abs(x) < 2147483648.0 else -2147483648
+
+
+def seek_poses(forest, entries, maps, depth, W, H, fx, fy, cx, cy, *, centers_blur=15, centers_nms=40, pose_blur=35,
+               pose_nms=35, max_loc=12, max_yaw_pitch=7, max_roll=3, min_loc_ratio=0.5, min_yp_ratio=0.5, should_detect=None):
+    """HFTest.cpp:694-925, literally, per class: blur + NMS of the centre map, then for every kept centre the window walk
+    over the back-map (`entries`, from cast_votes(want_entries=True): one (u, v, (tree, leaf)) per CAST VOTE, so a leaf that
+    cast n votes on a pixel is listed n times there and all n of its votes are walked every time, :763-766), z histogram
+    with the window pixel's depth standing in for the patch centre (:766-775), yaw/pitch map with its +-360 wrap copies
+    (:778-791), z mode (:803-812), yaw/pitch peaks kept in [180, 540]^2 (:817-836), roll histogram from the leaves whose
+    (yaw, pitch) bins lie in the blur box of the peak (:852-872), roll peaks at least 7 degrees apart (:903-921).
+    Choices shared with the oracle (its header, C8 / C9 / C10): Q16 integer weights, window pixels outside the image carry
+    no depth, bins outside a histogram are dropped.  Returns [(cls, cx, cy, z, yaw, pitch, roll, loc_score, yp_score,
+    roll_score)] in the reference's emission order."""
+    import math
+    K = forest["K"]
+    NB, ZB = 720, 300
+    z_bin_size = f32(0.01)
+    out = []
+    for c in range(K):
+        if should_detect is not None and not should_detect[c]:
+            continue
+        centres = nms(blur_reference(maps[c], centers_blur), centers_nms, centers_nms)
+        back = {}
+        for (u, v, tl) in entries[c]:
+            back.setdefault((u, v), []).append(tl)
+        n_loc = min(max_loc[c] if hasattr(max_loc, "__len__") else max_loc, len(centres))
+        half = centers_nms // 2
+        for k in range(n_loc):
+            loc_score, ctr_x, ctr_y = centres[k]
+            if f32(loc_score) / f32(centres[0][0]) < f32(min_loc_ratio):
+                continue
+            zacc = np.zeros(ZB, np.uint64)
+            ypacc = np.zeros((NB, NB), np.uint64)
+            roll_map = {}
+            for row in range(ctr_y - half, ctr_y + half):
+                for col in range(ctr_x - half, ctr_x + half):
+                    if (col, row) not in back:
+                        continue
+                    inside = 0 <= row < H and 0 <= col < W
+                    dpix = int(depth[row, col]) if inside else 0
+                    for (t, lo) in back[(col, row)]:
+                        leaf = forest["trees"][t][1][lo]
+                        w = np.uint64(int(f32(leaf.class_prob[c]) * f32(65536.0) + f32(0.5)))
+                        for vote in leaf.votes[c]:
+                            if dpix != 0:
+                                R = xtion_rotmat(vote[0], vote[1], vote[2])
+                                zpix = f32(dpix) / f32(1000.0)
+                                acc = f32(f32(R[2, 0] * -vote[3]) + R[2, 1] * -vote[4])
+                                acc = f32(acc + R[2, 2] * -vote[5])
+                                zc = f32(acc + zpix * f32(1.0))
+                                zb = int(_f2i(np.array([zc / z_bin_size], f32))[0])
+                                if 0 <= zb < ZB:
+                                    zacc[zb] += w
+                            yaw = _d2i(float(vote[0]) / math.pi * 180.0)
+                            pitch = _d2i(float(vote[1]) / math.pi * 180.0)
+                            sy = -1 if yaw < 0 else 1
+                            sp = -1 if pitch < 0 else 1
+                            for k1 in range(2):
+                                for k2 in range(2):
+                                    cy_ = yaw - sy * k1 * 360 + 360
+                                    cp_ = pitch - sp * k2 * 360 + 360
+                                    if 0 <= cy_ < NB and 0 <= cp_ < NB:
+                                        ypacc[cy_, cp_] += w
+                                    if k1 == 0 and k2 == 0:
+                                        roll_map.setdefault((cy_, cp_), []).append((t, lo))
+            zf = (zacc.astype(np.float64) / 65536.0).astype(f32).reshape(ZB, 1)
+            zh = nms(zf, 1, 20)
+            if not zh:
+                continue
+            mode_z = f32(zh[0][2]) * z_bin_size
+            yph = [h for h in nms(blur_reference(ypacc, pose_blur), pose_nms, pose_nms)
+                   if not (h[1] < 180 or h[1] > 540 or h[2] < 180 or h[2] > 540)]
+            bh = pose_blur // 2
+            for h2 in range(min(max_yaw_pitch, len(yph))):
+                yp_score = f32(yph[h2][0]) / f32(yph[0][0])
+                if yp_score < f32(min_yp_ratio):
+                    break
+                Pp, Yp = yph[h2][1], yph[h2][2]  # x = column = pitch bin, y = row = yaw bin
+                racc = np.zeros(NB, np.uint64)
+                for row in range(Yp - bh, Yp + bh):
+                    for col in range(Pp - bh, Pp + bh):
+                        for (t, lo) in roll_map.get((row, col), ()):
+                            leaf = forest["trees"][t][1][lo]
+                            w = np.uint64(int(f32(leaf.class_prob[c]) * f32(65536.0) + f32(0.5)))
+                            for vote in leaf.votes[c]:
+                                r = _d2i(float(f32(vote[2]) * f32(180.0)) / math.pi)
+                                b0, b1 = r + 360, (r + 720 if r < 0 else r)
+                                if 0 <= b0 < NB:
+                                    racc[b0] += w
+                                if 0 <= b1 < NB:
+                                    racc[b1] += w
+                # cv::blur(Size(1, k)) on the 720 x 1 column
+                m = racc.astype(np.float64) / 65536.0
+                mp = np.pad(m, pose_blur // 2, mode="reflect")
+                cs = np.concatenate([[0.0], np.cumsum(mp)])
+                rf = ((cs[pose_blur:pose_blur + NB] - cs[0:NB]) * (1.0 / pose_blur)).astype(f32).reshape(NB, 1)
+                rh = [h for h in nms(rf, 1, pose_nms) if not (h[2] < 180 or h[2] > 540)]
+                n_roll, prev = 0, f32(3.402823466e+38)
+                for h in rh:
+                    if n_roll >= max_roll:
+                        break
+                    roll_score = f32(h[0]) / f32(rh[0][0])
+                    ry = h[2]
+                    a = float(f32(prev / f32(180.0))) * math.pi
+                    b = float(f32(f32(ry) / f32(180.0))) * math.pi
+                    dot = f32(math.cos(a) * math.cos(b) + math.sin(a) * math.sin(b))
+                    if n_roll == 0 or math.acos(float(dot)) / math.pi * float(f32(180.0)) > 7:
+                        out.append((c, ctr_x, ctr_y, float(mode_z), Yp - 360, Pp - 360, ry - 360, float(f32(loc_score)),
+                                    float(yp_score), float(roll_score)))
+                        prev = f32(ry)
+                        n_roll += 1
+    return out

@@ -225,6 +225,42 @@ def test_hypotheses_are_consistent(small):
         assert np.allclose(pose[:3, :3] @ pose[:3, :3].T, np.eye(3), atol=1e-5)
 
 
+def test_pose_seeking_matches_independent_restatement(small):
+    """A10 - A12 (HFTest.cpp:694-925): centre selection, window walk over the back-map with its per-vote multiplicity, z
+    histogram and mode, yaw/pitch map with wrap copies, roll histogram, 7-degree separation -- the C oracle against the
+    pure-Python restatement in tests/npref.py on a whole 320x240 frame: every hypothesis tuple and every score, bit for bit."""
+    p = small["params"]
+    locs = small["locs_all"][:small["Pp"]]
+    feats = O.encode(O.normalise(O.gather(small["bgr"], small["depth"], p, locs)), small["layers"])
+    _, ords = O.traverse(small["forest"], feats)
+    max_loc = [5, 3]
+    hyp = O.hypotheses(small["forest"], ords, locs, small["depth"], p, max_loc=max_loc)
+    pf = npref.read_forest(small["forest_dir"])
+    maps, entries = npref.cast_votes(pf, ords, locs, small["depth"], p.W, p.H, p.fx, p.fy, p.cx, p.cy, want_entries=True)
+    ref = npref.seek_poses(pf, entries, maps, small["depth"], p.W, p.H, p.fx, p.fy, p.cx, p.cy,
+                           centers_blur=p.centers_blur_size, centers_nms=p.centers_nms_wsize, pose_blur=p.pose_blur_size,
+                           pose_nms=p.pose_nms_wsize, max_loc=max_loc, max_yaw_pitch=p.max_yaw_pitch_hypotheses,
+                           max_roll=p.max_roll_hypotheses, min_loc_ratio=p.min_location_score_ratio,
+                           min_yp_ratio=p.min_yaw_pitch_drop_ratio)
+    assert len(ref) == len(hyp) > 50
+    for a, h in zip(ref, hyp):
+        b = (int(h["cls"]), int(h["cx"]), int(h["cy"]), float(h["z"]), int(h["yaw_deg"]), int(h["pitch_deg"]), int(h["roll_deg"]),
+             float(h["loc_score"]), float(h["yawpitch_score"]), float(h["roll_score"]))
+        assert a == b
+    # a class switched off produces nothing, the other class is untouched (HFTest.cpp:695)
+    sd = np.array([0, 1], np.uint8)
+    hyp1 = O.hypotheses(small["forest"], ords, locs, small["depth"], p, should_detect=sd, max_loc=max_loc)
+    maps1, entries1 = npref.cast_votes(pf, ords, locs, small["depth"], p.W, p.H, p.fx, p.fy, p.cx, p.cy, should_detect=sd,
+                                       want_entries=True)
+    ref1 = npref.seek_poses(pf, entries1, maps1, small["depth"], p.W, p.H, p.fx, p.fy, p.cx, p.cy,
+                            centers_blur=p.centers_blur_size, centers_nms=p.centers_nms_wsize, pose_blur=p.pose_blur_size,
+                            pose_nms=p.pose_nms_wsize, max_loc=max_loc, max_yaw_pitch=p.max_yaw_pitch_hypotheses,
+                            max_roll=p.max_roll_hypotheses, min_loc_ratio=p.min_location_score_ratio,
+                            min_yp_ratio=p.min_yaw_pitch_drop_ratio, should_detect=sd)
+    assert len(ref1) == len(hyp1) > 0 and all(h["cls"] == 1 for h in hyp1)
+    assert [r[:7] for r in ref1] == [r[:7] for r in ref if r[0] == 1]
+
+
 def test_empty_and_far_frames(small):
     p = small["params"]
     zero = np.zeros_like(small["depth"])
